@@ -1,0 +1,230 @@
+// C-ABI layer of libvoicemap_b200.so: argument checks, TMA descriptor creation, error strings, and the
+// whole-encoder launcher.  See include/voicemap_b200.h for the contract of each entry point.
+#include <stdio.h>
+#include <string.h>
+
+#include "vm_kernels.h"
+
+namespace vm {
+
+static thread_local char g_err[512] = "no error";
+static int g_conv3_desc_mode = 0;
+static int g_max_ctas = 0;
+
+int set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+  return VM_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return set_error(VM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(VM_ERR_SHAPE, "TMA base pointer not 16B aligned");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16 != 0) return set_error(VM_ERR_SHAPE, "TMA stride not a multiple of 16 bytes");
+    gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle == VM_SWIZZLE_32B) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  if (swizzle == VM_SWIZZLE_64B) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  if (swizzle == VM_SWIZZLE_128B) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+    return VM_ERR_CUDA;
+  }
+  return VM_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct EncoderPlan {
+  int l1, l2, l3, t4, c4_pad;
+  size_t a1, a2, a3, part, total;  // plane sizes in bytes (single plane), offsets derived below
+};
+static EncoderPlan plan_encoder(int N, int L, int filters) {
+  EncoderPlan pl{};
+  pl.l1 = L / 4; pl.l2 = pl.l1 / 2; pl.l3 = pl.l2 / 2;
+  pl.t4 = (pl.l3 + 255) / 256;
+  pl.c4_pad = (4 * filters + 127) / 128 * 128;
+  pl.a1 = align_up(size_t(N) * pl.l1 * filters * 2, 1024);
+  pl.a2 = align_up(size_t(N) * pl.l2 * 2 * filters * 2, 1024);
+  pl.a3 = align_up(size_t(N) * pl.l3 * 3 * filters * 2, 1024);
+  pl.part = align_up(size_t(N) * pl.t4 * pl.c4_pad * 4, 1024);
+  pl.total = 2 * pl.a1 + 2 * pl.a2 + 2 * pl.a3 + pl.part;
+  return pl;
+}
+
+}  // namespace vm
+
+using namespace vm;
+
+extern "C" {
+
+int vm_version(void) { return 100; }
+const char* vm_last_error_string(void) { return g_err; }
+
+int vm_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDevice");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute");
+  if (major != 10) return set_error(VM_ERR_ARCH, "voicemap_b200 requires an sm_100 (B200) device");
+  return VM_OK;
+}
+
+int vm_padded_channels(int cout) { return (cout + 127) / 128 * 128; }
+size_t vm_conv1_wpack_bytes(int cout) { return size_t(vm_padded_channels(cout)) / 128 * 16384; }
+size_t vm_conv3_wpack_bytes(int cin, int cout) { return size_t(2) * 3 * vm_padded_channels(cout) * cin * 2; }
+size_t vm_epi_bytes(int cout) { return size_t(vm_padded_channels(cout)) * 16; }
+int vm_conv3_num_position_tiles(int L) { return (L + 255) / 256; }
+
+int vm_set_option(const char* key, int value) {
+  if (key == nullptr) return set_error(VM_ERR_SHAPE, "vm_set_option: null key");
+  int* slot = nullptr;
+  if (strcmp(key, "conv3_desc_mode") == 0) slot = &g_conv3_desc_mode;
+  if (strcmp(key, "max_ctas") == 0) slot = &g_max_ctas;
+  if (slot == nullptr) return set_error(VM_ERR_SHAPE, "vm_set_option: unknown key");
+  int old = *slot;
+  *slot = value;
+  return old;
+}
+
+int vm_pack_conv1(const float* kernel, const float* bias, const float* gamma, const float* beta, const float* mean,
+                  const float* var, float eps, int cout, void* wpack, float* epi, void* stream) {
+  return launch_pack_conv1(kernel, bias, gamma, beta, mean, var, eps, cout, wpack, epi, (cudaStream_t)stream);
+}
+int vm_pack_conv3(const float* kernel, const float* bias, const float* gamma, const float* beta, const float* mean,
+                  const float* var, float eps, int cin, int cout, void* wpack, float* epi, void* stream) {
+  return launch_pack_conv3(kernel, bias, gamma, beta, mean, var, eps, cin, cout, wpack, epi, (cudaStream_t)stream);
+}
+
+int vm_conv1_relu_bn_pool4_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi,
+                               uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream) {
+  if (x == nullptr || wpack == nullptr || epi == nullptr || out_hi == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv1: null pointer");
+  if (precision == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 3");
+  return launch_conv1(x, N, L, cout, wpack, epi, reinterpret_cast<__half*>(out_hi),
+                      reinterpret_cast<__half*>(out_lo), precision, g_max_ctas, (cudaStream_t)stream);
+}
+
+int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
+                               const void* wpack, const float* epi, uint16_t* out_hi, uint16_t* out_lo,
+                               float* gmax_partial, int precision, void* stream) {
+  if (in_hi == nullptr || wpack == nullptr || epi == nullptr) return set_error(VM_ERR_SHAPE, "conv3: null pointer");
+  if (gmax_partial == nullptr && precision == 3 && out_lo == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 3");
+  return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
+                      static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
+                      reinterpret_cast<__half*>(out_lo), gmax_partial, precision, g_conv3_desc_mode, g_max_ctas,
+                      (cudaStream_t)stream);
+}
+
+int vm_gmax_dense_fwd(const float* gmax_partial, int N, int T, int C, const float* epi, const float* dense_w,
+                      const float* dense_b, int E, float* gmax_out, float* emb, void* stream) {
+  if (gmax_partial == nullptr || epi == nullptr) return set_error(VM_ERR_SHAPE, "gmax_dense: null pointer");
+  return launch_gmax_dense(gmax_partial, N, T, C, vm_padded_channels(C), epi, dense_w, dense_b, E, gmax_out, emb,
+                           (cudaStream_t)stream);
+}
+
+int vm_pair_head_loss_fwd(const float* e1, const float* e2, int N, int E, int metric, const float* head_w,
+                          const float* head_b, const float* y_true, int loss_kind, float* dist, float* prob,
+                          float* loss, void* stream) {
+  if (e1 == nullptr || e2 == nullptr || head_w == nullptr || head_b == nullptr)
+    return set_error(VM_ERR_SHAPE, "pair_head_loss: null pointer");
+  return launch_pair_head_loss(e1, e2, N, E, metric, head_w, head_b, y_true, loss_kind, dist, prob, loss,
+                               (cudaStream_t)stream);
+}
+
+int vm_split_planes(const float* x, size_t n, uint16_t* hi, uint16_t* lo, void* stream) {
+  if (x == nullptr || hi == nullptr) return set_error(VM_ERR_SHAPE, "split_planes: null pointer");
+  return launch_split_planes(x, n, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo),
+                             (cudaStream_t)stream);
+}
+int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, void* stream) {
+  if (x == nullptr || hi == nullptr) return set_error(VM_ERR_SHAPE, "merge_planes: null pointer");
+  return launch_merge_planes(reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), n, x,
+                             (cudaStream_t)stream);
+}
+
+size_t vm_encoder_workspace_bytes(int N, int L, int filters) {
+  if (N <= 0 || L < 32 || filters <= 0) return 0;
+  return plan_encoder(N, L, filters).total;
+}
+
+int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const* wpack, const float* const* epi,
+                   const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
+                   void* stream) {
+  if (x == nullptr || wpack == nullptr || epi == nullptr || workspace == nullptr || emb == nullptr)
+    return set_error(VM_ERR_SHAPE, "encoder: null pointer");
+  if (N <= 0 || filters <= 0) return set_error(VM_ERR_SHAPE, "encoder: bad shape");
+  if (L < 32) return set_error(VM_ERR_SHAPE, "encoder: L must be >= 32 (four pooling stages 4*2*2*2)");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+    return set_error(VM_ERR_SHAPE, "encoder: workspace must be 1024-byte aligned");
+  const EncoderPlan pl = plan_encoder(N, L, filters);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __half* a1h = reinterpret_cast<__half*>(ws);
+  __half* a1l = reinterpret_cast<__half*>(ws + pl.a1);
+  __half* a2h = reinterpret_cast<__half*>(ws + 2 * pl.a1);
+  __half* a2l = reinterpret_cast<__half*>(ws + 2 * pl.a1 + pl.a2);
+  __half* a3h = reinterpret_cast<__half*>(ws + 2 * pl.a1 + 2 * pl.a2);
+  __half* a3l = reinterpret_cast<__half*>(ws + 2 * pl.a1 + 2 * pl.a2 + pl.a3);
+  float* part = reinterpret_cast<float*>(ws + 2 * pl.a1 + 2 * pl.a2 + 2 * pl.a3);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int f = filters;
+  int rc;
+  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, precision, g_max_ctas, st))) return rc;
+  if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
+                         nullptr, precision, g_conv3_desc_mode, g_max_ctas, st)))
+    return rc;
+  if ((rc = launch_conv3(a2h, a2l, N, pl.l2, 2 * f, 3 * f, static_cast<const __half*>(wpack[2]), epi[2], a3h, a3l,
+                         nullptr, precision, g_conv3_desc_mode, g_max_ctas, st)))
+    return rc;
+  if ((rc = launch_conv3(a3h, a3l, N, pl.l3, 3 * f, 4 * f, static_cast<const __half*>(wpack[3]), epi[3], nullptr,
+                         nullptr, part, precision, g_conv3_desc_mode, g_max_ctas, st)))
+    return rc;
+  return launch_gmax_dense(part, N, pl.t4, 4 * f, pl.c4_pad, epi[3], dense_w, dense_b, E, nullptr, emb, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+// Block 1 of the voicemap encoder: Conv1D(filters, 32, 'same') + bias + ReLU + BatchNorm(eval) + MaxPool1D(4,4)
+// on the raw waveform (Cin = 1).  Reference: voicemap/models.py:13-19 (zero pad 15 left / 16 right).
+//
+// HBM-bound layer (AI ~62 F/B): the 32-tap filter bank is run on tcgen05 tensor cores so that arithmetic is
+// free and the kernel streams at the output-write rate.  D[cout, position] = W[cout, tap] * T[position, tap]
+// where T is the Toeplitz (im2col) matrix of the waveform: T[p, k] = x[p + k - 15].
+//   * producer warps read a 39-sample strip per 8 positions, split it into fp16 (hi, lo) and write the
+//     Toeplitz tile straight into the canonical no-swizzle K-major UMMA layout in shared memory
+//     (core matrix = 8 positions x 8 taps; row-group stride padded to 528 B so the 16-byte stores are
+//     bank-conflict free);
+//   * one thread issues 6 MMAs per tile (2 K-steps x {Th*Wh, Tl*Wh, Th*Wl}) into a double-buffered TMEM
+//     accumulator (128 cout lanes x 256 positions);
+//   * 4 epilogue warps pool the raw accumulators 4:1, apply bias/ReLU/BN, split to fp16 (hi, lo) planes and
+//     store channels-last.  As in vm_conv3.cu the packed weights carry sigma = sign(BN scale) so that the
+//     max-pool commutes with the affine.
+#include "vm_common.cuh"
+#include "vm_kernels.h"
+
+namespace vm {
+
+namespace c1 {
+constexpr int kTileN = 256;
+constexpr int kTileM = 128;
+constexpr int kGroupStride = 528;                        // 8-row group: 4 k-chunks x 128 B + 16 B pad
+constexpr int kPlaneBytes = (kTileN / 8) * kGroupStride;  // 16896
+constexpr int kStageBytes = 2 * kPlaneBytes;             // hi + lo
+constexpr int kStages = 4;
+constexpr int kWPlaneBytes = kTileM * 64;                // 128 cout x 32 taps fp16 = 8192
+constexpr int kWSlabBytes = 2 * kWPlaneBytes;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 288;                            // warps 0-3 epilogue, 4 MMA, 5-8 producers
+constexpr int kMaxSlabs = 4;
+__host__ __device__ constexpr int smem_bytes(int nslab) {
+  return nslab * kWSlabBytes + kStages * kStageBytes + 1024 + 256;
+}
+}  // namespace c1
+
+struct __align__(8) Conv1Barriers {
+  uint64_t full[c1::kStages], empty[c1::kStages];
+  uint64_t tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
+}
+
+__global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Params p) {
+  using namespace c1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;
+  uint8_t* stages = smem + p.nslab * kWSlabBytes;
+  Conv1Barriers* bars = reinterpret_cast<Conv1Barriers*>(stages + kStages * kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntiles = p.N * p.nptile;
+  const int nplanes = (p.products == 3) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 128); }
+    fence_mbar_init();
+  }
+  // packed weights -> shared memory (already in the UMMA smem image layout)
+  {
+    const uint4* src = p.wpack;
+    uint4* dst = reinterpret_cast<uint4*>(wsm);
+    const int n16 = p.nslab * kWSlabBytes / 16;
+    for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    fence_proxy_async_smem();
+  }
+  if (warp == 4) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp >= 5) {
+    // ===================== Toeplitz producers: warp q fills stage q for local tiles q, q+4, ... =============
+    const int q = warp - 5;
+    uint32_t i = q;
+    for (int tile = blockIdx.x + q * gridDim.x; tile < ntiles; tile += kStages * gridDim.x, i += kStages) {
+      const int n = tile / p.nptile;
+      const int p0 = (tile % p.nptile) * kTileN;
+      const float* xc = p.x + size_t(n) * p.L;
+      // lane owns the 8 positions p0 + 8*lane .. +7; it needs x[p0 - 15 + 8*lane + i], i = 0..38
+      const int e0 = p0 - 15 + 8 * lane;
+      float xv[39];
+#pragma unroll
+      for (int k = 0; k < 39; ++k) {
+        const int e = e0 + k;
+        xv[k] = (e >= 0 && e < p.L) ? __ldg(xc + e) : 0.f;
+      }
+      __half hh[39], hl[39];
+#pragma unroll
+      for (int k = 0; k < 39; ++k) split_f32(xv[k], hh[k], hl[k]);
+
+      mbar_wait(&bars->empty[q], (((i / kStages) & 1) ^ 1));
+      uint8_t* st = stages + q * kStageBytes + lane * kGroupStride;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        if (pl < nplanes) {
+          const __half* h = pl ? hl : hh;
+          uint32_t pe[19], po[19];  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2])
+#pragma unroll
+          for (int k = 0; k < 19; ++k) {
+            pe[k] = pack_h2(h[2 * k], h[2 * k + 1]);
+            po[k] = pack_h2(h[2 * k + 1], h[2 * k + 2]);
+          }
+          uint8_t* base = st + pl * kPlaneBytes;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = r + 8 * j;  // first element of this 8-tap chunk
+              uint4 w;
+              w.x = (o & 1) ? po[(o - 1) / 2 + 0] : pe[o / 2 + 0];
+              w.y = (o & 1) ? po[(o - 1) / 2 + 1] : pe[o / 2 + 1];
+              w.z = (o & 1) ? po[(o - 1) / 2 + 2] : pe[o / 2 + 2];
+              w.w = (o & 1) ? po[(o - 1) / 2 + 3] : pe[o / 2 + 3];
+              *reinterpret_cast<uint4*>(base + j * 128 + r * 16) = w;
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->full[q]);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+      uint32_t i = 0, ait = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % kStages;
+        mbar_wait(&bars->full[s], (i / kStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t th = smem_u32(stages + s * kStageBytes);
+        const uint32_t tl = th + kPlaneBytes;
+        for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
+          const int buf = ait & 1;
+          mbar_wait(&bars->tempty[buf], ((ait >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + buf * kTileN;
+          const uint32_t wh = smem_u32(wsm + slab * kWSlabBytes);
+          const uint32_t wl = wh + kWPlaneBytes;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
+                     make_smem_desc(th + k * 256, 128, kGroupStride, kLayoutNone), idesc, k);
+          if (nplanes == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
+                       make_smem_desc(tl + k * 256, 128, kGroupStride, kLayoutNone), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_f16(d_tmem, make_smem_desc(wl + k * 256, 128, 512, kLayoutNone),
+                       make_smem_desc(th + k * 256, 128, kGroupStride, kLayoutNone), idesc, 1);
+          }
+          umma_commit(&bars->tfull[buf]);
+        }
+        umma_commit(&bars->empty[s]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3): thread = cout channel =====================
+    const int q = warp;
+    uint32_t ait = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int n = tile / p.nptile;
+      const int p0 = (tile % p.nptile) * kTileN;
+      for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
+        const int buf = ait & 1;
+        const int co = slab * kTileM + q * 32 + lane;
+        const float4 ep = p.epi[co];
+        const bool co_ok = co < p.cout;
+        __half* oh = p.out_hi + (size_t(n) * p.lout) * p.cout + co;
+        __half* ol = p.out_lo + (size_t(n) * p.lout) * p.cout + co;
+        mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
+#pragma unroll 1
+        for (int g = 0; g < kTileN / 32; ++g) {
+          float v[32];
+          tmem_ld_32x32(taddr + g * 32, v);
+          if (g == kTileN / 32 - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&bars->tempty[buf]);
+          }
+          const int j0 = (p0 + g * 32) >> 2;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+            const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
+            if (co_ok && (j0 + j) < p.lout) {
+              __half h, l;
+              split_f32(y, h, l);
+              oh[size_t(j0 + j) * p.cout] = h;
+              if (p.out_lo != nullptr) ol[size_t(j0 + j) * p.cout] = l;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
+                 __half* out_lo, int products, int max_ctas, cudaStream_t stream) {
+  using namespace c1;
+  if (N <= 0 || L < 4) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= 4");
+  if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
+  if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv1: products must be 1 or 3");
+  const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
+  const int nslab = cout_pad / kTileM;
+  if (nslab > kMaxSlabs) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout > 512 not supported");
+  Conv1Params p{};
+  p.x = x; p.N = N; p.L = L; p.cout = cout; p.cout_pad = cout_pad; p.nslab = nslab;
+  p.lout = L / 4;
+  p.nptile = (L + kTileN - 1) / kTileN;
+  p.products = products;
+  p.wpack = reinterpret_cast<const uint4*>(wpack);
+  p.epi = reinterpret_cast<const float4*>(epi);
+  p.out_hi = out_hi; p.out_lo = out_lo;
+  const int smem = smem_bytes(nslab);
+  cudaError_t e = cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "conv1: cudaFuncSetAttribute");
+  const int ntiles = N * p.nptile;
+  int grid = max_ctas > 0 ? max_ctas : num_sms();
+  if (grid > ntiles) grid = ntiles;
+  conv1_kernel<<<grid, kThreads, smem, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv1: launch");
+  return VM_OK;
+}
+
+}  // namespace vm

@@ -1,0 +1,313 @@
+// Blocks 2-4 of the voicemap encoder: Conv1D(k=3,'same') + bias + ReLU + BatchNorm(eval) + MaxPool1D(2),
+// optionally merged with GlobalMaxPool1D (block 4).  Reference: voicemap/models.py:22-37.
+//
+// Implicit GEMM on tcgen05 tensor cores, transposed so that D[cout, position]:
+//   A (M=128)  = packed weights  Wp[plane][tap][cout][cin]   (K-major, TMA 2D, SWIZZLE_128B)
+//   B (N=256)  = activations     X[plane][n][l][cin]         (K-major = channels-last, TMA 3D, SWIZZLE_128B)
+//   D          = 128 cout lanes x 256 position columns, fp32 in TMEM (double buffered: 2 x 256 columns)
+// The three taps reuse ONE halo tile of 258 position rows: tap t reads the same shared-memory tile through a
+// descriptor whose start address is shifted by t rows (t*128 B); 'same' zero padding is TMA out-of-bounds fill.
+//
+// fp32-grade accuracy from fp16 tensor cores: every fp32 operand is carried as two fp16 planes (hi, lo) with
+// x = hi + lo to ~2^-22; D = Xh*Wh + Xl*Wh + Xh*Wl (three MMAs per K step, fp32 accumulate).  `products == 1`
+// keeps only Xh*Wh (throughput mode, ~2^-11 operand rounding).
+//
+// Epilogue (4 warps, thread = one cout channel, columns = consecutive positions): pooling is done on the raw
+// accumulators first -- weights of channels with a negative BN scale are packed negated (sigma = -1) so that
+// max-pooling commutes with the affine:  y = s * relu(sigma * max(acc) + bias) + t.
+#include "vm_common.cuh"
+#include "vm_kernels.h"
+
+namespace vm {
+
+namespace c3 {
+constexpr int kTileN = 256;              // positions per tile (MMA N)
+constexpr int kTileM = 128;              // cout per slab (MMA M)
+constexpr int kKC = 64;                  // channels per K chunk (one 128-byte swizzle row of fp16)
+constexpr int kXRows = 264;              // 258 halo rows, padded to a multiple of 8
+constexpr int kXPlaneBytes = kXRows * 128;         // 33792
+constexpr int kXMainBytes = 256 * 128;             // 32768 (rows 0..255)
+constexpr int kXHaloBytes = 8 * 128;               // 1024  (rows 256..263)
+constexpr int kXSlotBytes = 2 * kXPlaneBytes;      // hi + lo
+constexpr int kXStages = 2;
+constexpr int kWTileBytes = kTileM * 128;          // 16384
+constexpr int kWStages = 5;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 256;
+constexpr int kSmemBytes = kXStages * kXSlotBytes + kWStages * kWTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+}  // namespace c3
+
+struct __align__(8) Conv3Barriers {
+  uint64_t xfull[c3::kXStages], xempty[c3::kXStages];
+  uint64_t wfull[c3::kWStages], wempty[c3::kWStages];
+  uint64_t tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(c3::kThreads, 1)
+conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
+             const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
+             const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+             const Conv3Params p) {
+  using namespace c3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xring = smem;
+  uint8_t* wring = smem + kXStages * kXSlotBytes;
+  Conv3Barriers* bars = reinterpret_cast<Conv3Barriers*>(wring + kWStages * kWTileBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntiles = p.N * p.nptile * p.nslab;
+  const int wplanes = (p.products == 3) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&bars->wfull[i], 1); mbar_init(&bars->wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== X producer: one halo tile (hi+lo) per (tile, K chunk) =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_xh_main); tma_prefetch_desc(&tm_xh_halo);
+      tma_prefetch_desc(&tm_xl_main); tma_prefetch_desc(&tm_xl_halo);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int pt_lin = tile / p.nslab;
+        const int n = pt_lin / p.nptile;
+        const int p0 = (pt_lin % p.nptile) * kTileN;
+        for (int c = 0; c < p.nchunk; ++c, ++it) {
+          const int s = it % kXStages;
+          mbar_wait(&bars->xempty[s], ((it / kXStages) & 1) ^ 1);
+          uint8_t* dst = xring + s * kXSlotBytes;
+          mbar_arrive_expect_tx(&bars->xfull[s], wplanes * kXPlaneBytes);
+          tma_load_3d(dst, &tm_xh_main, &bars->xfull[s], c * kKC, p0 - 1, n);
+          tma_load_3d(dst + kXMainBytes, &tm_xh_halo, &bars->xfull[s], c * kKC, p0 + 255, n);
+          if (wplanes == 2) {
+            tma_load_3d(dst + kXPlaneBytes, &tm_xl_main, &bars->xfull[s], c * kKC, p0 - 1, n);
+            tma_load_3d(dst + kXPlaneBytes + kXMainBytes, &tm_xl_halo, &bars->xfull[s], c * kKC, p0 + 255, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== W producer: one [128 cout x 64 cin] tile per (tile, chunk, tap, plane) ==========
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_wh); tma_prefetch_desc(&tm_wl);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int slab = tile % p.nslab;
+        for (int c = 0; c < p.nchunk; ++c) {
+          for (int tap = 0; tap < 3; ++tap) {
+            for (int pl = 0; pl < wplanes; ++pl, ++it) {
+              const int s = it % kWStages;
+              mbar_wait(&bars->wempty[s], ((it / kWStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars->wfull[s], kWTileBytes);
+              tma_load_2d(wring + s * kWTileBytes, pl == 0 ? &tm_wh : &tm_wl, &bars->wfull[s], c * kKC,
+                          tap * p.cout_pad + slab * kTileM);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+      uint32_t xit = 0, wit = 0, tit = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
+        const int buf = tit & 1;
+        mbar_wait(&bars->tempty[buf], ((tit >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * kTileN;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.nchunk; ++c, ++xit) {
+          const int xs = xit % kXStages;
+          mbar_wait(&bars->xfull[xs], (xit / kXStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t xh = smem_u32(xring + xs * kXSlotBytes);
+          const uint32_t xl = xh + kXPlaneBytes;
+          for (int tap = 0; tap < 3; ++tap) {
+            const uint32_t bo = (p.desc_mode == 1) ? uint32_t(tap) : 0u;
+            const uint32_t bh = xh + tap * 128, bl = xl + tap * 128;
+            {  // W hi: Xh*Wh (+ Xl*Wh)
+              const int ws = wit % kWStages;
+              mbar_wait(&bars->wfull[ws], (wit / kWStages) & 1);
+              tc_fence_after_sync();
+              const uint32_t wa = smem_u32(wring + ws * kWTileBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128, bo), idesc, acc);
+                acc = 1;
+              }
+              if (wplanes == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                           make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128, bo), idesc, 1);
+              }
+              umma_commit(&bars->wempty[ws]);
+              ++wit;
+            }
+            if (wplanes == 2) {  // W lo: Xh*Wl
+              const int ws = wit % kWStages;
+              mbar_wait(&bars->wfull[ws], (wit / kWStages) & 1);
+              tc_fence_after_sync();
+              const uint32_t wa = smem_u32(wring + ws * kWTileBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128, bo), idesc, 1);
+              umma_commit(&bars->wempty[ws]);
+              ++wit;
+            }
+          }
+          umma_commit(&bars->xempty[xs]);
+        }
+        umma_commit(&bars->tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = cout channel, columns = positions =====================
+    const int q = warp & 3;  // TMEM lane quarter
+    uint32_t tit = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
+      const int slab = tile % p.nslab;
+      const int pt_lin = tile / p.nslab;
+      const int n = pt_lin / p.nptile;
+      const int pt = pt_lin % p.nptile;
+      const int p0 = pt * kTileN;
+      const int buf = tit & 1;
+      const int co = slab * kTileM + q * 32 + lane;
+      const float4 ep = p.epi[co];  // {sigma, bias, s, t}; padded channels hold zeros
+      const bool co_ok = co < p.cout;
+      mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
+      const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
+      if (p.gmax_partial != nullptr) {
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int g = 0; g < kTileN / 32; ++g) {
+          float v[32];
+          tmem_ld_32x32(taddr + g * 32, v);
+          const int pos = p0 + g * 32;
+          if (pos + 32 <= lvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (pos + j < lvalid) m = fmaxf(m, v[j]);
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&bars->tempty[buf]);
+        p.gmax_partial[(size_t(n) * p.nptile + pt) * p.cout_pad + co] = m;
+      } else {
+        __half* oh = p.out_hi + (size_t(n) * p.lout) * p.cout + co;
+        __half* ol = p.out_lo + (size_t(n) * p.lout) * p.cout + co;
+#pragma unroll 1
+        for (int g = 0; g < kTileN / 32; ++g) {
+          float v[32];
+          tmem_ld_32x32(taddr + g * 32, v);
+          if (g == kTileN / 32 - 1) {  // all TMEM reads of this buffer are done
+            tc_fence_before_sync();
+            mbar_arrive(&bars->tempty[buf]);
+          }
+          const int j0 = (p0 + g * 32) >> 1;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float mx = fmaxf(v[2 * j], v[2 * j + 1]);
+            const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
+            if (co_ok && (j0 + j) < p.lout) {
+              __half h, l;
+              split_f32(y, h, l);
+              oh[size_t(j0 + j) * p.cout] = h;
+              if (p.out_lo != nullptr) ol[size_t(j0 + j) * p.cout] = l;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int desc_mode,
+                 int max_ctas, cudaStream_t stream) {
+  using namespace c3;
+  if (N <= 0 || L <= 0) return set_error(VM_ERR_SHAPE, "conv3: N and L must be positive");
+  if (cin % kKC != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 64");
+  if (cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cout must be a multiple of 8");
+  if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1 or 3");
+  if (gmax_partial == nullptr && out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv3: no output given");
+  if (L / 2 <= 0) return set_error(VM_ERR_SHAPE, "conv3: L must be >= 2");
+  const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
+
+  Conv3Params p{};
+  p.N = N; p.L = L; p.cin = cin; p.cout = cout; p.cout_pad = cout_pad;
+  p.lout = L / 2;
+  p.nptile = (L + kTileN - 1) / kTileN;
+  p.nslab = cout_pad / kTileM;
+  p.nchunk = cin / kKC;
+  p.products = products;
+  p.desc_mode = desc_mode;
+  p.epi = reinterpret_cast<const float4*>(epi);
+  p.out_hi = out_hi; p.out_lo = out_lo; p.gmax_partial = gmax_partial;
+
+  CUtensorMap xh_main, xh_halo, xl_main, xl_halo, wh, wl;
+  // X planes: (N, L, Cin) fp16, dims fastest-first {Cin, L, N}
+  const uint64_t xdims[3] = {uint64_t(cin), uint64_t(L), uint64_t(N)};
+  const uint64_t xstr[2] = {uint64_t(cin) * 2, uint64_t(L) * cin * 2};
+  const uint32_t box_main[3] = {kKC, 256, 1}, box_halo[3] = {kKC, 8, 1};
+  int rc;
+  if ((rc = make_tensor_map(&xh_main, in_hi, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&xh_halo, in_hi, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
+  const __half* lo_src = (products == 3) ? in_lo : in_hi;
+  if (products == 3 && in_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: lo plane required for products=3");
+  if ((rc = make_tensor_map(&xl_main, lo_src, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&xl_halo, lo_src, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
+  // W planes: [plane][tap*cout_pad + cout][cin] fp16
+  const uint64_t wdims[2] = {uint64_t(cin), uint64_t(3) * cout_pad};
+  const uint64_t wstr[1] = {uint64_t(cin) * 2};
+  const uint32_t wbox[2] = {kKC, kTileM};
+  const __half* w_hi = wpack;
+  const __half* w_lo = wpack + size_t(3) * cout_pad * cin;
+  if ((rc = make_tensor_map(&wh, w_hi, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&wl, w_lo, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int ntiles = N * p.nptile * p.nslab;
+  int grid = max_ctas > 0 ? max_ctas : num_sms();
+  if (grid > ntiles) grid = ntiles;
+  conv3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv3: launch");
+  return VM_OK;
+}
+
+}  // namespace vm

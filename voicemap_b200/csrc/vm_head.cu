@@ -1,0 +1,244 @@
+// Small CUDA-core kernels around the two conv kernels:
+//   * weight packing (Keras layout fp32 -> fp16 (hi, lo) planes in the layouts the MMA kernels consume, BN folded
+//     into per-channel epilogue constants)                                   voicemap/models.py:13-35
+//   * fp32 <-> (hi, lo) plane conversion for the per-block C-ABI and the tests
+//   * GlobalMaxPool1D finalisation + Dense(embedding_dimension)               voicemap/models.py:37-39
+//   * siamese head (pairwise L2 / |.|, Dense(1), sigmoid) + contrastive / BCE loss
+//                                                   voicemap/models.py:55-69, voicemap/utils.py:77-85
+#include "vm_common.cuh"
+#include "vm_kernels.h"
+
+namespace vm {
+
+// epilogue constants: y = s * relu(sigma * max(acc') + bias) + t with acc' computed from sigma-scaled weights
+__device__ __forceinline__ float4 fold_bn(float bias, float gamma, float beta, float mean, float var, float eps) {
+  const float s = gamma * (1.0f / sqrtf(var + eps));
+  const float t = beta - mean * s;
+  const float sigma = (s < 0.f) ? -1.f : 1.f;
+  return make_float4(sigma, bias, s, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv3 weights: w (3, cin, cout) fp32 -> wpack [plane][tap][cout_pad][cin] fp16
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cin,
+                                  int cout, int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
+  const size_t total = size_t(3) * cout_pad * cin;
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < size_t(cout_pad)) {
+    const int co = int(idx);
+    epi[co] = (co < cout) ? fold_bn(bias[co], gamma[co], beta[co], mean[co], var[co], eps)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (idx >= total) return;
+  const int ci = int(idx % cin);
+  const int co = int((idx / cin) % cout_pad);
+  const int tap = int(idx / (size_t(cin) * cout_pad));
+  float v = 0.f;
+  if (co < cout) {
+    const float s = gamma[co] * (1.0f / sqrtf(var[co] + eps));
+    v = w[(size_t(tap) * cin + ci) * cout + co];
+    if (s < 0.f) v = -v;
+  }
+  __half h, l;
+  split_f32(v, h, l);
+  wpack[idx] = h;
+  wpack[total + idx] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1 weights: w (32, 1, cout) fp32 -> [slab][plane] 8 KB smem images (no-swizzle K-major core matrices:
+// byte offset of (row, tap) = (row/8)*512 + (tap/8)*128 + (row%8)*16 + (tap%8)*2)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
+                                  int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < cout_pad)
+    epi[idx] = (idx < cout) ? fold_bn(bias[idx], gamma[idx], beta[idx], mean[idx], var[idx], eps)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx >= cout_pad * 32) return;
+  const int tap = idx & 31;
+  const int co = idx >> 5;
+  float v = 0.f;
+  if (co < cout) {
+    const float s = gamma[co] * (1.0f / sqrtf(var[co] + eps));
+    v = w[size_t(tap) * cout + co];
+    if (s < 0.f) v = -v;
+  }
+  __half h, l;
+  split_f32(v, h, l);
+  const int slab = co >> 7, row = co & 127;
+  const int off = (row >> 3) * 256 + (tap >> 3) * 64 + (row & 7) * 8 + (tap & 7);  // in halves
+  __half* img = wpack + size_t(slab) * 8192;                                        // 2 planes x 4096 halves
+  img[off] = h;
+  img[4096 + off] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ hi,
+                                    __half* __restrict__ lo) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    __half h, l;
+    split_f32(x[i], h, l);
+    hi[i] = h;
+    if (lo != nullptr) lo[i] = l;
+  }
+}
+__global__ void merge_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t n,
+                                    float* __restrict__ x) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    x[i] = __half2float(hi[i]) + (lo != nullptr ? __half2float(lo[i]) : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GlobalMaxPool finalisation + Dense.  partial: (N, T, c_pad) raw accumulator maxima per position tile.
+// ---------------------------------------------------------------------------------------------
+__global__ void gmax_dense_kernel(const float* __restrict__ partial, int T, int C, int c_pad,
+                                  const float4* __restrict__ epi, const float* __restrict__ dense_w,
+                                  const float* __restrict__ dense_b, int E, float* __restrict__ gmax_out,
+                                  float* __restrict__ emb) {
+  extern __shared__ float g[];
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) m = fmaxf(m, partial[(size_t(n) * T + t) * c_pad + c]);
+    const float4 ep = epi[c];
+    const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, m, ep.y), 0.f), ep.w);
+    g[c] = y;
+    if (gmax_out != nullptr) gmax_out[size_t(n) * C + c] = y;
+  }
+  __syncthreads();
+  if (emb == nullptr) return;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(g[c], dense_w[size_t(c) * E + e], acc);
+    emb[size_t(n) * E + e] = acc + dense_b[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// siamese head + loss.  metric 0: uniform_euclidean (head_w, head_b scalars), 1: weighted_l1 (head_w[E]).
+// loss_kind 0: none, 1: contrastive (margin 1), 2: binary cross-entropy (keras clip 1e-7).  One block.
+// ---------------------------------------------------------------------------------------------
+__global__ void pair_head_loss_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int N, int E,
+                                      int metric, const float* __restrict__ head_w, const float* __restrict__ head_b,
+                                      const float* __restrict__ y_true, int loss_kind, float* __restrict__ dist,
+                                      float* __restrict__ prob, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float local = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* a = e1 + size_t(n) * E;
+    const float* b = e2 + size_t(n) * E;
+    float z;
+    if (metric == 0) {
+      float ss = 0.f;
+      for (int j = 0; j < E; ++j) {
+        const float d = a[j] - b[j];
+        ss = fmaf(d, d, ss);
+      }
+      const float d = sqrtf(fmaxf(ss, 0.f));
+      if (dist != nullptr) dist[n] = d;
+      z = fmaf(d, head_w[0], head_b[0]);
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < E; ++j) acc = fmaf(fabsf(a[j] - b[j]), head_w[j], acc);
+      z = acc + head_b[0];
+    }
+    const float pr = 1.0f / (1.0f + expf(-z));
+    if (prob != nullptr) prob[n] = pr;
+    if (loss_kind == 1) {
+      const float y = y_true[n];
+      const float mg = fmaxf(1.0f - pr, 0.f);
+      local += (1.f - y) * pr * pr + y * mg * mg;
+    } else if (loss_kind == 2) {
+      const float y = y_true[n];
+      const float pc = fminf(fmaxf(pr, 1e-7f), 1.0f - 1e-7f);
+      local += -y * logf(pc) - (1.f - y) * logf(1.0f - pc);
+    }
+  }
+  if (loss_kind == 0 || loss == nullptr) return;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) loss[0] = v / float(N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  return VM_OK;
+}
+
+int launch_pack_conv3(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                      const float* var, float eps, int cin, int cout, void* wpack, float* epi, cudaStream_t stream) {
+  if (cin <= 0 || cout <= 0) return set_error(VM_ERR_SHAPE, "pack_conv3: bad shape");
+  const int cout_pad = (cout + 127) / 128 * 128;
+  const size_t total = size_t(3) * cout_pad * cin;
+  const int threads = 256;
+  const unsigned blocks = unsigned((total + threads - 1) / threads);
+  pack_conv3_kernel<<<blocks, threads, 0, stream>>>(w, bias, gamma, beta, mean, var, eps, cin, cout, cout_pad,
+                                                   static_cast<__half*>(wpack), reinterpret_cast<float4*>(epi));
+  return check_launch("pack_conv3");
+}
+
+int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                      const float* var, float eps, int cout, void* wpack, float* epi, cudaStream_t stream) {
+  if (cout <= 0) return set_error(VM_ERR_SHAPE, "pack_conv1: bad shape");
+  const int cout_pad = (cout + 127) / 128 * 128;
+  const int total = cout_pad * 32;
+  pack_conv1_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, bias, gamma, beta, mean, var, eps, cout, cout_pad,
+                                                            static_cast<__half*>(wpack),
+                                                            reinterpret_cast<float4*>(epi));
+  return check_launch("pack_conv1");
+}
+
+int launch_split_planes(const float* x, size_t n, __half* hi, __half* lo, cudaStream_t stream) {
+  if (n == 0) return VM_OK;
+  const unsigned blocks = unsigned(min(size_t(148 * 16), (n + 255) / 256));
+  split_planes_kernel<<<blocks, 256, 0, stream>>>(x, n, hi, lo);
+  return check_launch("split_planes");
+}
+
+int launch_merge_planes(const __half* hi, const __half* lo, size_t n, float* x, cudaStream_t stream) {
+  if (n == 0) return VM_OK;
+  const unsigned blocks = unsigned(min(size_t(148 * 16), (n + 255) / 256));
+  merge_planes_kernel<<<blocks, 256, 0, stream>>>(hi, lo, n, x);
+  return check_launch("merge_planes");
+}
+
+int launch_gmax_dense(const float* partial, int N, int T, int C, int c_pad, const float* epi, const float* dense_w,
+                      const float* dense_b, int E, float* gmax_out, float* emb, cudaStream_t stream) {
+  if (N <= 0 || T <= 0 || C <= 0 || c_pad < C) return set_error(VM_ERR_SHAPE, "gmax_dense: bad shape");
+  if (emb != nullptr && (E <= 0 || dense_w == nullptr || dense_b == nullptr))
+    return set_error(VM_ERR_SHAPE, "gmax_dense: dense weights missing");
+  if (size_t(C) * sizeof(float) > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "gmax_dense: C > 12288");
+  gmax_dense_kernel<<<N, 128, C * sizeof(float), stream>>>(partial, T, C, c_pad, reinterpret_cast<const float4*>(epi),
+                                                          dense_w, dense_b, E, gmax_out, emb);
+  return check_launch("gmax_dense");
+}
+
+int launch_pair_head_loss(const float* e1, const float* e2, int N, int E, int metric, const float* head_w,
+                          const float* head_b, const float* y_true, int loss_kind, float* dist, float* prob,
+                          float* loss, cudaStream_t stream) {
+  if (N <= 0 || E <= 0) return set_error(VM_ERR_SHAPE, "pair_head_loss: bad shape");
+  if (metric != 0 && metric != 1) return set_error(VM_ERR_UNSUPPORTED, "pair_head_loss: metric not implemented");
+  if (loss_kind != 0 && y_true == nullptr) return set_error(VM_ERR_SHAPE, "pair_head_loss: y_true required");
+  pair_head_loss_kernel<<<1, 256, 0, stream>>>(e1, e2, N, E, metric, head_w, head_b, y_true, loss_kind, dist, prob,
+                                               loss);
+  return check_launch("pair_head_loss");
+}
+
+}  // namespace vm

@@ -1,0 +1,70 @@
+// Internal declarations shared by the kernel translation units and the C-ABI layer (vm_api.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/voicemap_b200.h"
+
+namespace vm {
+
+// ---- error reporting (thread-local last error string, C-ABI: vm_last_error_string) ----
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+int num_sms();
+
+// ---- TMA descriptor creation through the driver entry point (no link-time libcuda dependency) ----
+enum { VM_SWIZZLE_NONE = 0, VM_SWIZZLE_32B = 1, VM_SWIZZLE_64B = 2, VM_SWIZZLE_128B = 3 };
+int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle);
+
+// ---- block 1 ----
+struct Conv1Params {
+  const float* x;        // (N, L) fp32 (Keras (N, L, 1))
+  int N, L;
+  int cout, cout_pad, nslab;
+  int lout;              // L / 4
+  int nptile;            // ceil(L / 256)
+  int products;          // 3: fp16x3 (fp32-grade), 1: fp16x1
+  const uint4* wpack;    // [slab][plane][8 KB smem image]
+  const float4* epi;     // [cout_pad] {sigma, bias, s, t}
+  __half* out_hi;        // (N, lout, cout)
+  __half* out_lo;
+};
+int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
+                 __half* out_lo, int products, int max_ctas, cudaStream_t stream);
+
+// ---- blocks 2-4 ----
+struct Conv3Params {
+  int N, L, cin, cout, cout_pad;
+  int lout;              // L / 2
+  int nptile;            // ceil(L / 256)
+  int nslab;             // cout_pad / 128
+  int nchunk;            // cin / 64
+  int products;
+  int desc_mode;         // 0: tap shift via start address only; 1: also set the descriptor base_offset
+  const float4* epi;     // [cout_pad]
+  __half* out_hi;        // (N, lout, cout) or null
+  __half* out_lo;
+  float* gmax_partial;   // (N, nptile, cout_pad) raw accumulator maxima, or null
+};
+int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int desc_mode,
+                 int max_ctas, cudaStream_t stream);
+
+// ---- small kernels (vm_head.cu) ----
+int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                      const float* var, float eps, int cout, void* wpack, float* epi, cudaStream_t stream);
+int launch_pack_conv3(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                      const float* var, float eps, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);
+int launch_split_planes(const float* x, size_t n, __half* hi, __half* lo, cudaStream_t stream);
+int launch_merge_planes(const __half* hi, const __half* lo, size_t n, float* x, cudaStream_t stream);
+int launch_gmax_dense(const float* partial, int N, int T, int C, int c_pad, const float* epi, const float* dense_w,
+                      const float* dense_b, int E, float* gmax_out, float* emb, cudaStream_t stream);
+int launch_pair_head_loss(const float* e1, const float* e2, int N, int E, int metric, const float* head_w,
+                          const float* head_b, const float* y_true, int loss_kind, float* dist, float* prob,
+                          float* loss, cudaStream_t stream);
+
+}  // namespace vm
