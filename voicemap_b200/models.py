@@ -1,0 +1,378 @@
+"""voicemap.models on B200: the two builder functions of the reference with unchanged signatures
+(voicemap/models.py:6 and :44), returning objects that expose the Keras-method subset voicemap's scripts call
+(SURVEY.md 8(b)).  All network arithmetic runs in libvoicemap_b200.so through ``EncoderEngine``.
+"""
+from __future__ import annotations
+
+import json
+from collections import OrderedDict
+
+import numpy as np
+
+from .keras_compat import Adam, Dense
+
+DISTANCE_METRICS = ('uniform_euclidean', 'weighted_euclidean',
+                    'uniform_l1', 'weighted_l1',
+                    'dot_product', 'cosine_distance')
+
+_PREDICT_CHUNK = 4096  # clips per device launch in predict(); results do not depend on it (eval mode)
+
+
+def _glorot_uniform(shape, rng):
+    if len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rec = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
+    limit = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+class LayerInfo:
+    """Entry of ``model.layers`` (name / class / config / weight names), enough for summary() and indexing."""
+
+    def __init__(self, name, class_name, config=None, weight_names=(), model=None):
+        self.name = name
+        self.class_name = class_name
+        self.config = dict(config or {})
+        self.weight_names = tuple(weight_names)
+        self._model = model
+
+    def __repr__(self):
+        return f"<{self.class_name} {self.name}>"
+
+
+class _ModelBase:
+    optimizer = None
+    loss = None
+    metrics = None
+    _engine = None
+
+    # ---- Keras plumbing shared by both model kinds
+    def compile(self, loss=None, optimizer=None, metrics=None, **_):
+        """model.compile(loss=<str|callable>, optimizer=Adam(...), metrics=['accuracy'])
+        (experiments/train_siamese.py:57, siamese_contrastive_loss.py:70)."""
+        from .utils import contrastive_loss
+        if callable(loss):
+            if loss is not contrastive_loss:
+                raise NotImplementedError("only voicemap.utils.contrastive_loss is supported as a callable loss")
+            loss = "contrastive_loss"
+        if loss not in ("binary_crossentropy", "categorical_crossentropy", "contrastive_loss"):
+            raise NotImplementedError(f"loss {loss!r} is not used on the voicemap path")
+        self.loss = loss
+        self.optimizer = optimizer if optimizer is not None else Adam()
+        self.metrics = list(metrics or [])
+
+    def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None,
+                      validation_data=None, validation_steps=None, workers=1, use_multiprocessing=False,
+                      initial_epoch=0, **_):
+        from .training import fit_generator
+        return fit_generator(self, generator, steps_per_epoch=steps_per_epoch, epochs=epochs, verbose=verbose,
+                             callbacks=callbacks, validation_data=validation_data,
+                             validation_steps=validation_steps, initial_epoch=initial_epoch)
+
+    def summary(self, print_fn=None):
+        lines = ["_" * 65, f"{'Layer (type)':<40}{'Param #':>25}", "=" * 65]
+        total = 0
+        for layer in self.layers:
+            n = int(sum(np.prod(self._weight(w).shape) for w in layer.weight_names)) if layer.weight_names else 0
+            if isinstance(layer, _ModelBase):
+                n = layer.count_params()
+                lines.append(f"{layer.name + ' (Sequential)':<40}{n:>25}")
+            else:
+                lines.append(f"{layer.name + ' (' + layer.class_name + ')':<40}{n:>25}")
+            total += n
+        lines += ["=" * 65, f"Total params: {total:,}", "_" * 65]
+        text = "\n".join(lines)
+        (print_fn or print)(text)
+        return None
+
+    def save(self, filepath, overwrite=True):
+        """Full-model container (architecture json + weights).  npz, not HDF5."""
+        arrays = {f"w{i}": w for i, w in enumerate(self.get_weights())}
+        arrays["config"] = np.frombuffer(json.dumps(self.get_config()).encode(), dtype=np.uint8)
+        with open(filepath, "wb") as fh:
+            np.savez(fh, **arrays)
+
+
+class EncoderModel(_ModelBase):
+    """Sequential returned by get_baseline_convolutional_encoder (voicemap/models.py:6-41), optionally extended
+    with a classification head through ``add(Dense(n, activation='softmax'))``."""
+
+    def __init__(self, filters, embedding_dimension, input_shape=None, dropout=0.05, seed=None, name="sequential_1"):
+        self.name = name
+        self.filters = int(filters)
+        self.embedding_dimension = int(embedding_dimension)
+        self.input_shape = tuple(input_shape) if input_shape is not None else None
+        self.dropout = float(dropout)
+        self.precision = 3
+        rng = np.random.default_rng(seed)
+        f = self.filters
+        self.weights = OrderedDict()
+        self.layers = []
+        cin = 1
+        for i, (k, mult, pool) in enumerate(((32, 1, 4), (3, 2, 2), (3, 3, 2), (3, 4, 2)), start=1):
+            cout = mult * f
+            self.weights[f"conv{i}_kernel"] = _glorot_uniform((k, cin, cout), rng)
+            self.weights[f"conv{i}_bias"] = np.zeros((cout,), np.float32)
+            self.weights[f"bn{i}_gamma"] = np.ones((cout,), np.float32)
+            self.weights[f"bn{i}_beta"] = np.zeros((cout,), np.float32)
+            self.weights[f"bn{i}_mean"] = np.zeros((cout,), np.float32)
+            self.weights[f"bn{i}_var"] = np.ones((cout,), np.float32)
+            self.layers += [
+                LayerInfo(f"conv1d_{i}", "Conv1D", dict(filters=cout, kernel_size=k, padding="same", activation="relu"),
+                          (f"conv{i}_kernel", f"conv{i}_bias"), self),
+                LayerInfo(f"batch_normalization_{i}", "BatchNormalization", dict(epsilon=1e-3, momentum=0.99),
+                          (f"bn{i}_gamma", f"bn{i}_beta", f"bn{i}_mean", f"bn{i}_var"), self),
+                LayerInfo(f"spatial_dropout1d_{i}", "SpatialDropout1D", dict(rate=self.dropout), (), self),
+                LayerInfo(f"max_pooling1d_{i}", "MaxPooling1D", dict(pool_size=pool, strides=pool), (), self),
+            ]
+            cin = cout
+        self.layers.append(LayerInfo("global_max_pooling1d_1", "GlobalMaxPooling1D", {}, (), self))
+        self.weights["dense_kernel"] = _glorot_uniform((4 * f, self.embedding_dimension), rng)
+        self.weights["dense_bias"] = np.zeros((self.embedding_dimension,), np.float32)
+        self.layers.append(LayerInfo("dense_1", "Dense", dict(units=self.embedding_dimension, activation="linear"),
+                                     ("dense_kernel", "dense_bias"), self))
+        self._n_encoder_layers = len(self.layers)
+        self._head = None          # classification head: dict(units, activation)
+        self._has_embedding_dense = True
+        self._rng = rng
+        self._engine = None
+        self._engine_dirty = True
+
+    # ---- Sequential API
+    def add(self, layer):
+        """classifier.add(Dense(num_classes, activation='softmax')) (experiments/train_classifier.py:112)."""
+        if not isinstance(layer, Dense):
+            raise NotImplementedError("only a Dense head can be added to the voicemap encoder")
+        if self._head is not None:
+            raise NotImplementedError("a single Dense head is supported")
+        self._head = dict(units=layer.units, activation=layer.activation or "linear")
+        self.weights["head_kernel"] = _glorot_uniform((self.embedding_dimension, layer.units), self._rng)
+        self.weights["head_bias"] = np.zeros((layer.units,), np.float32)
+        self.layers.append(LayerInfo("dense_2", "Dense", dict(units=layer.units, activation=layer.activation),
+                                     ("head_kernel", "head_bias"), self))
+
+    def pop(self):
+        """Remove the last layer (voicemap/utils.py:145 strips the softmax head of a classifier clone)."""
+        if self._head is None:
+            raise NotImplementedError("only an added Dense head can be popped from the voicemap encoder")
+        self.layers.pop()
+        self._head = None
+        del self.weights["head_kernel"], self.weights["head_bias"]
+
+    def _weight(self, name):
+        return self.weights[name]
+
+    def count_params(self):
+        return int(sum(w.size for w in self.weights.values()))
+
+    def get_weights(self):
+        """Keras order: per layer kernel,bias / gamma,beta,moving_mean,moving_variance / ... / dense / head."""
+        return [w.copy() for w in self.weights.values()]
+
+    def set_weights(self, weights):
+        weights = list(weights)
+        if len(weights) != len(self.weights):
+            raise ValueError(f"You called `set_weights(weights)` with a weight list of length {len(weights)}, "
+                             f"but the model was expecting {len(self.weights)} weights.")
+        for (name, old), new in zip(self.weights.items(), weights):
+            new = np.asarray(new, dtype=np.float32)
+            if new.shape != old.shape:
+                raise ValueError(f"Layer weight shape {old.shape} not compatible with provided weight shape "
+                                 f"{new.shape} ({name})")
+            self.weights[name] = new.copy()
+        self._engine_dirty = True
+
+    def set_named_weights(self, mapping):
+        for name, value in mapping.items():
+            value = np.asarray(value, dtype=np.float32)
+            if value.shape != self.weights[name].shape:
+                raise ValueError(f"{name}: expected {self.weights[name].shape}, got {value.shape}")
+            self.weights[name] = value.copy()
+        self._engine_dirty = True
+
+    def get_config(self):
+        return dict(kind="encoder", filters=self.filters, embedding_dimension=self.embedding_dimension,
+                    input_shape=self.input_shape, dropout=self.dropout, head=self._head)
+
+    def _clone(self):
+        m = EncoderModel(self.filters, self.embedding_dimension, self.input_shape, self.dropout)
+        if self._head is not None:
+            m.add(Dense(self._head["units"], activation=self._head["activation"]))
+        return m
+
+    # ---- device
+    def _get_engine(self):
+        from .engine import EncoderEngine
+        if self._engine is None:
+            self._engine = EncoderEngine(self.filters, self.embedding_dimension, precision=self.precision)
+            self._engine_dirty = True
+        if self._engine_dirty:
+            self._engine.set_weights(self.weights)
+            self._engine_dirty = False
+        return self._engine
+
+    def _check_input(self, x):
+        x = np.asarray(x)
+        if x.ndim != 3 or x.shape[2] != 1:
+            raise ValueError(f"Error when checking input: expected input to have shape (N, L, 1) but got array "
+                             f"with shape {x.shape}")
+        if self.input_shape is not None and tuple(x.shape[1:]) != tuple(self.input_shape):
+            raise ValueError(f"Error when checking input: expected conv1d_1_input to have shape "
+                             f"{self.input_shape} but got array with shape {x.shape[1:]}")
+        return x
+
+    def embed_device(self, x_dev):
+        """x_dev: CUDA fp32 (N, L[, 1]) -> CUDA (N, embedding_dimension)."""
+        return self._get_engine().forward(x_dev)
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """model.predict(x): eval-mode forward (moving BN statistics, no dropout).  x: numpy (N, L, 1), any float
+        dtype (cast to float32 like Keras' floatx).  Returns numpy float32."""
+        import torch
+        x = self._check_input(x)
+        eng = self._get_engine()
+        outs = []
+        for i in range(0, x.shape[0], _PREDICT_CHUNK):
+            xb = torch.from_numpy(np.ascontiguousarray(x[i:i + _PREDICT_CHUNK, :, 0], dtype=np.float32))
+            emb = eng.forward(xb.to(eng.device, non_blocking=False))
+            if self._head is not None:
+                emb = self._apply_head(emb)
+            outs.append(emb.cpu().numpy())
+        return np.concatenate(outs, axis=0) if len(outs) != 1 else outs[0]
+
+    def _apply_head(self, emb):
+        # classifier head Dense(num_classes, softmax): adjacent to the hot path, device-side
+        import torch
+        w = torch.from_numpy(self.weights["head_kernel"]).to(emb.device)
+        b = torch.from_numpy(self.weights["head_bias"]).to(emb.device)
+        z = emb @ w + b
+        act = self._head["activation"]
+        if act == "softmax":
+            return torch.softmax(z, dim=-1)
+        if act == "sigmoid":
+            return torch.sigmoid(z)
+        return z
+
+
+class SiameseModel(_ModelBase):
+    """Model returned by build_siamese_net (voicemap/models.py:44-81): the shared encoder on two inputs, a distance
+    layer and Dense(1, sigmoid).  ``layers[2]`` is the encoder (voicemap/utils.py:141)."""
+
+    def __init__(self, encoder, input_shape, distance_metric, seed=None):
+        self.name = "model_1"
+        self.encoder = encoder
+        self.input_shape = tuple(input_shape)
+        self.distance_metric = distance_metric
+        rng = np.random.default_rng(seed)
+        emb = encoder.embedding_dimension
+        in_dim = emb if distance_metric == 'weighted_l1' else 1
+        self.head_weights = OrderedDict(
+            head_kernel=_glorot_uniform((in_dim, 1), rng), head_bias=np.zeros((1,), np.float32))
+        if distance_metric == 'weighted_l1':
+            mid = [LayerInfo("subtract_1", "Subtract", {}, (), self), LayerInfo("lambda_1", "Lambda", {}, (), self)]
+        else:
+            mid = [LayerInfo("subtract_embeddings", "Subtract", {}, (), self),
+                   LayerInfo("euclidean_distance", "Lambda", {}, (), self)]
+        self.layers = [LayerInfo("input_1", "InputLayer", {}, (), self), LayerInfo("input_2", "InputLayer", {}, (), self),
+                       encoder, *mid,
+                       LayerInfo("dense_2", "Dense", dict(units=1, activation="sigmoid"),
+                                 ("head_kernel", "head_bias"), self)]
+        self._head_dev = None
+
+    def _weight(self, name):
+        return self.head_weights[name]
+
+    def count_params(self):
+        return self.encoder.count_params() + int(sum(w.size for w in self.head_weights.values()))
+
+    def get_weights(self):
+        return self.encoder.get_weights() + [w.copy() for w in self.head_weights.values()]
+
+    def set_weights(self, weights):
+        weights = list(weights)
+        n_enc = len(self.encoder.weights)
+        if len(weights) != n_enc + 2:
+            raise ValueError(f"expected {n_enc + 2} weight arrays, got {len(weights)}")
+        self.encoder.set_weights(weights[:n_enc])
+        for (name, old), new in zip(self.head_weights.items(), weights[n_enc:]):
+            new = np.asarray(new, np.float32)
+            if new.shape != old.shape:
+                raise ValueError(f"{name}: expected {old.shape}, got {new.shape}")
+            self.head_weights[name] = new.copy()
+        self._head_dev = None
+
+    def get_config(self):
+        return dict(kind="siamese", encoder=self.encoder.get_config(), input_shape=self.input_shape,
+                    distance_metric=self.distance_metric)
+
+    def _clone(self):
+        return SiameseModel(self.encoder._clone(), self.input_shape, self.distance_metric)
+
+    def _head_device(self, device):
+        import torch
+        if self._head_dev is None or self._head_dev[0].device != device:
+            self._head_dev = (torch.from_numpy(self.head_weights["head_kernel"].reshape(-1).copy()).to(device),
+                              torch.from_numpy(self.head_weights["head_bias"].copy()).to(device))
+        return self._head_dev
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """siamese.predict([input_1, input_2]) -> (N, 1) sigmoid outputs (voicemap/utils.py:133)."""
+        import torch
+        from .engine import pair_head_loss
+        if not isinstance(x, (list, tuple)) or len(x) != 2:
+            raise ValueError("Error when checking model input: the siamese network expects a list of 2 arrays")
+        x1 = self.encoder._check_input(x[0])
+        x2 = self.encoder._check_input(x[1])
+        if x1.shape != x2.shape:
+            raise ValueError(f"siamese inputs must have the same shape, got {x1.shape} and {x2.shape}")
+        if tuple(x1.shape[1:]) != self.input_shape:
+            raise ValueError(f"Error when checking input: expected input_1 to have shape {self.input_shape} but got "
+                             f"array with shape {x1.shape[1:]}")
+        eng = self.encoder._get_engine()
+        w, b = self._head_device(eng.device)
+        outs = []
+        half = _PREDICT_CHUNK // 2
+        for i in range(0, x1.shape[0], half):
+            n = min(half, x1.shape[0] - i)
+            # both branches share weights and eval-mode BN: run them as one 2n-clip batch
+            xb = np.concatenate([x1[i:i + n, :, 0], x2[i:i + n, :, 0]], axis=0).astype(np.float32, copy=False)
+            emb = eng.forward(torch.from_numpy(np.ascontiguousarray(xb)).to(eng.device))
+            prob, _, _ = pair_head_loss(emb[:n].contiguous(), emb[n:].contiguous(), w, b, self.distance_metric)
+            outs.append(prob.cpu().numpy())
+        return np.concatenate(outs, axis=0) if len(outs) != 1 else outs[0]
+
+
+# --------------------------------------------------------------------------------------------------------
+# the reference's public builders
+# --------------------------------------------------------------------------------------------------------
+def get_baseline_convolutional_encoder(filters, embedding_dimension, input_shape=None, dropout=0.05):
+    """voicemap/models.py:6-41: 4 x [Conv1D+ReLU -> BatchNorm -> SpatialDropout1D -> MaxPool] ->
+    GlobalMaxPool1D -> Dense(embedding_dimension)."""
+    return EncoderModel(filters, embedding_dimension, input_shape=input_shape, dropout=dropout)
+
+
+def build_siamese_net(encoder, input_shape, distance_metric='uniform_euclidean'):
+    """voicemap/models.py:44-81."""
+    assert distance_metric in DISTANCE_METRICS
+    if distance_metric not in ('weighted_l1', 'uniform_euclidean'):
+        raise NotImplementedError  # voicemap/models.py:70-77
+    return SiameseModel(encoder, input_shape, distance_metric)
+
+
+def load_model(filepath, custom_objects=None):
+    """Counterpart of _ModelBase.save (keras.models.load_model call site: experiments/k_way_accuracy.py:45)."""
+    with np.load(filepath) as z:
+        cfg = json.loads(bytes(z["config"]).decode())
+        weights = [z[f"w{i}"] for i in range(len(z.files) - 1)]
+    if cfg["kind"] == "encoder":
+        m = EncoderModel(cfg["filters"], cfg["embedding_dimension"], cfg["input_shape"], cfg["dropout"])
+        if cfg.get("head"):
+            m.add(Dense(cfg["head"]["units"], activation=cfg["head"]["activation"]))
+    else:
+        e = cfg["encoder"]
+        enc = EncoderModel(e["filters"], e["embedding_dimension"], e["input_shape"], e["dropout"])
+        m = SiameseModel(enc, cfg["input_shape"], cfg["distance_metric"])
+    m.set_weights(weights)
+    return m
