@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the voicemap hot path on B200 (contract: see the task brief / DESIGN.md).
+
+Metric (BASELINE.json): audio-seconds/sec embedded, 3 s clips, encoder forward (eval mode) of the baseline
+1D-CNN (filters=128, embedding 64).  Workload = BASELINE config[1]: batch 256 clips per GPU, each clip entering
+the network as 12000 samples (3 s @ 16 kHz after the reference's x4 decimation, voicemap/utils.py:29;
+--length 48000 benches raw 16 kHz input instead).  Weak scaling: every rank embeds its own 256 clips, no
+data-path collective.
+
+    python bench.py [--gpus N --steps K --warmup W]         # this repo's CUDA path
+    python bench.py --impl reference [...]                  # the reference's CPU path (oracle port), rank 0 only
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FILTERS, EMB = 128, 64
+CLIP_SECONDS = 3.0
+METRIC = "audio_seconds_per_sec_embedded_3s_clips"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--length", type=int, default=12000, help="samples per clip entering the encoder")
+    ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
+                    help="3: fp16x3 split (fp32-grade, parity mode); 1: fp16x1 (throughput mode)")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# algorithmic work per clip: FLOP = 2*L*K*Cin*Cout, bytes = 4*(L*Cin + floor(L/p)*Cout)
+# ------------------------------------------------------------------------------------------------------------
+def block_work(length, f=FILTERS):
+    blocks = []
+    l, cin = length, 1
+    for k, mult, pool in ((32, 1, 4), (3, 2, 2), (3, 3, 2), (3, 4, 2)):
+        cout = mult * f
+        lout = l // pool
+        out_elems = lout * cout if len(blocks) < 3 else cout  # block 4 is fused with the global max
+        blocks.append(dict(flop=2.0 * l * k * cin * cout, bytes=4.0 * (l * cin + out_elems)))
+        l, cin = lout, cout
+    return blocks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port: torch-CPU fp32 restatement of voicemap/models.py:6-41)
+# ------------------------------------------------------------------------------------------------------------
+def time_oracle(length, clips, budget_s, steps=None, warmup=1):
+    import torch
+    from oracle import voicemap_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_encoder_params(FILTERS, EMB, seed=0, randomize_bn=True, random_bias=True)
+    x = O.synthetic_clips(clips, length, seed=1234)
+    for _ in range(warmup):
+        O.encoder_forward(x, params, torch.float32)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        O.encoder_forward(x, params, torch.float32)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and (len(times) >= steps or time.perf_counter() - t_start > 150.0):
+            break  # bounded: at most `steps` passes and ~150 s of CPU time
+        if steps is None and (time.perf_counter() - t_start > budget_s and len(times) >= 3):
+            break
+    med = float(np.median(times))
+    return dict(value=clips * CLIP_SECONDS / med, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{clips} clips x {length} samples per pass, {len(times)} timed passes (median), "
+                       f"torch-CPU fp32 oracle, {warmup} warm-up"), med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    clips = 8  # BASELINE config[0]: batch 8, CPU reference path
+    cb, med = time_oracle(args.length, clips, budget_s=0, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=med * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=f"baseline 1D-CNN encoder fwd, filters={FILTERS}, emb={EMB}, "
+                                     f"{clips} clips/step x {args.length} samples (bounded sample of the "
+                                     f"batch-{args.batch} workload), CPU oracle port of voicemap/models.py:6-41"),
+                cpu_baseline=cb,
+                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import voicemap_oracle as O  # weights / synthetic input generators only (not timed, not compute)
+    from voicemap_b200.engine import EncoderEngine
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, length, steps, warmup = args.batch, args.length, args.steps, max(args.warmup, 3)
+    params = O.init_encoder_params(FILTERS, EMB, seed=0, randomize_bn=True, random_bias=True)
+    model = get_baseline_convolutional_encoder(FILTERS, EMB, input_shape=(length, 1))
+    model.set_named_weights(params)
+    model.precision = args.precision
+    eng = model._get_engine()
+    eng.pack()
+
+    # inputs: rotate over a set larger than L2 (126 MB) so no step finds its input cached from the previous one
+    n_sets = max(2, int(np.ceil(160e6 / (n * length * 4))))
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_sets = [(O.WHITEN_RMS * torch.randn(n, length, generator=g)).pin_memory() for _ in range(n_sets)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    out = torch.empty((n, EMB), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(warmup):
+        eng.forward(dev_sets[i % n_sets], out=out)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.forward(dev_sets[i % n_sets], out=out)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / steps
+    value = world * n * CLIP_SECONDS / (ms_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> encoder -> D2H embeddings
+    for i in range(warmup):
+        model.predict(host_sets[i % n_sets])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        emb_host = model.predict(host_sets[i % n_sets])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * n * CLIP_SECONDS * steps / e2e_s
+    assert emb_host.shape == (n, EMB) and np.isfinite(emb_host).all()
+
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline object
+    names = ["conv1", "conv3_b2", "conv3_b3", "conv3_b4", "gmax_dense"]
+    acc = {k: 0.0 for k in names}
+    prof_steps = min(steps, 20)
+    for i in range(prof_steps + 2):
+        x = dev_sets[i % n_sets]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        evs[0].record()
+        h1 = eng.block1(x); evs[1].record()
+        h2 = eng.block3(2, *h1); evs[2].record()
+        h3 = eng.block3(3, *h2); evs[3].record()
+        part = eng.block3(4, *h3, gmax=True); evs[4].record()
+        eng.gmax_dense(part); evs[5].record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            for j, k in enumerate(names):
+                acc[k] += evs[j].elapsed_time(evs[j + 1])
+    kern_ms = {k: v / prof_steps for k, v in acc.items()}
+
+    if rank == 0:
+        peaks = load_peaks()
+        work = block_work(length)
+        conv3_ms = kern_ms["conv3_b2"] + kern_ms["conv3_b3"] + kern_ms["conv3_b4"]
+        conv3_flop = sum(b["flop"] for b in work[1:]) * n
+        achieved_tf = conv3_flop / (conv3_ms * 1e-3) / 1e12
+        blocks = []
+        for b, k in zip(work, names[:4]):
+            t_ms = kern_ms[k]
+            blocks.append(dict(kernel=k, ms=round(t_ms, 4),
+                               tflops=round(b["flop"] * n / (t_ms * 1e-3) / 1e12, 1),
+                               gbs=round(b["bytes"] * n / (t_ms * 1e-3) / 1e9, 1)))
+        # network-level bound of BASELINE.md: sum_blocks max(t_HBM, t_tensor); tensor peak named explicitly
+        def bound_us(tensor_tflops):
+            return sum(max(b["bytes"] / (peaks["hbm_gbs"] * 1e9), b["flop"] / (tensor_tflops * 1e12)) for b in work) * 1e6
+        us_per_clip = ms_step * 1e3 / n
+        roofline = dict(
+            bound="tensor", kernel="conv3_kernel (blocks 2-4, 3 launches/step)",
+            achieved=round(achieved_tf, 1), peak=peaks["bf16_tflops"], unit="TFLOP/s",
+            frac=round(achieved_tf / peaks["bf16_tflops"], 4),
+            peak_source=peaks["source"] + ", burst bf16 figure",
+            note=("achieved counts ALGORITHMIC flops 2*L*K*Cin*Cout once; precision=3 issues 3 fp16 MMAs per "
+                  "algorithmic MAC (fp32-grade split), so tensor-pipe utilisation is 3x this fraction"
+                  if args.precision == 3 else "precision=1: one fp16 MMA per algorithmic MAC"),
+            mma_issue_frac=round(achieved_tf * args.precision / peaks["bf16_tflops"], 4),
+            traffic=None,
+            blocks=blocks,
+            network=dict(us_per_clip=round(us_per_clip, 3),
+                         frac_of_tf32_roofline=round(bound_us(peaks["bf16_tflops"] / 2) / us_per_clip, 4),
+                         frac_of_bf16_roofline=round(bound_us(peaks["bf16_tflops"]) / us_per_clip, 4),
+                         note="BASELINE.md section 3 bounds: sum over blocks of max(bytes/HBM, flops/peak); "
+                              "TF32 peak taken as bf16/2"))
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            cpu_baseline, _ = time_oracle(length, 8, budget_s=args.cpu_baseline_seconds)
+        line = dict(
+            metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
+            ms_per_step=round(ms_step, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="fp16x3->f32 (fp32-grade split on fp16 tensor cores)" if args.precision == 3 else "fp16 (fp32 accumulate)",
+            data="synthetic",
+            config=dict(workload=f"baseline 1D-CNN encoder fwd (eval), filters={FILTERS}, emb={EMB}, batch={n} clips/GPU, "
+                                 f"{length} samples/clip (3 s @ 16 kHz {'raw' if length == 48000 else 'after the reference x4 decimation'}), "
+                                 f"precision={args.precision}",
+                        l2=f"inputs rotate over {n_sets} batches ({n_sets * n * length * 4 / 1e6:.0f} MB > 126 MB L2); "
+                           f"activations {eng.lib.vm_encoder_workspace_bytes(n, length, FILTERS) / 1e6:.0f} MB/step",
+                        parallelism=f"dp{world} (independent clips, no collective)"),
+            clocks=clocks,
+            e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=n * length * 4,
+                     d2h_bytes_per_step=n * EMB * 4,
+                     note="model.predict(pinned host batch): H2D + 5 kernels + D2H + sync, wall clock"),
+            gpu_launches=5 * steps,
+            kernel_ms=kern_ms,
+            roofline=roofline,
+            cpu_baseline=cpu_baseline,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

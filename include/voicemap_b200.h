@@ -30,7 +30,7 @@ extern "C" {
 
 #define VM_OK 0
 #define VM_ERR_SHAPE (-1)       /* bad shape / argument */
-#define VM_ERR_UNSUPPORTED (-2) /* configuration not implemented (e.g. Cin not a multiple of 64) */
+#define VM_ERR_UNSUPPORTED (-2) /* configuration not implemented (e.g. channel count not a multiple of 8) */
 #define VM_ERR_CUDA (-3)        /* CUDA runtime / driver error, see vm_last_error_string() */
 #define VM_ERR_ARCH (-4)        /* device is not sm_100 */
 
@@ -49,7 +49,7 @@ int vm_check_device(void);
 size_t vm_conv1_wpack_bytes(int cout);          /* packed block-1 weights */
 size_t vm_conv3_wpack_bytes(int cin, int cout); /* packed block-2..4 weights */
 size_t vm_epi_bytes(int cout);                  /* per-channel epilogue constants (padded to 128 channels) */
-int vm_conv3_num_position_tiles(int L);         /* T of the gmax_partial tensor */
+int vm_conv3_num_position_tiles(int L);         /* T of the gmax_partial tensor: 2 * ceil(L / 256) */
 int vm_padded_channels(int cout);
 
 /* ---- weight preparation ---------------------------------------------------------------------------------
@@ -106,7 +106,7 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
                    void* stream);
 
 /* ---- testing / tuning knobs -------------------------------------------------------------------------------
- * key "conv3_desc_mode" (0/1), "max_ctas" (0 = all SMs).  Returns the previous value or VM_ERR_SHAPE. */
+ * key "max_ctas" (0 = all SMs; limits the persistent grid).  Returns the previous value or VM_ERR_SHAPE. */
 int vm_set_option(const char* key, int value);
 
 #ifdef __cplusplus

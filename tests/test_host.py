@@ -1,0 +1,237 @@
+"""Host-side logic that needs no GPU: builder API surface, Keras-method subset, preprocessing, batcher sampling,
+callbacks (mirrors the reference's tests/tests.py where it has tests: verification batches, n-shot tasks,
+whitening)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import voicemap_oracle as O
+from voicemap_b200 import utils
+from voicemap_b200.keras_compat import (Adam, CSVLogger, Dense, ModelCheckpoint, ReduceLROnPlateau, clone_model,
+                                        to_categorical)
+from voicemap_b200.librispeech import LibriSpeechDataset
+from voicemap_b200.models import (build_siamese_net, get_baseline_convolutional_encoder, load_model)
+
+
+# ----------------------------------------------------------------------------------------------- builders
+def test_encoder_builder_signature_and_layers():
+    enc = get_baseline_convolutional_encoder(128, 64, (12000, 1))
+    names = [l.name for l in enc.layers]
+    assert names[:4] == ["conv1d_1", "batch_normalization_1", "spatial_dropout1d_1", "max_pooling1d_1"]
+    assert names[-2:] == ["global_max_pooling1d_1", "dense_1"]
+    assert enc.layers[3].config["pool_size"] == 4 and enc.layers[7].config["pool_size"] == 2
+    assert enc.dropout == 0.05  # default of the reference signature
+    w = enc.get_weights()
+    assert [a.shape for a in w[:6]] == [(32, 1, 128), (128,), (128,), (128,), (128,), (128,)]
+    assert w[-2].shape == (512, 64) and w[-1].shape == (64,)
+    trainable = sum(a.size for i, a in enumerate(w) if i % 6 not in (4, 5) or i >= 24)
+    assert trainable == 1_023_808
+
+
+def test_classifier_add_pop_clone_roundtrip():
+    clf = get_baseline_convolutional_encoder(16, 8, (4000, 1))
+    clf.add(Dense(11, activation="softmax"))
+    assert clf.layers[-1].name == "dense_2" and len(clf.get_weights()) == 28
+    enc = clone_model(clf)
+    enc.set_weights(clf.get_weights())
+    enc.pop()
+    assert len(enc.get_weights()) == 26 and enc.layers[-1].name == "dense_1"
+    for a, b in zip(enc.get_weights(), clf.get_weights()[:26]):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        enc.set_weights(clf.get_weights())
+
+
+def test_siamese_builder_contract():
+    enc = get_baseline_convolutional_encoder(16, 8, dropout=0.0)
+    sia = build_siamese_net(enc, (4000, 1), distance_metric="uniform_euclidean")
+    assert sia.layers[2] is enc  # voicemap/utils.py:141
+    assert [l.name for l in sia.layers if l is not enc] == ["input_1", "input_2", "subtract_embeddings",
+                                                           "euclidean_distance", "dense_2"]
+    assert sia.head_weights["head_kernel"].shape == (1, 1)
+    l1 = build_siamese_net(get_baseline_convolutional_encoder(16, 8), (4000, 1), "weighted_l1")
+    assert l1.head_weights["head_kernel"].shape == (8, 1)
+    with pytest.raises(NotImplementedError):
+        build_siamese_net(enc, (4000, 1), "cosine_distance")
+    with pytest.raises(AssertionError):
+        build_siamese_net(enc, (4000, 1), "manhattan")
+
+
+def test_compile_accepts_reference_losses():
+    sia = build_siamese_net(get_baseline_convolutional_encoder(16, 8), (4000, 1))
+    sia.compile(loss="binary_crossentropy", optimizer=Adam(clipnorm=1.), metrics=["accuracy"])
+    assert sia.loss == "binary_crossentropy" and sia.optimizer.clipnorm == 1.0 and sia.optimizer.epsilon == 1e-7
+    sia.compile(loss=utils.contrastive_loss, optimizer=Adam(clipnorm=1., decay=2e-5))
+    assert sia.loss == "contrastive_loss"
+    with pytest.raises(NotImplementedError):
+        sia.compile(loss="mse", optimizer=Adam())
+
+
+def test_save_load_roundtrip(tmp_path):
+    enc = get_baseline_convolutional_encoder(16, 8, dropout=0.0)
+    sia = build_siamese_net(enc, (4000, 1))
+    path = str(tmp_path / "m.npz")
+    sia.save(path)
+    back = load_model(path)
+    for a, b in zip(sia.get_weights(), back.get_weights()):
+        np.testing.assert_array_equal(a, b)
+    assert back.layers[2].filters == 16
+
+
+def test_predict_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    enc = get_baseline_convolutional_encoder(16, 8)
+    with pytest.raises(Exception) as exc:
+        enc.predict(np.zeros((1, 4000, 1), np.float32))
+    assert "CUDA" in str(exc.value) or "cuda" in str(exc.value)
+
+
+# ----------------------------------------------------------------------------------------------- preprocessing
+def test_whiten_matches_oracle_and_reference_known_answer():
+    rng = np.random.default_rng(0)
+    clip = rng.normal(0, 0.3, 48000)
+    batch = np.stack([clip, clip])[:, :, np.newaxis]  # reference tests/tests.py:76
+    w = utils.whiten(batch)
+    np.testing.assert_allclose(w, O.whiten_literal(batch), rtol=1e-12, atol=1e-15)
+    assert abs(w[0].mean()) < 1e-9
+    rms = np.sqrt(np.power(w[0, :, 0], 2).mean())
+    assert abs(rms - 0.038021) < 0.038021 * 0.02  # the reference test allows places=5 on a zero-mean clip
+    with pytest.raises(ValueError):
+        utils.whiten(np.zeros((4, 10)))
+
+
+def test_batch_preprocessor_modes():
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4))
+    a, b = np.random.rand(2, 64, 1), np.random.rand(2, 64, 1)
+    [o1, o2], y = pre(([a, b], np.zeros((2, 1))))
+    assert o1.shape == (2, 16, 1) and o2.shape == (2, 16, 1)
+    clf = utils.BatchPreProcessor("classifier", utils.preprocess_instances(4), lambda y: y + 1)
+    x, y = clf((a, np.zeros((2, 1))))
+    assert x.shape == (2, 16, 1) and (y == 1).all()
+    with pytest.raises(AssertionError):
+        utils.BatchPreProcessor("other", None)
+
+
+def test_contrastive_loss_numpy_matches_oracle():
+    y = np.array([[0.], [1.], [1.]])
+    p = np.array([[0.3], [0.2], [1.4]])
+    assert np.isclose(utils.contrastive_loss(y, p), O.contrastive_loss(y, p))
+
+
+def test_to_categorical():
+    out = to_categorical(np.array([[0], [2], [1]]), 4)
+    assert out.shape == (3, 4) and out[1, 2] == 1 and out.sum() == 3
+
+
+# ----------------------------------------------------------------------------------------------- batcher
+def _fake_dataset(seconds=1, n_speakers=8, files_per_speaker=5, pad=False, stochastic=True):
+    rng = np.random.default_rng(0)
+    rows, audio = [], {}
+    for spk in range(n_speakers):
+        for j in range(files_per_speaker):
+            path = f"/fake/{spk}/{j}.flac"
+            length = int(16000 * (1.2 + rng.random()))
+            audio[path] = rng.normal(0, 0.1, length) + spk  # speaker id recoverable from the mean
+            rows.append(dict(id=100 + spk, sex="M" if spk % 2 else "F", subset="dev-clean", minutes=10.0,
+                             name=f"s{spk}", filepath=path, length=length, seconds=length / 16000.0))
+    reader = lambda p: (audio[p], 16000)  # noqa: E731
+    return LibriSpeechDataset("dev-clean", seconds, stochastic=stochastic, pad=pad, index=pd.DataFrame(rows),
+                              reader=reader)
+
+
+def test_verification_batch_like_reference_test():
+    # reference tests/tests.py:16-29: alike pairs share a speaker, differing pairs do not; labels 0 then 1
+    ds = _fake_dataset()
+    [i1, i2], y = ds.build_verification_batch(8)
+    assert i1.shape == (8, 16000, 1) and i2.shape == (8, 16000, 1) and y.shape == (8, 1)
+    np.testing.assert_array_equal(y[:, 0], [0, 0, 0, 0, 1, 1, 1, 1])
+    spk1, spk2 = np.round(i1.mean(axis=(1, 2))), np.round(i2.mean(axis=(1, 2)))
+    assert (spk1[:4] == spk2[:4]).all() and (spk1[4:] != spk2[4:]).all()
+
+
+def test_n_shot_task_like_reference_test():
+    # reference tests/tests.py:31-68
+    ds = _fake_dataset()
+    for k, n in ((5, 1), (3, 2)):
+        (q, q_label), (support, labels) = ds.build_n_shot_task(k, n)
+        assert support.shape == (k * n, 16000) and len(labels) == k * n
+        assert (labels[:n] == q_label).all()              # the first n support samples are the query speaker
+        assert len(np.unique(labels)) == k                 # k unique speakers
+        for c in range(k):
+            assert len(np.unique(labels[c * n:(c + 1) * n])) == 1   # ordered [c1]*n + [c2]*n + ...
+    with pytest.raises(ValueError):
+        ds.build_n_shot_task(8)
+    with pytest.raises(ValueError):
+        ds.build_n_shot_task(1)
+
+
+def test_getitem_padding_and_labels():
+    ds = _fake_dataset(seconds=3, pad=True, stochastic=False)
+    x, label = ds[0]
+    assert x.shape == (48000,) and label == 100
+    assert (x[int(16000 * 2.3):] == 0).all()  # deterministic padding appends zeros
+    sex = LibriSpeechDataset("dev-clean", 1, label="sex", index=_fake_dataset().df.rename(
+        columns={"speaker_id": "id", "speaker_minutes": "minutes"}).drop(columns=["id"], errors="ignore").assign(
+        id=lambda d: d.index), reader=lambda p: (np.zeros(20000), 16000))
+    assert sex[0][1] in (True, False)
+    assert ds.num_classes() == 8 and len(ds) == 40
+
+
+# ----------------------------------------------------------------------------------------------- n-shot eval + callbacks
+class _StubEncoder:
+    """Embeds a clip as (mean, 0): speakers are separable, so every task must be solved."""
+    def predict(self, x):
+        m = x.mean(axis=(1, 2))
+        return np.stack([m, np.zeros_like(m)], axis=1) * 1000.0
+
+
+class _StubSiamese:
+    layers = [None, None, _StubEncoder()]
+
+    def predict(self, x):
+        a, b = _StubEncoder().predict(x[0]), _StubEncoder().predict(x[1])
+        return np.linalg.norm(a - b, axis=1, keepdims=True)
+
+
+def test_n_shot_task_evaluation_paths():
+    ds = _fake_dataset()
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4, whitening=False))
+    assert utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, num_tasks=6, n=1, k=4) == 6
+    for dist in ("euclidean", "cosine", "dot_product"):
+        got = utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, num_tasks=4, n=2, k=3, distance=dist)
+        assert 0 <= got <= 4
+    assert utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 4, n=2, k=3, distance="euclidean") == 4
+
+
+def test_nshot_callback_writes_logs_and_checkpoint_uses_them(tmp_path):
+    ds = _fake_dataset()
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4, whitening=False))
+    cb = utils.NShotEvaluationCallback(4, 1, 3, ds, preprocessor=pre)
+    cb.set_model(_StubSiamese())
+    logs = {"loss": 1.0}
+    cb.on_epoch_end(0, logs)
+    assert logs["val_1-shot_acc"] == 1.0
+
+    saved = []
+
+    class M:
+        optimizer = Adam(lr=0.5)
+        def save(self, path):
+            saved.append(path)
+    ck = ModelCheckpoint(str(tmp_path / "m.npz"), monitor="val_1-shot_acc", mode="max", save_best_only=True)
+    ck.set_model(M())
+    ck.on_epoch_end(0, logs)
+    ck.on_epoch_end(1, {"val_1-shot_acc": 0.5})
+    assert len(saved) == 1
+    rl = ReduceLROnPlateau(monitor="val_1-shot_acc", mode="max", patience=2)
+    rl.set_model(M())
+    for e in range(4):
+        rl.on_epoch_end(e, {"val_1-shot_acc": 0.1})
+    assert np.isclose(M.optimizer.lr, 0.05)
+    log = CSVLogger(str(tmp_path / "log.csv"))
+    log.on_train_begin()
+    log.on_epoch_end(0, {"loss": 1.0, "val_1-shot_acc": 0.5})
+    log.on_train_end()
+    assert "val_1-shot_acc" in open(tmp_path / "log.csv").read()

@@ -41,7 +41,6 @@ def main():
     args = ap.parse_args()
 
     lib = _lib.load()
-    lib.vm_set_option(b"conv3_desc_mode", args.desc_mode)
     params = O.init_encoder_params(args.filters, args.emb, seed=0, randomize_bn=bool(args.randbn),
                                    random_bias=True)
     eng = EncoderEngine(args.filters, args.emb, precision=args.precision)

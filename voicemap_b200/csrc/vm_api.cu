@@ -8,7 +8,6 @@
 namespace vm {
 
 static thread_local char g_err[512] = "no error";
-static int g_conv3_desc_mode = 0;
 static int g_max_ctas = 0;
 
 int set_error(int code, const char* msg) {
@@ -84,7 +83,7 @@ struct EncoderPlan {
 static EncoderPlan plan_encoder(int N, int L, int filters) {
   EncoderPlan pl{};
   pl.l1 = L / 4; pl.l2 = pl.l1 / 2; pl.l3 = pl.l2 / 2;
-  pl.t4 = (pl.l3 + 255) / 256;
+  pl.t4 = 2 * ((pl.l3 + 255) / 256);  // two partial rows (column halves) per 256-position tile
   pl.c4_pad = (4 * filters + 127) / 128 * 128;
   pl.a1 = align_up(size_t(N) * pl.l1 * filters * 2, 1024);
   pl.a2 = align_up(size_t(N) * pl.l2 * 2 * filters * 2, 1024);
@@ -118,12 +117,11 @@ int vm_padded_channels(int cout) { return (cout + 127) / 128 * 128; }
 size_t vm_conv1_wpack_bytes(int cout) { return size_t(vm_padded_channels(cout)) / 128 * 16384; }
 size_t vm_conv3_wpack_bytes(int cin, int cout) { return size_t(2) * 3 * vm_padded_channels(cout) * cin * 2; }
 size_t vm_epi_bytes(int cout) { return size_t(vm_padded_channels(cout)) * 16; }
-int vm_conv3_num_position_tiles(int L) { return (L + 255) / 256; }
+int vm_conv3_num_position_tiles(int L) { return 2 * ((L + 255) / 256); }
 
 int vm_set_option(const char* key, int value) {
   if (key == nullptr) return set_error(VM_ERR_SHAPE, "vm_set_option: null key");
   int* slot = nullptr;
-  if (strcmp(key, "conv3_desc_mode") == 0) slot = &g_conv3_desc_mode;
   if (strcmp(key, "max_ctas") == 0) slot = &g_max_ctas;
   if (slot == nullptr) return set_error(VM_ERR_SHAPE, "vm_set_option: unknown key");
   int old = *slot;
@@ -157,7 +155,7 @@ int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int
     return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 3");
   return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
                       static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), gmax_partial, precision, g_conv3_desc_mode, g_max_ctas,
+                      reinterpret_cast<__half*>(out_lo), gmax_partial, precision, g_max_ctas,
                       (cudaStream_t)stream);
 }
 
@@ -216,13 +214,13 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
   int rc;
   if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, precision, g_max_ctas, st))) return rc;
   if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
-                         nullptr, precision, g_conv3_desc_mode, g_max_ctas, st)))
+                         nullptr, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a2h, a2l, N, pl.l2, 2 * f, 3 * f, static_cast<const __half*>(wpack[2]), epi[2], a3h, a3l,
-                         nullptr, precision, g_conv3_desc_mode, g_max_ctas, st)))
+                         nullptr, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a3h, a3l, N, pl.l3, 3 * f, 4 * f, static_cast<const __half*>(wpack[3]), epi[3], nullptr,
-                         nullptr, part, precision, g_conv3_desc_mode, g_max_ctas, st)))
+                         nullptr, part, precision, g_max_ctas, st)))
     return rc;
   return launch_gmax_dense(part, N, pl.t4, 4 * f, pl.c4_pad, epi[3], dense_w, dense_b, E, nullptr, emb, st);
 }

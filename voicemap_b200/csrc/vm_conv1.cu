@@ -24,19 +24,22 @@ constexpr int kTileM = 128;
 constexpr int kGroupStride = 528;                        // 8-row group: 4 k-chunks x 128 B + 16 B pad
 constexpr int kPlaneBytes = (kTileN / 8) * kGroupStride;  // 16896
 constexpr int kStageBytes = 2 * kPlaneBytes;             // hi + lo
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
+constexpr int kOutBoxBytes = 64 * 128;                   // TMA store box: 64 pooled positions x 64 channels fp16
+constexpr int kOutBufBytes = 4 * kOutBoxBytes;           // [plane][channel half][pos][64 ch] = 32 KB
 constexpr int kWPlaneBytes = kTileM * 64;                // 128 cout x 32 taps fp16 = 8192
 constexpr int kWSlabBytes = 2 * kWPlaneBytes;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 288;                            // warps 0-3 epilogue, 4 MMA, 5-8 producers
+constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quarter (column halves)
+constexpr int kThreads = (kEpiWarps + 1 + 4) * 32;       // warps 0-7 epilogue, 8 MMA, 9-12 producers
 constexpr int kMaxSlabs = 4;
-__host__ __device__ constexpr int smem_bytes(int nslab) {
-  return nslab * kWSlabBytes + kStages * kStageBytes + 1024 + 256;
+__host__ __device__ constexpr int smem_bytes(int nslab, int nstages) {
+  return nslab * kWSlabBytes + nstages * kStageBytes + 2 * kOutBufBytes + 1024 + 256;
 }
 }  // namespace c1
 
 struct __align__(8) Conv1Barriers {
-  uint64_t full[c1::kStages], empty[c1::kStages];
+  uint64_t full[c1::kMaxStages], empty[c1::kMaxStages];
   uint64_t tfull[2], tempty[2];
   uint32_t tmem_base;
 };
@@ -45,13 +48,17 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
 }
 
-__global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Params p) {
+__global__ void __launch_bounds__(c1::kThreads, 1)
+conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol,
+             const Conv1Params p) {
   using namespace c1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;
   uint8_t* stages = smem + p.nslab * kWSlabBytes;
-  Conv1Barriers* bars = reinterpret_cast<Conv1Barriers*>(stages + kStages * kStageBytes);
+  const int kStages = p.nstages;
+  uint8_t* outbuf = stages + kStages * kStageBytes;
+  Conv1Barriers* bars = reinterpret_cast<Conv1Barriers*>(outbuf + 2 * kOutBufBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -59,29 +66,33 @@ __global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Param
   const int nplanes = (p.products == 3) ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 128); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
     fence_mbar_init();
   }
   // packed weights -> shared memory (already in the UMMA smem image layout)
   {
     const uint4* src = p.wpack;
-    uint4* dst = reinterpret_cast<uint4*>(wsm);
+    const uint32_t dst = smem_u32(wsm);
     const int n16 = p.nslab * kWSlabBytes / 16;
-    for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n16; i += kThreads) {
+      const uint4 w = __ldg(src + i);
+      sts_v4(dst + i * 16, w.x, w.y, w.z, w.w);
+    }
     fence_proxy_async_smem();
   }
-  if (warp == 4) tmem_alloc(&bars->tmem_base, kTmemCols);
+  if (warp == kEpiWarps) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp >= 5) {
+  if (warp > kEpiWarps) {
     // ===================== Toeplitz producers: warp q fills stage q for local tiles q, q+4, ... =============
-    const int q = warp - 5;
+    const int q = warp - kEpiWarps - 1;
     uint32_t i = q;
-    for (int tile = blockIdx.x + q * gridDim.x; tile < ntiles; tile += kStages * gridDim.x, i += kStages) {
+    for (int tile = blockIdx.x + q * gridDim.x; q < kStages && tile < ntiles;
+         tile += kStages * gridDim.x, i += kStages) {
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
       const float* xc = p.x + size_t(n) * p.L;
@@ -98,7 +109,7 @@ __global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Param
       for (int k = 0; k < 39; ++k) split_f32(xv[k], hh[k], hl[k]);
 
       mbar_wait(&bars->empty[q], (((i / kStages) & 1) ^ 1));
-      uint8_t* st = stages + q * kStageBytes + lane * kGroupStride;
+      const uint32_t st = smem_u32(stages + q * kStageBytes + lane * kGroupStride);
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
         if (pl < nplanes) {
@@ -109,18 +120,15 @@ __global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Param
             pe[k] = pack_h2(h[2 * k], h[2 * k + 1]);
             po[k] = pack_h2(h[2 * k + 1], h[2 * k + 2]);
           }
-          uint8_t* base = st + pl * kPlaneBytes;
+          const uint32_t base = st + pl * kPlaneBytes;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int o = r + 8 * j;  // first element of this 8-tap chunk
-              uint4 w;
-              w.x = (o & 1) ? po[(o - 1) / 2 + 0] : pe[o / 2 + 0];
-              w.y = (o & 1) ? po[(o - 1) / 2 + 1] : pe[o / 2 + 1];
-              w.z = (o & 1) ? po[(o - 1) / 2 + 2] : pe[o / 2 + 2];
-              w.w = (o & 1) ? po[(o - 1) / 2 + 3] : pe[o / 2 + 3];
-              *reinterpret_cast<uint4*>(base + j * 128 + r * 16) = w;
+              sts_v4(base + j * 128 + r * 16, (o & 1) ? po[(o - 1) / 2 + 0] : pe[o / 2 + 0],
+                     (o & 1) ? po[(o - 1) / 2 + 1] : pe[o / 2 + 1], (o & 1) ? po[(o - 1) / 2 + 2] : pe[o / 2 + 2],
+                     (o & 1) ? po[(o - 1) / 2 + 3] : pe[o / 2 + 3]);
             }
           }
         }
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Param
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[q]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kEpiWarps) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTileM, kTileN);
@@ -167,50 +175,70 @@ __global__ void __launch_bounds__(c1::kThreads, 1) conv1_kernel(const Conv1Param
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3): thread = cout channel =====================
-    const int q = warp;
+    // ===================== epilogue (warps 0-7): thread = cout channel, warp pair splits the columns ==========
+    // Pooled outputs are staged in shared memory ([plane][channel half][64 positions][64 channels], double
+    // buffered) and written with TMA bulk tensor stores (positions / channels out of range are clipped).
+    const int q = warp & 3;          // TMEM lane quarter
+    const int chalf = warp >> 2;     // which half of the 256 position columns
+    const bool leader = (threadIdx.x == 0);
+    const int ch = q * 32 + lane;
     uint32_t ait = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
       for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
         const int buf = ait & 1;
-        const int co = slab * kTileM + q * 32 + lane;
+        const int co = slab * kTileM + ch;
         const float4 ep = p.epi[co];
-        const bool co_ok = co < p.cout;
-        __half* oh = p.out_hi + (size_t(n) * p.lout) * p.cout + co;
-        __half* ol = p.out_lo + (size_t(n) * p.lout) * p.cout + co;
+        uint8_t* ob = outbuf + buf * kOutBufBytes;
+        const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
+        const uint32_t st_l = st_h + 2 * kOutBoxBytes;
+        if (leader) tma_store_wait_read<1>();  // the stores issued from this buffer two tiles ago have been read
+        named_bar_sync(1, kEpiWarps * 32);
         mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
 #pragma unroll 1
-        for (int g = 0; g < kTileN / 32; ++g) {
+        for (int gg = 0; gg < kTileN / 64; ++gg) {
+          const int g = chalf * (kTileN / 64) + gg;
           float v[32];
           tmem_ld_32x32(taddr + g * 32, v);
-          if (g == kTileN / 32 - 1) {
+          if (gg == kTileN / 64 - 1) {
             tc_fence_before_sync();
             mbar_arrive(&bars->tempty[buf]);
           }
-          const int j0 = (p0 + g * 32) >> 2;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float mx = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+            const float mx = max3(fmaxf(v[4 * j], v[4 * j + 1]), v[4 * j + 2], v[4 * j + 3]);
             const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
-            if (co_ok && (j0 + j) < p.lout) {
-              __half h, l;
-              split_f32(y, h, l);
-              oh[size_t(j0 + j) * p.cout] = h;
-              if (p.out_lo != nullptr) ol[size_t(j0 + j) * p.cout] = l;
+            __half h, l;
+            split_f32(y, h, l);
+            sts_u16(st_h + (g * 8 + j) * 128, h);
+            if (nplanes == 2) sts_u16(st_l + (g * 8 + j) * 128, l);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiWarps * 32);
+        if (leader) {
+          const int pos = p0 >> 2;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c0 = slab * kTileM + half * 64;
+            if (c0 < p.cout) {
+              tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+              if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
             }
           }
+          tma_store_commit();
         }
       }
     }
+    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -233,13 +261,25 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   p.wpack = reinterpret_cast<const uint4*>(wpack);
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo;
-  const int smem = smem_bytes(nslab);
+  p.nstages = (nslab == 1) ? 4 : (nslab <= 3 ? 3 : 2);
+  if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products=3");
+  CUtensorMap oh, ol;
+  {
+    const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
+    const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};
+    const uint32_t obox[3] = {64, 64, 1};
+    int rc;
+    if ((rc = make_tensor_map(&oh, out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE))) return rc;
+    if ((rc = make_tensor_map(&ol, products == 3 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
+      return rc;
+  }
+  const int smem = smem_bytes(nslab, p.nstages);
   cudaError_t e = cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return set_cuda_error(e, "conv1: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > ntiles) grid = ntiles;
-  conv1_kernel<<<grid, kThreads, smem, stream>>>(p);
+  conv1_kernel<<<grid, kThreads, smem, stream>>>(oh, ol, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv1: launch");
   return VM_OK;

@@ -31,10 +31,15 @@ constexpr int kXHaloBytes = 8 * 128;               // 1024  (rows 256..263)
 constexpr int kXSlotBytes = 2 * kXPlaneBytes;      // hi + lo
 constexpr int kXStages = 2;
 constexpr int kWTileBytes = kTileM * 128;          // 16384
-constexpr int kWStages = 5;
+constexpr int kWStages = 4;
+constexpr int kStagePos = 32;                       // pooled positions per output granule
+constexpr int kStageBoxBytes = kStagePos * 128;     // one TMA store box: 32 positions x 64 channels fp16
+constexpr int kStageBytes = 4 * kStageBoxBytes;     // [plane][channel half][pos][64 ch]
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 256;
-constexpr int kSmemBytes = kXStages * kXSlotBytes + kWStages * kWTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quarter
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int kSmemBytes =
+    kXStages * kXSlotBytes + kWStages * kWTileBytes + kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 }  // namespace c3
 
 struct __align__(8) Conv3Barriers {
@@ -48,13 +53,15 @@ __global__ void __launch_bounds__(c3::kThreads, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
              const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+             const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol,
              const Conv3Params p) {
   using namespace c3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;
   uint8_t* wring = smem + kXStages * kXSlotBytes;
-  Conv3Barriers* bars = reinterpret_cast<Conv3Barriers*>(wring + kWStages * kWTileBytes);
+  uint8_t* stage = wring + kWStages * kWTileBytes;
+  Conv3Barriers* bars = reinterpret_cast<Conv3Barriers*>(stage + kStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,7 +71,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(&bars->wfull[i], 1); mbar_init(&bars->wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -135,7 +142,6 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
           const uint32_t xh = smem_u32(xring + xs * kXSlotBytes);
           const uint32_t xl = xh + kXPlaneBytes;
           for (int tap = 0; tap < 3; ++tap) {
-            const uint32_t bo = (p.desc_mode == 1) ? uint32_t(tap) : 0u;
             const uint32_t bh = xh + tap * 128, bl = xl + tap * 128;
             {  // W hi: Xh*Wh (+ Xl*Wh)
               const int ws = wit % kWStages;
@@ -145,14 +151,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128, bo), idesc, acc);
+                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, acc);
                 acc = 1;
               }
               if (wplanes == 2) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                           make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128, bo), idesc, 1);
+                           make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
               }
               umma_commit(&bars->wempty[ws]);
               ++wit;
@@ -165,7 +171,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128, bo), idesc, 1);
+                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
               umma_commit(&bars->wempty[ws]);
               ++wit;
             }
@@ -177,7 +183,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: thread = cout channel, columns = positions =====================
-    const int q = warp & 3;  // TMEM lane quarter
+    const int q = warp & 3;             // TMEM lane quarter
+    const int chalf = (warp - 4) >> 2;  // which 32-column half of every 64-column group
     uint32_t tit = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
       const int slab = tile % p.nslab;
@@ -196,7 +203,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       if (p.gmax_partial != nullptr) {
         float m = -INFINITY;
 #pragma unroll 1
-        for (int g = 0; g < kTileN / 32; ++g) {
+        for (int gg = 0; gg < kTileN / 64; ++gg) {
+          const int g = 2 * gg + chalf;
           float v[32];
           tmem_ld_32x32(taddr + g * 32, v);
           const int pos = p0 + g * 32;
@@ -211,33 +219,57 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         }
         tc_fence_before_sync();
         mbar_arrive(&bars->tempty[buf]);
-        p.gmax_partial[(size_t(n) * p.nptile + pt) * p.cout_pad + co] = m;
+        // the two column halves keep separate partial rows: (N, 2*nptile, cout_pad)
+        p.gmax_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = m;
       } else {
-        __half* oh = p.out_hi + (size_t(n) * p.lout) * p.cout + co;
-        __half* ol = p.out_lo + (size_t(n) * p.lout) * p.cout + co;
+        // pooled outputs go through a shared-memory staging granule (32 positions x 128 channels x 2 planes)
+        // and leave with TMA bulk tensor stores; out-of-range positions / channels are clipped by the TMA unit.
+        const bool leader = (threadIdx.x == 4 * 32);
+        const int ch = q * 32 + lane;
+        const uint32_t st_h = smem_u32(stage) + (ch >> 6) * kStageBoxBytes + (ch & 63) * 2;
+        const uint32_t st_l = st_h + 2 * kStageBoxBytes;
 #pragma unroll 1
-        for (int g = 0; g < kTileN / 32; ++g) {
-          float v[32];
-          tmem_ld_32x32(taddr + g * 32, v);
-          if (g == kTileN / 32 - 1) {  // all TMEM reads of this buffer are done
-            tc_fence_before_sync();
-            mbar_arrive(&bars->tempty[buf]);
-          }
-          const int j0 = (p0 + g * 32) >> 1;
+        for (int gr = 0; gr < kTileN / 64; ++gr) {
+          if (leader) tma_store_wait_read<0>();  // previous granule has been read out of the staging buffer
+          named_bar_sync(1, kEpiWarps * 32);
+          {
+            const int sub = chalf;
+            float v[32];
+            tmem_ld_32x32(taddr + gr * 64 + sub * 32, v);
+            if (gr == kTileN / 64 - 1) {  // all TMEM reads of this buffer are done
+              tc_fence_before_sync();
+              mbar_arrive(&bars->tempty[buf]);
+            }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float mx = fmaxf(v[2 * j], v[2 * j + 1]);
-            const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
-            if (co_ok && (j0 + j) < p.lout) {
+            for (int j = 0; j < 16; ++j) {
+              const float mx = fmaxf(v[2 * j], v[2 * j + 1]);
+              const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
               __half h, l;
               split_f32(y, h, l);
-              oh[size_t(j0 + j) * p.cout] = h;
-              if (p.out_lo != nullptr) ol[size_t(j0 + j) * p.cout] = l;
+              sts_u16(st_h + (sub * 16 + j) * 128, h);
+              if (wplanes == 2) sts_u16(st_l + (sub * 16 + j) * 128, l);
             }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiWarps * 32);
+          if (leader) {
+            const int pos = (p0 >> 1) + gr * kStagePos;
+            if (pos < p.lout) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int c0 = slab * kTileM + half * 64;
+                if (c0 < p.cout) {
+                  tma_store_3d(&tm_oh, stage + half * kStageBoxBytes, c0, pos, n);
+                  if (wplanes == 2) tma_store_3d(&tm_ol, stage + (2 + half) * kStageBoxBytes, c0, pos, n);
+                }
+              }
+            }
+            tma_store_commit();
           }
         }
       }
     }
+    if (threadIdx.x == 4 * 32) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
@@ -252,11 +284,12 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 // host launcher
 // ---------------------------------------------------------------------------------------------
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
-                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int desc_mode,
-                 int max_ctas, cudaStream_t stream) {
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int max_ctas,
+                 cudaStream_t stream) {
   using namespace c3;
   if (N <= 0 || L <= 0) return set_error(VM_ERR_SHAPE, "conv3: N and L must be positive");
-  if (cin % kKC != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 64");
+  // K chunks are 64 channels wide; a ragged last chunk is zero-filled by TMA in both operands
+  if (cin % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 8");
   if (cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cout must be a multiple of 8");
   if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1 or 3");
   if (gmax_partial == nullptr && out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv3: no output given");
@@ -268,9 +301,8 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   p.lout = L / 2;
   p.nptile = (L + kTileN - 1) / kTileN;
   p.nslab = cout_pad / kTileM;
-  p.nchunk = cin / kKC;
+  p.nchunk = (cin + kKC - 1) / kKC;
   p.products = products;
-  p.desc_mode = desc_mode;
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo; p.gmax_partial = gmax_partial;
 
@@ -295,17 +327,27 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   if ((rc = make_tensor_map(&wh, w_hi, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&wl, w_lo, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
-    attr_set = true;
+  // pooled output planes (N, lout, cout) fp16 -- TMA store boxes of 64 channels x 32 positions
+  CUtensorMap oh, ol;
+  if (gmax_partial == nullptr) {
+    if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: out_lo required for products=3");
+    const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
+    const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};
+    const uint32_t obox[3] = {64, kStagePos, 1};
+    if ((rc = make_tensor_map(&oh, out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE))) return rc;
+    if ((rc = make_tensor_map(&ol, products == 3 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
+      return rc;
+  } else {
+    oh = wh;  // unused by the kernel in gmax mode
+    ol = wh;
   }
+  cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile * p.nslab;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > ntiles) grid = ntiles;
-  conv3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, p);
-  cudaError_t e = cudaGetLastError();
+  conv3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: launch");
   return VM_OK;
 }

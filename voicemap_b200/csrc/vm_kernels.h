@@ -28,6 +28,7 @@ struct Conv1Params {
   int lout;              // L / 4
   int nptile;            // ceil(L / 256)
   int products;          // 3: fp16x3 (fp32-grade), 1: fp16x1
+  int nstages;           // Toeplitz ring depth (2..4, limited by shared memory when Cout > 128)
   const uint4* wpack;    // [slab][plane][8 KB smem image]
   const float4* epi;     // [cout_pad] {sigma, bias, s, t}
   __half* out_hi;        // (N, lout, cout)
@@ -42,17 +43,16 @@ struct Conv3Params {
   int lout;              // L / 2
   int nptile;            // ceil(L / 256)
   int nslab;             // cout_pad / 128
-  int nchunk;            // cin / 64
+  int nchunk;            // ceil(cin / 64)
   int products;
-  int desc_mode;         // 0: tap shift via start address only; 1: also set the descriptor base_offset
   const float4* epi;     // [cout_pad]
   __half* out_hi;        // (N, lout, cout) or null
   __half* out_lo;
   float* gmax_partial;   // (N, nptile, cout_pad) raw accumulator maxima, or null
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
-                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int desc_mode,
-                 int max_ctas, cudaStream_t stream);
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int max_ctas,
+                 cudaStream_t stream);
 
 // ---- small kernels (vm_head.cu) ----
 int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,

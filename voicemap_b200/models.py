@@ -213,34 +213,49 @@ class EncoderModel(_ModelBase):
             self._engine_dirty = False
         return self._engine
 
-    def _check_input(self, x):
-        x = np.asarray(x)
-        if x.ndim != 3 or x.shape[2] != 1:
-            raise ValueError(f"Error when checking input: expected input to have shape (N, L, 1) but got array "
-                             f"with shape {x.shape}")
-        if self.input_shape is not None and tuple(x.shape[1:]) != tuple(self.input_shape):
-            raise ValueError(f"Error when checking input: expected conv1d_1_input to have shape "
-                             f"{self.input_shape} but got array with shape {x.shape[1:]}")
-        return x
-
     def embed_device(self, x_dev):
         """x_dev: CUDA fp32 (N, L[, 1]) -> CUDA (N, embedding_dimension)."""
         return self._get_engine().forward(x_dev)
 
-    def predict(self, x, batch_size=32, verbose=0):
-        """model.predict(x): eval-mode forward (moving BN statistics, no dropout).  x: numpy (N, L, 1), any float
-        dtype (cast to float32 like Keras' floatx).  Returns numpy float32."""
+    def _host_batch(self, x):
+        """numpy (N, L, 1) of any float dtype, or a torch CPU tensor (N, L[, 1]) (pinned memory makes the
+        host->device copy asynchronous) -> contiguous float32 torch CPU tensor (N, L)."""
         import torch
-        x = self._check_input(x)
+        if isinstance(x, torch.Tensor):
+            if x.is_cuda:
+                raise ValueError("predict() takes host data; use embed_device() for CUDA tensors")
+            if x.dim() == 2:
+                x = x.unsqueeze(-1)
+            shape = tuple(x.shape)
+        else:
+            x = np.asarray(x)
+            shape = x.shape
+        if len(shape) != 3 or shape[2] != 1:
+            raise ValueError(f"Error when checking input: expected input to have shape (N, L, 1) but got array "
+                             f"with shape {shape}")
+        if self.input_shape is not None and tuple(shape[1:]) != tuple(self.input_shape):
+            raise ValueError(f"Error when checking input: expected conv1d_1_input to have shape "
+                             f"{self.input_shape} but got array with shape {shape[1:]}")
+        if isinstance(x, torch.Tensor):
+            xt = x.reshape(shape[0], shape[1])
+            return xt if (xt.dtype == torch.float32 and xt.is_contiguous()) else xt.float().contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x[:, :, 0], dtype=np.float32))
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """model.predict(x): eval-mode forward (moving BN statistics, no dropout).  x: numpy (N, L, 1) of any float
+        dtype (cast to float32 like Keras' floatx) or a torch CPU tensor.  Returns numpy float32.  ``batch_size``
+        is accepted for compatibility; results do not depend on it."""
+        import torch
+        xt = self._host_batch(x)
         eng = self._get_engine()
         outs = []
-        for i in range(0, x.shape[0], _PREDICT_CHUNK):
-            xb = torch.from_numpy(np.ascontiguousarray(x[i:i + _PREDICT_CHUNK, :, 0], dtype=np.float32))
-            emb = eng.forward(xb.to(eng.device, non_blocking=False))
+        for i in range(0, xt.shape[0], _PREDICT_CHUNK):
+            emb = eng.forward(xt[i:i + _PREDICT_CHUNK].to(eng.device, non_blocking=True))
             if self._head is not None:
                 emb = self._apply_head(emb)
-            outs.append(emb.cpu().numpy())
-        return np.concatenate(outs, axis=0) if len(outs) != 1 else outs[0]
+            outs.append(emb)
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        return out.cpu().numpy()
 
     def _apply_head(self, emb):
         # classifier head Dense(num_classes, softmax): adjacent to the hot path (SURVEY.md 8(a) a12), device-side
@@ -323,13 +338,13 @@ class SiameseModel(_ModelBase):
         from .engine import pair_head_loss
         if not isinstance(x, (list, tuple)) or len(x) != 2:
             raise ValueError("Error when checking model input: the siamese network expects a list of 2 arrays")
-        x1 = self.encoder._check_input(x[0])
-        x2 = self.encoder._check_input(x[1])
+        x1 = self.encoder._host_batch(x[0])
+        x2 = self.encoder._host_batch(x[1])
         if x1.shape != x2.shape:
-            raise ValueError(f"siamese inputs must have the same shape, got {x1.shape} and {x2.shape}")
-        if tuple(x1.shape[1:]) != self.input_shape:
+            raise ValueError(f"siamese inputs must have the same shape, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+        if (x1.shape[1], 1) != self.input_shape:
             raise ValueError(f"Error when checking input: expected input_1 to have shape {self.input_shape} but got "
-                             f"array with shape {x1.shape[1:]}")
+                             f"array with shape {(x1.shape[1], 1)}")
         eng = self.encoder._get_engine()
         w, b = self._head_device(eng.device)
         outs = []
@@ -337,11 +352,14 @@ class SiameseModel(_ModelBase):
         for i in range(0, x1.shape[0], half):
             n = min(half, x1.shape[0] - i)
             # both branches share weights and eval-mode BN: run them as one 2n-clip batch
-            xb = np.concatenate([x1[i:i + n, :, 0], x2[i:i + n, :, 0]], axis=0).astype(np.float32, copy=False)
-            emb = eng.forward(torch.from_numpy(np.ascontiguousarray(xb)).to(eng.device))
-            prob, _, _ = pair_head_loss(emb[:n].contiguous(), emb[n:].contiguous(), w, b, self.distance_metric)
-            outs.append(prob.cpu().numpy())
-        return np.concatenate(outs, axis=0) if len(outs) != 1 else outs[0]
+            xb = torch.empty((2 * n, x1.shape[1]), dtype=torch.float32, device=eng.device)
+            xb[:n].copy_(x1[i:i + n], non_blocking=True)
+            xb[n:].copy_(x2[i:i + n], non_blocking=True)
+            emb = eng.forward(xb)
+            prob, _, _ = pair_head_loss(emb[:n], emb[n:], w, b, self.distance_metric)
+            outs.append(prob)
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        return out.cpu().numpy()
 
 
 # --------------------------------------------------------------------------------------------------------
