@@ -82,23 +82,27 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []      # (arrival time, csv line)
         self.proc = None
         self.index = index
+        self.window = None  # (t0, t1) perf_counter bounds of the timed region
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 3.0:  # wait for the first sample (tool start-up)
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -110,7 +114,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if self.window is not None:
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1]]
+            # a very short timed region can fall between two samples: then take the nearest ones around it
+            rows = inside if inside else sorted(rows, key=lambda r: abs(r[0] - self.window[1]))[:2]
+        for _, r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -213,19 +222,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value")
-    for i in range(warmup):
-        eng.forward(dev_sets[i % n_sets], out=out)
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for i in range(warmup):
+        eng.forward(dev_sets[i % n_sets], out=out)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.perf_counter()
     e0.record()
     for i in range(steps):
         eng.forward(dev_sets[i % n_sets], out=out)
     e1.record()
     barrier()
+    t_w1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    if sampler:
+        sampler.window = (t_w0, t_w1)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -252,8 +265,9 @@ def run_b200(args):
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline object
     names = ["conv1", "conv3_b2", "conv3_b3", "conv3_b4", "gmax_dense"]
-    acc = {k: 0.0 for k in names}
     prof_steps = min(steps, 20)
+    all_evs = []
+    torch.cuda.synchronize()
     for i in range(prof_steps + 2):
         x = dev_sets[i % n_sets]
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
@@ -263,10 +277,12 @@ def run_b200(args):
         h3 = eng.block3(3, *h2); evs[3].record()
         part = eng.block3(4, *h3, gmax=True); evs[4].record()
         eng.gmax_dense(part); evs[5].record()
-        torch.cuda.synchronize()
-        if i >= 2:
-            for j, k in enumerate(names):
-                acc[k] += evs[j].elapsed_time(evs[j + 1])
+        all_evs.append(evs)
+    torch.cuda.synchronize()   # one sync at the end: the stream never drains between kernels
+    acc = {k: 0.0 for k in names}
+    for evs in all_evs[2:]:
+        for j, k in enumerate(names):
+            acc[k] += evs[j].elapsed_time(evs[j + 1])
     kern_ms = {k: v / prof_steps for k, v in acc.items()}
 
     if rank == 0:

@@ -105,6 +105,71 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
                    const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
                    void* stream);
 
+/* =============================================================================================================
+ * Training (SURVEY.md 8(a) a3 train mode, a4, a13): what Keras' fit_generator does implicitly for
+ * experiments/train_siamese.py:56-65 / train_classifier.py:114-120.  "BN group" = one application of the shared
+ * encoder (the siamese net applies it once per branch: voicemap/models.py:52-53); clips [g*N/G, (g+1)*N/G) are
+ * group g.  Gradients carry the loss scale folded into vm_pair_head_loss_bwd; vm_adam_step divides it out.
+ * ============================================================================================================= */
+
+/* "raw" packing for train mode: identity BN, sigma = +1, epilogue y = relu(acc + bias).  bias may be NULL. */
+int vm_pack_conv1_raw(const float* kernel, const float* bias, int cout, void* wpack, float* epi, void* stream);
+int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout, void* wpack, float* epi,
+                      void* stream);
+/* dgrad operand: tap-flipped, channel-transposed kernel in the conv3 layout with (cin' = Cout, cout' = Cin);
+ * wpack holds vm_conv3_wpack_bytes(cout, cin) bytes, epi vm_epi_bytes(cin). */
+int vm_pack_conv3_dgrad(const float* kernel /* (3, Cin, Cout) */, int cin, int cout, void* wpack, float* epi,
+                        void* stream);
+
+/* Train-mode conv forward: u = relu(conv(x) + bias), un-pooled fp32 (N, L, Cout), plus per-channel {sum, sumsq}
+ * partial rows stat_partial (N * 2*ceil(L/256), Cpad) float2 (may be NULL). */
+int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
+                     float* stat_partial, int precision, void* stream);
+/* linear = 0: as above for blocks 2-4.  linear = 1: plain convolution output (dgrad: in = dU planes, wpack from
+ * vm_pack_conv3_dgrad, out = dX fp32 (N, L, Cin)). */
+int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
+                     const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
+                     void* stream);
+int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
+
+/* Batch statistics -> bn_const (G, C) x {s, t, mean, rstd}; Keras moving-average update (momentum .99, sample
+ * variance n/(n-(1+eps))) applied once per group, in order.  moving_* may be NULL. */
+int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
+                         const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                         float* moving_var, float* bn_const, void* stream);
+/* y = bn(u) * mask -> MaxPool1D(pool) -> planes (N, L/pool, C).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
+int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                   uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* block 4: bn -> MaxPool1D(2) -> GlobalMaxPool1D merged; gmax (N, C), argmax (N, C) un-pooled position. */
+int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
+                   int32_t* argmax, void* stream);
+int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, void* stream);
+
+/* Backward of the siamese head + loss (emb (2N, E): branch 1 rows then branch 2 rows). */
+int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
+                          const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
+                          float* d_head_b, void* stream);
+int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
+                 void* stream);
+/* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax + argmax
+ * (block 4).  Outputs: dgamma, dbeta, dbias (C), dU planes (N, L, C).  scratch_f2 / scratch_f hold
+ * N * chunks * max(1, 512/C) rows of C float2 / float; bwd_const (G, C) float4. */
+int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
+              int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
+              float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
+              float* dbias, void* stream);
+/* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; partial: scratch. */
+int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
+              int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream);
+/* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co]. */
+int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, float* partial,
+              size_t partial_bytes, float* dw, void* stream);
+/* keras.optimizers.Adam update with global-norm clipping on a flat parameter buffer:
+ * g' = g * inv_scale * min(1, clipnorm / ||g * inv_scale||) (clipnorm <= 0: off); m, v, p updated in place with
+ * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller. */
+int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* scratch, float inv_scale,
+                 float clipnorm, float lr_t, float beta1, float beta2, float eps, void* stream);
+
 /* ---- testing / tuning knobs -------------------------------------------------------------------------------
  * key "max_ctas" (0 = all SMs; limits the persistent grid).  Returns the previous value or VM_ERR_SHAPE. */
 int vm_set_option(const char* key, int value);

@@ -321,3 +321,93 @@ def keras_adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps
         v[k] = beta2 * v[k] + (1 - beta2) * np.square(g)
         params[k] = params[k] - lr_t * m[k] / (np.sqrt(v[k]) + eps)
     return params, m, v
+
+
+# ----------------------------------------------------------------------------
+# training-mode restatement with autograd (the checker for the backward kernels)
+# ----------------------------------------------------------------------------
+def bn_moving_update(moving_mean, moving_var, mean, var, n, momentum=BN_MOMENTUM, eps=BN_EPS):
+    """keras.layers.BatchNormalization.call (Keras 2.2.2, training branch): the batch variance is turned into the
+    sample variance var * n / (n - (1 + eps)) before the moving-average update; moving <- moving * momentum +
+    stat * (1 - momentum).  (TF's zero_debias bookkeeping of K.moving_average_update is not restated: its extra
+    variables are not part of the Keras weights and cannot be pinned from the reference.)"""
+    var_unbiased = var * (n / (n - (1.0 + eps)))
+    return (moving_mean * momentum + mean * (1.0 - momentum),
+            moving_var * momentum + var_unbiased * (1.0 - momentum))
+
+
+def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None):
+    """Train-mode encoder on torch tensors (autograd-capable).  x (N, L, 1); P: dict name -> tensor.
+    dropout_masks: optional list of 4 keep-masks (N, 1, C) already scaled by 1/(1-p) (SpatialDropout1D,
+    voicemap/models.py:18,24,29,34).  Returns emb and per-block (mean, var, count)."""
+    h = x
+    stats = []
+    for i in range(1, 5):
+        h = conv1d_same_relu(h, P[f"conv{i}_kernel"], P[f"conv{i}_bias"])
+        n_red = h.shape[0] * h.shape[1]
+        h, m, v = batchnorm_train(h, P[f"bn{i}_gamma"], P[f"bn{i}_beta"])
+        stats.append((m.detach(), v.detach(), n_red))
+        if dropout_masks is not None and dropout_masks[i - 1] is not None:
+            h = h * dropout_masks[i - 1]
+        h = maxpool1d_valid(h, pools[i - 1])
+    gmax = h.amax(dim=1)
+    return gmax @ P["dense_kernel"] + P["dense_bias"], stats
+
+
+TRAINABLE_SUFFIXES = ("kernel", "bias", "gamma", "beta")
+
+
+def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_crossentropy",
+                             distance_metric="uniform_euclidean", dtype=torch.float64, dropout_masks=(None, None)):
+    """One training-mode forward/backward of build_siamese_net (voicemap/models.py:49-79) with the loss of
+    experiments/train_siamese.py:57 ('binary_crossentropy') or siamese_contrastive_loss.py:70 (contrastive_loss).
+    The shared encoder is applied once per branch, so BN batch statistics are per branch.
+    Returns dict(loss, prob, grads {name: array}, head grads, stats [branch][block] -> (mean, var, n))."""
+    P = {k: _t(v, dtype).clone().requires_grad_(any(k.endswith(s) for s in TRAINABLE_SUFFIXES))
+         for k, v in params.items()}
+    hw = _t(np.asarray(head_w, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
+    hb = _t(np.asarray(head_b, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
+    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0])
+    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1])
+    diff = e1 - e2
+    if distance_metric == "uniform_euclidean":
+        d = torch.sqrt(torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=0.0))
+        z = d * hw[0] + hb[0]
+    elif distance_metric == "weighted_l1":
+        z = (diff.abs() * hw).sum(dim=-1, keepdim=True) + hb[0]
+    else:
+        raise NotImplementedError(distance_metric)
+    p = torch.sigmoid(z)
+    yt = _t(np.asarray(y, dtype=np.float64).reshape(-1, 1), dtype)
+    if loss == "binary_crossentropy":
+        pc = torch.clamp(p, 1e-7, 1 - 1e-7)
+        lv = (-(yt * torch.log(pc)) - (1 - yt) * torch.log(1 - pc)).mean()
+    elif loss == "contrastive_loss":
+        lv = ((1 - yt) * p * p + yt * torch.clamp(1.0 - p, min=0.0) ** 2).mean()
+    else:
+        raise NotImplementedError(loss)
+    lv.backward()
+    grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad}
+    return dict(loss=float(lv.item()), prob=p.detach().numpy(), grads=grads,
+                head_w_grad=hw.grad.numpy().copy(), head_b_grad=hb.grad.numpy().copy(),
+                stats=[[(m.numpy(), v.numpy(), n) for (m, v, n) in s] for s in (s1, s2)],
+                e1=e1.detach().numpy(), e2=e2.detach().numpy())
+
+
+def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dtype=torch.float64,
+                                dropout_masks=None):
+    """Encoder + Dense(num_classes, softmax) + categorical_crossentropy
+    (experiments/train_classifier.py:110-115), training mode."""
+    P = {k: _t(v, dtype).clone().requires_grad_(any(k.endswith(s) for s in TRAINABLE_SUFFIXES))
+         for k, v in params.items()}
+    hk = _t(head_kernel, dtype).clone().requires_grad_(True)
+    hb = _t(head_bias, dtype).clone().requires_grad_(True)
+    emb, stats = _encoder_forward_train_torch(_t(x, dtype), P, dropout_masks=dropout_masks)
+    logits = emb @ hk + hb
+    logp = torch.log_softmax(logits, dim=-1)
+    lv = -(_t(y_onehot, dtype) * logp).sum(dim=-1).mean()
+    lv.backward()
+    grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad}
+    return dict(loss=float(lv.item()), grads=grads, head_kernel_grad=hk.grad.numpy().copy(),
+                head_bias_grad=hb.grad.numpy().copy(), stats=[(m.numpy(), v.numpy(), n) for (m, v, n) in stats],
+                probs=torch.softmax(logits, dim=-1).detach().numpy())

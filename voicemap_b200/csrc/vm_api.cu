@@ -48,7 +48,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle) {
+                    const uint32_t* box, int swizzle, int f32) {
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) return set_error(VM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(VM_ERR_SHAPE, "TMA base pointer not 16B aligned");
@@ -64,7 +64,7 @@ int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   if (swizzle == VM_SWIZZLE_32B) sw = CU_TENSOR_MAP_SWIZZLE_32B;
   if (swizzle == VM_SWIZZLE_64B) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   if (swizzle == VM_SWIZZLE_128B) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bdim,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bdim,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -144,7 +144,8 @@ int vm_conv1_relu_bn_pool4_fwd(const float* x, int N, int L, int cout, const voi
     return set_error(VM_ERR_SHAPE, "conv1: null pointer");
   if (precision == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 3");
   return launch_conv1(x, N, L, cout, wpack, epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), precision, g_max_ctas, (cudaStream_t)stream);
+                      reinterpret_cast<__half*>(out_lo), nullptr, nullptr, precision, g_max_ctas,
+                      (cudaStream_t)stream);
 }
 
 int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
@@ -155,7 +156,7 @@ int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int
     return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 3");
   return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
                       static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), gmax_partial, precision, g_max_ctas,
+                      reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, precision, g_max_ctas,
                       (cudaStream_t)stream);
 }
 
@@ -186,6 +187,90 @@ int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, 
                              (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// training entry points
+// ---------------------------------------------------------------------------------------------------------
+#define ST ((cudaStream_t)stream)
+#define H16(p) reinterpret_cast<__half*>(p)
+#define CH16(p) reinterpret_cast<const __half*>(p)
+
+int vm_pack_conv1_raw(const float* kernel, const float* bias, int cout, void* wpack, float* epi, void* stream) {
+  return launch_pack_conv1(kernel, bias, nullptr, nullptr, nullptr, nullptr, 0.f, cout, wpack, epi, ST);
+}
+int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout, void* wpack, float* epi,
+                      void* stream) {
+  return launch_pack_conv3(kernel, bias, nullptr, nullptr, nullptr, nullptr, 0.f, cin, cout, wpack, epi, ST);
+}
+int vm_pack_conv3_dgrad(const float* kernel, int cin, int cout, void* wpack, float* epi, void* stream) {
+  return launch_pack_conv3_dgrad(kernel, cin, cout, wpack, epi, ST);
+}
+int vm_stat_rows_per_clip(int L) { return 2 * ((L + 255) / 256); }
+
+int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
+                     float* stat_partial, int precision, void* stream) {
+  if (x == nullptr || wpack == nullptr || epi == nullptr || u == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv1_raw: null pointer");
+  return launch_conv1(x, N, L, cout, wpack, epi, nullptr, nullptr, u, stat_partial, precision, g_max_ctas, ST);
+}
+int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
+                     const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
+                     void* stream) {
+  if (in_hi == nullptr || wpack == nullptr || epi == nullptr || out == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3_raw: null pointer");
+  return launch_conv3(CH16(in_hi), CH16(in_lo), N, L, cin, cout, static_cast<const __half*>(wpack), epi, nullptr,
+                      nullptr, nullptr, out, stat_partial, linear, precision, g_max_ctas, ST);
+}
+int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
+                         const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                         float* moving_var, float* bn_const, void* stream) {
+  return launch_bn_stats_finalize(stat_partial, rows_per_clip, vm_padded_channels(C), N, G, L, C, gamma, beta, eps,
+                                  momentum, moving_mean, moving_var, bn_const, ST);
+}
+int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                   uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+  return launch_bn_pool_fwd(u, N, L, C, G, pool, bn_const, mask, H16(out_hi), H16(out_lo), ST);
+}
+int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
+                   int32_t* argmax, void* stream) {
+  return launch_bn_gmax_fwd(u, N, L, C, G, bn_const, mask, gmax, argmax, ST);
+}
+int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, void* stream) {
+  return launch_dense_fwd(x, N, C, w, b, E, y, ST);
+}
+int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
+                          const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
+                          float* d_head_b, void* stream) {
+  return launch_pair_head_loss_bwd(emb, N, E, metric, head_w, head_b, y_true, loss_kind, loss_scale, d_emb, d_head_w,
+                                   d_head_b, ST);
+}
+int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
+                 void* stream) {
+  return launch_dense_bwd(x, dy, w, N, C, E, dw, db, dx, ST);
+}
+int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
+              int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
+              float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
+              float* dbias, void* stream) {
+  return launch_bn_bwd(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks, bwd_const,
+                       dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f, dbias, ST);
+}
+int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
+              int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream) {
+  return launch_wgrad3(CH16(x_hi), CH16(x_lo), CH16(du_hi), CH16(du_lo), N, L, cin, cout, precision, partial,
+                       partial_bytes, dw, ST);
+}
+int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, float* partial,
+              size_t partial_bytes, float* dw, void* stream) {
+  return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, ST);
+}
+int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* scratch, float inv_scale,
+                 float clipnorm, float lr_t, float beta1, float beta2, float eps, void* stream) {
+  return launch_adam_step(p, g, m, v, n, scratch, inv_scale, clipnorm, lr_t, beta1, beta2, eps, ST);
+}
+#undef ST
+#undef H16
+#undef CH16
+
 size_t vm_encoder_workspace_bytes(int N, int L, int filters) {
   if (N <= 0 || L < 32 || filters <= 0) return 0;
   return plan_encoder(N, L, filters).total;
@@ -212,15 +297,16 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
   cudaStream_t st = (cudaStream_t)stream;
   const int f = filters;
   int rc;
-  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, precision, g_max_ctas, st))) return rc;
+  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, precision, g_max_ctas, st)))
+    return rc;
   if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
-                         nullptr, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a2h, a2l, N, pl.l2, 2 * f, 3 * f, static_cast<const __half*>(wpack[2]), epi[2], a3h, a3l,
-                         nullptr, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a3h, a3l, N, pl.l3, 3 * f, 4 * f, static_cast<const __half*>(wpack[3]), epi[3], nullptr,
-                         nullptr, part, precision, g_max_ctas, st)))
+                         nullptr, part, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   return launch_gmax_dense(part, N, pl.t4, 4 * f, pl.c4_pad, epi[3], dense_w, dense_b, E, nullptr, emb, st);
 }

@@ -207,6 +207,29 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Fused bias + ReLU + BatchNorm affine on a pooled accumulator maximum, constants from vm_pack_conv*: {a, c, t, s}.
+__device__ __forceinline__ float apply_epi(const float4& ep, float m) {
+  const float v = fmaf(ep.x, m, ep.y);
+  return (ep.w >= 0.f) ? fmaxf(v, ep.z) : fminf(v, ep.z);
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 -> (hi, lo) fp16 split.  hi = rn16(x), lo = rn16(x - hi).  hi+lo carries ~22 significant
 // bits (absolute floor 2^-25 from the fp16 subnormal grid); products of hi/lo pairs are exact in fp32.

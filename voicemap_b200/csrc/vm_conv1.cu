@@ -99,36 +99,55 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       // lane owns the 8 positions p0 + 8*lane .. +7; it needs x[p0 - 15 + 8*lane + i], i = 0..38
       const int e0 = p0 - 15 + 8 * lane;
       float xv[39];
+      if (e0 >= 0 && e0 + 39 <= p.L) {  // interior strip: no bounds predicates
 #pragma unroll
-      for (int k = 0; k < 39; ++k) {
-        const int e = e0 + k;
-        xv[k] = (e >= 0 && e < p.L) ? __ldg(xc + e) : 0.f;
+        for (int k = 0; k < 39; ++k) xv[k] = __ldg(xc + e0 + k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 39; ++k) {
+          const int e = e0 + k;
+          xv[k] = (e >= 0 && e < p.L) ? __ldg(xc + e) : 0.f;
+        }
       }
-      __half hh[39], hl[39];
+      // fp16 (hi, lo) split with packed conversions.  pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]).
+      uint32_t pe[19], po[19], le[19], lo[19];
+      {
+        float r[39];
 #pragma unroll
-      for (int k = 0; k < 39; ++k) split_f32(xv[k], hh[k], hl[k]);
+        for (int k = 0; k < 19; ++k) {
+          const __half2 e2 = __floats2half2_rn(xv[2 * k], xv[2 * k + 1]);
+          const __half2 o2 = __floats2half2_rn(xv[2 * k + 1], xv[2 * k + 2]);
+          pe[k] = *reinterpret_cast<const uint32_t*>(&e2);
+          po[k] = *reinterpret_cast<const uint32_t*>(&o2);
+          const float2 f = __half22float2(e2);
+          r[2 * k] = xv[2 * k] - f.x;
+          r[2 * k + 1] = xv[2 * k + 1] - f.y;
+          if (k == 18) r[38] = xv[38] - __high2float(o2);
+        }
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+          const __half2 e2 = __floats2half2_rn(r[2 * k], r[2 * k + 1]);
+          const __half2 o2 = __floats2half2_rn(r[2 * k + 1], r[2 * k + 2]);
+          le[k] = *reinterpret_cast<const uint32_t*>(&e2);
+          lo[k] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+      }
 
       mbar_wait(&bars->empty[q], (((i / kStages) & 1) ^ 1));
       const uint32_t st = smem_u32(stages + q * kStageBytes + lane * kGroupStride);
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
         if (pl < nplanes) {
-          const __half* h = pl ? hl : hh;
-          uint32_t pe[19], po[19];  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2])
-#pragma unroll
-          for (int k = 0; k < 19; ++k) {
-            pe[k] = pack_h2(h[2 * k], h[2 * k + 1]);
-            po[k] = pack_h2(h[2 * k + 1], h[2 * k + 2]);
-          }
+          const uint32_t* ev = pl ? le : pe;
+          const uint32_t* ov = pl ? lo : po;
           const uint32_t base = st + pl * kPlaneBytes;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int o = r + 8 * j;  // first element of this 8-tap chunk
-              sts_v4(base + j * 128 + r * 16, (o & 1) ? po[(o - 1) / 2 + 0] : pe[o / 2 + 0],
-                     (o & 1) ? po[(o - 1) / 2 + 1] : pe[o / 2 + 1], (o & 1) ? po[(o - 1) / 2 + 2] : pe[o / 2 + 2],
-                     (o & 1) ? po[(o - 1) / 2 + 3] : pe[o / 2 + 3]);
+              const uint32_t* src = (o & 1) ? (ov + (o - 1) / 2) : (ev + o / 2);
+              sts_v4(base + j * 128 + r * 16, src[0], src[1], src[2], src[3]);
             }
           }
         }
@@ -182,7 +201,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
     const int chalf = warp >> 2;     // which half of the 256 position columns
     const bool leader = (threadIdx.x == 0);
     const int ch = q * 32 + lane;
-    uint32_t ait = 0;
+    uint32_t ait = 0, git = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
@@ -190,6 +209,51 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
         const int buf = ait & 1;
         const int co = slab * kTileM + ch;
         const float4 ep = p.epi[co];
+        if (p.out_f32 != nullptr) {
+          // train-mode forward: un-pooled u = relu(acc + bias) as fp32 + per-channel {sum, sum of squares}
+          // partials.  Granule = 64 positions x 128 channels fp32 = one 32 KB staging buffer (4 TMA boxes of 32
+          // channels); the two warps of a lane quarter take 32 columns each.
+          mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
+          tc_fence_after_sync();
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+          for (int gr = 0; gr < kTileN / 64; ++gr, ++git) {
+            uint8_t* ob = outbuf + (git & 1) * kOutBufBytes;
+            const uint32_t st = smem_u32(ob) + (ch >> 5) * 8192 + (ch & 31) * 4 + chalf * 32 * 128;
+            if (leader) tma_store_wait_read<1>();
+            named_bar_sync(1, kEpiWarps * 32);
+            float v[32];
+            tmem_ld_32x32(taddr + gr * 64 + chalf * 32, v);
+            if (gr == kTileN / 64 - 1) {
+              tc_fence_before_sync();
+              mbar_arrive(&bars->tempty[buf]);
+            }
+            const int pos0 = p0 + gr * 64 + chalf * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float y = apply_epi(ep, v[j]);
+              if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
+              sts_f32(st + j * 128, y);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiWarps * 32);
+            if (leader) {
+              const int pos = p0 + gr * 64;
+              if (pos < p.L) {
+#pragma unroll
+                for (int b4 = 0; b4 < 4; ++b4) {
+                  const int c0 = slab * kTileM + b4 * 32;
+                  if (c0 < p.cout) tma_store_3d(&tm_oh, ob + b4 * 8192, c0, pos, n);
+                }
+              }
+              tma_store_commit();
+            }
+          }
+          if (p.stat_partial != nullptr)
+            p.stat_partial[(size_t(tile) * 2 + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+          continue;
+        }
         uint8_t* ob = outbuf + buf * kOutBufBytes;
         const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
         const uint32_t st_l = st_h + 2 * kOutBoxBytes;
@@ -210,7 +274,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float mx = max3(fmaxf(v[4 * j], v[4 * j + 1]), v[4 * j + 2], v[4 * j + 3]);
-            const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
+            const float y = apply_epi(ep, mx);
             __half h, l;
             split_f32(y, h, l);
             sts_u16(st_h + (g * 8 + j) * 128, h);
@@ -245,7 +309,8 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 }
 
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
-                 __half* out_lo, int products, int max_ctas, cudaStream_t stream) {
+                 __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
+                 cudaStream_t stream) {
   using namespace c1;
   if (N <= 0 || L < 4) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= 4");
   if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
@@ -262,9 +327,19 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo;
   p.nstages = (nslab == 1) ? 4 : (nslab <= 3 ? 3 : 2);
-  if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products=3");
+  p.out_f32 = out_f32;
+  p.stat_partial = reinterpret_cast<float2*>(stat_partial);
   CUtensorMap oh, ol;
-  {
+  if (out_f32 != nullptr) {
+    const uint64_t odims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+    const uint64_t ostr[2] = {uint64_t(cout) * 4, uint64_t(L) * cout * 4};
+    const uint32_t obox[3] = {32, 64, 1};
+    int rc;
+    if ((rc = make_tensor_map(&oh, out_f32, 3, odims, ostr, obox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
+    ol = oh;
+  } else {
+    if (out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv1: no output given");
+    if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products=3");
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};
     const uint32_t obox[3] = {64, 64, 1};

@@ -221,6 +221,47 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         mbar_arrive(&bars->tempty[buf]);
         // the two column halves keep separate partial rows: (N, 2*nptile, cout_pad)
         p.gmax_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = m;
+      } else if (p.out_f32 != nullptr) {
+        // un-pooled fp32 output (train-mode forward: u = relu(acc + bias) with per-channel sum / sum-of-squares
+        // partials; dgrad: y = acc).  Staging granule = 32 positions x 128 channels fp32 (4 TMA boxes of
+        // 32 channels); the two warps of a lane quarter split the 32 columns 16/16.
+        const bool leader = (threadIdx.x == 4 * 32);
+        const int ch = q * 32 + lane;
+        const uint32_t st = smem_u32(stage) + (ch >> 5) * 4096 + (ch & 31) * 4 + chalf * 16 * 128;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int gr = 0; gr < kTileN / 32; ++gr) {
+          if (leader) tma_store_wait_read<0>();
+          named_bar_sync(1, kEpiWarps * 32);
+          float v[16];
+          tmem_ld_32x16(taddr + gr * 32 + chalf * 16, v);
+          if (gr == kTileN / 32 - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&bars->tempty[buf]);
+          }
+          const int pos0 = p0 + gr * 32 + chalf * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float y = p.linear ? v[j] : apply_epi(ep, v[j]);
+            if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
+            sts_f32(st + j * 128, y);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiWarps * 32);
+          if (leader) {
+            const int pos = p0 + gr * 32;
+            if (pos < p.L) {
+#pragma unroll
+              for (int b4 = 0; b4 < 4; ++b4) {
+                const int c0 = slab * kTileM + b4 * 32;
+                if (c0 < p.cout) tma_store_3d(&tm_oh, stage + b4 * 4096, c0, pos, n);
+              }
+            }
+            tma_store_commit();
+          }
+        }
+        if (p.stat_partial != nullptr)
+          p.stat_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
       } else {
         // pooled outputs go through a shared-memory staging granule (32 positions x 128 channels x 2 planes)
         // and leave with TMA bulk tensor stores; out-of-range positions / channels are clipped by the TMA unit.
@@ -243,7 +284,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float mx = fmaxf(v[2 * j], v[2 * j + 1]);
-              const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, mx, ep.y), 0.f), ep.w);
+              const float y = apply_epi(ep, mx);
               __half h, l;
               split_f32(y, h, l);
               sts_u16(st_h + (sub * 16 + j) * 128, h);
@@ -284,15 +325,16 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 // host launcher
 // ---------------------------------------------------------------------------------------------
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
-                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int max_ctas,
-                 cudaStream_t stream) {
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
+                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream) {
   using namespace c3;
   if (N <= 0 || L <= 0) return set_error(VM_ERR_SHAPE, "conv3: N and L must be positive");
   // K chunks are 64 channels wide; a ragged last chunk is zero-filled by TMA in both operands
   if (cin % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 8");
   if (cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cout must be a multiple of 8");
   if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1 or 3");
-  if (gmax_partial == nullptr && out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv3: no output given");
+  if (gmax_partial == nullptr && out_hi == nullptr && out_f32 == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3: no output given");
   if (L / 2 <= 0) return set_error(VM_ERR_SHAPE, "conv3: L must be >= 2");
   const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
 
@@ -305,6 +347,7 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   p.products = products;
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo; p.gmax_partial = gmax_partial;
+  p.out_f32 = out_f32; p.stat_partial = reinterpret_cast<float2*>(stat_partial); p.linear = linear;
 
   CUtensorMap xh_main, xh_halo, xl_main, xl_halo, wh, wl;
   // X planes: (N, L, Cin) fp16, dims fastest-first {Cin, L, N}
@@ -329,7 +372,14 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
 
   // pooled output planes (N, lout, cout) fp16 -- TMA store boxes of 64 channels x 32 positions
   CUtensorMap oh, ol;
-  if (gmax_partial == nullptr) {
+  if (out_f32 != nullptr) {
+    // un-pooled fp32 output (N, L, cout): TMA store boxes of 32 channels x 32 positions
+    const uint64_t odims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+    const uint64_t ostr[2] = {uint64_t(cout) * 4, uint64_t(L) * cout * 4};
+    const uint32_t obox[3] = {32, 32, 1};
+    if ((rc = make_tensor_map(&oh, out_f32, 3, odims, ostr, obox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
+    ol = oh;
+  } else if (gmax_partial == nullptr) {
     if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: out_lo required for products=3");
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};

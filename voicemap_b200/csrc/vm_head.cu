@@ -10,12 +10,18 @@
 
 namespace vm {
 
-// epilogue constants: y = s * relu(sigma * max(acc') + bias) + t with acc' computed from sigma-scaled weights
+// Epilogue constants {a, c, t, s}.  With acc' = sigma * acc (weights are packed sigma-scaled, sigma = sign(s)) and
+// M = max over the pool window of acc':   y = s * relu(sigma * M + bias) + t
+//                                           = s >= 0 ? max(a * M + c, t) : min(a * M + c, t),  a = s * sigma, c = s * bias + t
+// (one FFMA + one FMNMX per pooled value; s only selects min/max).
+__device__ __forceinline__ float bn_scale(const float* gamma, const float* var, float eps, int c) {
+  return gamma ? gamma[c] * (1.0f / sqrtf(var[c] + eps)) : 1.0f;  // null BN = identity (train-mode "raw" packing)
+}
 __device__ __forceinline__ float4 fold_bn(float bias, float gamma, float beta, float mean, float var, float eps) {
   const float s = gamma * (1.0f / sqrtf(var + eps));
   const float t = beta - mean * s;
   const float sigma = (s < 0.f) ? -1.f : 1.f;
-  return make_float4(sigma, bias, s, t);
+  return make_float4(s * sigma, fmaf(s, bias, t), t, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -29,8 +35,9 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __re
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx < size_t(cout_pad)) {
     const int co = int(idx);
-    epi[co] = (co < cout) ? fold_bn(bias[co], gamma[co], beta[co], mean[co], var[co], eps)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (co >= cout) epi[co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (gamma == nullptr) epi[co] = make_float4(1.f, bias ? bias[co] : 0.f, 0.f, 1.f);  // y = relu(acc + bias)
+    else epi[co] = fold_bn(bias[co], gamma[co], beta[co], mean[co], var[co], eps);
   }
   if (idx >= total) return;
   const int ci = int(idx % cin);
@@ -38,7 +45,7 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __re
   const int tap = int(idx / (size_t(cin) * cout_pad));
   float v = 0.f;
   if (co < cout) {
-    const float s = gamma[co] * (1.0f / sqrtf(var[co] + eps));
+    const float s = bn_scale(gamma, var, eps, co);
     v = w[(size_t(tap) * cin + ci) * cout + co];
     if (s < 0.f) v = -v;
   }
@@ -57,15 +64,17 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
                                   int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < cout_pad)
-    epi[idx] = (idx < cout) ? fold_bn(bias[idx], gamma[idx], beta[idx], mean[idx], var[idx], eps)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < cout_pad) {
+    if (idx >= cout) epi[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (gamma == nullptr) epi[idx] = make_float4(1.f, bias ? bias[idx] : 0.f, 0.f, 1.f);
+    else epi[idx] = fold_bn(bias[idx], gamma[idx], beta[idx], mean[idx], var[idx], eps);
+  }
   if (idx >= cout_pad * 32) return;
   const int tap = idx & 31;
   const int co = idx >> 5;
   float v = 0.f;
   if (co < cout) {
-    const float s = gamma[co] * (1.0f / sqrtf(var[co] + eps));
+    const float s = bn_scale(gamma, var, eps, co);
     v = w[size_t(tap) * cout + co];
     if (s < 0.f) v = -v;
   }
@@ -76,6 +85,27 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
   __half* img = wpack + size_t(slab) * 8192;                                        // 2 planes x 4096 halves
   img[off] = h;
   img[4096 + off] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad weights: dX[p][ci] = sum_t sum_co dU[p + t - 1][co] * W[2 - t][ci][co] is a k=3 'same' convolution of dU with
+// the tap-flipped, channel-transposed kernel.  w (3, cin, cout) -> wpack [plane][tap][cin_pad][cout] fp16, i.e. the
+// conv3 operand layout with the roles (cin' = cout, cout' = cin).
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad,
+                                        __half* __restrict__ wpack, float4* __restrict__ epi) {
+  const size_t total = size_t(3) * cin_pad * cout;
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < size_t(cin_pad)) epi[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // unused (linear epilogue)
+  if (idx >= total) return;
+  const int co = int(idx % cout);
+  const int ci = int((idx / cout) % cin_pad);
+  const int tap = int(idx / (size_t(cout) * cin_pad));
+  const float v = (ci < cin) ? w[(size_t(2 - tap) * cin + ci) * cout + co] : 0.f;
+  __half h, l;
+  split_f32(v, h, l);
+  wpack[idx] = h;
+  wpack[total + idx] = l;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -99,26 +129,38 @@ __global__ void merge_planes_kernel(const __half* __restrict__ hi, const __half*
 // ---------------------------------------------------------------------------------------------
 // GlobalMaxPool finalisation + Dense.  partial: (N, T, c_pad) raw accumulator maxima per position tile.
 // ---------------------------------------------------------------------------------------------
-__global__ void gmax_dense_kernel(const float* __restrict__ partial, int T, int C, int c_pad,
-                                  const float4* __restrict__ epi, const float* __restrict__ dense_w,
-                                  const float* __restrict__ dense_b, int E, float* __restrict__ gmax_out,
-                                  float* __restrict__ emb) {
-  extern __shared__ float g[];
+__global__ void __launch_bounds__(256)
+gmax_dense_kernel(const float* __restrict__ partial, int T, int C, int c_pad, const float4* __restrict__ epi,
+                  const float* __restrict__ dense_w, const float* __restrict__ dense_b, int E,
+                  float* __restrict__ gmax_out, float* __restrict__ emb) {
+  extern __shared__ float g[];      // [C] pooled activations, then [4][E] partial dot products
+  float* red = g + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float m = -INFINITY;
     for (int t = 0; t < T; ++t) m = fmaxf(m, partial[(size_t(n) * T + t) * c_pad + c]);
-    const float4 ep = epi[c];
-    const float y = fmaf(ep.z, fmaxf(fmaf(ep.x, m, ep.y), 0.f), ep.w);
+    const float y = apply_epi(epi[c], m);
     g[c] = y;
     if (gmax_out != nullptr) gmax_out[size_t(n) * C + c] = y;
   }
   __syncthreads();
   if (emb == nullptr) return;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+  // 4 channel quarters x 64 outputs per pass: each thread accumulates a quarter of the dot product
+  const int part = threadIdx.x >> 6, lane_e = threadIdx.x & 63;
+  const int cq = (C + 3) / 4;
+  const int c0 = part * cq, c1 = min(C, c0 + cq);
+  for (int e0 = 0; e0 < E; e0 += 64) {
+    const int e = e0 + lane_e;
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(g[c], dense_w[size_t(c) * E + e], acc);
-    emb[size_t(n) * E + e] = acc + dense_b[e];
+    if (e < E) {
+#pragma unroll 8
+      for (int c = c0; c < c1; ++c) acc = fmaf(g[c], __ldg(dense_w + size_t(c) * E + e), acc);
+    }
+    red[part * 64 + lane_e] = acc;
+    __syncthreads();
+    if (part == 0 && e < E)
+      emb[size_t(n) * E + e] = ((red[lane_e] + red[64 + lane_e]) + (red[128 + lane_e] + red[192 + lane_e])) + dense_b[e];
+    __syncthreads();
   }
 }
 
@@ -194,6 +236,16 @@ int launch_pack_conv3(const float* w, const float* bias, const float* gamma, con
   return check_launch("pack_conv3");
 }
 
+int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream) {
+  if (cin <= 0 || cout <= 0) return set_error(VM_ERR_SHAPE, "pack_conv3_dgrad: bad shape");
+  const int cin_pad = (cin + 127) / 128 * 128;
+  const size_t total = size_t(3) * cin_pad * cout;
+  pack_conv3_dgrad_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(w, cin, cout, cin_pad,
+                                                                            static_cast<__half*>(wpack),
+                                                                            reinterpret_cast<float4*>(epi));
+  return check_launch("pack_conv3_dgrad");
+}
+
 int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
                       const float* var, float eps, int cout, void* wpack, float* epi, cudaStream_t stream) {
   if (cout <= 0) return set_error(VM_ERR_SHAPE, "pack_conv1: bad shape");
@@ -224,9 +276,10 @@ int launch_gmax_dense(const float* partial, int N, int T, int C, int c_pad, cons
   if (N <= 0 || T <= 0 || C <= 0 || c_pad < C) return set_error(VM_ERR_SHAPE, "gmax_dense: bad shape");
   if (emb != nullptr && (E <= 0 || dense_w == nullptr || dense_b == nullptr))
     return set_error(VM_ERR_SHAPE, "gmax_dense: dense weights missing");
-  if (size_t(C) * sizeof(float) > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "gmax_dense: C > 12288");
-  gmax_dense_kernel<<<N, 128, C * sizeof(float), stream>>>(partial, T, C, c_pad, reinterpret_cast<const float4*>(epi),
-                                                          dense_w, dense_b, E, gmax_out, emb);
+  if (size_t(C + 256) * sizeof(float) > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "gmax_dense: C too large");
+  gmax_dense_kernel<<<N, 256, (C + 256) * sizeof(float), stream>>>(partial, T, C, c_pad,
+                                                                  reinterpret_cast<const float4*>(epi), dense_w, dense_b,
+                                                                  E, gmax_out, emb);
   return check_launch("gmax_dense");
 }
 

@@ -18,7 +18,8 @@ int num_sms();
 // ---- TMA descriptor creation through the driver entry point (no link-time libcuda dependency) ----
 enum { VM_SWIZZLE_NONE = 0, VM_SWIZZLE_32B = 1, VM_SWIZZLE_64B = 2, VM_SWIZZLE_128B = 3 };
 int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle);
+                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle,
+                    int f32 = 0);
 
 // ---- block 1 ----
 struct Conv1Params {
@@ -33,9 +34,12 @@ struct Conv1Params {
   const float4* epi;     // [cout_pad] {sigma, bias, s, t}
   __half* out_hi;        // (N, lout, cout)
   __half* out_lo;
+  float* out_f32;        // (N, L, cout) un-pooled fp32 output (train-mode forward), or null
+  float2* stat_partial;  // (N*nptile*2, cout_pad) {sum, sum of squares} over valid positions, or null
 };
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
-                 __half* out_lo, int products, int max_ctas, cudaStream_t stream);
+                 __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
+                 cudaStream_t stream);
 
 // ---- blocks 2-4 ----
 struct Conv3Params {
@@ -48,11 +52,50 @@ struct Conv3Params {
   const float4* epi;     // [cout_pad]
   __half* out_hi;        // (N, lout, cout) or null
   __half* out_lo;
-  float* gmax_partial;   // (N, nptile, cout_pad) raw accumulator maxima, or null
+  float* gmax_partial;   // (N, 2*nptile, cout_pad) raw accumulator maxima, or null
+  float* out_f32;        // (N, L, cout) un-pooled fp32 output (train-mode forward / dgrad), or null
+  float2* stat_partial;  // (N, 2*nptile, cout_pad) {sum, sum of squares} of out_f32 over valid positions, or null
+  int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
-                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, int products, int max_ctas,
-                 cudaStream_t stream);
+                 const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
+                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream);
+
+// ---- weight gradients (vm_wgrad.cu) ----
+struct Wgrad3Params {
+  int N, L, cin, cout, products;
+  int nchunk;            // ceil(L / 64) position chunks per clip
+  int nco_tiles, ncombo; // (ci slab, co tile) work items
+  int nsplit;            // reduction splits over (clip, chunk) steps
+  float* partial;        // [nsplit][3][cin][cout]
+};
+int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, const __half* du_lo, int N, int L,
+                  int cin, int cout, int products, float* partial, size_t partial_bytes, float* dw,
+                  cudaStream_t stream);
+int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
+                  size_t partial_bytes, float* dw, cudaStream_t stream);
+
+// ---- training elementwise / reduction kernels (vm_train.cu) ----
+int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,
+                             const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                             float* moving_var, float* bn_const, cudaStream_t st);
+int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
+                       const float* mask, __half* out_hi, __half* out_lo, cudaStream_t st);
+int launch_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask,
+                       float* gmax, int* argmax, cudaStream_t st);
+int launch_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, cudaStream_t st);
+int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db,
+                     float* dx, cudaStream_t st);
+int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
+                              const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
+                              float* d_head_b, cudaStream_t st);
+int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
+                  int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
+                  float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
+                  float* dbias, cudaStream_t st);
+int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
+                     float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
+int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);
 
 // ---- small kernels (vm_head.cu) ----
 int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,

@@ -1,0 +1,574 @@
+// Training-mode kernels around the tensor-core convolutions (CUDA cores; all HBM-bound elementwise / reduction work).
+//
+// Forward (train):  conv (RAW mode: u = relu(acc + bias), fp32, un-pooled, + {sum, sumsq} partials)
+//                   -> bn_stats_finalize (batch moments per BN group, Keras moving-average update)
+//                   -> bn_pool_fwd (y = s*u + t, SpatialDropout mask, MaxPool -> fp16 (hi, lo) planes)
+//                      / bn_gmax_fwd for block 4 (MaxPool(2) + GlobalMaxPool1D merged, with argmax)
+//                   -> dense_fwd -> pair head + loss (vm_head.cu)
+// Backward:         pair_head_loss_bwd -> dense_bwd -> per block (4..1):
+//                   bn_bwd_reduce (sum dy, sum dy*xhat) -> bn_bwd_finalize (+ dgamma, dbeta)
+//                   -> bn_relu_bwd (dU as fp16 planes, + conv-bias gradient partials)
+//                   -> wgrad (vm_wgrad.cu) and dgrad (conv3_kernel on flipped/transposed weights).
+// Reference semantics: keras BatchNormalization / SpatialDropout1D / MaxPool1D / GlobalMaxPool1D / Dense in training
+// mode as used by voicemap/models.py:6-81; losses voicemap/utils.py:77-85 and keras binary_crossentropy.
+//
+// A "BN group" is one application of the shared encoder (the siamese net applies it once per branch, so batch
+// statistics are per branch: voicemap/models.py:52-53); clips [g*N/G, (g+1)*N/G) form group g.
+// All gradients flowing through these kernels carry the loss scale the caller folded into the loss gradient.
+#include "vm_common.cuh"
+#include "vm_kernels.h"
+
+namespace vm {
+
+static int check_launch_t(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  return VM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch statistics -> BN constants {s, t, mean, rstd} per (group, channel); moving-average update
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_stats_finalize_kernel(const float2* __restrict__ partial, int rows_per_clip, int c_pad, int N,
+                                         int G, int L, int C, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float momentum,
+                                         float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                         float4* __restrict__ bn_const) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int clips = N / G;
+  const double cnt = double(clips) * double(L);
+  float mm = moving_mean ? moving_mean[c] : 0.f;
+  float mv = moving_var ? moving_var[c] : 0.f;
+  for (int g = 0; g < G; ++g) {
+    double s1 = 0.0, s2 = 0.0;
+    const size_t r0 = size_t(g) * clips * rows_per_clip;
+    for (size_t r = 0; r < size_t(clips) * rows_per_clip; ++r) {
+      const float2 v = partial[(r0 + r) * c_pad + c];
+      s1 += double(v.x);
+      s2 += double(v.y);
+    }
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;  // biased batch variance (tf.nn.moments)
+    if (var < 0.0) var = 0.0;
+    const float rstd = float(1.0 / sqrt(var + double(eps)));
+    const float s = gamma[c] * rstd;
+    bn_const[size_t(g) * C + c] = make_float4(s, beta[c] - float(mean) * s, float(mean), rstd);
+    // keras: sample variance var * n / (n - (1 + eps)); moving <- moving * momentum + stat * (1 - momentum)
+    const float var_unbiased = float(var * (cnt / (cnt - (1.0 + double(eps)))));
+    mm = mm * momentum + float(mean) * (1.f - momentum);
+    mv = mv * momentum + var_unbiased * (1.f - momentum);
+  }
+  if (moving_mean) moving_mean[c] = mm;
+  if (moving_var) moving_var[c] = mv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN affine (+ dropout mask) + MaxPool -> (hi, lo) planes.  One thread = 4 channels of one pooled position.
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G, int pool,
+                                   const float4* __restrict__ bn_const, const float* __restrict__ mask,
+                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int lout = L / pool;
+  const int c4n = C >> 2;
+  const size_t total = size_t(N) * lout * c4n;
+  for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += size_t(gridDim.x) * blockDim.x) {
+    const int c4 = int(idx % c4n);
+    const size_t nj = idx / c4n;
+    const int j = int(nj % lout);
+    const int n = int(nj / lout);
+    const int g = n / (N / G);
+    float sv[4], tv[4], best[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 bc = bn_const[size_t(g) * C + 4 * c4 + k];
+      const float mk = mask ? mask[size_t(n) * C + 4 * c4 + k] : 1.f;
+      sv[k] = bc.x * mk;
+      tv[k] = bc.y * mk;
+      best[k] = -INFINITY;
+    }
+    for (int i = 0; i < pool; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(u + (size_t(n) * L + size_t(j) * pool + i) * C + 4 * c4);
+      best[0] = fmaxf(best[0], fmaf(sv[0], x.x, tv[0]));
+      best[1] = fmaxf(best[1], fmaf(sv[1], x.y, tv[1]));
+      best[2] = fmaxf(best[2], fmaf(sv[2], x.z, tv[2]));
+      best[3] = fmaxf(best[3], fmaf(sv[3], x.w, tv[3]));
+    }
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_f32(best[k], h[k], l[k]);
+    const size_t o = (size_t(n) * lout + j) * C + 4 * c4;
+    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(
+        uint32_t(__half_as_ushort(h[0])) | (uint32_t(__half_as_ushort(h[1])) << 16),
+        uint32_t(__half_as_ushort(h[2])) | (uint32_t(__half_as_ushort(h[3])) << 16));
+    *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(
+        uint32_t(__half_as_ushort(l[0])) | (uint32_t(__half_as_ushort(l[1])) << 16),
+        uint32_t(__half_as_ushort(l[2])) | (uint32_t(__half_as_ushort(l[3])) << 16));
+  }
+}
+
+// Block 4: BN affine (+ mask) -> MaxPool(2,'valid') -> GlobalMaxPool1D == max over positions l < 2*floor(L/2).
+// grid (N, ceil(C/32)); block (32 channels, 8 position lanes).  Writes the max and the un-pooled argmax position.
+__global__ void bn_gmax_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G,
+                                   const float4* __restrict__ bn_const, const float* __restrict__ mask,
+                                   float* __restrict__ gmax, int* __restrict__ argmax) {
+  __shared__ float smax[8][32];
+  __shared__ int sidx[8][32];
+  const int n = blockIdx.x;
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  const int g = n / (N / G);
+  const int lvalid = (L / 2) * 2;
+  float best = -INFINITY;
+  int bi = 0;
+  if (c < C) {
+    const float4 bc = bn_const[size_t(g) * C + c];
+    const float mk = mask ? mask[size_t(n) * C + c] : 1.f;
+    const float s = bc.x * mk, t = bc.y * mk;
+    for (int l = threadIdx.y; l < lvalid; l += 8) {
+      const float y = fmaf(s, u[(size_t(n) * L + l) * C + c], t);
+      if (y > best) { best = y; bi = l; }
+    }
+  }
+  smax[threadIdx.y][threadIdx.x] = best;
+  sidx[threadIdx.y][threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) {
+      const float v = smax[k][threadIdx.x];
+      const int i = sidx[k][threadIdx.x];
+      if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    gmax[size_t(n) * C + c] = best;
+    argmax[size_t(n) * C + c] = bi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense forward / backward (embedding layer, voicemap/models.py:39)
+// ---------------------------------------------------------------------------------------------
+__global__ void dense_fwd_kernel(const float* __restrict__ x, int N, int C, const float* __restrict__ w,
+                                 const float* __restrict__ b, int E, float* __restrict__ y) {
+  extern __shared__ float xs[];
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) xs[c] = x[size_t(n) * C + c];
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(xs[c], w[size_t(c) * E + e], acc);
+    y[size_t(n) * E + e] = acc + b[e];
+  }
+}
+// dW[c][e] = sum_n x[n][c] * dy[n][e]  (grid C blocks, E threads);  db[e] = sum_n dy[n][e] (block 0)
+__global__ void dense_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, int N, int C, int E,
+                                   float* __restrict__ dw, float* __restrict__ db) {
+  const int c = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float d = dy[size_t(n) * E + e];
+      acc = fmaf(x[size_t(n) * C + c], d, acc);
+      accb += d;
+    }
+    dw[size_t(c) * E + e] = acc;
+    if (c == 0) db[e] = accb;
+  }
+}
+// dx[n][c] = sum_e dy[n][e] * w[c][e]   (grid N blocks, C threads strided)
+__global__ void dense_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, int N, int C, int E,
+                                   float* __restrict__ dx) {
+  extern __shared__ float ds[];
+  const int n = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) ds[e] = dy[size_t(n) * E + e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(ds[e], w[size_t(c) * E + e], acc);
+    dx[size_t(n) * C + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Siamese head + loss backward.  emb (2N, E): rows [0,N) branch 1, [N,2N) branch 2.  One block.
+// d_emb (2N, E), d_head_w (1 or E), d_head_b (1); everything multiplied by loss_scale.
+// ---------------------------------------------------------------------------------------------
+__global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, int E, int metric,
+                                          const float* __restrict__ head_w, const float* __restrict__ head_b,
+                                          const float* __restrict__ y_true, int loss_kind, float loss_scale,
+                                          float* __restrict__ d_emb, float* __restrict__ d_head_w,
+                                          float* __restrict__ d_head_b) {
+  extern __shared__ float dzs[];  // [N] dL/dz (scaled), then [N] distance
+  float* dist = dzs + N;
+  const float* e1 = emb;
+  const float* e2 = emb + size_t(N) * E;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float* a = e1 + size_t(n) * E;
+    const float* b = e2 + size_t(n) * E;
+    float z, d = 0.f;
+    if (metric == 0) {
+      float ss = 0.f;
+      for (int j = 0; j < E; ++j) { const float t = a[j] - b[j]; ss = fmaf(t, t, ss); }
+      d = sqrtf(fmaxf(ss, 0.f));
+      z = fmaf(d, head_w[0], head_b[0]);
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < E; ++j) acc = fmaf(fabsf(a[j] - b[j]), head_w[j], acc);
+      z = acc + head_b[0];
+    }
+    const float p = 1.0f / (1.0f + expf(-z));
+    const float y = y_true[n];
+    float dp;
+    if (loss_kind == 1) {  // contrastive: (1-y) p^2 + y max(1-p,0)^2
+      dp = (1.f - y) * 2.f * p - y * 2.f * fmaxf(1.f - p, 0.f);
+    } else {               // BCE on clip(p, 1e-7, 1-1e-7): zero gradient outside the clip range
+      const float lo = 1e-7f, hi = 1.0f - 1e-7f;
+      dp = (p < lo || p > hi) ? 0.f : (-y / p + (1.f - y) / (1.f - p));
+    }
+    dzs[n] = dp * p * (1.f - p) * (loss_scale / float(N));
+    dist[n] = d;
+  }
+  __syncthreads();
+  // d_emb
+  for (int idx = threadIdx.x; idx < N * E; idx += blockDim.x) {
+    const int n = idx / E, j = idx % E;
+    const float diff = e1[idx] - e2[idx];
+    float g;
+    if (metric == 0) {
+      const float d = dist[n];
+      g = (d > 0.f) ? dzs[n] * head_w[0] * diff / d : 0.f;  // sqrt'(0) guarded (the reference yields NaN there)
+    } else {
+      g = dzs[n] * head_w[j] * ((diff > 0.f) - (diff < 0.f));
+    }
+    d_emb[idx] = g;
+    d_emb[size_t(N) * E + idx] = -g;
+  }
+  // head gradients
+  if (metric == 0) {
+    if (threadIdx.x == 0) {
+      float gw = 0.f, gb = 0.f;
+      for (int n = 0; n < N; ++n) { gw = fmaf(dzs[n], dist[n], gw); gb += dzs[n]; }
+      d_head_w[0] = gw;
+      d_head_b[0] = gb;
+    }
+  } else {
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+      float gw = 0.f;
+      for (int n = 0; n < N; ++n) gw = fmaf(dzs[n], fabsf(e1[size_t(n) * E + j] - e2[size_t(n) * E + j]), gw);
+      d_head_w[j] = gw;
+    }
+    if (threadIdx.x == 0) {
+      float gb = 0.f;
+      for (int n = 0; n < N; ++n) gb += dzs[n];
+      d_head_b[0] = gb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN backward, pass 1: per-channel sums of dy and dy * xhat over the batch.
+//   dense  (dy_pooled != null): gradient arrives on the pooled tensor (N, L/pool, C) and is routed to the
+//                               arg-max of each window (recomputed from u);
+//   sparse (dy_pooled == null): block 4, gradient d_gmax (N, C) sits at position argmax[n][c].
+// grid (N, chunks), block = 128 threads over channels; partial rows [(n*chunks + chunk)][C] float2.
+// ---------------------------------------------------------------------------------------------
+// Thread layout of the two big elementwise passes: one thread owns 4 adjacent channels (float4 loads, 8-byte plane
+// stores); a block of 128 threads covers C/4 channel groups x (512/C) interleaved position streams.
+__device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+// arg-max of s*u + t over a pool window == arg-max of u (s >= 0) or arg-min of u (s < 0); first winner on ties
+__device__ __forceinline__ void window_argmax4(const float* __restrict__ up, int C, int pool, const float (&s)[4],
+                                               int (&bi)[4], float (&bu)[4]) {
+  const float4 v0 = *reinterpret_cast<const float4*>(up);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { bi[k] = 0; bu[k] = f4get(v0, k); }
+  for (int i = 1; i < pool; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(up + size_t(i) * C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = f4get(v, k);
+      if ((s[k] >= 0.f) ? (x > bu[k]) : (x < bu[k])) { bu[k] = x; bi[k] = i; }
+    }
+  }
+}
+
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
+                                     const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
+                                     int C, int G, int pool, const float4* __restrict__ bn_const,
+                                     const float* __restrict__ mask, float2* __restrict__ partial) {
+  const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+  const int g = n / (N / G);
+  const int groups = C >> 2;
+  const int nstream = max(1, int(blockDim.x) / groups);
+  for (int item = threadIdx.x; item < groups * nstream; item += blockDim.x) {
+    const int cg = item % groups, stream = item / groups;
+    const int c = 4 * cg;
+    float sc[4], mean[4], rstd[4], mk[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 bc = bn_const[size_t(g) * C + c + k];
+      mk[k] = mask ? mask[size_t(n) * C + c + k] : 1.f;
+      sc[k] = bc.x * mk[k]; mean[k] = bc.z; rstd[k] = bc.w;
+    }
+    if (dy_pooled != nullptr) {
+      const int lout = L / pool;
+      const int per = (lout + chunks - 1) / chunks;
+      const int j0 = chunk * per, j1 = min(lout, j0 + per);
+      for (int j = j0 + stream; j < j1; j += nstream) {
+        const float* up = u + (size_t(n) * L + size_t(j) * pool) * C + c;
+        int bi[4]; float bu[4];
+        window_argmax4(up, C, pool, sc, bi, bu);
+        const float4 dv = *reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + j) * C + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float dy = f4get(dv, k) * mk[k];
+          s1[k] += dy;
+          s2[k] = fmaf(dy, (bu[k] - mean[k]) * rstd[k], s2[k]);
+        }
+      }
+    } else if (chunk == 0 && stream == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int l = argmax[size_t(n) * C + c + k];
+        const float dy = d_gmax[size_t(n) * C + c + k] * mk[k];
+        s1[k] = dy;
+        s2[k] = dy * (u[(size_t(n) * L + l) * C + c + k] - mean[k]) * rstd[k];
+      }
+    }
+    float2* row = partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[k] = make_float2(s1[k], s2[k]);
+  }
+}
+
+// pass 2: per (group, channel) means -> bwd constants {s, mean_dy, mean_dyxhat, 0}; dgamma/dbeta summed over groups.
+__global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int rows_per_clip, int N, int G, int L,
+                                       int C, const float4* __restrict__ bn_const, float4* __restrict__ bwd_const,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int clips = N / G;
+  const double cnt = double(clips) * double(L);
+  double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    double s1 = 0.0, s2 = 0.0;
+    const size_t r0 = size_t(g) * clips * rows_per_clip;
+    for (size_t r = 0; r < size_t(clips) * rows_per_clip; ++r) {
+      const float2 v = partial[(r0 + r) * C + c];
+      s1 += double(v.x);
+      s2 += double(v.y);
+    }
+    bwd_const[size_t(g) * C + c] = make_float4(bn_const[size_t(g) * C + c].x, float(s1 / cnt), float(s2 / cnt), 0.f);
+    tb += s1;
+    tg += s2;
+  }
+  dgamma[c] = float(tg);
+  dbeta[c] = float(tb);
+}
+
+// pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) as fp16 (hi, lo) planes; conv-bias gradient
+// partials sum_positions dU per channel.  grid (N, chunks) over pool windows (incl. the 'valid' tail window, which
+// receives no dy but still the batch-statistics terms).
+__device__ __forceinline__ uint2 pack4h(const __half (&h)[4]) {
+  return make_uint2(uint32_t(__half_as_ushort(h[0])) | (uint32_t(__half_as_ushort(h[1])) << 16),
+                    uint32_t(__half_as_ushort(h[2])) | (uint32_t(__half_as_ushort(h[3])) << 16));
+}
+__global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
+                                   const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
+                                   int C, int G, int pool, const float4* __restrict__ bn_const,
+                                   const float4* __restrict__ bwd_const, const float* __restrict__ mask,
+                                   __half* __restrict__ du_hi, __half* __restrict__ du_lo,
+                                   float* __restrict__ dbias_partial) {
+  const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+  const int g = n / (N / G);
+  const int lout = L / pool;
+  const int wins = (L + pool - 1) / pool;
+  const int per = (wins + chunks - 1) / chunks;
+  const int w0 = chunk * per, w1 = min(wins, w0 + per);
+  const int groups = C >> 2;
+  const int nstream = max(1, int(blockDim.x) / groups);
+  for (int item = threadIdx.x; item < groups * nstream; item += blockDim.x) {
+    const int cg = item % groups, stream = item / groups;
+    const int c = 4 * cg;
+    float sc[4], mean[4], rstd[4], mk[4], bs[4], mdy[4], mdx[4], dg[4], sb[4] = {0, 0, 0, 0};
+    int am[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 bc = bn_const[size_t(g) * C + c + k];
+      const float4 bw = bwd_const[size_t(g) * C + c + k];
+      mk[k] = mask ? mask[size_t(n) * C + c + k] : 1.f;
+      sc[k] = bc.x * mk[k]; mean[k] = bc.z; rstd[k] = bc.w;
+      bs[k] = bw.x; mdy[k] = bw.y; mdx[k] = bw.z;
+      am[k] = (dy_pooled == nullptr) ? argmax[size_t(n) * C + c + k] : -1;
+      dg[k] = (dy_pooled == nullptr) ? d_gmax[size_t(n) * C + c + k] * mk[k] : 0.f;
+    }
+    for (int w = w0 + stream; w < w1; w += nstream) {
+      const int l0 = w * pool;
+      const int wl = min(pool, L - l0);
+      const float* up = u + (size_t(n) * L + l0) * C + c;
+      int bi[4] = {-1, -1, -1, -1};
+      float dyw[4] = {0, 0, 0, 0};
+      if (dy_pooled != nullptr && w < lout) {
+        float bu[4];
+        window_argmax4(up, C, pool, sc, bi, bu);
+        const float4 dv = *reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dyw[k] = f4get(dv, k) * mk[k];
+      }
+      for (int i = 0; i < wl; ++i) {
+        const float4 uv4 = *reinterpret_cast<const float4*>(up + size_t(i) * C);
+        __half h[4], lw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float uv = f4get(uv4, k);
+          const float dy = (dy_pooled != nullptr) ? ((i == bi[k]) ? dyw[k] : 0.f) : ((l0 + i == am[k]) ? dg[k] : 0.f);
+          const float xhat = (uv - mean[k]) * rstd[k];
+          const float du = (uv > 0.f) ? bs[k] * (dy - mdy[k] - xhat * mdx[k]) : 0.f;
+          sb[k] += du;
+          split_f32(du, h[k], lw[k]);
+        }
+        const size_t o = (size_t(n) * L + l0 + i) * C + c;
+        *reinterpret_cast<uint2*>(du_hi + o) = pack4h(h);
+        if (du_lo != nullptr) *reinterpret_cast<uint2*>(du_lo + o) = pack4h(lw);
+      }
+    }
+    float* row = dbias_partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[k] = sb[k];
+  }
+}
+
+// column sums of a (rows, C) fp32 matrix -> out[C]
+__global__ void colsum_kernel(const float* __restrict__ m, size_t rows, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (size_t r = 0; r < rows; ++r) s += double(m[r * C + c]);
+  out[c] = float(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras Adam with global-norm clipping (keras.optimizers.Adam(clipnorm=...))
+// ---------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const double v = double(g[i]);
+    s += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+// p -= lr_t * m / (sqrt(v) + eps) with g' = g * inv_scale * min(1, clipnorm / ||g * inv_scale||)
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, size_t n, const double* __restrict__ sumsq, float inv_scale,
+                                 float clipnorm, float lr_t, float beta1, float beta2, float eps) {
+  float coef = inv_scale;
+  if (clipnorm > 0.f) {
+    const float norm = float(sqrt(*sumsq)) * inv_scale;
+    if (norm > clipnorm) coef *= clipnorm / norm;
+  }
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,
+                             const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                             float* moving_var, float* bn_const, cudaStream_t st) {
+  if (N <= 0 || G <= 0 || N % G != 0 || C <= 0) return set_error(VM_ERR_SHAPE, "bn_stats_finalize: bad shape");
+  bn_stats_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float2*>(partial), rows_per_clip,
+                                                        c_pad, N, G, L, C, gamma, beta, eps, momentum, moving_mean,
+                                                        moving_var, reinterpret_cast<float4*>(bn_const));
+  return check_launch_t("bn_stats_finalize");
+}
+
+int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
+                       const float* mask, __half* out_hi, __half* out_lo, cudaStream_t st) {
+  if (C % 4 != 0 || N % G != 0 || pool <= 0 || L / pool <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
+  const size_t total = size_t(N) * (L / pool) * (C / 4);
+  const unsigned blocks = unsigned(min(size_t(148 * 32), (total + 255) / 256));
+  bn_pool_fwd_kernel<<<blocks, 256, 0, st>>>(u, N, L, C, G, pool, reinterpret_cast<const float4*>(bn_const), mask,
+                                            out_hi, out_lo);
+  return check_launch_t("bn_pool_fwd");
+}
+
+int launch_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask,
+                       float* gmax, int* argmax, cudaStream_t st) {
+  if (N % G != 0 || L < 2) return set_error(VM_ERR_SHAPE, "bn_gmax_fwd: bad shape");
+  bn_gmax_fwd_kernel<<<dim3(N, (C + 31) / 32), dim3(32, 8), 0, st>>>(u, N, L, C, G,
+                                                                    reinterpret_cast<const float4*>(bn_const), mask,
+                                                                    gmax, argmax);
+  return check_launch_t("bn_gmax_fwd");
+}
+
+int launch_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, cudaStream_t st) {
+  if (size_t(C) * 4 > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "dense_fwd: C too large");
+  dense_fwd_kernel<<<N, 128, C * sizeof(float), st>>>(x, N, C, w, b, E, y);
+  return check_launch_t("dense_fwd");
+}
+
+int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db,
+                     float* dx, cudaStream_t st) {
+  dense_bwd_w_kernel<<<C, 64, 0, st>>>(x, dy, N, C, E, dw, db);
+  dense_bwd_x_kernel<<<N, 128, E * sizeof(float), st>>>(dy, w, N, C, E, dx);
+  return check_launch_t("dense_bwd");
+}
+
+int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
+                              const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
+                              float* d_head_b, cudaStream_t st) {
+  if (N <= 0 || E <= 0 || (metric != 0 && metric != 1) || (loss_kind != 1 && loss_kind != 2))
+    return set_error(VM_ERR_SHAPE, "pair_head_loss_bwd: bad arguments");
+  if (size_t(N) * 8 > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "pair_head_loss_bwd: N too large");
+  pair_head_loss_bwd_kernel<<<1, 256, 2 * N * sizeof(float), st>>>(emb, N, E, metric, head_w, head_b, y_true,
+                                                                   loss_kind, loss_scale, d_emb, d_head_w, d_head_b);
+  return check_launch_t("pair_head_loss_bwd");
+}
+
+int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
+                  int G, int pool, const float* bn_const, const float* mask, float* partial /* N*chunks*C float2 */,
+                  int chunks /* partial buffers hold N*chunks*max(1,512/C) rows */, float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo,
+                  float* dbias_partial /* N*chunks*C */, float* dbias, cudaStream_t st) {
+  if (N % G != 0 || chunks <= 0) return set_error(VM_ERR_SHAPE, "bn_bwd: bad shape");
+  if ((dy_pooled == nullptr) == (d_gmax == nullptr)) return set_error(VM_ERR_SHAPE, "bn_bwd: give dy_pooled xor d_gmax");
+  if (C % 4 != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: C must be a multiple of 4");
+  const float4* bc = reinterpret_cast<const float4*>(bn_const);
+  const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;  // must match the kernels' thread layout
+  bn_bwd_reduce_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc, mask,
+                                                        reinterpret_cast<float2*>(partial));
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float2*>(partial), chunks * nstream, N, G,
+                                                      L, C, bc, reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
+  bn_relu_bwd_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc,
+                                                      reinterpret_cast<const float4*>(bwd_const), mask, du_hi, du_lo,
+                                                      dbias_partial);
+  colsum_kernel<<<(C + 63) / 64, 64, 0, st>>>(dbias_partial, size_t(N) * chunks * nstream, C, dbias);
+  return check_launch_t("bn_bwd");
+}
+
+int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
+                     float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st) {
+  if (n == 0) return VM_OK;
+  cudaError_t e = cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "adam: memset");
+  const unsigned blocks = unsigned(min(size_t(148 * 4), (n + 255) / 256));
+  sumsq_kernel<<<blocks, 256, 0, st>>>(g, n, sumsq_scratch);
+  adam_step_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, sumsq_scratch, inv_scale, clipnorm, lr_t, beta1, beta2, eps);
+  return check_launch_t("adam_step");
+}
+
+}  // namespace vm

@@ -1,0 +1,295 @@
+// Weight gradients of the convolutions (training backward).
+//
+// wgrad3 (blocks 2-4):  dW[tap][ci][co] = sum_{n,p} X[n][p + tap - 1][ci] * dU[n][p][co]
+//   A GEMM whose reduction dimension is the POSITION axis, so both operands are "MN-major" for the tensor core:
+//   a shared-memory tile [position rows][64 channels = 128 B] as TMA writes it (SWIZZLE_128B) is read by tcgen05
+//   with a_major = b_major = MN (rows are the K dimension, 8-row groups 1024 B apart, the two 64-channel atoms
+//   of a 128-wide operand LBO apart).  The three taps are, again, the same X tile read through descriptors shifted
+//   by `tap` rows.  D[tap] = 128 ci lanes x 128 co columns fp32 in TMEM (3 x 128 columns), accumulated over the
+//   CTA's slice of (clip, 64-position chunk) steps, then written to a per-split partial buffer that
+//   wgrad_reduce sums deterministically (no atomics).
+//   Operands are fp16 (hi, lo) planes; products = 3 gives fp32-grade gradients, products = 1 plain fp16.
+//
+// wgrad1 (block 1):  dW1[k][co] = sum_{n,p} x[n][p + k - 15] * dU1[n][p][co]   (CUDA cores, fp32; 4% of the FLOPs)
+#include "vm_common.cuh"
+#include "vm_kernels.h"
+
+namespace vm {
+
+namespace wg {
+constexpr int kPosChunk = 64;                    // positions per pipeline stage (4 MMA K-steps of 16)
+constexpr int kXRows = 72;                       // 66 halo rows (p0-1 .. p0+64) padded to a multiple of 8
+constexpr int kXHalfBytes = kXRows * 128;        // one 64-channel atom of the X tile
+constexpr int kUHalfBytes = kPosChunk * 128;     // one 64-channel atom of the dU tile
+constexpr int kXPlaneBytes = 2 * kXHalfBytes;    // 128 ci
+constexpr int kUPlaneBytes = 2 * kUHalfBytes;    // 128 co
+constexpr int kStageBytes = 2 * kXPlaneBytes + 2 * kUPlaneBytes;  // hi + lo of both operands = 69632
+constexpr int kStages = 3;
+constexpr int kThreads = 192;                    // warp 0 TMA producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+}  // namespace wg
+
+struct __align__(8) WgradBarriers {
+  uint64_t full[wg::kStages], empty[wg::kStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+// instruction descriptor with both operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
+  return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(wg::kThreads, 1)
+wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+              const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUtensorMap tm_ul,
+              const Wgrad3Params p) {
+  using namespace wg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = (p.products == 3) ? 2 : 1;
+
+  // work item: (ci slab, co tile, split)
+  const int combo = blockIdx.x % p.ncombo;
+  const int split = blockIdx.x / p.ncombo;
+  const int ci0 = (combo / p.nco_tiles) * 128;
+  const int co0 = (combo % p.nco_tiles) * 128;
+  const int steps_total = p.N * p.nchunk;                 // (clip, 64-position chunk) pairs
+  const int per = (steps_total + p.nsplit - 1) / p.nsplit;
+  const int s0 = split * per, s1 = min(steps_total, s0 + per);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_xh); tma_prefetch_desc(&tm_uh);
+      uint32_t it = 0;
+      for (int st = s0; st < s1; ++st, ++it) {
+        const int n = st / p.nchunk, p0 = (st % p.nchunk) * kPosChunk;
+        const int s = it % kStages;
+        mbar_wait(&bars->empty[s], ((it / kStages) & 1) ^ 1);
+        uint8_t* base = smem + s * kStageBytes;
+        mbar_arrive_expect_tx(&bars->full[s], nplanes * (kXPlaneBytes + kUPlaneBytes));
+        for (int pl = 0; pl < nplanes; ++pl) {
+          uint8_t* xb = base + pl * kXPlaneBytes;
+          uint8_t* ub = base + 2 * kXPlaneBytes + pl * kUPlaneBytes;
+          const CUtensorMap* mx = pl ? &tm_xl : &tm_xh;
+          const CUtensorMap* mu = pl ? &tm_ul : &tm_uh;
+          tma_load_3d(xb, mx, &bars->full[s], ci0, p0 - 1, n);
+          tma_load_3d(xb + kXHalfBytes, mx, &bars->full[s], ci0 + 64, p0 - 1, n);
+          tma_load_3d(ub, mu, &bars->full[s], co0, p0, n);
+          tma_load_3d(ub + kUHalfBytes, mu, &bars->full[s], co0 + 64, p0, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16_mn(128, 128);
+      uint32_t it = 0;
+      for (int st = s0; st < s1; ++st, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&bars->full[s], (it / kStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t base = smem_u32(smem + s * kStageBytes);
+        const uint32_t xh = base, xl = base + kXPlaneBytes;
+        const uint32_t uh = base + 2 * kXPlaneBytes, ul = uh + kUPlaneBytes;
+        for (int tap = 0; tap < 3; ++tap) {
+          const uint32_t d = tmem_base + tap * 128;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t arow = (tap + 16 * kk) * 128, brow = (16 * kk) * 128;
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
+                     make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, acc);
+            if (nplanes == 2) {
+              umma_f16(d, make_smem_desc(xl + arow, kXHalfBytes, 1024, kLayoutSW128),
+                       make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
+              umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
+                       make_smem_desc(ul + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
+            }
+          }
+        }
+        umma_commit(&bars->empty[s]);
+      }
+      umma_commit(&bars->done);
+    }
+  } else {
+    // epilogue: TMEM lane = ci row; write partial[split][tap][ci][co]
+    const int q = warp & 3;
+    mbar_wait(&bars->done, 0);
+    tc_fence_after_sync();
+    const int ci = ci0 + q * 32 + lane;
+    const bool any = s1 > s0;
+    for (int tap = 0; tap < 3; ++tap) {
+      float* row = p.partial + ((size_t(split) * 3 + tap) * p.cin + ci) * p.cout + co0;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + tap * 128 + g * 32, v);
+        if (ci < p.cin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (co0 + g * 32 + j < p.cout) row[g * 32 + j] = any ? v[j] : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dW[i] = scale * sum_s partial[s][i]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, size_t n, float scale,
+                                    float* __restrict__ out) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += partial[size_t(k) * n + i];
+    out[i] = s * scale;
+  }
+}
+
+int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, const __half* du_lo, int N, int L,
+                  int cin, int cout, int products, float* partial, size_t partial_bytes, float* dw,
+                  cudaStream_t stream) {
+  using namespace wg;
+  if (N <= 0 || L <= 0 || cin % 8 != 0 || cout % 8 != 0) return set_error(VM_ERR_SHAPE, "wgrad3: bad shape");
+  if (products == 3 && (x_lo == nullptr || du_lo == nullptr)) return set_error(VM_ERR_SHAPE, "wgrad3: lo planes required");
+  Wgrad3Params p{};
+  p.N = N; p.L = L; p.cin = cin; p.cout = cout; p.products = products;
+  p.nchunk = (L + kPosChunk - 1) / kPosChunk;
+  p.nco_tiles = (cout + 127) / 128;
+  p.ncombo = ((cin + 127) / 128) * p.nco_tiles;
+  const size_t wsize = size_t(3) * cin * cout;
+  int nsplit = max(1, (2 * num_sms()) / p.ncombo);
+  nsplit = min(nsplit, N * p.nchunk);
+  while (nsplit > 1 && size_t(nsplit) * wsize * 4 > partial_bytes) --nsplit;
+  if (size_t(nsplit) * wsize * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad3: partial buffer too small");
+  p.nsplit = nsplit;
+  p.partial = partial;
+
+  CUtensorMap xh, xl, uh, ul;
+  const uint64_t xdims[3] = {uint64_t(cin), uint64_t(L), uint64_t(N)};
+  const uint64_t xstr[2] = {uint64_t(cin) * 2, uint64_t(L) * cin * 2};
+  const uint32_t xbox[3] = {64, kXRows, 1};
+  const uint64_t udims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+  const uint64_t ustr[2] = {uint64_t(cout) * 2, uint64_t(L) * cout * 2};
+  const uint32_t ubox[3] = {64, kPosChunk, 1};
+  int rc;
+  if ((rc = make_tensor_map(&xh, x_hi, 3, xdims, xstr, xbox, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&xl, products == 3 ? x_lo : x_hi, 3, xdims, xstr, xbox, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&uh, du_hi, 3, udims, ustr, ubox, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&ul, products == 3 ? du_lo : du_hi, 3, udims, ustr, ubox, VM_SWIZZLE_128B))) return rc;
+
+  cudaError_t e = cudaFuncSetAttribute(wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad3: cudaFuncSetAttribute");
+  wgrad3_kernel<<<p.ncombo * nsplit, kThreads, kSmemBytes, stream>>>(xh, xl, uh, ul, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad3: launch");
+  const unsigned blocks = unsigned(min(size_t(148 * 8), (wsize + 255) / 256));
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, nsplit, wsize, 1.0f, dw);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad3: reduce launch");
+  return VM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad1: block = 128 threads; thread (k8 = tid / 32, c4 = tid % 32) accumulates taps 8*k8..+7 x channels 4*c4..+3.
+// grid (N, position chunks); per-CTA partial [32][cout] -> deterministic reduce.
+// ---------------------------------------------------------------------------------------------
+constexpr int kW1Chunk = 1024;  // positions per CTA
+constexpr int kW1Sub = 64;      // positions per shared-memory sub-tile
+
+__global__ void __launch_bounds__(128)
+wgrad1_kernel(const float* __restrict__ x, const __half* __restrict__ du_hi, const __half* __restrict__ du_lo, int N,
+              int L, int cout, int co_base, float* __restrict__ partial) {
+  __shared__ float xs[kW1Chunk + 32];
+  __shared__ __align__(16) float us[kW1Sub][128];
+  const int n = blockIdx.x, chunk = blockIdx.y;
+  const int p0 = chunk * kW1Chunk;
+  const int plen = min(kW1Chunk, L - p0);
+  const int k8 = threadIdx.x >> 5, c4 = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kW1Chunk + 31; i += 128) {
+    const int e = p0 - 15 + i;
+    xs[i] = (e >= 0 && e < L) ? x[size_t(n) * L + e] : 0.f;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  for (int sp = 0; sp < plen; sp += kW1Sub) {
+    __syncthreads();
+    const int sl = min(kW1Sub, plen - sp);
+    for (int i = threadIdx.x; i < kW1Sub * 128; i += 128) {
+      const int r = i >> 7, c = i & 127;
+      float v = 0.f;
+      if (r < sl && co_base + c < cout) {
+        const size_t o = (size_t(n) * L + p0 + sp + r) * cout + co_base + c;
+        v = __half2float(du_hi[o]) + (du_lo ? __half2float(du_lo[o]) : 0.f);
+      }
+      us[r][c] = v;
+    }
+    __syncthreads();
+    // sliding window of 8 samples: position r uses x[p + 8*k8 + a - 15], a = 0..7  ->  xs[sp + r + 8*k8 + a]
+    float xr[8];
+#pragma unroll
+    for (int a = 0; a < 7; ++a) xr[a + 1] = xs[sp + 8 * k8 + a];
+    for (int r = 0; r < sl; ++r) {
+#pragma unroll
+      for (int a = 0; a < 7; ++a) xr[a] = xr[a + 1];
+      xr[7] = xs[sp + r + 8 * k8 + 7];
+      const float4 d = *reinterpret_cast<const float4*>(&us[r][4 * c4]);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        acc[a][0] = fmaf(xr[a], d.x, acc[a][0]);
+        acc[a][1] = fmaf(xr[a], d.y, acc[a][1]);
+        acc[a][2] = fmaf(xr[a], d.z, acc[a][2]);
+        acc[a][3] = fmaf(xr[a], d.w, acc[a][3]);
+      }
+    }
+  }
+  float* out = partial + (size_t(n) * gridDim.y + chunk) * 32 * cout;
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int co = co_base + 4 * c4 + b;
+      if (co < cout) out[size_t(8 * k8 + a) * cout + co] = acc[a][b];
+    }
+}
+
+int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
+                  size_t partial_bytes, float* dw, cudaStream_t stream) {
+  if (N <= 0 || L <= 0 || cout <= 0) return set_error(VM_ERR_SHAPE, "wgrad1: bad shape");
+  const int chunks = (L + kW1Chunk - 1) / kW1Chunk;
+  const size_t wsize = size_t(32) * cout;
+  if (size_t(N) * chunks * wsize * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad1: partial buffer too small");
+  for (int co_base = 0; co_base < cout; co_base += 128)
+    wgrad1_kernel<<<dim3(N, chunks), 128, 0, stream>>>(x, du_hi, du_lo, N, L, cout, co_base, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: launch");
+  const unsigned blocks = unsigned((wsize + 255) / 256);
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, N * chunks, wsize, 1.0f, dw);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: reduce launch");
+  return VM_OK;
+}
+
+}  // namespace vm
