@@ -105,6 +105,22 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
                    const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
                    void* stream);
 
+/* ---- fused preprocessing (voicemap/utils.py:22-34, 88-101) ------------------------------------------------
+ * The reference decimates raw 16 kHz clips on the host (instances[:, ::downsampling, :]) and whitens them: per-clip
+ * mean removal, then ONE scale rms / sqrt(mean(batch^2)) per whiten() call, taken over the un-centred decimated
+ * batch.  vm_preprocess_stats computes mean (N) and scale (N; equal inside each of the G groups = whiten() calls)
+ * in double precision; `scale` must hold N floats followed by 4*N + 4 floats of scratch.
+ * vm_encoder_fwd_raw runs the encoder on raw audio x (N, T) fp32 with the decimation (strided read) and the
+ * whitening affine fused into block 1's operand producer: L = ceil(T / downsampling) samples enter the network.
+ * whiten_groups = 0 disables whitening.  `workspace` must hold vm_encoder_workspace_bytes(N, L, filters) +
+ * vm_preprocess_scratch_bytes(N) bytes. */
+size_t vm_preprocess_scratch_bytes(int N);
+int vm_preprocess_stats(const float* x, int N, int T, int downsampling, int G, float rms, float* mean, float* scale,
+                        void* stream);
+int vm_encoder_fwd_raw(const float* x, int N, int T, int downsampling, int whiten_groups, float rms, int filters,
+                       const void* const* wpack, const float* const* epi, const float* dense_w, const float* dense_b,
+                       int E, void* workspace, float* emb, int precision, void* stream);
+
 /* =============================================================================================================
  * Training (SURVEY.md 8(a) a3 train mode, a4, a13): what Keras' fit_generator does implicitly for
  * experiments/train_siamese.py:56-65 / train_classifier.py:114-120.  "BN group" = one application of the shared
@@ -116,7 +132,7 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
 int vm_pack_conv1_raw(const float* kernel, const float* bias, int cout, void* wpack, float* epi, void* stream);
 int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout, void* wpack, float* epi,
                       void* stream);
-/* dgrad operand: tap-flipped, channel-transposed kernel in the conv3 layout with (cin' = Cout, cout' = Cin);
+/* dgrad operand: tap-flipped, channel-transposed kernel (bf16 planes) in the conv3 layout with (cin' = Cout, cout' = Cin);
  * wpack holds vm_conv3_wpack_bytes(cout, cin) bytes, epi vm_epi_bytes(cin). */
 int vm_pack_conv3_dgrad(const float* kernel /* (3, Cin, Cout) */, int cin, int cout, void* wpack, float* epi,
                         void* stream);
@@ -125,7 +141,7 @@ int vm_pack_conv3_dgrad(const float* kernel /* (3, Cin, Cout) */, int cin, int c
  * partial rows stat_partial (N * 2*ceil(L/256), Cpad) float2 (may be NULL). */
 int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
                      float* stat_partial, int precision, void* stream);
-/* linear = 0: as above for blocks 2-4.  linear = 1: plain convolution output (dgrad: in = dU planes, wpack from
+/* linear = 0: as above for blocks 2-4.  linear = 1: plain convolution output (dgrad: in = dU bf16 planes, wpack from
  * vm_pack_conv3_dgrad, out = dX fp32 (N, L, Cin)). */
 int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
                      const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
@@ -137,9 +153,11 @@ int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
                          float* moving_var, float* bn_const, void* stream);
-/* y = bn(u) * mask -> MaxPool1D(pool) -> planes (N, L/pool, C).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
+/* y = bn(u) * mask -> MaxPool1D(pool) -> fp16 planes (N, L/pool, C) for the next block's forward conv, and
+ * (optional, both or neither) the same values as bf16 planes for vm_wgrad3 (the tensor core cannot mix fp16 with
+ * bf16 operands).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
 int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                   uint16_t* out_hi, uint16_t* out_lo, void* stream);
+                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* bf_hi, uint16_t* bf_lo, void* stream);
 /* block 4: bn -> MaxPool1D(2) -> GlobalMaxPool1D merged; gmax (N, C), argmax (N, C) un-pooled position. */
 int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
                    int32_t* argmax, void* stream);
@@ -152,13 +170,15 @@ int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const floa
 int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
                  void* stream);
 /* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax + argmax
- * (block 4).  Outputs: dgamma, dbeta, dbias (C), dU planes (N, L, C).  scratch_f2 / scratch_f hold
+ * (block 4).  Outputs: dgamma, dbeta, dbias (C), dU as bf16 (hi, lo) planes (N, L, C) -- gradients are carried in
+ * bf16 pairs (fp32 exponent range, ~16 significant bits), so no loss scaling is required.  scratch_f2 / scratch_f hold
  * N * chunks * max(1, 512/C) rows of C float2 / float; bwd_const (G, C) float4. */
 int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
               int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
               float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
               float* dbias, void* stream);
-/* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; partial: scratch. */
+/* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; x_* and du_* are bf16 planes;
+ * partial: scratch. */
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
               int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream);
 /* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co]. */

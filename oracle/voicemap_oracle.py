@@ -336,7 +336,7 @@ def bn_moving_update(moving_mean, moving_var, mean, var, n, momentum=BN_MOMENTUM
             moving_var * momentum + var_unbiased * (1.0 - momentum))
 
 
-def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None):
+def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=None):
     """Train-mode encoder on torch tensors (autograd-capable).  x (N, L, 1); P: dict name -> tensor.
     dropout_masks: optional list of 4 keep-masks (N, 1, C) already scaled by 1/(1-p) (SpatialDropout1D,
     voicemap/models.py:18,24,29,34).  Returns emb and per-block (mean, var, count)."""
@@ -344,6 +344,9 @@ def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None):
     stats = []
     for i in range(1, 5):
         h = conv1d_same_relu(h, P[f"conv{i}_kernel"], P[f"conv{i}_bias"])
+        if keep is not None:          # expose d loss / d u (post-ReLU, pre-BN) to the kernel-level tests
+            h.retain_grad()
+            keep.append(h)
         n_red = h.shape[0] * h.shape[1]
         h, m, v = batchnorm_train(h, P[f"bn{i}_gamma"], P[f"bn{i}_beta"])
         stats.append((m.detach(), v.detach(), n_red))
@@ -367,8 +370,9 @@ def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_cro
          for k, v in params.items()}
     hw = _t(np.asarray(head_w, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
     hb = _t(np.asarray(head_b, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
-    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0])
-    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1])
+    k1, k2 = [], []
+    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0], keep=k1)
+    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1], keep=k2)
     diff = e1 - e2
     if distance_metric == "uniform_euclidean":
         d = torch.sqrt(torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=0.0))
@@ -391,7 +395,9 @@ def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_cro
     return dict(loss=float(lv.item()), prob=p.detach().numpy(), grads=grads,
                 head_w_grad=hw.grad.numpy().copy(), head_b_grad=hb.grad.numpy().copy(),
                 stats=[[(m.numpy(), v.numpy(), n) for (m, v, n) in s] for s in (s1, s2)],
-                e1=e1.detach().numpy(), e2=e2.detach().numpy())
+                e1=e1.detach().numpy(), e2=e2.detach().numpy(),
+                u=[[h.detach().numpy() for h in k] for k in (k1, k2)],
+                du=[[h.grad.numpy().copy() for h in k] for k in (k1, k2)])
 
 
 def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dtype=torch.float64,

@@ -239,3 +239,67 @@ def test_unsupported_configuration_is_an_error_not_a_fallback():
     eng.set_weights(params)
     with pytest.raises(_lib.VoicemapB200Error):
         eng.forward(torch.zeros(2, 4000, device="cuda"))
+
+
+@pytest.mark.parametrize("n,t,ds", [(6, 48000, 4), (3, 16001, 4), (4, 12000, 1)])
+def test_fused_preprocessing_matches_host_preprocessing(stress_params, n, t, ds):
+    """predict_raw = predict(preprocess_instances(ds)(x)): decimation x[:, ::ds] and whitening with the reference's
+    batch-global scale (voicemap/utils.py:22-34, 88-101) fused into block 1."""
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+    rng = np.random.default_rng(t)
+    raw = (rng.normal(0.01, 0.05, (n, t, 1)) * rng.uniform(0.3, 3.0, (n, 1, 1))).astype(np.float32)
+    enc = get_baseline_convolutional_encoder(128, 64)
+    enc.set_named_weights(stress_params)
+    got = enc.predict_raw(raw, downsampling=ds)
+    pre = O.preprocess_instances(ds)(raw.astype(np.float64))
+    assert pre.shape[1] == -(-t // ds)
+    ref = O.encoder_forward(pre, stress_params, torch.float32)
+    assert _per_clip(got, ref) <= TOL
+    assert _per_clip(got, enc.predict(pre)) <= 2e-5          # device preprocessing == host preprocessing + predict
+    nowhite = enc.predict_raw(raw, downsampling=ds, whitening=False)
+    assert _per_clip(nowhite, O.encoder_forward(raw[:, ::ds], stress_params, torch.float32)) <= TOL
+
+
+def test_batched_n_shot_evaluation_equals_reference_loop(stress_params):
+    """many tasks per launch, identical count of solved tasks for the same task sequence."""
+    import pandas as pd
+    from voicemap_b200 import utils
+    from voicemap_b200.librispeech import LibriSpeechDataset
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    rng = np.random.default_rng(0)
+    rows, audio = [], {}
+    for spk in range(8):
+        for j in range(4):
+            path = f"/fake/{spk}/{j}"
+            length = int(16000 * 0.3 + rng.integers(0, 2000))
+            t = np.arange(length) / 16000.0
+            audio[path] = 0.05 * np.sin(2 * np.pi * (120 + 35 * spk) * t + rng.uniform(0, 6)) + 0.01 * rng.normal(size=length)
+            rows.append(dict(id=spk, sex="M", subset="s", minutes=1.0, name=str(spk), filepath=path, length=length,
+                             seconds=length / 16000.0))
+    ds = LibriSpeechDataset("s", 0.25, stochastic=False, index=pd.DataFrame(rows), reader=lambda p: (audio[p], 16000))
+    enc = get_baseline_convolutional_encoder(128, 64, dropout=0.0)
+    enc.set_named_weights(stress_params)
+    sia = build_siamese_net(enc, (1000, 1))
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4))
+    for n, k, kind in ((1, 5, "siamese"), (2, 3, "siamese")):
+        np.random.seed(7)
+        a = utils.n_shot_task_evaluation(sia, ds, pre, 12, n, k, network_type=kind)
+        np.random.seed(7)
+        b = utils.n_shot_task_evaluation_batched(sia, ds, pre, 12, n, k, network_type=kind, tasks_per_launch=5)
+        assert a == b
+
+
+def test_reference_checkpoint_weights_fixture():
+    """Real trained weights (the reference's shipped Keras checkpoint, read by voicemap_b200/keras_hdf5.py) through
+    the CUDA path vs the oracle's committed outputs: filters=32, embedding 128, weighted_l1 head."""
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "checkpoint_f32.npz"))
+    enc = get_baseline_convolutional_encoder(32, 128)
+    enc.set_named_weights({k[2:]: z[k] for k in z.files if k.startswith("w_")})
+    got = enc.predict(z["x"])
+    assert _per_clip(got, z["emb32"]) <= TOL and _per_clip(got, z["emb64"]) <= TOL
+    sia = build_siamese_net(enc, (12000, 1), "weighted_l1")
+    sia.head_weights["head_kernel"] = z["head_kernel"].copy()
+    sia.head_weights["head_bias"] = z["head_bias"].copy()
+    prob = sia.predict([z["x"][:3], z["x"][3:]])
+    assert np.abs(prob - z["prob64"]).max() < 1e-4

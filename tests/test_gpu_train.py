@@ -1,0 +1,205 @@
+"""Training-path parity (GPU box): train-mode forward, every gradient, BN moving statistics and the Keras-Adam update
+of one siamese / classifier step against the autograd oracle (oracle/voicemap_oracle.py, fp64)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import voicemap_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return np.abs(a - ref).max() / (np.abs(ref).max() + 1e-30)
+
+
+def _grad_errors(grads, ref_grads):
+    """max|d| per tensor relative to max(|ref tensor|, 1e-3 * the largest gradient entry of the whole step): a tensor
+    whose true gradient vanishes (the embedding bias of a siamese net cancels in e1 - e2) is judged on the global
+    scale instead of dividing by ~0."""
+    floor = 1e-3 * max(np.abs(np.asarray(g)).max() for g in ref_grads.values())
+    return {k: np.abs(np.asarray(grads[k], np.float64).reshape(np.asarray(g).shape) - g).max() /
+            max(np.abs(g).max(), floor) for k, g in ref_grads.items()}
+
+
+def _make(filters, emb, loss, metric="uniform_euclidean", seed=0, dropout=0.0):
+    from voicemap_b200.keras_compat import Adam
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    from voicemap_b200.training import TrainEngine
+    params = O.init_encoder_params(filters, emb, seed=seed, randomize_bn=False, random_bias=True)
+    rng = np.random.default_rng(seed + 1)
+    for i in range(1, 5):   # non-trivial gamma / beta (incl. negative gamma)
+        params[f"bn{i}_gamma"] = rng.uniform(-1.2, 1.5, params[f"bn{i}_gamma"].shape).astype(np.float32)
+        params[f"bn{i}_beta"] = rng.normal(0, 0.2, params[f"bn{i}_beta"].shape).astype(np.float32)
+    enc = get_baseline_convolutional_encoder(filters, emb, dropout=dropout)
+    enc.set_named_weights(params)
+    sia = build_siamese_net(enc, (1024, 1), metric)
+    if metric == "uniform_euclidean":
+        sia.head_weights["head_kernel"][:] = 0.05
+        sia.head_weights["head_bias"][:] = -0.3
+    opt = Adam(clipnorm=1.0)
+    sia.compile(loss=loss, optimizer=opt)
+    tr = TrainEngine(sia, opt, sia.loss)
+    return params, sia, tr
+
+
+@pytest.mark.parametrize("filters,emb,loss,metric", [(32, 16, "binary_crossentropy", "uniform_euclidean"),
+                                                     (128, 64, "contrastive_loss", "uniform_euclidean"),
+                                                     (64, 32, "binary_crossentropy", "weighted_l1")])
+def test_siamese_step_forward_and_gradients(filters, emb, loss, metric):
+    params, sia, tr = _make(filters, emb, loss, metric)
+    n, length = 4, 1024
+    x1 = O.synthetic_clips(n, length, seed=11)
+    x2 = O.synthetic_clips(n, length, seed=12)
+    y = np.array([0, 0, 1, 1], dtype=np.float32)
+    hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
+    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=loss, distance_metric=metric)
+    lv, acc = tr.siamese_step(x1, x2, y, apply=False)
+    torch.cuda.synchronize()
+    # train-mode forward
+    emb_gpu = tr.embv.cpu().numpy()
+    assert _rel(emb_gpu[:n], ref["e1"]) < 1e-4 and _rel(emb_gpu[n:], ref["e2"]) < 1e-4
+    assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    # batch statistics per branch
+    for branch in range(2):
+        for b in range(4):
+            m, v, _ = ref["stats"][branch][b]
+            bnc = tr.bnc[b][branch].cpu().numpy()
+            assert _rel(bnc[:, 2], m) < 1e-4
+            assert _rel(1.0 / np.square(bnc[:, 3]) - O.BN_EPS, v) < 1e-3
+    # gradients
+    # kernel-level diagnostics: block-1 activations and their gradients (the last dU left in the buffer is block 1's)
+    u1 = tr.U[0].cpu().numpy()
+    u1_ref = np.concatenate([ref["u"][0][0], ref["u"][1][0]], axis=0)
+    nu = u1.size
+    bits = tr.dU[:, :nu].cpu().numpy().view(np.uint16).astype(np.uint32) << 16
+    du1 = (bits[0].view(np.float32) + bits[1].view(np.float32)).reshape(u1.shape) / tr.loss_scale
+    du1_ref = np.concatenate([ref["du"][0][0], ref["du"][1][0]], axis=0)
+    err = np.abs(du1 - du1_ref)
+    print("U1 rel err", _rel(u1, u1_ref), "dU1 rel err", err.max() / np.abs(du1_ref).max(),
+          "worst (n, l, c)", np.unravel_index(err.argmax(), err.shape),
+          "bad entries", int((err > 1e-4 * np.abs(du1_ref).max()).sum()), "of", err.size)
+    grads = tr.gradients()
+    refg = dict(ref["grads"], head_kernel=ref["head_w_grad"], head_bias=ref["head_b_grad"])
+    worst = _grad_errors(grads, refg)
+    print({k: f"{v:.2e}" for k, v in worst.items()})
+    assert max(worst.values()) < 2e-3, worst
+
+
+def test_moving_statistics_and_adam_update():
+    params, sia, tr = _make(32, 16, "binary_crossentropy")
+    n, length = 4, 1024
+    x1, x2 = O.synthetic_clips(n, length, seed=21), O.synthetic_clips(n, length, seed=22)
+    y = np.array([0, 1, 0, 1], dtype=np.float32)
+    hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
+    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y)
+    before = {k: v.clone() for k, v in tr.p.items()}
+    tr.siamese_step(x1, x2, y, apply=True)
+    torch.cuda.synchronize()
+    # moving statistics: two sequential Keras updates (branch 1 then branch 2)
+    for b in range(4):
+        mm, mv = params[f"bn{b + 1}_mean"].astype(np.float64), params[f"bn{b + 1}_var"].astype(np.float64)
+        for branch in range(2):
+            m, v, cnt = ref["stats"][branch][b]
+            mm, mv = O.bn_moving_update(mm, mv, m, v, cnt)
+        assert _rel(tr.moving[f"bn{b + 1}_mean"].cpu().numpy(), mm) < 1e-4
+        assert _rel(tr.moving[f"bn{b + 1}_var"].cpu().numpy(), mv) < 1e-4
+    # Adam(clipnorm=1) arithmetic: oracle update applied to the SAME gradients the device produced (gradient parity
+    # is checked above; the first Adam step is sign-like, so it must not be compared across gradient sources)
+    p = {k: before[k].cpu().numpy().astype(np.float64) for k in before}
+    g = {k: v.astype(np.float64) for k, v in tr.gradients().items()}
+    m0 = {k: np.zeros_like(v) for k, v in p.items()}
+    v0 = {k: np.zeros_like(v) for k, v in p.items()}
+    O.keras_adam_step(p, g, m0, v0, t=1, clipnorm=1.0)
+    for k in p:
+        step_ref = p[k] - before[k].cpu().numpy()
+        step_gpu = tr.p[k].cpu().numpy() - before[k].cpu().numpy()
+        assert np.abs(step_gpu - step_ref).max() <= 1e-3 * np.abs(step_ref).max() + 1e-8, k  # lr = 1e-3
+    # second step exercises the moment recursion and the bias-corrected learning rate
+    tr.siamese_step(x1, x2, y, apply=False)
+    g2 = {k: v.astype(np.float64) for k, v in tr.gradients().items()}
+    prev = {k: v.clone() for k, v in tr.p.items()}
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    p2 = {k: prev[k].cpu().numpy().astype(np.float64) for k in prev}
+    O.keras_adam_step(p2, g2, m0, v0, t=2, clipnorm=1.0)
+    for k in p2:
+        step_ref = p2[k] - prev[k].cpu().numpy()
+        step_gpu = tr.p[k].cpu().numpy() - prev[k].cpu().numpy()
+        assert np.abs(step_gpu - step_ref).max() <= 1e-3 * np.abs(step_ref).max() + 1e-8, k  # lr = 1e-3
+
+
+def test_classifier_step_gradients():
+    from voicemap_b200.keras_compat import Adam, Dense
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+    from voicemap_b200.training import TrainEngine
+    filters, emb, classes, n, length = 32, 16, 7, 6, 1024
+    params = O.init_encoder_params(filters, emb, seed=5, random_bias=True)
+    clf = get_baseline_convolutional_encoder(filters, emb, (length, 1), dropout=0.0)
+    clf.set_named_weights(params)
+    clf.add(Dense(classes, activation="softmax"))
+    opt = Adam(clipnorm=1.0)
+    clf.compile(loss="categorical_crossentropy", optimizer=opt, metrics=["accuracy"])
+    tr = TrainEngine(clf, opt, clf.loss)
+    x = O.synthetic_clips(n, length, seed=31)
+    y = np.eye(classes, dtype=np.float32)[np.arange(n) % classes]
+    ref = O.classifier_train_step_grads(params, clf.weights["head_kernel"], clf.weights["head_bias"], x, y)
+    lv, acc = tr.classifier_step(x, y, apply=False)
+    torch.cuda.synchronize()
+    assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    grads = tr.gradients()
+    worst = _grad_errors(grads, dict(ref["grads"], head_kernel=ref["head_kernel_grad"], head_bias=ref["head_bias_grad"]))
+    print({k: f"{v:.2e}" for k, v in worst.items()})
+    assert max(worst.values()) < 2e-3, worst
+
+
+def test_dropout_mask_semantics():
+    """SpatialDropout1D: one keep/drop decision per (clip, channel), scaled by 1/(1-p); explicit masks make the
+    train-mode forward comparable with the oracle."""
+    params, sia, tr = _make(32, 16, "binary_crossentropy", dropout=0.25)
+    n, length = 4, 1024
+    x1, x2 = O.synthetic_clips(n, length, seed=41), O.synthetic_clips(n, length, seed=42)
+    y = np.array([0, 0, 1, 1], dtype=np.float32)
+    rng = np.random.default_rng(0)
+    masks = [(rng.random((2 * n, c)) < 0.75).astype(np.float32) / 0.75 for c in tr.channels]
+    dm = [torch.from_numpy(m).cuda() for m in masks]
+    om1 = [torch.from_numpy(m[:n, None, :]).double() for m in masks]
+    om2 = [torch.from_numpy(m[n:, None, :]).double() for m in masks]
+    hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
+    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, dropout_masks=(om1, om2))
+    lv, _ = tr.siamese_step(x1, x2, y, apply=False, masks=dm)
+    torch.cuda.synchronize()
+    assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert max(_grad_errors(tr.gradients(), ref["grads"]).values()) < 2e-3
+    tr._draw_masks(8)
+    m = tr.masks[0].cpu().numpy()
+    assert set(np.unique(m)).issubset({0.0, np.float32(1 / 0.75)}) and m.shape == (8, 32)
+
+
+def test_fit_generator_reduces_loss(tmp_path):
+    """A few epochs on a separable toy problem through the Keras-style API incl. callbacks."""
+    from voicemap_b200.keras_compat import Adam, CSVLogger
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    rng = np.random.default_rng(0)
+    length, n = 1024, 16
+
+    def gen():
+        while True:
+            t = np.arange(length)[None, :]
+            f1 = rng.uniform(0.02, 0.04, (n, 1)); f2 = rng.uniform(0.2, 0.3, (n, 1))
+            cls_a = rng.integers(0, 2, n); same = (np.arange(n) < n // 2)
+            cls_b = np.where(same, cls_a, 1 - cls_a)
+            fa = np.where(cls_a[:, None] == 0, f1, f2); fb = np.where(cls_b[:, None] == 0, f1, f2)
+            xa = 0.05 * np.sin(2 * np.pi * fa * t + rng.uniform(0, 6, (n, 1)))
+            xb = 0.05 * np.sin(2 * np.pi * fb * t + rng.uniform(0, 6, (n, 1)))
+            yield [xa[:, :, None], xb[:, :, None]], (~same).astype(np.float64)[:, None]
+
+    enc = get_baseline_convolutional_encoder(16, 8, dropout=0.0)
+    sia = build_siamese_net(enc, (length, 1))
+    sia.compile(loss="binary_crossentropy", optimizer=Adam(lr=3e-3, clipnorm=1.0), metrics=["accuracy"])
+    hist = sia.fit_generator(gen(), steps_per_epoch=15, epochs=4, validation_data=gen(), validation_steps=2, verbose=0,
+                             callbacks=[CSVLogger(str(tmp_path / "log.csv"))])
+    assert hist[-1]["loss"] < hist[0]["loss"]
+    assert "val_loss" in hist[-1] and "acc" in hist[-1]
+    assert np.isfinite(sia.predict(next(gen())[0])).all()

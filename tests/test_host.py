@@ -235,3 +235,17 @@ def test_nshot_callback_writes_logs_and_checkpoint_uses_them(tmp_path):
     log.on_epoch_end(0, {"loss": 1.0, "val_1-shot_acc": 0.5})
     log.on_train_end()
     assert "val_1-shot_acc" in open(tmp_path / "log.csv").read()
+
+
+def test_keras_hdf5_reader_on_synthetic_file(tmp_path):
+    """The pure-Python HDF5 reader is exercised on the reference's real checkpoint when building the golden fixture
+    (tests/golden/make_checkpoint_fixture.py); here: the committed fixture carries the survey's known answers."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "checkpoint_f32.npz"))
+    k = z["w_conv1_kernel"]
+    assert k.shape == (32, 1, 32)
+    assert abs(float(k.mean()) - 0.000365) < 1e-6 and abs(float(k.std()) - 0.115049) < 1e-6
+    assert abs(float(k.min()) + 0.36339) < 1e-5 and abs(float(k.max()) - 0.40413) < 1e-5
+    assert abs(float(z["head_bias"][0]) + 2.692142) < 1e-6
+    assert z["w_dense_kernel"].shape == (128, 128) and z["head_kernel"].shape == (128, 1)
+    assert z["w_bn1_var"].min() < 1e-6 and z["w_bn4_var"].max() > 29

@@ -1,0 +1,63 @@
+"""N>1 host logic on CPU: two gloo ranks exercise sharding, the flat-gradient all-reduce (+ identical Adam update on
+every rank), max-over-ranks timing and uneven-shard loss means."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import voicemap_oracle as O
+from voicemap_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    parallel.init_from_env(backend="gloo")
+    assert parallel.world() == (rank, world_size)
+    # sharding: 7 pairs over 2 ranks -> [0,4) and [4,7)
+    lo, hi = parallel.shard_bounds(7)
+    # per-rank "gradients" of a toy quadratic on this rank's shard; the all-reduced sum must equal the full-batch
+    # gradient and the Adam update must be bit-identical on both ranks
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(7, 5))
+    w = np.linspace(-1, 1, 5)
+    local = torch.from_numpy((data[lo:hi] * (data[lo:hi] @ w)[:, None]).sum(axis=0))
+    flat = parallel.allreduce_sum_(local.clone())
+    full = (data * (data @ w)[:, None]).sum(axis=0)
+    p = {"w": w.copy()}
+    O.keras_adam_step(p, {"w": flat.numpy() / 7.0}, {"w": np.zeros(5)}, {"w": np.zeros(5)}, t=1, clipnorm=1.0)
+    t_max = parallel.max_over_ranks(1.0 + rank)
+    mean = parallel.global_mean(float(np.arange(lo, hi).sum()), hi - lo)
+    rows = parallel.gather_rows(torch.full((hi - lo, 2), float(rank)))
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, hi=hi, flat=flat.numpy(), full=full, w=p["w"], t_max=t_max,
+             mean=mean, rows=rows.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    assert (int(r0["lo"]), int(r0["hi"]), int(r1["lo"]), int(r1["hi"])) == (0, 4, 4, 7)
+    np.testing.assert_allclose(r0["flat"], r0["full"], rtol=1e-12)
+    np.testing.assert_array_equal(r0["flat"], r1["flat"])
+    np.testing.assert_array_equal(r0["w"], r1["w"])          # identical update on every rank
+    assert r0["t_max"] == r1["t_max"] == 2.0                  # slowest rank defines the step time
+    assert abs(float(r0["mean"]) - 3.0) < 1e-12               # mean over the global batch, uneven shards
+    assert r0["rows"].shape == (7, 2) and r0["rows"][:4].sum() == 0 and r0["rows"][4:].sum() == 6
+
+
+def test_single_process_defaults():
+    assert parallel.world() == (0, 1)
+    assert parallel.shard_bounds(10) == (0, 10)
+    assert parallel.shard_bounds(10, 1, 4) == (3, 6) and parallel.shard_bounds(10, 3, 4) == (8, 10)
+    t = torch.ones(3)
+    assert parallel.allreduce_sum_(t) is t and parallel.max_over_ranks(2.5) == 2.5

@@ -44,6 +44,10 @@ SIGNATURES = {
     "vm_encoder_workspace_bytes": (_sz, [_i, _i, _i]),
     "vm_encoder_fwd": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "vm_set_option": (_i, [C.c_char_p, _i]),
+    "vm_preprocess_scratch_bytes": (_sz, [_i]),
+    "vm_preprocess_stats": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "vm_encoder_fwd_raw": (_i, [_vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp,
+                                _i, _vp]),
     # training
     "vm_pack_conv1_raw": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "vm_pack_conv3_raw": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
@@ -52,7 +56,7 @@ SIGNATURES = {
     "vm_conv3_raw_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "vm_stat_rows_per_clip": (_i, [_i]),
     "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
-    "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_gmax_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),

@@ -156,7 +156,7 @@ int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int
     return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 3");
   return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
                       static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, precision, g_max_ctas,
+                      reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, 0, precision, g_max_ctas,
                       (cudaStream_t)stream);
 }
 
@@ -218,7 +218,7 @@ int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L,
   if (in_hi == nullptr || wpack == nullptr || epi == nullptr || out == nullptr)
     return set_error(VM_ERR_SHAPE, "conv3_raw: null pointer");
   return launch_conv3(CH16(in_hi), CH16(in_lo), N, L, cin, cout, static_cast<const __half*>(wpack), epi, nullptr,
-                      nullptr, nullptr, out, stat_partial, linear, precision, g_max_ctas, ST);
+                      nullptr, nullptr, out, stat_partial, linear, /*in_bf16=*/linear, precision, g_max_ctas, ST);
 }
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
@@ -227,8 +227,9 @@ int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, in
                                   momentum, moving_mean, moving_var, bn_const, ST);
 }
 int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                   uint16_t* out_hi, uint16_t* out_lo, void* stream) {
-  return launch_bn_pool_fwd(u, N, L, C, G, pool, bn_const, mask, H16(out_hi), H16(out_lo), ST);
+                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* bf_hi, uint16_t* bf_lo, void* stream) {
+  if ((bf_hi == nullptr) != (bf_lo == nullptr)) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: give both bf16 planes");
+  return launch_bn_pool_fwd(u, N, L, C, G, pool, bn_const, mask, H16(out_hi), H16(out_lo), bf_hi, bf_lo, ST);
 }
 int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
                    int32_t* argmax, void* stream) {
@@ -276,15 +277,10 @@ size_t vm_encoder_workspace_bytes(int N, int L, int filters) {
   return plan_encoder(N, L, filters).total;
 }
 
-int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const* wpack, const float* const* epi,
-                   const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
-                   void* stream) {
-  if (x == nullptr || wpack == nullptr || epi == nullptr || workspace == nullptr || emb == nullptr)
-    return set_error(VM_ERR_SHAPE, "encoder: null pointer");
-  if (N <= 0 || filters <= 0) return set_error(VM_ERR_SHAPE, "encoder: bad shape");
-  if (L < 32) return set_error(VM_ERR_SHAPE, "encoder: L must be >= 32 (four pooling stages 4*2*2*2)");
-  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
-    return set_error(VM_ERR_SHAPE, "encoder: workspace must be 1024-byte aligned");
+static int encoder_fwd_impl(const float* x, int N, int L, int filters, const void* const* wpack,
+                            const float* const* epi, const float* dense_w, const float* dense_b, int E,
+                            void* workspace, float* emb, int precision, cudaStream_t st, int x_stride,
+                            long long x_clip_stride, const float* pre_mean, const float* pre_scale) {
   const EncoderPlan pl = plan_encoder(N, L, filters);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __half* a1h = reinterpret_cast<__half*>(ws);
@@ -294,21 +290,71 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
   __half* a3h = reinterpret_cast<__half*>(ws + 2 * pl.a1 + 2 * pl.a2);
   __half* a3l = reinterpret_cast<__half*>(ws + 2 * pl.a1 + 2 * pl.a2 + pl.a3);
   float* part = reinterpret_cast<float*>(ws + 2 * pl.a1 + 2 * pl.a2 + 2 * pl.a3);
-  cudaStream_t st = (cudaStream_t)stream;
   const int f = filters;
   int rc;
-  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, precision, g_max_ctas, st)))
+  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, precision, g_max_ctas, st, x_stride,
+                         x_clip_stride, pre_mean, pre_scale)))
     return rc;
   if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
-                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a2h, a2l, N, pl.l2, 2 * f, 3 * f, static_cast<const __half*>(wpack[2]), epi[2], a3h, a3l,
-                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a3h, a3l, N, pl.l3, 3 * f, 4 * f, static_cast<const __half*>(wpack[3]), epi[3], nullptr,
-                         nullptr, part, nullptr, nullptr, 0, precision, g_max_ctas, st)))
+                         nullptr, part, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
     return rc;
   return launch_gmax_dense(part, N, pl.t4, 4 * f, pl.c4_pad, epi[3], dense_w, dense_b, E, nullptr, emb, st);
+}
+
+static int encoder_args_ok(const void* x, const void* wpack, const void* epi, const void* workspace, const void* emb,
+                           int N, int L, int filters) {
+  if (x == nullptr || wpack == nullptr || epi == nullptr || workspace == nullptr || emb == nullptr)
+    return set_error(VM_ERR_SHAPE, "encoder: null pointer");
+  if (N <= 0 || filters <= 0) return set_error(VM_ERR_SHAPE, "encoder: bad shape");
+  if (L < 32) return set_error(VM_ERR_SHAPE, "encoder: L must be >= 32 (four pooling stages 4*2*2*2)");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+    return set_error(VM_ERR_SHAPE, "encoder: workspace must be 1024-byte aligned");
+  return VM_OK;
+}
+
+int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const* wpack, const float* const* epi,
+                   const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
+                   void* stream) {
+  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters);
+  if (rc) return rc;
+  return encoder_fwd_impl(x, N, L, filters, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
+                          (cudaStream_t)stream, 1, 0, nullptr, nullptr);
+}
+
+size_t vm_preprocess_scratch_bytes(int N) { return N > 0 ? align_up(size_t(N) * 4 * 6 + 64, 1024) : 0; }
+
+int vm_preprocess_stats(const float* x, int N, int T, int downsampling, int G, float rms, float* mean, float* scale,
+                        void* stream) {
+  if (x == nullptr || mean == nullptr || scale == nullptr) return set_error(VM_ERR_SHAPE, "preprocess: null pointer");
+  return launch_preprocess_stats(x, N, T, downsampling, G, rms, mean, scale, (cudaStream_t)stream);
+}
+
+int vm_encoder_fwd_raw(const float* x, int N, int T, int downsampling, int whiten_groups, float rms, int filters,
+                       const void* const* wpack, const float* const* epi, const float* dense_w, const float* dense_b,
+                       int E, void* workspace, float* emb, int precision, void* stream) {
+  if (downsampling <= 0 || T <= 0) return set_error(VM_ERR_SHAPE, "encoder_raw: bad downsampling / length");
+  const int L = (T + downsampling - 1) / downsampling;  // numpy x[:, ::d] keeps ceil(T / d) samples
+  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters);
+  if (rc) return rc;
+  const float* mean = nullptr;
+  const float* scale = nullptr;
+  if (whiten_groups > 0) {
+    if (N % whiten_groups != 0) return set_error(VM_ERR_SHAPE, "encoder_raw: N must be a multiple of whiten_groups");
+    float* m = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan_encoder(N, L, filters).total);
+    float* sc = m + N;
+    if ((rc = launch_preprocess_stats(x, N, T, downsampling, whiten_groups, rms, m, sc, (cudaStream_t)stream)))
+      return rc;
+    mean = m;
+    scale = sc;
+  }
+  return encoder_fwd_impl(x, N, L, filters, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
+                          (cudaStream_t)stream, downsampling, T, mean, scale);
 }
 
 }  // extern "C"

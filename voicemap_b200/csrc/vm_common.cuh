@@ -2,6 +2,7 @@
 // wrappers.  Everything here is Blackwell-only; there is no fallback path.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -150,8 +151,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // ---------------------------------------------------------------------------------------------
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (F32), a_format[7,10)=0 (F16),
 // b_format[10,13)=0 (F16), a_major bit15=0 (K), b_major bit16=0 (K), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+// a_bf16 / b_bf16 select bf16 instead of fp16 for that operand (kind::f16 takes either, independently).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_bf16 = 0, int b_bf16 = 0) {
+  return (1u << 4) | (uint32_t(a_bf16 & 1) << 7) | (uint32_t(b_bf16 & 1) << 10) | (uint32_t(N >> 3) << 17) |
+         (uint32_t(M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major operand.
@@ -238,5 +241,14 @@ __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
+
+// bf16 (hi, lo) split for gradients: fp32 exponent range (no loss scaling needed), ~16 significant bits.
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(uint32_t(b) << 16); }
 
 }  // namespace vm

@@ -95,18 +95,23 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
          tile += kStages * gridDim.x, i += kStages) {
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
-      const float* xc = p.x + size_t(n) * p.L;
+      const float* xc = p.x + size_t(n) * size_t(p.x_clip_stride);
+      const int xs = p.x_stride;
+      // fused preprocessing (voicemap/utils.py:22-34,88-101): decimation = strided read, whitening = per-clip
+      // affine; 'same' zero padding applies to the preprocessed signal
+      const float pm = p.pre_mean ? __ldg(p.pre_mean + n) : 0.f;
+      const float ps = p.pre_scale ? __ldg(p.pre_scale + n) : 1.f;
       // lane owns the 8 positions p0 + 8*lane .. +7; it needs x[p0 - 15 + 8*lane + i], i = 0..38
       const int e0 = p0 - 15 + 8 * lane;
       float xv[39];
       if (e0 >= 0 && e0 + 39 <= p.L) {  // interior strip: no bounds predicates
 #pragma unroll
-        for (int k = 0; k < 39; ++k) xv[k] = __ldg(xc + e0 + k);
+        for (int k = 0; k < 39; ++k) xv[k] = (__ldg(xc + size_t(e0 + k) * xs) - pm) * ps;
       } else {
 #pragma unroll
         for (int k = 0; k < 39; ++k) {
           const int e = e0 + k;
-          xv[k] = (e >= 0 && e < p.L) ? __ldg(xc + e) : 0.f;
+          xv[k] = (e >= 0 && e < p.L) ? (__ldg(xc + size_t(e) * xs) - pm) * ps : 0.f;
         }
       }
       // fp16 (hi, lo) split with packed conversions.  pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]).
@@ -310,7 +315,8 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
                  __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int x_stride, long long x_clip_stride, const float* pre_mean,
+                 const float* pre_scale) {
   using namespace c1;
   if (N <= 0 || L < 4) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= 4");
   if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
@@ -319,7 +325,10 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   const int nslab = cout_pad / kTileM;
   if (nslab > kMaxSlabs) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout > 512 not supported");
   Conv1Params p{};
-  p.x = x; p.N = N; p.L = L; p.cout = cout; p.cout_pad = cout_pad; p.nslab = nslab;
+  p.x = x; p.N = N; p.L = L; p.cout = cout;
+  p.x_stride = x_stride > 0 ? x_stride : 1;
+  p.x_clip_stride = x_clip_stride > 0 ? x_clip_stride : (long long)L * p.x_stride;
+  p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.cout_pad = cout_pad; p.nslab = nslab;
   p.lout = L / 4;
   p.nptile = (L + kTileN - 1) / kTileN;
   p.products = products;

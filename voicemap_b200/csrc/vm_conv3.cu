@@ -127,7 +127,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, kTileN);
+      const uint32_t idesc = make_idesc_f16(kTileM, kTileN, p.in_bf16, p.in_bf16);  // dgrad: both operands bf16
       uint32_t xit = 0, wit = 0, tit = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
         const int buf = tit & 1;
@@ -326,7 +326,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
-                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream) {
+                 float* stat_partial, int linear, int in_bf16, int products, int max_ctas, cudaStream_t stream) {
   using namespace c3;
   if (N <= 0 || L <= 0) return set_error(VM_ERR_SHAPE, "conv3: N and L must be positive");
   // K chunks are 64 channels wide; a ragged last chunk is zero-filled by TMA in both operands
@@ -348,6 +348,7 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo; p.gmax_partial = gmax_partial;
   p.out_f32 = out_f32; p.stat_partial = reinterpret_cast<float2*>(stat_partial); p.linear = linear;
+  p.in_bf16 = in_bf16;
 
   CUtensorMap xh_main, xh_halo, xl_main, xl_halo, wh, wl;
   // X planes: (N, L, Cin) fp16, dims fastest-first {Cin, L, N}

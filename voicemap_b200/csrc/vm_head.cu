@@ -90,7 +90,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
 // ---------------------------------------------------------------------------------------------
 // dgrad weights: dX[p][ci] = sum_t sum_co dU[p + t - 1][co] * W[2 - t][ci][co] is a k=3 'same' convolution of dU with
 // the tap-flipped, channel-transposed kernel.  w (3, cin, cout) -> wpack [plane][tap][cin_pad][cout] fp16, i.e. the
-// conv3 operand layout with the roles (cin' = cout, cout' = cin).
+// conv3 operand layout with the roles (cin' = cout, cout' = cin), as bf16 (hi, lo) planes.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad,
                                         __half* __restrict__ wpack, float4* __restrict__ epi) {
@@ -102,10 +102,10 @@ __global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, in
   const int ci = int((idx / cout) % cin_pad);
   const int tap = int(idx / (size_t(cout) * cin_pad));
   const float v = (ci < cin) ? w[(size_t(2 - tap) * cin + ci) * cout + co] : 0.f;
-  __half h, l;
-  split_f32(v, h, l);
-  wpack[idx] = h;
-  wpack[total + idx] = l;
+  uint16_t h, l;  // bf16 planes: the dgrad MMA runs bf16 x bf16 (its other operand, dU, is bf16)
+  split_bf16(v, h, l);
+  wpack[idx] = __ushort_as_half(h);
+  wpack[total + idx] = __ushort_as_half(l);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,6 +216,49 @@ __global__ void pair_head_loss_kernel(const float* __restrict__ e1, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Preprocessing statistics (voicemap/utils.py:22-34, 88-101): decimate x[:, ::stride], then per-clip mean and ONE
+// scale rms / sqrt(mean(batch^2)) per whiten() call (= per group of clips; the mean of squares is taken over the
+// un-centred decimated batch).  Accumulates in double like the reference's float64 numpy.
+// ---------------------------------------------------------------------------------------------
+__global__ void preprocess_clip_sums_kernel(const float* __restrict__ x, int T, int stride, int L,
+                                            double* __restrict__ sums /* (N, 2) */) {
+  __shared__ double r1[32], r2[32];
+  const int n = blockIdx.x;
+  const float* xc = x + size_t(n) * T;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const double v = double(xc[size_t(i) * stride]);
+    s1 += v;
+    s2 += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) { a += r1[w]; b += r2[w]; }
+    sums[2 * n] = a;
+    sums[2 * n + 1] = b;
+  }
+}
+__global__ void preprocess_finalize_kernel(const double* __restrict__ sums, int N, int G, int L, float rms,
+                                           float* __restrict__ mean, float* __restrict__ scale) {
+  const int clips = N / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double sq = 0.0;
+    for (int n = g * clips; n < (g + 1) * clips; ++n) sq += sums[2 * n + 1];
+    const float sc = float(double(rms) / sqrt(sq / (double(clips) * double(L))));
+    for (int n = g * clips; n < (g + 1) * clips; ++n) {
+      mean[n] = float(sums[2 * n] / double(L));
+      scale[n] = sc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static int check_launch(const char* what) {
@@ -255,6 +298,18 @@ int launch_pack_conv1(const float* w, const float* bias, const float* gamma, con
                                                             static_cast<__half*>(wpack),
                                                             reinterpret_cast<float4*>(epi));
   return check_launch("pack_conv1");
+}
+
+int launch_preprocess_stats(const float* x, int N, int T, int stride, int G, float rms, float* mean, float* scale,
+                            cudaStream_t stream) {
+  if (N <= 0 || T <= 0 || stride <= 0 || G <= 0 || N % G != 0) return set_error(VM_ERR_SHAPE, "preprocess: bad shape");
+  // scratch: the (N, 2) double sums live in the tail of the `scale` allocation contract: caller provides
+  // mean (N floats) and scale (N floats + 4*N floats of scratch)
+  double* sums = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(scale + N) + 7) & ~uintptr_t(7));
+  const int L = (T + stride - 1) / stride;
+  preprocess_clip_sums_kernel<<<N, 256, 0, stream>>>(x, T, stride, L, sums);
+  preprocess_finalize_kernel<<<1, 128, 0, stream>>>(sums, N, G, L, rms, mean, scale);
+  return check_launch("preprocess_stats");
 }
 
 int launch_split_planes(const float* x, size_t n, __half* hi, __half* lo, cudaStream_t stream) {

@@ -23,8 +23,12 @@ int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t
 
 // ---- block 1 ----
 struct Conv1Params {
-  const float* x;        // (N, L) fp32 (Keras (N, L, 1))
-  int N, L;
+  const float* x;        // (N, L) fp32 (Keras (N, L, 1)), or raw audio when x_stride > 1
+  int N, L;              // L = samples per clip entering the convolution (after decimation)
+  int x_stride;          // decimation stride into x (voicemap/utils.py:29), 1 = none
+  long long x_clip_stride;  // elements between consecutive clips in x
+  const float* pre_mean; // fused whitening: sample = (x - pre_mean[n]) * pre_scale[n]; null = off
+  const float* pre_scale;
   int cout, cout_pad, nslab;
   int lout;              // L / 4
   int nptile;            // ceil(L / 256)
@@ -39,7 +43,10 @@ struct Conv1Params {
 };
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
                  __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int x_stride = 1, long long x_clip_stride = 0,
+                 const float* pre_mean = nullptr, const float* pre_scale = nullptr);
+int launch_preprocess_stats(const float* x, int N, int T, int stride, int G, float rms, float* mean, float* scale,
+                            cudaStream_t stream);
 
 // ---- blocks 2-4 ----
 struct Conv3Params {
@@ -56,10 +63,11 @@ struct Conv3Params {
   float* out_f32;        // (N, L, cout) un-pooled fp32 output (train-mode forward / dgrad), or null
   float2* stat_partial;  // (N, 2*nptile, cout_pad) {sum, sum of squares} of out_f32 over valid positions, or null
   int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
+  int in_bf16;           // input AND weight planes are bf16 (dgrad) instead of fp16 (kind::f16 cannot mix the two)
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
-                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream);
+                 float* stat_partial, int linear, int in_bf16, int products, int max_ctas, cudaStream_t stream);
 
 // ---- weight gradients (vm_wgrad.cu) ----
 struct Wgrad3Params {
@@ -80,7 +88,8 @@ int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad,
                              const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
                              float* moving_var, float* bn_const, cudaStream_t st);
 int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
-                       const float* mask, __half* out_hi, __half* out_lo, cudaStream_t st);
+                       const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
+                       cudaStream_t st);
 int launch_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask,
                        float* gmax, int* argmax, cudaStream_t st);
 int launch_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, cudaStream_t st);

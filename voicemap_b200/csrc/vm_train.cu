@@ -68,7 +68,8 @@ __global__ void bn_stats_finalize_kernel(const float2* __restrict__ partial, int
 // ---------------------------------------------------------------------------------------------
 __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G, int pool,
                                    const float4* __restrict__ bn_const, const float* __restrict__ mask,
-                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                   uint16_t* __restrict__ bf_hi, uint16_t* __restrict__ bf_lo) {
   const int lout = L / pool;
   const int c4n = C >> 2;
   const size_t total = size_t(N) * lout * c4n;
@@ -105,6 +106,15 @@ __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, in
     *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(
         uint32_t(__half_as_ushort(l[0])) | (uint32_t(__half_as_ushort(l[1])) << 16),
         uint32_t(__half_as_ushort(l[2])) | (uint32_t(__half_as_ushort(l[3])) << 16));
+    if (bf_hi != nullptr) {  // bf16 copy of the same activations: the wgrad MMA needs X in dU's format
+      uint16_t bh[4], bl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_bf16(best[k], bh[k], bl[k]);
+      *reinterpret_cast<uint2*>(bf_hi + o) = make_uint2(uint32_t(bh[0]) | (uint32_t(bh[1]) << 16),
+                                                        uint32_t(bh[2]) | (uint32_t(bh[3]) << 16));
+      *reinterpret_cast<uint2*>(bf_lo + o) = make_uint2(uint32_t(bl[0]) | (uint32_t(bl[1]) << 16),
+                                                        uint32_t(bl[2]) | (uint32_t(bl[3]) << 16));
+    }
   }
 }
 
@@ -365,12 +375,11 @@ __global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int r
   dbeta[c] = float(tb);
 }
 
-// pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) as fp16 (hi, lo) planes; conv-bias gradient
+// pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) as bf16 (hi, lo) planes; conv-bias gradient
 // partials sum_positions dU per channel.  grid (N, chunks) over pool windows (incl. the 'valid' tail window, which
 // receives no dy but still the batch-statistics terms).
-__device__ __forceinline__ uint2 pack4h(const __half (&h)[4]) {
-  return make_uint2(uint32_t(__half_as_ushort(h[0])) | (uint32_t(__half_as_ushort(h[1])) << 16),
-                    uint32_t(__half_as_ushort(h[2])) | (uint32_t(__half_as_ushort(h[3])) << 16));
+__device__ __forceinline__ uint2 pack4u(const uint16_t (&h)[4]) {
+  return make_uint2(uint32_t(h[0]) | (uint32_t(h[1]) << 16), uint32_t(h[2]) | (uint32_t(h[3]) << 16));
 }
 __global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
                                    const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
@@ -416,7 +425,7 @@ __global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __r
       }
       for (int i = 0; i < wl; ++i) {
         const float4 uv4 = *reinterpret_cast<const float4*>(up + size_t(i) * C);
-        __half h[4], lw[4];
+        uint16_t h[4], lw[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float uv = f4get(uv4, k);
@@ -424,11 +433,11 @@ __global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __r
           const float xhat = (uv - mean[k]) * rstd[k];
           const float du = (uv > 0.f) ? bs[k] * (dy - mdy[k] - xhat * mdx[k]) : 0.f;
           sb[k] += du;
-          split_f32(du, h[k], lw[k]);
+          split_bf16(du, h[k], lw[k]);
         }
         const size_t o = (size_t(n) * L + l0 + i) * C + c;
-        *reinterpret_cast<uint2*>(du_hi + o) = pack4h(h);
-        if (du_lo != nullptr) *reinterpret_cast<uint2*>(du_lo + o) = pack4h(lw);
+        *reinterpret_cast<uint2*>(du_hi + o) = pack4u(h);
+        if (du_lo != nullptr) *reinterpret_cast<uint2*>(du_lo + o) = pack4u(lw);
       }
     }
     float* row = dbias_partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;
@@ -498,12 +507,13 @@ int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad,
 }
 
 int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
-                       const float* mask, __half* out_hi, __half* out_lo, cudaStream_t st) {
+                       const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
+                       cudaStream_t st) {
   if (C % 4 != 0 || N % G != 0 || pool <= 0 || L / pool <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
   const size_t total = size_t(N) * (L / pool) * (C / 4);
   const unsigned blocks = unsigned(min(size_t(148 * 32), (total + 255) / 256));
   bn_pool_fwd_kernel<<<blocks, 256, 0, st>>>(u, N, L, C, G, pool, reinterpret_cast<const float4*>(bn_const), mask,
-                                            out_hi, out_lo);
+                                            out_hi, out_lo, bf_hi, bf_lo);
   return check_launch_t("bn_pool_fwd");
 }
 

@@ -8,7 +8,9 @@
 //   by `tap` rows.  D[tap] = 128 ci lanes x 128 co columns fp32 in TMEM (3 x 128 columns), accumulated over the
 //   CTA's slice of (clip, 64-position chunk) steps, then written to a per-split partial buffer that
 //   wgrad_reduce sums deterministically (no atomics).
-//   Operands are fp16 (hi, lo) planes; products = 3 gives fp32-grade gradients, products = 1 plain fp16.
+//   Both operands are bf16 (hi, lo) planes: gradients keep the fp32 exponent range (no loss scaling) and kind::f16
+//   cannot mix fp16 with bf16, so bn_pool_fwd also emits a bf16 copy of the activations for this kernel.
+//   products = 3 gives ~2^-16 relative gradients, products = 1 plain bf16.
 //
 // wgrad1 (block 1):  dW1[k][co] = sum_{n,p} x[n][p + k - 15] * dU1[n][p][co]   (CUDA cores, fp32; 4% of the FLOPs)
 #include "vm_common.cuh"
@@ -38,7 +40,7 @@ struct __align__(8) WgradBarriers {
 
 // instruction descriptor with both operands MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
-  return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);
+  return make_idesc_f16(M, N, /*A = X bf16*/ 1, /*B = dU bf16*/ 1) | (1u << 15) | (1u << 16);
 }
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
@@ -242,7 +244,8 @@ wgrad1_kernel(const float* __restrict__ x, const __half* __restrict__ du_hi, con
       float v = 0.f;
       if (r < sl && co_base + c < cout) {
         const size_t o = (size_t(n) * L + p0 + sp + r) * cout + co_base + c;
-        v = __half2float(du_hi[o]) + (du_lo ? __half2float(du_lo[o]) : 0.f);
+        v = bf16_bits_to_float(__half_as_ushort(du_hi[o])) +
+            (du_lo ? bf16_bits_to_float(__half_as_ushort(du_lo[o])) : 0.f);
       }
       us[r][c] = v;
     }

@@ -110,6 +110,7 @@ class EncoderEngine:
         key = (n, length)
         if self._ws_key != key:
             nbytes = self.lib.vm_encoder_workspace_bytes(n, length, self.filters)
+            nbytes += self.lib.vm_preprocess_scratch_bytes(n) if nbytes else 0
             if nbytes == 0:
                 raise ValueError(f"input of shape ({n}, {length}) is too short for the encoder (L >= 32)")
             self._workspace = None
@@ -139,6 +140,31 @@ class EncoderEngine:
                                          _ptr(self.params["dense_bias"]), self.embedding_dimension, ws, _ptr(out),
                                          self.precision, _stream())
         _lib.check(rc, "vm_encoder_fwd")
+        return out
+
+    def forward_raw(self, x, downsampling=4, whiten_groups=1, rms=0.038021, out=None):
+        """Raw audio (N, T) fp32 on the device -> embeddings, with the reference's preprocessing
+        (voicemap/utils.py:22-34: x[:, ::downsampling], whiten) fused into block 1.  ``whiten_groups`` = number of
+        separate whiten() calls the batch stands for (their scales are batch-global per call); 0 = no whitening."""
+        if x.dim() == 3:
+            x = x.reshape(x.shape[0], x.shape[1])
+        if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous():
+            raise ValueError("raw input must be a contiguous CUDA float32 tensor")
+        if not self._packed:
+            self.pack()
+        n, t = x.shape
+        length = (t + downsampling - 1) // downsampling
+        if out is None:
+            out = torch.empty((n, self.embedding_dimension), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self._get_workspace(n, length)
+            wp = (C.c_void_p * 4)(*[w.data_ptr() for w in self.wpack])
+            ep = (C.c_void_p * 4)(*[e.data_ptr() for e in self.epi])
+            rc = self.lib.vm_encoder_fwd_raw(_ptr(x), n, t, int(downsampling), int(whiten_groups), C.c_float(rms),
+                                             self.filters, wp, ep, _ptr(self.params["dense_kernel"]),
+                                             _ptr(self.params["dense_bias"]), self.embedding_dimension, ws, _ptr(out),
+                                             self.precision, _stream())
+        _lib.check(rc, "vm_encoder_fwd_raw")
         return out
 
     # ------------------------------------------------------------------ per-block views (tests, profiling)

@@ -257,6 +257,22 @@ class EncoderModel(_ModelBase):
         out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         return out.cpu().numpy()
 
+    def predict_raw(self, x, downsampling=4, whitening=True):
+        """Embeddings of RAW clips (N, T, 1) (e.g. 48000 samples of 16 kHz audio): equivalent to
+        ``predict(preprocess_instances(downsampling, whitening)(x))`` with the decimation and whitening of
+        voicemap/utils.py:22-34 done on the device inside block 1 (x is one whiten() batch)."""
+        import torch
+        shape_check, self.input_shape = self.input_shape, None   # the raw length differs from the model's input
+        try:
+            xt = self._host_batch(x)
+        finally:
+            self.input_shape = shape_check
+        eng = self._get_engine()
+        emb = eng.forward_raw(xt.to(eng.device, non_blocking=True), downsampling, 1 if whitening else 0)
+        if self._head is not None:
+            emb = self._apply_head(emb)
+        return emb.cpu().numpy()
+
     def _apply_head(self, emb):
         # classifier head Dense(num_classes, softmax): adjacent to the hot path (SURVEY.md 8(a) a12), device-side
         import torch
@@ -379,8 +395,76 @@ def build_siamese_net(encoder, input_shape, distance_metric='uniform_euclidean')
     return SiameseModel(encoder, input_shape, distance_metric)
 
 
+def _load_keras_hdf5(filepath):
+    """Keras 2.2.x full-model HDF5 checkpoint (what the reference's ModelCheckpoint writes,
+    experiments/train_siamese.py:81-87) -> EncoderModel / SiameseModel.  Weights are matched by name, so both the
+    nested (siamese: trainable first, moving statistics last) and the flat Sequential orders load."""
+    import warnings
+    from .keras_hdf5 import load_keras_weights
+    cfg, layers = load_keras_weights(filepath)
+    flat = OrderedDict()
+    for _, ws in layers:
+        for wname, arr in ws:
+            flat[wname.split(":")[0]] = np.asarray(arr, dtype=np.float32)
+
+    def find(suffix):
+        hits = [k for k in flat if k.endswith(suffix)]
+        if len(hits) != 1:
+            raise ValueError(f"checkpoint has {len(hits)} weights matching {suffix!r}")
+        return flat[hits[0]]
+
+    filters = find("conv1d_1/kernel").shape[2]
+    emb = find("dense_1/kernel").shape[1]
+    named = OrderedDict()
+    for i in range(1, 5):
+        named[f"conv{i}_kernel"] = find(f"conv1d_{i}/kernel")
+        named[f"conv{i}_bias"] = find(f"conv1d_{i}/bias")
+        named[f"bn{i}_gamma"] = find(f"batch_normalization_{i}/gamma")
+        named[f"bn{i}_beta"] = find(f"batch_normalization_{i}/beta")
+        named[f"bn{i}_mean"] = find(f"batch_normalization_{i}/moving_mean")
+        named[f"bn{i}_var"] = find(f"batch_normalization_{i}/moving_variance")
+    named["dense_kernel"], named["dense_bias"] = find("dense_1/kernel"), find("dense_1/bias")
+    pools = []
+
+    def walk(o):
+        if isinstance(o, dict):
+            if o.get("class_name") == "MaxPooling1D":
+                pools.append(tuple(o["config"].get("pool_size", ())))
+            for v in o.values():
+                walk(v)
+        elif isinstance(o, list):
+            for v in o:
+                walk(v)
+
+    walk(cfg)
+    if pools and pools[0] != (4,):
+        warnings.warn("checkpoint was trained with an older voicemap architecture (first MaxPool1D 2 instead of 4, "
+                      "SURVEY.md F9); weights are loaded into the current architecture (voicemap/models.py:19)")
+    is_siamese = any(k.startswith("dense_2/") for k in flat)
+    enc = EncoderModel(filters, emb, dropout=0.05)
+    enc.set_named_weights(named)
+    if not is_siamese:
+        return enc
+    head_k = flat["dense_2/kernel"]
+    metric = "weighted_l1" if head_k.shape[0] == emb and emb != 1 else "uniform_euclidean"
+    lshape = None
+    for layer in cfg.get("config", {}).get("layers", []):
+        if layer.get("class_name") == "InputLayer":
+            lshape = tuple(layer["config"]["batch_input_shape"][1:])
+            break
+    m = SiameseModel(enc, lshape if lshape and lshape[0] else (12000, 1), metric)
+    m.head_weights["head_kernel"] = head_k.reshape(m.head_weights["head_kernel"].shape).copy()
+    m.head_weights["head_bias"] = flat["dense_2/bias"].copy()
+    return m
+
+
 def load_model(filepath, custom_objects=None):
-    """Counterpart of _ModelBase.save (keras.models.load_model call site: experiments/k_way_accuracy.py:45)."""
+    """keras.models.load_model call site: experiments/k_way_accuracy.py:45.  Reads this package's npz container
+    (counterpart of ``save``) and Keras 2.2.x HDF5 checkpoints (pure-Python reader, no h5py)."""
+    with open(filepath, "rb") as fh:
+        magic = fh.read(8)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        return _load_keras_hdf5(filepath)
     with np.load(filepath) as z:
         cfg = json.loads(bytes(z["config"]).decode())
         weights = [z[f"w{i}"] for i in range(len(z.files) - 1)]

@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing (one process per GPU, ``torch.distributed``): the hot path shards by independent clips, so
+inference needs no data-path collective; training all-reduces ONE flat fp32 gradient buffer per step
+(SURVEY.md 8(e)).  Everything here is backend-agnostic host logic (NCCL on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size) -- (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend="nccl", device=None):
+    """Initialise the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun); no-op for one process."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1 or dist.is_initialized():
+        return world()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    kwargs = {}
+    if backend == "nccl" and device is not None:
+        kwargs["device_id"] = device
+    dist.init_process_group(backend, **kwargs)
+    return world()
+
+
+def shard_bounds(n_items, rank=None, world_size=None):
+    """Contiguous shard [lo, hi) of ``n_items`` independent units for this rank; sizes differ by at most one and
+    both members of a verification pair stay on one rank when the caller shards PAIRS."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(flat):
+    """In-place sum of the flat gradient buffer over all ranks (a single bucket: the 4.1 MB message is
+    latency-bound on NVLink)."""
+    if world()[1] > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def max_over_ranks(value, device="cpu"):
+    """Timing reduction of the bench: the slowest rank defines the step time."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def global_mean(local_sum, local_count, device="cpu"):
+    """Mean of a per-sample quantity over the GLOBAL batch (the loss mean must not be a mean of rank means when
+    shards are uneven)."""
+    t = torch.tensor([float(local_sum), float(local_count)], dtype=torch.float64, device=device)
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0].item() / max(t[1].item(), 1.0))
+
+
+def gather_rows(x):
+    """All-gather of per-rank embedding rows (k-way evaluation across ranks); rows may differ per rank."""
+    rank, ws = world()
+    if ws == 1:
+        return x
+    counts = [torch.zeros(1, dtype=torch.int64, device=x.device) for _ in range(ws)]
+    dist.all_gather(counts, torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device))
+    counts = [int(c.item()) for c in counts]
+    pad = max(counts)
+    buf = torch.zeros((pad,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    buf[:x.shape[0]] = x
+    out = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)

@@ -1,0 +1,469 @@
+"""Training on B200: what ``model.fit_generator`` does in the reference (experiments/train_siamese.py:56-94,
+train_classifier.py:114-150, siamese_contrastive_loss.py:70-100) -- train-mode forward (batch-statistics
+BatchNorm per encoder application, SpatialDropout1D), backward, Keras Adam with global-norm clipping, the Keras
+callback protocol -- with every FLOP of the encoder/head in libvoicemap_b200.so.  PyTorch supplies device memory,
+streams and (multi-GPU) ``torch.distributed.all_reduce`` of the flat gradient buffer.
+
+Data parallelism: each rank trains on its own shard of the batch; ONE flat fp32 gradient
+all-reduce (sum) per step over NCCL, then the identical clip + Adam update on every rank.  BatchNorm statistics
+are per rank (local BN) -- a documented deviation from the single-device reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import BN_EPS, PRECISION_FP32_GRADE, EncoderEngine, _ptr, _stream
+
+BN_MOMENTUM = 0.99
+POOLS = (4, 2, 2, 2)
+_BWD_CHUNKS = 8
+
+
+def _check(rc, what):
+    _lib.check(rc, what)
+
+
+class TrainEngine:
+    """One training step of encoder (+ siamese head | classifier head) on the current CUDA device."""
+
+    def __init__(self, model, optimizer, loss, loss_scale=1.0, precision=PRECISION_FP32_GRADE, bwd_precision=None,
+                 seed=0):
+        from .models import EncoderModel, SiameseModel
+        self.lib = _lib.load()
+        self.model = model
+        self.optimizer = optimizer
+        self.loss = loss
+        self.loss_scale = float(loss_scale)
+        self.precision = int(precision)
+        self.bwd_precision = int(bwd_precision if bwd_precision is not None else precision)
+        if isinstance(model, SiameseModel):
+            self.kind = "siamese"
+            self.encoder_model = model.encoder
+            if loss not in ("binary_crossentropy", "contrastive_loss"):
+                raise NotImplementedError(f"siamese training with loss {loss!r}")
+            head = model.head_weights
+            self.head_names = ["head_kernel", "head_bias"]
+        elif isinstance(model, EncoderModel):
+            self.kind = "classifier"
+            self.encoder_model = model
+            if model._head is None or model._head["activation"] != "softmax" or loss != "categorical_crossentropy":
+                raise NotImplementedError("classifier training needs a Dense(softmax) head and "
+                                          "categorical_crossentropy")
+            head = OrderedDict((k, model.weights[k]) for k in ("head_kernel", "head_bias"))
+            self.head_names = ["head_kernel", "head_bias"]
+        else:
+            raise TypeError("unknown model type")
+        enc = self.encoder_model
+        self.eng: EncoderEngine = enc._get_engine()
+        self.device = self.eng.device
+        self.filters, self.emb = enc.filters, enc.embedding_dimension
+        self.channels = [self.filters * m for m in (1, 2, 3, 4)]
+        self.dropout = float(enc.dropout)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+
+        # ---- flat trainable-parameter buffer in Keras weight order (moving statistics excluded)
+        self.layout = OrderedDict()
+        off = 0
+        for name, w in enc.weights.items():
+            if name.endswith("_mean") or name.endswith("_var") or name.startswith("head_"):
+                continue
+            self.layout[name] = (off, tuple(w.shape))
+            off += int(np.prod(w.shape))
+        for name in self.head_names:
+            self.layout[name] = (off, tuple(head[name].shape))
+            off += int(np.prod(head[name].shape))
+        self.nparams = off
+        dev = self.device
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.p = OrderedDict()   # parameter views
+        self.g = OrderedDict()   # gradient views
+        for name, (o, shape) in self.layout.items():
+            n = int(np.prod(shape))
+            self.p[name] = self.flat[o:o + n].view(shape)
+            self.g[name] = self.grad[o:o + n].view(shape)
+            src = head[name] if name in self.head_names else enc.weights[name]
+            self.p[name].copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)))
+        # moving statistics stay in the eval engine's tensors; trainable views are shared with it so that
+        # predict()/validation see the current weights without copies
+        self.moving = OrderedDict((k, self.eng.params[k]) for k in self.eng.params if k.endswith(("_mean", "_var")))
+        for name in self.eng.params:
+            if name in self.p:
+                self.eng.params[name] = self.p[name]
+        self.eng._packed = False
+
+        # ---- packed operands for train mode
+        self.wraw, self.eraw, self.wdg, self.edg = [], [], [None], [None]
+        cin = 1
+        for i, cout in enumerate(self.channels):
+            nb = self.lib.vm_conv1_wpack_bytes(cout) if i == 0 else self.lib.vm_conv3_wpack_bytes(cin, cout)
+            self.wraw.append(torch.zeros(nb, dtype=torch.uint8, device=dev))
+            self.eraw.append(torch.zeros(self.lib.vm_epi_bytes(cout) // 4, dtype=torch.float32, device=dev))
+            if i > 0:
+                self.wdg.append(torch.zeros(self.lib.vm_conv3_wpack_bytes(cout, cin), dtype=torch.uint8, device=dev))
+                self.edg.append(torch.zeros(self.lib.vm_epi_bytes(cin) // 4, dtype=torch.float32, device=dev))
+            cin = cout
+        self._buf_key = None
+        self.iterations = 0
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, nb, length, groups):
+        key = (nb, length, groups)
+        if self._buf_key == key:
+            return
+        dev, f32, f16 = self.device, torch.float32, torch.float16
+        ls = [length]
+        for p in POOLS:
+            ls.append(ls[-1] // p)
+        if ls[4] < 1:
+            raise ValueError("clips are too short for the encoder")
+        self.ls = ls  # ls[b] = input length of block b+1 = un-pooled length of block b+1's conv
+        c = self.channels
+        self.U = [torch.empty((nb, ls[b], c[b]), dtype=f32, device=dev) for b in range(4)]
+        self.X = [torch.empty((2, nb, ls[b + 1], c[b]), dtype=f16, device=dev) for b in range(3)]  # fp16 [hi/lo]
+        self.XB = [torch.empty((2, nb, ls[b + 1], c[b]), dtype=torch.int16, device=dev) for b in range(3)]  # bf16
+        rows = [self.lib.vm_stat_rows_per_clip(ls[b]) for b in range(4)]
+        self.stat = [torch.empty((nb * rows[b], self.lib.vm_padded_channels(c[b]), 2), dtype=f32, device=dev)
+                     for b in range(4)]
+        self.stat_rows = rows
+        self.bnc = [torch.empty((groups, c[b], 4), dtype=f32, device=dev) for b in range(4)]
+        self.bwc = [torch.empty((groups, c[b], 4), dtype=f32, device=dev) for b in range(4)]
+        self.gmax = torch.empty((nb, c[3]), dtype=f32, device=dev)
+        self.argmax = torch.empty((nb, c[3]), dtype=torch.int32, device=dev)
+        self.embv = torch.empty((nb, self.emb), dtype=f32, device=dev)
+        self.d_emb = torch.empty((nb, self.emb), dtype=f32, device=dev)
+        self.d_gmax = torch.empty((nb, c[3]), dtype=f32, device=dev)
+        max_u = max(ls[b] * c[b] for b in range(4))
+        self.dU = torch.empty((2, nb * max_u), dtype=f16, device=dev)
+        max_x = max(ls[b + 1] * c[b] for b in range(3))
+        self.dX = torch.empty(nb * max_x, dtype=f32, device=dev)
+        # BN-backward partial rows: N * chunks * nstream rows of C entries with nstream * C == max(512, C)
+        scr_elems = nb * _BWD_CHUNKS * max(512, max(c))
+        self.scr2 = torch.empty((scr_elems, 2), dtype=f32, device=dev)
+        self.scr1 = torch.empty((scr_elems,), dtype=f32, device=dev)
+        # wgrad split partials (the launcher lowers its split count to fit) / wgrad1 per-CTA partials
+        w1_bytes = nb * ((ls[0] + 1023) // 1024) * 32 * c[0] * 4
+        self.wpart = torch.empty(max(64 << 20, w1_bytes) // 4, dtype=f32, device=dev)
+        self.masks = [None] * 4
+        self._buf_key = key
+
+    def _pack(self):
+        p = self.p
+        cin = 1
+        for i, cout in enumerate(self.channels, start=1):
+            if i == 1:
+                rc = self.lib.vm_pack_conv1_raw(_ptr(p["conv1_kernel"]), _ptr(p["conv1_bias"]), cout,
+                                                _ptr(self.wraw[0]), _ptr(self.eraw[0]), _stream())
+            else:
+                rc = self.lib.vm_pack_conv3_raw(_ptr(p[f"conv{i}_kernel"]), _ptr(p[f"conv{i}_bias"]), cin, cout,
+                                                _ptr(self.wraw[i - 1]), _ptr(self.eraw[i - 1]), _stream())
+                _check(rc, "vm_pack_conv3_raw")
+                rc = self.lib.vm_pack_conv3_dgrad(_ptr(p[f"conv{i}_kernel"]), cin, cout, _ptr(self.wdg[i - 1]),
+                                                  _ptr(self.edg[i - 1]), _stream())
+            _check(rc, "train pack")
+            cin = cout
+
+    def _draw_masks(self, nb):
+        if not (0.0 < self.dropout < 1.0):   # keras guards 0 < rate < 1: identity otherwise
+            self.masks = [None] * 4
+            return
+        keep = 1.0 - self.dropout
+        self.masks = []
+        for c in self.channels:  # SpatialDropout1D: one Bernoulli draw per (clip, channel), scaled by 1/keep
+            m = (torch.rand((nb, c), generator=self.gen, device=self.device) < keep).to(torch.float32) / keep
+            self.masks.append(m)
+
+    # ------------------------------------------------------------------ forward (train mode)
+    def forward_train(self, x, groups, masks=None, update_moving=True):
+        """x: CUDA fp32 (NB, L).  Returns embeddings (NB, E).  Keeps everything backward needs."""
+        lib = self.lib
+        nb, length = x.shape
+        self._buffers(nb, length, groups)
+        if masks is not None:
+            self.masks = masks
+        else:
+            self._draw_masks(nb)
+        self._pack()
+        self.x_in = x
+        c, ls, st = self.channels, self.ls, _stream()
+        for b in range(4):
+            if b == 0:
+                rc = lib.vm_conv1_raw_fwd(_ptr(x), nb, length, c[0], _ptr(self.wraw[0]), _ptr(self.eraw[0]),
+                                          _ptr(self.U[0]), _ptr(self.stat[0]), self.precision, st)
+            else:
+                rc = lib.vm_conv3_raw_fwd(_ptr(self.X[b - 1][0]), _ptr(self.X[b - 1][1]), nb, ls[b], c[b - 1], c[b],
+                                          _ptr(self.wraw[b]), _ptr(self.eraw[b]), _ptr(self.U[b]),
+                                          _ptr(self.stat[b]), 0, self.precision, st)
+            _check(rc, f"train conv block {b + 1}")
+            mm = self.moving[f"bn{b + 1}_mean"] if update_moving else None
+            mv = self.moving[f"bn{b + 1}_var"] if update_moving else None
+            rc = lib.vm_bn_stats_finalize(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, ls[b], c[b],
+                                          _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
+                                          C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
+                                          _ptr(self.bnc[b]), st)
+            _check(rc, "vm_bn_stats_finalize")
+            if b < 3:
+                rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, POOLS[b], _ptr(self.bnc[b]),
+                                        _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
+                                        _ptr(self.XB[b][0]), _ptr(self.XB[b][1]), st)
+                _check(rc, "vm_bn_pool_fwd")
+            else:
+                rc = lib.vm_bn_gmax_fwd(_ptr(self.U[3]), nb, ls[3], c[3], groups, _ptr(self.bnc[3]),
+                                        _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.argmax), st)
+                _check(rc, "vm_bn_gmax_fwd")
+        rc = lib.vm_dense_fwd(_ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]), _ptr(self.p["dense_bias"]),
+                              self.emb, _ptr(self.embv), st)
+        _check(rc, "vm_dense_fwd")
+        self.groups = groups
+        return self.embv
+
+    # ------------------------------------------------------------------ backward of the encoder
+    def backward_encoder(self, d_emb):
+        """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters."""
+        lib, st = self.lib, _stream()
+        nb = d_emb.shape[0]
+        c, ls, g, groups = self.channels, self.ls, self.g, self.groups
+        rc = lib.vm_dense_bwd(_ptr(self.gmax), _ptr(d_emb), _ptr(self.p["dense_kernel"]), nb, c[3], self.emb,
+                              _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
+        _check(rc, "vm_dense_bwd")
+        bp = self.bwd_precision
+        for b in (3, 2, 1, 0):
+            n_u = nb * ls[b] * c[b]
+            du_hi, du_lo = self.dU[0][:n_u], self.dU[1][:n_u]
+            if b == 3:
+                dy, dg, am = None, self.d_gmax, self.argmax
+            else:
+                dy, dg, am = self.dX, None, None
+            rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, POOLS[b],
+                               _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
+                               _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
+                               _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), st)
+            _check(rc, f"vm_bn_bwd block {b + 1}")
+            if b == 0:
+                rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], _ptr(self.wpart),
+                                   self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
+                _check(rc, "vm_wgrad1")
+            else:
+                rc = lib.vm_wgrad3(_ptr(self.XB[b - 1][0]), _ptr(self.XB[b - 1][1]), _ptr(du_hi), _ptr(du_lo), nb,
+                                   ls[b], c[b - 1], c[b], bp, _ptr(self.wpart), self.wpart.numel() * 4,
+                                   _ptr(g[f"conv{b + 1}_kernel"]), st)
+                _check(rc, f"vm_wgrad3 block {b + 1}")
+                # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
+                rc = lib.vm_conv3_raw_fwd(_ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b], c[b - 1], _ptr(self.wdg[b]),
+                                          _ptr(self.edg[b]), _ptr(self.dX), None, 1, bp, st)
+                _check(rc, f"dgrad block {b + 1}")
+
+    # ------------------------------------------------------------------ optimizer
+    def apply_gradients(self, world=1):
+        opt = self.optimizer
+        self.iterations += 1
+        t = self.iterations
+        lr = opt.lr
+        if opt.decay > 0:
+            lr = lr * (1.0 / (1.0 + opt.decay * (t - 1)))
+        lr_t = lr * np.sqrt(1.0 - opt.beta_2 ** t) / (1.0 - opt.beta_1 ** t)
+        rc = self.lib.vm_adam_step(_ptr(self.flat), _ptr(self.grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                                   self.nparams, _ptr(self.sumsq), C.c_float(1.0 / (self.loss_scale * world)),
+                                   C.c_float(opt.clipnorm if opt.clipnorm else 0.0), C.c_float(lr_t),
+                                   C.c_float(opt.beta_1), C.c_float(opt.beta_2), C.c_float(opt.epsilon), _stream())
+        _check(rc, "vm_adam_step")
+        opt.iterations = t
+        self.eng._packed = False
+
+    # ------------------------------------------------------------------ full steps
+    def _to_device(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            a = np.asarray(a)
+            if a.ndim == 3:
+                a = a[:, :, 0]
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        if t.dim() == 3:
+            t = t.reshape(t.shape[0], t.shape[1])
+        return t.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def siamese_step(self, x1, x2, y, apply=True, masks=None, allreduce=None, world=1):
+        """One train_on_batch of the siamese model.  Returns (loss, accuracy) as python floats lazily (tensors)."""
+        from .engine import pair_head_loss
+        lib, st = self.lib, _stream()
+        a, b = self._to_device(x1), self._to_device(x2)
+        n = a.shape[0]
+        x = torch.cat([a, b], dim=0)
+        yt = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(self.device)
+        emb = self.forward_train(x, groups=2, masks=masks)
+        metric = self.model.distance_metric
+        hw = self.p["head_kernel"].reshape(-1)
+        hb = self.p["head_bias"]
+        loss_name = "contrastive" if self.loss == "contrastive_loss" else "binary_crossentropy"
+        prob, _, lossv = pair_head_loss(emb[:n], emb[n:], hw, hb, metric, yt, loss_name)
+        metric_id = {"uniform_euclidean": 0, "weighted_l1": 1}[metric]
+        rc = lib.vm_pair_head_loss_bwd(_ptr(emb), n, self.emb, metric_id, _ptr(hw), _ptr(hb), _ptr(yt),
+                                       1 if self.loss == "contrastive_loss" else 2, C.c_float(self.loss_scale),
+                                       _ptr(self.d_emb), _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), st)
+        _check(rc, "vm_pair_head_loss_bwd")
+        self.backward_encoder(self.d_emb)
+        if allreduce is not None:
+            allreduce(self.grad)
+        if apply:
+            self.apply_gradients(world)
+        acc = ((prob.reshape(-1) > 0.5).to(torch.float32) == yt).to(torch.float32).mean()
+        return lossv.reshape(()), acc
+
+    def classifier_step(self, x, y_onehot, apply=True, masks=None, allreduce=None, world=1):
+        """Encoder + Dense(softmax) + categorical cross-entropy.  The softmax head is adjacent to the hot path
+         and runs as torch device ops."""
+        xd = self._to_device(x)
+        n = xd.shape[0]
+        yt = torch.as_tensor(np.asarray(y_onehot, dtype=np.float32)).to(self.device)
+        emb = self.forward_train(xd, groups=1, masks=masks)
+        hk, hb = self.p["head_kernel"], self.p["head_bias"]
+        logits = emb @ hk + hb
+        logp = torch.log_softmax(logits, dim=-1)
+        lossv = -(yt * logp).sum(dim=-1).mean()
+        dlogits = (torch.softmax(logits, dim=-1) - yt) * (self.loss_scale / n)
+        self.g["head_kernel"].copy_(emb.t() @ dlogits)
+        self.g["head_bias"].copy_(dlogits.sum(dim=0))
+        self.d_emb.copy_(dlogits @ hk.t())
+        self.backward_encoder(self.d_emb)
+        if allreduce is not None:
+            allreduce(self.grad)
+        if apply:
+            self.apply_gradients(world)
+        acc = (logits.argmax(dim=-1) == yt.argmax(dim=-1)).to(torch.float32).mean()
+        return lossv, acc
+
+    # ------------------------------------------------------------------ weights back to the host model
+    def sync_to_model(self):
+        enc = self.encoder_model
+        for name in enc.weights:
+            if name in self.p and name not in self.head_names:
+                enc.weights[name] = self.p[name].detach().cpu().numpy().copy()
+            elif name in self.moving:
+                enc.weights[name] = self.moving[name].detach().cpu().numpy().copy()
+        target = self.model.head_weights if self.kind == "siamese" else enc.weights
+        for name in self.head_names:
+            target[name] = self.p[name].detach().cpu().numpy().copy()
+        if self.kind == "siamese":
+            self.model._head_dev = None
+
+    def gradients(self):
+        """Unscaled gradients as numpy arrays (tests)."""
+        return OrderedDict((k, (v / self.loss_scale).detach().cpu().numpy()) for k, v in self.g.items())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fit_generator (Keras 2.2.2 semantics for the subset the scripts use)
+# ----------------------------------------------------------------------------------------------------------------
+def _next_batch(gen_iter, generator, step):
+    if hasattr(generator, "__getitem__") and hasattr(generator, "__len__"):
+        return generator[step % len(generator)]
+    return next(gen_iter)
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size()
+    return None, 1
+
+
+def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
+                  validation_steps=None, initial_epoch=0):
+    """model.fit_generator(...) of experiments/train_siamese.py:65-94 / train_classifier.py:120-150."""
+    if model.loss is None or model.optimizer is None:
+        raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+    is_seq = hasattr(generator, "__getitem__") and hasattr(generator, "__len__")
+    if steps_per_epoch is None:
+        if not is_seq:
+            raise ValueError("`steps_per_epoch=None` is only valid for a generator based on the `Sequence` class.")
+        steps_per_epoch = len(generator)
+    trainer = getattr(model, "_trainer", None)
+    if trainer is None or trainer.optimizer is not model.optimizer or trainer.loss != model.loss:
+        trainer = TrainEngine(model, model.optimizer, model.loss)
+        model._trainer = trainer
+    dist, world = _dist_info()
+    allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    callbacks = list(callbacks or [])
+    for cb in callbacks:
+        cb.set_model(model)
+        cb.set_params(dict(epochs=epochs, steps=steps_per_epoch, verbose=verbose))
+        cb.on_train_begin()
+    gen_iter = None if is_seq else iter(generator)
+    val_iter = None
+    if validation_data is not None and not isinstance(validation_data, (tuple, list)):
+        val_iter = iter(validation_data)
+    history = []
+    for epoch in range(initial_epoch, epochs):
+        for cb in callbacks:
+            cb.on_epoch_begin(epoch)
+        losses, accs = [], []
+        for step in range(steps_per_epoch):
+            batch = _next_batch(gen_iter, generator, step)
+            x, y = batch[0], batch[1]
+            if trainer.kind == "siamese":
+                lv, acc = trainer.siamese_step(x[0], x[1], y, allreduce=allreduce, world=world)
+            else:
+                lv, acc = trainer.classifier_step(x, y, allreduce=allreduce, world=world)
+            losses.append(lv)
+            accs.append(acc)
+        logs = {"loss": float(torch.stack(losses).mean().item())}
+        if "accuracy" in (model.metrics or []) or "acc" in (model.metrics or []):
+            logs["acc"] = float(torch.stack(accs).mean().item())
+        trainer.sync_to_model()
+        if validation_data is not None:
+            vl, va = _validate(model, trainer, validation_data, val_iter, validation_steps)
+            logs["val_loss"] = vl
+            if "acc" in logs:
+                logs["val_acc"] = va
+        if is_seq:
+            generator.on_epoch_end()
+        for cb in callbacks:
+            cb.on_epoch_end(epoch, logs)
+        if verbose:
+            print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+        history.append(dict(logs))
+    for cb in callbacks:
+        cb.on_train_end()
+    return history
+
+
+def _validate(model, trainer, validation_data, val_iter, validation_steps):
+    """Eval-mode loss / accuracy (moving BN statistics, no dropout) over the validation batches, Keras-style
+    sample-weighted means.  Predictions come from the CUDA eval path; the scalar loss formulas run on the host."""
+    if val_iter is None:
+        batches = [validation_data]
+    else:
+        if validation_steps is None:
+            raise ValueError("`validation_steps` is required when validation_data is a generator")
+        batches = (next(val_iter) for _ in range(validation_steps))
+    tot, tl, ta = 0, 0.0, 0.0
+    for batch in batches:
+        x, y = batch[0], np.asarray(batch[1], dtype=np.float32)
+        pred = model.predict(x).astype(np.float32)
+        n = pred.shape[0]
+        if trainer.kind == "siamese":
+            y = y.reshape(-1, 1)
+            if model.loss == "contrastive_loss":
+                lv = float(np.mean((1 - y) * np.square(pred) + y * np.square(np.maximum(1 - pred, 0))))
+            else:
+                pc = np.clip(pred, np.float32(1e-7), np.float32(1 - 1e-7))
+                lv = float(np.mean(-y * np.log(pc) - (1 - y) * np.log(1 - pc)))
+            acc = float(np.mean((pred > 0.5).astype(np.float32) == y))
+        else:
+            pc = np.clip(pred / pred.sum(axis=-1, keepdims=True), 1e-7, 1 - 1e-7)
+            lv = float(np.mean(-(y * np.log(pc)).sum(axis=-1)))
+            acc = float(np.mean(pred.argmax(axis=-1) == y.argmax(axis=-1)))
+        tot += n
+        tl += lv * n
+        ta += acc * n
+    return tl / max(tot, 1), ta / max(tot, 1)

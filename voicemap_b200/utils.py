@@ -144,11 +144,86 @@ def n_shot_task_evaluation(model, dataset, preprocessor, num_tasks, n, k, networ
     return n_correct
 
 
+def n_shot_task_evaluation_batched(model, dataset, preprocessor, num_tasks, n, k, network_type='siamese',
+                                   distance='euclidean', tasks_per_launch=64):
+    """Same tasks, same preprocessing and same decision rule as ``n_shot_task_evaluation`` but the encoder runs
+    once per ``tasks_per_launch`` tasks instead of 1-2 tiny ``predict`` calls per task (the reference spends its
+    per-epoch evaluation in 500 batch-5 forwards: experiments/train_siamese.py:75-78, voicemap/utils.py:121-137).
+    Eval-mode embeddings do not depend on batch composition, so the count of correct tasks is identical for an
+    identical task sequence (tasks are drawn in the same order, one ``build_n_shot_task`` call each)."""
+    import torch
+    from .engine import pair_head_loss
+    siamese_direct = (n == 1 and network_type == 'siamese')
+    if siamese_direct:
+        encoder = model.encoder
+    elif network_type == 'siamese':
+        encoder = model.layers[2]
+    elif network_type == 'classifier':
+        encoder = clone_model(model)
+        encoder.set_weights(model.get_weights())
+        encoder.pop()
+    else:
+        raise ValueError('mode must be one of (siamese, classifier)')
+    if n < 1:
+        raise ValueError("n must be >= 1")
+    if distance not in ('euclidean', 'cosine', 'dot_product'):
+        raise ValueError('Distance must be in (euclidean, cosine, dot_product)')
+
+    n_correct = 0
+    done = 0
+    while done < num_tasks:
+        t = min(tasks_per_launch, num_tasks - done)
+        queries, supports = [], []
+        for _ in range(t):
+            query_sample, support_set_samples = dataset.build_n_shot_task(k, n)
+            if siamese_direct:
+                # the reference whitens [query]*k and the k supports as two separate batches
+                input_1 = np.stack([query_sample[0]] * k)[:, :, np.newaxis]
+                input_2 = support_set_samples[0][:, :, np.newaxis]
+                ([input_1, input_2], _) = preprocessor(([input_1, input_2], []))
+                queries.append(input_1[:1])
+                supports.append(input_2)
+            else:
+                queries.append(preprocessor.instance_preprocessor(query_sample[0].reshape(1, -1, 1)))
+                supports.append(preprocessor.instance_preprocessor(support_set_samples[0][:, :, np.newaxis]))
+        batch = np.concatenate(queries + supports, axis=0)
+        xt = encoder._host_batch(batch)
+        eng = encoder._get_engine()
+        emb = eng.forward(xt.to(eng.device, non_blocking=True))
+        eq, es = emb[:t], emb[t:].reshape(t, k * n, -1)
+        if siamese_direct:
+            w, b = model._head_device(eng.device)
+            e1 = eq[:, None, :].expand(t, k, eq.shape[1]).reshape(t * k, -1).contiguous()
+            prob, _, _ = pair_head_loss(e1, es.reshape(t * k, -1).contiguous(), w, b, model.distance_metric)
+            n_correct += int((prob.reshape(t, k).argmin(dim=1) == 0).sum().item())
+        else:
+            eqn, esn = eq.cpu().numpy(), es.cpu().numpy()
+            for i in range(t):
+                support_set_embeddings = esn[i]
+                if distance == 'euclidean':
+                    means = _class_means(support_set_embeddings, n, k)
+                    pred = np.sqrt(np.power(eqn[i:i + 1] - means, 2).sum(axis=1))
+                else:
+                    magnitudes = np.linalg.norm(support_set_embeddings, axis=1, keepdims=True)
+                    mean_units = _class_means(support_set_embeddings / magnitudes, n, k)
+                    if distance == 'cosine':
+                        q = eqn[i]
+                        pred = 1.0 - (mean_units @ q) / (np.linalg.norm(mean_units, axis=1) * np.linalg.norm(q))
+                    else:
+                        mean_magnitudes = magnitudes.reshape(k, n).sum(axis=1, keepdims=True) / n
+                        pred = -np.dot(eqn[i][np.newaxis, :], (mean_magnitudes * mean_units).T)
+                if np.argmin(pred) == 0:
+                    n_correct += 1
+        done += t
+    return n_correct
+
+
 class NShotEvaluationCallback(Callback):
     """Evaluate a network on n-shot classification tasks after every epoch (voicemap/utils.py:219-252)."""
 
-    def __init__(self, num_tasks, n_shot, k_way, dataset, preprocessor=lambda x: x, mode='siamese'):
+    def __init__(self, num_tasks, n_shot, k_way, dataset, preprocessor=lambda x: x, mode='siamese', batch_tasks=0):
         super(NShotEvaluationCallback, self).__init__()
+        self.batch_tasks = batch_tasks  # > 0: evaluate that many tasks per encoder launch (same result)
         self.num_tasks = num_tasks
         self.n_shot = n_shot
         self.k_way = k_way
@@ -159,8 +234,13 @@ class NShotEvaluationCallback(Callback):
 
     def on_epoch_end(self, epoch, logs=None):
         logs = logs if logs is not None else {}
-        n_correct = n_shot_task_evaluation(self.model, self.dataset, self.preprocessor, self.num_tasks, self.n_shot,
-                                           self.k_way, network_type=self.mode)
+        if self.batch_tasks > 0:
+            n_correct = n_shot_task_evaluation_batched(self.model, self.dataset, self.preprocessor, self.num_tasks,
+                                                       self.n_shot, self.k_way, network_type=self.mode,
+                                                       tasks_per_launch=self.batch_tasks)
+        else:
+            n_correct = n_shot_task_evaluation(self.model, self.dataset, self.preprocessor, self.num_tasks,
+                                               self.n_shot, self.k_way, network_type=self.mode)
         n_shot_acc = n_correct * 1. / self.num_tasks
         logs['val_{}-shot_acc'.format(self.n_shot)] = n_shot_acc
         print('val_{}-shot_acc: {:.4f}'.format(self.n_shot, n_shot_acc))
