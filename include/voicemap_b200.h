@@ -147,12 +147,14 @@ int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L,
                      const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
                      void* stream);
 int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
+/* bytes of the `red_scratch` buffer the two-stage (deterministic, atomics-free) channel reductions need */
+size_t vm_reduce_scratch_bytes(int G, int C);
 
 /* Batch statistics -> bn_const (G, C) x {s, t, mean, rstd}; Keras moving-average update (momentum .99, sample
  * variance n/(n-(1+eps))) applied once per group, in order.  moving_* may be NULL. */
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
-                         float* moving_var, float* bn_const, void* stream);
+                         float* moving_var, float* bn_const, double* red_scratch, void* stream);
 /* y = bn(u) * mask -> MaxPool1D(pool) -> fp16 planes (N, L/pool, C) for the next block's forward conv, and
  * (optional, both or neither) the same values as bf16 planes for vm_wgrad3 (the tensor core cannot mix fp16 with
  * bf16 operands).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
@@ -176,7 +178,7 @@ int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, 
 int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
               int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
               float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
-              float* dbias, void* stream);
+              float* dbias, double* red_scratch, void* stream);
 /* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; x_* and du_* are bf16 planes;
  * partial: scratch. */
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,

@@ -157,16 +157,21 @@ def _t(a, dtype):
     return torch.as_tensor(np.asarray(a)).to(dtype)
 
 
-def conv1d_same_relu(x, kernel, bias):
+def conv1d_same_relu(x, kernel, bias, relu_mask=None):
     """keras.layers.Conv1D(filters, K, padding='same', activation='relu')
     (voicemap/models.py:13,16,22,27,32).  Cross-correlation, stride 1, zero pad
-    left (K-1)//2, right K-1-left (K=32 -> 15/16)."""
+    left (K-1)//2, right K-1-left (K=32 -> 15/16).
+    ``relu_mask`` (N, L, Cout), optional: use this 0/1 pattern instead of (pre-activation > 0).  Gradient tests pass
+    the device's own activation pattern so that a pre-activation within rounding of zero (where fp32 and fp64
+    legitimately disagree on the ReLU branch) does not turn into a spurious gradient mismatch."""
     k = kernel.shape[0]
     left = (k - 1) // 2
     right = k - 1 - left
     xin = F.pad(x.transpose(1, 2), (left, right))                  # (N, Cin, L+K-1)
     w = kernel.permute(2, 1, 0).contiguous()                       # (Cout, Cin, K)
     y = F.conv1d(xin, w, bias)
+    if relu_mask is not None:
+        return (y * relu_mask.transpose(1, 2)).transpose(1, 2)
     return torch.relu(y).transpose(1, 2)                           # (N, L, Cout)
 
 
@@ -336,14 +341,15 @@ def bn_moving_update(moving_mean, moving_var, mean, var, n, momentum=BN_MOMENTUM
             moving_var * momentum + var_unbiased * (1.0 - momentum))
 
 
-def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=None):
+def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=None, relu_masks=None):
     """Train-mode encoder on torch tensors (autograd-capable).  x (N, L, 1); P: dict name -> tensor.
     dropout_masks: optional list of 4 keep-masks (N, 1, C) already scaled by 1/(1-p) (SpatialDropout1D,
     voicemap/models.py:18,24,29,34).  Returns emb and per-block (mean, var, count)."""
     h = x
     stats = []
     for i in range(1, 5):
-        h = conv1d_same_relu(h, P[f"conv{i}_kernel"], P[f"conv{i}_bias"])
+        h = conv1d_same_relu(h, P[f"conv{i}_kernel"], P[f"conv{i}_bias"], relu_mask=None if relu_masks is None
+                             else relu_masks[i - 1])
         if keep is not None:          # expose d loss / d u (post-ReLU, pre-BN) to the kernel-level tests
             h.retain_grad()
             keep.append(h)
@@ -361,7 +367,8 @@ TRAINABLE_SUFFIXES = ("kernel", "bias", "gamma", "beta")
 
 
 def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_crossentropy",
-                             distance_metric="uniform_euclidean", dtype=torch.float64, dropout_masks=(None, None)):
+                             distance_metric="uniform_euclidean", dtype=torch.float64, dropout_masks=(None, None),
+                             relu_masks=(None, None)):
     """One training-mode forward/backward of build_siamese_net (voicemap/models.py:49-79) with the loss of
     experiments/train_siamese.py:57 ('binary_crossentropy') or siamese_contrastive_loss.py:70 (contrastive_loss).
     The shared encoder is applied once per branch, so BN batch statistics are per branch.
@@ -371,8 +378,9 @@ def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_cro
     hw = _t(np.asarray(head_w, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
     hb = _t(np.asarray(head_b, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
     k1, k2 = [], []
-    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0], keep=k1)
-    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1], keep=k2)
+    rm = [None if m is None else [_t(a, dtype) for a in m] for m in relu_masks]
+    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0], keep=k1, relu_masks=rm[0])
+    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1], keep=k2, relu_masks=rm[1])
     diff = e1 - e2
     if distance_metric == "uniform_euclidean":
         d = torch.sqrt(torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=0.0))
@@ -401,14 +409,15 @@ def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_cro
 
 
 def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dtype=torch.float64,
-                                dropout_masks=None):
+                                dropout_masks=None, relu_masks=None):
     """Encoder + Dense(num_classes, softmax) + categorical_crossentropy
     (experiments/train_classifier.py:110-115), training mode."""
     P = {k: _t(v, dtype).clone().requires_grad_(any(k.endswith(s) for s in TRAINABLE_SUFFIXES))
          for k, v in params.items()}
     hk = _t(head_kernel, dtype).clone().requires_grad_(True)
     hb = _t(head_bias, dtype).clone().requires_grad_(True)
-    emb, stats = _encoder_forward_train_torch(_t(x, dtype), P, dropout_masks=dropout_masks)
+    rm = None if relu_masks is None else [_t(a, dtype) for a in relu_masks]
+    emb, stats = _encoder_forward_train_torch(_t(x, dtype), P, dropout_masks=dropout_masks, relu_masks=rm)
     logits = emb @ hk + hb
     logp = torch.log_softmax(logits, dim=-1)
     lv = -(_t(y_onehot, dtype) * logp).sum(dim=-1).mean()

@@ -55,14 +55,15 @@ SIGNATURES = {
     "vm_conv1_raw_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_raw_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "vm_stat_rows_per_clip": (_i, [_i]),
-    "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "vm_reduce_scratch_bytes": (_sz, [_i, _i]),
     "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_gmax_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp]),
+                       _vp, _vp]),
     "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "vm_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _f, _vp]),

@@ -205,6 +205,7 @@ int vm_pack_conv3_dgrad(const float* kernel, int cin, int cout, void* wpack, flo
   return launch_pack_conv3_dgrad(kernel, cin, cout, wpack, epi, ST);
 }
 int vm_stat_rows_per_clip(int L) { return 2 * ((L + 255) / 256); }
+size_t vm_reduce_scratch_bytes(int G, int C) { return size_t(G > 0 ? G : 1) * 32 * size_t(C) * 16; }
 
 int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
                      float* stat_partial, int precision, void* stream) {
@@ -222,9 +223,9 @@ int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L,
 }
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
-                         float* moving_var, float* bn_const, void* stream) {
+                         float* moving_var, float* bn_const, double* red_scratch, void* stream) {
   return launch_bn_stats_finalize(stat_partial, rows_per_clip, vm_padded_channels(C), N, G, L, C, gamma, beta, eps,
-                                  momentum, moving_mean, moving_var, bn_const, ST);
+                                  momentum, moving_mean, moving_var, bn_const, red_scratch, ST);
 }
 int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
                    uint16_t* out_hi, uint16_t* out_lo, uint16_t* bf_hi, uint16_t* bf_lo, void* stream) {
@@ -251,9 +252,9 @@ int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, 
 int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
               int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
               float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
-              float* dbias, void* stream) {
+              float* dbias, double* red_scratch, void* stream) {
   return launch_bn_bwd(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks, bwd_const,
-                       dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f, dbias, ST);
+                       dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch, ST);
 }
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
               int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream) {

@@ -86,7 +86,7 @@ int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int 
 // ---- training elementwise / reduction kernels (vm_train.cu) ----
 int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,
                              const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
-                             float* moving_var, float* bn_const, cudaStream_t st);
+                             float* moving_var, float* bn_const, double* red_scratch, cudaStream_t st);
 int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
                        const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
                        cudaStream_t st);
@@ -101,7 +101,7 @@ int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const 
 int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
                   int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
                   float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
-                  float* dbias, cudaStream_t st);
+                  float* dbias, double* red_scratch, cudaStream_t st);
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
                      float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
 int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);

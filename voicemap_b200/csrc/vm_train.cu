@@ -27,9 +27,54 @@ static int check_launch_t(const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Deterministic two-stage column reduction of a (rows, stride) fp32 matrix with NC interleaved components per entry
+// (NC = 2: float2 {a, b}; NC = 1: float).  Stage 1: grid (ceil(C/32), G*kRB), block (32, 8): row block rb of group
+// g -> tmp[(g*kRB + rb)][c] (double2).  Stage 2 (inside the finalize kernels): sum the kRB partials per (g, c).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRB = 32;
+
+template <int NC>
+__global__ void rowsum_stage1_kernel(const float* __restrict__ m, size_t rows_per_group, int stride, int C,
+                                     double2* __restrict__ tmp) {
+  __shared__ double2 sm[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = blockIdx.y / kRB, rb = blockIdx.y % kRB;
+  const size_t per = (rows_per_group + kRB - 1) / kRB;
+  const size_t r0 = size_t(g) * rows_per_group + size_t(rb) * per;
+  const size_t r1 = min(size_t(g + 1) * rows_per_group, r0 + per);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      if (NC == 2) {
+        const float2 v = reinterpret_cast<const float2*>(m)[r * stride + c];
+        a += double(v.x);
+        b += double(v.y);
+      } else {
+        a += double(m[r * stride + c]);
+      }
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = make_double2(a, b);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) { a += sm[k][threadIdx.x].x; b += sm[k][threadIdx.x].y; }
+    tmp[size_t(blockIdx.y) * C + c] = make_double2(a, b);
+  }
+}
+__device__ __forceinline__ double2 rowsum_stage2(const double2* __restrict__ tmp, int g, int C, int c) {
+  double a = 0.0, b = 0.0;
+  for (int rb = 0; rb < kRB; ++rb) {
+    const double2 v = tmp[(size_t(g) * kRB + rb) * C + c];
+    a += v.x;
+    b += v.y;
+  }
+  return make_double2(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
 // batch statistics -> BN constants {s, t, mean, rstd} per (group, channel); moving-average update
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_stats_finalize_kernel(const float2* __restrict__ partial, int rows_per_clip, int c_pad, int N,
+__global__ void bn_stats_finalize_kernel(const double2* __restrict__ tmp, int N,
                                          int G, int L, int C, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* __restrict__ moving_mean, float* __restrict__ moving_var,
@@ -41,13 +86,8 @@ __global__ void bn_stats_finalize_kernel(const float2* __restrict__ partial, int
   float mm = moving_mean ? moving_mean[c] : 0.f;
   float mv = moving_var ? moving_var[c] : 0.f;
   for (int g = 0; g < G; ++g) {
-    double s1 = 0.0, s2 = 0.0;
-    const size_t r0 = size_t(g) * clips * rows_per_clip;
-    for (size_t r = 0; r < size_t(clips) * rows_per_clip; ++r) {
-      const float2 v = partial[(r0 + r) * c_pad + c];
-      s1 += double(v.x);
-      s2 += double(v.y);
-    }
+    const double2 sums = rowsum_stage2(tmp, g, C, c);
+    const double s1 = sums.x, s2 = sums.y;
     const double mean = s1 / cnt;
     double var = s2 / cnt - mean * mean;  // biased batch variance (tf.nn.moments)
     if (var < 0.0) var = 0.0;
@@ -351,7 +391,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ u, const float* _
 }
 
 // pass 2: per (group, channel) means -> bwd constants {s, mean_dy, mean_dyxhat, 0}; dgamma/dbeta summed over groups.
-__global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int rows_per_clip, int N, int G, int L,
+__global__ void bn_bwd_finalize_kernel(const double2* __restrict__ tmp, int N, int G, int L,
                                        int C, const float4* __restrict__ bn_const, float4* __restrict__ bwd_const,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,13 +400,8 @@ __global__ void bn_bwd_finalize_kernel(const float2* __restrict__ partial, int r
   const double cnt = double(clips) * double(L);
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
-    double s1 = 0.0, s2 = 0.0;
-    const size_t r0 = size_t(g) * clips * rows_per_clip;
-    for (size_t r = 0; r < size_t(clips) * rows_per_clip; ++r) {
-      const float2 v = partial[(r0 + r) * C + c];
-      s1 += double(v.x);
-      s2 += double(v.y);
-    }
+    const double2 sums = rowsum_stage2(tmp, g, C, c);
+    const double s1 = sums.x, s2 = sums.y;
     bwd_const[size_t(g) * C + c] = make_float4(bn_const[size_t(g) * C + c].x, float(s1 / cnt), float(s2 / cnt), 0.f);
     tb += s1;
     tg += s2;
@@ -446,13 +481,10 @@ __global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __r
   }
 }
 
-// column sums of a (rows, C) fp32 matrix -> out[C]
-__global__ void colsum_kernel(const float* __restrict__ m, size_t rows, int C, float* __restrict__ out) {
+// second stage of a plain column sum -> out[C]
+__global__ void colsum_finalize_kernel(const double2* __restrict__ tmp, int C, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (size_t r = 0; r < rows; ++r) s += double(m[r * C + c]);
-  out[c] = float(s);
+  if (c < C) out[c] = float(rowsum_stage2(tmp, 0, C, c).x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -498,10 +530,13 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,
                              const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
-                             float* moving_var, float* bn_const, cudaStream_t st) {
+                             float* moving_var, float* bn_const, double* red_scratch, cudaStream_t st) {
   if (N <= 0 || G <= 0 || N % G != 0 || C <= 0) return set_error(VM_ERR_SHAPE, "bn_stats_finalize: bad shape");
-  bn_stats_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float2*>(partial), rows_per_clip,
-                                                        c_pad, N, G, L, C, gamma, beta, eps, momentum, moving_mean,
+  if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_stats_finalize: reduction scratch missing");
+  double2* tmp = reinterpret_cast<double2*>(red_scratch);
+  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp);
+  bn_stats_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, N, G, L, C, gamma, beta, eps, momentum, moving_mean,
                                                         moving_var, reinterpret_cast<float4*>(bn_const));
   return check_launch_t("bn_stats_finalize");
 }
@@ -553,7 +588,9 @@ int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const 
 int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
                   int G, int pool, const float* bn_const, const float* mask, float* partial /* N*chunks*C float2 */,
                   int chunks /* partial buffers hold N*chunks*max(1,512/C) rows */, float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo,
-                  float* dbias_partial /* N*chunks*C */, float* dbias, cudaStream_t st) {
+                  float* dbias_partial /* N*chunks*C */, float* dbias, double* red_scratch, cudaStream_t st) {
+  if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd: reduction scratch missing");
+  double2* tmp = reinterpret_cast<double2*>(red_scratch);
   if (N % G != 0 || chunks <= 0) return set_error(VM_ERR_SHAPE, "bn_bwd: bad shape");
   if ((dy_pooled == nullptr) == (d_gmax == nullptr)) return set_error(VM_ERR_SHAPE, "bn_bwd: give dy_pooled xor d_gmax");
   if (C % 4 != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: C must be a multiple of 4");
@@ -561,12 +598,16 @@ int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, c
   const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;  // must match the kernels' thread layout
   bn_bwd_reduce_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc, mask,
                                                         reinterpret_cast<float2*>(partial));
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float2*>(partial), chunks * nstream, N, G,
-                                                      L, C, bc, reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
+  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * chunks * nstream, C, C, tmp);
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, N, G, L, C, bc, reinterpret_cast<float4*>(bwd_const), dgamma,
+                                                      dbeta);
   bn_relu_bwd_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc,
                                                       reinterpret_cast<const float4*>(bwd_const), mask, du_hi, du_lo,
                                                       dbias_partial);
-  colsum_kernel<<<(C + 63) / 64, 64, 0, st>>>(dbias_partial, size_t(N) * chunks * nstream, C, dbias);
+  rowsum_stage1_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial,
+                                                                           size_t(N) * chunks * nstream, C, C, tmp);
+  colsum_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, C, dbias);
   return check_launch_t("bn_bwd");
 }
 

@@ -113,8 +113,9 @@ class EncoderEngine:
             nbytes += self.lib.vm_preprocess_scratch_bytes(n) if nbytes else 0
             if nbytes == 0:
                 raise ValueError(f"input of shape ({n}, {length}) is too short for the encoder (L >= 32)")
-            self._workspace = None
-            self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            if self._workspace is None or self._workspace.numel() < nbytes + 1024:   # grow-only
+                self._workspace = None
+                self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             self._ws_key = key
         base = self._workspace.data_ptr()
         return C.c_void_p((base + 1023) // 1024 * 1024)

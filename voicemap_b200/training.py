@@ -150,6 +150,7 @@ class TrainEngine:
         scr_elems = nb * _BWD_CHUNKS * max(512, max(c))
         self.scr2 = torch.empty((scr_elems, 2), dtype=f32, device=dev)
         self.scr1 = torch.empty((scr_elems,), dtype=f32, device=dev)
+        self.red = torch.empty(self.lib.vm_reduce_scratch_bytes(groups, max(c)) // 8, dtype=torch.float64, device=dev)
         # wgrad split partials (the launcher lowers its split count to fit) / wgrad1 per-CTA partials
         w1_bytes = nb * ((ls[0] + 1023) // 1024) * 32 * c[0] * 4
         self.wpart = torch.empty(max(64 << 20, w1_bytes) // 4, dtype=f32, device=dev)
@@ -209,7 +210,7 @@ class TrainEngine:
             rc = lib.vm_bn_stats_finalize(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, ls[b], c[b],
                                           _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
                                           C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
-                                          _ptr(self.bnc[b]), st)
+                                          _ptr(self.bnc[b]), _ptr(self.red), st)
             _check(rc, "vm_bn_stats_finalize")
             if b < 3:
                 rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, POOLS[b], _ptr(self.bnc[b]),
@@ -246,7 +247,8 @@ class TrainEngine:
             rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, POOLS[b],
                                _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
                                _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
-                               _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), st)
+                               _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
+                               _ptr(self.red), st)
             _check(rc, f"vm_bn_bwd block {b + 1}")
             if b == 0:
                 rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], _ptr(self.wpart),
