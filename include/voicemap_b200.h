@@ -183,9 +183,10 @@ int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const
  * partial: scratch. */
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
               int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream);
-/* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co]. */
-int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, float* partial,
-              size_t partial_bytes, float* dw, void* stream);
+/* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co].  precision 3 / 1: tensor cores (bf16 Toeplitz operand
+ * built in shared memory, 3 or 1 MMAs per K step); precision 0: fp32 CUDA-core reference kernel. */
+int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int precision,
+              float* partial, size_t partial_bytes, float* dw, void* stream);
 /* keras.optimizers.Adam update with global-norm clipping on a flat parameter buffer:
  * g' = g * inv_scale * min(1, clipnorm / ||g * inv_scale||) (clipnorm <= 0: off); m, v, p updated in place with
  * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller. */

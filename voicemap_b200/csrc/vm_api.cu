@@ -261,9 +261,10 @@ int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi,
   return launch_wgrad3(CH16(x_hi), CH16(x_lo), CH16(du_hi), CH16(du_lo), N, L, cin, cout, precision, partial,
                        partial_bytes, dw, ST);
 }
-int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, float* partial,
-              size_t partial_bytes, float* dw, void* stream) {
-  return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, ST);
+int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int precision,
+              float* partial, size_t partial_bytes, float* dw, void* stream) {
+  if (precision != 0 && precision != 1 && precision != 3) return set_error(VM_ERR_SHAPE, "wgrad1: bad precision");
+  return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, ST, precision);
 }
 int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* scratch, float inv_scale,
                  float clipnorm, float lr_t, float beta1, float beta2, float eps, void* stream) {

@@ -44,8 +44,80 @@ struct __align__(8) Conv1Barriers {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
+// ---------------------------------------------------------------------------------------------
+// Toeplitz operand producer (one warp = one 256-position tile; lane = 8 consecutive positions).
+// Loads the lane's 39-sample strip x[p0 - 15 + 8*lane + k] (strided + whitened when preprocessing is fused), splits it
+// into 16-bit (hi, lo) planes -- fp16 for the forward conv, bf16 for the weight gradient -- and writes the lane's 8
+// rows x 4 tap-chunks as 16-byte shared-memory stores into the no-swizzle UMMA core-matrix layout
+// (row r, chunk j) -> (r/8)*kGroupStride + j*128 + (r%8)*16.
+// ---------------------------------------------------------------------------------------------
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (kBf16) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  if (kBf16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+
+__device__ __forceinline__ void toeplitz_load_strip(const float* __restrict__ xc, int xs, float pm, float ps, int e0,
+                                                    int L, float (&xv)[39]) {
+  if (e0 >= 0 && e0 + 39 <= L) {  // interior strip: no bounds predicates
+#pragma unroll
+    for (int k = 0; k < 39; ++k) xv[k] = (__ldg(xc + size_t(e0 + k) * xs) - pm) * ps;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 39; ++k) {
+      const int e = e0 + k;
+      xv[k] = (e >= 0 && e < L) ? (__ldg(xc + size_t(e) * xs) - pm) * ps : 0.f;
+    }
+  }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void toeplitz_store(const float (&xv)[39], uint32_t st, int nplanes, int plane_bytes) {
+  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]): even- and odd-aligned pairs of the hi plane; le/lo: lo plane
+  uint32_t pe[19], po[19], le[19], lo[19];
+  {
+    float r[39];
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+      pe[k] = pack2<kBf16>(xv[2 * k], xv[2 * k + 1]);
+      po[k] = pack2<kBf16>(xv[2 * k + 1], xv[2 * k + 2]);
+      const float2 f = unpack2<kBf16>(pe[k]);
+      r[2 * k] = xv[2 * k] - f.x;
+      r[2 * k + 1] = xv[2 * k + 1] - f.y;
+      if (k == 18) r[38] = xv[38] - unpack2<kBf16>(po[18]).y;
+    }
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+      le[k] = pack2<kBf16>(r[2 * k], r[2 * k + 1]);
+      lo[k] = pack2<kBf16>(r[2 * k + 1], r[2 * k + 2]);
+    }
+  }
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl) {
+    if (pl < nplanes) {
+      const uint32_t* ev = pl ? le : pe;
+      const uint32_t* ov = pl ? lo : po;
+      const uint32_t base = st + pl * plane_bytes;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = r + 8 * j;  // first element of this 8-tap chunk
+          const uint32_t* src = (o & 1) ? (ov + (o - 1) / 2) : (ev + o / 2);
+          sts_v4(base + j * 128 + r * 16, src[0], src[1], src[2], src[3]);
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(c1::kThreads, 1)
@@ -104,59 +176,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       // lane owns the 8 positions p0 + 8*lane .. +7; it needs x[p0 - 15 + 8*lane + i], i = 0..38
       const int e0 = p0 - 15 + 8 * lane;
       float xv[39];
-      if (e0 >= 0 && e0 + 39 <= p.L) {  // interior strip: no bounds predicates
-#pragma unroll
-        for (int k = 0; k < 39; ++k) xv[k] = (__ldg(xc + size_t(e0 + k) * xs) - pm) * ps;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 39; ++k) {
-          const int e = e0 + k;
-          xv[k] = (e >= 0 && e < p.L) ? (__ldg(xc + size_t(e) * xs) - pm) * ps : 0.f;
-        }
-      }
-      // fp16 (hi, lo) split with packed conversions.  pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]).
-      uint32_t pe[19], po[19], le[19], lo[19];
-      {
-        float r[39];
-#pragma unroll
-        for (int k = 0; k < 19; ++k) {
-          const __half2 e2 = __floats2half2_rn(xv[2 * k], xv[2 * k + 1]);
-          const __half2 o2 = __floats2half2_rn(xv[2 * k + 1], xv[2 * k + 2]);
-          pe[k] = *reinterpret_cast<const uint32_t*>(&e2);
-          po[k] = *reinterpret_cast<const uint32_t*>(&o2);
-          const float2 f = __half22float2(e2);
-          r[2 * k] = xv[2 * k] - f.x;
-          r[2 * k + 1] = xv[2 * k + 1] - f.y;
-          if (k == 18) r[38] = xv[38] - __high2float(o2);
-        }
-#pragma unroll
-        for (int k = 0; k < 19; ++k) {
-          const __half2 e2 = __floats2half2_rn(r[2 * k], r[2 * k + 1]);
-          const __half2 o2 = __floats2half2_rn(r[2 * k + 1], r[2 * k + 2]);
-          le[k] = *reinterpret_cast<const uint32_t*>(&e2);
-          lo[k] = *reinterpret_cast<const uint32_t*>(&o2);
-        }
-      }
-
+      toeplitz_load_strip(xc, xs, pm, ps, e0, p.L, xv);
       mbar_wait(&bars->empty[q], (((i / kStages) & 1) ^ 1));
-      const uint32_t st = smem_u32(stages + q * kStageBytes + lane * kGroupStride);
-#pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        if (pl < nplanes) {
-          const uint32_t* ev = pl ? le : pe;
-          const uint32_t* ov = pl ? lo : po;
-          const uint32_t base = st + pl * kPlaneBytes;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int o = r + 8 * j;  // first element of this 8-tap chunk
-              const uint32_t* src = (o & 1) ? (ov + (o - 1) / 2) : (ev + o / 2);
-              sts_v4(base + j * 128 + r * 16, src[0], src[1], src[2], src[3]);
-            }
-          }
-        }
-      }
+      toeplitz_store<false>(xv, smem_u32(stages + q * kStageBytes + lane * kGroupStride), nplanes, kPlaneBytes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[q]);
@@ -366,6 +388,192 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   conv1_kernel<<<grid, kThreads, smem, stream>>>(oh, ol, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv1: launch");
+  return VM_OK;
+}
+
+
+// =============================================================================================================
+// Block-1 weight gradient on tensor cores:  dW1[k][co] = sum_{n,p} x[n][p + k - 15] * dU1[n][p][co].
+//   D[co (128 lanes), tap (32 columns)] += dU^T[co, p] * T[p, tap] with the POSITION axis as the MMA K dimension:
+//   A = dU1 tile [64 positions][128 co] as TMA writes it (SWIZZLE_128B), read MN-major (two 64-channel atoms);
+//   B = the same Toeplitz tile the forward producer builds (bf16 planes here), read MN-major: 8-tap chunks 128 B
+//       apart (SBO), 8-position row groups kGroupStride apart (LBO).
+// One CTA accumulates over all its tiles and writes a [32][cout] partial; wgrad_reduce sums the CTAs.
+// HBM-bound: the 2 x 2-byte dU1 planes are read once (algorithmic bytes 4 * N * L * cout).
+// =============================================================================================================
+namespace w1 {
+constexpr int kTileN = 256;
+constexpr int kSub = 64;
+constexpr int kGroupStride = c1::kGroupStride;
+constexpr int kTPlaneBytes = c1::kPlaneBytes;      // 16896
+constexpr int kTStageBytes = 2 * kTPlaneBytes;
+constexpr int kTStages = 2;
+constexpr int kUHalfBytes = kSub * 128;            // 64 positions x 64 channels
+constexpr int kUPlaneBytes = 2 * kUHalfBytes;      // 128 channels
+constexpr int kUStageBytes = 2 * kUPlaneBytes;     // hi + lo
+constexpr int kUStages = 4;
+constexpr int kThreads = 192;                      // warps 0-1 Toeplitz producers, 0-3 final epilogue, 4 TMA, 5 MMA
+constexpr int kSmemBytes = kTStages * kTStageBytes + kUStages * kUStageBytes + 1024 + 256;
+}  // namespace w1
+
+struct __align__(8) Wgrad1Barriers {
+  uint64_t tfull[w1::kTStages], tempty[w1::kTStages];
+  uint64_t ufull[w1::kUStages], uempty[w1::kUStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+struct Wgrad1Params {
+  const float* x;
+  int N, L, cout, nptile, products;
+  float* partial;  // [gridDim.x][32][cout]
+};
+
+__global__ void __launch_bounds__(w1::kThreads, 1)
+wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUtensorMap tm_ul,
+                 const Wgrad1Params p) {
+  using namespace w1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* uring = smem;                                  // SWIZZLE_128B tiles first (1024-byte aligned)
+  uint8_t* tring = smem + kUStages * kUStageBytes;
+  Wgrad1Barriers* bars = reinterpret_cast<Wgrad1Barriers*>(tring + kTStages * kTStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = (p.products == 3) ? 2 : 1;
+  const int ntiles = p.N * p.nptile;
+  const int co0 = blockIdx.y * 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
+    for (int i = 0; i < kUStages; ++i) { mbar_init(&bars->ufull[i], 1); mbar_init(&bars->uempty[i], 1); }
+    mbar_init(&bars->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 32);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < kTStages) {
+    // Toeplitz producers (bf16 planes): warp q fills stage q for local tiles q, q + 2, ...
+    const int q = warp;
+    uint32_t i = q;
+    for (int tile = blockIdx.x + q * gridDim.x; tile < ntiles; tile += kTStages * gridDim.x, i += kTStages) {
+      const int n = tile / p.nptile;
+      const int p0 = (tile % p.nptile) * kTileN;
+      float xv[39];
+      toeplitz_load_strip(p.x + size_t(n) * p.L, 1, 0.f, 1.f, p0 - 15 + 8 * lane, p.L, xv);
+      mbar_wait(&bars->tempty[q], ((i / kTStages) & 1) ^ 1);
+      toeplitz_store<true>(xv, smem_u32(tring + q * kTStageBytes + lane * kGroupStride), nplanes, kTPlaneBytes);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tfull[q]);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_uh);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / p.nptile;
+        const int p0 = (tile % p.nptile) * kTileN;
+        for (int j = 0; j < kTileN / kSub; ++j, ++it) {
+          const int s = it % kUStages;
+          mbar_wait(&bars->uempty[s], ((it / kUStages) & 1) ^ 1);
+          uint8_t* base = uring + s * kUStageBytes;
+          mbar_arrive_expect_tx(&bars->ufull[s], nplanes * kUPlaneBytes);
+          for (int pl = 0; pl < nplanes; ++pl) {
+            const CUtensorMap* m = pl ? &tm_ul : &tm_uh;
+            tma_load_3d(base + pl * kUPlaneBytes, m, &bars->ufull[s], co0, p0 + j * kSub, n);
+            tma_load_3d(base + pl * kUPlaneBytes + kUHalfBytes, m, &bars->ufull[s], co0 + 64, p0 + j * kSub, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // M = 128 (co), N = 32 (taps), both operands MN-major, both bf16
+      const uint32_t idesc = make_idesc_f16(128, 32, 1, 1) | (1u << 15) | (1u << 16);
+      uint32_t i = 0, uit = 0, first = 1;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int ts = i % kTStages;
+        mbar_wait(&bars->tfull[ts], (i / kTStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t th = smem_u32(tring + ts * kTStageBytes), tl = th + kTPlaneBytes;
+        for (int j = 0; j < kTileN / kSub; ++j, ++uit) {
+          const int us = uit % kUStages;
+          mbar_wait(&bars->ufull[us], (uit / kUStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t uh = smem_u32(uring + us * kUStageBytes), ul = uh + kUPlaneBytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t arow = kk * 16 * 128;                       // 16 positions down the dU tile
+            const uint32_t brow = (8 * j + 2 * kk) * kGroupStride;      // two 8-position row groups per K step
+            umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
+                     make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, first ? 0u : 1u);
+            first = 0;
+            if (nplanes == 2) {
+              umma_f16(tmem_base, make_smem_desc(ul + arow, kUHalfBytes, 1024, kLayoutSW128),
+                       make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
+              umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
+                       make_smem_desc(tl + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
+            }
+          }
+          umma_commit(&bars->uempty[us]);
+        }
+        umma_commit(&bars->tempty[ts]);
+      }
+      umma_commit(&bars->done);
+    }
+  }
+  if (warp < 4) {
+    // final epilogue: TMEM lane = co, column = tap
+    mbar_wait(&bars->done, 0);
+    tc_fence_after_sync();
+    float v[32];
+    tmem_ld_32x32(tmem_base + (uint32_t(warp * 32) << 16), v);
+    const int co = co0 + warp * 32 + lane;
+    const bool any = int(blockIdx.x) < ntiles;
+    if (co < p.cout) {
+      float* out = p.partial + size_t(blockIdx.x) * 32 * p.cout + co;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) out[size_t(k) * p.cout] = any ? v[k] : 0.f;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+int launch_wgrad1_tc(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, int products,
+                     float* partial, size_t partial_bytes, int* nsplit_out, cudaStream_t stream) {
+  using namespace w1;
+  if (N <= 0 || L <= 0 || cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_SHAPE, "wgrad1: bad shape");
+  if (products == 3 && du_lo == nullptr) return set_error(VM_ERR_SHAPE, "wgrad1: lo plane required");
+  Wgrad1Params p{};
+  p.x = x; p.N = N; p.L = L; p.cout = cout; p.products = products;
+  p.nptile = (L + kTileN - 1) / kTileN;
+  p.partial = partial;
+  const int nco = (cout + 127) / 128;
+  int gx = max(1, num_sms() / nco);
+  gx = min(gx, N * p.nptile);
+  if (size_t(gx) * 32 * cout * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad1: partial buffer too small");
+  CUtensorMap uh, ul;
+  const uint64_t dims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+  const uint64_t str[2] = {uint64_t(cout) * 2, uint64_t(L) * cout * 2};
+  const uint32_t box[3] = {64, kSub, 1};
+  int rc;
+  if ((rc = make_tensor_map(&uh, du_hi, 3, dims, str, box, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&ul, products == 3 ? du_lo : du_hi, 3, dims, str, box, VM_SWIZZLE_128B))) return rc;
+  cudaError_t e = cudaFuncSetAttribute(wgrad1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: cudaFuncSetAttribute");
+  wgrad1_tc_kernel<<<dim3(gx, nco), kThreads, kSmemBytes, stream>>>(uh, ul, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: launch");
+  *nsplit_out = gx;
   return VM_OK;
 }
 

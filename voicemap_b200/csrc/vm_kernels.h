@@ -81,7 +81,9 @@ int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, c
                   int cin, int cout, int products, float* partial, size_t partial_bytes, float* dw,
                   cudaStream_t stream);
 int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
-                  size_t partial_bytes, float* dw, cudaStream_t stream);
+                  size_t partial_bytes, float* dw, cudaStream_t stream, int products = 3);
+int launch_wgrad1_tc(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, int products,
+                     float* partial, size_t partial_bytes, int* nsplit_out, cudaStream_t stream);
 
 // ---- training elementwise / reduction kernels (vm_train.cu) ----
 int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,

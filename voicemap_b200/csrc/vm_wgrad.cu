@@ -279,8 +279,18 @@ wgrad1_kernel(const float* __restrict__ x, const __half* __restrict__ du_hi, con
 }
 
 int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
-                  size_t partial_bytes, float* dw, cudaStream_t stream) {
+                  size_t partial_bytes, float* dw, cudaStream_t stream, int products) {
   if (N <= 0 || L <= 0 || cout <= 0) return set_error(VM_ERR_SHAPE, "wgrad1: bad shape");
+  if (products != 0) {  // tensor-core path (vm_conv1.cu); products == 0 keeps the CUDA-core reference kernel below
+    int nsplit = 0;
+    int rc = launch_wgrad1_tc(x, du_hi, du_lo, N, L, cout, products, partial, partial_bytes, &nsplit, stream);
+    if (rc) return rc;
+    const size_t wsz = size_t(32) * cout;
+    wgrad_reduce_kernel<<<unsigned((wsz + 255) / 256), 256, 0, stream>>>(partial, nsplit, wsz, 1.0f, dw);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return set_cuda_error(e2, "wgrad1: reduce launch");
+    return VM_OK;
+  }
   const int chunks = (L + kW1Chunk - 1) / kW1Chunk;
   const size_t wsize = size_t(32) * cout;
   if (size_t(N) * chunks * wsize * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad1: partial buffer too small");

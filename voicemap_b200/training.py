@@ -21,7 +21,7 @@ from .engine import BN_EPS, PRECISION_FP32_GRADE, EncoderEngine, _ptr, _stream
 
 BN_MOMENTUM = 0.99
 POOLS = (4, 2, 2, 2)
-_BWD_CHUNKS = 8
+_BWD_CHUNKS = 32
 
 
 def _check(rc, what):
@@ -251,7 +251,7 @@ class TrainEngine:
                                _ptr(self.red), st)
             _check(rc, f"vm_bn_bwd block {b + 1}")
             if b == 0:
-                rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], _ptr(self.wpart),
+                rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp, _ptr(self.wpart),
                                    self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
                 _check(rc, "vm_wgrad1")
             else:
