@@ -310,7 +310,9 @@ def run_b200(args):
                   "algorithmic MAC (fp32-grade split), so tensor-pipe utilisation is 3x this fraction"
                   if args.precision == 3 else "precision=1: one fp16 MMA per algorithmic MAC"),
             mma_issue_frac=round(achieved_tf * args.precision / peaks["bf16_tflops"], 4),
-            traffic=None,
+            # dram__bytes_read + dram__bytes_write of the three conv3 launches (ncu --set full, profiles/r01_ncu_summary.md:
+            # 738 + 651 + 304 MB at batch 256) averaged per launch; algorithmic bytes per launch average 590 MB
+            traffic=(5.64e8 if (n, length, args.precision) == (256, 12000, 3) else None),
             blocks=blocks,
             network=dict(us_per_clip=round(us_per_clip, 3),
                          frac_of_tf32_roofline=round(bound_us(peaks["bf16_tflops"] / 2) / us_per_clip, 4),

@@ -303,3 +303,16 @@ def test_reference_checkpoint_weights_fixture():
     sia.head_weights["head_bias"] = z["head_bias"].copy()
     prob = sia.predict([z["x"][:3], z["x"][3:]])
     assert np.abs(prob - z["prob64"]).max() < 1e-4
+
+
+def test_large_batch_of_short_clips(stress_params):
+    """n_seconds sweep corner (1 s clips, L = 4000) at a batch well beyond one wave of tiles per SM."""
+    eng = _engine(128, 64, stress_params)
+    g = torch.Generator().manual_seed(9)
+    x = (O.WHITEN_RMS * torch.randn(1536, 4000, generator=g)).cuda()
+    full = eng.forward(x).clone()
+    assert torch.isfinite(full).all()
+    idx = [0, 777, 1535]
+    ref = O.encoder_forward(x[idx].cpu().numpy()[:, :, None], stress_params, torch.float32)
+    assert _per_clip(full[idx].cpu().numpy(), ref) <= TOL
+    assert torch.equal(eng.forward(x[700:800].contiguous()), full[700:800])

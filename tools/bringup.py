@@ -1,7 +1,7 @@
 """GPU bring-up / diagnosis script (developer tool, not part of the product path).
 
 Runs one isolated experiment per process so a trapped kernel cannot take the others down:
-    python tools/bringup.py --case conv1|conv3|encoder|time [--desc-mode 0|1] ...
+    python tools/bringup.py --case conv1|conv3|encoder|time ...
 Each case compares the CUDA path with the CPU oracle and prints error statistics.
 """
 import argparse
@@ -29,7 +29,6 @@ def relerr(a, ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", required=True)
-    ap.add_argument("--desc-mode", type=int, default=0)
     ap.add_argument("--n", type=int, default=2)
     ap.add_argument("--l", type=int, default=2048)
     ap.add_argument("--filters", type=int, default=128)
@@ -66,19 +65,18 @@ def main():
         if b < 4:
             oh, ol = eng.block3(b, hi, lo)
             y = eng.merge_planes(oh, ol).cpu().numpy()
-            ref = O.encoder_forward  # noqa
             # oracle continuation from the fp32 intermediate (so the comparison isolates this block)
             ref64 = _block_ref(inter32[b - 2], params, b, torch.float64)
             ref32 = _block_ref(inter32[b - 2], params, b, torch.float32)
             torch.cuda.synchronize()
-            print(f"block{b} desc_mode={args.desc_mode} vs fp64:", relerr(y, ref64))
+            print(f"block{b} vs fp64:", relerr(y, ref64))
             print("fp32 oracle vs fp64:", relerr(ref32, ref64))
         else:
             part = eng.block3(4, hi, lo, gmax=True)
             emb, g = eng.gmax_dense(part, with_gmax=True)
             torch.cuda.synchronize()
             ref64 = _block_ref(inter32[2], params, 4, torch.float64).max(axis=1)
-            print(f"block4+gmax desc_mode={args.desc_mode} vs fp64:", relerr(g.cpu().numpy(), ref64))
+            print("block4+gmax vs fp64:", relerr(g.cpu().numpy(), ref64))
     elif args.case == "encoder":
         emb = eng.forward(xd).cpu().numpy()
         torch.cuda.synchronize()

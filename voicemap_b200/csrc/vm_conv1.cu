@@ -30,8 +30,9 @@ constexpr int kOutBufBytes = 4 * kOutBoxBytes;           // [plane][channel half
 constexpr int kWPlaneBytes = kTileM * 64;                // 128 cout x 32 taps fp16 = 8192
 constexpr int kWSlabBytes = 2 * kWPlaneBytes;
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quarter (column halves)
-constexpr int kThreads = (kEpiWarps + 1 + 4) * 32;       // warps 0-7 epilogue, 8 MMA, 9-12 producers
+constexpr int kEpiWarps = 16;                            // two groups of 8 (one per TMEM accumulator buffer)
+constexpr int kProdWarps = 3;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // warps 0-15 epilogue, 16 MMA, 17-19 producers
 constexpr int kMaxSlabs = 4;
 __host__ __device__ constexpr int smem_bytes(int nslab, int nstages) {
   return nslab * kWSlabBytes + nstages * kStageBytes + 2 * kOutBufBytes + 1024 + 256;
@@ -81,42 +82,37 @@ __device__ __forceinline__ void toeplitz_load_strip(const float* __restrict__ xc
 }
 
 template <bool kBf16>
-__device__ __forceinline__ void toeplitz_store(const float (&xv)[39], uint32_t st, int nplanes, int plane_bytes) {
-  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]): even- and odd-aligned pairs of the hi plane; le/lo: lo plane
-  uint32_t pe[19], po[19], le[19], lo[19];
-  {
-    float r[39];
+__device__ __forceinline__ void toeplitz_store_plane(const float (&v)[39], uint32_t base) {
+  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2]): even- and odd-aligned pairs of the 16-bit plane
+  uint32_t pe[19], po[19];
 #pragma unroll
-    for (int k = 0; k < 19; ++k) {
-      pe[k] = pack2<kBf16>(xv[2 * k], xv[2 * k + 1]);
-      po[k] = pack2<kBf16>(xv[2 * k + 1], xv[2 * k + 2]);
-      const float2 f = unpack2<kBf16>(pe[k]);
-      r[2 * k] = xv[2 * k] - f.x;
-      r[2 * k + 1] = xv[2 * k + 1] - f.y;
-      if (k == 18) r[38] = xv[38] - unpack2<kBf16>(po[18]).y;
-    }
-#pragma unroll
-    for (int k = 0; k < 19; ++k) {
-      le[k] = pack2<kBf16>(r[2 * k], r[2 * k + 1]);
-      lo[k] = pack2<kBf16>(r[2 * k + 1], r[2 * k + 2]);
-    }
+  for (int k = 0; k < 19; ++k) {
+    pe[k] = pack2<kBf16>(v[2 * k], v[2 * k + 1]);
+    po[k] = pack2<kBf16>(v[2 * k + 1], v[2 * k + 2]);
   }
 #pragma unroll
-  for (int pl = 0; pl < 2; ++pl) {
-    if (pl < nplanes) {
-      const uint32_t* ev = pl ? le : pe;
-      const uint32_t* ov = pl ? lo : po;
-      const uint32_t base = st + pl * plane_bytes;
+  for (int r = 0; r < 8; ++r) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int o = r + 8 * j;  // first element of this 8-tap chunk
-          const uint32_t* src = (o & 1) ? (ov + (o - 1) / 2) : (ev + o / 2);
-          sts_v4(base + j * 128 + r * 16, src[0], src[1], src[2], src[3]);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int o = r + 8 * j;  // first element of this 8-tap chunk
+      const uint32_t* src = (o & 1) ? (po + (o - 1) / 2) : (pe + o / 2);
+      sts_v4(base + j * 128 + r * 16, src[0], src[1], src[2], src[3]);
     }
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ float round16(float x) {
+  if (kBf16) return __bfloat162float(__float2bfloat16_rn(x));
+  return __half2float(__float2half_rn(x));
+}
+// hi plane first, then the residuals in place for the lo plane (keeps the register peak at one plane's worth)
+template <bool kBf16>
+__device__ __forceinline__ void toeplitz_store(float (&xv)[39], uint32_t st, int nplanes, int plane_bytes) {
+  toeplitz_store_plane<kBf16>(xv, st);
+  if (nplanes == 2) {
+#pragma unroll
+    for (int k = 0; k < 39; ++k) xv[k] -= round16<kBf16>(xv[k]);
+    toeplitz_store_plane<kBf16>(xv, st + plane_bytes);
   }
 }
 
@@ -139,7 +135,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 256); }
     fence_mbar_init();
   }
   // packed weights -> shared memory (already in the UMMA smem image layout)
@@ -160,11 +156,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp > kEpiWarps) {
-    // ===================== Toeplitz producers: warp q fills stage q for local tiles q, q+4, ... =============
+    // ===================== Toeplitz producers: warp q builds local tiles q, q + P, ...; tile i uses stage i % S ===
     const int q = warp - kEpiWarps - 1;
-    uint32_t i = q;
-    for (int tile = blockIdx.x + q * gridDim.x; q < kStages && tile < ntiles;
-         tile += kStages * gridDim.x, i += kStages) {
+    for (uint32_t i = q; int(blockIdx.x + i * gridDim.x) < ntiles; i += kProdWarps) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int sidx = i % kStages;
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
       const float* xc = p.x + size_t(n) * size_t(p.x_clip_stride);
@@ -177,11 +173,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       const int e0 = p0 - 15 + 8 * lane;
       float xv[39];
       toeplitz_load_strip(xc, xs, pm, ps, e0, p.L, xv);
-      mbar_wait(&bars->empty[q], (((i / kStages) & 1) ^ 1));
-      toeplitz_store<false>(xv, smem_u32(stages + q * kStageBytes + lane * kGroupStride), nplanes, kPlaneBytes);
+      mbar_wait(&bars->empty[sidx], (((i / kStages) & 1) ^ 1));
+      toeplitz_store<false>(xv, smem_u32(stages + sidx * kStageBytes + lane * kGroupStride), nplanes, kPlaneBytes);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->full[q]);
+      if (lane == 0) mbar_arrive(&bars->full[sidx]);
     }
   } else if (warp == kEpiWarps) {
     // ===================== MMA issuer =====================
@@ -221,35 +217,42 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 0-7): thread = cout channel, warp pair splits the columns ==========
-    // Pooled outputs are staged in shared memory ([plane][channel half][64 positions][64 channels], double
-    // buffered) and written with TMA bulk tensor stores (positions / channels out of range are clipped).
-    const int q = warp & 3;          // TMEM lane quarter
-    const int chalf = warp >> 2;     // which half of the 256 position columns
-    const bool leader = (threadIdx.x == 0);
+    // ===================== epilogue (warps 0-15) =====================
+    // Two independent groups of 8 warps: group g owns TMEM buffer g (every second accumulator), one 32 KB staging
+    // buffer, its own named barrier and its own TMA-store leader, so the epilogues of consecutive tiles overlap.
+    // Inside a group: thread = cout channel (TMEM lane), the two warps of a lane quarter split the 256 columns.
+    // Outputs are staged in shared memory and written with TMA bulk tensor stores (positions / channels out of
+    // range are clipped by the TMA unit).
+    const int grp = warp >> 3;
+    const int wg = warp & 7;
+    const int q = wg & 3;            // TMEM lane quarter
+    const int chalf = wg >> 2;       // which half of the 256 position columns
+    const bool leader = (wg == 0 && lane == 0);
+    const uint32_t bar_id = 1 + grp;
     const int ch = q * 32 + lane;
-    uint32_t ait = 0, git = 0;
+    uint8_t* ob = outbuf + grp * kOutBufBytes;
+    const int buf = grp;
+    uint32_t ait = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int n = tile / p.nptile;
       const int p0 = (tile % p.nptile) * kTileN;
       for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
-        const int buf = ait & 1;
+        if (int(ait & 1) != grp) continue;
         const int co = slab * kTileM + ch;
         const float4 ep = p.epi[co];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
         if (p.out_f32 != nullptr) {
           // train-mode forward: un-pooled u = relu(acc + bias) as fp32 + per-channel {sum, sum of squares}
-          // partials.  Granule = 64 positions x 128 channels fp32 = one 32 KB staging buffer (4 TMA boxes of 32
+          // partials.  Granule = 64 positions x 128 channels fp32 = the group's staging buffer (4 TMA boxes of 32
           // channels); the two warps of a lane quarter take 32 columns each.
           mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
           tc_fence_after_sync();
-          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-          for (int gr = 0; gr < kTileN / 64; ++gr, ++git) {
-            uint8_t* ob = outbuf + (git & 1) * kOutBufBytes;
+          for (int gr = 0; gr < kTileN / 64; ++gr) {
             const uint32_t st = smem_u32(ob) + (ch >> 5) * 8192 + (ch & 31) * 4 + chalf * 32 * 128;
-            if (leader) tma_store_wait_read<1>();
-            named_bar_sync(1, kEpiWarps * 32);
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, 256);
             float v[32];
             tmem_ld_32x32(taddr + gr * 64 + chalf * 32, v);
             if (gr == kTileN / 64 - 1) {
@@ -264,7 +267,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
               sts_f32(st + j * 128, y);
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, kEpiWarps * 32);
+            named_bar_sync(bar_id, 256);
             if (leader) {
               const int pos = p0 + gr * 64;
               if (pos < p.L) {
@@ -281,14 +284,12 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
             p.stat_partial[(size_t(tile) * 2 + chalf) * p.cout_pad + co] = make_float2(s1, s2);
           continue;
         }
-        uint8_t* ob = outbuf + buf * kOutBufBytes;
         const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
         const uint32_t st_l = st_h + 2 * kOutBoxBytes;
-        if (leader) tma_store_wait_read<1>();  // the stores issued from this buffer two tiles ago have been read
-        named_bar_sync(1, kEpiWarps * 32);
+        if (leader) tma_store_wait_read<0>();  // this group's previous tile has been read out of the staging buffer
+        named_bar_sync(bar_id, 256);
         mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
 #pragma unroll 1
         for (int gg = 0; gg < kTileN / 64; ++gg) {
           const int g = chalf * (kTileN / 64) + gg;
@@ -309,7 +310,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, kEpiWarps * 32);
+        named_bar_sync(bar_id, 256);
         if (leader) {
           const int pos = p0 >> 2;
 #pragma unroll

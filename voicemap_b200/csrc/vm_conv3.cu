@@ -27,7 +27,6 @@ constexpr int kKC = 64;                  // channels per K chunk (one 128-byte s
 constexpr int kXRows = 264;              // 258 halo rows, padded to a multiple of 8
 constexpr int kXPlaneBytes = kXRows * 128;         // 33792
 constexpr int kXMainBytes = 256 * 128;             // 32768 (rows 0..255)
-constexpr int kXHaloBytes = 8 * 128;               // 1024  (rows 256..263)
 constexpr int kXSlotBytes = 2 * kXPlaneBytes;      // hi + lo
 constexpr int kXStages = 2;
 constexpr int kWTileBytes = kTileM * 128;          // 16384
@@ -194,8 +193,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       const int p0 = pt * kTileN;
       const int buf = tit & 1;
       const int co = slab * kTileM + q * 32 + lane;
-      const float4 ep = p.epi[co];  // {sigma, bias, s, t}; padded channels hold zeros
-      const bool co_ok = co < p.cout;
+      const float4 ep = p.epi[co];  // {a, c, t, s} (see fold_bn); padded channels hold zeros
       mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;

@@ -416,7 +416,8 @@ __global__ void bn_bwd_finalize_kernel(const double2* __restrict__ tmp, int N, i
 __device__ __forceinline__ uint2 pack4u(const uint16_t (&h)[4]) {
   return make_uint2(uint32_t(h[0]) | (uint32_t(h[1]) << 16), uint32_t(h[2]) | (uint32_t(h[3]) << 16));
 }
-__global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
+__global__ void __launch_bounds__(128, 5)
+bn_relu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
                                    const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
                                    int C, int G, int pool, const float4* __restrict__ bn_const,
                                    const float4* __restrict__ bwd_const, const float* __restrict__ mask,
@@ -449,30 +450,44 @@ __global__ void bn_relu_bwd_kernel(const float* __restrict__ u, const float* __r
       const int l0 = w * pool;
       const int wl = min(pool, L - l0);
       const float* up = u + (size_t(n) * L + l0) * C + c;
+      // the window's rows (pool <= 4) are loaded once and kept in registers
+      float4 ur[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        ur[i] = (i < wl) ? __ldcs(reinterpret_cast<const float4*>(up + size_t(i) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
       int bi[4] = {-1, -1, -1, -1};
       float dyw[4] = {0, 0, 0, 0};
       if (dy_pooled != nullptr && w < lout) {
-        float bu[4];
-        window_argmax4(up, C, pool, sc, bi, bu);
-        const float4 dv = *reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dyw[k] = f4get(dv, k) * mk[k];
-      }
-      for (int i = 0; i < wl; ++i) {
-        const float4 uv4 = *reinterpret_cast<const float4*>(up + size_t(i) * C);
-        uint16_t h[4], lw[4];
+        const float4 dv = __ldcs(reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float uv = f4get(uv4, k);
-          const float dy = (dy_pooled != nullptr) ? ((i == bi[k]) ? dyw[k] : 0.f) : ((l0 + i == am[k]) ? dg[k] : 0.f);
-          const float xhat = (uv - mean[k]) * rstd[k];
-          const float du = (uv > 0.f) ? bs[k] * (dy - mdy[k] - xhat * mdx[k]) : 0.f;
-          sb[k] += du;
-          split_bf16(du, h[k], lw[k]);
+          float bu = f4get(ur[0], k);
+          bi[k] = 0;
+#pragma unroll
+          for (int i = 1; i < 4; ++i) {
+            const float x = f4get(ur[i], k);
+            if (i < pool && ((sc[k] >= 0.f) ? (x > bu) : (x < bu))) { bu = x; bi[k] = i; }
+          }
+          dyw[k] = f4get(dv, k) * mk[k];
         }
-        const size_t o = (size_t(n) * L + l0 + i) * C + c;
-        *reinterpret_cast<uint2*>(du_hi + o) = pack4u(h);
-        if (du_lo != nullptr) *reinterpret_cast<uint2*>(du_lo + o) = pack4u(lw);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < wl) {
+          uint16_t h[4], lw[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float uv = f4get(ur[i], k);
+            const float dy = (dy_pooled != nullptr) ? ((i == bi[k]) ? dyw[k] : 0.f) : ((l0 + i == am[k]) ? dg[k] : 0.f);
+            const float xhat = (uv - mean[k]) * rstd[k];
+            const float du = (uv > 0.f) ? bs[k] * (dy - mdy[k] - xhat * mdx[k]) : 0.f;
+            sb[k] += du;
+            split_bf16(du, h[k], lw[k]);
+          }
+          const size_t o = (size_t(n) * L + l0 + i) * C + c;
+          __stcs(reinterpret_cast<uint2*>(du_hi + o), pack4u(h));
+          if (du_lo != nullptr) __stcs(reinterpret_cast<uint2*>(du_lo + o), pack4u(lw));
+        }
       }
     }
     float* row = dbias_partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;

@@ -270,8 +270,11 @@ class EncoderModel(_ModelBase):
             return out
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_bufs = None
         main = torch.cuda.current_stream(dev)
-        bufs = [torch.empty((chunk, length), dtype=torch.float32, device=dev) for _ in range(2)]
+        if self._copy_bufs is None or self._copy_bufs[0].shape != (chunk, length):
+            self._copy_bufs = [torch.empty((chunk, length), dtype=torch.float32, device=dev) for _ in range(2)]
+        bufs = self._copy_bufs
         freed = [None, None]
         self._copy_stream.wait_stream(main)
         for k, lo in enumerate(range(0, n, chunk)):

@@ -372,6 +372,50 @@ def _next_batch(gen_iter, generator, step):
     return next(gen_iter)
 
 
+class _Prefetcher:
+    """Pulls batches from the user's generator / Sequence on one background thread so that host-side batch
+    construction (FLAC decode, pair sampling, whitening) overlaps the device step -- the role of Keras'
+    ``workers`` / ``use_multiprocessing`` queue (experiments/train_siamese.py:71-72).  Order is preserved and the
+    generator is only ever touched from that one thread."""
+
+    def __init__(self, generator, depth=2):
+        import queue
+        import threading
+        self.generator = generator
+        self.is_seq = hasattr(generator, "__getitem__") and hasattr(generator, "__len__")
+        self.it = None if self.is_seq else iter(generator)
+        self.q = queue.Queue(maxsize=depth)
+        self.step = 0
+        self.stop = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            while not self.stop:
+                item = _next_batch(self.it, self.generator, self.step)
+                self.step += 1
+                while not self.stop:
+                    try:
+                        self.q.put(item, timeout=0.1)
+                        break
+                    except Exception:
+                        continue
+        except BaseException as exc:  # surfaced to the training loop
+            self.q.put(exc)
+
+    def next(self):
+        item = self.q.get()
+        if isinstance(item, BaseException):
+            if isinstance(item, StopIteration):
+                raise StopIteration
+            raise item
+        return item
+
+    def close(self):
+        self.stop = True
+
+
 def _dist_info():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -400,7 +444,7 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
         cb.set_model(model)
         cb.set_params(dict(epochs=epochs, steps=steps_per_epoch, verbose=verbose))
         cb.on_train_begin()
-    gen_iter = None if is_seq else iter(generator)
+    prefetch = _Prefetcher(generator) if not is_seq else None   # Sequences are indexed (and reshuffled) per epoch
     val_iter = None
     if validation_data is not None and not isinstance(validation_data, (tuple, list)):
         val_iter = iter(validation_data)
@@ -410,7 +454,7 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
             cb.on_epoch_begin(epoch)
         losses, accs = [], []
         for step in range(steps_per_epoch):
-            batch = _next_batch(gen_iter, generator, step)
+            batch = prefetch.next() if prefetch is not None else generator[step % len(generator)]
             x, y = batch[0], batch[1]
             if trainer.kind == "siamese":
                 lv, acc = trainer.siamese_step(x[0], x[1], y, allreduce=allreduce, world=world)
@@ -434,6 +478,8 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
         if verbose:
             print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
         history.append(dict(logs))
+    if prefetch is not None:
+        prefetch.close()
     for cb in callbacks:
         cb.on_train_end()
     return history
