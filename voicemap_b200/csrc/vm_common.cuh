@@ -210,10 +210,33 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Fused bias + ReLU + BatchNorm affine on a pooled accumulator maximum, constants from vm_pack_conv*: {a, c, t, s}.
+// Fused bias + ReLU + BatchNorm affine on a pooled accumulator maximum m, constants {a, c, lo, hi} from vm_pack_conv*:
+//   BN scale s >= 0:  max_pool(s*relu(acc + b) + t) = s*max(M, -b) + (s*b + t)           -> {s, s*b + t, -b, +inf}
+//   BN scale s <  0:  weights are packed negated (M = max_pool(-acc)) and the pool becomes a min:
+//                     s*min_pool(relu(acc + b)) + t = (-s)*min(M, b) + (s*b + t)          -> {-s, s*b + t, -inf, b}
+// i.e. y = a*clamp(M, lo, hi) + c.  kClampHi = false is the specialisation for "all scales >= 0" (hi = +inf).
+template <bool kClampHi = true>
 __device__ __forceinline__ float apply_epi(const float4& ep, float m) {
-  const float v = fmaf(ep.x, m, ep.y);
-  return (ep.w >= 0.f) ? fmaxf(v, ep.z) : fminf(v, ep.z);
+  float v = fmaxf(m, ep.z);
+  if (kClampHi) v = fminf(v, ep.w);
+  return fmaf(ep.x, v, ep.y);
+}
+// pooled variants: the lower clamp rides in the last 3-input max of the pool
+template <bool kClampHi = true>
+__device__ __forceinline__ float apply_epi_pool2(const float4& ep, float v0, float v1) {
+  float v = max3(v0, v1, ep.z);
+  if (kClampHi) v = fminf(v, ep.w);
+  return fmaf(ep.x, v, ep.y);
+}
+template <bool kClampHi = true>
+__device__ __forceinline__ float apply_epi_pool4(const float4& ep, float v0, float v1, float v2, float v3) {
+  float v = max3(max3(v0, v1, v2), v3, ep.z);
+  if (kClampHi) v = fminf(v, ep.w);
+  return fmaf(ep.x, v, ep.y);
+}
+// true when no lane of the warp needs the upper clamp
+__device__ __forceinline__ bool epi_no_upper_clamp(const float4& ep) {
+  return __all_sync(0xffffffffu, ep.w == INFINITY);
 }
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
@@ -228,6 +251,17 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");

@@ -232,12 +232,17 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
     const int ch = q * 32 + lane;
     uint8_t* ob = outbuf + grp * kOutBufBytes;
     const int buf = grp;
-    uint32_t ait = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int n = tile / p.nptile;
-      const int p0 = (tile % p.nptile) * kTileN;
-      for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
-        if (int(ait & 1) != grp) continue;
+    // this group's accumulators are ait = grp, grp + 2, ...; (tile, slab, n, p0) advance incrementally
+    const int dn = int(gridDim.x) / p.nptile, dpt = int(gridDim.x) % p.nptile;
+    int tile = blockIdx.x, n = tile / p.nptile, pt = tile % p.nptile, slab = grp;
+    const auto next_tile = [&]() {
+      tile += gridDim.x; n += dn; pt += dpt;
+      if (pt >= p.nptile) { pt -= p.nptile; ++n; }
+    };
+    while (slab >= p.nslab && tile < ntiles) { slab -= p.nslab; next_tile(); }
+    for (uint32_t it = 0; tile < ntiles; ++it) {
+      const int p0 = pt * kTileN;
+      {
         const int co = slab * kTileM + ch;
         const float4 ep = p.epi[co];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
@@ -245,14 +250,14 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           // train-mode forward: un-pooled u = relu(acc + bias) as fp32 + per-channel {sum, sum of squares}
           // partials.  Granule = 64 positions x 128 channels fp32 = the group's staging buffer (4 TMA boxes of 32
           // channels); the two warps of a lane quarter take 32 columns each.
-          mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
-          tc_fence_after_sync();
+          if (wg == 0) mbar_wait(&bars->tfull[buf], it & 1);  // one polling warp per group; the rest block in bar.sync
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
           for (int gr = 0; gr < kTileN / 64; ++gr) {
             const uint32_t st = smem_u32(ob) + (ch >> 5) * 8192 + (ch & 31) * 4 + chalf * 32 * 128;
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(bar_id, 256);
+            tc_fence_after_sync();
             float v[32];
             tmem_ld_32x32(taddr + gr * 64 + chalf * 32, v);
             if (gr == kTileN / 64 - 1) {
@@ -282,48 +287,66 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           }
           if (p.stat_partial != nullptr)
             p.stat_partial[(size_t(tile) * 2 + chalf) * p.cout_pad + co] = make_float2(s1, s2);
-          continue;
-        }
-        const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
-        const uint32_t st_l = st_h + 2 * kOutBoxBytes;
-        if (leader) tma_store_wait_read<0>();  // this group's previous tile has been read out of the staging buffer
-        named_bar_sync(bar_id, 256);
-        mbar_wait(&bars->tfull[buf], (ait >> 1) & 1);
-        tc_fence_after_sync();
+        } else {
+          const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
+          const uint32_t st_l = st_h + 2 * kOutBoxBytes;
+          // warp 0 of the group waits for (a) this group's previous TMA store to have drained the staging buffer
+          // and (b) the accumulator; the other seven warps block in the named barrier instead of spinning
+          if (wg == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            mbar_wait(&bars->tfull[buf], it & 1);
+          }
+          named_bar_sync(bar_id, 256);
+          tc_fence_after_sync();
+          const bool no_hi = epi_no_upper_clamp(ep);
 #pragma unroll 1
-        for (int gg = 0; gg < kTileN / 64; ++gg) {
-          const int g = chalf * (kTileN / 64) + gg;
-          float v[32];
-          tmem_ld_32x32(taddr + g * 32, v);
-          if (gg == kTileN / 64 - 1) {
-            tc_fence_before_sync();
-            mbar_arrive(&bars->tempty[buf]);
-          }
+          for (int gg = 0; gg < kTileN / 64; ++gg) {
+            const int g = chalf * (kTileN / 64) + gg;
+            float v[32];
+            tmem_ld_32x32(taddr + g * 32, v);
+            if (gg == kTileN / 64 - 1) {
+              tc_fence_before_sync();
+              mbar_arrive(&bars->tempty[buf]);
+            }
+            const uint32_t sh = st_h + g * 8 * 128, sl = st_l + g * 8 * 128;
+            if (no_hi) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float mx = max3(fmaxf(v[4 * j], v[4 * j + 1]), v[4 * j + 2], v[4 * j + 3]);
-            const float y = apply_epi(ep, mx);
-            __half h, l;
-            split_f32(y, h, l);
-            sts_u16(st_h + (g * 8 + j) * 128, h);
-            if (nplanes == 2) sts_u16(st_l + (g * 8 + j) * 128, l);
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 256);
-        if (leader) {
-          const int pos = p0 >> 2;
+              for (int j = 0; j < 8; ++j) {
+                const float y = apply_epi_pool4<false>(ep, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __half h, l;
+                split_f32(y, h, l);
+                sts_u16(sh + j * 128, h);
+                if (nplanes == 2) sts_u16(sl + j * 128, l);
+              }
+            } else {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int c0 = slab * kTileM + half * 64;
-            if (c0 < p.cout) {
-              tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
-              if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+              for (int j = 0; j < 8; ++j) {
+                const float y = apply_epi_pool4<true>(ep, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __half h, l;
+                split_f32(y, h, l);
+                sts_u16(sh + j * 128, h);
+                if (nplanes == 2) sts_u16(sl + j * 128, l);
+              }
             }
           }
-          tma_store_commit();
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 256);
+          if (leader) {
+            const int pos = p0 >> 2;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = slab * kTileM + half * 64;
+              if (c0 < p.cout) {
+                tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+                if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+              }
+            }
+            tma_store_commit();
+          }
         }
       }
+      slab += 2;
+      while (slab >= p.nslab && tile < ntiles) { slab -= p.nslab; next_tile(); }
     }
     if (leader) tma_store_wait_all<0>();
   }

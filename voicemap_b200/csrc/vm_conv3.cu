@@ -31,9 +31,10 @@ constexpr int kXSlotBytes = 2 * kXPlaneBytes;      // hi + lo
 constexpr int kXStages = 2;
 constexpr int kWTileBytes = kTileM * 128;          // 16384
 constexpr int kWStages = 4;
-constexpr int kStagePos = 32;                       // pooled positions per output granule
-constexpr int kStageBoxBytes = kStagePos * 128;     // one TMA store box: 32 positions x 64 channels fp16
-constexpr int kStageBytes = 4 * kStageBoxBytes;     // [plane][channel half][pos][64 ch]
+constexpr int kStagePos = 16;                       // pooled positions per output granule
+constexpr int kStageBoxBytes = kStagePos * 128;     // one TMA store box: 16 positions x 64 channels fp16
+constexpr int kStageBufBytes = 4 * kStageBoxBytes;  // [plane][channel half][pos][64 ch] = 8 KB
+constexpr int kStageBytes = 2 * kStageBufBytes;     // double-buffered
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quarter
 constexpr int kThreads = (4 + kEpiWarps) * 32;
@@ -126,10 +127,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, kTileN, p.in_bf16, p.in_bf16);  // dgrad: both operands bf16
       uint32_t xit = 0, wit = 0, tit = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
         const int buf = tit & 1;
+        // the last position tile of a clip is usually ragged: issue only as many MMA columns (multiple of 16) as
+        // there are positions left -- the tensor pipe is the bound, so unused columns are pure waste
+        const int p0 = ((tile / p.nslab) % p.nptile) * kTileN;
+        const int ncols = min(kTileN, (p.L - p0 + 15) & ~15);
+        const uint32_t idesc = make_idesc_f16(kTileM, ncols, p.in_bf16, p.in_bf16);  // dgrad: both operands bf16
         mbar_wait(&bars->tempty[buf], ((tit >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * kTileN;
@@ -182,9 +187,17 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: thread = cout channel, columns = positions =====================
-    const int q = warp & 3;             // TMEM lane quarter
-    const int chalf = (warp - 4) >> 2;  // which 32-column half of every 64-column group
-    uint32_t tit = 0;
+    // 8 warps: q = TMEM lane quarter, chalf = which half of every output granule's columns.  Output granules go
+    // through a double-buffered 2 x 8 KB staging area and leave with TMA bulk tensor stores (positions / channels
+    // out of range are clipped by the TMA unit).  Per granule there is one named barrier: before arriving, the
+    // leader waits until the store issued one granule earlier has drained its buffer (that store had a whole
+    // granule of compute to finish), so the buffer written next is known to be free by everyone who passes.
+    const int q = warp & 3;
+    const int chalf = (warp - 4) >> 2;
+    const bool leader = (threadIdx.x == 4 * 32);
+    const int ch = q * 32 + lane;
+    const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
+    uint32_t tit = 0, gcount = 0;   // gcount: granules staged so far (selects the staging buffer)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
       const int slab = tile % p.nslab;
       const int pt_lin = tile / p.nslab;
@@ -192,12 +205,13 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       const int pt = pt_lin % p.nptile;
       const int p0 = pt * kTileN;
       const int buf = tit & 1;
-      const int co = slab * kTileM + q * 32 + lane;
-      const float4 ep = p.epi[co];  // {a, c, t, s} (see fold_bn); padded channels hold zeros
-      mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
+      const int co = slab * kTileM + ch;
+      const float4 ep = p.epi[co];  // {a, c, lo, hi} (see apply_epi); padded channels hold zeros
+      // one polling warp; the other seven block in bar.sync instead of spinning on the mbarrier
+      if (warp == 4) mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
+      named_bar_sync(1, kEpiWarps * 32);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
-      const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
       if (p.gmax_partial != nullptr) {
         float m = -INFINITY;
 #pragma unroll 1
@@ -217,42 +231,40 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         }
         tc_fence_before_sync();
         mbar_arrive(&bars->tempty[buf]);
-        // the two column halves keep separate partial rows: (N, 2*nptile, cout_pad)
+        // the two column halves keep separate partial rows: (N, 2*nptile, cout_pad), raw accumulator maxima
         p.gmax_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = m;
       } else if (p.out_f32 != nullptr) {
         // un-pooled fp32 output (train-mode forward: u = relu(acc + bias) with per-channel sum / sum-of-squares
-        // partials; dgrad: y = acc).  Staging granule = 32 positions x 128 channels fp32 (4 TMA boxes of
-        // 32 channels); the two warps of a lane quarter split the 32 columns 16/16.
-        const bool leader = (threadIdx.x == 4 * 32);
-        const int ch = q * 32 + lane;
-        const uint32_t st = smem_u32(stage) + (ch >> 5) * 4096 + (ch & 31) * 4 + chalf * 16 * 128;
+        // partials; dgrad: y = acc).  Granule = 16 positions x 128 channels fp32 (4 TMA boxes of 32 channels);
+        // the two warps of a lane quarter take 8 columns each.
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int gr = 0; gr < kTileN / 32; ++gr) {
-          if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, kEpiWarps * 32);
-          float v[16];
-          tmem_ld_32x16(taddr + gr * 32 + chalf * 16, v);
-          if (gr == kTileN / 32 - 1) {
+        for (int gr = 0; gr < kTileN / 16; ++gr, ++gcount) {
+          uint8_t* sbuf = stage + (gcount & 1) * kStageBufBytes;
+          const uint32_t st = smem_u32(sbuf) + (ch >> 5) * 2048 + (ch & 31) * 4 + chalf * 8 * 128;
+          float v[8];
+          tmem_ld_32x8(taddr + gr * 16 + chalf * 8, v);
+          if (gr == kTileN / 16 - 1) {
             tc_fence_before_sync();
             mbar_arrive(&bars->tempty[buf]);
           }
-          const int pos0 = p0 + gr * 32 + chalf * 16;
+          const int pos0 = p0 + gr * 16 + chalf * 8;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float y = p.linear ? v[j] : apply_epi(ep, v[j]);
             if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
             sts_f32(st + j * 128, y);
           }
           fence_proxy_async_smem();
+          if (leader) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiWarps * 32);
           if (leader) {
-            const int pos = p0 + gr * 32;
+            const int pos = p0 + gr * 16;
             if (pos < p.L) {
 #pragma unroll
               for (int b4 = 0; b4 < 4; ++b4) {
                 const int c0 = slab * kTileM + b4 * 32;
-                if (c0 < p.cout) tma_store_3d(&tm_oh, stage + b4 * 4096, c0, pos, n);
+                if (c0 < p.cout) tma_store_3d(&tm_oh, sbuf + b4 * 2048, c0, pos, n);
               }
             }
             tma_store_commit();
@@ -261,35 +273,41 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         if (p.stat_partial != nullptr)
           p.stat_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
       } else {
-        // pooled outputs go through a shared-memory staging granule (32 positions x 128 channels x 2 planes)
-        // and leave with TMA bulk tensor stores; out-of-range positions / channels are clipped by the TMA unit.
-        const bool leader = (threadIdx.x == 4 * 32);
-        const int ch = q * 32 + lane;
-        const uint32_t st_h = smem_u32(stage) + (ch >> 6) * kStageBoxBytes + (ch & 63) * 2;
-        const uint32_t st_l = st_h + 2 * kStageBoxBytes;
+        // pooled outputs: granule = 16 pooled positions x 128 channels x 2 planes; the two warps of a lane quarter
+        // take 16 raw columns (8 pooled positions) each.
+        const bool no_hi = epi_no_upper_clamp(ep);
 #pragma unroll 1
-        for (int gr = 0; gr < kTileN / 64; ++gr) {
-          if (leader) tma_store_wait_read<0>();  // previous granule has been read out of the staging buffer
-          named_bar_sync(1, kEpiWarps * 32);
-          {
-            const int sub = chalf;
-            float v[32];
-            tmem_ld_32x32(taddr + gr * 64 + sub * 32, v);
-            if (gr == kTileN / 64 - 1) {  // all TMEM reads of this buffer are done
-              tc_fence_before_sync();
-              mbar_arrive(&bars->tempty[buf]);
-            }
+        for (int gr = 0; gr < kTileN / 32; ++gr, ++gcount) {
+          uint8_t* sbuf = stage + (gcount & 1) * kStageBufBytes;
+          const uint32_t st_h = smem_u32(sbuf) + (ch >> 6) * kStageBoxBytes + (ch & 63) * 2 + chalf * 8 * 128;
+          const uint32_t st_l = st_h + 2 * kStageBoxBytes;
+          float v[16];
+          tmem_ld_32x16(taddr + gr * 32 + chalf * 16, v);
+          if (gr == kTileN / 32 - 1) {  // all TMEM reads of this buffer are done
+            tc_fence_before_sync();
+            mbar_arrive(&bars->tempty[buf]);
+          }
+          if (no_hi) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float mx = fmaxf(v[2 * j], v[2 * j + 1]);
-              const float y = apply_epi(ep, mx);
+            for (int j = 0; j < 8; ++j) {
+              const float y = apply_epi_pool2<false>(ep, v[2 * j], v[2 * j + 1]);
               __half h, l;
               split_f32(y, h, l);
-              sts_u16(st_h + (sub * 16 + j) * 128, h);
-              if (wplanes == 2) sts_u16(st_l + (sub * 16 + j) * 128, l);
+              sts_u16(st_h + j * 128, h);
+              if (wplanes == 2) sts_u16(st_l + j * 128, l);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float y = apply_epi_pool2<true>(ep, v[2 * j], v[2 * j + 1]);
+              __half h, l;
+              split_f32(y, h, l);
+              sts_u16(st_h + j * 128, h);
+              if (wplanes == 2) sts_u16(st_l + j * 128, l);
             }
           }
           fence_proxy_async_smem();
+          if (leader) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiWarps * 32);
           if (leader) {
             const int pos = (p0 >> 1) + gr * kStagePos;
@@ -298,8 +316,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
               for (int half = 0; half < 2; ++half) {
                 const int c0 = slab * kTileM + half * 64;
                 if (c0 < p.cout) {
-                  tma_store_3d(&tm_oh, stage + half * kStageBoxBytes, c0, pos, n);
-                  if (wplanes == 2) tma_store_3d(&tm_ol, stage + (2 + half) * kStageBoxBytes, c0, pos, n);
+                  tma_store_3d(&tm_oh, sbuf + half * kStageBoxBytes, c0, pos, n);
+                  if (wplanes == 2) tma_store_3d(&tm_ol, sbuf + (2 + half) * kStageBoxBytes, c0, pos, n);
                 }
               }
             }
@@ -308,7 +326,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         }
       }
     }
-    if (threadIdx.x == 4 * 32) tma_store_wait_all<0>();
+    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
@@ -369,13 +387,13 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   if ((rc = make_tensor_map(&wh, w_hi, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&wl, w_lo, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
 
-  // pooled output planes (N, lout, cout) fp16 -- TMA store boxes of 64 channels x 32 positions
+  // pooled output planes (N, lout, cout) fp16 -- TMA store boxes of 64 channels x 16 positions
   CUtensorMap oh, ol;
   if (out_f32 != nullptr) {
-    // un-pooled fp32 output (N, L, cout): TMA store boxes of 32 channels x 32 positions
+    // un-pooled fp32 output (N, L, cout): TMA store boxes of 32 channels x 16 positions
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 4, uint64_t(L) * cout * 4};
-    const uint32_t obox[3] = {32, 32, 1};
+    const uint32_t obox[3] = {32, 16, 1};
     if ((rc = make_tensor_map(&oh, out_f32, 3, odims, ostr, obox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
     ol = oh;
   } else if (gmax_partial == nullptr) {

@@ -20,9 +20,12 @@ __device__ __forceinline__ float bn_scale(const float* gamma, const float* var, 
 __device__ __forceinline__ float4 fold_bn(float bias, float gamma, float beta, float mean, float var, float eps) {
   const float s = gamma * (1.0f / sqrtf(var + eps));
   const float t = beta - mean * s;
-  const float sigma = (s < 0.f) ? -1.f : 1.f;
-  return make_float4(s * sigma, fmaf(s, bias, t), t, s);
+  const float c = fmaf(s, bias, t);
+  return (s < 0.f) ? make_float4(-s, c, -INFINITY, bias) : make_float4(s, c, -bias, INFINITY);  // see apply_epi
 }
+
+// y = relu(acc + bias) = max(acc, -bias) + bias (bit-identical: both branches round once)
+__device__ __forceinline__ float4 epi_relu_only(float bias) { return make_float4(1.f, bias, -bias, INFINITY); }
 
 // ---------------------------------------------------------------------------------------------
 // conv3 weights: w (3, cin, cout) fp32 -> wpack [plane][tap][cout_pad][cin] fp16
@@ -36,7 +39,7 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __re
   if (idx < size_t(cout_pad)) {
     const int co = int(idx);
     if (co >= cout) epi[co] = make_float4(0.f, 0.f, 0.f, 0.f);
-    else if (gamma == nullptr) epi[co] = make_float4(1.f, bias ? bias[co] : 0.f, 0.f, 1.f);  // y = relu(acc + bias)
+    else if (gamma == nullptr) epi[co] = epi_relu_only(bias ? bias[co] : 0.f);
     else epi[co] = fold_bn(bias[co], gamma[co], beta[co], mean[co], var[co], eps);
   }
   if (idx >= total) return;
@@ -66,7 +69,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < cout_pad) {
     if (idx >= cout) epi[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    else if (gamma == nullptr) epi[idx] = make_float4(1.f, bias ? bias[idx] : 0.f, 0.f, 1.f);
+    else if (gamma == nullptr) epi[idx] = epi_relu_only(bias ? bias[idx] : 0.f);
     else epi[idx] = fold_bn(bias[idx], gamma[idx], beta[idx], mean[idx], var[idx], eps);
   }
   if (idx >= cout_pad * 32) return;
