@@ -199,6 +199,23 @@ def test_models_api_predict_matches_oracle(stress_params):
         clf.predict(x[:, :3000])
 
 
+def test_predict_pipelined_host_batch_is_bit_identical(stress_params):
+    """predict() of a pinned host batch runs as growing chunks whose copies overlap the kernels
+    (models._pipeline_plan); eval-mode embeddings do not depend on the chunking, bit for bit."""
+    from voicemap_b200.models import _pipeline_plan, get_baseline_convolutional_encoder
+    enc = get_baseline_convolutional_encoder(128, 64, dropout=0.0)
+    enc.set_named_weights(stress_params)
+    g = torch.Generator().manual_seed(11)
+    x = (O.WHITEN_RMS * torch.randn(300, 4000, 1, generator=g)).pin_memory()
+    assert len(_pipeline_plan(300)) >= 3
+    got = enc.predict(x)
+    eng = enc._get_engine()
+    whole = eng.forward(x[:, :, 0].cuda().contiguous()).cpu().numpy()
+    assert np.array_equal(got, whole)
+    assert np.array_equal(enc.predict(x.numpy()), whole)        # pageable numpy input: same numbers
+    assert np.array_equal(enc.predict(x), whole)                # buffer reuse across calls
+
+
 def test_full_batch_properties(stress_params):
     """BASELINE config[1] size (256 clips x 12000): batch-composition independence (bit-exact), permutation
     equivariance, and spot parity of a few clips against the oracle."""

@@ -4,15 +4,17 @@
 // HBM-bound layer (AI ~62 F/B): the 32-tap filter bank is run on tcgen05 tensor cores so that arithmetic is
 // free and the kernel streams at the output-write rate.  D[cout, position] = W[cout, tap] * T[position, tap]
 // where T is the Toeplitz (im2col) matrix of the waveform: T[p, k] = x[p + k - 15].
-//   * producer warps read a 39-sample strip per 8 positions, split it into fp16 (hi, lo) and write the
-//     Toeplitz tile straight into the canonical no-swizzle K-major UMMA layout in shared memory
-//     (core matrix = 8 positions x 8 taps; row-group stride padded to 528 B so the 16-byte stores are
-//     bank-conflict free);
+//   * producer warps split the waveform into fp16 (hi, lo) and write the Toeplitz operand in the no-swizzle K-major
+//     UMMA layout with OVERLAPPING core matrices: the 8x8 core matrix of (position group g, tap chunk c) holds
+//     x[8(g+c) + i + j] (row i, tap j), i.e. it depends on g + c only, so with LBO = SBO one 128-byte block
+//     (at a 144-byte pitch) per value of g + c serves every (g, c) pair: 36 blocks (4.5 KB) per plane and tile instead of the
+//     32 x 4 blocks of a materialised im2col tile -- 8x duplication of the waveform instead of 32x;
 //   * one thread issues 6 MMAs per tile (2 K-steps x {Th*Wh, Tl*Wh, Th*Wl}) into a double-buffered TMEM
 //     accumulator (128 cout lanes x 256 positions);
-//   * 4 epilogue warps pool the raw accumulators 4:1, apply bias/ReLU/BN, split to fp16 (hi, lo) planes and
-//     store channels-last.  As in vm_conv3.cu the packed weights carry sigma = sign(BN scale) so that the
-//     max-pool commutes with the affine.
+//   * 16 epilogue warps (two groups of 8, one per accumulator buffer) pool the raw accumulators 4:1, apply
+//     bias/ReLU/BN, split to fp16 (hi, lo) planes, stage them in shared memory and store channels-last with TMA.
+//     As in vm_conv3.cu the packed weights carry sigma = sign(BN scale) so that the max-pool commutes with the
+//     affine.
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 
@@ -21,9 +23,12 @@ namespace vm {
 namespace c1 {
 constexpr int kTileN = 256;
 constexpr int kTileM = 128;
-constexpr int kGroupStride = 528;                        // 8-row group: 4 k-chunks x 128 B + 16 B pad
-constexpr int kPlaneBytes = (kTileN / 8) * kGroupStride;  // 16896
-constexpr int kStageBytes = 2 * kPlaneBytes;             // hi + lo
+constexpr int kGroupStride = 528;                        // materialised tile (wgrad1): 4 k-chunks x 128 B + 16 B pad
+constexpr int kPlaneBytes = (kTileN / 8) * kGroupStride;  // 16896 (wgrad1)
+constexpr int kBlocks = kTileN / 8 + 4;                  // overlapped layout: g + c = 0 .. 35
+constexpr int kBlockStride = 144;                        // 128 B + 16 B pad: the lanes' 16-byte stores hit distinct banks
+constexpr int kOvPlaneBytes = kBlocks * kBlockStride;    // 5184
+constexpr int kStageBytes = 2 * kOvPlaneBytes;           // hi + lo
 constexpr int kMaxStages = 4;
 constexpr int kOutBoxBytes = 64 * 128;                   // TMA store box: 64 pooled positions x 64 channels fp16
 constexpr int kOutBufBytes = 4 * kOutBoxBytes;           // [plane][channel half][pos][64 ch] = 32 KB
@@ -116,6 +121,67 @@ __device__ __forceinline__ void toeplitz_store(float (&xv)[39], uint32_t st, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Overlapped Toeplitz producer for the forward conv (see the file header).  Block m of a tile holds the eight
+// 16-byte rows  row i = h[8m + i .. 8m + i + 7],  h[q] = fp16 plane of the preprocessed sample x[p0 - 15 + q].
+// One lane builds one block from 15 samples: an aligned 16-float window when the clip is contiguous and the window
+// is interior, guarded scalar loads otherwise (strided / decimated input, clip borders -> 'same' zero padding).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void toeplitz_block_load(const float* __restrict__ xc, int xs, float pm, float ps, int e0,
+                                                    int L, float (&v)[15]) {
+  // needs x[e0 .. e0 + 14]; e0 = p0 - 15 + 8m, so e0 - 1 is a multiple of 8
+  const float* w = xc + (e0 - 1);
+  if (xs == 1 && e0 >= 1 && e0 + 15 <= L && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4 a = __ldg(w4), b = __ldg(w4 + 1), c = __ldg(w4 + 2), d = __ldg(w4 + 3);
+    const float t[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 15; ++k) v[k] = (t[k + 1] - pm) * ps;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+      const int e = e0 + k;
+      v[k] = (e >= 0 && e < L) ? (__ldg(xc + size_t(e) * xs) - pm) * ps : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void toeplitz_block_store_plane(const float (&v)[15], uint32_t dst) {
+  uint32_t pe[7], po[7];  // pe[k] = (h[2k], h[2k+1]), po[k] = (h[2k+1], h[2k+2])
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    pe[k] = pack2<false>(v[2 * k], v[2 * k + 1]);
+    po[k] = pack2<false>(v[2 * k + 1], v[2 * k + 2]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t* src = (i & 1) ? (po + (i - 1) / 2) : (pe + i / 2);
+    sts_v4(dst + i * 16, src[0], src[1], src[2], src[3]);
+  }
+}
+__device__ __forceinline__ void toeplitz_block_store(float (&v)[15], uint32_t dst, int nplanes) {
+  toeplitz_block_store_plane(v, dst);
+  if (nplanes == 2) {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) v[k] -= round16<false>(v[k]);
+    toeplitz_block_store_plane(v, dst + c1::kOvPlaneBytes);
+  }
+}
+
+// 32 accumulator columns of one channel -> 8 pooled outputs (MaxPool 4) -> bias/ReLU/BN -> fp16 (hi, lo) -> staging
+template <bool kClampHi>
+__device__ __forceinline__ void pool4_epilogue(const float4& ep, const uint32_t (&r)[32], uint32_t sh, uint32_t sl,
+                                               int nplanes) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float y = apply_epi_pool4<kClampHi>(ep, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    __half h, l;
+    split_f32(y, h, l);
+    sts_u16(sh + j * 128, h);
+    if (nplanes == 2) sts_u16(sl + j * 128, l);
+  }
+}
+
 __global__ void __launch_bounds__(c1::kThreads, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol,
              const Conv1Params p) {
@@ -169,12 +235,14 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       // affine; 'same' zero padding applies to the preprocessed signal
       const float pm = p.pre_mean ? __ldg(p.pre_mean + n) : 0.f;
       const float ps = p.pre_scale ? __ldg(p.pre_scale + n) : 1.f;
-      // lane owns the 8 positions p0 + 8*lane .. +7; it needs x[p0 - 15 + 8*lane + i], i = 0..38
-      const int e0 = p0 - 15 + 8 * lane;
-      float xv[39];
-      toeplitz_load_strip(xc, xs, pm, ps, e0, p.L, xv);
+      // lane builds block m = lane (and lanes 0-3 block 32 + lane): samples x[p0 - 15 + 8m + (0..14)]
+      float xv[15], xw[15];
+      toeplitz_block_load(xc, xs, pm, ps, p0 - 15 + 8 * lane, p.L, xv);
+      if (lane < kBlocks - 32) toeplitz_block_load(xc, xs, pm, ps, p0 - 15 + 8 * (32 + lane), p.L, xw);
       mbar_wait(&bars->empty[sidx], (((i / kStages) & 1) ^ 1));
-      toeplitz_store<false>(xv, smem_u32(stages + sidx * kStageBytes + lane * kGroupStride), nplanes, kPlaneBytes);
+      const uint32_t sb = smem_u32(stages + sidx * kStageBytes);
+      toeplitz_block_store(xv, sb + lane * kBlockStride, nplanes);
+      if (lane < kBlocks - 32) toeplitz_block_store(xw, sb + (32 + lane) * kBlockStride, nplanes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[sidx]);
@@ -189,7 +257,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
         mbar_wait(&bars->full[s], (i / kStages) & 1);
         tc_fence_after_sync();
         const uint32_t th = smem_u32(stages + s * kStageBytes);
-        const uint32_t tl = th + kPlaneBytes;
+        const uint32_t tl = th + kOvPlaneBytes;
         for (int slab = 0; slab < p.nslab; ++slab, ++ait) {
           const int buf = ait & 1;
           mbar_wait(&bars->tempty[buf], ((ait >> 1) & 1) ^ 1);
@@ -200,16 +268,16 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
-                     make_smem_desc(th + k * 256, 128, kGroupStride, kLayoutNone), idesc, k);
+                     make_smem_desc(th + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, k);
           if (nplanes == 2) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
-                       make_smem_desc(tl + k * 256, 128, kGroupStride, kLayoutNone), idesc, 1);
+                       make_smem_desc(tl + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, 1);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               umma_f16(d_tmem, make_smem_desc(wl + k * 256, 128, 512, kLayoutNone),
-                       make_smem_desc(th + k * 256, 128, kGroupStride, kLayoutNone), idesc, 1);
+                       make_smem_desc(th + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, 1);
           }
           umma_commit(&bars->tfull[buf]);
         }
@@ -299,35 +367,28 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           named_bar_sync(bar_id, 256);
           tc_fence_after_sync();
           const bool no_hi = epi_no_upper_clamp(ep);
-#pragma unroll 1
-          for (int gg = 0; gg < kTileN / 64; ++gg) {
-            const int g = chalf * (kTileN / 64) + gg;
-            float v[32];
-            tmem_ld_32x32(taddr + g * 32, v);
-            if (gg == kTileN / 64 - 1) {
+          // software-pipelined TMEM reads: the load of the next 32 columns is in flight while these are processed
+          const int g0 = chalf * (kTileN / 64);
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32_issue(taddr + g0 * 32, ra);
+          const auto emit = [&](const uint32_t (&r)[32], int g) {
+            const uint32_t sh = st_h + g * 8 * 128, sl = st_l + g * 8 * 128;
+            if (no_hi) pool4_epilogue<false>(ep, r, sh, sl, nplanes);
+            else pool4_epilogue<true>(ep, r, sh, sl, nplanes);
+          };
+#pragma unroll
+          for (int gg = 0; gg < kTileN / 64; gg += 2) {
+            tmem_ld_wait(ra);
+            tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
+            emit(ra, g0 + gg);
+            tmem_ld_wait(rb);
+            if (gg + 2 < kTileN / 64) {
+              tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
+            } else {  // all TMEM reads of this accumulator are done
               tc_fence_before_sync();
               mbar_arrive(&bars->tempty[buf]);
             }
-            const uint32_t sh = st_h + g * 8 * 128, sl = st_l + g * 8 * 128;
-            if (no_hi) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float y = apply_epi_pool4<false>(ep, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __half h, l;
-                split_f32(y, h, l);
-                sts_u16(sh + j * 128, h);
-                if (nplanes == 2) sts_u16(sl + j * 128, l);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float y = apply_epi_pool4<true>(ep, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __half h, l;
-                split_f32(y, h, l);
-                sts_u16(sh + j * 128, h);
-                if (nplanes == 2) sts_u16(sl + j * 128, l);
-              }
-            }
+            emit(rb, g0 + gg + 1);
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 256);
@@ -381,7 +442,7 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   p.wpack = reinterpret_cast<const uint4*>(wpack);
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo;
-  p.nstages = (nslab == 1) ? 4 : (nslab <= 3 ? 3 : 2);
+  p.nstages = kMaxStages;
   p.out_f32 = out_f32;
   p.stat_partial = reinterpret_cast<float2*>(stat_partial);
   CUtensorMap oh, ol;

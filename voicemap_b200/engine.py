@@ -180,21 +180,26 @@ class EncoderEngine:
         _lib.check(self.lib.vm_merge_planes(_ptr(hi), _ptr(lo), hi.numel(), _ptr(x), _stream()), "vm_merge_planes")
         return x
 
-    def block1(self, x):
-        """x (N, L) fp32 -> planes (N, L//4, f)."""
+    def block1(self, x, out=None):
+        """x (N, L) fp32 -> planes (N, L//4, f).  ``out`` = (hi, lo) reuses caller-owned planes."""
         if not self._packed:
             self.pack()
         n, length = x.shape
         f = self.channels[0]
-        hi = torch.empty((n, length // 4, f), dtype=torch.float16, device=self.device)
-        lo = torch.empty_like(hi)
+        if out is not None:
+            hi, lo = out
+            assert hi.shape == (n, length // 4, f) and lo.shape == hi.shape and hi.dtype == torch.float16
+        else:
+            hi = torch.empty((n, length // 4, f), dtype=torch.float16, device=self.device)
+            lo = torch.empty_like(hi)
         rc = self.lib.vm_conv1_relu_bn_pool4_fwd(_ptr(x), n, length, f, _ptr(self.wpack[0]), _ptr(self.epi[0]),
                                                  _ptr(hi), _ptr(lo), self.precision, _stream())
         _lib.check(rc, "vm_conv1_relu_bn_pool4_fwd")
         return hi, lo
 
-    def block3(self, index, in_hi, in_lo, gmax=False):
-        """Block `index` in {2,3,4}: planes (N, L, Cin) -> planes (N, L//2, Cout), or gmax partials."""
+    def block3(self, index, in_hi, in_lo, gmax=False, out=None):
+        """Block `index` in {2,3,4}: planes (N, L, Cin) -> planes (N, L//2, Cout), or gmax partials.
+        ``out`` = (hi, lo) planes, or the partials tensor with gmax=True, reuses caller-owned buffers."""
         if not self._packed:
             self.pack()
         n, length, cin = in_hi.shape
@@ -203,14 +208,19 @@ class EncoderEngine:
         if gmax:
             t = self.lib.vm_conv3_num_position_tiles(length)
             cpad = self.lib.vm_padded_channels(cout)
-            part = torch.empty((n, t, cpad), dtype=torch.float32, device=self.device)
+            part = out if out is not None else torch.empty((n, t, cpad), dtype=torch.float32, device=self.device)
+            assert part.shape == (n, t, cpad) and part.dtype == torch.float32
             rc = self.lib.vm_conv3_relu_bn_pool2_fwd(_ptr(in_hi), _ptr(in_lo), n, length, cin, cout,
                                                      _ptr(self.wpack[index - 1]), _ptr(self.epi[index - 1]),
                                                      None, None, _ptr(part), self.precision, _stream())
             _lib.check(rc, "vm_conv3_relu_bn_pool2_fwd(gmax)")
             return part
-        hi = torch.empty((n, length // 2, cout), dtype=torch.float16, device=self.device)
-        lo = torch.empty_like(hi)
+        if out is not None:
+            hi, lo = out
+            assert hi.shape == (n, length // 2, cout) and lo.shape == hi.shape and hi.dtype == torch.float16
+        else:
+            hi = torch.empty((n, length // 2, cout), dtype=torch.float16, device=self.device)
+            lo = torch.empty_like(hi)
         rc = self.lib.vm_conv3_relu_bn_pool2_fwd(_ptr(in_hi), _ptr(in_lo), n, length, cin, cout,
                                                  _ptr(self.wpack[index - 1]), _ptr(self.epi[index - 1]), _ptr(hi),
                                                  _ptr(lo), None, self.precision, _stream())

@@ -16,6 +16,28 @@ DISTANCE_METRICS = ('uniform_euclidean', 'weighted_euclidean',
                     'dot_product', 'cosine_distance')
 
 _PREDICT_CHUNK = 4096  # clips per device launch in predict(); results do not depend on it (eval mode)
+_PIPELINE_BUFFER_BYTES = 1 << 31  # device staging buffer for host batches in predict()
+
+
+def _pipeline_plan(n, pinned=True):
+    """[(lo, hi), ...] covering range(n).  The first chunk is small (its copy is the only exposed one); each next
+    chunk is ~2.5x larger, because the encoder needs ~2.4x longer per clip than a PCIe copy of it does, so every
+    copy finishes while the previous chunk is still being embedded.  Pageable memory copies synchronously: plain
+    chunks of _PREDICT_CHUNK clips."""
+    if not pinned or n < 96:
+        return [(lo, min(n, lo + _PREDICT_CHUNK)) for lo in range(0, n, _PREDICT_CHUNK)]
+    plan, lo = [], 0
+    size = max(16, -(-n // 11 // 8) * 8)
+    while lo < n:
+        size = min(size, _PREDICT_CHUNK)
+        hi = lo + size
+        if n - hi < size:       # a short tail rides with this chunk
+            hi = n if n - lo <= _PREDICT_CHUNK else hi
+        hi = min(hi, n)
+        plan.append((lo, hi))
+        lo = hi
+        size = -(-int(size * 2.5) // 8) * 8
+    return plan
 
 
 def _glorot_uniform(shape, rng):
@@ -254,42 +276,34 @@ class EncoderModel(_ModelBase):
         return emb.cpu().numpy()
 
     def _embed_pipelined(self, xt, eng):
-        """Host batch (N, L) -> device embeddings.  Batches of >= 128 clips in pinned memory are cut into chunks whose
-        host->device copies run on a side stream and overlap the previous chunk's kernels (double buffering)."""
+        """Host batch (N, L) -> device embeddings.  A pinned batch is cut into chunks of geometrically growing size
+        (``_pipeline_plan``): the host->device copies run back to back on a side stream while the main stream
+        embeds every chunk as soon as it has landed, so only the first small copy is exposed."""
         import torch
         n, length = xt.shape
         dev = eng.device
         out = torch.empty((n, self.embedding_dimension), dtype=torch.float32, device=dev)
-        chunk = _PREDICT_CHUNK
-        if n >= 128 and xt.is_pinned():
-            # two chunks: the second copy hides behind the first chunk's kernels; more chunks cost more launch /
-            # descriptor overhead than they hide (measured: 4 chunks of 64 clips were slower than 1 x 256)
-            chunk = max(64, min(_PREDICT_CHUNK, -(-n // (2 if n < 2048 else 4))))
-        if chunk >= n:
+        rows = max(1, min(n, _PIPELINE_BUFFER_BYTES // (4 * length)))   # device input buffer, grow-only
+        if not xt.is_pinned() and n <= _PREDICT_CHUNK:
             eng.forward(xt.to(dev, non_blocking=True), out=out)
             return out
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._copy_bufs = None
+            self._copy_buf = None
+        if self._copy_buf is None or self._copy_buf.numel() < rows * length:
+            self._copy_buf = torch.empty(rows * length, dtype=torch.float32, device=dev)
+        xin = self._copy_buf[:rows * length].view(rows, length)
         main = torch.cuda.current_stream(dev)
-        if self._copy_bufs is None or self._copy_bufs[0].shape != (chunk, length):
-            self._copy_bufs = [torch.empty((chunk, length), dtype=torch.float32, device=dev) for _ in range(2)]
-        bufs = self._copy_bufs
-        freed = [None, None]
-        self._copy_stream.wait_stream(main)
-        for k, lo in enumerate(range(0, n, chunk)):
-            hi = min(n, lo + chunk)
-            slot = k & 1
-            with torch.cuda.stream(self._copy_stream):
-                if freed[slot] is not None:
-                    self._copy_stream.wait_event(freed[slot])       # the kernels that read this buffer are done
-                bufs[slot][:hi - lo].copy_(xt[lo:hi], non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(self._copy_stream)
-            main.wait_event(copied)
-            eng.forward(bufs[slot][:hi - lo], out=out[lo:hi])
-            freed[slot] = torch.cuda.Event()
-            freed[slot].record(main)
+        for base in range(0, n, rows):
+            m = min(rows, n - base)
+            self._copy_stream.wait_stream(main)     # earlier kernels that read the buffer are done
+            for lo, hi in _pipeline_plan(m, xt.is_pinned()):
+                with torch.cuda.stream(self._copy_stream):
+                    xin[lo:hi].copy_(xt[base + lo:base + hi], non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(self._copy_stream)
+                main.wait_event(copied)
+                eng.forward(xin[lo:hi], out=out[base + lo:base + hi])
         return out
 
     def predict_raw(self, x, downsampling=4, whitening=True):
