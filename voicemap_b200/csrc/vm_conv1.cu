@@ -168,13 +168,13 @@ __device__ __forceinline__ void toeplitz_block_store(float (&v)[15], uint32_t ds
 }
 
 // 32 accumulator columns of one channel -> 8 pooled outputs (MaxPool 4) -> bias/ReLU/BN -> fp16 (hi, lo) -> staging
-template <bool kClampHi>
-__device__ __forceinline__ void pool4_epilogue(const float4& ep, const uint32_t (&r)[32], uint32_t sh, uint32_t sl,
-                                               int nplanes) {
+__device__ __forceinline__ void pool4_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32],
+                                                      uint32_t sh, uint32_t sl, int nplanes) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float y = apply_epi_pool4<kClampHi>(ep, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    const float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
+    const float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
+    const float y = no_hi ? apply_epi_pool4<false>(ep, v0, v1, v2, v3) : apply_epi_pool4<true>(ep, v0, v1, v2, v3);
     __half h, l;
     split_f32(y, h, l);
     sts_u16(sh + j * 128, h);
@@ -371,10 +371,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           const int g0 = chalf * (kTileN / 64);
           uint32_t ra[32], rb[32];
           tmem_ld_32x32_issue(taddr + g0 * 32, ra);
+          // Both clamp forms are evaluated and one is selected (pool4_epilogue): measured faster than branching
+          // on no_hi per 32 columns or per tile, because branches inside the pipelined loop serialise the TMEM
+          // loads against the arithmetic (profiles/r01_conv1_epilogue_ab.log: 0.097 vs 0.111 ms per launch).
           const auto emit = [&](const uint32_t (&r)[32], int g) {
-            const uint32_t sh = st_h + g * 8 * 128, sl = st_l + g * 8 * 128;
-            if (no_hi) pool4_epilogue<false>(ep, r, sh, sl, nplanes);
-            else pool4_epilogue<true>(ep, r, sh, sl, nplanes);
+            pool4_epilogue(ep, no_hi, r, st_h + g * 8 * 128, st_l + g * 8 * 128, nplanes);
           };
 #pragma unroll
           for (int gg = 0; gg < kTileN / 64; gg += 2) {
