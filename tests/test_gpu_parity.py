@@ -207,7 +207,7 @@ def test_predict_pipelined_host_batch_is_bit_identical(stress_params):
     enc.set_named_weights(stress_params)
     g = torch.Generator().manual_seed(11)
     x = (O.WHITEN_RMS * torch.randn(300, 4000, 1, generator=g)).pin_memory()
-    assert len(_pipeline_plan(300)) >= 3
+    assert len(_pipeline_plan(300)) >= 2
     got = enc.predict(x)
     eng = enc._get_engine()
     whole = eng.forward(x[:, :, 0].cuda().contiguous()).cpu().numpy()

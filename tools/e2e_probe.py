@@ -48,6 +48,33 @@ def main():
     print(f"device forward      {wall(fwd):.3f} ms")
     t = wall(h2d)
     print(f"H2D 12.3 MB pinned  {t:.3f} ms  ({N * L * 4 / t / 1e6:.1f} GB/s)")
+    def zc():
+        k[0] += 1
+        eng.forward(sets[k[0] % 6][:, :, 0], out=out)
+    print(f"zero-copy forward (block 1 reads pinned host memory)  {wall(zc):.3f} ms")
+
+    def zc_e2e():
+        k[0] += 1
+        eng.forward(sets[k[0] % 6][:, :, 0], out=out)
+        return out.cpu().numpy()
+    print(f"zero-copy forward + D2H                               {wall(zc_e2e):.3f} ms")
+
+    def split_e2e(frac):
+        # first part zero-copy, rest by DMA issued up front on the side stream
+        k[0] += 1
+        x = sets[k[0] % 6][:, :, 0]
+        m = int(N * frac) // 8 * 8
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            dev[1][m:].copy_(x[m:], non_blocking=True)
+            evc = torch.cuda.Event(); evc.record(side)
+        eng.forward(x[:m], out=out[:m])
+        torch.cuda.current_stream().wait_event(evc)
+        eng.forward(dev[1][m:], out=out[m:])
+        return out.cpu().numpy()
+    side = torch.cuda.Stream()
+    for frac in (0.25, 0.5, 0.75):
+        print(f"zero-copy first {frac:.2f} + DMA rest + D2H                  {wall(lambda: split_e2e(frac)):.3f} ms")
     plans = {
         "single": [N],
         "2 equal": [128, 128],

@@ -121,13 +121,15 @@ class EncoderEngine:
         return C.c_void_p((base + 1023) // 1024 * 1024)
 
     def forward(self, x, out=None):
-        """x: CUDA fp32 tensor (N, L) or (N, L, 1), contiguous.  Returns (N, E) fp32 embeddings (CUDA)."""
+        """x: contiguous fp32 tensor (N, L) or (N, L, 1), on the device or in PINNED host memory (block 1 then reads
+        the waveform over PCIe/C2C directly -- pinned allocations are device-mapped under unified addressing; the
+        caller keeps the tensor alive and unchanged until the stream has run).  Returns (N, E) fp32 (CUDA)."""
         if x.dim() == 3:
             if x.shape[2] != 1:
                 raise ValueError("encoder input must have one channel: (N, L, 1)")
             x = x.reshape(x.shape[0], x.shape[1])
-        if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous():
-            raise ValueError("encoder input must be a contiguous CUDA float32 tensor")
+        if x.dtype != torch.float32 or not (x.is_cuda or x.is_pinned()) or not x.is_contiguous():
+            raise ValueError("encoder input must be a contiguous float32 tensor on the device or in pinned memory")
         if not self._packed:
             self.pack()
         n, length = x.shape

@@ -20,34 +20,21 @@ _PIPELINE_BUFFER_BYTES = 1 << 31  # device staging buffer for host batches in pr
 
 
 def _pipeline_plan(n, pinned=True):
-    """[(lo, hi), ...] covering range(n).  The first chunk is small (its copy is the only exposed one); each next
-    chunk is ~2.5x larger, because the encoder needs ~2.4x longer per clip than a PCIe copy of it does, so every
-    copy finishes while the previous chunk is still being embedded.  Pageable memory copies synchronously: plain
-    chunks of _PREDICT_CHUNK clips."""
+    """[(lo, hi), ...] covering range(n).  A pinned batch is cut into a small first chunk (n/8 clips: its copy is
+    the only one that is not hidden) and the rest, in pieces of at most _PREDICT_CHUNK clips.  Measured on B200
+    (tools/e2e_probe.py, profiles/r01_e2e_probe.log): copies that run concurrently with the encoder kernels drop
+    to ~1/4 of their stand-alone rate and every extra chunk costs ~0.05 ms of fixed kernel prologue, so finer
+    plans (3-4 chunks) are not faster.  Pageable memory copies synchronously: plain chunks."""
     if not pinned or n < 96:
         return [(lo, min(n, lo + _PREDICT_CHUNK)) for lo in range(0, n, _PREDICT_CHUNK)]
-    plan, lo = [], 0
-    size = max(16, -(-n // 11 // 8) * 8)
+    first = min(_PREDICT_CHUNK, max(16, n // 8 // 8 * 8))
+    plan = [(0, first)]
+    lo = first
     while lo < n:
-        size = min(size, _PREDICT_CHUNK)
-        hi = lo + size
-        if n - hi < size:       # a short tail rides with this chunk
-            hi = n if n - lo <= _PREDICT_CHUNK else hi
-        hi = min(hi, n)
+        hi = min(n, lo + _PREDICT_CHUNK)
         plan.append((lo, hi))
         lo = hi
-        size = -(-int(size * 2.5) // 8) * 8
     return plan
-
-
-def _glorot_uniform(shape, rng):
-    if len(shape) == 2:
-        fan_in, fan_out = shape
-    else:
-        rec = int(np.prod(shape[:-2]))
-        fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
-    limit = np.sqrt(6.0 / (fan_in + fan_out))
-    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
 
 
 class LayerInfo:
@@ -276,9 +263,9 @@ class EncoderModel(_ModelBase):
         return emb.cpu().numpy()
 
     def _embed_pipelined(self, xt, eng):
-        """Host batch (N, L) -> device embeddings.  A pinned batch is cut into chunks of geometrically growing size
+        """Host batch (N, L) -> device embeddings.  A pinned batch is cut into a small first chunk and the rest
         (``_pipeline_plan``): the host->device copies run back to back on a side stream while the main stream
-        embeds every chunk as soon as it has landed, so only the first small copy is exposed."""
+        embeds every chunk as soon as it has landed."""
         import torch
         n, length = xt.shape
         dev = eng.device
