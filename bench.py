@@ -337,7 +337,7 @@ def run_b200(args):
                                  f"{length} samples/clip (3 s @ 16 kHz {'raw' if length == 48000 else 'after the reference x4 decimation'}), "
                                  f"precision={args.precision}",
                         l2=f"inputs rotate over {n_sets} batches ({n_sets * n * length * 4 / 1e6:.0f} MB > 126 MB L2); "
-                           f"activations {eng.lib.vm_encoder_workspace_bytes(n, length, FILTERS) / 1e6:.0f} MB/step",
+                           f"activations {eng.lib.vm_encoder_workspace_bytes(n, length, FILTERS, 4) / 1e6:.0f} MB/step",
                         parallelism=f"dp{world} (independent clips, no collective)"),
             clocks=clocks,
             e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=n * length * 4,

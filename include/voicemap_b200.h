@@ -55,9 +55,10 @@ int vm_padded_channels(int cout);
 /* ---- weight preparation ---------------------------------------------------------------------------------
  * Replaces the (implicit) Keras weight layout of Conv1D + BatchNormalization (voicemap/models.py:13-35):
  * kernel (K, Cin, Cout), bias, BN gamma/beta/moving_mean/moving_variance, eps (Keras default 1e-3) are folded
- * into fp16 (hi, lo) weight planes in the MMA operand layout and per-channel constants {sigma, bias, s, t} with
- * s = gamma / sqrt(var + eps), t = beta - mean * s, sigma = sign(s) (weights are stored sigma-scaled so that
- * max-pooling commutes with the BN affine when gamma < 0). */
+ * into fp16 (hi, lo) weight planes in the MMA operand layout and four per-channel epilogue constants (opaque to the
+ * caller).  With s = gamma / sqrt(var + eps), t = beta - mean * s, sigma = sign(s): weights are stored sigma-scaled
+ * so that max-pooling commutes with the BN affine when gamma < 0, and bias + ReLU + BN become one clamp and one
+ * FMA on the pooled accumulator maximum. */
 int vm_pack_conv1(const float* kernel /* (32, 1, Cout) */, const float* bias, const float* gamma,
                   const float* beta, const float* mean, const float* var, float eps, int cout, void* wpack,
                   float* epi, void* stream);
@@ -65,10 +66,12 @@ int vm_pack_conv3(const float* kernel /* (3, Cin, Cout) */, const float* bias, c
                   const float* beta, const float* mean, const float* var, float eps, int cin, int cout, void* wpack,
                   float* epi, void* stream);
 
-/* ---- block 1: Conv1D(filters, 32, 'same', relu) -> BatchNormalization -> MaxPool1D(4, 4) ------------------
- * voicemap/models.py:13-19.  x (N, L) fp32 (Keras (N, L, 1)); out planes (N, L/4, Cout). */
-int vm_conv1_relu_bn_pool4_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi,
-                               uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream);
+/* ---- block 1: Conv1D(filters, 32, 'same', relu) -> BatchNormalization -> MaxPool1D(pool, pool) ------------
+ * voicemap/models.py:13-19.  x (N, L) fp32 (Keras (N, L, 1)); out planes (N, L/pool, Cout).  pool = 4 is the
+ * reference architecture (voicemap/models.py:19); pool = 2 is the older architecture of the checkpoint shipped
+ * under models/n_seconds/ (its model_config has four MaxPooling1D(2)). */
+int vm_conv1_relu_bn_pool_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,
+                              uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream);
 
 /* ---- blocks 2-4: Conv1D(C, 3, 'same', relu) -> BatchNormalization -> MaxPool1D(2) -------------------------
  * voicemap/models.py:22-35.  in planes (N, L, Cin); out planes (N, L/2, Cout).
@@ -99,11 +102,12 @@ int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, 
 
 /* ---- whole encoder (voicemap/models.py:6-41, eval mode) ---------------------------------------------------
  * x (N, L) fp32 -> emb (N, E).  `wpack[i]`, `epi[i]` (i = 0..3) from vm_pack_conv1 / vm_pack_conv3 for channel
- * widths filters*{1,2,3,4}.  `workspace` must hold vm_encoder_workspace_bytes(N, L, filters) bytes. */
-size_t vm_encoder_workspace_bytes(int N, int L, int filters);
-int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const* wpack, const float* const* epi,
-                   const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
-                   void* stream);
+ * widths filters*{1,2,3,4}.  first_pool = size of the first MaxPool1D (4, or 2 for the older architecture, see
+ * vm_conv1_relu_bn_pool_fwd).  `workspace` must hold vm_encoder_workspace_bytes(N, L, filters, first_pool) bytes. */
+size_t vm_encoder_workspace_bytes(int N, int L, int filters, int first_pool);
+int vm_encoder_fwd(const float* x, int N, int L, int filters, int first_pool, const void* const* wpack,
+                   const float* const* epi, const float* dense_w, const float* dense_b, int E, void* workspace,
+                   float* emb, int precision, void* stream);
 
 /* ---- fused preprocessing (voicemap/utils.py:22-34, 88-101) ------------------------------------------------
  * The reference decimates raw 16 kHz clips on the host (instances[:, ::downsampling, :]) and whitens them: per-clip
@@ -112,14 +116,14 @@ int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const*
  * in double precision; `scale` must hold N floats followed by 4*N + 4 floats of scratch.
  * vm_encoder_fwd_raw runs the encoder on raw audio x (N, T) fp32 with the decimation (strided read) and the
  * whitening affine fused into block 1's operand producer: L = ceil(T / downsampling) samples enter the network.
- * whiten_groups = 0 disables whitening.  `workspace` must hold vm_encoder_workspace_bytes(N, L, filters) +
- * vm_preprocess_scratch_bytes(N) bytes. */
+ * whiten_groups = 0 disables whitening.  `workspace` must hold vm_encoder_workspace_bytes(N, L, filters, first_pool)
+ * + vm_preprocess_scratch_bytes(N) bytes. */
 size_t vm_preprocess_scratch_bytes(int N);
 int vm_preprocess_stats(const float* x, int N, int T, int downsampling, int G, float rms, float* mean, float* scale,
                         void* stream);
 int vm_encoder_fwd_raw(const float* x, int N, int T, int downsampling, int whiten_groups, float rms, int filters,
-                       const void* const* wpack, const float* const* epi, const float* dense_w, const float* dense_b,
-                       int E, void* workspace, float* emb, int precision, void* stream);
+                       int first_pool, const void* const* wpack, const float* const* epi, const float* dense_w,
+                       const float* dense_b, int E, void* workspace, float* emb, int precision, void* stream);
 
 /* =============================================================================================================
  * Training (SURVEY.md 8(a) a3 train mode, a4, a13): what Keras' fit_generator does implicitly for

@@ -38,9 +38,11 @@ def test_size_helpers(built_library):
     # workspace: planes of the three stored activations + gmax partials (fp16 hi+lo = 4 bytes/element)
     n, l, f = 8, 12000, 128
     expect = 4 * n * (3000 * f + 1500 * 2 * f + 750 * 3 * f) + 4 * n * 6 * 4 * f
-    got = lib.vm_encoder_workspace_bytes(n, l, f)
+    got = lib.vm_encoder_workspace_bytes(n, l, f, 4)
     assert expect <= got <= expect + 8 * 1024
-    assert lib.vm_encoder_workspace_bytes(8, 16, 128) == 0  # too short for four pooling stages
+    assert lib.vm_encoder_workspace_bytes(8, 16, 128, 4) == 0  # too short for four pooling stages
+    assert lib.vm_encoder_workspace_bytes(8, 16, 128, 2) > 0   # older architecture: pools 2*2*2*2
+    assert lib.vm_encoder_workspace_bytes(8, 4096, 128, 3) == 0
 
 
 def test_errors_are_codes_not_exceptions(built_library):
@@ -48,7 +50,7 @@ def test_errors_are_codes_not_exceptions(built_library):
     assert lib.vm_set_option(b"no_such_option", 1) == _lib.VM_ERR_SHAPE
     assert b"unknown key" in lib.vm_last_error_string()
     # null pointers are rejected before any CUDA call is made
-    rc = lib.vm_conv1_relu_bn_pool4_fwd(None, 1, 1024, 128, None, None, None, None, 3, None)
+    rc = lib.vm_conv1_relu_bn_pool_fwd(None, 1, 1024, 128, 4, None, None, None, None, 3, None)
     assert rc == _lib.VM_ERR_SHAPE
 
 

@@ -322,6 +322,43 @@ def test_reference_checkpoint_weights_fixture():
     assert np.abs(prob - z["prob64"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("n,length", [(4, 12000), (3, 1999), (2, 516), (5, 16)])
+def test_first_pool_2_architecture_matches_oracle(stress_params, n, length):
+    """Older reference architecture (MaxPool1D 2,2,2,2 -- the shipped checkpoint): block 1 pools 2:1 in
+    two staging passes per tile.  Ragged lengths exercise the clipped second pass."""
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+    enc = get_baseline_convolutional_encoder(128, 64, dropout=0.0, first_pool=2)
+    enc.set_named_weights(stress_params)
+    x = O.synthetic_clips(n, length, seed=77 + length, padded=(length == 12000))
+    ref = O.encoder_forward(x, stress_params, torch.float32, pools=(2, 2, 2, 2))
+    assert _per_clip(enc.predict(x), ref) <= TOL
+    eng = enc._get_engine()
+    hi, lo = eng.block1(torch.from_numpy(x[:, :, 0].astype(np.float32)).cuda())
+    assert hi.shape == (n, length // 2, 128)
+    inter = O.encoder_forward(x, stress_params, torch.float64, pools=(2, 2, 2, 2), return_intermediates=True)[1]
+    got = eng.merge_planes(hi, lo).cpu().numpy()
+    assert np.abs(got - inter[0]).max() <= 1e-5 * np.abs(inter[0]).max()
+
+
+def test_shipped_checkpoint_in_its_own_architecture():
+    """Real trained weights (checkpoint_f32.npz = the reference's shipped checkpoint) in the architecture they were
+    trained in (first pool 2, embedding 128, weighted_l1 head) against the oracle."""
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "checkpoint_f32.npz"))
+    w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
+    enc = get_baseline_convolutional_encoder(32, 128, first_pool=2)
+    enc.set_named_weights(w)
+    ref64 = O.encoder_forward(z["x"], w, torch.float64, pools=(2, 2, 2, 2))
+    assert _per_clip(enc.predict(z["x"]), ref64) <= TOL
+    sia = build_siamese_net(enc, (12000, 1), "weighted_l1")
+    sia.head_weights["head_kernel"] = z["head_kernel"].copy()
+    sia.head_weights["head_bias"] = z["head_bias"].copy()
+    prob = sia.predict([z["x"][:3], z["x"][3:]])
+    refp, _ = O.siamese_head(ref64[:3], ref64[3:], z["head_kernel"].reshape(-1).astype(np.float64),
+                             float(z["head_bias"][0]), "weighted_l1")
+    assert np.abs(prob - refp).max() < 1e-4
+
+
 def test_large_batch_of_short_clips(stress_params):
     """n_seconds sweep corner (1 s clips, L = 4000) at a batch well beyond one wave of tiles per SM."""
     eng = _engine(128, 64, stress_params)

@@ -249,3 +249,31 @@ def test_keras_hdf5_reader_on_synthetic_file(tmp_path):
     assert abs(float(z["head_bias"][0]) + 2.692142) < 1e-6
     assert z["w_dense_kernel"].shape == (128, 128) and z["head_kernel"].shape == (128, 1)
     assert z["w_bn1_var"].min() < 1e-6 and z["w_bn4_var"].max() > 29
+
+
+def test_load_model_selects_the_checkpoints_own_architecture():
+    """The checkpoint the reference ships (models/n_seconds/...) was trained with four MaxPooling1D(2)
+    and a weighted_l1 head; load_model must rebuild exactly that (first_pool = 2), not force the weights into the
+    current architecture.  The file exists only where the reference is mounted."""
+    import os
+    import pytest
+    path = "/root/reference/models/n_seconds/siamese__nseconds_3.0__filters_32__embed_64__drop_0.05__r_0.hdf5"
+    if not os.path.exists(path):
+        pytest.skip("reference checkpoint not available on this box")
+    from voicemap_b200.models import load_model
+    m = load_model(path)
+    assert m.distance_metric == "weighted_l1"
+    enc = m.layers[2]
+    assert enc.first_pool == 2 and enc.filters == 32 and enc.embedding_dimension == 128
+    assert [l.config["pool_size"] for l in enc.layers if l.class_name == "MaxPooling1D"] == [2, 2, 2, 2]
+    clone = enc._clone()
+    assert clone.first_pool == 2 and clone.get_config()["first_pool"] == 2
+
+
+def test_first_pool_argument_is_validated():
+    import pytest
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+    assert get_baseline_convolutional_encoder(16, 8).first_pool == 4          # the reference architecture
+    assert get_baseline_convolutional_encoder(16, 8, first_pool=2).first_pool == 2
+    with pytest.raises(ValueError):
+        get_baseline_convolutional_encoder(16, 8, first_pool=3)

@@ -59,7 +59,7 @@ def main():
     eng = enc._get_engine()
     for rate, lengths in ((4000, (4000, 12000, 20000, 40000)), (16000, (16000, 48000, 80000, 160000))):
         for length in lengths:
-            per_clip = lib.vm_encoder_workspace_bytes(64, length, 128) / 64 + 4 * length
+            per_clip = lib.vm_encoder_workspace_bytes(64, length, 128, 4) / 64 + 4 * length
             n_auto = int(0.9 * total / per_clip)
             n = min(n_auto, max(64, int(2 ** 31 // (length * 512 * 4)) // 4, 1))      # keep index math in int32 range
             n = min(n, 2048 if length <= 20000 else 512)

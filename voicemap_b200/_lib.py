@@ -35,18 +35,18 @@ SIGNATURES = {
     "vm_padded_channels": (_i, [_i]),
     "vm_pack_conv1": (_i, [_vp] * 6 + [_f, _i, _vp, _vp, _vp]),
     "vm_pack_conv3": (_i, [_vp] * 6 + [_f, _i, _i, _vp, _vp, _vp]),
-    "vm_conv1_relu_bn_pool4_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vm_conv1_relu_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_relu_bn_pool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_gmax_dense_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "vm_pair_head_loss_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "vm_split_planes": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "vm_merge_planes": (_i, [_vp, _vp, _sz, _vp, _vp]),
-    "vm_encoder_workspace_bytes": (_sz, [_i, _i, _i]),
-    "vm_encoder_fwd": (_i, [_vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "vm_encoder_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "vm_encoder_fwd": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "vm_set_option": (_i, [C.c_char_p, _i]),
     "vm_preprocess_scratch_bytes": (_sz, [_i]),
     "vm_preprocess_stats": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
-    "vm_encoder_fwd_raw": (_i, [_vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp,
+    "vm_encoder_fwd_raw": (_i, [_vp, _i, _i, _i, _i, _f, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp,
                                 _i, _vp]),
     # training
     "vm_pack_conv1_raw": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),

@@ -80,9 +80,9 @@ struct EncoderPlan {
   int l1, l2, l3, t4, c4_pad;
   size_t a1, a2, a3, part, total;  // plane sizes in bytes (single plane), offsets derived below
 };
-static EncoderPlan plan_encoder(int N, int L, int filters) {
+static EncoderPlan plan_encoder(int N, int L, int filters, int first_pool) {
   EncoderPlan pl{};
-  pl.l1 = L / 4; pl.l2 = pl.l1 / 2; pl.l3 = pl.l2 / 2;
+  pl.l1 = L / first_pool; pl.l2 = pl.l1 / 2; pl.l3 = pl.l2 / 2;
   pl.t4 = 2 * ((pl.l3 + 255) / 256);  // two partial rows (column halves) per 256-position tile
   pl.c4_pad = (4 * filters + 127) / 128 * 128;
   pl.a1 = align_up(size_t(N) * pl.l1 * filters * 2, 1024);
@@ -138,14 +138,14 @@ int vm_pack_conv3(const float* kernel, const float* bias, const float* gamma, co
   return launch_pack_conv3(kernel, bias, gamma, beta, mean, var, eps, cin, cout, wpack, epi, (cudaStream_t)stream);
 }
 
-int vm_conv1_relu_bn_pool4_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi,
-                               uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream) {
+int vm_conv1_relu_bn_pool_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,
+                              uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream) {
   if (x == nullptr || wpack == nullptr || epi == nullptr || out_hi == nullptr)
     return set_error(VM_ERR_SHAPE, "conv1: null pointer");
   if (precision == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 3");
   return launch_conv1(x, N, L, cout, wpack, epi, reinterpret_cast<__half*>(out_hi),
                       reinterpret_cast<__half*>(out_lo), nullptr, nullptr, precision, g_max_ctas,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, 1, 0, nullptr, nullptr, pool);
 }
 
 int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
@@ -274,16 +274,16 @@ int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double*
 #undef H16
 #undef CH16
 
-size_t vm_encoder_workspace_bytes(int N, int L, int filters) {
-  if (N <= 0 || L < 32 || filters <= 0) return 0;
-  return plan_encoder(N, L, filters).total;
+size_t vm_encoder_workspace_bytes(int N, int L, int filters, int first_pool) {
+  if (N <= 0 || filters <= 0 || (first_pool != 2 && first_pool != 4) || L < 8 * first_pool) return 0;
+  return plan_encoder(N, L, filters, first_pool).total;
 }
 
-static int encoder_fwd_impl(const float* x, int N, int L, int filters, const void* const* wpack,
+static int encoder_fwd_impl(const float* x, int N, int L, int filters, int first_pool, const void* const* wpack,
                             const float* const* epi, const float* dense_w, const float* dense_b, int E,
                             void* workspace, float* emb, int precision, cudaStream_t st, int x_stride,
                             long long x_clip_stride, const float* pre_mean, const float* pre_scale) {
-  const EncoderPlan pl = plan_encoder(N, L, filters);
+  const EncoderPlan pl = plan_encoder(N, L, filters, first_pool);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __half* a1h = reinterpret_cast<__half*>(ws);
   __half* a1l = reinterpret_cast<__half*>(ws + pl.a1);
@@ -295,7 +295,7 @@ static int encoder_fwd_impl(const float* x, int N, int L, int filters, const voi
   const int f = filters;
   int rc;
   if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, precision, g_max_ctas, st, x_stride,
-                         x_clip_stride, pre_mean, pre_scale)))
+                         x_clip_stride, pre_mean, pre_scale, first_pool)))
     return rc;
   if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
                          nullptr, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
@@ -310,22 +310,24 @@ static int encoder_fwd_impl(const float* x, int N, int L, int filters, const voi
 }
 
 static int encoder_args_ok(const void* x, const void* wpack, const void* epi, const void* workspace, const void* emb,
-                           int N, int L, int filters) {
+                           int N, int L, int filters, int first_pool) {
   if (x == nullptr || wpack == nullptr || epi == nullptr || workspace == nullptr || emb == nullptr)
     return set_error(VM_ERR_SHAPE, "encoder: null pointer");
   if (N <= 0 || filters <= 0) return set_error(VM_ERR_SHAPE, "encoder: bad shape");
-  if (L < 32) return set_error(VM_ERR_SHAPE, "encoder: L must be >= 32 (four pooling stages 4*2*2*2)");
+  if (first_pool != 2 && first_pool != 4)
+    return set_error(VM_ERR_UNSUPPORTED, "encoder: first MaxPool1D size must be 4 (voicemap/models.py:19) or 2");
+  if (L < 8 * first_pool) return set_error(VM_ERR_SHAPE, "encoder: L must cover the four pooling stages (p*2*2*2)");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
     return set_error(VM_ERR_SHAPE, "encoder: workspace must be 1024-byte aligned");
   return VM_OK;
 }
 
-int vm_encoder_fwd(const float* x, int N, int L, int filters, const void* const* wpack, const float* const* epi,
-                   const float* dense_w, const float* dense_b, int E, void* workspace, float* emb, int precision,
-                   void* stream) {
-  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters);
+int vm_encoder_fwd(const float* x, int N, int L, int filters, int first_pool, const void* const* wpack,
+                   const float* const* epi, const float* dense_w, const float* dense_b, int E, void* workspace,
+                   float* emb, int precision, void* stream) {
+  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters, first_pool);
   if (rc) return rc;
-  return encoder_fwd_impl(x, N, L, filters, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
+  return encoder_fwd_impl(x, N, L, filters, first_pool, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
                           (cudaStream_t)stream, 1, 0, nullptr, nullptr);
 }
 
@@ -338,24 +340,24 @@ int vm_preprocess_stats(const float* x, int N, int T, int downsampling, int G, f
 }
 
 int vm_encoder_fwd_raw(const float* x, int N, int T, int downsampling, int whiten_groups, float rms, int filters,
-                       const void* const* wpack, const float* const* epi, const float* dense_w, const float* dense_b,
-                       int E, void* workspace, float* emb, int precision, void* stream) {
+                       int first_pool, const void* const* wpack, const float* const* epi, const float* dense_w,
+                       const float* dense_b, int E, void* workspace, float* emb, int precision, void* stream) {
   if (downsampling <= 0 || T <= 0) return set_error(VM_ERR_SHAPE, "encoder_raw: bad downsampling / length");
   const int L = (T + downsampling - 1) / downsampling;  // numpy x[:, ::d] keeps ceil(T / d) samples
-  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters);
+  int rc = encoder_args_ok(x, wpack, epi, workspace, emb, N, L, filters, first_pool);
   if (rc) return rc;
   const float* mean = nullptr;
   const float* scale = nullptr;
   if (whiten_groups > 0) {
     if (N % whiten_groups != 0) return set_error(VM_ERR_SHAPE, "encoder_raw: N must be a multiple of whiten_groups");
-    float* m = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan_encoder(N, L, filters).total);
+    float* m = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plan_encoder(N, L, filters, first_pool).total);
     float* sc = m + N;
     if ((rc = launch_preprocess_stats(x, N, T, downsampling, whiten_groups, rms, m, sc, (cudaStream_t)stream)))
       return rc;
     mean = m;
     scale = sc;
   }
-  return encoder_fwd_impl(x, N, L, filters, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
+  return encoder_fwd_impl(x, N, L, filters, first_pool, wpack, epi, dense_w, dense_b, E, workspace, emb, precision,
                           (cudaStream_t)stream, downsampling, T, mean, scale);
 }
 

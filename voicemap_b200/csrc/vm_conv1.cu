@@ -167,14 +167,23 @@ __device__ __forceinline__ void toeplitz_block_store(float (&v)[15], uint32_t ds
   }
 }
 
-// 32 accumulator columns of one channel -> 8 pooled outputs (MaxPool 4) -> bias/ReLU/BN -> fp16 (hi, lo) -> staging
-__device__ __forceinline__ void pool4_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32],
-                                                      uint32_t sh, uint32_t sl, int nplanes) {
+// 32 accumulator columns of one channel -> 32 / kPool pooled outputs (MaxPool kPool) -> bias/ReLU/BN -> fp16 (hi, lo)
+// -> staging rows sh/sl + j * 128.  Both clamp forms are evaluated and one is selected: measured faster than
+// branching on no_hi inside the pipelined loop (profiles/r01_conv1_epilogue_ab.log: 0.097 vs 0.111 ms per launch).
+template <int kPool>
+__device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32], uint32_t sh,
+                                              uint32_t sl, int nplanes) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
-    const float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-    const float y = no_hi ? apply_epi_pool4<false>(ep, v0, v1, v2, v3) : apply_epi_pool4<true>(ep, v0, v1, v2, v3);
+  for (int j = 0; j < 32 / kPool; ++j) {
+    float y;
+    if (kPool == 4) {
+      const float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
+      const float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
+      y = no_hi ? apply_epi_pool4<false>(ep, v0, v1, v2, v3) : apply_epi_pool4<true>(ep, v0, v1, v2, v3);
+    } else {
+      const float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
+      y = no_hi ? apply_epi_pool2<false>(ep, v0, v1) : apply_epi_pool2<true>(ep, v0, v1);
+    }
     __half h, l;
     split_f32(y, h, l);
     sts_u16(sh + j * 128, h);
@@ -182,6 +191,7 @@ __device__ __forceinline__ void pool4_epilogue(const float4& ep, bool no_hi, con
   }
 }
 
+template <int kPool>
 __global__ void __launch_bounds__(c1::kThreads, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol,
              const Conv1Params p) {
@@ -358,52 +368,59 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
         } else {
           const uint32_t st_h = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (ch & 63) * 2;
           const uint32_t st_l = st_h + 2 * kOutBoxBytes;
-          // warp 0 of the group waits for (a) this group's previous TMA store to have drained the staging buffer
-          // and (b) the accumulator; the other seven warps block in the named barrier instead of spinning
-          if (wg == 0) {
-            if (lane == 0) tma_store_wait_read<0>();
-            mbar_wait(&bars->tfull[buf], it & 1);
-          }
-          named_bar_sync(bar_id, 256);
-          tc_fence_after_sync();
           const bool no_hi = epi_no_upper_clamp(ep);
-          // software-pipelined TMEM reads: the load of the next 32 columns is in flight while these are processed
-          const int g0 = chalf * (kTileN / 64);
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32_issue(taddr + g0 * 32, ra);
-          // Both clamp forms are evaluated and one is selected (pool4_epilogue): measured faster than branching
-          // on no_hi per 32 columns or per tile, because branches inside the pipelined loop serialise the TMEM
-          // loads against the arithmetic (profiles/r01_conv1_epilogue_ab.log: 0.097 vs 0.111 ms per launch).
-          const auto emit = [&](const uint32_t (&r)[32], int g) {
-            pool4_epilogue(ep, no_hi, r, st_h + g * 8 * 128, st_l + g * 8 * 128, nplanes);
-          };
-#pragma unroll
-          for (int gg = 0; gg < kTileN / 64; gg += 2) {
-            tmem_ld_wait(ra);
-            tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
-            emit(ra, g0 + gg);
-            tmem_ld_wait(rb);
-            if (gg + 2 < kTileN / 64) {
-              tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
-            } else {  // all TMEM reads of this accumulator are done
-              tc_fence_before_sync();
-              mbar_arrive(&bars->tempty[buf]);
+          // The staging buffer holds 64 pooled positions: MaxPool 4 stages the whole tile in one pass, MaxPool 2
+          // (first pool of the older reference architecture) takes two passes of 128 columns.
+          constexpr int kPasses = 4 / kPool;
+          constexpr int kLoads = (kTileN / 64) / kPasses;   // 32-column TMEM loads per warp and pass
+          constexpr int kOutPerLoad = 32 / kPool;
+#pragma unroll 1
+          for (int pass = 0; pass < kPasses; ++pass) {
+            // warp 0 of the group waits for (a) this group's previous TMA store to have drained the staging buffer
+            // and (b) the accumulator; the other seven warps block in the named barrier instead of spinning
+            if (wg == 0) {
+              if (lane == 0) tma_store_wait_read<0>();
+              if (pass == 0) mbar_wait(&bars->tfull[buf], it & 1);
             }
-            emit(rb, g0 + gg + 1);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(bar_id, 256);
-          if (leader) {
-            const int pos = p0 >> 2;
+            named_bar_sync(bar_id, 256);
+            tc_fence_after_sync();
+            // software-pipelined TMEM reads: the next 32 columns are in flight while these are processed
+            const int g0 = pass * 2 * kLoads + chalf * kLoads;   // first 32-column group of this warp
+            const uint32_t row0 = chalf * kLoads * kOutPerLoad * 128;
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32_issue(taddr + g0 * 32, ra);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int c0 = slab * kTileM + half * 64;
-              if (c0 < p.cout) {
-                tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
-                if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+            for (int gg = 0; gg < kLoads; gg += 2) {
+              tmem_ld_wait(ra);
+              tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
+              pool_epilogue<kPool>(ep, no_hi, ra, st_h + row0 + gg * kOutPerLoad * 128,
+                                   st_l + row0 + gg * kOutPerLoad * 128, nplanes);
+              tmem_ld_wait(rb);
+              if (gg + 2 < kLoads) {
+                tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
+              } else if (pass == kPasses - 1) {  // all TMEM reads of this accumulator are done
+                tc_fence_before_sync();
+                mbar_arrive(&bars->tempty[buf]);
               }
+              pool_epilogue<kPool>(ep, no_hi, rb, st_h + row0 + (gg + 1) * kOutPerLoad * 128,
+                                   st_l + row0 + (gg + 1) * kOutPerLoad * 128, nplanes);
             }
-            tma_store_commit();
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 256);
+            if (leader) {
+              const int pos = p0 / kPool + pass * 64;
+              if (pos < p.lout) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int c0 = slab * kTileM + half * 64;
+                  if (c0 < p.cout) {
+                    tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+                    if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+                  }
+                }
+              }
+              tma_store_commit();
+            }
           }
         }
       }
@@ -424,9 +441,10 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
                  __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
                  cudaStream_t stream, int x_stride, long long x_clip_stride, const float* pre_mean,
-                 const float* pre_scale) {
+                 const float* pre_scale, int pool) {
   using namespace c1;
-  if (N <= 0 || L < 4) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= 4");
+  if (pool != 2 && pool != 4) return set_error(VM_ERR_UNSUPPORTED, "conv1: first MaxPool1D size must be 2 or 4");
+  if (N <= 0 || L < pool) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= pool size");
   if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
   if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv1: products must be 1 or 3");
   const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
@@ -437,7 +455,7 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   p.x_stride = x_stride > 0 ? x_stride : 1;
   p.x_clip_stride = x_clip_stride > 0 ? x_clip_stride : (long long)L * p.x_stride;
   p.pre_mean = pre_mean; p.pre_scale = pre_scale; p.cout_pad = cout_pad; p.nslab = nslab;
-  p.lout = L / 4;
+  p.lout = L / pool;
   p.nptile = (L + kTileN - 1) / kTileN;
   p.products = products;
   p.wpack = reinterpret_cast<const uint4*>(wpack);
@@ -466,12 +484,13 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
       return rc;
   }
   const int smem = smem_bytes(nslab, p.nstages);
-  cudaError_t e = cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const auto kern = (pool == 2) ? conv1_kernel<2> : conv1_kernel<4>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return set_cuda_error(e, "conv1: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > ntiles) grid = ntiles;
-  conv1_kernel<<<grid, kThreads, smem, stream>>>(oh, ol, p);
+  kern<<<grid, kThreads, smem, stream>>>(oh, ol, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv1: launch");
   return VM_OK;

@@ -44,7 +44,7 @@ struct Conv1Params {
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
                  __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
                  cudaStream_t stream, int x_stride = 1, long long x_clip_stride = 0,
-                 const float* pre_mean = nullptr, const float* pre_scale = nullptr);
+                 const float* pre_mean = nullptr, const float* pre_scale = nullptr, int pool = 4);
 int launch_preprocess_stats(const float* x, int N, int T, int stride, int G, float rms, float* mean, float* scale,
                             cudaStream_t stream);
 

@@ -49,7 +49,12 @@ def encoder_param_shapes(filters, embedding_dimension):
 class EncoderEngine:
     """get_baseline_convolutional_encoder (voicemap/models.py:6-41) in eval mode on one B200."""
 
-    def __init__(self, filters, embedding_dimension, device=None, precision=PRECISION_FP32_GRADE):
+    def __init__(self, filters, embedding_dimension, device=None, precision=PRECISION_FP32_GRADE, first_pool=4):
+        """first_pool: size of the first MaxPool1D -- 4 (voicemap/models.py:19) or 2 (the older architecture of the
+        checkpoint the reference ships under models/n_seconds/)."""
+        if first_pool not in (2, 4):
+            raise ValueError("first_pool must be 4 (voicemap/models.py:19) or 2 (older checkpoints)")
+        self.first_pool = int(first_pool)
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.VoicemapB200Error("voicemap_b200 needs a CUDA device (no CPU fallback)")
@@ -109,10 +114,10 @@ class EncoderEngine:
     def _get_workspace(self, n, length):
         key = (n, length)
         if self._ws_key != key:
-            nbytes = self.lib.vm_encoder_workspace_bytes(n, length, self.filters)
+            nbytes = self.lib.vm_encoder_workspace_bytes(n, length, self.filters, self.first_pool)
             nbytes += self.lib.vm_preprocess_scratch_bytes(n) if nbytes else 0
             if nbytes == 0:
-                raise ValueError(f"input of shape ({n}, {length}) is too short for the encoder (L >= 32)")
+                raise ValueError(f"input of shape ({n}, {length}) is too short for the encoder (L >= {8 * self.first_pool})")
             if self._workspace is None or self._workspace.numel() < nbytes + 1024:   # grow-only
                 self._workspace = None
                 self._workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
@@ -139,7 +144,7 @@ class EncoderEngine:
             ws = self._get_workspace(n, length)
             wp = (C.c_void_p * 4)(*[t.data_ptr() for t in self.wpack])
             ep = (C.c_void_p * 4)(*[t.data_ptr() for t in self.epi])
-            rc = self.lib.vm_encoder_fwd(_ptr(x), n, length, self.filters, wp, ep, _ptr(self.params["dense_kernel"]),
+            rc = self.lib.vm_encoder_fwd(_ptr(x), n, length, self.filters, self.first_pool, wp, ep, _ptr(self.params["dense_kernel"]),
                                          _ptr(self.params["dense_bias"]), self.embedding_dimension, ws, _ptr(out),
                                          self.precision, _stream())
         _lib.check(rc, "vm_encoder_fwd")
@@ -164,9 +169,9 @@ class EncoderEngine:
             wp = (C.c_void_p * 4)(*[w.data_ptr() for w in self.wpack])
             ep = (C.c_void_p * 4)(*[e.data_ptr() for e in self.epi])
             rc = self.lib.vm_encoder_fwd_raw(_ptr(x), n, t, int(downsampling), int(whiten_groups), C.c_float(rms),
-                                             self.filters, wp, ep, _ptr(self.params["dense_kernel"]),
-                                             _ptr(self.params["dense_bias"]), self.embedding_dimension, ws, _ptr(out),
-                                             self.precision, _stream())
+                                             self.filters, self.first_pool, wp, ep,
+                                             _ptr(self.params["dense_kernel"]), _ptr(self.params["dense_bias"]),
+                                             self.embedding_dimension, ws, _ptr(out), self.precision, _stream())
         _lib.check(rc, "vm_encoder_fwd_raw")
         return out
 
@@ -183,20 +188,20 @@ class EncoderEngine:
         return x
 
     def block1(self, x, out=None):
-        """x (N, L) fp32 -> planes (N, L//4, f).  ``out`` = (hi, lo) reuses caller-owned planes."""
+        """x (N, L) fp32 -> planes (N, L//first_pool, f).  ``out`` = (hi, lo) reuses caller-owned planes."""
         if not self._packed:
             self.pack()
         n, length = x.shape
         f = self.channels[0]
         if out is not None:
             hi, lo = out
-            assert hi.shape == (n, length // 4, f) and lo.shape == hi.shape and hi.dtype == torch.float16
+            assert hi.shape == (n, length // self.first_pool, f) and lo.shape == hi.shape and hi.dtype == torch.float16
         else:
-            hi = torch.empty((n, length // 4, f), dtype=torch.float16, device=self.device)
+            hi = torch.empty((n, length // self.first_pool, f), dtype=torch.float16, device=self.device)
             lo = torch.empty_like(hi)
-        rc = self.lib.vm_conv1_relu_bn_pool4_fwd(_ptr(x), n, length, f, _ptr(self.wpack[0]), _ptr(self.epi[0]),
-                                                 _ptr(hi), _ptr(lo), self.precision, _stream())
-        _lib.check(rc, "vm_conv1_relu_bn_pool4_fwd")
+        rc = self.lib.vm_conv1_relu_bn_pool_fwd(_ptr(x), n, length, f, self.first_pool, _ptr(self.wpack[0]),
+                                                _ptr(self.epi[0]), _ptr(hi), _ptr(lo), self.precision, _stream())
+        _lib.check(rc, "vm_conv1_relu_bn_pool_fwd")
         return hi, lo
 
     def block3(self, index, in_hi, in_lo, gmax=False, out=None):

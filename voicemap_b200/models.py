@@ -37,6 +37,16 @@ def _pipeline_plan(n, pinned=True):
     return plan
 
 
+def _glorot_uniform(shape, rng):
+    if len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rec = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rec, shape[-1] * rec
+    limit = np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
 class LayerInfo:
     """Entry of ``model.layers`` (name / class / config / weight names), enough for summary() and indexing."""
 
@@ -108,7 +118,13 @@ class EncoderModel(_ModelBase):
     """Sequential returned by get_baseline_convolutional_encoder (voicemap/models.py:6-41), optionally extended
     with a classification head through ``add(Dense(n, activation='softmax'))``."""
 
-    def __init__(self, filters, embedding_dimension, input_shape=None, dropout=0.05, seed=None, name="sequential_1"):
+    def __init__(self, filters, embedding_dimension, input_shape=None, dropout=0.05, seed=None, name="sequential_1",
+                 first_pool=4):
+        """first_pool = 4 is voicemap/models.py:19; first_pool = 2 rebuilds the older architecture of the checkpoint
+        shipped under models/n_seconds/ (four MaxPooling1D(2)), which ``load_model`` selects itself."""
+        if first_pool not in (2, 4):
+            raise ValueError("first_pool must be 4 (voicemap/models.py:19) or 2 (older checkpoints)")
+        self.first_pool = int(first_pool)
         self.name = name
         self.filters = int(filters)
         self.embedding_dimension = int(embedding_dimension)
@@ -120,7 +136,7 @@ class EncoderModel(_ModelBase):
         self.weights = OrderedDict()
         self.layers = []
         cin = 1
-        for i, (k, mult, pool) in enumerate(((32, 1, 4), (3, 2, 2), (3, 3, 2), (3, 4, 2)), start=1):
+        for i, (k, mult, pool) in enumerate(((32, 1, self.first_pool), (3, 2, 2), (3, 3, 2), (3, 4, 2)), start=1):
             cout = mult * f
             self.weights[f"conv{i}_kernel"] = _glorot_uniform((k, cin, cout), rng)
             self.weights[f"conv{i}_bias"] = np.zeros((cout,), np.float32)
@@ -203,10 +219,11 @@ class EncoderModel(_ModelBase):
 
     def get_config(self):
         return dict(kind="encoder", filters=self.filters, embedding_dimension=self.embedding_dimension,
-                    input_shape=self.input_shape, dropout=self.dropout, head=self._head)
+                    input_shape=self.input_shape, dropout=self.dropout, head=self._head, first_pool=self.first_pool)
 
     def _clone(self):
-        m = EncoderModel(self.filters, self.embedding_dimension, self.input_shape, self.dropout)
+        m = EncoderModel(self.filters, self.embedding_dimension, self.input_shape, self.dropout,
+                         first_pool=self.first_pool)
         if self._head is not None:
             m.add(Dense(self._head["units"], activation=self._head["activation"]))
         return m
@@ -215,7 +232,8 @@ class EncoderModel(_ModelBase):
     def _get_engine(self):
         from .engine import EncoderEngine
         if self._engine is None:
-            self._engine = EncoderEngine(self.filters, self.embedding_dimension, precision=self.precision)
+            self._engine = EncoderEngine(self.filters, self.embedding_dimension, precision=self.precision,
+                                         first_pool=self.first_pool)
             self._engine_dirty = True
         if self._engine_dirty:
             self._engine.set_weights(self.weights)
@@ -417,10 +435,11 @@ class SiameseModel(_ModelBase):
 # --------------------------------------------------------------------------------------------------------
 # the reference's public builders
 # --------------------------------------------------------------------------------------------------------
-def get_baseline_convolutional_encoder(filters, embedding_dimension, input_shape=None, dropout=0.05):
+def get_baseline_convolutional_encoder(filters, embedding_dimension, input_shape=None, dropout=0.05, first_pool=4):
     """voicemap/models.py:6-41: 4 x [Conv1D+ReLU -> BatchNorm -> SpatialDropout1D -> MaxPool] ->
-    GlobalMaxPool1D -> Dense(embedding_dimension)."""
-    return EncoderModel(filters, embedding_dimension, input_shape=input_shape, dropout=dropout)
+    GlobalMaxPool1D -> Dense(embedding_dimension).  ``first_pool`` (not in the reference signature; default = the
+    reference's 4) selects the older architecture of the shipped checkpoints when set to 2."""
+    return EncoderModel(filters, embedding_dimension, input_shape=input_shape, dropout=dropout, first_pool=first_pool)
 
 
 def build_siamese_net(encoder, input_shape, distance_metric='uniform_euclidean'):
@@ -473,11 +492,12 @@ def _load_keras_hdf5(filepath):
                 walk(v)
 
     walk(cfg)
-    if pools and pools[0] != (4,):
-        warnings.warn("checkpoint was trained with an older voicemap architecture (first MaxPool1D 2 instead of 4, "
-                      "SURVEY.md F9); weights are loaded into the current architecture (voicemap/models.py:19)")
+    first_pool = int(pools[0][0]) if pools and pools[0] else 4
+    if first_pool not in (2, 4) or any(p != (2,) for p in pools[1:4]):
+        raise ValueError(f"checkpoint pooling sizes {pools} are not a voicemap encoder (4,2,2,2 or 2,2,2,2)")
     is_siamese = any(k.startswith("dense_2/") for k in flat)
-    enc = EncoderModel(filters, emb, dropout=0.05)
+    # older checkpoints (models/n_seconds/*.hdf5) were trained with a first MaxPool1D of 2
+    enc = EncoderModel(filters, emb, dropout=0.05, first_pool=first_pool)
     enc.set_named_weights(named)
     if not is_siamese:
         return enc
@@ -505,12 +525,14 @@ def load_model(filepath, custom_objects=None):
         cfg = json.loads(bytes(z["config"]).decode())
         weights = [z[f"w{i}"] for i in range(len(z.files) - 1)]
     if cfg["kind"] == "encoder":
-        m = EncoderModel(cfg["filters"], cfg["embedding_dimension"], cfg["input_shape"], cfg["dropout"])
+        m = EncoderModel(cfg["filters"], cfg["embedding_dimension"], cfg["input_shape"], cfg["dropout"],
+                         first_pool=cfg.get("first_pool", 4))
         if cfg.get("head"):
             m.add(Dense(cfg["head"]["units"], activation=cfg["head"]["activation"]))
     else:
         e = cfg["encoder"]
-        enc = EncoderModel(e["filters"], e["embedding_dimension"], e["input_shape"], e["dropout"])
+        enc = EncoderModel(e["filters"], e["embedding_dimension"], e["input_shape"], e["dropout"],
+                           first_pool=e.get("first_pool", 4))
         m = SiameseModel(enc, cfg["input_shape"], cfg["distance_metric"])
     m.set_weights(weights)
     return m

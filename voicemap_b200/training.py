@@ -63,6 +63,7 @@ class TrainEngine:
         self.device = self.eng.device
         self.filters, self.emb = enc.filters, enc.embedding_dimension
         self.channels = [self.filters * m for m in (1, 2, 3, 4)]
+        self.pools = (enc.first_pool,) + POOLS[1:]
         self.dropout = float(enc.dropout)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
@@ -122,7 +123,7 @@ class TrainEngine:
             return
         dev, f32, f16 = self.device, torch.float32, torch.float16
         ls = [length]
-        for p in POOLS:
+        for p in self.pools:
             ls.append(ls[-1] // p)
         if ls[4] < 1:
             raise ValueError("clips are too short for the encoder")
@@ -213,7 +214,7 @@ class TrainEngine:
                                           _ptr(self.bnc[b]), _ptr(self.red), st)
             _check(rc, "vm_bn_stats_finalize")
             if b < 3:
-                rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, POOLS[b], _ptr(self.bnc[b]),
+                rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
                                         _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
                                         _ptr(self.XB[b][0]), _ptr(self.XB[b][1]), st)
                 _check(rc, "vm_bn_pool_fwd")
@@ -244,7 +245,7 @@ class TrainEngine:
                 dy, dg, am = None, self.d_gmax, self.argmax
             else:
                 dy, dg, am = self.dX, None, None
-            rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, POOLS[b],
+            rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, self.pools[b],
                                _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
                                _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
                                _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
