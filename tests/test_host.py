@@ -277,3 +277,91 @@ def test_first_pool_argument_is_validated():
     assert get_baseline_convolutional_encoder(16, 8, first_pool=2).first_pool == 2
     with pytest.raises(ValueError):
         get_baseline_convolutional_encoder(16, 8, first_pool=3)
+
+
+def _randomize(model, seed):
+    rng = np.random.default_rng(seed)
+    ws = [rng.normal(size=w.shape).astype(np.float32) for w in model.get_weights()]
+    model.set_weights(ws)
+    return ws
+
+
+def test_hdf5_checkpoints_round_trip_all_model_kinds(tmp_path):
+    """model.save('*.hdf5') writes the Keras 2.2.x layout (root attrs, /model_weights/<layer>/<weight>); load_model
+    restores architecture (first pool, dropout, head kind, input shape) and every weight bit for bit."""
+    from voicemap_b200.keras_compat import Adam, Dense
+    from voicemap_b200.keras_hdf5 import KerasH5, load_keras_weights
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder, load_model
+    sia = build_siamese_net(get_baseline_convolutional_encoder(16, 8, dropout=0.1, first_pool=2), (4000, 1), "weighted_l1")
+    sia.compile(loss="binary_crossentropy", optimizer=Adam(clipnorm=1.), metrics=["accuracy"])
+    ws = _randomize(sia, 1)
+    path = str(tmp_path / "siamese.hdf5")
+    sia.save(path)
+    m = load_model(path)
+    assert m.distance_metric == "weighted_l1" and m.encoder.first_pool == 2 and m.encoder.dropout == 0.1
+    assert tuple(m.input_shape) == (4000, 1)
+    assert all(np.array_equal(a, b) for a, b in zip(ws, m.get_weights()))
+    # same group / attribute structure as the reference's own checkpoint (SURVEY.md 8(c))
+    cfg, layers = load_keras_weights(path)
+    assert [n for n, _ in layers] == ["input_1", "input_2", "sequential_1", "subtract_1", "lambda_1", "dense_2"]
+    names = [w for w, _ in layers[2][1]]
+    assert names[0] == "sequential_1/conv1d_1/kernel:0" and names[-1] == "sequential_1/batch_normalization_4/moving_variance:0"
+    assert names.index("sequential_1/dense_1/bias:0") < names.index("sequential_1/batch_normalization_1/moving_mean:0")
+    f = KerasH5(path)
+    assert f.attr("/", "keras_version") == "2.2.2" and f.attr("/", "backend") == "tensorflow"
+    assert '"clipnorm": 1.0' in f.attr("/", "training_config")
+    assert cfg["config"]["layers"][2]["config"][3]["config"]["pool_size"] == [2]
+
+    clf = get_baseline_convolutional_encoder(16, 8, (12000, 1))
+    clf.add(Dense(10, activation="softmax"))
+    ws = _randomize(clf, 2)
+    path = str(tmp_path / "classifier.h5")
+    clf.save(path)
+    m = load_model(path)
+    assert m._head == {"units": 10, "activation": "softmax"} and m.input_shape == (12000, 1) and m.first_pool == 4
+    assert all(np.array_equal(a, b) for a, b in zip(ws, m.get_weights()))
+
+    sia2 = build_siamese_net(get_baseline_convolutional_encoder(16, 8), (12000, 1))
+    ws = _randomize(sia2, 3)
+    path = str(tmp_path / "euclid.hdf5")
+    sia2.save(path)
+    m = load_model(path)
+    assert m.distance_metric == "uniform_euclidean"
+    assert all(np.array_equal(a, b) for a, b in zip(ws, m.get_weights()))
+    # other suffixes keep the npz container
+    sia2.save(str(tmp_path / "model.npz"))
+    assert not open(tmp_path / "model.npz", "rb").read(8).startswith(b"\x89HDF")
+
+
+def test_hdf5_writer_structure(tmp_path):
+    """Byte-level invariants libhdf5 relies on: superblock fields, end-of-file address, 8-byte alignment of every
+    object, symbol-table entries sorted by name, and the float32 datatype message identical to the one in the
+    reference's checkpoint."""
+    import struct
+    from voicemap_b200.keras_hdf5 import UNDEF, KerasH5, save_keras_weights
+    layers = [("zeta", [("zeta/kernel:0", np.arange(6, dtype=np.float32).reshape(2, 3)), ("zeta/bias:0", np.zeros(3, np.float32))]),
+              ("alpha", []), ("mid", [("mid/w:0", np.ones((1,), np.float32))])]
+    path = str(tmp_path / "w.h5")
+    save_keras_weights(path, {"class_name": "Sequential", "config": []}, layers)
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89HDF\r\n\x1a\n" and b[8:16] == bytes([0, 0, 0, 0, 0, 8, 8, 0])
+    base, free, eof, driver = struct.unpack_from("<QQQQ", b, 24)
+    assert (base, free, eof, driver) == (0, UNDEF, len(b), UNDEF) and len(b) % 8 == 0
+    f = KerasH5(path)
+    seen = []
+
+    def walk(addr):
+        assert addr % 8 == 0 and b[addr] == 1          # version-1 object header, aligned
+        kids = f.children(addr)
+        seen.append(list(kids))
+        for child in kids.values():
+            walk(child)
+    walk(f.root)
+    assert seen[0] == ["model_weights"] and seen[1] == ["alpha", "mid", "zeta"]      # strcmp order inside the node
+    assert f.attr("/model_weights", "layer_names") == ["zeta", "alpha", "mid"]       # attribute keeps model order
+    assert f.attr("/model_weights/alpha", "weight_names") == []
+    assert np.array_equal(f.dataset("/model_weights/zeta/zeta/kernel:0"), np.arange(6, dtype=np.float32).reshape(2, 3))
+    ref_dtype = bytes.fromhex("11201f000400000000002000170800177f000000")   # float32 message of the reference's file
+    for mtype, data in f._messages(f.resolve("/model_weights/mid/mid/w:0")):
+        if mtype == 0x03:
+            assert data[:20] == ref_dtype

@@ -50,6 +50,14 @@ class Adam:
         self.clipnorm = None if clipnorm is None else float(clipnorm)
         self.iterations = 0
 
+    def get_config(self):
+        """keras optimizer_config of a saved model (training_config attribute)."""
+        cfg = dict(lr=self.lr, beta_1=self.beta_1, beta_2=self.beta_2, decay=self.decay, epsilon=self.epsilon,
+                   amsgrad=False)
+        if self.clipnorm is not None:
+            cfg["clipnorm"] = self.clipnorm
+        return cfg
+
 
 # ---------------------------------------------------------------------------------------------- utils
 class Sequence:
@@ -166,8 +174,8 @@ def _monitor_op(mode, monitor):
 
 class ModelCheckpoint(Callback):
     """keras.callbacks.ModelCheckpoint(filepath, monitor, mode, save_best_only, verbose)
-    (experiments/train_siamese.py:81-87).  Saves through ``model.save`` (npz container; HDF5 interchange is a
-    later row of SURVEY.md 8(f))."""
+    (experiments/train_siamese.py:81-87).  Saves through ``model.save``: a Keras-layout HDF5 file for ``*.hdf5`` /
+    ``*.h5`` paths (what the reference's scripts name their checkpoints), an npz container otherwise."""
 
     def __init__(self, filepath, monitor="val_loss", verbose=0, save_best_only=False, save_weights_only=False,
                  mode="auto", period=1):

@@ -221,3 +221,156 @@ def load_keras_weights(path):
         wnames = f.attr(f"/model_weights/{lname}", "weight_names")
         layers.append((lname, [(w, f.dataset(f"/model_weights/{lname}/{w}")) for w in wnames]))
     return cfg, layers
+
+
+# ======================================================================================================================
+# Writer: the same subset of HDF5 the reader understands, laid out the way libhdf5 1.8/1.10 writes a Keras 2.2.x
+# ``model.save`` file (superblock v0, old-style groups = v1 B-tree + local heap + one symbol-table node, version-1 object
+# headers in a single chunk, contiguous little-endian float32 datasets, fixed-length null-padded string attributes).
+# Structure of a checkpoint (keras/engine/saving.py of Keras 2.2.2, the version the reference pins):
+#   /            attrs keras_version, backend, model_config (JSON), training_config (JSON, optional)
+#   /model_weights            attrs layer_names [..], backend, keras_version
+#   /model_weights/<layer>    attr  weight_names ['conv1d_1/kernel:0', ...]; datasets at <layer>/<weight_name>
+# No libhdf5 / h5py exists in the build image: files are verified by reading them back with ``KerasH5`` (which was
+# written against, and is tested on, a real Keras file) and by structural checks in tests/test_host.py.
+# ======================================================================================================================
+class _Group:
+    def __init__(self):
+        self.attrs = []        # (name, value): str -> scalar string, list[str] -> 1-D string array
+        self.children = {}     # name -> _Group | np.ndarray
+
+
+def _pad8(b):
+    return b + b"\x00" * (-len(b) % 8)
+
+
+def _message(mtype, payload):
+    payload = _pad8(payload)
+    return struct.pack("<HHB3x", mtype, len(payload), 0) + payload
+
+
+def _attr_message(name, value):
+    nm = name.encode() + b"\x00"
+    if isinstance(value, (list, tuple)):
+        items = [v.encode() for v in value]
+        size = max([len(i) for i in items] + [1])
+        space = struct.pack("<BBB5xQQ", 1, 1, 1, len(items), len(items))   # rank 1, max dims present
+        data = b"".join(i.ljust(size, b"\x00") for i in items)
+    else:
+        raw = value.encode()
+        size = max(len(raw), 1)
+        space = struct.pack("<BBB5x", 1, 0, 0)                             # scalar
+        data = raw.ljust(size, b"\x00")
+    dtype = struct.pack("<BBBBI", 0x13, 0x01, 0, 0, size)                  # class 3 string v1, null-padded, ASCII
+    body = struct.pack("<BBHHH", 1, 0, len(nm), len(dtype), len(space)) + _pad8(nm) + _pad8(dtype) + _pad8(space) + data
+    if len(body) > 0xFFF0:
+        raise ValueError(f"attribute {name!r} does not fit a version-1 object-header message (64 KB)")
+    return _message(0x0C, body)
+
+
+class _H5Writer:
+    INTERNAL_K = 16
+
+    def __init__(self, root):
+        self.buf = bytearray(96)            # superblock is written last
+        widest = [1]
+
+        def scan(g):
+            widest[0] = max(widest[0], len(g.children))
+            for c in g.children.values():
+                if isinstance(c, _Group):
+                    scan(c)
+        scan(root)
+        self.leaf_k = max(4, (widest[0] + 1) // 2)   # one symbol-table node (2K entries) holds any group of this file
+        hdr, btree, heap = self._group(root)
+        eof = len(self.buf)
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.leaf_k, self.INTERNAL_K, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQII", 0, hdr, 1, 0) + struct.pack("<QQ", btree, heap)   # root symbol-table entry
+        assert len(sb) == 96
+        self.buf[:96] = sb
+
+    def _alloc(self, data):
+        assert len(self.buf) % 8 == 0
+        addr = len(self.buf)
+        self.buf += _pad8(bytes(data))
+        return addr
+
+    def _dataset(self, arr):
+        arr = np.ascontiguousarray(arr, dtype="<f4")
+        data_addr = self._alloc(arr.tobytes()) if arr.size else UNDEF
+        dims = arr.shape
+        space = struct.pack("<BBB5x", 1, len(dims), 1 if dims else 0)
+        space += b"".join(struct.pack("<Q", d) for d in dims) * (2 if dims else 0)   # dims then max dims
+        # IEEE little-endian float32: class 1 v1; bit offset 0, precision 32, exponent at 23 (8 bits), mantissa 23 bits
+        dtype = struct.pack("<BBBBI", 0x11, 0x20, 0x1F, 0x00, 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+        fill = struct.pack("<BBBBI", 2, 2, 2, 1, 0)            # v2: late allocation, fill written if set, size 0
+        layout = struct.pack("<BBQQ", 3, 1, data_addr, arr.nbytes)
+        msgs = _message(0x01, space) + _message(0x03, dtype) + _message(0x05, fill) + _message(0x08, layout)
+        return self._alloc(struct.pack("<BBHII4x", 1, 0, 4, 1, len(msgs)) + msgs)
+
+    def _group(self, g):
+        names = sorted(g.children, key=lambda s: s.encode())
+        entries = []
+        for name in names:
+            child = g.children[name]
+            if isinstance(child, _Group):
+                entries.append((name, *self._group(child)))
+            else:
+                entries.append((name, self._dataset(child), None, None))
+        # local heap: "" at offset 0, the link names, one trailing free block {next = 1 (none), size}
+        seg = bytearray(8)
+        offsets = []
+        for name in names:
+            offsets.append(len(seg))
+            seg += _pad8(name.encode() + b"\x00")
+        free_off = len(seg)
+        seg += struct.pack("<QQ", 1, 32) + bytes(16)
+        seg_addr = self._alloc(seg)
+        heap = self._alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(seg), free_off, seg_addr))
+        snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(names)))
+        for (name, hdr, bt, hp), off in zip(entries, offsets):
+            if bt is None:
+                snod += struct.pack("<QQII16x", off, hdr, 0, 0)
+            else:
+                snod += struct.pack("<QQIIQQ", off, hdr, 1, 0, bt, hp)
+        snod += bytes(8 + 2 * self.leaf_k * 40 - len(snod))
+        snod_addr = self._alloc(snod)
+        tree = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if names else 0, UNDEF, UNDEF))
+        if names:
+            tree += struct.pack("<QQQ", 0, snod_addr, offsets[-1])     # key0 = "", child, key1 = largest name
+        tree += bytes(24 + (2 * self.INTERNAL_K + 1) * 8 + 2 * self.INTERNAL_K * 8 - len(tree))
+        btree = self._alloc(tree)
+        msgs = _message(0x11, struct.pack("<QQ", btree, heap))
+        for name, value in g.attrs:
+            msgs += _attr_message(name, value)
+        nmsg = 1 + len(g.attrs)
+        hdr = self._alloc(struct.pack("<BBHII4x", 1, 0, nmsg, 1, len(msgs)) + msgs)
+        return hdr, btree, heap
+
+
+def save_keras_weights(path, model_config, layers, training_config=None, keras_version="2.2.2", backend="tensorflow"):
+    """Write a Keras-2.2.x-style full-model checkpoint.  ``model_config`` / ``training_config``: JSON-serialisable
+    dicts; ``layers``: [(layer name, [(weight name such as 'conv1d_1/kernel:0', ndarray), ...]), ...] in
+    ``model.layers`` order (weight-less layers carry an empty list), i.e. what ``load_keras_weights`` returns."""
+    import json
+    root = _Group()
+    root.attrs = [("keras_version", keras_version), ("backend", backend), ("model_config", json.dumps(model_config))]
+    if training_config is not None:
+        root.attrs.append(("training_config", json.dumps(training_config)))
+    mw = _Group()
+    mw.attrs = [("layer_names", [n for n, _ in layers]), ("backend", backend), ("keras_version", keras_version)]
+    for lname, weights in layers:
+        lg = _Group()
+        lg.attrs = [("weight_names", [w for w, _ in weights])]
+        for wname, arr in weights:
+            node = lg
+            parts = wname.split("/")
+            for part in parts[:-1]:
+                node = node.children.setdefault(part, _Group())
+            node.children[parts[-1]] = np.asarray(arr)
+        mw.children[lname] = lg
+    root.children["model_weights"] = mw
+    w = _H5Writer(root)
+    with open(path, "wb") as fh:
+        fh.write(bytes(w.buf))

@@ -107,11 +107,35 @@ class _ModelBase:
         return None
 
     def save(self, filepath, overwrite=True):
-        """Full-model container (architecture json + weights).  npz, not HDF5."""
+        """model.save (keras ModelCheckpoint call site: experiments/train_siamese.py:81-87).  ``*.h5`` / ``*.hdf5``
+        paths get a Keras-2.2.x-layout HDF5 checkpoint (voicemap_b200/keras_hdf5.py: model_config, training_config,
+        /model_weights/<layer>/<weight>), any other path this package's npz container.  ``load_model`` reads both."""
+        if str(filepath).lower().endswith((".h5", ".hdf5")):
+            from .keras_hdf5 import save_keras_weights
+            training = None
+            if self.loss is not None:
+                opt = self.optimizer
+                training = dict(loss=self.loss, metrics=list(self.metrics or []), loss_weights=None,
+                                sample_weight_mode=None,
+                                optimizer_config=dict(class_name="Adam", config=opt.get_config()) if opt else None)
+            save_keras_weights(filepath, self._keras_config(), self._keras_layers(), training)
+            return
         arrays = {f"w{i}": w for i, w in enumerate(self.get_weights())}
         arrays["config"] = np.frombuffer(json.dumps(self.get_config()).encode(), dtype=np.uint8)
         with open(filepath, "wb") as fh:
             np.savez(fh, **arrays)
+
+
+_GLOROT = {"class_name": "VarianceScaling",
+           "config": {"distribution": "uniform", "scale": 1.0, "seed": None, "mode": "fan_avg"}}
+_ZEROS, _ONES = {"class_name": "Zeros", "config": {}}, {"class_name": "Ones", "config": {}}
+
+
+def _dense_config(name, units, activation):
+    return {"class_name": "Dense", "config": {
+        "name": name, "trainable": True, "units": int(units), "activation": activation, "use_bias": True,
+        "kernel_initializer": _GLOROT, "bias_initializer": _ZEROS, "kernel_regularizer": None,
+        "bias_regularizer": None, "activity_regularizer": None, "kernel_constraint": None, "bias_constraint": None}}
 
 
 class EncoderModel(_ModelBase):
@@ -227,6 +251,65 @@ class EncoderModel(_ModelBase):
         if self._head is not None:
             m.add(Dense(self._head["units"], activation=self._head["activation"]))
         return m
+
+    # ---- Keras 2.2.x serialisation (what keras/engine/saving.py stores; keys as in the reference's checkpoints)
+    def _keras_layer_configs(self):
+        shape = [None] + [int(v) if v is not None else None for v in (self.input_shape or (None, 1))]
+        out = []
+        for i, (k, mult, pool) in enumerate(((32, 1, self.first_pool), (3, 2, 2), (3, 3, 2), (3, 4, 2)), start=1):
+            conv = {"name": f"conv1d_{i}", "trainable": True, "filters": mult * self.filters, "kernel_size": [k],
+                    "strides": [1], "padding": "same", "data_format": "channels_last", "dilation_rate": [1],
+                    "activation": "relu", "use_bias": True, "kernel_initializer": _GLOROT,
+                    "bias_initializer": _ZEROS, "kernel_regularizer": None, "bias_regularizer": None,
+                    "activity_regularizer": None, "kernel_constraint": None, "bias_constraint": None}
+            if i == 1:
+                conv["batch_input_shape"] = shape
+            out.append({"class_name": "Conv1D", "config": conv})
+            out.append({"class_name": "BatchNormalization", "config": {
+                "name": f"batch_normalization_{i}", "trainable": True, "axis": -1, "momentum": 0.99, "epsilon": 0.001,
+                "center": True, "scale": True, "beta_initializer": _ZEROS, "gamma_initializer": _ONES,
+                "moving_mean_initializer": _ZEROS, "moving_variance_initializer": _ONES, "beta_regularizer": None,
+                "gamma_regularizer": None, "beta_constraint": None, "gamma_constraint": None}})
+            out.append({"class_name": "SpatialDropout1D", "config": {
+                "name": f"spatial_dropout1d_{i}", "trainable": True, "rate": self.dropout, "noise_shape": None,
+                "seed": None}})
+            out.append({"class_name": "MaxPooling1D", "config": {
+                "name": f"max_pooling1d_{i}", "trainable": True, "pool_size": [pool], "strides": [pool],
+                "padding": "valid"}})
+        out.append({"class_name": "GlobalMaxPooling1D", "config": {"name": "global_max_pooling1d_1", "trainable": True}})
+        out.append(_dense_config("dense_1", self.embedding_dimension, "linear"))
+        if self._head is not None:
+            out.append(_dense_config("dense_2", self._head["units"], self._head["activation"]))
+        return out
+
+    def _keras_config(self):
+        return {"class_name": "Sequential", "config": self._keras_layer_configs()}   # Keras 2.2.2: a plain list
+
+    _KERAS_NAMES = {"kernel": "kernel", "bias": "bias", "gamma": "gamma", "beta": "beta", "mean": "moving_mean",
+                    "var": "moving_variance"}
+
+    def _keras_weight_items(self, trainable_first=False):
+        """[(keras layer name, keras weight name, array)] in Keras order."""
+        items = []
+        for key, arr in self.weights.items():
+            blk, kind = key.rsplit("_", 1)
+            if blk.startswith("conv"):
+                layer = f"conv1d_{blk[4:]}"
+            elif blk.startswith("bn"):
+                layer = f"batch_normalization_{blk[2:]}"
+            else:
+                layer = "dense_1" if blk == "dense" else "dense_2"
+            items.append((layer, f"{layer}/{self._KERAS_NAMES[kind]}:0", arr))
+        if trainable_first:   # nested model: trainable weights, then the moving statistics
+            moving = [it for it in items if "moving_" in it[1]]
+            items = [it for it in items if "moving_" not in it[1]] + moving
+        return items
+
+    def _keras_layers(self):
+        by_layer = OrderedDict((c["config"]["name"], []) for c in self._keras_layer_configs())
+        for layer, wname, arr in self._keras_weight_items():
+            by_layer[layer].append((wname, arr))
+        return list(by_layer.items())
 
     # ---- device
     def _get_engine(self):
@@ -392,6 +475,34 @@ class SiameseModel(_ModelBase):
         return dict(kind="siamese", encoder=self.encoder.get_config(), input_shape=self.input_shape,
                     distance_metric=self.distance_metric)
 
+    def _keras_config(self):
+        shape = [None] + [int(v) for v in self.input_shape]
+        inp = lambda n: {"class_name": "InputLayer", "name": n, "inbound_nodes": [], "config": {
+            "name": n, "dtype": "float32", "sparse": False, "batch_input_shape": shape}}
+        # the distance layers are Python lambdas (voicemap/models.py:57,66); Keras stores them as interpreter-specific
+        # bytecode, which cannot be produced here: ``function`` is null, so the file round-trips through this
+        # package's load_model and keras' load_weights, but not through keras' load_model
+        lam = {"class_name": "Lambda", "name": "lambda_1", "inbound_nodes": [[["subtract_1", 0, 0, {}]]], "config": {
+            "name": "lambda_1", "trainable": True, "function": None, "function_type": "lambda", "arguments": {},
+            "output_shape": None, "output_shape_type": "raw", "voicemap_distance_metric": self.distance_metric}}
+        head = _dense_config("dense_2", 1, "sigmoid")
+        head.update(name="dense_2", inbound_nodes=[[["lambda_1", 0, 0, {}]]])
+        layers = [inp("input_1"), inp("input_2"),
+                  {"class_name": "Sequential", "name": "sequential_1", "config": self.encoder._keras_layer_configs(),
+                   "inbound_nodes": [[["input_1", 0, 0, {}]], [["input_2", 0, 0, {}]]]},
+                  {"class_name": "Subtract", "name": "subtract_1", "config": {"name": "subtract_1", "trainable": True},
+                   "inbound_nodes": [[["sequential_1", 1, 0, {}], ["sequential_1", 2, 0, {}]]]},
+                  lam, head]
+        return {"class_name": "Model", "config": {
+            "name": "model_1", "layers": layers, "input_layers": [["input_1", 0, 0], ["input_2", 0, 0]],
+            "output_layers": [["dense_2", 0, 0]]}}
+
+    def _keras_layers(self):
+        enc = [(f"sequential_1/{w}", a) for _, w, a in self.encoder._keras_weight_items(trainable_first=True)]
+        head = [("dense_2/kernel:0", self.head_weights["head_kernel"]), ("dense_2/bias:0", self.head_weights["head_bias"])]
+        return [("input_1", []), ("input_2", []), ("sequential_1", enc), ("subtract_1", []), ("lambda_1", []),
+                ("dense_2", head)]
+
     def _clone(self):
         return SiameseModel(self.encoder._clone(), self.input_shape, self.distance_metric)
 
@@ -495,22 +606,54 @@ def _load_keras_hdf5(filepath):
     first_pool = int(pools[0][0]) if pools and pools[0] else 4
     if first_pool not in (2, 4) or any(p != (2,) for p in pools[1:4]):
         raise ValueError(f"checkpoint pooling sizes {pools} are not a voicemap encoder (4,2,2,2 or 2,2,2,2)")
-    is_siamese = any(k.startswith("dense_2/") for k in flat)
+    is_siamese = cfg.get("class_name") == "Model"
+    drops = []
+
+    def walk_drop(o):
+        if isinstance(o, dict):
+            if o.get("class_name") == "SpatialDropout1D":
+                drops.append(float(o["config"].get("rate", 0.05)))
+            for v in o.values():
+                walk_drop(v)
+        elif isinstance(o, list):
+            for v in o:
+                walk_drop(v)
+
+    walk_drop(cfg)
+    lshape = None
+
+    def walk_shape(o):
+        nonlocal lshape
+        if isinstance(o, dict):
+            if lshape is None and o.get("batch_input_shape"):
+                lshape = tuple(o["batch_input_shape"][1:])
+            for v in o.values():
+                walk_shape(v)
+        elif isinstance(o, list):
+            for v in o:
+                walk_shape(v)
+
+    walk_shape(cfg)
+    lshape = lshape if lshape and lshape[0] else None
     # older checkpoints (models/n_seconds/*.hdf5) were trained with a first MaxPool1D of 2
-    enc = EncoderModel(filters, emb, dropout=0.05, first_pool=first_pool)
+    enc = EncoderModel(filters, emb, input_shape=None if is_siamese else lshape,
+                       dropout=drops[0] if drops else 0.05, first_pool=first_pool)
     enc.set_named_weights(named)
     if not is_siamese:
+        if any(k.endswith("dense_2/kernel") for k in flat):     # classifier: Dense(num_classes, softmax) on top
+            act = "softmax"
+            seq = cfg.get("config")
+            for layer in (seq if isinstance(seq, list) else seq.get("layers", [])):
+                if layer.get("config", {}).get("name") == "dense_2":
+                    act = layer["config"].get("activation", act)
+            enc.add(Dense(find("dense_2/kernel").shape[1], activation=act))
+            enc.set_named_weights({"head_kernel": find("dense_2/kernel"), "head_bias": find("dense_2/bias")})
         return enc
-    head_k = flat["dense_2/kernel"]
+    head_k = find("dense_2/kernel")
     metric = "weighted_l1" if head_k.shape[0] == emb and emb != 1 else "uniform_euclidean"
-    lshape = None
-    for layer in cfg.get("config", {}).get("layers", []):
-        if layer.get("class_name") == "InputLayer":
-            lshape = tuple(layer["config"]["batch_input_shape"][1:])
-            break
-    m = SiameseModel(enc, lshape if lshape and lshape[0] else (12000, 1), metric)
+    m = SiameseModel(enc, lshape if lshape else (12000, 1), metric)
     m.head_weights["head_kernel"] = head_k.reshape(m.head_weights["head_kernel"].shape).copy()
-    m.head_weights["head_bias"] = flat["dense_2/bias"].copy()
+    m.head_weights["head_bias"] = find("dense_2/bias").copy()
     return m
 
 
