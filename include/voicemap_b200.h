@@ -183,6 +183,27 @@ int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const
               int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
               float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
               float* dbias, double* red_scratch, void* stream);
+/* Synchronised BatchNorm across data-parallel ranks (the reference's BN sees the whole batch on one
+ * device).  The two calls above are split at the point where the per-(group, channel) sums exist, so that the caller
+ * can all-reduce them (torch.distributed / NCCL) in between:
+ *   forward : vm_bn_stats_sums -> all-reduce(sums) -> vm_bn_stats_from_sums(count = global clips per group * L)
+ *   backward: vm_bn_bwd_sums   -> all-reduce(copy of sums) -> vm_bn_bwd_from_sums(local sums, global sums, count)
+ * sums: (G, C) x {sum, sum of squares} resp. {sum dy, sum dy*xhat} as doubles.  dgamma / dbeta are formed from the
+ * LOCAL sums (the gradient all-reduce adds the ranks), the batch means from the GLOBAL sums.  With one rank
+ * (global = local) the results equal vm_bn_stats_finalize / vm_bn_bwd bit for bit. */
+int vm_bn_stats_sums(const float* stat_partial, int rows_per_clip, int N, int G, int C, double* red_scratch,
+                     double* sums, void* stream);
+int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
+                          float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
+                          void* stream);
+int vm_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L,
+                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
+                   double* red_scratch, double* sums, void* stream);
+int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
+                        const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C, int G,
+                        int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
+                        float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f, float* dbias,
+                        double* red_scratch, void* stream);
 /* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; x_* and du_* are bf16 planes;
  * partial: scratch. */
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,

@@ -214,3 +214,28 @@ def test_fit_generator_reduces_loss(tmp_path):
     assert hist[-1]["loss"] < hist[0]["loss"]
     assert "val_loss" in hist[-1] and "acc" in hist[-1]
     assert np.isfinite(sia.predict(next(gen())[0])).all()
+
+
+def test_sync_bn_split_path_equals_fused_path_on_one_rank():
+    """Synchronised BatchNorm splits the statistics at the all-reduce point (vm_bn_stats_sums / _from_sums,
+    vm_bn_bwd_sums / _from_sums).  With one rank (identity all-reduce) the split path must reproduce the fused
+    kernels bit for bit: loss, every gradient, moving statistics."""
+    n, length = 4, 1024
+    x1, x2 = O.synthetic_clips(n, length, seed=21), O.synthetic_clips(n, length, seed=22)
+    y = np.array([0, 1, 0, 1], dtype=np.float32)
+    out = []
+    for sync in (False, True):
+        _, sia, tr = _make(64, 32, "contrastive_loss", seed=3)
+        calls = []
+        if sync:
+            tr.set_sync_bn(lambda t: calls.append(t.numel()), 1)
+        lv, _ = tr.siamese_step(x1, x2, y, apply=False)
+        torch.cuda.synchronize()
+        out.append((float(lv.item()), tr.gradients(), {k: v.clone() for k, v in tr.moving.items()}))
+        if sync:   # 4 blocks forward + 4 backward, each (2 groups, C, 2) doubles
+            assert calls == [2 * c * 2 for c in (64, 128, 192, 256)] + [2 * c * 2 for c in (256, 192, 128, 64)]
+    assert out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    for k in out[0][2]:
+        assert torch.equal(out[0][2][k], out[1][2][k]), k

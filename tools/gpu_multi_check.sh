@@ -10,4 +10,5 @@ run python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 run python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 2 --warmup 1
 run python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/train_bench.py --steps 10
 run python tools/train_bench.py --pairs-per-gpu $((128 / N)) --steps 10
+run python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tools/ddp_parity.py
 tail -n 40 $LOG

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--bwd-precision", type=int, default=3)
+    ap.add_argument("--local-bn", action="store_true", help="per-rank BatchNorm statistics instead of synchronised")
     args = ap.parse_args()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -50,6 +51,7 @@ def main():
     x2 = (0.038021 * torch.randn(pairs, args.length, generator=g)).to(dev)
     y = np.concatenate([np.zeros(pairs // 2), np.ones(pairs - pairs // 2)]).astype(np.float32)
     allreduce = parallel.allreduce_sum_ if world > 1 else None
+    tr.set_sync_bn(None if args.local_bn else allreduce, world)
 
     for _ in range(max(args.warmup, 3)):
         tr.siamese_step(x1, x2, y, allreduce=allreduce, world=world)
@@ -74,7 +76,8 @@ def main():
                                                    f"{pairs} pairs/GPU x {args.length} samples, filters={args.filters}, "
                                                    f"fwd fp16x3, bwd bf16x{args.bwd_precision}",
                                           parallelism=f"dp{world}, one flat fp32 gradient all-reduce "
-                                                      f"({tr.nparams * 4 / 1e6:.1f} MB) per step"),
+                                                      f"({tr.nparams * 4 / 1e6:.1f} MB) per step, BatchNorm "
+                                                      f"{'per rank' if (args.local_bn or world == 1) else 'synchronised (8 small all-reduces)'}"),
                               final_loss=float(lv.item()))), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

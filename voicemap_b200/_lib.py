@@ -64,6 +64,11 @@ SIGNATURES = {
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp]),
+    "vm_bn_stats_sums": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "vm_bn_stats_from_sums": (_i, [_vp, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "vm_bn_bwd_from_sums": (_i, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "vm_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _f, _vp]),

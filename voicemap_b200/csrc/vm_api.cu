@@ -256,6 +256,30 @@ int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const
   return launch_bn_bwd(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks, bwd_const,
                        dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch, ST);
 }
+int vm_bn_stats_sums(const float* stat_partial, int rows_per_clip, int N, int G, int C, double* red_scratch,
+                     double* sums, void* stream) {
+  return launch_bn_stats_sums(stat_partial, rows_per_clip, vm_padded_channels(C), N, G, C, red_scratch, sums, ST);
+}
+int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
+                          float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
+                          void* stream) {
+  return launch_bn_stats_from_sums(sums, count, G, C, gamma, beta, eps, momentum, moving_mean, moving_var, bn_const, ST);
+}
+int vm_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L,
+                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
+                   double* red_scratch, double* sums, void* stream) {
+  return launch_bn_bwd_sums(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks,
+                            red_scratch, sums, ST);
+}
+int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
+                        const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C, int G,
+                        int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
+                        float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f, float* dbias,
+                        double* red_scratch, void* stream) {
+  return launch_bn_bwd_from_sums(local_sums, global_sums, count, u, dy_pooled, d_gmax, argmax, N, L, C, G, pool,
+                                 bn_const, mask, chunks, bwd_const, dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f,
+                                 dbias, red_scratch, ST);
+}
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
               int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream) {
   return launch_wgrad3(CH16(x_hi), CH16(x_lo), CH16(du_hi), CH16(du_lo), N, L, cin, cout, precision, partial,

@@ -104,6 +104,20 @@ int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, c
                   int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
                   float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
                   float* dbias, double* red_scratch, cudaStream_t st);
+// split forms for synchronised BatchNorm (sums -> caller's all-reduce -> constants)
+int launch_bn_stats_sums(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C, double* red_scratch,
+                         double* sums, cudaStream_t st);
+int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
+                              float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
+                              cudaStream_t st);
+int launch_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
+                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
+                       double* red_scratch, double* sums, cudaStream_t st);
+int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
+                            const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C, int G,
+                            int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
+                            float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
+                            float* dbias, double* red_scratch, cudaStream_t st);
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
                      float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
 int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);

@@ -104,6 +104,58 @@ __global__ void bn_stats_finalize_kernel(const double2* __restrict__ tmp, int N,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Split form of the statistics for synchronised BatchNorm across ranks: (1) per-(group, channel) double sums,
+// (2) the caller all-reduces them, (3) constants from the global sums and the global count.
+// ---------------------------------------------------------------------------------------------
+__global__ void stage2_sums_kernel(const double2* __restrict__ tmp, int G, int C, double2* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (int g = 0; g < G; ++g) sums[size_t(g) * C + c] = rowsum_stage2(tmp, g, C, c);
+}
+__global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, double cnt, int G, int C,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                          float momentum, float* __restrict__ moving_mean,
+                                          float* __restrict__ moving_var, float4* __restrict__ bn_const) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mm = moving_mean ? moving_mean[c] : 0.f;
+  float mv = moving_var ? moving_var[c] : 0.f;
+  for (int g = 0; g < G; ++g) {   // same arithmetic as bn_stats_finalize_kernel
+    const double2 sm = sums[size_t(g) * C + c];
+    const double mean = sm.x / cnt;
+    double var = sm.y / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = float(1.0 / sqrt(var + double(eps)));
+    const float s = gamma[c] * rstd;
+    bn_const[size_t(g) * C + c] = make_float4(s, beta[c] - float(mean) * s, float(mean), rstd);
+    const float var_unbiased = float(var * (cnt / (cnt - (1.0 + double(eps)))));
+    mm = mm * momentum + float(mean) * (1.f - momentum);
+    mv = mv * momentum + var_unbiased * (1.f - momentum);
+  }
+  if (moving_mean) moving_mean[c] = mm;
+  if (moving_var) moving_var[c] = mv;
+}
+// backward: the batch means of dy and dy*xhat come from the GLOBAL sums, dgamma / dbeta from this rank's own sums
+// (the gradient all-reduce adds the ranks' contributions)
+__global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const double2* __restrict__ global,
+                                        double cnt, int G, int C, const float4* __restrict__ bn_const,
+                                        float4* __restrict__ bwd_const, float* __restrict__ dgamma,
+                                        float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const double2 gs = global[size_t(g) * C + c], ls = local[size_t(g) * C + c];
+    bwd_const[size_t(g) * C + c] =
+        make_float4(bn_const[size_t(g) * C + c].x, float(gs.x / cnt), float(gs.y / cnt), 0.f);
+    tb += ls.x;
+    tg += ls.y;
+  }
+  dgamma[c] = float(tg);
+  dbeta[c] = float(tb);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BN affine (+ dropout mask) + MaxPool -> (hi, lo) planes.  One thread = 4 channels of one pooled position.
 // ---------------------------------------------------------------------------------------------
 __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G, int pool,
@@ -556,6 +608,27 @@ int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad,
   return check_launch_t("bn_stats_finalize");
 }
 
+int launch_bn_stats_sums(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C, double* red_scratch,
+                         double* sums, cudaStream_t st) {
+  if (N <= 0 || G <= 0 || N % G != 0 || C <= 0) return set_error(VM_ERR_SHAPE, "bn_stats_sums: bad shape");
+  if (red_scratch == nullptr || sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_stats_sums: null buffer");
+  double2* tmp = reinterpret_cast<double2*>(red_scratch);
+  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp);
+  stage2_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, G, C, reinterpret_cast<double2*>(sums));
+  return check_launch_t("bn_stats_sums");
+}
+
+int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
+                              float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
+                              cudaStream_t st) {
+  if (G <= 0 || C <= 0 || !(count > 1.0)) return set_error(VM_ERR_SHAPE, "bn_stats_from_sums: bad shape");
+  bn_stats_from_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const double2*>(sums), count, G, C, gamma,
+                                                         beta, eps, momentum, moving_mean, moving_var,
+                                                         reinterpret_cast<float4*>(bn_const));
+  return check_launch_t("bn_stats_from_sums");
+}
+
 int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
                        const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
                        cudaStream_t st) {
@@ -600,30 +673,90 @@ int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const 
   return check_launch_t("pair_head_loss_bwd");
 }
 
-int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
-                  int G, int pool, const float* bn_const, const float* mask, float* partial /* N*chunks*C float2 */,
-                  int chunks /* partial buffers hold N*chunks*max(1,512/C) rows */, float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo,
-                  float* dbias_partial /* N*chunks*C */, float* dbias, double* red_scratch, cudaStream_t st) {
+static int bn_bwd_check(const double* red_scratch, int N, int G, int C, int chunks, const void* dy_pooled,
+                        const void* d_gmax) {
   if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd: reduction scratch missing");
-  double2* tmp = reinterpret_cast<double2*>(red_scratch);
   if (N % G != 0 || chunks <= 0) return set_error(VM_ERR_SHAPE, "bn_bwd: bad shape");
   if ((dy_pooled == nullptr) == (d_gmax == nullptr)) return set_error(VM_ERR_SHAPE, "bn_bwd: give dy_pooled xor d_gmax");
   if (C % 4 != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: C must be a multiple of 4");
+  return VM_OK;
+}
+
+// passes 1-2: per-(group, channel) sums of dy and dy*xhat over this rank's clips -> tmp (and, if asked, `sums`)
+static int bn_bwd_reduce(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
+                         int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
+                         double* red_scratch, double* sums, cudaStream_t st) {
+  double2* tmp = reinterpret_cast<double2*>(red_scratch);
   const float4* bc = reinterpret_cast<const float4*>(bn_const);
   const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;  // must match the kernels' thread layout
   bn_bwd_reduce_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc, mask,
                                                         reinterpret_cast<float2*>(partial));
   rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
       partial, size_t(N / G) * chunks * nstream, C, C, tmp);
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, N, G, L, C, bc, reinterpret_cast<float4*>(bwd_const), dgamma,
-                                                      dbeta);
-  bn_relu_bwd_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc,
+  if (sums != nullptr) stage2_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, G, C, reinterpret_cast<double2*>(sums));
+  return VM_OK;
+}
+
+// pass 3 + conv-bias gradient, given bwd_const
+static int bn_bwd_apply(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
+                        int C, int G, int pool, const float* bn_const, const float* mask, int chunks,
+                        const float* bwd_const, __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias,
+                        double* red_scratch, cudaStream_t st) {
+  double2* tmp = reinterpret_cast<double2*>(red_scratch);
+  const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;
+  bn_relu_bwd_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool,
+                                                      reinterpret_cast<const float4*>(bn_const),
                                                       reinterpret_cast<const float4*>(bwd_const), mask, du_hi, du_lo,
                                                       dbias_partial);
   rowsum_stage1_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial,
                                                                            size_t(N) * chunks * nstream, C, C, tmp);
   colsum_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, C, dbias);
+  return VM_OK;
+}
+
+int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
+                  int G, int pool, const float* bn_const, const float* mask, float* partial /* N*chunks*C float2 */,
+                  int chunks /* partial buffers hold N*chunks*max(1,512/C) rows */, float* bwd_const, float* dgamma,
+                  float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial /* N*chunks*C */, float* dbias,
+                  double* red_scratch, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+  if (rc) return rc;
+  bn_bwd_reduce(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, partial, chunks, red_scratch, nullptr,
+                st);
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<double2*>(red_scratch), N, G, L, C,
+                                                      reinterpret_cast<const float4*>(bn_const),
+                                                      reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
+  bn_bwd_apply(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, chunks, bwd_const, du_hi, du_lo,
+               dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd");
+}
+
+int launch_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
+                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
+                       double* red_scratch, double* sums, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+  if (rc) return rc;
+  if (sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd_sums: null sums");
+  bn_bwd_reduce(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, partial, chunks, red_scratch, sums, st);
+  return check_launch_t("bn_bwd_sums");
+}
+
+int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
+                            const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C, int G,
+                            int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
+                            float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
+                            float* dbias, double* red_scratch, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+  if (rc) return rc;
+  if (local_sums == nullptr || global_sums == nullptr || !(count > 0.0))
+    return set_error(VM_ERR_SHAPE, "bn_bwd_from_sums: bad sums / count");
+  bn_bwd_from_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<const double2*>(local_sums),
+                                                       reinterpret_cast<const double2*>(global_sums), count, G, C,
+                                                       reinterpret_cast<const float4*>(bn_const),
+                                                       reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
+  bn_bwd_apply(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, chunks, bwd_const, du_hi, du_lo,
+               dbias_partial, dbias, red_scratch, st);
+  return check_launch_t("bn_bwd_from_sums");
 }
 
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,

@@ -41,6 +41,10 @@ class TrainEngine:
         self.loss_scale = float(loss_scale)
         self.precision = int(precision)
         self.bwd_precision = int(bwd_precision if bwd_precision is not None else precision)
+        # Synchronised BatchNorm: set_sync_bn(allreduce, world) makes the batch statistics those of
+        # the GLOBAL batch, as on the reference's single device; None = per-rank statistics
+        self.sync_allreduce = None
+        self.sync_world = 1
         if isinstance(model, SiameseModel):
             self.kind = "siamese"
             self.encoder_model = model.encoder
@@ -152,6 +156,7 @@ class TrainEngine:
         self.scr2 = torch.empty((scr_elems, 2), dtype=f32, device=dev)
         self.scr1 = torch.empty((scr_elems,), dtype=f32, device=dev)
         self.red = torch.empty(self.lib.vm_reduce_scratch_bytes(groups, max(c)) // 8, dtype=torch.float64, device=dev)
+        self.sums = torch.zeros((2, groups * max(c) * 2), dtype=torch.float64, device=dev)   # [local | global]
         # wgrad split partials (the launcher lowers its split count to fit) / wgrad1 per-CTA partials
         w1_bytes = nb * ((ls[0] + 1023) // 1024) * 32 * c[0] * 4
         self.wpart = torch.empty(max(64 << 20, w1_bytes) // 4, dtype=f32, device=dev)
@@ -208,11 +213,24 @@ class TrainEngine:
             _check(rc, f"train conv block {b + 1}")
             mm = self.moving[f"bn{b + 1}_mean"] if update_moving else None
             mv = self.moving[f"bn{b + 1}_var"] if update_moving else None
-            rc = lib.vm_bn_stats_finalize(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, ls[b], c[b],
-                                          _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
-                                          C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
-                                          _ptr(self.bnc[b]), _ptr(self.red), st)
-            _check(rc, "vm_bn_stats_finalize")
+            if self.sync_allreduce is None:
+                rc = lib.vm_bn_stats_finalize(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, ls[b], c[b],
+                                              _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
+                                              C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
+                                              _ptr(self.bnc[b]), _ptr(self.red), st)
+                _check(rc, "vm_bn_stats_finalize")
+            else:
+                sums = self.sums[1][:groups * c[b] * 2]
+                rc = lib.vm_bn_stats_sums(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, c[b], _ptr(self.red),
+                                          _ptr(sums), st)
+                _check(rc, "vm_bn_stats_sums")
+                self.sync_allreduce(sums)
+                count = float(self.sync_world) * (nb // groups) * ls[b]   # equal shards on every rank
+                rc = lib.vm_bn_stats_from_sums(_ptr(sums), C.c_double(count), groups, c[b],
+                                               _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
+                                               C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
+                                               _ptr(self.bnc[b]), st)
+                _check(rc, "vm_bn_stats_from_sums")
             if b < 3:
                 rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
                                         _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
@@ -227,6 +245,12 @@ class TrainEngine:
         _check(rc, "vm_dense_fwd")
         self.groups = groups
         return self.embv
+
+    def set_sync_bn(self, allreduce, world):
+        """allreduce(tensor): in-place SUM over ranks (torch.distributed.all_reduce); world: number of ranks, each
+        feeding the same number of clips per step.  allreduce=None restores per-rank statistics."""
+        self.sync_allreduce = allreduce
+        self.sync_world = int(world) if allreduce is not None else 1
 
     # ------------------------------------------------------------------ backward of the encoder
     def backward_encoder(self, d_emb):
@@ -245,12 +269,30 @@ class TrainEngine:
                 dy, dg, am = None, self.d_gmax, self.argmax
             else:
                 dy, dg, am = self.dX, None, None
-            rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, self.pools[b],
-                               _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
-                               _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
-                               _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
-                               _ptr(self.red), st)
-            _check(rc, f"vm_bn_bwd block {b + 1}")
+            if self.sync_allreduce is None:
+                rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
+                                   self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
+                                   _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
+                                   _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
+                                   _ptr(self.red), st)
+                _check(rc, f"vm_bn_bwd block {b + 1}")
+            else:
+                k = groups * c[b] * 2
+                loc, glo = self.sums[0][:k], self.sums[1][:k]
+                rc = lib.vm_bn_bwd_sums(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
+                                        self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2),
+                                        _BWD_CHUNKS, _ptr(self.red), _ptr(loc), st)
+                _check(rc, f"vm_bn_bwd_sums block {b + 1}")
+                glo.copy_(loc)
+                self.sync_allreduce(glo)
+                count = float(self.sync_world) * (nb // groups) * ls[b]
+                rc = lib.vm_bn_bwd_from_sums(_ptr(loc), _ptr(glo), C.c_double(count), _ptr(self.U[b]), _ptr(dy),
+                                             _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, self.pools[b],
+                                             _ptr(self.bnc[b]), _ptr(self.masks[b]), _BWD_CHUNKS, _ptr(self.bwc[b]),
+                                             _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]), _ptr(du_hi),
+                                             _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
+                                             _ptr(self.red), st)
+                _check(rc, f"vm_bn_bwd_from_sums block {b + 1}")
             if b == 0:
                 rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp, _ptr(self.wpart),
                                    self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
@@ -440,6 +482,9 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
         model._trainer = trainer
     dist, world = _dist_info()
     allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    # BatchNorm sees the whole batch in the reference (one device); data-parallel ranks therefore share their batch
+    # statistics unless the model opts out with ``model.sync_batchnorm = False``
+    trainer.set_sync_bn(allreduce if getattr(model, "sync_batchnorm", True) else None, world)
     callbacks = list(callbacks or [])
     for cb in callbacks:
         cb.set_model(model)
