@@ -173,6 +173,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// One lane of the (converged) warp.  The MMA issue loops run on the whole warp with only tcgen05.mma / commit under this
+// predicate, so that descriptor arithmetic stays warp-uniform (uniform registers) instead of being computed under a
+// divergent `if (lane == 0)` and moved into uniform registers through ELECT / R2UR waterfall loops.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(

@@ -258,8 +258,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&bars->full[sidx]);
     }
   } else if (warp == kEpiWarps) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: whole warp runs the loop, one elected lane issues (see elect_one_sync) ====
+    {
+      const bool elected = elect_one_sync();
       const uint32_t idesc = make_idesc_f16(kTileM, kTileN);
       uint32_t i = 0, ait = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
@@ -277,21 +278,21 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           const uint32_t wl = wh + kWPlaneBytes;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
+            if (elected) umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
                      make_smem_desc(th + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, k);
           if (nplanes == 2) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
+              if (elected) umma_f16(d_tmem, make_smem_desc(wh + k * 256, 128, 512, kLayoutNone),
                        make_smem_desc(tl + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, 1);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma_f16(d_tmem, make_smem_desc(wl + k * 256, 128, 512, kLayoutNone),
+              if (elected) umma_f16(d_tmem, make_smem_desc(wl + k * 256, 128, 512, kLayoutNone),
                        make_smem_desc(th + k * 2 * kBlockStride, kBlockStride, kBlockStride, kLayoutNone), idesc, 1);
           }
-          umma_commit(&bars->tfull[buf]);
+          if (elected) umma_commit(&bars->tfull[buf]);
         }
-        umma_commit(&bars->empty[s]);
+        if (elected) umma_commit(&bars->empty[s]);
       }
     }
   } else {
@@ -596,7 +597,8 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {
+      const bool elected = elect_one_sync();   // whole warp runs the loop (uniform descriptor math), one lane issues
       // M = 128 (co), N = 32 (taps), both operands MN-major, both bf16
       const uint32_t idesc = make_idesc_f16(128, 32, 1, 1) | (1u << 15) | (1u << 16);
       uint32_t i = 0, uit = 0, first = 1;
@@ -614,21 +616,21 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t arow = kk * 16 * 128;                       // 16 positions down the dU tile
             const uint32_t brow = (8 * j + 2 * kk) * kGroupStride;      // two 8-position row groups per K step
-            umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
+            if (elected) umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
                      make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, first ? 0u : 1u);
             first = 0;
             if (nplanes == 2) {
-              umma_f16(tmem_base, make_smem_desc(ul + arow, kUHalfBytes, 1024, kLayoutSW128),
+              if (elected) umma_f16(tmem_base, make_smem_desc(ul + arow, kUHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
-              umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
+              if (elected) umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(tl + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
             }
           }
-          umma_commit(&bars->uempty[us]);
+          if (elected) umma_commit(&bars->uempty[us]);
         }
-        umma_commit(&bars->tempty[ts]);
+        if (elected) umma_commit(&bars->tempty[ts]);
       }
-      umma_commit(&bars->done);
+      if (elected) umma_commit(&bars->done);
     }
   }
   if (warp < 4) {

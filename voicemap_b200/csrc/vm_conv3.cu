@@ -125,8 +125,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
+      const bool elected = elect_one_sync();
       uint32_t xit = 0, wit = 0, tit = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
         const int buf = tit & 1;
@@ -154,17 +155,19 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
               const uint32_t wa = smem_u32(wring + ws * kWTileBytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, acc);
+                if (elected)
+                  umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                           make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, acc);
                 acc = 1;
               }
               if (wplanes == 2) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                           make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
+                  if (elected)
+                    umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                             make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
               }
-              umma_commit(&bars->wempty[ws]);
+              if (elected) umma_commit(&bars->wempty[ws]);
               ++wit;
             }
             if (wplanes == 2) {  // W lo: Xh*Wl
@@ -174,15 +177,16 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
               const uint32_t wa = smem_u32(wring + ws * kWTileBytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                         make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
-              umma_commit(&bars->wempty[ws]);
+                if (elected)
+                  umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                           make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
+              if (elected) umma_commit(&bars->wempty[ws]);
               ++wit;
             }
           }
-          umma_commit(&bars->xempty[xs]);
+          if (elected) umma_commit(&bars->xempty[xs]);
         }
-        umma_commit(&bars->tfull[buf]);
+        if (elected) umma_commit(&bars->tfull[buf]);
       }
     }
   } else if (warp >= 4) {

@@ -97,7 +97,8 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool elected = elect_one_sync();   // whole warp runs the loop (uniform descriptor math), one lane issues
       const uint32_t idesc = make_idesc_f16_mn(128, 128);
       uint32_t it = 0;
       for (int st = s0; st < s1; ++st, ++it) {
@@ -113,19 +114,19 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t arow = (tap + 16 * kk) * 128, brow = (16 * kk) * 128;
             const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
+            if (elected) umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
                      make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, acc);
             if (nplanes == 2) {
-              umma_f16(d, make_smem_desc(xl + arow, kXHalfBytes, 1024, kLayoutSW128),
+              if (elected) umma_f16(d, make_smem_desc(xl + arow, kXHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
-              umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
+              if (elected) umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(ul + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
             }
           }
         }
-        umma_commit(&bars->empty[s]);
+        if (elected) umma_commit(&bars->empty[s]);
       }
-      umma_commit(&bars->done);
+      if (elected) umma_commit(&bars->done);
     }
   } else {
     // epilogue: TMEM lane = ci row; write partial[split][tap][ci][co]
