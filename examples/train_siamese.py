@@ -66,7 +66,7 @@ def main():
         callbacks=[
             NShotEvaluationCallback(args.eval_tasks, 1, args.k_way, valid, preprocessor=pre),
             CSVLogger(os.path.join(args.out, "logs", tag + ".csv")),
-            ModelCheckpoint(os.path.join(args.out, "models", tag + ".npz"), monitor=monitor, mode="max",
+            ModelCheckpoint(os.path.join(args.out, "models", tag + ".hdf5"), monitor=monitor, mode="max",
                             save_best_only=True, verbose=True),
             ReduceLROnPlateau(monitor=monitor, mode="max", verbose=1),
         ])

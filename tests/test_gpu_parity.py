@@ -237,9 +237,10 @@ def test_full_batch_properties(stress_params):
     assert torch.equal(eng.forward(x), full)
 
 
-@pytest.mark.parametrize("filters,emb", [(16, 32), (32, 64), (64, 128), (256, 64)])
+@pytest.mark.parametrize("filters,emb", [(16, 32), (32, 64), (64, 128), (256, 64), (512, 512)])
 def test_encoder_parity_filter_sweep(filters, emb):
-    """grid_search_siamese_network.py:23-25 sweeps filters in [16, 32, 64, 128] and embedding in [32..512]."""
+    """grid_search_siamese_network.py:23-25 sweeps filters in [16, 32, 64, 128] and embedding in [32..512]; 256 and
+    512 are the stretch widths of SURVEY.md 8(d) C5 (block 4 then has 2048 output channels = 16 cout slabs)."""
     params = O.init_encoder_params(filters, emb, seed=filters, randomize_bn=True, random_bias=True)
     eng = _engine(filters, emb, params)
     x = O.synthetic_clips(3, 6000, seed=8)

@@ -365,3 +365,22 @@ def test_hdf5_writer_structure(tmp_path):
     for mtype, data in f._messages(f.resolve("/model_weights/mid/mid/w:0")):
         if mtype == 0x03:
             assert data[:20] == ref_dtype
+
+
+def test_summary_of_both_model_kinds_counts_parameters():
+    """model.summary() (experiments/train_siamese.py:58, train_classifier.py:116): one line per layer, the siamese net
+    lists its shared encoder as a nested Sequential; totals as Keras reports them (1 023 808
+    trainable encoder parameters + 2 560 moving statistics at filters=128, emb=64; +2 for the siamese head)."""
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    enc = get_baseline_convolutional_encoder(128, 64)
+    lines = []
+    enc.summary(print_fn=lines.append)
+    text = "\n".join(lines)
+    assert "conv1d_1 (Conv1D)" in text and "dense_1 (Dense)" in text
+    assert f"Total params: {1023808 + 2560:,}" in text
+    sia = build_siamese_net(enc, (12000, 1))
+    lines = []
+    sia.summary(print_fn=lines.append)
+    text = "\n".join(lines)
+    assert "sequential_1 (Sequential)" in text and "dense_2 (Dense)" in text
+    assert f"Total params: {1023808 + 2560 + 2:,}" in text

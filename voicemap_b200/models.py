@@ -94,11 +94,11 @@ class _ModelBase:
         lines = ["_" * 65, f"{'Layer (type)':<40}{'Param #':>25}", "=" * 65]
         total = 0
         for layer in self.layers:
-            n = int(sum(np.prod(self._weight(w).shape) for w in layer.weight_names)) if layer.weight_names else 0
-            if isinstance(layer, _ModelBase):
+            if isinstance(layer, _ModelBase):     # the shared encoder inside a siamese model
                 n = layer.count_params()
                 lines.append(f"{layer.name + ' (Sequential)':<40}{n:>25}")
             else:
+                n = int(sum(np.prod(self._weight(w).shape) for w in layer.weight_names))
                 lines.append(f"{layer.name + ' (' + layer.class_name + ')':<40}{n:>25}")
             total += n
         lines += ["=" * 65, f"Total params: {total:,}", "_" * 65]
