@@ -37,7 +37,8 @@ def main():
 
     if args.synthetic:
         from synthetic_speakers import SyntheticCorpus
-        tr, va = SyntheticCorpus(40, 6, seed=0), SyntheticCorpus(12, 6, subset="synthetic-dev", seed=1)
+        # the reference's differing-pair draw excludes every speaker of its first draw: keep speakers >> batchsize / 2
+        tr, va = SyntheticCorpus(120, 4, seed=0), SyntheticCorpus(80, 3, subset="synthetic-dev", seed=1)
         train = LibriSpeechDataset("synthetic", args.seconds, pad=True, index=tr.index, reader=tr.reader)
         valid = LibriSpeechDataset("synthetic-dev", args.seconds, stochastic=False, pad=True, index=va.index,
                                    reader=va.reader)

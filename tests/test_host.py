@@ -384,3 +384,26 @@ def test_summary_of_both_model_kinds_counts_parameters():
     text = "\n".join(lines)
     assert "sequential_1 (Sequential)" in text and "dense_2 (Dense)" in text
     assert f"Total params: {1023808 + 2560 + 2:,}" in text
+
+
+def test_verification_batches_on_a_small_corpus():
+    """The reference draws pairs with ``df.sample(n, weights='length')`` (voicemap/librispeech.py:143-167); current pandas
+    rejects that draw on small corpora (n * max weight > total weight).  The batcher keeps the reference's semantics
+    (distinct rows, probability proportional to length) through numpy.  (The reference's differing-pair draw needs
+    more speakers than pairs: it excludes every speaker of the first draw.)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    from synthetic_speakers import SyntheticCorpus
+    from voicemap_b200.librispeech import LibriSpeechDataset
+    va = SyntheticCorpus(40, 3, subset="synthetic-dev", seed=1)
+    valid = LibriSpeechDataset("synthetic-dev", 3, stochastic=False, pad=True, index=va.index, reader=va.reader)
+    np.random.seed(0)
+    for _ in range(5):
+        (a, b), y = valid.build_verification_batch(32)
+        assert a.shape == b.shape == (32, 48000, 1) and y.shape == (32, 1)
+        assert y[:16].sum() == 0 and y[16:].sum() == 16
+    pairs = valid.get_differing_pairs(16)
+    spk = valid.df.set_index("id")["speaker_id"]
+    assert all(spk[i] != spk[j] for i, j in pairs)
+    assert all(spk[i] == spk[j] for i, j in valid.get_alike_pairs(16))

@@ -27,6 +27,16 @@ def _default_reader(path):
     return sf.read(path)
 
 
+def _sample_by_length(df, n):
+    """``df.sample(n, weights='length')`` with the semantics of the pandas the reference pins (0.23): n distinct rows
+    drawn with numpy's weighted choice without replacement from the global ``np.random`` state.  pandas >= 2.2 refuses
+    that draw whenever n * max(weight) > sum(weights) ("Weighted sampling cannot be achieved with replace=False"),
+    which small corpora hit at the reference's batch sizes."""
+    w = df['length'].to_numpy(dtype=np.float64)
+    locs = np.random.choice(len(df), size=n, replace=False, p=w / w.sum())
+    return df.iloc[locs]
+
+
 class LibriSpeechDataset(Sequence):
     """Sequence whose __getitem__ returns (raw audio fragment float64[fragment_length], label); also builds
     verification batches and k-way n-shot tasks.
@@ -146,7 +156,7 @@ class LibriSpeechDataset(Sequence):
     def get_alike_pairs(self, num_pairs):
         """List of 2-tuples of dataset IDs belonging to the same speaker (voicemap/librispeech.py:143-153)."""
         alike_pairs = pd.merge(
-            self.df.sample(num_pairs * 2, weights='length'),
+            _sample_by_length(self.df, num_pairs * 2),
             self.df,
             on='speaker_id'
         ).sample(num_pairs)[['speaker_id', 'id_x', 'id_y']]
@@ -154,9 +164,9 @@ class LibriSpeechDataset(Sequence):
 
     def get_differing_pairs(self, num_pairs):
         """List of 2-tuples of dataset IDs belonging to different speakers (voicemap/librispeech.py:155-167)."""
-        random_sample = self.df.sample(num_pairs, weights='length')
-        random_sample_from_other_speakers = self.df[~self.df['speaker_id'].isin(
-            random_sample['speaker_id'])].sample(num_pairs, weights='length')
+        random_sample = _sample_by_length(self.df, num_pairs)
+        random_sample_from_other_speakers = _sample_by_length(
+            self.df[~self.df['speaker_id'].isin(random_sample['speaker_id'])], num_pairs)
         return list(zip(random_sample['id'].values, random_sample_from_other_speakers['id'].values))
 
     def build_verification_batch(self, batchsize):
@@ -193,12 +203,12 @@ class LibriSpeechDataset(Sequence):
         if k <= 1:
             raise ValueError('k must be greater than or equal to one!')
 
-        query = self.df.sample(1, weights='length')
+        query = _sample_by_length(self.df, 1)
         query_sample = self[query.index.values[0]]
 
         is_query_speaker = self.df['speaker_id'] == query['speaker_id'].values[0]
         not_same_sample = self.df.index != query.index.values[0]
-        correct_samples = self.df[is_query_speaker & not_same_sample].sample(n, weights='length')
+        correct_samples = _sample_by_length(self.df[is_query_speaker & not_same_sample], n)
 
         # Sample k-1 speakers
         other_support_set_speakers = np.random.choice(
@@ -208,7 +218,7 @@ class LibriSpeechDataset(Sequence):
         for i in range(k - 1):
             is_same_speaker = self.df['speaker_id'] == other_support_set_speakers[i]
             other_support_samples.append(
-                self.df[~is_query_speaker & is_same_speaker].sample(n, weights='length')
+                _sample_by_length(self.df[~is_query_speaker & is_same_speaker], n)
             )
         support_set = pd.concat([correct_samples] + other_support_samples)
         support_set_samples = tuple(np.stack(i) for i in zip(*[self[i] for i in support_set.index]))
