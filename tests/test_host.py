@@ -407,3 +407,13 @@ def test_verification_batches_on_a_small_corpus():
     spk = valid.df.set_index("id")["speaker_id"]
     assert all(spk[i] != spk[j] for i, j in pairs)
     assert all(spk[i] == spk[j] for i, j in valid.get_alike_pairs(16))
+
+
+def test_empty_batches_give_empty_results_without_a_device():
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    enc = get_baseline_convolutional_encoder(16, 8)
+    assert enc.predict(np.zeros((0, 4000, 1))).shape == (0, 8)
+    sia = build_siamese_net(enc, (4000, 1))
+    assert sia.predict([np.zeros((0, 4000, 1)), np.zeros((0, 4000, 1))]).shape == (0, 1)
+    with pytest.raises(ValueError):
+        sia.predict([np.zeros((0, 4000, 1)), np.zeros((0, 3000, 1))])

@@ -357,6 +357,9 @@ class EncoderModel(_ModelBase):
         is accepted for compatibility; results do not depend on it."""
         import torch
         xt = self._host_batch(x)
+        if xt.shape[0] == 0:     # an empty batch yields an empty result (as numpy-style APIs do); nothing to launch
+            units = self._head["units"] if self._head is not None else self.embedding_dimension
+            return np.zeros((0, units), dtype=np.float32)
         eng = self._get_engine()
         emb = self._embed_pipelined(xt, eng)
         if self._head is not None:
@@ -526,6 +529,8 @@ class SiameseModel(_ModelBase):
         if (x1.shape[1], 1) != self.input_shape:
             raise ValueError(f"Error when checking input: expected input_1 to have shape {self.input_shape} but got "
                              f"array with shape {(x1.shape[1], 1)}")
+        if x1.shape[0] == 0:
+            return np.zeros((0, 1), dtype=np.float32)
         eng = self.encoder._get_engine()
         w, b = self._head_device(eng.device)
         outs = []
