@@ -1,256 +1,251 @@
-"""voicemap.librispeech batcher with the reference's signatures (voicemap/librispeech.py:15-281), ported to
-Python 3.  Host-side I/O only (FLAC decoding is outside the hot path): the audio reader is pluggable --
-``soundfile`` when installed, else any callable ``reader(path) -> (samples, samplerate)`` -- and an index
-DataFrame can be injected so the sampling logic runs without LibriSpeech on disk.
+"""LibriSpeech batcher behind the reference's ``voicemap.librispeech`` interface (constructor, ``__getitem__``,
+pair / verification-batch / n-shot-task builders, ``.df`` columns: voicemap/librispeech.py:31-281).
+
+Host-side I/O, outside the CUDA hot path.  The implementation is array based: after the index is loaded the
+corpus is three numpy vectors (speaker id, length in samples, sex flag) plus a path list; every draw is a
+vectorised ``np.random`` call on those vectors instead of DataFrame merges, and the DataFrame the reference's callers
+read (``dataset.df``) is kept only as a view of the same rows.
+
+Sampling distributions are the reference's:
+  * files are drawn without replacement with probability proportional to their length (`df.sample(weights='length')`,
+    voicemap/librispeech.py:145,157,161,219,226,236);
+  * an alike pair is a uniform pick among all (anchor, same-speaker file) combinations of 2n length-weighted anchors,
+    the anchor itself included (the merge-then-sample of voicemap/librispeech.py:144-151);
+  * a differing pair is a length-weighted file plus a length-weighted file of any speaker absent from the first draw
+    (voicemap/librispeech.py:157-165);
+  * labels of a verification batch are 0 (same speaker) for the first half and 1 for the second (:179-194).
+
+Extensions (keyword-only): ``reader`` plugs in any decoder ``path -> (samples, rate)`` (``soundfile`` is the default
+and is imported lazily), ``index`` injects a ready index table so the batcher runs without the corpus on disk,
+``data_path`` replaces ``config.PATH``.
 """
 from __future__ import annotations
 
 import os
+from collections import defaultdict
 
 import numpy as np
 import pandas as pd
-from tqdm import tqdm
 
 from .config import LIBRISPEECH_SAMPLING_RATE, PATH
 from .keras_compat import Sequence
 
 sex_to_label = {'M': False, 'F': True}
-label_to_sex = {False: 'M', True: 'F'}
+label_to_sex = {flag: sex for sex, flag in sex_to_label.items()}
+
+_LABEL_KINDS = ('sex', 'speaker')
+_SPEAKER_FIELDS = ('id', 'sex', 'subset', 'minutes', 'name')
+_FILE_FIELDS = ('id', 'filepath', 'length', 'seconds')
 
 
-def _default_reader(path):
+def _soundfile_reader(path):
     try:
-        import soundfile as sf
+        import soundfile
     except ImportError as exc:  # pragma: no cover - depends on the environment
-        raise ImportError("reading LibriSpeech FLAC files needs `soundfile`; pass reader=... to "
-                          "LibriSpeechDataset to plug in another decoder") from exc
-    return sf.read(path)
+        raise ImportError('decoding LibriSpeech FLAC needs the `soundfile` package; alternatively construct '
+                          'LibriSpeechDataset(..., reader=callable(path) -> (samples, samplerate))') from exc
+    return soundfile.read(path)
 
 
-def _sample_by_length(df, n):
-    """``df.sample(n, weights='length')`` with the semantics of the pandas the reference pins (0.23): n distinct rows
-    drawn with numpy's weighted choice without replacement from the global ``np.random`` state.  pandas >= 2.2 refuses
-    that draw whenever n * max(weight) > sum(weights) ("Weighted sampling cannot be achieved with replace=False"),
-    which small corpora hit at the reference's batch sizes."""
-    w = df['length'].to_numpy(dtype=np.float64)
-    locs = np.random.choice(len(df), size=n, replace=False, p=w / w.sum())
-    return df.iloc[locs]
+def read_speaker_table(path):
+    """Parse LibriSpeech's SPEAKERS.TXT (``;`` comment lines, then ``ID | SEX | SUBSET | MINUTES | NAME`` records).
+    Records that do not have exactly five fields are dropped, which is what the reference's
+    ``read_csv(..., error_bad_lines=False)`` does with them (voicemap/librispeech.py:64-71)."""
+    records = []
+    with open(path, encoding='utf-8', errors='replace') as handle:
+        for line in handle:
+            if line.startswith(';') or not line.strip():
+                continue
+            parts = [p.strip() for p in line.rstrip('\n').split('|')]
+            if len(parts) != len(_SPEAKER_FIELDS):
+                continue
+            records.append((int(parts[0]), parts[1], parts[2], float(parts[3]), parts[4]))
+    return pd.DataFrame.from_records(records, columns=_SPEAKER_FIELDS)
+
+
+def _flac_files(subset_dir):
+    """(speaker id, path) of every .flac below ``subset_dir`` (layout <subset>/<speaker>/<chapter>/<utterance>.flac)."""
+    found = []
+    for folder, _, names in os.walk(subset_dir):
+        flacs = sorted(n for n in names if n.endswith('.flac'))
+        if flacs:
+            speaker = int(os.path.basename(os.path.dirname(os.path.normpath(folder))))
+            found.extend((speaker, os.path.join(folder, n)) for n in flacs)
+    return found
 
 
 class LibriSpeechDataset(Sequence):
-    """Sequence whose __getitem__ returns (raw audio fragment float64[fragment_length], label); also builds
-    verification batches and k-way n-shot tasks.
+    """``dataset[i] -> (float64[fragment_length], label)`` plus verification batches and k-way n-shot tasks.
 
-    # Arguments (voicemap/librispeech.py:31)
-        subsets, seconds, label ('speaker'|'sex'), stochastic, pad, cache: as in the reference.
-    # Extensions (keyword-only)
-        reader: callable(path) -> (samples, samplerate).
-        index: pre-built pandas DataFrame with the reference's index columns
-               (id, sex, subset, minutes, name, filepath, length, seconds); skips disk indexing.
-        data_path: root containing ``data/LibriSpeech`` (default config.PATH).
+    # Arguments (same meaning as voicemap/librispeech.py:31-41)
+        subsets: subset name or list of names ('dev-clean', 'train-clean-100', ...)
+        seconds: fragment length; files not longer than this are dropped unless ``pad``
+        label: 'speaker' or 'sex'
+        stochastic: random fragment position (and random split of the padding) instead of the file start
+        pad: keep short files and zero-pad them to ``seconds``
+        cache: reuse / write ``<data_path>/data/<subset>.index.csv``
     """
+
     def __init__(self, subsets, seconds, label='speaker', stochastic=True, pad=False, cache=True, *,
                  reader=None, index=None, data_path=None):
-        assert label in ('sex', 'speaker'), 'Label type must be one of (\'sex\', \'speaker\')'
+        assert label in _LABEL_KINDS, "Label type must be one of ('sex', 'speaker')"
         self.subset = subsets
-        self.fragment_seconds = seconds
-        self.fragment_length = int(seconds * LIBRISPEECH_SAMPLING_RATE)
+        self.label = label
         self.stochastic = stochastic
         self.pad = pad
-        self.label = label
-        self.reader = reader or _default_reader
-        self.data_path = data_path or PATH
+        self.fragment_seconds = seconds
+        self.fragment_length = int(seconds * LIBRISPEECH_SAMPLING_RATE)
+        self.reader = reader if reader is not None else _soundfile_reader
+        self.data_path = data_path if data_path is not None else PATH
 
         print('Initialising LibriSpeechDataset with minimum length = {}s and subsets = {}'.format(seconds, subsets))
-
-        if isinstance(subsets, str):
-            subsets = [subsets]
-
-        if index is not None:
-            self.df = index.copy()
+        names = [subsets] if isinstance(subsets, str) else list(subsets)
+        if index is None:
+            table = pd.concat([self._subset_table(name, cache) for name in names], ignore_index=True)
         else:
-            cached_df = []
-            found_cache = {s: False for s in subsets}
-            if cache:
-                for s in subsets:
-                    subset_index_path = self.data_path + '/data/{}.index.csv'.format(s)
-                    if os.path.exists(subset_index_path):
-                        cached_df.append(pd.read_csv(subset_index_path))
-                        found_cache[s] = True
+            table = pd.DataFrame(index)
+        if not pad:
+            table = table[table['seconds'] > seconds]
+        self.unique_speakers = int(table['id'].nunique())
 
-            if all(found_cache.values()) and cache:
-                self.df = pd.concat(cached_df)
-            else:
-                df = pd.read_csv(self.data_path + '/data/LibriSpeech/SPEAKERS.TXT', skiprows=11, delimiter='|',
-                                 on_bad_lines='skip')
-                df.columns = [col.strip().replace(';', '').lower() for col in df.columns]
-                df = df.assign(
-                    sex=df['sex'].apply(lambda x: x.strip()),
-                    subset=df['subset'].apply(lambda x: x.strip()),
-                    name=df['name'].apply(lambda x: x.strip()),
-                )
-                audio_files = []
-                for subset, found in found_cache.items():
-                    if not found:
-                        audio_files += self.index_subset(subset, reader=self.reader, data_path=self.data_path)
-                df = pd.merge(df, pd.DataFrame(audio_files))
-                self.df = pd.concat(cached_df + [df])
+        # row number == dataset id; the speaker's LibriVox id moves to `speaker_id` (voicemap/librispeech.py:88-96)
+        table = table.rename(columns={'id': 'speaker_id', 'minutes': 'speaker_minutes'}).reset_index(drop=True)
+        table['id'] = np.arange(len(table))
+        self.df = table
 
-            for s in subsets:
-                self.df[self.df['subset'] == s].to_csv(self.data_path + '/data/{}.index.csv'.format(s), index=False)
-
-        # Trim too-small files
-        if not self.pad:
-            self.df = self.df[self.df['seconds'] > self.fragment_seconds]
-        self.unique_speakers = len(self.df['id'].unique())
-
-        # Renaming for clarity
-        self.df = self.df.rename(columns={'id': 'speaker_id', 'minutes': 'speaker_minutes'})
-
-        # Index of dataframe has direct correspondence to item in dataset
-        self.df = self.df.reset_index(drop=True)
-        self.df = self.df.assign(id=self.df.index.values)
-
-        self.datasetid_to_filepath = self.df.to_dict()['filepath']
-        self.datasetid_to_speaker_id = self.df.to_dict()['speaker_id']
-        self.datasetid_to_sex = self.df.to_dict()['sex']
-
+        self._paths = table['filepath'].tolist()
+        self._speaker = table['speaker_id'].to_numpy()
+        self._weight = table['length'].to_numpy(dtype=np.float64)
+        self._sex = table['sex'].tolist()
+        members = defaultdict(list)
+        for row, speaker in enumerate(self._speaker):
+            members[speaker].append(row)
+        self._members = {speaker: np.asarray(rows) for speaker, rows in members.items()}
+        self._group_size = np.asarray([len(self._members[s]) for s in self._speaker], dtype=np.int64)
+        # the reference's lookup tables, kept for code that pokes at them
+        self.datasetid_to_filepath = dict(enumerate(self._paths))
+        self.datasetid_to_speaker_id = dict(enumerate(self._speaker.tolist()))
+        self.datasetid_to_sex = dict(enumerate(self._sex))
         print('Finished indexing data. {} usable files found.'.format(len(self)))
 
-    def __getitem__(self, index):
-        instance, samplerate = self.reader(self.datasetid_to_filepath[index])
-        # Choose a random sample of the file
-        if self.stochastic:
-            fragment_start_index = np.random.randint(0, max(len(instance) - self.fragment_length, 1))
-        else:
-            fragment_start_index = 0
-
-        instance = instance[fragment_start_index:fragment_start_index + self.fragment_length]
-
-        # Check for required length and pad if necessary
-        if self.pad and len(instance) < self.fragment_length:
-            less_timesteps = self.fragment_length - len(instance)
-            if self.stochastic:
-                # random number of 0s before, the rest after
-                before_len = np.random.randint(0, less_timesteps)
-                after_len = less_timesteps - before_len
-                instance = np.pad(instance, (before_len, after_len), 'constant')
-            else:
-                instance = np.pad(instance, (0, less_timesteps), 'constant')
-
-        if self.label == 'sex':
-            label = sex_to_label[self.datasetid_to_sex[index]]
-        elif self.label == 'speaker':
-            label = self.datasetid_to_speaker_id[index]
-        else:
-            raise ValueError('Label type must be one of (\'sex\', \'speaker\')')
-
-        return instance, label
-
-    def __len__(self):
-        return len(self.df)
-
-    def num_classes(self):
-        return len(self.df['speaker_id'].unique())
-
-    def get_alike_pairs(self, num_pairs):
-        """List of 2-tuples of dataset IDs belonging to the same speaker (voicemap/librispeech.py:143-153)."""
-        alike_pairs = pd.merge(
-            _sample_by_length(self.df, num_pairs * 2),
-            self.df,
-            on='speaker_id'
-        ).sample(num_pairs)[['speaker_id', 'id_x', 'id_y']]
-        return list(zip(alike_pairs['id_x'].values, alike_pairs['id_y'].values))
-
-    def get_differing_pairs(self, num_pairs):
-        """List of 2-tuples of dataset IDs belonging to different speakers (voicemap/librispeech.py:155-167)."""
-        random_sample = _sample_by_length(self.df, num_pairs)
-        random_sample_from_other_speakers = _sample_by_length(
-            self.df[~self.df['speaker_id'].isin(random_sample['speaker_id'])], num_pairs)
-        return list(zip(random_sample['id'].values, random_sample_from_other_speakers['id'].values))
-
-    def build_verification_batch(self, batchsize):
-        """Batch of verification pairs: first half same-speaker pairs (label 0), second half different speakers
-        (label 1) (voicemap/librispeech.py:169-196).  Returns ([input_1, input_2] each (B, T, 1), labels (B, 1))."""
-        half = batchsize // 2
-        alike_pairs = self.get_alike_pairs(half)
-        input_1_alike = np.stack([self[i][0] for i in list(zip(*alike_pairs))[0]])
-        input_2_alike = np.stack([self[i][0] for i in list(zip(*alike_pairs))[1]])
-
-        differing_pairs = self.get_differing_pairs(half)
-        input_1_different = np.stack([self[i][0] for i in list(zip(*differing_pairs))[0]])
-        input_2_different = np.stack([self[i][0] for i in list(zip(*differing_pairs))[1]])
-
-        input_1 = np.vstack([input_1_alike, input_1_different])[:, :, np.newaxis]
-        input_2 = np.vstack([input_2_alike, input_2_different])[:, :, np.newaxis]
-
-        outputs = np.append(np.zeros(half), np.ones(half))[:, np.newaxis]
-
-        return [input_1, input_2], outputs
-
-    def yield_verification_batches(self, batchsize):
-        """Convenience function to yield verification batches forever."""
-        while True:
-            ([input_1, input_2], labels) = self.build_verification_batch(batchsize)
-            yield ([input_1, input_2], labels)
-
-    def build_n_shot_task(self, k, n=1):
-        """k-way n-shot task: (query_sample, support_set_samples); the first n support samples belong to the
-        query's speaker (voicemap/librispeech.py:204-240)."""
-        if k >= self.unique_speakers:
-            raise ValueError('k must be smaller than the number of unique speakers in this dataset!')
-
-        if k <= 1:
-            raise ValueError('k must be greater than or equal to one!')
-
-        query = _sample_by_length(self.df, 1)
-        query_sample = self[query.index.values[0]]
-
-        is_query_speaker = self.df['speaker_id'] == query['speaker_id'].values[0]
-        not_same_sample = self.df.index != query.index.values[0]
-        correct_samples = _sample_by_length(self.df[is_query_speaker & not_same_sample], n)
-
-        # Sample k-1 speakers
-        other_support_set_speakers = np.random.choice(
-            self.df[~is_query_speaker]['speaker_id'].unique(), k - 1, replace=False)
-
-        other_support_samples = []
-        for i in range(k - 1):
-            is_same_speaker = self.df['speaker_id'] == other_support_set_speakers[i]
-            other_support_samples.append(
-                _sample_by_length(self.df[~is_query_speaker & is_same_speaker], n)
-            )
-        support_set = pd.concat([correct_samples] + other_support_samples)
-        support_set_samples = tuple(np.stack(i) for i in zip(*[self[i] for i in support_set.index]))
-
-        return query_sample, support_set_samples
+    # ------------------------------------------------------------------------------------------------ index
+    def _subset_table(self, name, cache):
+        csv_path = os.path.join(self.data_path, 'data', '{}.index.csv'.format(name))
+        if cache and os.path.exists(csv_path):
+            return pd.read_csv(csv_path)
+        speakers = read_speaker_table(os.path.join(self.data_path, 'data', 'LibriSpeech', 'SPEAKERS.TXT'))
+        files = pd.DataFrame(self.index_subset(name, reader=self.reader, data_path=self.data_path),
+                             columns=_FILE_FIELDS)
+        table = speakers.merge(files, on='id')
+        table.to_csv(csv_path, index=False)
+        return table
 
     @staticmethod
     def index_subset(subset, reader=None, data_path=None):
-        """Index a subset: speaker ID, filepath and length of every .flac (voicemap/librispeech.py:243-281)."""
-        reader = reader or _default_reader
-        data_path = data_path or PATH
-        audio_files = []
+        """One record {id, filepath, length, seconds} per .flac of ``subset`` (voicemap/librispeech.py:243-281);
+        every file is decoded once to learn its length."""
+        from tqdm import tqdm
+        reader = reader if reader is not None else _soundfile_reader
+        root = os.path.join(data_path if data_path is not None else PATH, 'data', 'LibriSpeech', subset)
         print('Indexing {}...'.format(subset))
-        subset_len = 0
-        for root, folders, files in os.walk(data_path + '/data/LibriSpeech/{}/'.format(subset)):
-            subset_len += len([f for f in files if f.endswith('.flac')])
+        records = []
+        for speaker, path in tqdm(_flac_files(root)):
+            samples, _ = reader(path)
+            records.append({'id': speaker, 'filepath': path, 'length': len(samples),
+                            'seconds': len(samples) / float(LIBRISPEECH_SAMPLING_RATE)})
+        return records
 
-        progress_bar = tqdm(total=subset_len)
-        for root, folders, files in os.walk(data_path + '/data/LibriSpeech/{}/'.format(subset)):
-            if len(files) == 0:
-                continue
-            librispeech_id = int(root.split('/')[-2])
-            for f in files:
-                if not f.endswith('.flac'):
-                    continue
-                progress_bar.update(1)
-                instance, samplerate = reader(os.path.join(root, f))
-                audio_files.append({
-                    'id': librispeech_id,
-                    'filepath': os.path.join(root, f),
-                    'length': len(instance),
-                    'seconds': len(instance) * 1. / LIBRISPEECH_SAMPLING_RATE
-                })
-        progress_bar.close()
-        return audio_files
+    # ------------------------------------------------------------------------------------------------ items
+    def __len__(self):
+        return len(self._paths)
+
+    def num_classes(self):
+        return len(self._members)
+
+    def _fragment(self, samples):
+        """Crop to ``fragment_length`` (random offset if stochastic) and, with ``pad``, zero-fill short clips --
+        randomly split front/back if stochastic, at the back otherwise (voicemap/librispeech.py:105-124)."""
+        want = self.fragment_length
+        start = np.random.randint(0, max(len(samples) - want, 1)) if self.stochastic else 0
+        piece = samples[start:start + want]
+        missing = want - len(piece)
+        if missing <= 0 or not self.pad:
+            return piece
+        lead = np.random.randint(0, missing) if self.stochastic else 0
+        out = np.zeros(want, dtype=piece.dtype)
+        out[lead:lead + len(piece)] = piece
+        return out
+
+    def __getitem__(self, index):
+        samples, _ = self.reader(self._paths[index])
+        if self.label == 'speaker':
+            label = self._speaker[index]
+        elif self.label == 'sex':
+            label = sex_to_label[self._sex[index]]
+        else:
+            raise ValueError("Label type must be one of ('sex', 'speaker')")
+        return self._fragment(samples), label
+
+    def _clips(self, rows):
+        return np.stack([self[int(r)][0] for r in rows])
+
+    # ------------------------------------------------------------------------------------------------ draws
+    def _draw(self, count, among=None):
+        """``count`` distinct dataset ids, probability proportional to file length, optionally restricted to the id
+        array ``among``.  (numpy's weighted choice without replacement is what the pandas 0.23 pinned by the reference
+        calls; pandas >= 2.2 refuses the same request when count * max(weight) > sum(weights), which small corpora
+        hit at the reference's batch sizes.)"""
+        pool = np.arange(len(self)) if among is None else np.asarray(among)
+        w = self._weight[pool]
+        return pool[np.random.choice(len(pool), size=count, replace=False, p=w / w.sum())]
+
+    def get_alike_pairs(self, num_pairs):
+        """``num_pairs`` (id, id) tuples whose files share a speaker (voicemap/librispeech.py:143-153)."""
+        anchors = self._draw(2 * num_pairs)
+        ends = np.cumsum(self._group_size[anchors])          # combinations contributed by each anchor
+        picks = np.random.choice(int(ends[-1]), size=num_pairs, replace=False)
+        which = np.searchsorted(ends, picks, side='right')
+        nth = picks - (ends[which] - self._group_size[anchors[which]])
+        first = anchors[which]
+        second = [self._members[self._speaker[a]][j] for a, j in zip(first, nth)]
+        return list(zip(first.tolist(), (int(s) for s in second)))
+
+    def get_differing_pairs(self, num_pairs):
+        """``num_pairs`` (id, id) tuples from different speakers (voicemap/librispeech.py:155-167)."""
+        first = self._draw(num_pairs)
+        others = np.flatnonzero(~np.isin(self._speaker, self._speaker[first]))
+        second = self._draw(num_pairs, among=others)
+        return list(zip(first.tolist(), second.tolist()))
+
+    def build_verification_batch(self, batchsize):
+        """([input_1, input_2], labels): inputs (B, T, 1), labels (B, 1); first half alike pairs labelled 0, second
+        half differing pairs labelled 1 (voicemap/librispeech.py:169-196)."""
+        half = batchsize // 2
+        pairs = self.get_alike_pairs(half) + self.get_differing_pairs(half)
+        left, right = zip(*pairs)
+        inputs = [self._clips(side)[:, :, np.newaxis] for side in (left, right)]
+        labels = np.repeat([0.0, 1.0], half)[:, np.newaxis]
+        return inputs, labels
+
+    def yield_verification_batches(self, batchsize):
+        """Endless stream of verification batches (voicemap/librispeech.py:198-202)."""
+        while True:
+            yield self.build_verification_batch(batchsize)
+
+    def build_n_shot_task(self, k, n=1):
+        """((query, label), (support[k*n, T], labels[k*n])): the first n support clips are other files of the query's
+        speaker, followed by n clips of each of k-1 other speakers (voicemap/librispeech.py:204-240)."""
+        if k >= self.unique_speakers:
+            raise ValueError('k must be smaller than the number of unique speakers in this dataset!')
+        if k <= 1:
+            raise ValueError('k must be greater than or equal to one!')
+        query = int(self._draw(1)[0])
+        query_sample = self[query]
+        speaker = self._speaker[query]
+        same = self._members[speaker]
+        support = [self._draw(n, among=same[same != query])]
+        rivals = np.random.choice(np.asarray([s for s in self._members if s != speaker]), k - 1, replace=False)
+        support.extend(self._draw(n, among=self._members[r]) for r in rivals)
+        items = [self[int(r)] for r in np.concatenate(support)]
+        clips, labels = zip(*items)
+        return query_sample, (np.stack(clips), np.stack(labels))

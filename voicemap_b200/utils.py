@@ -1,246 +1,243 @@
-"""voicemap.utils for the B200 build: preprocessing, contrastive loss, n-shot evaluation and its callback,
-with the reference's names and argument meaning (voicemap/utils.py).  Host-side numpy as in the reference;
-the model calls inside go to the CUDA engine.
+"""``voicemap.utils`` for the B200 build -- the callers either side of the encoder: waveform
+preprocessing, the contrastive loss, k-way n-shot evaluation and its per-epoch callback.  Names, arguments and
+error behaviour follow voicemap/utils.py; the structure does not: preprocessing is an introspectable object (so
+the engine can fuse decimation + whitening into block 1, ``EncoderModel.predict_raw``), and n-shot evaluation is
+one pipeline (draw tasks -> embed -> score) that either calls ``predict`` per task like the reference or embeds
+many tasks per launch.
 """
 from __future__ import annotations
 
 import numpy as np
-from tqdm import tqdm
 
 from .keras_compat import Callback, clone_model
 
+WHITENING_RMS = 0.038021
+
+
+# ------------------------------------------------------------------------------------------------ preprocessing
+def whiten(batch, rms=WHITENING_RMS):
+    """Remove every clip's own mean, then multiply the whole batch by ONE scalar ``rms / sqrt(mean(batch ** 2))``
+    taken over the un-centred batch (voicemap/utils.py:88-101; SURVEY.md F8 -- not a per-clip RMS)."""
+    batch = np.asarray(batch)
+    if batch.ndim != 3:
+        raise ValueError('Input must be a 3D array of shape (n_segments, n_timesteps, 1).')
+    gain = rms / np.sqrt(np.mean(np.square(batch)))
+    return (batch - batch.mean(axis=1, keepdims=True)) * gain
+
+
+class _InstancePreprocessor(object):
+    """``instances[:, ::downsampling, :]`` then optionally ``whiten`` (voicemap/utils.py:22-34)."""
+
+    def __init__(self, downsampling, whitening):
+        self.downsampling = downsampling
+        self.whitening = whitening
+
+    def __call__(self, instances):
+        out = instances[:, ::self.downsampling, :]
+        return whiten(out) if self.whitening else out
+
 
 def preprocess_instances(downsampling, whitening=True):
-    """This is the canonical preprocessing function for this project (voicemap/utils.py:22-34).
+    """The project's canonical preprocessing (voicemap/utils.py:22-34): plain decimation by ``downsampling``
+    followed by ``whiten``.  Returns a callable taking a (n, timesteps, 1) batch."""
+    return _InstancePreprocessor(downsampling, whitening)
 
-    1. Downsampling audio segments to desired sampling rate (plain decimation)
-    2. Whiten audio segments to 0 mean and fixed RMS (aka volume)
-    """
-    def preprocess_instances_(instances):
-        instances = instances[:, ::downsampling, :]
-        if whitening:
-            instances = whiten(instances)
-        return instances
 
-    return preprocess_instances_
+def _identity(x):
+    return x
 
 
 class BatchPreProcessor(object):
-    """Wrapper class for instance and label pre-processing (voicemap/utils.py:37-74).
+    """Apply one instance preprocessor (and optionally a target preprocessor) to classifier batches
+    ``(inputs, targets)`` or siamese batches ``([input_1, input_2], targets)`` (voicemap/utils.py:37-74)."""
 
-    Pre-processes classifier-style batches (inputs, outputs) and siamese network-style batches
-    ([input_1, input_2], outputs) identically.
-    """
-    def __init__(self, mode, instance_preprocessor, target_preprocessor=lambda x: x):
+    def __init__(self, mode, instance_preprocessor, target_preprocessor=_identity):
         assert mode in ('siamese', 'classifier')
         self.mode = mode
         self.instance_preprocessor = instance_preprocessor
         self.target_preprocessor = target_preprocessor
 
     def __call__(self, batch):
+        inputs, targets = batch
         if self.mode == 'siamese':
-            ([input_1, input_2], labels) = batch
-            input_1 = self.instance_preprocessor(input_1)
-            input_2 = self.instance_preprocessor(input_2)
-            labels = self.target_preprocessor(labels)
-            return [input_1, input_2], labels
+            inputs = [self.instance_preprocessor(side) for side in inputs]
         elif self.mode == 'classifier':
-            instances, labels = batch
-            instances = self.instance_preprocessor(instances)
-            labels = self.target_preprocessor(labels)
-            return instances, labels
+            inputs = self.instance_preprocessor(inputs)
         else:
             raise ValueError
+        return inputs, self.target_preprocessor(targets)
 
 
+# ------------------------------------------------------------------------------------------------ loss
 def contrastive_loss(y_true, y_pred):
-    """Contrastive loss from Hadsell-et-al.'06 (voicemap/utils.py:77-85), margin 1, y: 0 = same speaker.
+    """Hadsell et al. '06 with margin 1 (voicemap/utils.py:77-85): same-speaker pairs (y = 0) pay ``p ** 2``,
+    different-speaker pairs (y = 1) pay ``max(1 - p, 0) ** 2``; mean over the batch.
 
-    Passing this function to ``model.compile(loss=contrastive_loss)`` selects the fused CUDA head+loss kernel;
-    calling it directly evaluates the same expression on numpy arrays."""
+    ``model.compile(loss=contrastive_loss)`` selects the fused CUDA head + loss kernel by identity of this function;
+    a direct call evaluates the same expression with numpy."""
+    y = np.asarray(y_true)
+    p = np.asarray(y_pred)
     margin = 1
-    y_true = np.asarray(y_true)
-    y_pred = np.asarray(y_pred)
-    return np.mean((1 - y_true) * np.square(y_pred) + y_true * np.square(np.maximum(margin - y_pred, 0)))
+    pull = np.square(p)
+    push = np.square(np.clip(margin - p, 0, None))
+    return np.mean((1 - y) * pull + y * push)
 
 
-def whiten(batch, rms=0.038021):
-    """Whiten a batch: per-sample mean removal, then one batch-global scale rms / sqrt(mean(batch**2))
-    (voicemap/utils.py:88-101; the scale is taken over the whole un-centred batch)."""
-    if len(batch.shape) != 3:
-        raise ValueError('Input must be a 3D array of shape (n_segments, n_timesteps, 1).')
-    sample_wise_mean = batch.mean(axis=1, keepdims=True)
-    sample_wise_rescaling = rms / np.sqrt(np.power(batch, 2).mean())
-    return (batch - sample_wise_mean) * sample_wise_rescaling
+# ------------------------------------------------------------------------------------------------ n-shot evaluation
+def _per_class(values, k, n):
+    """Mean over the n shots of each of the k classes; rows are ordered [class 1] * n + ... + [class k] * n."""
+    return values.reshape(k, n, -1).mean(axis=1)
 
 
-def _class_means(embeddings, n, k):
-    return embeddings.reshape(k, n, -1).mean(axis=1)
+def _score_euclidean(query, support, k, n):
+    return np.linalg.norm(_per_class(support, k, n) - query, axis=1)
+
+
+def _score_cosine(query, support, k, n):
+    # cosine distance between the query and the mean of each class's unit vectors (scipy cdist(..., 'cosine'))
+    norms = np.linalg.norm(support, axis=1, keepdims=True)
+    centre = _per_class(support / norms, k, n)
+    return 1.0 - centre.dot(query) / (np.linalg.norm(centre, axis=1) * np.linalg.norm(query))
+
+
+def _score_dot_product(query, support, k, n):
+    # minus the projection of the query on (mean magnitude * mean direction) of each class
+    norms = np.linalg.norm(support, axis=1, keepdims=True)
+    centre = _per_class(support / norms, k, n) * _per_class(norms, k, n)
+    return -centre.dot(query)
+
+
+_SCORES = {'euclidean': _score_euclidean, 'cosine': _score_cosine, 'dot_product': _score_dot_product}
+
+
+def _embedding_network(model, network_type):
+    """The encoder inside ``model``: layer 2 of a siamese net, or a classifier without its softmax layer
+    (voicemap/utils.py:140-147)."""
+    if network_type == 'siamese':
+        return model.layers[2]
+    if network_type == 'classifier':
+        stripped = clone_model(model)
+        stripped.set_weights(model.get_weights())
+        stripped.pop()
+        return stripped
+    raise ValueError('mode must be one of (siamese, classifier)')
+
+
+def _task_inputs(dataset, preprocessor, k, n, pairwise):
+    """Draw one task and preprocess it.  Pairwise (siamese, n = 1): the query repeated k times and the k support
+    clips go through the batch preprocessor as one siamese batch, i.e. each side is whitened on its own
+    (voicemap/utils.py:122-131).  Otherwise query (1 clip) and support (k*n clips) are preprocessed separately
+    (:150-153)."""
+    (query, _), (support, _) = dataset.build_n_shot_task(k, n)
+    support = support[:, :, np.newaxis]
+    if pairwise:
+        repeated = np.repeat(query[np.newaxis, :, np.newaxis], k, axis=0)
+        (left, right), _ = preprocessor(([repeated, support], []))
+        return left, right
+    instance = preprocessor.instance_preprocessor
+    return instance(query.reshape(1, -1, 1)), instance(support)
+
+
+def _solved_pairwise(model, tasks, k):
+    """Tasks whose smallest siamese output belongs to support item 0, scoring all tasks of the list with one
+    encoder launch and one head launch (one task: falls back to ``model.predict`` like the reference)."""
+    if len(tasks) == 1:
+        left, right = tasks[0]
+        return int(np.argmin(model.predict([left, right])[:, 0]) == 0)
+    from .engine import pair_head_loss
+    t = len(tasks)
+    encoder = model.encoder
+    engine = encoder._get_engine()
+    # eval-mode embeddings are independent of batch composition, so the query is embedded once per task
+    clips = np.concatenate([left[:1] for left, _ in tasks] + [right for _, right in tasks], axis=0)
+    emb = engine.forward(encoder._host_batch(clips).to(engine.device, non_blocking=True))
+    width = emb.shape[1]
+    queries = emb[:t, None, :].expand(t, k, width).reshape(t * k, width).contiguous()
+    kernel, bias = model._head_device(engine.device)
+    prob, _, _ = pair_head_loss(queries, emb[t:].contiguous(), kernel, bias, model.distance_metric)
+    return int((prob.reshape(t, k).argmin(dim=1) == 0).sum().item())
+
+
+def _solved_by_embedding(encoder, tasks, k, n, score):
+    """Tasks whose nearest class (under ``score``) is class 0."""
+    if len(tasks) == 1:
+        query, support = tasks[0]
+        embedded = [(encoder.predict(query), encoder.predict(support))]
+    else:
+        t = len(tasks)
+        clips = np.concatenate([q for q, _ in tasks] + [s for _, s in tasks], axis=0)
+        emb = encoder.predict(clips)
+        shots = emb[t:].reshape(t, k * n, -1)
+        embedded = [(emb[i:i + 1], shots[i]) for i in range(t)]
+    return sum(int(np.argmin(score(q[0], s, k, n)) == 0) for q, s in embedded)
 
 
 def n_shot_task_evaluation(model, dataset, preprocessor, num_tasks, n, k, network_type='siamese',
-                           distance='euclidean'):
-    """Evaluate a network on k-way, n-shot classification tasks (voicemap/utils.py:104-216).
+                           distance='euclidean', tasks_per_launch=1):
+    """Number of correctly solved k-way n-shot tasks out of ``num_tasks`` (voicemap/utils.py:104-216).
 
-    Returns the number of correctly solved tasks.  A task is correct when the closest support item / class mean
-    is index 0 (by construction of ``dataset.build_n_shot_task``)."""
-    n_correct = 0
+    A task is solved when support item / class 0 -- the query's speaker by construction of
+    ``dataset.build_n_shot_task`` -- is the closest: for a siamese network and n = 1 by the network's own pairwise
+    output (smallest wins), otherwise by ``distance`` ('euclidean' | 'cosine' | 'dot_product') between the query
+    embedding and the per-class mean embedding.
 
-    if n == 1 and network_type == 'siamese':
-        # Directly use siamese network to get pairwise verification score, minimum is closest
-        for i_eval in tqdm(range(num_tasks)):
-            query_sample, support_set_samples = dataset.build_n_shot_task(k, n)
-            input_1 = np.stack([query_sample[0]] * k)[:, :, np.newaxis]
-            input_2 = support_set_samples[0][:, :, np.newaxis]
-            # Pass an empty list to the labels parameter as preprocessor functions work on batches not samples
-            ([input_1, input_2], _) = preprocessor(([input_1, input_2], []))
-            pred = model.predict([input_1, input_2])
-            if np.argmin(pred[:, 0]) == 0:
-                n_correct += 1
-    elif n > 1 or network_type == 'classifier':
-        # Create encoder network from earlier layers
-        if network_type == 'siamese':
-            encoder = model.layers[2]
-        elif network_type == 'classifier':
-            encoder = clone_model(model)
-            encoder.set_weights(model.get_weights())
-            encoder.pop()
-        else:
-            raise ValueError('mode must be one of (siamese, classifier)')
-
-        for i_eval in tqdm(range(num_tasks)):
-            query_sample, support_set_samples = dataset.build_n_shot_task(k, n)
-            query_instance = preprocessor.instance_preprocessor(query_sample[0].reshape(1, -1, 1))
-            support_set_instances = preprocessor.instance_preprocessor(support_set_samples[0][:, :, np.newaxis])
-
-            query_embedding = encoder.predict(query_instance)
-            support_set_embeddings = encoder.predict(support_set_instances)
-
-            if distance == 'euclidean':
-                # mean position of support set embeddings; labels are [class_1]*n + ... + [class_k]*n
-                mean_support_set_embeddings = _class_means(support_set_embeddings, n, k)
-                pred = np.sqrt(np.power(query_embedding - mean_support_set_embeddings, 2).sum(axis=1))
-            elif distance == 'cosine':
-                magnitudes = np.linalg.norm(support_set_embeddings, axis=1, keepdims=True)
-                unit_vectors = support_set_embeddings / magnitudes
-                mean_units = _class_means(unit_vectors, n, k)
-                q = query_embedding[0]
-                # scipy.spatial.distance.cdist(..., 'cosine')
-                pred = 1.0 - (mean_units @ q) / (np.linalg.norm(mean_units, axis=1) * np.linalg.norm(q))
-            elif distance == 'dot_product':
-                magnitudes = np.linalg.norm(support_set_embeddings, axis=1, keepdims=True)
-                unit_vectors = support_set_embeddings / magnitudes
-                mean_units = _class_means(unit_vectors, n, k)
-                mean_magnitudes = magnitudes.reshape(k, n).sum(axis=1, keepdims=True) / n
-                pred = -np.dot(query_embedding[0, :][np.newaxis, :], (mean_magnitudes * mean_units).T)
-            else:
-                raise ValueError('Distance must be in (euclidean, cosine, dot_product)')
-
-            if np.argmin(pred) == 0:
-                n_correct += 1
+    ``tasks_per_launch`` > 1 (an extension) embeds that many tasks per encoder launch instead of issuing one or two
+    tiny ``predict`` calls per task; tasks are drawn in the same order and scored by the same rule, so the count is
+    the same for the same random state."""
+    if n < 1:
+        raise ValueError('n must be >= 1')
+    pairwise = n == 1 and network_type == 'siamese'
+    if pairwise:
+        encoder, score = None, None
     else:
-        raise ValueError("n must be >= 1")
+        encoder = _embedding_network(model, network_type)
+        if distance not in _SCORES:
+            raise ValueError('Distance must be in (euclidean, cosine, dot_product)')
+        score = _SCORES[distance]
 
+    from tqdm import tqdm
+    n_correct = 0
+    progress = tqdm(total=num_tasks)
+    for first in range(0, num_tasks, max(1, tasks_per_launch)):
+        count = min(max(1, tasks_per_launch), num_tasks - first)
+        tasks = [_task_inputs(dataset, preprocessor, k, n, pairwise) for _ in range(count)]
+        if pairwise:
+            n_correct += _solved_pairwise(model, tasks, k)
+        else:
+            n_correct += _solved_by_embedding(encoder, tasks, k, n, score)
+        progress.update(count)
+    progress.close()
     return n_correct
 
 
 def n_shot_task_evaluation_batched(model, dataset, preprocessor, num_tasks, n, k, network_type='siamese',
                                    distance='euclidean', tasks_per_launch=64):
-    """Same tasks, same preprocessing and same decision rule as ``n_shot_task_evaluation`` but the encoder runs
-    once per ``tasks_per_launch`` tasks instead of 1-2 tiny ``predict`` calls per task (the reference spends its
-    per-epoch evaluation in 500 batch-5 forwards: experiments/train_siamese.py:75-78, voicemap/utils.py:121-137).
-    Eval-mode embeddings do not depend on batch composition, so the count of correct tasks is identical for an
-    identical task sequence (tasks are drawn in the same order, one ``build_n_shot_task`` call each)."""
-    import torch
-    from .engine import pair_head_loss
-    siamese_direct = (n == 1 and network_type == 'siamese')
-    if siamese_direct:
-        encoder = model.encoder
-    elif network_type == 'siamese':
-        encoder = model.layers[2]
-    elif network_type == 'classifier':
-        encoder = clone_model(model)
-        encoder.set_weights(model.get_weights())
-        encoder.pop()
-    else:
-        raise ValueError('mode must be one of (siamese, classifier)')
-    if n < 1:
-        raise ValueError("n must be >= 1")
-    if distance not in ('euclidean', 'cosine', 'dot_product'):
-        raise ValueError('Distance must be in (euclidean, cosine, dot_product)')
-
-    n_correct = 0
-    done = 0
-    while done < num_tasks:
-        t = min(tasks_per_launch, num_tasks - done)
-        queries, supports = [], []
-        for _ in range(t):
-            query_sample, support_set_samples = dataset.build_n_shot_task(k, n)
-            if siamese_direct:
-                # the reference whitens [query]*k and the k supports as two separate batches
-                input_1 = np.stack([query_sample[0]] * k)[:, :, np.newaxis]
-                input_2 = support_set_samples[0][:, :, np.newaxis]
-                ([input_1, input_2], _) = preprocessor(([input_1, input_2], []))
-                queries.append(input_1[:1])
-                supports.append(input_2)
-            else:
-                queries.append(preprocessor.instance_preprocessor(query_sample[0].reshape(1, -1, 1)))
-                supports.append(preprocessor.instance_preprocessor(support_set_samples[0][:, :, np.newaxis]))
-        batch = np.concatenate(queries + supports, axis=0)
-        xt = encoder._host_batch(batch)
-        eng = encoder._get_engine()
-        emb = eng.forward(xt.to(eng.device, non_blocking=True))
-        eq, es = emb[:t], emb[t:].reshape(t, k * n, -1)
-        if siamese_direct:
-            w, b = model._head_device(eng.device)
-            e1 = eq[:, None, :].expand(t, k, eq.shape[1]).reshape(t * k, -1).contiguous()
-            prob, _, _ = pair_head_loss(e1, es.reshape(t * k, -1).contiguous(), w, b, model.distance_metric)
-            n_correct += int((prob.reshape(t, k).argmin(dim=1) == 0).sum().item())
-        else:
-            eqn, esn = eq.cpu().numpy(), es.cpu().numpy()
-            for i in range(t):
-                support_set_embeddings = esn[i]
-                if distance == 'euclidean':
-                    means = _class_means(support_set_embeddings, n, k)
-                    pred = np.sqrt(np.power(eqn[i:i + 1] - means, 2).sum(axis=1))
-                else:
-                    magnitudes = np.linalg.norm(support_set_embeddings, axis=1, keepdims=True)
-                    mean_units = _class_means(support_set_embeddings / magnitudes, n, k)
-                    if distance == 'cosine':
-                        q = eqn[i]
-                        pred = 1.0 - (mean_units @ q) / (np.linalg.norm(mean_units, axis=1) * np.linalg.norm(q))
-                    else:
-                        mean_magnitudes = magnitudes.reshape(k, n).sum(axis=1, keepdims=True) / n
-                        pred = -np.dot(eqn[i][np.newaxis, :], (mean_magnitudes * mean_units).T)
-                if np.argmin(pred) == 0:
-                    n_correct += 1
-        done += t
-    return n_correct
+    """``n_shot_task_evaluation`` with many tasks per encoder launch (the reference spends its per-epoch evaluation in
+    500 batch-5 forwards: experiments/train_siamese.py:75-78)."""
+    return n_shot_task_evaluation(model, dataset, preprocessor, num_tasks, n, k, network_type=network_type,
+                                  distance=distance, tasks_per_launch=tasks_per_launch)
 
 
 class NShotEvaluationCallback(Callback):
-    """Evaluate a network on n-shot classification tasks after every epoch (voicemap/utils.py:219-252)."""
+    """After every epoch, run ``num_tasks`` k-way n-shot tasks on ``dataset`` and publish the accuracy as
+    ``logs['val_{n}-shot_acc']`` for the callbacks that follow in the list (voicemap/utils.py:219-252).
+    ``batch_tasks`` > 0 (an extension) evaluates that many tasks per encoder launch."""
 
-    def __init__(self, num_tasks, n_shot, k_way, dataset, preprocessor=lambda x: x, mode='siamese', batch_tasks=0):
+    def __init__(self, num_tasks, n_shot, k_way, dataset, preprocessor=_identity, mode='siamese', batch_tasks=0):
         super(NShotEvaluationCallback, self).__init__()
-        self.batch_tasks = batch_tasks  # > 0: evaluate that many tasks per encoder launch (same result)
-        self.num_tasks = num_tasks
-        self.n_shot = n_shot
-        self.k_way = k_way
+        assert mode in ('siamese', 'classifier')
+        self.num_tasks, self.n_shot, self.k_way = num_tasks, n_shot, k_way
         self.dataset = dataset
         self.preprocessor = preprocessor
-        assert mode in ('siamese', 'classifier')
         self.mode = mode
+        self.batch_tasks = batch_tasks
 
     def on_epoch_end(self, epoch, logs=None):
-        logs = logs if logs is not None else {}
-        if self.batch_tasks > 0:
-            n_correct = n_shot_task_evaluation_batched(self.model, self.dataset, self.preprocessor, self.num_tasks,
-                                                       self.n_shot, self.k_way, network_type=self.mode,
-                                                       tasks_per_launch=self.batch_tasks)
-        else:
-            n_correct = n_shot_task_evaluation(self.model, self.dataset, self.preprocessor, self.num_tasks,
-                                               self.n_shot, self.k_way, network_type=self.mode)
-        n_shot_acc = n_correct * 1. / self.num_tasks
-        logs['val_{}-shot_acc'.format(self.n_shot)] = n_shot_acc
-        print('val_{}-shot_acc: {:.4f}'.format(self.n_shot, n_shot_acc))
+        solved = n_shot_task_evaluation(self.model, self.dataset, self.preprocessor, self.num_tasks, self.n_shot,
+                                        self.k_way, network_type=self.mode,
+                                        tasks_per_launch=max(1, self.batch_tasks))
+        key = 'val_{}-shot_acc'.format(self.n_shot)
+        accuracy = solved / float(self.num_tasks)
+        if logs is not None:
+            logs[key] = accuracy
+        print('{}: {:.4f}'.format(key, accuracy))
