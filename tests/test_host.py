@@ -417,3 +417,82 @@ def test_empty_batches_give_empty_results_without_a_device():
     assert sia.predict([np.zeros((0, 4000, 1)), np.zeros((0, 4000, 1))]).shape == (0, 1)
     with pytest.raises(ValueError):
         sia.predict([np.zeros((0, 4000, 1)), np.zeros((0, 3000, 1))])
+
+
+def test_corpus_indexing_from_disk_and_cache(tmp_path):
+    """SPEAKERS.TXT parsing, the <subset>/<speaker>/<chapter>/*.flac walk, the per-subset CSV cache and the length
+    filter (voicemap/librispeech.py:43-101, 243-281), on a miniature corpus written here."""
+    from voicemap_b200.librispeech import LibriSpeechDataset, read_speaker_table
+    root = tmp_path / "data" / "LibriSpeech"
+    lengths = {}
+    for spk, chapters in ((14, (100, 101)), (16, (200,)), (17, (300,))):
+        for ch in chapters:
+            d = root / "dev-clean" / str(spk) / str(ch)
+            d.mkdir(parents=True)
+            for u in range(3):
+                p = d / f"{spk}-{ch}-{u:04d}.flac"
+                p.write_bytes(b"")
+                lengths[str(p)] = 16000 * (1 + u)        # 1 s, 2 s, 3 s
+            (d / f"{spk}-{ch}.trans.txt").write_text("not audio")
+    (root / "SPEAKERS.TXT").write_text(
+        "; comment\n;ID  |SEX| SUBSET           |MINUTES| NAME\n"
+        "14   | F | dev-clean  | 25.03 | Reader One\n"
+        "16   | M | dev-clean  | 25.11 | Reader Two\n"
+        "17   | M | dev-clean  | 25.04 | Reader | With | Pipes\n"      # malformed: dropped, like read_csv does
+        "19   | F | train-clean-100  | 25.19 | Elsewhere\n")
+    table = read_speaker_table(str(root / "SPEAKERS.TXT"))
+    assert table["id"].tolist() == [14, 16, 19] and table["sex"].tolist() == ["F", "M", "F"]
+    assert table["subset"].tolist() == ["dev-clean", "dev-clean", "train-clean-100"]
+
+    calls = []
+
+    def reader(path):
+        calls.append(path)
+        return np.zeros(lengths[path]), 16000
+
+    ds = LibriSpeechDataset("dev-clean", 1.5, reader=reader, data_path=str(tmp_path))
+    # speakers 14 (2 chapters) and 16 (1 chapter) survive the merge; of 9 files the 1 s ones are too short
+    assert len(ds) == 6 and ds.num_classes() == 2 and ds.unique_speakers == 2
+    assert set(ds.df.columns) >= {"speaker_id", "speaker_minutes", "sex", "subset", "name", "filepath", "length",
+                                  "seconds", "id"}
+    assert ds.df["id"].tolist() == list(range(6)) and set(ds.df["speaker_id"]) == {14, 16}
+    assert (tmp_path / "data" / "dev-clean.index.csv").exists()
+    decoded = len(calls)
+    assert decoded == 12                                   # every .flac once (speaker 17's too), no .txt
+    again = LibriSpeechDataset(["dev-clean"], 0.5, reader=reader, data_path=str(tmp_path))
+    assert len(calls) == decoded and len(again) == 9       # served by the cache; shorter minimum keeps all files
+    x, label = again[0]
+    assert x.shape == (8000,) and label in (14, 16)
+
+
+def test_pair_draws_follow_the_reference_distribution():
+    """Alike pairs: uniform over (anchor, same-speaker file) combinations, the anchor itself included; differing pairs
+    never share a speaker; draws prefer long files (voicemap/librispeech.py:143-167)."""
+    ds = _fake_dataset(n_speakers=6, files_per_speaker=4)
+    np.random.seed(3)
+    spk = ds.df["speaker_id"].to_numpy()
+    same_file = 0
+    for _ in range(200):
+        pairs = ds.get_alike_pairs(3)
+        assert len(pairs) == 3 and all(spk[a] == spk[b] for a, b in pairs)
+        same_file += sum(a == b for a, b in pairs)
+        assert all(spk[a] != spk[b] for a, b in ds.get_differing_pairs(3))
+    assert 0.15 < same_file / 600.0 < 0.35                 # 1 in 4 partners is the anchor itself
+    ds._weight[:] = 1.0
+    ds._weight[5] = 1e6
+    assert all(5 in ds._draw(2) for _ in range(20))
+
+
+def test_n_shot_evaluation_batched_equals_per_task_calls():
+    ds = _fake_dataset()
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4))
+    for n, k, dist in ((2, 3, "euclidean"), (3, 2, "cosine"), (2, 4, "dot_product")):
+        np.random.seed(11)
+        one = utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 7, n, k, distance=dist)
+        np.random.seed(11)
+        many = utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 7, n, k, distance=dist, tasks_per_launch=3)
+        assert one == many
+    with pytest.raises(ValueError):
+        utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 2, 2, 3, distance="manhattan")
+    with pytest.raises(ValueError):
+        utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 2, 2, 3, network_type="other")
