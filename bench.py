@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--length", type=int, default=12000, help="samples per clip entering the encoder")
-    ap.add_argument("--precision", type=int, default=3, choices=[1, 3],
+    ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
                     help="3: fp16x3 split (fp32-grade, parity mode); 1: fp16x1 (throughput mode)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -312,9 +312,13 @@ def run_b200(args):
             achieved=round(achieved_tf, 1), peak=peaks["bf16_tflops"], unit="TFLOP/s",
             frac=round(achieved_tf / peaks["bf16_tflops"], 4),
             peak_source=peaks["source"] + ", burst bf16 figure",
-            note=("achieved counts ALGORITHMIC flops 2*L*K*Cin*Cout once; precision=3 issues 3 fp16 MMAs per "
-                  "algorithmic MAC (fp32-grade split), so tensor-pipe utilisation is 3x this fraction"
-                  if args.precision == 3 else "precision=1: one fp16 MMA per algorithmic MAC"),
+            note="achieved counts ALGORITHMIC flops 2*L*K*Cin*Cout once; " + {
+                3: "precision=3 issues 3 fp16 MMAs per algorithmic MAC (fp32-grade split), so tensor-pipe time is 3x "
+                   "this fraction",
+                2: "precision=2 issues one fp16 MMA plus one fp8 MMA over a doubled K (both correction products as "
+                   "e5m2 byte pairs, fp8 runs at twice the fp16 rate) per algorithmic MAC, so tensor-pipe time is 2x "
+                   "this fraction",
+                1: "precision=1: one fp16 MMA per algorithmic MAC (not a parity mode)"}[args.precision],
             mma_issue_frac=round(achieved_tf * args.precision / peaks["bf16_tflops"], 4),
             # dram__bytes_read + dram__bytes_write of the three conv3 launches (ncu --set full, profiles/r01_ncu_summary.md:
             # 738 + 651 + 304 MB at batch 256) averaged per launch; algorithmic bytes per launch average 590 MB
@@ -331,7 +335,9 @@ def run_b200(args):
         line = dict(
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
             ms_per_step=round(ms_step, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="fp16x3->f32 (fp32-grade split on fp16 tensor cores)" if args.precision == 3 else "fp16 (fp32 accumulate)",
+            dtype={3: "fp16x3->f32 (fp32-grade split on fp16 tensor cores)",
+                   2: "fp16+fp8(e5m2 pairs)->f32 (split precision: fp16 main product, fp8 correction product, fp32 accumulate)",
+                   1: "fp16 (fp32 accumulate)"}[args.precision],
             data="synthetic",
             config=dict(workload=f"baseline 1D-CNN encoder fwd (eval), filters={FILTERS}, emb={EMB}, batch={n} clips/GPU, "
                                  f"{length} samples/clip (3 s @ 16 kHz {'raw' if length == 48000 else 'after the reference x4 decimation'}), "

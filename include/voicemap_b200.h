@@ -15,7 +15,11 @@
  *   - "planes": an fp32 tensor carried as two fp16 tensors of the same shape, x = hi + lo (~22 significant
  *     bits).  This is the inter-block activation format (4 bytes/element, same HBM traffic as fp32) and lets the
  *     fp16 tensor cores produce fp32-grade results with three MMAs per K step (`precision` = 3).  `precision` = 1
- *     uses the hi plane only (throughput mode; lo pointers may be NULL).
+ *     uses the hi plane only (throughput mode; lo pointers may be NULL).  `precision` = 2 keeps the fp16 hi plane
+ *     and replaces the lo plane by a "Q" plane of the same shape: 16 bits per element holding two e5m2 numbers
+ *     {e5m2(x * 2^-6), e5m2((x - hi) * 2^6)}; the two small correction products of the split scheme then run as ONE
+ *     fp8 tensor-core product over those byte pairs (8 instead of 12 MMAs per K chunk) -- embeddings stay within
+ *     ~4e-5 of the fp64 oracle (tolerance 1e-4), see DESIGN.md section 2.  A forward-pass (eval) mode.
  *   - requires an sm_100a device (B200).
  */
 #ifndef VOICEMAP_B200_H
@@ -47,7 +51,7 @@ int vm_check_device(void);
 
 /* ---- sizes (host-side arithmetic only) ------------------------------------------------------------------- */
 size_t vm_conv1_wpack_bytes(int cout);          /* packed block-1 weights */
-size_t vm_conv3_wpack_bytes(int cin, int cout); /* packed block-2..4 weights */
+size_t vm_conv3_wpack_bytes(int cin, int cout); /* packed block-2..4 weights: fp16 hi, fp16 lo and e5m2x2 Q planes */
 size_t vm_epi_bytes(int cout);                  /* per-channel epilogue constants (padded to 128 channels) */
 int vm_conv3_num_position_tiles(int L);         /* T of the gmax_partial tensor: 2 * ceil(L / 256) */
 int vm_padded_channels(int cout);
@@ -99,6 +103,9 @@ int vm_pair_head_loss_fwd(const float* e1, const float* e2, int N, int E, int me
 /* ---- plane conversion (per-block fp32 views for callers and tests) ---------------------------------------- */
 int vm_split_planes(const float* x, size_t n, uint16_t* hi, uint16_t* lo, void* stream);
 int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, void* stream);
+/* the same for precision 2: (fp16 hi, e5m2x2 Q) planes; merging decodes hi + residual byte */
+int vm_split_planes_q(const float* x, size_t n, uint16_t* hi, uint16_t* q, void* stream);
+int vm_merge_planes_q(const uint16_t* hi, const uint16_t* q, size_t n, float* x, void* stream);
 
 /* ---- whole encoder (voicemap/models.py:6-41, eval mode) ---------------------------------------------------
  * x (N, L) fp32 -> emb (N, E).  `wpack[i]`, `epi[i]` (i = 0..3) from vm_pack_conv1 / vm_pack_conv3 for channel

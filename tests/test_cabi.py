@@ -32,7 +32,7 @@ def test_size_helpers(built_library):
     lib = _lib.load()
     assert lib.vm_padded_channels(128) == 128 and lib.vm_padded_channels(192) == 256
     assert lib.vm_conv1_wpack_bytes(128) == 16384
-    assert lib.vm_conv3_wpack_bytes(128, 256) == 2 * 3 * 256 * 128 * 2
+    assert lib.vm_conv3_wpack_bytes(128, 256) == 3 * 3 * 256 * 128 * 2   # planes: fp16 hi, fp16 lo, e5m2x2 Q
     assert lib.vm_epi_bytes(384) == 384 * 16
     assert lib.vm_conv3_num_position_tiles(3000) == 24
     # workspace: planes of the three stored activations + gmax partials (fp16 hi+lo = 4 bytes/element)

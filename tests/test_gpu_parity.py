@@ -1,7 +1,10 @@
 """Parity tests proper (GPU box): the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the
 same seeded inputs, against the committed golden fixture, and -- at BASELINE.json's full batch -- through
 size-independent properties.  Tolerance (north_star / SURVEY.md 8(d)): per-clip ||e_gpu - e_ref|| / ||e_ref|| <= 1e-4
-and max|d| / max|e_ref| <= 1e-4 against the fp32 oracle in parity mode (precision 3)."""
+and max|d| / max|e_ref| <= 1e-4 against the fp32 oracle in both parity modes: precision 3 (fp16 x 3, measured ~7e-6)
+and precision 2 (fp16 + one e5m2-pair fp8 correction product, the default of predict(); measured 1e-5 .. 4.5e-5).
+Per-block tests run precision 3 at fp32-grade tolerances, plus precision 2 at its own (the merged view of a
+precision-2 plane pair carries ~14 bits)."""
 import os
 
 import numpy as np
@@ -78,6 +81,43 @@ def test_block234_parity_incl_ragged_lengths(stress_params, block, n, length):
         assert _rel(g.cpu().numpy(), ref.max(axis=1)) < 2e-5
 
 
+@pytest.mark.parametrize("block,n,length", [(2, 2, 512), (2, 3, 499), (3, 2, 300), (4, 2, 750), (4, 3, 187)])
+def test_block234_precision2_incl_ragged_lengths(stress_params, block, n, length):
+    """precision 2: Xh*Wh on the fp16 pipe + (Xl*Wh + Xh*Wl) as one fp8 product over e5m2 byte pairs."""
+    eng = _engine(128, 64, stress_params, precision=2)
+    cin = 128 * (block - 1)
+    rng = np.random.default_rng(block * 100 + length)
+    x = (rng.normal(0, 1.0, (n, length, cin)) * rng.uniform(0.1, 3.0, (1, 1, cin))).astype(np.float32)
+    hi, q = eng.split_planes(torch.from_numpy(x).cuda())
+    ref = _block_ref(x, stress_params, block, torch.float64)
+    if block < 4:
+        oh, oq = eng.block3(block, hi, q)
+        got = eng.merge_planes(oh, oq).cpu().numpy()
+        assert got.shape == ref.shape == (n, length // 2, 128 * block)
+        assert _rel(got, ref) < 1e-4
+    else:
+        part = eng.block3(4, hi, q, gmax=True)
+        emb, g = eng.gmax_dense(part, with_gmax=True)
+        assert _rel(g.cpu().numpy(), ref.max(axis=1)) < 1e-4
+
+
+def test_precision2_plane_pair_semantics():
+    """(hi, Q): hi = fp16(x); Q = {e5m2(x / 64), e5m2((x - hi) * 64)} (upper, lower byte)."""
+    from voicemap_b200.engine import EncoderEngine
+    eng = EncoderEngine(128, 64, precision=2)
+    x = torch.randn(1 << 14, device="cuda") * torch.logspace(-2, 3, 1 << 14, device="cuda")
+    hi, q = eng.split_planes(x)
+    assert torch.equal(hi, x.to(torch.float16))
+    qb = q.view(torch.uint8).reshape(-1, 2)                      # little endian: [lower, upper]
+    lower = qb[:, 0].contiguous().view(torch.float8_e5m2).float()
+    upper = qb[:, 1].contiguous().view(torch.float8_e5m2).float()
+    resid = (x - hi.float()) * 64.0
+    assert ((lower - resid).abs() <= 0.126 * resid.abs() + 2.0 ** -17).all()
+    assert ((upper - x / 64.0).abs() <= 0.126 * (x / 64.0).abs() + 2.0 ** -17).all()
+    back = eng.merge_planes(hi, q)
+    assert ((back - x).abs() <= 2.0 ** -13 * x.abs() + 2.0 ** -22).all()
+
+
 def test_planes_roundtrip_is_fp32_grade():
     from voicemap_b200.engine import EncoderEngine
     eng = EncoderEngine(128, 64)
@@ -88,11 +128,12 @@ def test_planes_roundtrip_is_fp32_grade():
     assert rel < 2.0 ** -21
 
 
+@pytest.mark.parametrize("precision", [2, 3])
 @pytest.mark.parametrize("n,length,padded", [(8, 12000, False), (8, 12000, True), (5, 11999, False), (3, 6000, True),
                                              (2, 48000, False), (4, 4000, False)])
-def test_encoder_parity_config0_and_lengths(stress_params, n, length, padded):
+def test_encoder_parity_config0_and_lengths(stress_params, n, length, padded, precision):
     """BASELINE config[0] (batch 8, 3 s) plus the reference's n_seconds sweep lengths and a raw 16 kHz clip."""
-    eng = _engine(128, 64, stress_params)
+    eng = _engine(128, 64, stress_params, precision)
     x = O.synthetic_clips(n, length, seed=1234, padded=padded)
     got = eng.forward(torch.from_numpy(x[:, :, 0].copy()).cuda()).cpu().numpy()
     ref32 = O.encoder_forward(x, stress_params, torch.float32)
@@ -101,9 +142,10 @@ def test_encoder_parity_config0_and_lengths(stress_params, n, length, padded):
     assert _per_clip(got, ref64) <= TOL
 
 
-def test_encoder_parity_keras_default_init():
+@pytest.mark.parametrize("precision", [2, 3])
+def test_encoder_parity_keras_default_init(precision):
     params = O.init_encoder_params(128, 64, seed=7)  # gamma 1, beta 0, mean 0, var 1, zero biases
-    eng = _engine(128, 64, params)
+    eng = _engine(128, 64, params, precision)
     x = O.synthetic_clips(4, 12000, seed=99)
     got = eng.forward(torch.from_numpy(x[:, :, 0].copy()).cuda()).cpu().numpy()
     ref = O.encoder_forward(x, params, torch.float32)
@@ -118,6 +160,8 @@ def test_golden_fixture():
     x = torch.from_numpy(z["x"][:, :, 0].copy()).cuda()
     got = eng.forward(x).cpu().numpy()
     assert _per_clip(got, z["emb64"]) <= TOL and _per_clip(got, z["emb32"]) <= TOL
+    got2 = _engine(int(z["filters"]), int(z["emb"]), params, precision=2).forward(x).cpu().numpy()
+    assert _per_clip(got2, z["emb64"]) <= TOL and _per_clip(got2, z["emb32"]) <= TOL
     hi, lo = eng.block1(x)
     b1 = eng.merge_planes(hi, lo).cpu().numpy()
     assert _rel(b1[:, :40, :], z["block1_sample"]) < 1e-5
@@ -237,12 +281,13 @@ def test_full_batch_properties(stress_params):
     assert torch.equal(eng.forward(x), full)
 
 
+@pytest.mark.parametrize("precision", [2, 3])
 @pytest.mark.parametrize("filters,emb", [(16, 32), (32, 64), (64, 128), (256, 64), (512, 512)])
-def test_encoder_parity_filter_sweep(filters, emb):
+def test_encoder_parity_filter_sweep(filters, emb, precision):
     """grid_search_siamese_network.py:23-25 sweeps filters in [16, 32, 64, 128] and embedding in [32..512]; 256 and
     512 are the stretch widths of SURVEY.md 8(d) C5 (block 4 then has 2048 output channels = 16 cout slabs)."""
     params = O.init_encoder_params(filters, emb, seed=filters, randomize_bn=True, random_bias=True)
-    eng = _engine(filters, emb, params)
+    eng = _engine(filters, emb, params, precision)
     x = O.synthetic_clips(3, 6000, seed=8)
     got = eng.forward(torch.from_numpy(x[:, :, 0].copy()).cuda()).cpu().numpy()
     ref = O.encoder_forward(x, params, torch.float32)
@@ -332,6 +377,8 @@ def test_first_pool_2_architecture_matches_oracle(stress_params, n, length):
     enc.set_named_weights(stress_params)
     x = O.synthetic_clips(n, length, seed=77 + length, padded=(length == 12000))
     ref = O.encoder_forward(x, stress_params, torch.float32, pools=(2, 2, 2, 2))
+    assert _per_clip(enc.predict(x), ref) <= TOL
+    enc.precision, enc._engine = 3, None        # fp16 (hi, lo) planes: the merged block output is fp32-grade
     assert _per_clip(enc.predict(x), ref) <= TOL
     eng = enc._get_engine()
     hi, lo = eng.block1(torch.from_numpy(x[:, :, 0].astype(np.float32)).cuda())

@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--l", type=int, default=2048)
     ap.add_argument("--filters", type=int, default=128)
     ap.add_argument("--emb", type=int, default=64)
-    ap.add_argument("--precision", type=int, default=3)
+    ap.add_argument("--precision", type=int, default=2)
     ap.add_argument("--block", type=int, default=2)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--randbn", type=int, default=1)

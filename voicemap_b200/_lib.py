@@ -41,6 +41,8 @@ SIGNATURES = {
     "vm_pair_head_loss_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "vm_split_planes": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "vm_merge_planes": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "vm_split_planes_q": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "vm_merge_planes_q": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "vm_encoder_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "vm_encoder_fwd": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "vm_set_option": (_i, [C.c_char_p, _i]),

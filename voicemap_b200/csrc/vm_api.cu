@@ -115,7 +115,7 @@ int vm_check_device(void) {
 
 int vm_padded_channels(int cout) { return (cout + 127) / 128 * 128; }
 size_t vm_conv1_wpack_bytes(int cout) { return size_t(vm_padded_channels(cout)) / 128 * 16384; }
-size_t vm_conv3_wpack_bytes(int cin, int cout) { return size_t(2) * 3 * vm_padded_channels(cout) * cin * 2; }
+size_t vm_conv3_wpack_bytes(int cin, int cout) { return size_t(3) * 3 * vm_padded_channels(cout) * cin * 2; }  // hi, lo, q
 size_t vm_epi_bytes(int cout) { return size_t(vm_padded_channels(cout)) * 16; }
 int vm_conv3_num_position_tiles(int L) { return 2 * ((L + 255) / 256); }
 
@@ -142,7 +142,7 @@ int vm_conv1_relu_bn_pool_fwd(const float* x, int N, int L, int cout, int pool, 
                               uint16_t* out_hi, uint16_t* out_lo, int precision, void* stream) {
   if (x == nullptr || wpack == nullptr || epi == nullptr || out_hi == nullptr)
     return set_error(VM_ERR_SHAPE, "conv1: null pointer");
-  if (precision == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 3");
+  if (precision >= 2 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 2 / 3");
   return launch_conv1(x, N, L, cout, wpack, epi, reinterpret_cast<__half*>(out_hi),
                       reinterpret_cast<__half*>(out_lo), nullptr, nullptr, precision, g_max_ctas,
                       (cudaStream_t)stream, 1, 0, nullptr, nullptr, pool);
@@ -152,8 +152,8 @@ int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int
                                const void* wpack, const float* epi, uint16_t* out_hi, uint16_t* out_lo,
                                float* gmax_partial, int precision, void* stream) {
   if (in_hi == nullptr || wpack == nullptr || epi == nullptr) return set_error(VM_ERR_SHAPE, "conv3: null pointer");
-  if (gmax_partial == nullptr && precision == 3 && out_lo == nullptr)
-    return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 3");
+  if (gmax_partial == nullptr && precision >= 2 && out_lo == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 2 / 3");
   return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
                       static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
                       reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, 0, precision, g_max_ctas,
@@ -185,6 +185,15 @@ int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, 
   if (x == nullptr || hi == nullptr) return set_error(VM_ERR_SHAPE, "merge_planes: null pointer");
   return launch_merge_planes(reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), n, x,
                              (cudaStream_t)stream);
+}
+
+int vm_split_planes_q(const float* x, size_t n, uint16_t* hi, uint16_t* q, void* stream) {
+  if (x == nullptr || hi == nullptr || q == nullptr) return set_error(VM_ERR_SHAPE, "split_planes_q: null pointer");
+  return launch_split_planes_q(x, n, reinterpret_cast<__half*>(hi), q, (cudaStream_t)stream);
+}
+int vm_merge_planes_q(const uint16_t* hi, const uint16_t* q, size_t n, float* x, void* stream) {
+  if (x == nullptr || hi == nullptr || q == nullptr) return set_error(VM_ERR_SHAPE, "merge_planes_q: null pointer");
+  return launch_merge_planes_q(reinterpret_cast<const __half*>(hi), q, n, x, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

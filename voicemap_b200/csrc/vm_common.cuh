@@ -199,6 +199,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4: the same shared-memory descriptors, but the 32 operand bytes per row that one instruction consumes are
+// 32 fp8 K elements instead of 16 fp16 ones -- twice the MACs per instruction at the same instruction time
+// (measured: an f8f6f4 MMA of M=128, N=256 issues at the rate of the f16 one, profiles/r01_f8_rate_probe.log).
+// Formats (cute::UMMA::F8F6F4Format): 0 = e4m3, 1 = e5m2.
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N, int a_fmt = 1, int b_fmt = 1) {
+  return (1u << 4) | (uint32_t(a_fmt & 7) << 7) | (uint32_t(b_fmt & 7) << 10) | (uint32_t(N >> 3) << 17) |
+         (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All MMAs issued so far by this thread -> one arrive on `bar` when they have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -323,6 +342,36 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
   hi = __bfloat16_as_ushort(h);
   lo = __bfloat16_as_ushort(l);
 }
+// ---------------------------------------------------------------------------------------------
+// "Q" planes (precision 2): the two correction products of the split scheme, Xl*Wh + Xh*Wl, only need a few bits, so
+// they run as ONE kind::f8f6f4 product over a doubled K: every fp32 value carries, next to its fp16 `hi`, a 16-bit
+// pair of e5m2 numbers {upper, lower} and the MMA contracts lower*lower + upper*upper over the byte pairs:
+//   activations: lower = e5m2((x - hi) * 2^6)   upper = e5m2(x * 2^-6)
+//   weights:     lower = e5m2(w * 2^-6)          upper = e5m2((w - hi) * 2^6)
+// so that lower*lower ~ Xl*W and upper*upper ~ X*Wl land in the accumulator at scale 1 (e5m2 has fp16's exponent
+// range, so the residuals 2^-12 below their values stay normal; e4m3 would need a second accumulator).  Error of the
+// corrections ~2^-3.5 of a 2^-12 term: embeddings 1e-5 .. 4e-5 from the fp64 oracle (tools/sim_split_precision.py).
+// ---------------------------------------------------------------------------------------------
+static constexpr float kQUp = 64.f, kQDown = 1.f / 64.f;
+__device__ __forceinline__ uint16_t pack_e5m2x2(float upper, float lower) {
+  uint16_t d;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(d) : "f"(upper), "f"(lower));
+  return d;
+}
+__device__ __forceinline__ void split_f16_q(float x, __half& hi, uint16_t& q) {
+  hi = __float2half_rn(x);
+  q = pack_e5m2x2(x * kQDown, (x - __half2float(hi)) * kQUp);
+}
+__device__ __forceinline__ void split_w_q(float w, __half& hi, uint16_t& q) {
+  hi = __float2half_rn(w);
+  q = pack_e5m2x2((w - __half2float(hi)) * kQUp, w * kQDown);
+}
+// decode of an activation pair: hi + lower / 2^6 (tests / plane merging)
+__device__ __forceinline__ float e5m2_to_float(uint32_t byte) { return __half2float(__ushort_as_half(uint16_t(byte << 8))); }
+__device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(uint32_t(b) << 16); }
 
 }  // namespace vm

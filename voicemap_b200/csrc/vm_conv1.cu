@@ -170,9 +170,10 @@ __device__ __forceinline__ void toeplitz_block_store(float (&v)[15], uint32_t ds
 // 32 accumulator columns of one channel -> 32 / kPool pooled outputs (MaxPool kPool) -> bias/ReLU/BN -> fp16 (hi, lo)
 // -> staging rows sh/sl + j * 128.  Both clamp forms are evaluated and one is selected: measured faster than
 // branching on no_hi inside the pipelined loop (profiles/r01_conv1_epilogue_ab.log: 0.097 vs 0.111 ms per launch).
-template <int kPool>
+// kSecond: second output plane -- 0 none, 1 fp16 residual, 2 e5m2x2 Q pair (precision 2, vm_common.cuh).
+template <int kPool, int kSecond>
 __device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32], uint32_t sh,
-                                              uint32_t sl, int nplanes) {
+                                              uint32_t sl) {
 #pragma unroll
   for (int j = 0; j < 32 / kPool; ++j) {
     float y;
@@ -184,11 +185,25 @@ __device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, cons
       const float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
       y = no_hi ? apply_epi_pool2<false>(ep, v0, v1) : apply_epi_pool2<true>(ep, v0, v1);
     }
-    __half h, l;
-    split_f32(y, h, l);
+    __half h;
+    if (kSecond == 2) {
+      uint16_t q;
+      split_f16_q(y, h, q);
+      sts_b16(sl + j * 128, q);
+    } else {
+      __half l;
+      split_f32(y, h, l);
+      if (kSecond == 1) sts_u16(sl + j * 128, l);
+    }
     sts_u16(sh + j * 128, h);
-    if (nplanes == 2) sts_u16(sl + j * 128, l);
   }
+}
+template <int kPool>
+__device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32], uint32_t sh,
+                                              uint32_t sl, int second) {
+  if (second == 2) pool_epilogue<kPool, 2>(ep, no_hi, r, sh, sl);
+  else if (second == 1) pool_epilogue<kPool, 1>(ep, no_hi, r, sh, sl);
+  else pool_epilogue<kPool, 0>(ep, no_hi, r, sh, sl);
 }
 
 template <int kPool>
@@ -207,7 +222,8 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntiles = p.N * p.nptile;
-  const int nplanes = (p.products == 3) ? 2 : 1;
+  const int nplanes = (p.products >= 2) ? 2 : 1;       // block 1 itself always runs fp16 x 3 for products >= 2
+  const int second = (p.products == 2) ? 2 : nplanes - 1;   // format of the second output plane
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -395,7 +411,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
               tmem_ld_wait(ra);
               tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
               pool_epilogue<kPool>(ep, no_hi, ra, st_h + row0 + gg * kOutPerLoad * 128,
-                                   st_l + row0 + gg * kOutPerLoad * 128, nplanes);
+                                   st_l + row0 + gg * kOutPerLoad * 128, second);
               tmem_ld_wait(rb);
               if (gg + 2 < kLoads) {
                 tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
@@ -404,7 +420,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
                 mbar_arrive(&bars->tempty[buf]);
               }
               pool_epilogue<kPool>(ep, no_hi, rb, st_h + row0 + (gg + 1) * kOutPerLoad * 128,
-                                   st_l + row0 + (gg + 1) * kOutPerLoad * 128, nplanes);
+                                   st_l + row0 + (gg + 1) * kOutPerLoad * 128, second);
             }
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 256);
@@ -447,7 +463,8 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   if (pool != 2 && pool != 4) return set_error(VM_ERR_UNSUPPORTED, "conv1: first MaxPool1D size must be 2 or 4");
   if (N <= 0 || L < pool) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= pool size");
   if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
-  if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv1: products must be 1 or 3");
+  if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "conv1: products must be 1, 2 or 3");
+  if (products == 2 && out_f32 != nullptr) products = 3;   // the un-pooled fp32 output has no second plane
   const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
   const int nslab = cout_pad / kTileM;
   if (nslab > kMaxSlabs) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout > 512 not supported");
@@ -475,13 +492,13 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
     ol = oh;
   } else {
     if (out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv1: no output given");
-    if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products=3");
+    if (products >= 2 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products>=2");
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};
     const uint32_t obox[3] = {64, 64, 1};
     int rc;
     if ((rc = make_tensor_map(&oh, out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE))) return rc;
-    if ((rc = make_tensor_map(&ol, products == 3 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
+    if ((rc = make_tensor_map(&ol, products >= 2 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
       return rc;
   }
   const int smem = smem_bytes(nslab, p.nstages);

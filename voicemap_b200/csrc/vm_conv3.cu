@@ -10,7 +10,9 @@
 //
 // fp32-grade accuracy from fp16 tensor cores: every fp32 operand is carried as two fp16 planes (hi, lo) with
 // x = hi + lo to ~2^-22; D = Xh*Wh + Xl*Wh + Xh*Wl (three MMAs per K step, fp32 accumulate).  `products == 1`
-// keeps only Xh*Wh (throughput mode, ~2^-11 operand rounding).
+// keeps only Xh*Wh (throughput mode, ~2^-11 operand rounding).  `products == 2` computes the two correction products
+// as ONE kind::f8f6f4 MMA over e5m2 byte pairs (the "Q" planes of vm_common.cuh: K doubles, the instruction count per
+// K chunk drops from 12 to 8), which is enough for them because they are 2^-12 of the main term.
 //
 // Epilogue (4 warps, thread = one cout channel, columns = consecutive positions): pooling is done on the raw
 // accumulators first -- weights of channels with a negative BN scale are packed negated (sigma = -1) so that
@@ -49,6 +51,27 @@ struct __align__(8) Conv3Barriers {
   uint32_t tmem_base;
 };
 
+// 16 accumulator columns of one channel -> 8 pooled outputs -> bias/ReLU/BN clamp form -> staging rows.
+// kSecond: 0 = hi plane only, 1 = fp16 residual plane, 2 = e5m2x2 Q plane.
+template <bool kClampHi, int kSecond>
+__device__ __forceinline__ void pooled_granule(const float4& ep, const float (&v)[16], uint32_t st_h, uint32_t st_l) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float y = apply_epi_pool2<kClampHi>(ep, v[2 * j], v[2 * j + 1]);
+    __half h;
+    if (kSecond == 2) {
+      uint16_t q;
+      split_f16_q(y, h, q);
+      sts_b16(st_l + j * 128, q);
+    } else {
+      __half l;
+      split_f32(y, h, l);
+      if (kSecond == 1) sts_u16(st_l + j * 128, l);
+    }
+    sts_u16(st_h + j * 128, h);
+  }
+}
+
 __global__ void __launch_bounds__(c3::kThreads, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
@@ -66,7 +89,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntiles = p.N * p.nptile * p.nslab;
-  const int wplanes = (p.products == 3) ? 2 : 1;
+  const int wplanes = (p.products >= 2) ? 2 : 1;
+  const bool mixed = (p.products == 2);   // second plane of X and W is the e5m2x2 Q plane
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
@@ -136,6 +160,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         const int p0 = ((tile / p.nslab) % p.nptile) * kTileN;
         const int ncols = min(kTileN, (p.L - p0 + 15) & ~15);
         const uint32_t idesc = make_idesc_f16(kTileM, ncols, p.in_bf16, p.in_bf16);  // dgrad: both operands bf16
+        const uint32_t idesc8 = make_idesc_f8(kTileM, ncols);
         mbar_wait(&bars->tempty[buf], ((tit >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * kTileN;
@@ -160,7 +185,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
                            make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, acc);
                 acc = 1;
               }
-              if (wplanes == 2) {
+              if (wplanes == 2 && !mixed) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   if (elected)
@@ -170,16 +195,24 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
               if (elected) umma_commit(&bars->wempty[ws]);
               ++wit;
             }
-            if (wplanes == 2) {  // W lo: Xh*Wl
+            if (wplanes == 2) {  // second W plane: Xh*Wl (fp16 lo planes), or Xq*Wq = Xl*Wh + Xh*Wl (e5m2 pairs)
               const int ws = wit % kWStages;
               mbar_wait(&bars->wfull[ws], (wit / kWStages) & 1);
               tc_fence_after_sync();
               const uint32_t wa = smem_u32(wring + ws * kWTileBytes);
+              if (mixed) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (elected)
-                  umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
-                           make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
+                for (int k = 0; k < 4; ++k)
+                  if (elected)
+                    umma_f8(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                            make_smem_desc(bl + k * 32, 16, 1024, kLayoutSW128), idesc8, 1);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (elected)
+                    umma_f16(d_tmem, make_smem_desc(wa + k * 32, 16, 1024, kLayoutSW128),
+                             make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, 1);
+              }
               if (elected) umma_commit(&bars->wempty[ws]);
               ++wit;
             }
@@ -291,24 +324,15 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
             tc_fence_before_sync();
             mbar_arrive(&bars->tempty[buf]);
           }
-          if (no_hi) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float y = apply_epi_pool2<false>(ep, v[2 * j], v[2 * j + 1]);
-              __half h, l;
-              split_f32(y, h, l);
-              sts_u16(st_h + j * 128, h);
-              if (wplanes == 2) sts_u16(st_l + j * 128, l);
-            }
+          if (mixed) {
+            if (no_hi) pooled_granule<false, 2>(ep, v, st_h, st_l);
+            else pooled_granule<true, 2>(ep, v, st_h, st_l);
+          } else if (wplanes == 2) {
+            if (no_hi) pooled_granule<false, 1>(ep, v, st_h, st_l);
+            else pooled_granule<true, 1>(ep, v, st_h, st_l);
           } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float y = apply_epi_pool2<true>(ep, v[2 * j], v[2 * j + 1]);
-              __half h, l;
-              split_f32(y, h, l);
-              sts_u16(st_h + j * 128, h);
-              if (wplanes == 2) sts_u16(st_l + j * 128, l);
-            }
+            if (no_hi) pooled_granule<false, 0>(ep, v, st_h, st_l);
+            else pooled_granule<true, 0>(ep, v, st_h, st_l);
           }
           fence_proxy_async_smem();
           if (leader) tma_store_wait_read<0>();
@@ -352,7 +376,9 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   // K chunks are 64 channels wide; a ragged last chunk is zero-filled by TMA in both operands
   if (cin % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 8");
   if (cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cout must be a multiple of 8");
-  if (products != 1 && products != 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1 or 3");
+  if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1, 2 or 3");
+  if (products == 2 && (out_f32 != nullptr || in_bf16))
+    return set_error(VM_ERR_UNSUPPORTED, "conv3: products=2 (e5m2 correction planes) is an eval-forward mode");
   if (gmax_partial == nullptr && out_hi == nullptr && out_f32 == nullptr)
     return set_error(VM_ERR_SHAPE, "conv3: no output given");
   if (L / 2 <= 0) return set_error(VM_ERR_SHAPE, "conv3: L must be >= 2");
@@ -378,8 +404,8 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   int rc;
   if ((rc = make_tensor_map(&xh_main, in_hi, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&xh_halo, in_hi, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
-  const __half* lo_src = (products == 3) ? in_lo : in_hi;
-  if (products == 3 && in_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: lo plane required for products=3");
+  const __half* lo_src = (products >= 2) ? in_lo : in_hi;
+  if (products >= 2 && in_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: second plane required for products>=2");
   if ((rc = make_tensor_map(&xl_main, lo_src, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&xl_halo, lo_src, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
   // W planes: [plane][tap*cout_pad + cout][cin] fp16
@@ -387,7 +413,8 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   const uint64_t wstr[1] = {uint64_t(cin) * 2};
   const uint32_t wbox[2] = {kKC, kTileM};
   const __half* w_hi = wpack;
-  const __half* w_lo = wpack + size_t(3) * cout_pad * cin;
+  // weight planes: [hi][lo][q]; products == 2 pairs the hi plane with the e5m2x2 plane
+  const __half* w_lo = wpack + size_t(products == 2 ? 2 : 1) * 3 * cout_pad * cin;
   if ((rc = make_tensor_map(&wh, w_hi, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&wl, w_lo, 2, wdims, wstr, wbox, VM_SWIZZLE_128B))) return rc;
 
@@ -401,12 +428,12 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
     if ((rc = make_tensor_map(&oh, out_f32, 3, odims, ostr, obox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
     ol = oh;
   } else if (gmax_partial == nullptr) {
-    if (products == 3 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: out_lo required for products=3");
+    if (products >= 2 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: out_lo required for products>=2");
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 2, uint64_t(p.lout) * cout * 2};
     const uint32_t obox[3] = {64, kStagePos, 1};
     if ((rc = make_tensor_map(&oh, out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE))) return rc;
-    if ((rc = make_tensor_map(&ol, products == 3 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
+    if ((rc = make_tensor_map(&ol, products >= 2 ? out_lo : out_hi, 3, odims, ostr, obox, VM_SWIZZLE_NONE)))
       return rc;
   } else {
     oh = wh;  // unused by the kernel in gmax mode

@@ -28,7 +28,8 @@ __device__ __forceinline__ float4 fold_bn(float bias, float gamma, float beta, f
 __device__ __forceinline__ float4 epi_relu_only(float bias) { return make_float4(1.f, bias, -bias, INFINITY); }
 
 // ---------------------------------------------------------------------------------------------
-// conv3 weights: w (3, cin, cout) fp32 -> wpack [plane][tap][cout_pad][cin] fp16
+// conv3 weights: w (3, cin, cout) fp32 -> wpack [plane][tap][cout_pad][cin], 16 bits per entry; planes: fp16 hi, fp16 lo,
+// e5m2x2 Q (split_w_q: the operand of the single-MMA correction product of precision 2)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -56,6 +57,9 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __re
   split_f32(v, h, l);
   wpack[idx] = h;
   wpack[total + idx] = l;
+  uint16_t q;
+  split_w_q(v, h, q);
+  wpack[2 * total + idx] = __ushort_as_half(q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,6 +126,22 @@ __global__ void split_planes_kernel(const float* __restrict__ x, size_t n, __hal
     hi[i] = h;
     if (lo != nullptr) lo[i] = l;
   }
+}
+// precision-2 planes: (fp16 hi, e5m2x2 Q) -- see vm_common.cuh
+__global__ void split_planes_q_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ hi,
+                                      uint16_t* __restrict__ q) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    __half h;
+    uint16_t qq;
+    split_f16_q(x[i], h, qq);
+    hi[i] = h;
+    q[i] = qq;
+  }
+}
+__global__ void merge_planes_q_kernel(const __half* __restrict__ hi, const uint16_t* __restrict__ q, size_t n,
+                                      float* __restrict__ x) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    x[i] = __half2float(hi[i]) + e5m2_to_float(q[i] & 0xFFu) * kQDown;
 }
 __global__ void merge_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t n,
                                     float* __restrict__ x) {
@@ -322,6 +342,18 @@ int launch_split_planes(const float* x, size_t n, __half* hi, __half* lo, cudaSt
   return check_launch("split_planes");
 }
 
+int launch_split_planes_q(const float* x, size_t n, __half* hi, uint16_t* q, cudaStream_t stream) {
+  if (n == 0) return VM_OK;
+  const unsigned blocks = unsigned(min(size_t(148 * 16), (n + 255) / 256));
+  split_planes_q_kernel<<<blocks, 256, 0, stream>>>(x, n, hi, q);
+  return check_launch("split_planes_q");
+}
+int launch_merge_planes_q(const __half* hi, const uint16_t* q, size_t n, float* x, cudaStream_t stream) {
+  if (n == 0) return VM_OK;
+  const unsigned blocks = unsigned(min(size_t(148 * 16), (n + 255) / 256));
+  merge_planes_q_kernel<<<blocks, 256, 0, stream>>>(hi, q, n, x);
+  return check_launch("merge_planes_q");
+}
 int launch_merge_planes(const __half* hi, const __half* lo, size_t n, float* x, cudaStream_t stream) {
   if (n == 0) return VM_OK;
   const unsigned blocks = unsigned(min(size_t(148 * 16), (n + 255) / 256));

@@ -32,7 +32,7 @@ struct Conv1Params {
   int cout, cout_pad, nslab;
   int lout;              // L / 4
   int nptile;            // ceil(L / 256)
-  int products;          // 3: fp16x3 (fp32-grade), 1: fp16x1
+  int products;          // 3: fp16x3 (fp32-grade), 2: same MMAs, output planes (fp16 hi, e5m2x2 Q), 1: fp16x1
   int nstages;           // Toeplitz ring depth (2..4, limited by shared memory when Cout > 128)
   const uint4* wpack;    // [slab][plane][8 KB smem image]
   const float4* epi;     // [cout_pad] {sigma, bias, s, t}
@@ -129,6 +129,8 @@ int launch_pack_conv3(const float* w, const float* bias, const float* gamma, con
                       const float* var, float eps, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);
 int launch_split_planes(const float* x, size_t n, __half* hi, __half* lo, cudaStream_t stream);
 int launch_merge_planes(const __half* hi, const __half* lo, size_t n, float* x, cudaStream_t stream);
+int launch_split_planes_q(const float* x, size_t n, __half* hi, uint16_t* q, cudaStream_t stream);
+int launch_merge_planes_q(const __half* hi, const uint16_t* q, size_t n, float* x, cudaStream_t stream);
 int launch_gmax_dense(const float* partial, int N, int T, int C, int c_pad, const float* epi, const float* dense_w,
                       const float* dense_b, int E, float* gmax_out, float* emb, cudaStream_t stream);
 int launch_pair_head_loss(const float* e1, const float* e2, int N, int E, int metric, const float* head_w,

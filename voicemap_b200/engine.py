@@ -18,6 +18,7 @@ BN_EPS = 1e-3  # keras.layers.BatchNormalization default
 POOLS = (4, 2, 2, 2)
 PRECISION_FP32_GRADE = 3   # fp16 (hi, lo) planes, three MMAs per K step
 PRECISION_THROUGHPUT = 1   # fp16 hi plane only
+PRECISION_MIXED = 2        # fp16 main product + one fp8 (e5m2 pairs) product for both corrections: 8 MMAs per K chunk
 
 
 def _ptr(t):
@@ -177,14 +178,17 @@ class EncoderEngine:
 
     # ------------------------------------------------------------------ per-block views (tests, profiling)
     def split_planes(self, x):
+        """fp32 -> the plane pair of this engine's precision: (hi, lo) fp16, or (hi, Q) with precision 2."""
         hi = torch.empty(x.shape, dtype=torch.float16, device=self.device)
         lo = torch.empty(x.shape, dtype=torch.float16, device=self.device)
-        _lib.check(self.lib.vm_split_planes(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), "vm_split_planes")
+        fn = self.lib.vm_split_planes_q if self.precision == PRECISION_MIXED else self.lib.vm_split_planes
+        _lib.check(fn(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), "vm_split_planes")
         return hi, lo
 
     def merge_planes(self, hi, lo):
         x = torch.empty(hi.shape, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.vm_merge_planes(_ptr(hi), _ptr(lo), hi.numel(), _ptr(x), _stream()), "vm_merge_planes")
+        fn = self.lib.vm_merge_planes_q if self.precision == PRECISION_MIXED else self.lib.vm_merge_planes
+        _lib.check(fn(_ptr(hi), _ptr(lo), hi.numel(), _ptr(x), _stream()), "vm_merge_planes")
         return x
 
     def block1(self, x, out=None):

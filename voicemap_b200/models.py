@@ -154,7 +154,9 @@ class EncoderModel(_ModelBase):
         self.embedding_dimension = int(embedding_dimension)
         self.input_shape = tuple(input_shape) if input_shape is not None else None
         self.dropout = float(dropout)
-        self.precision = 3
+        # eval-forward arithmetic: 2 = fp16 product + one fp8 (e5m2 pairs) correction product,
+        # embeddings 1e-5 .. 4.5e-5 from the fp64 oracle; 3 = fp16 x 3, ~7e-6; 1 = fp16 x 1, ~6e-4 (not parity)
+        self.precision = 2
         rng = np.random.default_rng(seed)
         f = self.filters
         self.weights = OrderedDict()
