@@ -48,6 +48,7 @@ struct __align__(8) Conv3Barriers {
   uint64_t xfull[c3::kXStages], xempty[c3::kXStages];
   uint64_t wfull[c3::kWStages], wempty[c3::kWStages];
   uint64_t tfull[2], tempty[2];
+  uint64_t sfull[2], sempty[2];   // pooled-output staging buffers: epilogue warps -> store warp -> epilogue warps
   uint32_t tmem_base;
 };
 
@@ -96,6 +97,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(&bars->wfull[i], 1); mbar_init(&bars->wempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->sfull[i], kEpiWarps * 32); mbar_init(&bars->sempty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -222,6 +224,40 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         if (elected) umma_commit(&bars->tfull[buf]);
       }
     }
+  } else if (warp == 2) {
+    // ===================== store warp (pooled outputs): staging buffer -> TMA bulk tensor stores =====================
+    // The epilogue warps hand over each 8 KB output granule through an mbarrier pair per staging buffer instead of
+    // meeting in a CTA-wide named barrier: no epilogue warp waits for another one or for the store issue, they only
+    // wait (rarely) for a staging buffer whose previous store has not been read out of shared memory yet.
+    if (lane == 0 && p.gmax_partial == nullptr && p.out_f32 == nullptr) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int slab = tile % p.nslab;
+        const int pt_lin = tile / p.nslab;
+        const int n = pt_lin / p.nptile;
+        const int p0 = (pt_lin % p.nptile) * kTileN;
+        for (int gr = 0; gr < kTileN / 32; ++gr, ++g) {
+          const int b = g & 1;
+          mbar_wait(&bars->sfull[b], (g >> 1) & 1);
+          const uint8_t* sbuf = stage + b * kStageBufBytes;
+          const int pos = (p0 >> 1) + gr * kStagePos;
+          if (pos < p.lout) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = slab * kTileM + half * 64;
+              if (c0 < p.cout) {
+                tma_store_3d(&tm_oh, sbuf + half * kStageBoxBytes, c0, pos, n);
+                if (wplanes == 2) tma_store_3d(&tm_ol, sbuf + (2 + half) * kStageBoxBytes, c0, pos, n);
+              }
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();          // this thread has nothing else to do: hand the buffer back as soon as
+          mbar_arrive(&bars->sempty[b]);     // the TMA unit has read it out of shared memory
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: thread = cout channel, columns = positions =====================
     // 8 warps: q = TMEM lane quarter, chalf = which half of every output granule's columns.  Output granules go
@@ -315,7 +351,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         const bool no_hi = epi_no_upper_clamp(ep);
 #pragma unroll 1
         for (int gr = 0; gr < kTileN / 32; ++gr, ++gcount) {
-          uint8_t* sbuf = stage + (gcount & 1) * kStageBufBytes;
+          const int sb = gcount & 1;
+          uint8_t* sbuf = stage + sb * kStageBufBytes;
           const uint32_t st_h = smem_u32(sbuf) + (ch >> 6) * kStageBoxBytes + (ch & 63) * 2 + chalf * 8 * 128;
           const uint32_t st_l = st_h + 2 * kStageBoxBytes;
           float v[16];
@@ -324,6 +361,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
             tc_fence_before_sync();
             mbar_arrive(&bars->tempty[buf]);
           }
+          // the store of the granule that used this staging buffer last (two granules ago) has read it out
+          if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
           if (mixed) {
             if (no_hi) pooled_granule<false, 2>(ep, v, st_h, st_l);
             else pooled_granule<true, 2>(ep, v, st_h, st_l);
@@ -334,23 +373,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
             if (no_hi) pooled_granule<false, 0>(ep, v, st_h, st_l);
             else pooled_granule<true, 0>(ep, v, st_h, st_l);
           }
-          fence_proxy_async_smem();
-          if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, kEpiWarps * 32);
-          if (leader) {
-            const int pos = (p0 >> 1) + gr * kStagePos;
-            if (pos < p.lout) {
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int c0 = slab * kTileM + half * 64;
-                if (c0 < p.cout) {
-                  tma_store_3d(&tm_oh, sbuf + half * kStageBoxBytes, c0, pos, n);
-                  if (wplanes == 2) tma_store_3d(&tm_ol, sbuf + (2 + half) * kStageBoxBytes, c0, pos, n);
-                }
-              }
-            }
-            tma_store_commit();
-          }
+          fence_proxy_async_smem();          // this thread's staging writes -> visible to the TMA store
+          mbar_arrive(&bars->sfull[sb]);     // 256 arrivals = granule complete; the store warp takes it from here
         }
       }
     }
