@@ -17,6 +17,8 @@
 // Epilogue (4 warps, thread = one cout channel, columns = consecutive positions): pooling is done on the raw
 // accumulators first -- weights of channels with a negative BN scale are packed negated (sigma = -1) so that
 // max-pooling commutes with the affine:  y = s * relu(sigma * max(acc) + bias) + t.
+#include <stdlib.h>
+
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 
@@ -50,6 +52,24 @@ struct __align__(8) Conv3Barriers {
   uint64_t tfull[2], tempty[2];
   uint64_t sfull[2], sempty[2];   // pooled-output staging buffers: epilogue warps -> store warp -> epilogue warps
   uint32_t tmem_base;
+};
+
+// Tile schedule.  tile = (position tile) * nslab + (cout slab).  A CTA takes "units" of `spu` consecutive tiles round
+// robin: spu = 1 deals single tiles (the slabs of a position tile run on neighbouring CTAs at the same time and share
+// the X tile through L2); spu = nslab keeps all slabs of a position tile on one CTA, which is used when the whole K
+// extent of the X tile fits the shared-memory ring (Cin <= 128): X is then loaded once per position tile instead of
+// once per slab, and the next position tile's X has nslab tiles of MMA time to arrive from HBM.
+struct TileIter {
+  int unit, s, spu, nunits, stride;
+  __device__ TileIter(int first, int stride_, int ntiles, int spu_)
+      : unit(first), s(0), spu(spu_), nunits(ntiles / spu_), stride(stride_) {}
+  __device__ bool valid() const { return unit < nunits; }
+  __device__ int tile() const { return unit * spu + s; }
+  __device__ bool first() const { return s == 0; }
+  __device__ bool last() const { return s == spu - 1; }
+  __device__ void next() {
+    if (++s == spu) { s = 0; unit += stride; }
+  }
 };
 
 // 16 accumulator columns of one channel -> 8 pooled outputs -> bias/ReLU/BN clamp form -> staging rows.
@@ -90,6 +110,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntiles = p.N * p.nptile * p.nslab;
+  const int spu = p.slabs_per_unit;
   const int wplanes = (p.products >= 2) ? 2 : 1;
   const bool mixed = (p.products == 2);   // second plane of X and W is the e5m2x2 Q plane
 
@@ -112,8 +133,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       tma_prefetch_desc(&tm_xh_main); tma_prefetch_desc(&tm_xh_halo);
       tma_prefetch_desc(&tm_xl_main); tma_prefetch_desc(&tm_xl_halo);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int pt_lin = tile / p.nslab;
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
+        if (!ti.first()) continue;   // the unit's later slabs reuse the resident X tile
+        const int pt_lin = ti.tile() / p.nslab;
         const int n = pt_lin / p.nptile;
         const int p0 = (pt_lin % p.nptile) * kTileN;
         for (int c = 0; c < p.nchunk; ++c, ++it) {
@@ -135,8 +157,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     if (lane == 0) {
       tma_prefetch_desc(&tm_wh); tma_prefetch_desc(&tm_wl);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int slab = tile % p.nslab;
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
+        const int slab = ti.tile() % p.nslab;
         for (int c = 0; c < p.nchunk; ++c) {
           for (int tap = 0; tap < 3; ++tap) {
             for (int pl = 0; pl < wplanes; ++pl, ++it) {
@@ -155,7 +177,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     {
       const bool elected = elect_one_sync();
       uint32_t xit = 0, wit = 0, tit = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next(), ++tit) {
+        const int tile = ti.tile();
         const int buf = tit & 1;
         // the last position tile of a clip is usually ragged: issue only as many MMA columns (multiple of 16) as
         // there are positions left -- the tensor pipe is the bound, so unused columns are pure waste
@@ -167,10 +190,13 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * kTileN;
         uint32_t acc = 0;
-        for (int c = 0; c < p.nchunk; ++c, ++xit) {
-          const int xs = xit % kXStages;
-          mbar_wait(&bars->xfull[xs], (xit / kXStages) & 1);
-          tc_fence_after_sync();
+        for (int c = 0; c < p.nchunk; ++c) {
+          const uint32_t xi = xit + c;   // X chunks of this unit (loaded once, by its first tile)
+          const int xs = xi % kXStages;
+          if (ti.first()) {
+            mbar_wait(&bars->xfull[xs], (xi / kXStages) & 1);
+            tc_fence_after_sync();
+          }
           const uint32_t xh = smem_u32(xring + xs * kXSlotBytes);
           const uint32_t xl = xh + kXPlaneBytes;
           for (int tap = 0; tap < 3; ++tap) {
@@ -219,8 +245,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
               ++wit;
             }
           }
-          if (elected) umma_commit(&bars->xempty[xs]);
+          if (ti.last() && elected) umma_commit(&bars->xempty[xs]);
         }
+        if (ti.last()) xit += p.nchunk;
         if (elected) umma_commit(&bars->tfull[buf]);
       }
     }
@@ -231,7 +258,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     // wait (rarely) for a staging buffer whose previous store has not been read out of shared memory yet.
     if (lane == 0 && p.gmax_partial == nullptr && p.out_f32 == nullptr) {
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
+        const int tile = ti.tile();
         const int slab = tile % p.nslab;
         const int pt_lin = tile / p.nslab;
         const int n = pt_lin / p.nptile;
@@ -271,7 +299,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     const int ch = q * 32 + lane;
     const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
     uint32_t tit = 0, gcount = 0;   // gcount: granules staged so far (selects the staging buffer)
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tit) {
+    for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next(), ++tit) {
+      const int tile = ti.tile();
       const int slab = tile % p.nslab;
       const int pt_lin = tile / p.nslab;
       const int n = pt_lin / p.nptile;
@@ -466,8 +495,11 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile * p.nslab;
+  // all cout slabs of a position tile on one CTA when its X tile fits the ring (see TileIter)
+  p.slabs_per_unit = (p.nchunk <= kXStages && p.nslab > 1 && getenv("VM_CONV3_NO_RESIDENT_X") == nullptr) ? p.nslab : 1;
+  const int nunits = ntiles / p.slabs_per_unit;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
-  if (grid > ntiles) grid = ntiles;
+  if (grid > nunits) grid = nunits;
   conv3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: launch");

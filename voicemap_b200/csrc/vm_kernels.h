@@ -64,6 +64,7 @@ struct Conv3Params {
   float2* stat_partial;  // (N, 2*nptile, cout_pad) {sum, sum of squares} of out_f32 over valid positions, or null
   int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
   int in_bf16;           // input AND weight planes are bf16 (dgrad) instead of fp16 (kind::f16 cannot mix the two)
+  int slabs_per_unit;    // tile schedule: 1, or nslab when the X tile stays in shared memory for all cout slabs
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
