@@ -75,10 +75,10 @@ struct TileIter {
 // 16 accumulator columns of one channel -> 8 pooled outputs -> bias/ReLU/BN clamp form -> staging rows.
 // kSecond: 0 = hi plane only, 1 = fp16 residual plane, 2 = e5m2x2 Q plane.
 template <bool kClampHi, int kSecond>
-__device__ __forceinline__ void pooled_granule(const float4& ep, const float (&v)[16], uint32_t st_h, uint32_t st_l) {
+__device__ __forceinline__ void pooled_granule(const float4& ep, const uint32_t (&r)[16], uint32_t st_h, uint32_t st_l) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float y = apply_epi_pool2<kClampHi>(ep, v[2 * j], v[2 * j + 1]);
+    const float y = apply_epi_pool2<kClampHi>(ep, __uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
     __half h;
     if (kSecond == 2) {
       uint16_t q;
@@ -90,6 +90,41 @@ __device__ __forceinline__ void pooled_granule(const float4& ep, const float (&v
       if (kSecond == 1) sts_u16(st_l + j * 128, l);
     }
     sts_u16(st_h + j * 128, h);
+  }
+}
+
+// Pooled epilogue of one accumulator tile for one warp: 8 granules of 16 columns, TMEM loads software-pipelined (the
+// next granule's columns are in flight while this one is pooled, converted and staged).  Granules are handed to the
+// store warp through the sfull / sempty mbarriers of the two staging buffers.
+template <bool kClampHi, int kSecond>
+__device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, uint8_t* stage, uint32_t thread_off,
+                                            Conv3Barriers* bars, int buf, uint32_t& gcount) {
+  using namespace c3;
+  auto granule = [&](const uint32_t (&r)[16]) {
+    const int sb = gcount & 1;
+    const uint32_t st_h = smem_u32(stage + sb * kStageBufBytes) + thread_off;
+    // the store of the granule that used this staging buffer last (two granules ago) has read it out
+    if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+    pooled_granule<kClampHi, kSecond>(ep, r, st_h, st_h + 2 * kStageBoxBytes);
+    fence_proxy_async_smem();          // this thread's staging writes -> visible to the TMA store
+    mbar_arrive(&bars->sfull[sb]);     // 256 arrivals = granule complete; the store warp takes it from here
+    ++gcount;
+  };
+  uint32_t ra[16], rb[16];
+  tmem_ld_32x16_issue(taddr, ra);
+#pragma unroll 1
+  for (int gr = 0; gr < kTileN / 32; gr += 2) {
+    tmem_ld_wait(ra);
+    tmem_ld_32x16_issue(taddr + (gr + 1) * 32, rb);
+    granule(ra);
+    tmem_ld_wait(rb);
+    if (gr + 2 < kTileN / 32) {
+      tmem_ld_32x16_issue(taddr + (gr + 2) * 32, ra);
+    } else {  // all TMEM reads of this accumulator are done
+      tc_fence_before_sync();
+      mbar_arrive(&bars->tempty[buf]);
+    }
+    granule(rb);
   }
 }
 
@@ -378,32 +413,17 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         // pooled outputs: granule = 16 pooled positions x 128 channels x 2 planes; the two warps of a lane quarter
         // take 16 raw columns (8 pooled positions) each.
         const bool no_hi = epi_no_upper_clamp(ep);
-#pragma unroll 1
-        for (int gr = 0; gr < kTileN / 32; ++gr, ++gcount) {
-          const int sb = gcount & 1;
-          uint8_t* sbuf = stage + sb * kStageBufBytes;
-          const uint32_t st_h = smem_u32(sbuf) + (ch >> 6) * kStageBoxBytes + (ch & 63) * 2 + chalf * 8 * 128;
-          const uint32_t st_l = st_h + 2 * kStageBoxBytes;
-          float v[16];
-          tmem_ld_32x16(taddr + gr * 32 + chalf * 16, v);
-          if (gr == kTileN / 32 - 1) {  // all TMEM reads of this buffer are done
-            tc_fence_before_sync();
-            mbar_arrive(&bars->tempty[buf]);
-          }
-          // the store of the granule that used this staging buffer last (two granules ago) has read it out
-          if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
-          if (mixed) {
-            if (no_hi) pooled_granule<false, 2>(ep, v, st_h, st_l);
-            else pooled_granule<true, 2>(ep, v, st_h, st_l);
-          } else if (wplanes == 2) {
-            if (no_hi) pooled_granule<false, 1>(ep, v, st_h, st_l);
-            else pooled_granule<true, 1>(ep, v, st_h, st_l);
-          } else {
-            if (no_hi) pooled_granule<false, 0>(ep, v, st_h, st_l);
-            else pooled_granule<true, 0>(ep, v, st_h, st_l);
-          }
-          fence_proxy_async_smem();          // this thread's staging writes -> visible to the TMA store
-          mbar_arrive(&bars->sfull[sb]);     // 256 arrivals = granule complete; the store warp takes it from here
+        const uint32_t toff = (ch >> 6) * kStageBoxBytes + (ch & 63) * 2 + chalf * 8 * 128;
+        const uint32_t ta = taddr + chalf * 16;
+        if (mixed) {
+          if (no_hi) pooled_tile<false, 2>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 2>(ep, ta, stage, toff, bars, buf, gcount);
+        } else if (wplanes == 2) {
+          if (no_hi) pooled_tile<false, 1>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 1>(ep, ta, stage, toff, bars, buf, gcount);
+        } else {
+          if (no_hi) pooled_tile<false, 0>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 0>(ep, ta, stage, toff, bars, buf, gcount);
         }
       }
     }
