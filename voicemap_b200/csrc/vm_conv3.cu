@@ -40,8 +40,7 @@ constexpr int kStageBoxBytes = kStagePos * 128;     // one TMA store box: 16 pos
 constexpr int kStageBufBytes = 4 * kStageBoxBytes;  // [plane][channel half][pos][64 ch] = 8 KB
 constexpr int kStageBytes = 2 * kStageBufBytes;     // double-buffered
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 16;                        // two sets of 8 (2 per TMEM lane quarter and set)
-constexpr int kSetThreads = 8 * 32;                  // threads of one epilogue set
+constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quarter
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kSmemBytes =
     kXStages * kXSlotBytes + kWStages * kWTileBytes + kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -94,13 +93,12 @@ __device__ __forceinline__ void pooled_granule(const float4& ep, const uint32_t 
   }
 }
 
-// Pooled epilogue of one accumulator tile for one warp: every second granule of 16 columns (the other epilogue set
-// takes the rest), TMEM loads software-pipelined (the next granule's columns are in flight while this one is pooled,
-// converted and staged).  Granules are handed to the
+// Pooled epilogue of one accumulator tile for one warp: 8 granules of 16 columns, TMEM loads software-pipelined (the
+// next granule's columns are in flight while this one is pooled, converted and staged).  Granules are handed to the
 // store warp through the sfull / sempty mbarriers of the two staging buffers.
 template <bool kClampHi, int kSecond>
-__device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, int gr0, uint8_t* stage,
-                                            uint32_t thread_off, Conv3Barriers* bars, int buf, uint32_t& gcount) {
+__device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, uint8_t* stage, uint32_t thread_off,
+                                            Conv3Barriers* bars, int buf, uint32_t& gcount) {
   using namespace c3;
   auto granule = [&](const uint32_t (&r)[16]) {
     const int sb = gcount & 1;
@@ -110,20 +108,19 @@ __device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, in
     pooled_granule<kClampHi, kSecond>(ep, r, st_h, st_h + 2 * kStageBoxBytes);
     fence_proxy_async_smem();          // this thread's staging writes -> visible to the TMA store
     mbar_arrive(&bars->sfull[sb]);     // 256 arrivals = granule complete; the store warp takes it from here
-    gcount += 2;
+    ++gcount;
   };
-  // this warp's granules: gr0, gr0 + 2, gr0 + 4, gr0 + 6 (gr0 = epilogue set)
   uint32_t ra[16], rb[16];
-  tmem_ld_32x16_issue(taddr + gr0 * 32, ra);
+  tmem_ld_32x16_issue(taddr, ra);
 #pragma unroll 1
-  for (int gr = gr0; gr < kTileN / 32; gr += 4) {
+  for (int gr = 0; gr < kTileN / 32; gr += 2) {
     tmem_ld_wait(ra);
-    tmem_ld_32x16_issue(taddr + (gr + 2) * 32, rb);
+    tmem_ld_32x16_issue(taddr + (gr + 1) * 32, rb);
     granule(ra);
     tmem_ld_wait(rb);
-    if (gr + 4 < kTileN / 32) {
-      tmem_ld_32x16_issue(taddr + (gr + 4) * 32, ra);
-    } else {  // all TMEM reads of this accumulator by this warp are done
+    if (gr + 2 < kTileN / 32) {
+      tmem_ld_32x16_issue(taddr + (gr + 2) * 32, ra);
+    } else {  // all TMEM reads of this accumulator are done
       tc_fence_before_sync();
       mbar_arrive(&bars->tempty[buf]);
     }
@@ -155,10 +152,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(&bars->wfull[i], 1); mbar_init(&bars->wempty[i], 1); }
-    // pooled outputs: both epilogue sets read every accumulator; gmax / un-pooled fp32 outputs: set 0 only
-    const uint32_t readers = (p.gmax_partial == nullptr && p.out_f32 == nullptr) ? 2 * kSetThreads : kSetThreads;
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], readers); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->sfull[i], kSetThreads); mbar_init(&bars->sempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->sfull[i], kEpiWarps * 32); mbar_init(&bars->sempty[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
@@ -328,23 +323,18 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: thread = cout channel, columns = positions =====================
-    // Two sets of 8 warps: q = TMEM lane quarter, chalf = which half of an output granule's columns.  Pooled outputs:
-    // set s takes the granules gr = s, s + 2, ... of every tile (= staging buffer s), so two granules are in work at
-    // a time -- the per-granule chain (TMEM load, pool, convert, stage, fence) is latency bound with two warps per
-    // scheduler and was longer than block 2's MMA time per tile.  Granules leave through the store warp (TMA bulk
-    // tensor stores; positions / channels out of range are clipped by the TMA unit).  gmax / un-pooled fp32 outputs
-    // (light resp. train-mode epilogues) run on set 0 alone.
+    // 8 warps: q = TMEM lane quarter, chalf = which half of every output granule's columns.  Output granules go
+    // through a double-buffered 2 x 8 KB staging area and leave with TMA bulk tensor stores (positions / channels
+    // out of range are clipped by the TMA unit).  Per granule there is one named barrier: before arriving, the
+    // leader waits until the store issued one granule earlier has drained its buffer (that store had a whole
+    // granule of compute to finish), so the buffer written next is known to be free by everyone who passes.
     const int q = warp & 3;
-    const int chalf = ((warp - 4) >> 2) & 1;
-    const int set = (warp - 4) >> 3;
-    const bool pooled_mode = (p.gmax_partial == nullptr && p.out_f32 == nullptr);
+    const int chalf = (warp - 4) >> 2;
     const bool leader = (threadIdx.x == 4 * 32);
     const int ch = q * 32 + lane;
-    int ntiles_guard = ntiles;
     const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
-    uint32_t tit = 0, gcount = set;   // gcount: index of this warp's next granule (parity = staging buffer = set)
-    if (set == 1 && !pooled_mode) ntiles_guard = 0;
-    for (TileIter ti(blockIdx.x, gridDim.x, ntiles_guard, spu); ti.valid(); ti.next(), ++tit) {
+    uint32_t tit = 0, gcount = 0;   // gcount: granules staged so far (selects the staging buffer)
+    for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next(), ++tit) {
       const int tile = ti.tile();
       const int slab = tile % p.nslab;
       const int pt_lin = tile / p.nslab;
@@ -354,9 +344,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       const int buf = tit & 1;
       const int co = slab * kTileM + ch;
       const float4 ep = p.epi[co];  // {a, c, lo, hi} (see apply_epi); padded channels hold zeros
-      // one polling warp per set; its other seven warps block in bar.sync instead of spinning on the mbarrier
-      if (warp == 4 + 8 * set) mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
-      named_bar_sync(1 + set, kSetThreads);
+      // one polling warp; the other seven block in bar.sync instead of spinning on the mbarrier
+      if (warp == 4) mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
+      named_bar_sync(1, kEpiWarps * 32);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
       if (p.gmax_partial != nullptr) {
@@ -404,7 +394,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
           }
           fence_proxy_async_smem();
           if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, kSetThreads);
+          named_bar_sync(1, kEpiWarps * 32);
           if (leader) {
             const int pos = p0 + gr * 16;
             if (pos < p.L) {
@@ -426,14 +416,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         const uint32_t toff = (ch >> 6) * kStageBoxBytes + (ch & 63) * 2 + chalf * 8 * 128;
         const uint32_t ta = taddr + chalf * 16;
         if (mixed) {
-          if (no_hi) pooled_tile<false, 2>(ep, ta, set, stage, toff, bars, buf, gcount);
-          else pooled_tile<true, 2>(ep, ta, set, stage, toff, bars, buf, gcount);
+          if (no_hi) pooled_tile<false, 2>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 2>(ep, ta, stage, toff, bars, buf, gcount);
         } else if (wplanes == 2) {
-          if (no_hi) pooled_tile<false, 1>(ep, ta, set, stage, toff, bars, buf, gcount);
-          else pooled_tile<true, 1>(ep, ta, set, stage, toff, bars, buf, gcount);
+          if (no_hi) pooled_tile<false, 1>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 1>(ep, ta, stage, toff, bars, buf, gcount);
         } else {
-          if (no_hi) pooled_tile<false, 0>(ep, ta, set, stage, toff, bars, buf, gcount);
-          else pooled_tile<true, 0>(ep, ta, set, stage, toff, bars, buf, gcount);
+          if (no_hi) pooled_tile<false, 0>(ep, ta, stage, toff, bars, buf, gcount);
+          else pooled_tile<true, 0>(ep, ta, stage, toff, bars, buf, gcount);
         }
       }
     }
