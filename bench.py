@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--length", type=int, default=12000, help="samples per clip entering the encoder")
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
-                    help="3: fp16x3 split (fp32-grade, parity mode); 1: fp16x1 (throughput mode)")
+                    help="2: fp16 product + fp8 (e5m2 pairs) correction product (parity mode, default); 3: fp16x3 split "
+                         "(parity mode, tighter); 1: fp16x1 (throughput mode, not parity)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -321,8 +322,9 @@ def run_b200(args):
                 1: "precision=1: one fp16 MMA per algorithmic MAC (not a parity mode)"}[args.precision],
             mma_issue_frac=round(achieved_tf * args.precision / peaks["bf16_tflops"], 4),
             # dram__bytes_read + dram__bytes_write of the three conv3 launches (ncu --set full, profiles/r01_ncu_summary.md:
-            # 738 + 651 + 304 MB at batch 256) averaged per launch; algorithmic bytes per launch average 590 MB
-            traffic=(5.64e8 if (n, length, args.precision) == (256, 12000, 3) else None),
+            # 738 + 651 + 304 MB at batch 256, the same for precision 2 and 3: both move 4 bytes per activation)
+            # averaged per launch; algorithmic bytes per launch average 590 MB
+            traffic=(5.64e8 if (n, length) == (256, 12000) and args.precision in (2, 3) else None),
             blocks=blocks,
             network=dict(us_per_clip=round(us_per_clip, 3),
                          frac_of_tf32_roofline=round(bound_us(peaks["bf16_tflops"] / 2) / us_per_clip, 4),

@@ -20,14 +20,15 @@ _PIPELINE_BUFFER_BYTES = 1 << 31  # device staging buffer for host batches in pr
 
 
 def _pipeline_plan(n, pinned=True):
-    """[(lo, hi), ...] covering range(n).  A pinned batch is cut into a small first chunk (n/8 clips: its copy is
-    the only one that is not hidden) and the rest, in pieces of at most _PREDICT_CHUNK clips.  Measured on B200
-    (tools/e2e_probe.py, profiles/r01_e2e_probe.log): copies that run concurrently with the encoder kernels drop
-    to ~1/4 of their stand-alone rate and every extra chunk costs ~0.05 ms of fixed kernel prologue, so finer
-    plans (3-4 chunks) are not faster.  Pageable memory copies synchronously: plain chunks."""
+    """[(lo, hi), ...] covering range(n).  A pinned batch is cut into a small first chunk (its copy is the only one
+    that is not hidden behind kernels) and the rest, in pieces of at most _PREDICT_CHUNK clips.  The first chunk is
+    3/16 of the batch: with the precision-2 kernels a 256-clip batch computes in ~0.83 ms and copies in ~0.23 ms, so
+    the second copy (13/16 of the bytes) just fits behind the first chunk's kernels plus their fixed ~0.06 ms of
+    launches and prologues.  Every extra chunk costs that fixed part again, so finer plans are not faster
+    (tools/e2e_probe.py, profiles/r01_e2e_probe.log).  Pageable memory copies synchronously: plain chunks."""
     if not pinned or n < 96:
         return [(lo, min(n, lo + _PREDICT_CHUNK)) for lo in range(0, n, _PREDICT_CHUNK)]
-    first = min(_PREDICT_CHUNK, max(16, n // 8 // 8 * 8))
+    first = min(_PREDICT_CHUNK, max(16, n * 3 // 16 // 8 * 8))
     plan = [(0, first)]
     lo = first
     while lo < n:
