@@ -15,6 +15,8 @@
 //     bias/ReLU/BN, split to fp16 (hi, lo) planes, stage them in shared memory and store channels-last with TMA.
 //     As in vm_conv3.cu the packed weights carry sigma = sign(BN scale) so that the max-pool commutes with the
 //     affine.
+#include <type_traits>
+
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 
@@ -197,13 +199,6 @@ __device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, cons
     }
     sts_u16(sh + j * 128, h);
   }
-}
-template <int kPool>
-__device__ __forceinline__ void pool_epilogue(const float4& ep, bool no_hi, const uint32_t (&r)[32], uint32_t sh,
-                                              uint32_t sl, int second) {
-  if (second == 2) pool_epilogue<kPool, 2>(ep, no_hi, r, sh, sl);
-  else if (second == 1) pool_epilogue<kPool, 1>(ep, no_hi, r, sh, sl);
-  else pool_epilogue<kPool, 0>(ep, no_hi, r, sh, sl);
 }
 
 template <int kPool>
@@ -391,54 +386,62 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
           constexpr int kPasses = 4 / kPool;
           constexpr int kLoads = (kTileN / 64) / kPasses;   // 32-column TMEM loads per warp and pass
           constexpr int kOutPerLoad = 32 / kPool;
+          // the second plane's format is fixed per launch: instantiate the pipelined loop per format instead of
+          // branching inside it (a branch in this loop costs ~10 %, profiles/r01_conv1_epilogue_ab.log)
+          auto passes = [&](auto second_tag) {
+            constexpr int kSecond = decltype(second_tag)::value;
 #pragma unroll 1
-          for (int pass = 0; pass < kPasses; ++pass) {
-            // warp 0 of the group waits for (a) this group's previous TMA store to have drained the staging buffer
-            // and (b) the accumulator; the other seven warps block in the named barrier instead of spinning
-            if (wg == 0) {
-              if (lane == 0) tma_store_wait_read<0>();
-              if (pass == 0) mbar_wait(&bars->tfull[buf], it & 1);
-            }
-            named_bar_sync(bar_id, 256);
-            tc_fence_after_sync();
-            // software-pipelined TMEM reads: the next 32 columns are in flight while these are processed
-            const int g0 = pass * 2 * kLoads + chalf * kLoads;   // first 32-column group of this warp
-            const uint32_t row0 = chalf * kLoads * kOutPerLoad * 128;
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32_issue(taddr + g0 * 32, ra);
-#pragma unroll
-            for (int gg = 0; gg < kLoads; gg += 2) {
-              tmem_ld_wait(ra);
-              tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
-              pool_epilogue<kPool>(ep, no_hi, ra, st_h + row0 + gg * kOutPerLoad * 128,
-                                   st_l + row0 + gg * kOutPerLoad * 128, second);
-              tmem_ld_wait(rb);
-              if (gg + 2 < kLoads) {
-                tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
-              } else if (pass == kPasses - 1) {  // all TMEM reads of this accumulator are done
-                tc_fence_before_sync();
-                mbar_arrive(&bars->tempty[buf]);
+            for (int pass = 0; pass < kPasses; ++pass) {
+              // warp 0 of the group waits for (a) this group's previous TMA store to have drained the staging buffer
+              // and (b) the accumulator; the other seven warps block in the named barrier instead of spinning
+              if (wg == 0) {
+                if (lane == 0) tma_store_wait_read<0>();
+                if (pass == 0) mbar_wait(&bars->tfull[buf], it & 1);
               }
-              pool_epilogue<kPool>(ep, no_hi, rb, st_h + row0 + (gg + 1) * kOutPerLoad * 128,
-                                   st_l + row0 + (gg + 1) * kOutPerLoad * 128, second);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(bar_id, 256);
-            if (leader) {
-              const int pos = p0 / kPool + pass * 64;
-              if (pos < p.lout) {
+              named_bar_sync(bar_id, 256);
+              tc_fence_after_sync();
+              // software-pipelined TMEM reads: the next 32 columns are in flight while these are processed
+              const int g0 = pass * 2 * kLoads + chalf * kLoads;   // first 32-column group of this warp
+              const uint32_t row0 = chalf * kLoads * kOutPerLoad * 128;
+              uint32_t ra[32], rb[32];
+              tmem_ld_32x32_issue(taddr + g0 * 32, ra);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                  const int c0 = slab * kTileM + half * 64;
-                  if (c0 < p.cout) {
-                    tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
-                    if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+              for (int gg = 0; gg < kLoads; gg += 2) {
+                tmem_ld_wait(ra);
+                tmem_ld_32x32_issue(taddr + (g0 + gg + 1) * 32, rb);
+                pool_epilogue<kPool, kSecond>(ep, no_hi, ra, st_h + row0 + gg * kOutPerLoad * 128,
+                                              st_l + row0 + gg * kOutPerLoad * 128);
+                tmem_ld_wait(rb);
+                if (gg + 2 < kLoads) {
+                  tmem_ld_32x32_issue(taddr + (g0 + gg + 2) * 32, ra);
+                } else if (pass == kPasses - 1) {  // all TMEM reads of this accumulator are done
+                  tc_fence_before_sync();
+                  mbar_arrive(&bars->tempty[buf]);
+                }
+                pool_epilogue<kPool, kSecond>(ep, no_hi, rb, st_h + row0 + (gg + 1) * kOutPerLoad * 128,
+                                              st_l + row0 + (gg + 1) * kOutPerLoad * 128);
+              }
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, 256);
+              if (leader) {
+                const int pos = p0 / kPool + pass * 64;
+                if (pos < p.lout) {
+#pragma unroll
+                  for (int half = 0; half < 2; ++half) {
+                    const int c0 = slab * kTileM + half * 64;
+                    if (c0 < p.cout) {
+                      tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+                      if (nplanes == 2) tma_store_3d(&tm_ol, ob + (2 + half) * kOutBoxBytes, c0, pos, n);
+                    }
                   }
                 }
+                tma_store_commit();
               }
-              tma_store_commit();
             }
-          }
+          };
+          if (second == 2) passes(std::integral_constant<int, 2>{});
+          else if (second == 1) passes(std::integral_constant<int, 1>{});
+          else passes(std::integral_constant<int, 0>{});
         }
       }
       slab += 2;
