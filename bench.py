@@ -138,10 +138,35 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU path (oracle port: torch-CPU fp32 restatement of voicemap/models.py:6-41)
 # ------------------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """Host threads this process can really run: the affinity mask, capped by the cgroup CPU quota (a container limited
+    to 8 CPUs on a 128-core host still reports 128 from os.cpu_count(), and 128 OpenMP threads on 8 CPUs thrash)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                fields = f.read().split()
+            if path.endswith("cpu.max"):
+                quota, period = fields[0], float(fields[1])
+            else:
+                quota = fields[0]
+                with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                    period = float(f.read().split()[0])
+            if quota not in ("max", "-1"):
+                n = max(1, min(n, int(np.ceil(float(quota) / period))))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 def time_oracle(length, clips, budget_s, steps=None, warmup=1):
     import torch
     from oracle import voicemap_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cpus())
     params = O.init_encoder_params(FILTERS, EMB, seed=0, randomize_bn=True, random_bias=True)
     x = O.synthetic_clips(clips, length, seed=1234)
     for _ in range(warmup):

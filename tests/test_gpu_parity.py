@@ -260,10 +260,11 @@ def test_predict_pipelined_host_batch_is_bit_identical(stress_params):
     assert np.array_equal(enc.predict(x), whole)                # buffer reuse across calls
 
 
-def test_full_batch_properties(stress_params):
+@pytest.mark.parametrize("precision", [2, 3])
+def test_full_batch_properties(stress_params, precision):
     """BASELINE config[1] size (256 clips x 12000): batch-composition independence (bit-exact), permutation
     equivariance, and spot parity of a few clips against the oracle."""
-    eng = _engine(128, 64, stress_params)
+    eng = _engine(128, 64, stress_params, precision)
     g = torch.Generator().manual_seed(5)
     x = (O.WHITEN_RMS * torch.randn(256, 12000, generator=g)).cuda()
     full = eng.forward(x).clone()
@@ -407,9 +408,10 @@ def test_shipped_checkpoint_in_its_own_architecture():
     assert np.abs(prob - refp).max() < 1e-4
 
 
-def test_large_batch_of_short_clips(stress_params):
+@pytest.mark.parametrize("precision", [2, 3])
+def test_large_batch_of_short_clips(stress_params, precision):
     """n_seconds sweep corner (1 s clips, L = 4000) at a batch well beyond one wave of tiles per SM."""
-    eng = _engine(128, 64, stress_params)
+    eng = _engine(128, 64, stress_params, precision)
     g = torch.Generator().manual_seed(9)
     x = (O.WHITEN_RMS * torch.randn(1536, 4000, generator=g)).cuda()
     full = eng.forward(x).clone()
