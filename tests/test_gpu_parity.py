@@ -379,7 +379,7 @@ def test_first_pool_2_architecture_matches_oracle(stress_params, n, length):
     x = O.synthetic_clips(n, length, seed=77 + length, padded=(length == 12000))
     ref = O.encoder_forward(x, stress_params, torch.float32, pools=(2, 2, 2, 2))
     assert _per_clip(enc.predict(x), ref) <= TOL
-    enc.precision, enc._engine = 3, None        # fp16 (hi, lo) planes: the merged block output is fp32-grade
+    enc.precision = 3        # fp16 (hi, lo) planes: the merged block output is fp32-grade
     assert _per_clip(enc.predict(x), ref) <= TOL
     eng = enc._get_engine()
     hi, lo = eng.block1(torch.from_numpy(x[:, :, 0].astype(np.float32)).cuda())

@@ -496,3 +496,14 @@ def test_n_shot_evaluation_batched_equals_per_task_calls():
         utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 2, 2, 3, distance="manhattan")
     with pytest.raises(ValueError):
         utils.n_shot_task_evaluation(_StubSiamese(), ds, pre, 2, 2, 3, network_type="other")
+
+
+def test_precision_is_validated_and_survives_clone():
+    from voicemap_b200.keras_compat import clone_model
+    from voicemap_b200.models import get_baseline_convolutional_encoder
+    enc = get_baseline_convolutional_encoder(16, 8)
+    assert enc.precision == 2
+    enc.precision = 3
+    assert clone_model(enc).precision == 3
+    with pytest.raises(ValueError):
+        enc.precision = 4

@@ -155,9 +155,7 @@ class EncoderModel(_ModelBase):
         self.embedding_dimension = int(embedding_dimension)
         self.input_shape = tuple(input_shape) if input_shape is not None else None
         self.dropout = float(dropout)
-        # eval-forward arithmetic: 2 = fp16 product + one fp8 (e5m2 pairs) correction product,
-        # embeddings 1e-5 .. 4.5e-5 from the fp64 oracle; 3 = fp16 x 3, ~7e-6; 1 = fp16 x 1, ~6e-4 (not parity)
-        self.precision = 2
+        self._precision = 2
         rng = np.random.default_rng(seed)
         f = self.filters
         self.weights = OrderedDict()
@@ -248,9 +246,25 @@ class EncoderModel(_ModelBase):
         return dict(kind="encoder", filters=self.filters, embedding_dimension=self.embedding_dimension,
                     input_shape=self.input_shape, dropout=self.dropout, head=self._head, first_pool=self.first_pool)
 
+    @property
+    def precision(self):
+        """Arithmetic of the eval forward: 2 (default) = fp16 product + one fp8 (e5m2 pairs)
+        correction product, embeddings 1e-5 .. 4.5e-5 from the fp64 oracle; 3 = fp16 x 3, ~7e-6; 1 = fp16 x 1, ~6e-4
+        (throughput mode, not parity).  Training always runs 3."""
+        return self._precision
+
+    @precision.setter
+    def precision(self, value):
+        if int(value) not in (1, 2, 3):
+            raise ValueError("precision must be 1, 2 or 3")
+        if int(value) != self._precision:
+            self._precision = int(value)
+            self._engine = None          # the engine is built for one arithmetic; the next predict() rebuilds it
+
     def _clone(self):
         m = EncoderModel(self.filters, self.embedding_dimension, self.input_shape, self.dropout,
                          first_pool=self.first_pool)
+        m.precision = self.precision
         if self._head is not None:
             m.add(Dense(self._head["units"], activation=self._head["activation"]))
         return m
