@@ -317,6 +317,28 @@ def run_b200(args):
             acc[k] += evs[j].elapsed_time(evs[j + 1])
     kern_ms = {k: v / prof_steps for k, v in acc.items()}
 
+    # ---- the same clips without the reference's x4 decimation (raw 16 kHz: 48000 samples per 3 s clip), for the record
+    raw16k = None
+    if length != 48000:
+        xr = O.WHITEN_RMS * torch.randn(64, 48000, generator=torch.Generator(device="cpu").manual_seed(99))
+        xr = xr.to(dev)
+        outr = torch.empty((64, EMB), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            eng.forward(xr, out=outr)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(20):
+            eng.forward(xr, out=outr)
+        r1.record()
+        torch.cuda.synchronize()
+        raw_ms = r0.elapsed_time(r1) / 20
+        raw16k = dict(value=round(world * 64 * CLIP_SECONDS / (raw_ms * 1e-3), 1), unit=UNIT, batch=64, length=48000,
+                      ms_per_step=round(raw_ms, 4),
+                      note="same encoder on un-decimated 16 kHz clips (the reference's scripts decimate x4 first, "
+                           "voicemap/utils.py:29; SURVEY.md F3); rank 0's timing x n_gpus, informational")
+        del xr, outr
+
     if rank == 0:
         peaks = load_peaks()
         work = block_work(length)
@@ -378,6 +400,7 @@ def run_b200(args):
                      note="model.predict(pinned host batch): H2D + 5 kernels + D2H + sync, wall clock"),
             gpu_launches=5 * steps,
             kernel_ms=kern_ms,
+            raw16k=raw16k,
             roofline=roofline,
             cpu_baseline=cpu_baseline,
         )
