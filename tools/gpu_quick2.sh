@@ -5,7 +5,5 @@ LOG=gpurun_out/quick2.log
 run() { echo "=== $*" >> $LOG; timeout ${TMO:-300} "$@" >> $LOG 2>&1; echo "--- exit $?" >> $LOG; }
 run python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 run python tools/bringup.py --case time --n 256 --l 12000 --precision 2 --iters 20
-run env VM_CONV3_NO_RESIDENT_X=1 python tools/bringup.py --case time --n 256 --l 12000 --precision 2 --iters 20
 run python tools/bringup.py --case time --n 256 --l 12000 --precision 3 --iters 20
-run env VM_CONV3_NO_RESIDENT_X=1 python tools/bringup.py --case time --n 256 --l 12000 --precision 3 --iters 20
 tail -n 50 $LOG | cut -c1-300

@@ -17,8 +17,6 @@
 // Epilogue (4 warps, thread = one cout channel, columns = consecutive positions): pooling is done on the raw
 // accumulators first -- weights of channels with a negative BN scale are packed negated (sigma = -1) so that
 // max-pooling commutes with the affine:  y = s * relu(sigma * max(acc) + bias) + t.
-#include <stdlib.h>
-
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 
@@ -516,7 +514,7 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile * p.nslab;
   // all cout slabs of a position tile on one CTA when its X tile fits the ring (see TileIter)
-  p.slabs_per_unit = (p.nchunk <= kXStages && p.nslab > 1 && getenv("VM_CONV3_NO_RESIDENT_X") == nullptr) ? p.nslab : 1;
+  p.slabs_per_unit = (p.nchunk <= kXStages && p.nslab > 1) ? p.nslab : 1;
   const int nunits = ntiles / p.slabs_per_unit;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > nunits) grid = nunits;
