@@ -176,8 +176,18 @@ gmax_dense_kernel(const float* __restrict__ partial, int T, int C, int c_pad, co
     const int e = e0 + lane_e;
     float acc = 0.f;
     if (e < E) {
-#pragma unroll 8
-      for (int c = c0; c < c1; ++c) acc = fmaf(g[c], __ldg(dense_w + size_t(c) * E + e), acc);
+      // latency bound on the L2-resident weight loads: keep 32 of them in flight (four accumulators break the FMA chain)
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      int c = c0;
+      for (; c + 32 <= c1; c += 32) {
+        float w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = __ldg(dense_w + size_t(c + i) * E + e);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a4[i & 3] = fmaf(g[c + i], w[i], a4[i & 3]);
+      }
+      for (; c < c1; ++c) a4[0] = fmaf(g[c], __ldg(dense_w + size_t(c) * E + e), a4[0]);
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     }
     red[part * 64 + lane_e] = acc;
     __syncthreads();
