@@ -183,7 +183,7 @@ def test_dropout_mask_semantics():
     ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, dropout_masks=(om1, om2), relu_masks=rmasks)
     assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
     assert max(_grad_errors(tr.gradients(), ref["grads"]).values()) < 2e-3
-    tr._draw_masks(8)
+    assert tr._set_masks(8, None)
     m = tr.masks[0].cpu().numpy()
     assert set(np.unique(m)).issubset({0.0, np.float32(1 / 0.75)}) and m.shape == (8, 32)
 

@@ -59,6 +59,7 @@ def main():
         torch.distributed.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
     for _ in range(args.steps):
         lv, _ = tr.siamese_step(x1, x2, y, allreduce=allreduce, world=world)
@@ -67,10 +68,16 @@ def main():
         torch.distributed.barrier()
     torch.cuda.synchronize()
     ms = parallel.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+    # host time to ISSUE a step: four steps from an idle device, so the launch queue never fills and blocks the host
+    t_host = time.perf_counter()
+    for _ in range(4):
+        tr.siamese_step(x1, x2, y, allreduce=allreduce, world=world)
+    t_host = (time.perf_counter() - t_host) / 4 * 1e3
+    torch.cuda.synchronize()
     if rank == 0:
         print(json.dumps(dict(metric="siamese_train_pairs_per_sec", value=round(world * pairs / (ms * 1e-3), 1),
                               unit="pairs/s", audio_seconds_per_sec=round(world * pairs * 2 * 3.0 / (ms * 1e-3), 1),
-                              n_gpus=world, ms_per_step=round(ms, 3), steps=args.steps, scaling="strong" if
+                              n_gpus=world, ms_per_step=round(ms, 3), host_issue_ms_per_step=round(t_host, 3), steps=args.steps, scaling="strong" if
                               args.pairs_per_gpu is None else "weak",
                               config=dict(workload=f"siamese train step (fwd+bwd+Adam), contrastive loss, "
                                                    f"{pairs} pairs/GPU x {args.length} samples, filters={args.filters}, "

@@ -28,6 +28,33 @@ def _check(rc, what):
     _lib.check(rc, what)
 
 
+class _Plan:
+    """A recorded sequence of C-ABI launches for one step shape.  Every buffer a training step touches is allocated
+    once per (batch, length) and keeps its address, so the ctypes argument objects are built once and a step replays
+    ``fn(*args)`` per kernel instead of re-wrapping ~20 pointers and scalars per launch.  At 16 pairs per GPU (the
+    128-pair batch of BASELINE config[2] over 8 ranks) building the arguments cost more host time than the kernels took
+    on the device (tools/train_bench.py: host_issue_ms_per_step).  ``host`` entries are python callables (the BatchNorm
+    all-reduces of the data-parallel path) that run in sequence with the launches."""
+
+    def __init__(self):
+        self.ops = []
+
+    def launch(self, fn, what, *args):
+        self.ops.append((fn, args, what))
+
+    def host(self, fn):
+        self.ops.append((None, fn, None))
+
+    def run(self):
+        for fn, args, what in self.ops:
+            if fn is None:
+                args()
+            else:
+                rc = fn(*args)
+                if rc:
+                    _lib.check(rc, what)
+
+
 class TrainEngine:
     """One training step of encoder (+ siamese head | classifier head) on the current CUDA device."""
 
@@ -118,6 +145,9 @@ class TrainEngine:
                 self.edg.append(torch.zeros(self.lib.vm_epi_bytes(cin) // 4, dtype=torch.float32, device=dev))
             cin = cout
         self._buf_key = None
+        self._plans = {}
+        self._pin = [None, None, None, None, None, None]   # pinned staging ring (two clip sides + labels per step, twice)
+        self._pin_next = 0
         self.iterations = 0
 
     # ------------------------------------------------------------------ buffers
@@ -160,91 +190,106 @@ class TrainEngine:
         # wgrad split partials (the launcher lowers its split count to fit) / wgrad1 per-CTA partials
         w1_bytes = nb * ((ls[0] + 1023) // 1024) * 32 * c[0] * 4
         self.wpart = torch.empty(max(64 << 20, w1_bytes) // 4, dtype=f32, device=dev)
+        self.xin = torch.empty((nb, length), dtype=f32, device=dev)            # the step's clips (both branches)
+        self.yin = torch.empty((max(1, nb // groups),), dtype=f32, device=dev)   # siamese pair labels
+        self.maskbuf = [torch.empty((nb, c[b]), dtype=f32, device=dev) for b in range(4)]
+        self.prob = torch.empty((max(1, nb // groups), 1), dtype=f32, device=dev)
+        self.lossv = torch.zeros((1,), dtype=f32, device=dev)
         self.masks = [None] * 4
+        self._plans = {}
         self._buf_key = key
 
-    def _pack(self):
+    def _plan_pack(self, plan, st):
         p = self.p
+        lib = self.lib
         cin = 1
         for i, cout in enumerate(self.channels, start=1):
             if i == 1:
-                rc = self.lib.vm_pack_conv1_raw(_ptr(p["conv1_kernel"]), _ptr(p["conv1_bias"]), cout,
-                                                _ptr(self.wraw[0]), _ptr(self.eraw[0]), _stream())
+                plan.launch(lib.vm_pack_conv1_raw, "vm_pack_conv1_raw", _ptr(p["conv1_kernel"]), _ptr(p["conv1_bias"]),
+                            cout, _ptr(self.wraw[0]), _ptr(self.eraw[0]), st)
             else:
-                rc = self.lib.vm_pack_conv3_raw(_ptr(p[f"conv{i}_kernel"]), _ptr(p[f"conv{i}_bias"]), cin, cout,
-                                                _ptr(self.wraw[i - 1]), _ptr(self.eraw[i - 1]), _stream())
-                _check(rc, "vm_pack_conv3_raw")
-                rc = self.lib.vm_pack_conv3_dgrad(_ptr(p[f"conv{i}_kernel"]), cin, cout, _ptr(self.wdg[i - 1]),
-                                                  _ptr(self.edg[i - 1]), _stream())
-            _check(rc, "train pack")
+                plan.launch(lib.vm_pack_conv3_raw, "vm_pack_conv3_raw", _ptr(p[f"conv{i}_kernel"]),
+                            _ptr(p[f"conv{i}_bias"]), cin, cout, _ptr(self.wraw[i - 1]), _ptr(self.eraw[i - 1]), st)
+                plan.launch(lib.vm_pack_conv3_dgrad, "vm_pack_conv3_dgrad", _ptr(p[f"conv{i}_kernel"]), cin, cout,
+                            _ptr(self.wdg[i - 1]), _ptr(self.edg[i - 1]), st)
             cin = cout
 
-    def _draw_masks(self, nb):
-        if not (0.0 < self.dropout < 1.0):   # keras guards 0 < rate < 1: identity otherwise
+    def _set_masks(self, nb, masks):
+        """Fill the static SpatialDropout1D mask buffers for this step; returns whether dropout is active.  One
+        Bernoulli draw per (clip, channel), scaled by 1 / keep (keras guards 0 < rate < 1: identity otherwise)."""
+        if masks is not None:
+            active = any(m is not None for m in masks)
+            for buf, m in zip(self.maskbuf, masks):
+                if active:
+                    buf.copy_(m) if m is not None else buf.fill_(1.0)
+            self.masks = list(self.maskbuf) if active else [None] * 4
+            return active
+        if not (0.0 < self.dropout < 1.0):
             self.masks = [None] * 4
-            return
+            return False
         keep = 1.0 - self.dropout
-        self.masks = []
-        for c in self.channels:  # SpatialDropout1D: one Bernoulli draw per (clip, channel), scaled by 1/keep
-            m = (torch.rand((nb, c), generator=self.gen, device=self.device) < keep).to(torch.float32) / keep
-            self.masks.append(m)
+        for buf in self.maskbuf:
+            buf.copy_((torch.rand(buf.shape, generator=self.gen, device=self.device) < keep).to(torch.float32) / keep)
+        self.masks = list(self.maskbuf)
+        return True
 
     # ------------------------------------------------------------------ forward (train mode)
     def forward_train(self, x, groups, masks=None, update_moving=True):
         """x: CUDA fp32 (NB, L).  Returns embeddings (NB, E).  Keeps everything backward needs."""
-        lib = self.lib
         nb, length = x.shape
         self._buffers(nb, length, groups)
-        if masks is not None:
-            self.masks = masks
-        else:
-            self._draw_masks(nb)
-        self._pack()
-        self.x_in = x
-        c, ls, st = self.channels, self.ls, _stream()
+        if x.data_ptr() != self.xin.data_ptr():
+            self.xin.copy_(x)
+        self.x_in = self.xin
+        self.groups = groups
+        dropout_on = self._set_masks(nb, masks)
+        key = ("fwd", dropout_on, bool(update_moving), self.sync_allreduce is not None,
+               torch.cuda.current_stream().cuda_stream)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._build_forward_plan(nb, length, groups, update_moving)
+        plan.run()
+        return self.embv
+
+    def _build_forward_plan(self, nb, length, groups, update_moving):
+        lib, plan, st = self.lib, _Plan(), _stream()
+        self._plan_pack(plan, st)
+        c, ls = self.channels, self.ls
+        eps, mom = C.c_float(BN_EPS), C.c_float(BN_MOMENTUM)
         for b in range(4):
             if b == 0:
-                rc = lib.vm_conv1_raw_fwd(_ptr(x), nb, length, c[0], _ptr(self.wraw[0]), _ptr(self.eraw[0]),
-                                          _ptr(self.U[0]), _ptr(self.stat[0]), self.precision, st)
+                plan.launch(lib.vm_conv1_raw_fwd, "train conv block 1", _ptr(self.xin), nb, length, c[0],
+                            _ptr(self.wraw[0]), _ptr(self.eraw[0]), _ptr(self.U[0]), _ptr(self.stat[0]), self.precision,
+                            st)
             else:
-                rc = lib.vm_conv3_raw_fwd(_ptr(self.X[b - 1][0]), _ptr(self.X[b - 1][1]), nb, ls[b], c[b - 1], c[b],
-                                          _ptr(self.wraw[b]), _ptr(self.eraw[b]), _ptr(self.U[b]),
-                                          _ptr(self.stat[b]), 0, self.precision, st)
-            _check(rc, f"train conv block {b + 1}")
+                plan.launch(lib.vm_conv3_raw_fwd, f"train conv block {b + 1}", _ptr(self.X[b - 1][0]),
+                            _ptr(self.X[b - 1][1]), nb, ls[b], c[b - 1], c[b], _ptr(self.wraw[b]), _ptr(self.eraw[b]),
+                            _ptr(self.U[b]), _ptr(self.stat[b]), 0, self.precision, st)
             mm = self.moving[f"bn{b + 1}_mean"] if update_moving else None
             mv = self.moving[f"bn{b + 1}_var"] if update_moving else None
+            gamma, beta = _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"])
             if self.sync_allreduce is None:
-                rc = lib.vm_bn_stats_finalize(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, ls[b], c[b],
-                                              _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
-                                              C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
-                                              _ptr(self.bnc[b]), _ptr(self.red), st)
-                _check(rc, "vm_bn_stats_finalize")
+                plan.launch(lib.vm_bn_stats_finalize, "vm_bn_stats_finalize", _ptr(self.stat[b]), self.stat_rows[b], nb,
+                            groups, ls[b], c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]),
+                            _ptr(self.red), st)
             else:
                 sums = self.sums[1][:groups * c[b] * 2]
-                rc = lib.vm_bn_stats_sums(_ptr(self.stat[b]), self.stat_rows[b], nb, groups, c[b], _ptr(self.red),
-                                          _ptr(sums), st)
-                _check(rc, "vm_bn_stats_sums")
-                self.sync_allreduce(sums)
+                plan.launch(lib.vm_bn_stats_sums, "vm_bn_stats_sums", _ptr(self.stat[b]), self.stat_rows[b], nb, groups,
+                            c[b], _ptr(self.red), _ptr(sums), st)
+                plan.host(lambda sums=sums: self.sync_allreduce(sums))
                 count = float(self.sync_world) * (nb // groups) * ls[b]   # equal shards on every rank
-                rc = lib.vm_bn_stats_from_sums(_ptr(sums), C.c_double(count), groups, c[b],
-                                               _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"]),
-                                               C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), _ptr(mm), _ptr(mv),
-                                               _ptr(self.bnc[b]), st)
-                _check(rc, "vm_bn_stats_from_sums")
+                plan.launch(lib.vm_bn_stats_from_sums, "vm_bn_stats_from_sums", _ptr(sums), C.c_double(count), groups,
+                            c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]), st)
             if b < 3:
-                rc = lib.vm_bn_pool_fwd(_ptr(self.U[b]), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
-                                        _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
-                                        _ptr(self.XB[b][0]), _ptr(self.XB[b][1]), st)
-                _check(rc, "vm_bn_pool_fwd")
+                plan.launch(lib.vm_bn_pool_fwd, "vm_bn_pool_fwd", _ptr(self.U[b]), nb, ls[b], c[b], groups, self.pools[b],
+                            _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
+                            _ptr(self.XB[b][0]), _ptr(self.XB[b][1]), st)
             else:
-                rc = lib.vm_bn_gmax_fwd(_ptr(self.U[3]), nb, ls[3], c[3], groups, _ptr(self.bnc[3]),
-                                        _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.argmax), st)
-                _check(rc, "vm_bn_gmax_fwd")
-        rc = lib.vm_dense_fwd(_ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]), _ptr(self.p["dense_bias"]),
-                              self.emb, _ptr(self.embv), st)
-        _check(rc, "vm_dense_fwd")
-        self.groups = groups
-        return self.embv
+                plan.launch(lib.vm_bn_gmax_fwd, "vm_bn_gmax_fwd", _ptr(self.U[3]), nb, ls[3], c[3], groups,
+                            _ptr(self.bnc[3]), _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.argmax), st)
+        plan.launch(lib.vm_dense_fwd, "vm_dense_fwd", _ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]),
+                    _ptr(self.p["dense_bias"]), self.emb, _ptr(self.embv), st)
+        return plan
 
     def set_sync_bn(self, allreduce, world):
         """allreduce(tensor): in-place SUM over ranks (torch.distributed.all_reduce); world: number of ranks, each
@@ -255,12 +300,20 @@ class TrainEngine:
     # ------------------------------------------------------------------ backward of the encoder
     def backward_encoder(self, d_emb):
         """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters."""
-        lib, st = self.lib, _stream()
-        nb = d_emb.shape[0]
+        if d_emb.data_ptr() != self.d_emb.data_ptr():
+            self.d_emb.copy_(d_emb)
+        key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None,
+               torch.cuda.current_stream().cuda_stream)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._build_backward_plan(self.d_emb.shape[0])
+        plan.run()
+
+    def _build_backward_plan(self, nb):
+        lib, plan, st = self.lib, _Plan(), _stream()
         c, ls, g, groups = self.channels, self.ls, self.g, self.groups
-        rc = lib.vm_dense_bwd(_ptr(self.gmax), _ptr(d_emb), _ptr(self.p["dense_kernel"]), nb, c[3], self.emb,
-                              _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
-        _check(rc, "vm_dense_bwd")
+        plan.launch(lib.vm_dense_bwd, "vm_dense_bwd", _ptr(self.gmax), _ptr(self.d_emb), _ptr(self.p["dense_kernel"]), nb,
+                    c[3], self.emb, _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
         bp = self.bwd_precision
         for b in (3, 2, 1, 0):
             n_u = nb * ls[b] * c[b]
@@ -269,43 +322,39 @@ class TrainEngine:
                 dy, dg, am = None, self.d_gmax, self.argmax
             else:
                 dy, dg, am = self.dX, None, None
+            grads = (_ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]))
             if self.sync_allreduce is None:
-                rc = lib.vm_bn_bwd(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
-                                   self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2), _BWD_CHUNKS,
-                                   _ptr(self.bwc[b]), _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]),
-                                   _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
-                                   _ptr(self.red), st)
-                _check(rc, f"vm_bn_bwd block {b + 1}")
+                plan.launch(lib.vm_bn_bwd, f"vm_bn_bwd block {b + 1}", _ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb,
+                            ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2),
+                            _BWD_CHUNKS, _ptr(self.bwc[b]), *grads, _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1),
+                            _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
             else:
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
-                rc = lib.vm_bn_bwd_sums(_ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
-                                        self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2),
-                                        _BWD_CHUNKS, _ptr(self.red), _ptr(loc), st)
-                _check(rc, f"vm_bn_bwd_sums block {b + 1}")
-                glo.copy_(loc)
-                self.sync_allreduce(glo)
+                plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.U[b]), _ptr(dy), _ptr(dg),
+                            _ptr(am), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
+                            _ptr(self.scr2), _BWD_CHUNKS, _ptr(self.red), _ptr(loc), st)
+
+                def share(loc=loc, glo=glo):
+                    glo.copy_(loc)
+                    self.sync_allreduce(glo)
+                plan.host(share)
                 count = float(self.sync_world) * (nb // groups) * ls[b]
-                rc = lib.vm_bn_bwd_from_sums(_ptr(loc), _ptr(glo), C.c_double(count), _ptr(self.U[b]), _ptr(dy),
-                                             _ptr(dg), _ptr(am), nb, ls[b], c[b], groups, self.pools[b],
-                                             _ptr(self.bnc[b]), _ptr(self.masks[b]), _BWD_CHUNKS, _ptr(self.bwc[b]),
-                                             _ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]), _ptr(du_hi),
-                                             _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
-                                             _ptr(self.red), st)
-                _check(rc, f"vm_bn_bwd_from_sums block {b + 1}")
+                plan.launch(lib.vm_bn_bwd_from_sums, f"vm_bn_bwd_from_sums block {b + 1}", _ptr(loc), _ptr(glo),
+                            C.c_double(count), _ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
+                            self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _BWD_CHUNKS, _ptr(self.bwc[b]), *grads,
+                            _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
             if b == 0:
-                rc = lib.vm_wgrad1(_ptr(self.x_in), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp, _ptr(self.wpart),
-                                   self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
-                _check(rc, "vm_wgrad1")
+                plan.launch(lib.vm_wgrad1, "vm_wgrad1", _ptr(self.xin), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp,
+                            _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
             else:
-                rc = lib.vm_wgrad3(_ptr(self.XB[b - 1][0]), _ptr(self.XB[b - 1][1]), _ptr(du_hi), _ptr(du_lo), nb,
-                                   ls[b], c[b - 1], c[b], bp, _ptr(self.wpart), self.wpart.numel() * 4,
-                                   _ptr(g[f"conv{b + 1}_kernel"]), st)
-                _check(rc, f"vm_wgrad3 block {b + 1}")
+                plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.XB[b - 1][0]), _ptr(self.XB[b - 1][1]),
+                            _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b - 1], c[b], bp, _ptr(self.wpart),
+                            self.wpart.numel() * 4, _ptr(g[f"conv{b + 1}_kernel"]), st)
                 # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
-                rc = lib.vm_conv3_raw_fwd(_ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b], c[b - 1], _ptr(self.wdg[b]),
-                                          _ptr(self.edg[b]), _ptr(self.dX), None, 1, bp, st)
-                _check(rc, f"dgrad block {b + 1}")
+                plan.launch(lib.vm_conv3_raw_fwd, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
+                            c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), _ptr(self.dX), None, 1, bp, st)
+        return plan
 
     # ------------------------------------------------------------------ optimizer
     def apply_gradients(self, world=1):
@@ -325,52 +374,87 @@ class TrainEngine:
         self.eng._packed = False
 
     # ------------------------------------------------------------------ full steps
-    def _to_device(self, a):
-        if isinstance(a, torch.Tensor):
-            t = a
-        else:
-            a = np.asarray(a)
-            if a.ndim == 3:
-                a = a[:, :, 0]
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
-        if t.dim() == 3:
-            t = t.reshape(t.shape[0], t.shape[1])
-        return t.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+    def _stage(self, src, dst):
+        """Host or device data -> the static device buffer ``dst`` without blocking the host: numpy batches (float64
+        from the batcher, voicemap/librispeech.py:103) are cast into a ring of pinned buffers and copied asynchronously,
+        so the host can issue the next step while this one runs."""
+        if isinstance(src, torch.Tensor):
+            t = src.reshape(dst.shape)
+            dst.copy_(t, non_blocking=True)
+            return
+        a = np.asarray(src)
+        if a.ndim == dst.dim() + 1:
+            a = a[..., 0]                      # (N, L, 1) -> (N, L)
+        a = a.reshape(dst.shape)
+        k = self._pin_next
+        self._pin_next = (k + 1) % len(self._pin)
+        slot = self._pin[k]
+        if slot is not None and slot[1] is not None:
+            slot[1].synchronize()              # the copy that used this slot three stagings ago
+        if slot is None or slot[0].numel() < a.size:
+            slot = self._pin[k] = [torch.empty(a.size, dtype=torch.float32).pin_memory(), None]
+        view = slot[0][:a.size].view(dst.shape)
+        view.numpy()[...] = a                  # cast + gather in one pass
+        dst.copy_(view, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+
+    @staticmethod
+    def _clip_shape(x):
+        shape = tuple(x.shape)
+        if len(shape) == 3:
+            if shape[2] != 1:
+                raise ValueError(f"clips must have one channel, got shape {shape}")
+            shape = shape[:2]
+        return shape
 
     def siamese_step(self, x1, x2, y, apply=True, masks=None, allreduce=None, world=1):
-        """One train_on_batch of the siamese model.  Returns (loss, accuracy) as python floats lazily (tensors)."""
-        from .engine import pair_head_loss
-        lib, st = self.lib, _stream()
-        a, b = self._to_device(x1), self._to_device(x2)
-        n = a.shape[0]
-        x = torch.cat([a, b], dim=0)
-        yt = torch.as_tensor(np.asarray(y, dtype=np.float32).reshape(-1)).to(self.device)
-        emb = self.forward_train(x, groups=2, masks=masks)
-        metric = self.model.distance_metric
-        hw = self.p["head_kernel"].reshape(-1)
-        hb = self.p["head_bias"]
-        loss_name = "contrastive" if self.loss == "contrastive_loss" else "binary_crossentropy"
-        prob, _, lossv = pair_head_loss(emb[:n], emb[n:], hw, hb, metric, yt, loss_name)
-        metric_id = {"uniform_euclidean": 0, "weighted_l1": 1}[metric]
-        rc = lib.vm_pair_head_loss_bwd(_ptr(emb), n, self.emb, metric_id, _ptr(hw), _ptr(hb), _ptr(yt),
-                                       1 if self.loss == "contrastive_loss" else 2, C.c_float(self.loss_scale),
-                                       _ptr(self.d_emb), _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), st)
-        _check(rc, "vm_pair_head_loss_bwd")
+        """One train_on_batch of the siamese model.  Returns (loss, accuracy) as 0-d device tensors (no host sync)."""
+        n, length = self._clip_shape(x1)
+        if self._clip_shape(x2) != (n, length):
+            raise ValueError("both inputs of a pair batch must have the same shape")
+        self._buffers(2 * n, length, 2)
+        self._stage(x1, self.xin[:n])
+        self._stage(x2, self.xin[n:])
+        self._stage(np.asarray(y, dtype=np.float32).reshape(-1) if not isinstance(y, torch.Tensor) else y, self.yin)
+        self.forward_train(self.xin, groups=2, masks=masks)
+        key = ("head", torch.cuda.current_stream().cuda_stream)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._build_siamese_head_plan(n)
+        plan.run()
         self.backward_encoder(self.d_emb)
         if allreduce is not None:
             allreduce(self.grad)
         if apply:
             self.apply_gradients(world)
-        acc = ((prob.reshape(-1) > 0.5).to(torch.float32) == yt).to(torch.float32).mean()
-        return lossv.reshape(()), acc
+        acc = ((self.prob.reshape(-1) > 0.5).to(torch.float32) == self.yin).to(torch.float32).mean()
+        return self.lossv.clone().reshape(()), acc
+
+    def _build_siamese_head_plan(self, n):
+        lib, plan, st = self.lib, _Plan(), _stream()
+        metric = self.model.distance_metric
+        metric_id = {"uniform_euclidean": 0, "weighted_l1": 1}[metric]
+        loss_id = 1 if self.loss == "contrastive_loss" else 2
+        hw, hb = self.p["head_kernel"].reshape(-1), self.p["head_bias"]
+        e1, e2 = self.embv[:n], self.embv[n:]
+        plan.launch(lib.vm_pair_head_loss_fwd, "vm_pair_head_loss_fwd", _ptr(e1), _ptr(e2), n, self.emb, metric_id,
+                    _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, None, _ptr(self.prob), _ptr(self.lossv), st)
+        plan.launch(lib.vm_pair_head_loss_bwd, "vm_pair_head_loss_bwd", _ptr(self.embv), n, self.emb, metric_id,
+                    _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, C.c_float(self.loss_scale), _ptr(self.d_emb),
+                    _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), st)
+        return plan
 
     def classifier_step(self, x, y_onehot, apply=True, masks=None, allreduce=None, world=1):
         """Encoder + Dense(softmax) + categorical cross-entropy.  The softmax head is adjacent to the hot path
          and runs as torch device ops."""
-        xd = self._to_device(x)
-        n = xd.shape[0]
-        yt = torch.as_tensor(np.asarray(y_onehot, dtype=np.float32)).to(self.device)
-        emb = self.forward_train(xd, groups=1, masks=masks)
+        n, length = self._clip_shape(x)
+        self._buffers(n, length, 1)
+        self._stage(x, self.xin)
+        yt = torch.as_tensor(np.asarray(y_onehot, dtype=np.float32)).to(self.device, non_blocking=True) \
+            if not isinstance(y_onehot, torch.Tensor) else y_onehot.to(self.device, dtype=torch.float32)
+        emb = self.forward_train(self.xin, groups=1, masks=masks)
         hk, hb = self.p["head_kernel"], self.p["head_bias"]
         logits = emb @ hk + hb
         logp = torch.log_softmax(logits, dim=-1)
