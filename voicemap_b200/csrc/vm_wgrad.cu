@@ -142,9 +142,14 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
         float v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + tap * 128 + g * 32, v);
         if (ci < p.cin) {
+          // a thread owns 32 consecutive floats of its row (one 128-byte line): 16-byte stores instead of 32 scalar
+          // ones, which each touched a different sector per lane (cout % 8 == 0, so a float4 is all in or all out)
+          float4* r4 = reinterpret_cast<float4*>(row + g * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (co0 + g * 32 + j < p.cout) row[g * 32 + j] = any ? v[j] : 0.f;
+          for (int k = 0; k < 8; ++k)
+            if (co0 + g * 32 + 4 * k < p.cout)
+              r4[k] = any ? make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3])
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }
