@@ -62,11 +62,15 @@ __global__ void rowsum_stage1_kernel(const float* __restrict__ m, size_t rows_pe
   }
 }
 __device__ __forceinline__ double2 rowsum_stage2(const double2* __restrict__ tmp, int g, int C, int c) {
+  // all kRB loads are issued before the first add (the sum order stays rb = 0, 1, ...: deterministic)
+  double2 v[kRB];
+#pragma unroll
+  for (int rb = 0; rb < kRB; ++rb) v[rb] = tmp[(size_t(g) * kRB + rb) * C + c];
   double a = 0.0, b = 0.0;
+#pragma unroll
   for (int rb = 0; rb < kRB; ++rb) {
-    const double2 v = tmp[(size_t(g) * kRB + rb) * C + c];
-    a += v.x;
-    b += v.y;
+    a += v[rb].x;
+    b += v[rb].y;
   }
   return make_double2(a, b);
 }
