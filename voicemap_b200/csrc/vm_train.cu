@@ -162,6 +162,7 @@ __global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const
 // ---------------------------------------------------------------------------------------------
 // BN affine (+ dropout mask) + MaxPool -> (hi, lo) planes.  One thread = 4 channels of one pooled position.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G, int pool,
                                    const float4* __restrict__ bn_const, const float* __restrict__ mask,
                                    __half* __restrict__ out_hi, __half* __restrict__ out_lo,
@@ -169,33 +170,41 @@ __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, in
   const int lout = L / pool;
   const int c4n = C >> 2;
   const size_t total = size_t(N) * lout * c4n;
-  for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += size_t(gridDim.x) * blockDim.x) {
-    const int c4 = int(idx % c4n);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  // One item = one pooled output of 4 adjacent channels (pool <= 4 rows of 16 bytes).  Two items per iteration: the rows
+  // of both are loaded before either is reduced (with pool = 2 one item keeps only 32 bytes per thread in flight).
+  struct Item {
+    float4 x[4];
+    int c4, j, n;
+  };
+  auto load_item = [&](size_t idx, Item& it) {
+    it.c4 = int(idx % c4n);
     const size_t nj = idx / c4n;
-    const int j = int(nj % lout);
-    const int n = int(nj / lout);
-    const int g = n / (N / G);
-    float sv[4], tv[4], best[4];
+    it.j = int(nj % lout);
+    it.n = int(nj / lout);
+    const float* up = u + (size_t(it.n) * L + size_t(it.j) * pool) * C + 4 * it.c4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      it.x[i] = (i < pool) ? *reinterpret_cast<const float4*>(up + size_t(i) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto finish_item = [&](const Item& it) {
+    const int g = it.n / (N / G);
+    float best[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 bc = bn_const[size_t(g) * C + 4 * c4 + k];
-      const float mk = mask ? mask[size_t(n) * C + 4 * c4 + k] : 1.f;
-      sv[k] = bc.x * mk;
-      tv[k] = bc.y * mk;
-      best[k] = -INFINITY;
-    }
-    for (int i = 0; i < pool; ++i) {
-      const float4 x = *reinterpret_cast<const float4*>(u + (size_t(n) * L + size_t(j) * pool + i) * C + 4 * c4);
-      best[0] = fmaxf(best[0], fmaf(sv[0], x.x, tv[0]));
-      best[1] = fmaxf(best[1], fmaf(sv[1], x.y, tv[1]));
-      best[2] = fmaxf(best[2], fmaf(sv[2], x.z, tv[2]));
-      best[3] = fmaxf(best[3], fmaf(sv[3], x.w, tv[3]));
+      const float4 bc = bn_const[size_t(g) * C + 4 * it.c4 + k];
+      const float mk = mask ? mask[size_t(it.n) * C + 4 * it.c4 + k] : 1.f;
+      const float sv = bc.x * mk, tv = bc.y * mk;
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < pool) m = fmaxf(m, fmaf(sv, f4get(it.x[i], k), tv));
+      best[k] = m;
     }
     __half h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) split_f32(best[k], h[k], l[k]);
-    const size_t o = (size_t(n) * lout + j) * C + 4 * c4;
+    const size_t o = (size_t(it.n) * lout + it.j) * C + 4 * it.c4;
     *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(
         uint32_t(__half_as_ushort(h[0])) | (uint32_t(__half_as_ushort(h[1])) << 16),
         uint32_t(__half_as_ushort(h[2])) | (uint32_t(__half_as_ushort(h[3])) << 16));
@@ -211,6 +220,14 @@ __global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, in
       *reinterpret_cast<uint2*>(bf_lo + o) = make_uint2(uint32_t(bl[0]) | (uint32_t(bl[1]) << 16),
                                                         uint32_t(bl[2]) | (uint32_t(bl[3]) << 16));
     }
+  };
+  for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += 2 * stride) {
+    Item a, b;
+    const bool two = (idx + stride < total);
+    load_item(idx, a);
+    if (two) load_item(idx + stride, b);
+    finish_item(a);
+    if (two) finish_item(b);
   }
 }
 
@@ -402,7 +419,6 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
 // ---------------------------------------------------------------------------------------------
 // Thread layout of the two big elementwise passes: one thread owns 4 adjacent channels (float4 loads, 8-byte plane
 // stores); a block of 128 threads covers C/4 channel groups x (512/C) interleaved position streams.
-__device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
 // arg-max of s*u + t over a pool window == arg-max of u (s >= 0) or arg-min of u (s < 0); first winner on ties
 __device__ __forceinline__ void window_argmax4(const float* __restrict__ up, int C, int pool, const float (&s)[4],
