@@ -15,9 +15,15 @@ Sampling distributions are the reference's:
     (voicemap/librispeech.py:157-165);
   * labels of a verification batch are 0 (same speaker) for the first half and 1 for the second (:179-194).
 
-Extensions (keyword-only): ``reader`` plugs in any decoder ``path -> (samples, rate)`` (``soundfile`` is the default
-and is imported lazily), ``index`` injects a ready index table so the batcher runs without the corpus on disk,
-``data_path`` replaces ``config.PATH``.
+Decoding: the reference calls ``soundfile.read`` (voicemap/librispeech.py:104,267); the default here is
+``audio_io.read`` -- our own C FLAC decoder (``csrc/vm_flac.c``, bit-exact, no dependency), ``wave`` for .wav,
+``soundfile`` for anything else if it is installed.  With the default reader a corpus is indexed from the FLAC stream
+headers (4 KB per file) instead of decoding every utterance, and the clips of a batch are decoded on a thread pool
+(the decoder runs outside the GIL); random fragment offsets are still drawn in batch order on the calling thread.
+
+Extensions (keyword-only): ``reader`` plugs in any decoder ``path -> (samples, rate)``, ``index`` injects a ready index
+table so the batcher runs without the corpus on disk, ``data_path`` replaces ``config.PATH``, ``decode_workers`` sizes
+the thread pool (default: up to 16, 0/1 = decode on the calling thread).
 """
 from __future__ import annotations
 
@@ -27,6 +33,7 @@ from collections import defaultdict
 import numpy as np
 import pandas as pd
 
+from . import audio_io
 from .config import LIBRISPEECH_SAMPLING_RATE, PATH
 from .keras_compat import Sequence
 
@@ -38,13 +45,14 @@ _SPEAKER_FIELDS = ('id', 'sex', 'subset', 'minutes', 'name')
 _FILE_FIELDS = ('id', 'filepath', 'length', 'seconds')
 
 
-def _soundfile_reader(path):
-    try:
-        import soundfile
-    except ImportError as exc:  # pragma: no cover - depends on the environment
-        raise ImportError('decoding LibriSpeech FLAC needs the `soundfile` package; alternatively construct '
-                          'LibriSpeechDataset(..., reader=callable(path) -> (samples, samplerate))') from exc
-    return soundfile.read(path)
+def _file_length(path, reader):
+    """Samples in an utterance: from the FLAC header when our decoder is the reader, else by decoding the file."""
+    if reader is audio_io.read and path.lower().endswith('.flac'):
+        frames = audio_io.flac_info(path)['frames']
+        if frames:
+            return frames
+    samples, _ = reader(path)
+    return len(samples)
 
 
 def read_speaker_table(path):
@@ -87,7 +95,7 @@ class LibriSpeechDataset(Sequence):
     """
 
     def __init__(self, subsets, seconds, label='speaker', stochastic=True, pad=False, cache=True, *,
-                 reader=None, index=None, data_path=None):
+                 reader=None, index=None, data_path=None, decode_workers=None):
         assert label in _LABEL_KINDS, "Label type must be one of ('sex', 'speaker')"
         self.subset = subsets
         self.label = label
@@ -95,7 +103,8 @@ class LibriSpeechDataset(Sequence):
         self.pad = pad
         self.fragment_seconds = seconds
         self.fragment_length = int(seconds * LIBRISPEECH_SAMPLING_RATE)
-        self.reader = reader if reader is not None else _soundfile_reader
+        self.reader = reader if reader is not None else audio_io.read
+        self.decode_workers = decode_workers
         self.data_path = data_path if data_path is not None else PATH
 
         print('Initialising LibriSpeechDataset with minimum length = {}s and subsets = {}'.format(seconds, subsets))
@@ -143,16 +152,16 @@ class LibriSpeechDataset(Sequence):
     @staticmethod
     def index_subset(subset, reader=None, data_path=None):
         """One record {id, filepath, length, seconds} per .flac of ``subset`` (voicemap/librispeech.py:243-281);
-        every file is decoded once to learn its length."""
+        lengths come from the FLAC headers with the default reader, from a full decode with a custom one."""
         from tqdm import tqdm
-        reader = reader if reader is not None else _soundfile_reader
+        reader = reader if reader is not None else audio_io.read
         root = os.path.join(data_path if data_path is not None else PATH, 'data', 'LibriSpeech', subset)
         print('Indexing {}...'.format(subset))
         records = []
         for speaker, path in tqdm(_flac_files(root)):
-            samples, _ = reader(path)
-            records.append({'id': speaker, 'filepath': path, 'length': len(samples),
-                            'seconds': len(samples) / float(LIBRISPEECH_SAMPLING_RATE)})
+            length = _file_length(path, reader)
+            records.append({'id': speaker, 'filepath': path, 'length': length,
+                            'seconds': length / float(LIBRISPEECH_SAMPLING_RATE)})
         return records
 
     # ------------------------------------------------------------------------------------------------ items
@@ -176,18 +185,66 @@ class LibriSpeechDataset(Sequence):
         out[lead:lead + len(piece)] = piece
         return out
 
-    def __getitem__(self, index):
-        samples, _ = self.reader(self._paths[index])
+    def _label(self, index):
         if self.label == 'speaker':
             label = self._speaker[index]
         elif self.label == 'sex':
             label = sex_to_label[self._sex[index]]
         else:
             raise ValueError("Label type must be one of ('sex', 'speaker')")
-        return self._fragment(samples), label
+        return label
+
+    def _native_flac(self, index):
+        return self.reader is audio_io.read and self._paths[index].lower().endswith('.flac')
+
+    def _draw_fragment(self, length):
+        """The random draws of ``_fragment`` for a file of ``length`` samples, in the same order, without the audio:
+        (start, samples to take, leading zeros)."""
+        want = self.fragment_length
+        start = np.random.randint(0, max(length - want, 1)) if self.stochastic else 0
+        take = max(min(want, length - start), 0)
+        missing = want - take
+        if missing <= 0 or not self.pad:
+            return start, take, 0
+        return start, take, (np.random.randint(0, missing) if self.stochastic else 0)
+
+    def _place(self, piece, take, lead, path):
+        if len(piece) != take:
+            raise ValueError('{}: the index promises {} more samples than the file holds; delete the cached '
+                             '*.index.csv and re-index'.format(path, take - len(piece)))
+        if take == self.fragment_length or not self.pad:
+            return piece
+        out = np.zeros(self.fragment_length, dtype=piece.dtype)
+        out[lead:lead + take] = piece
+        return out
+
+    def __getitem__(self, index):
+        if self._native_flac(index):      # decode only the frames under the fragment
+            start, take, lead = self._draw_fragment(int(self._weight[index]))
+            piece, _ = audio_io.read_flac_range(self._paths[index], start, take)
+            return self._place(piece, take, lead, self._paths[index]), self._label(index)
+        samples, _ = self.reader(self._paths[index])
+        return self._fragment(samples), self._label(index)
+
+    def _items(self, rows):
+        """``[self[r] for r in rows]`` with the files decoded concurrently.  Every random draw happens on the calling
+        thread in row order -- before decoding when the file lengths are known from the index (FLAC + our decoder: only
+        the fragment is decoded), after it otherwise -- so the random stream is the one the serial loop consumes."""
+        rows = [int(r) for r in rows]
+        workers = self.decode_workers
+        if all(self._native_flac(r) for r in rows):
+            plans = [self._draw_fragment(int(self._weight[r])) for r in rows]
+            jobs = [(self._paths[r], start, take) for r, (start, take, _) in zip(rows, plans)]
+            pieces = audio_io.read_many(jobs, reader=audio_io.read_flac_range, workers=workers)
+            return [(self._place(piece, take, lead, self._paths[r]), self._label(r))
+                    for r, (_, take, lead), (piece, _) in zip(rows, plans, pieces)]
+        if workers is None and self.reader is not audio_io.read:
+            workers = 1                      # a user-supplied Python reader gains nothing from threads
+        decoded = audio_io.read_many([self._paths[r] for r in rows], reader=self.reader, workers=workers)
+        return [(self._fragment(samples), self._label(r)) for r, (samples, _) in zip(rows, decoded)]
 
     def _clips(self, rows):
-        return np.stack([self[int(r)][0] for r in rows])
+        return np.stack([clip for clip, _ in self._items(rows)])
 
     # ------------------------------------------------------------------------------------------------ draws
     def _draw(self, count, among=None):
@@ -246,6 +303,6 @@ class LibriSpeechDataset(Sequence):
         support = [self._draw(n, among=same[same != query])]
         rivals = np.random.choice(np.asarray([s for s in self._members if s != speaker]), k - 1, replace=False)
         support.extend(self._draw(n, among=self._members[r]) for r in rivals)
-        items = [self[int(r)] for r in np.concatenate(support)]
+        items = self._items(np.concatenate(support))
         clips, labels = zip(*items)
         return query_sample, (np.stack(clips), np.stack(labels))
