@@ -5,10 +5,18 @@ TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 module.  The product path (``voicemap_b200``) never does: it fails loudly when
 the CUDA library is missing.
 
-PARITY UNPINNED.  The reference (oscarknagg/voicemap @ dd79c69) is Python 2.7 on
-Keras 2.2.2 / tensorflow-gpu 1.10.1 and cannot run in this image; its own tests
-(``tests/tests.py``) never build a model, so there are no golden activations,
-embeddings or losses to pin this restatement against.  What is pinned:
+PARITY UNPINNED against Keras itself.  The reference (oscarknagg/voicemap @ dd79c69) is Python 2.7 on
+Keras 2.2.2 / tensorflow-gpu 1.10.1, neither of which exists in this image, and its own tests
+(``tests/tests.py``) never build a model, so no golden activation computed BY KERAS exists.
+What is pinned:
+  * against the reference's own source, executed in the build container: ``voicemap/models.py``
+    (imported unchanged) and ``voicemap/utils.py`` run against a numpy stand-in for the Keras symbols
+    they use (``tests/golden/keras_standin.py``); the resulting embeddings, block activations, siamese
+    outputs of both heads, contrastive losses, preprocessing outputs and n-shot decision counts are
+    committed as ``tests/golden/reference_executed.npz`` and this oracle reproduces them to 1e-11
+    (``tests/test_reference_golden.py``).  That fixes architecture, wiring, heads, loss,
+    preprocessing and evaluation rules to the reference's code; the arithmetic inside each Keras
+    layer is a restatement there too (independent of this file: numpy, other formulations);
   * ``whiten`` against the one known-answer the reference's tests hold
     (``tests/tests.py:71-90``: zero mean, RMS 0.038021 for a repeated clip) and
     against a literal transcription of the reference's tile/transpose arithmetic;
