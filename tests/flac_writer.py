@@ -278,3 +278,74 @@ def id3v2_tag(payload_size):
     size = bytes([(payload_size >> 21) & 0x7f, (payload_size >> 14) & 0x7f, (payload_size >> 7) & 0x7f,
                   payload_size & 0x7f])
     return b"ID3\x04\x00\x00" + size + bytes(payload_size)
+
+
+# ------------------------------------------------------------------------------------------------ fast paths
+_CRC16_TABLE = []
+for _i in range(256):
+    _c = _i << 8
+    for _ in range(8):
+        _c = ((_c << 1) ^ 0x8005) & 0xffff if _c & 0x8000 else (_c << 1) & 0xffff
+    _CRC16_TABLE.append(_c)
+
+
+def _crc16_fast(data):
+    c = 0
+    table = _CRC16_TABLE
+    for byte in data:
+        c = ((c << 8) & 0xffff) ^ table[(c >> 8) ^ byte]
+    return c
+
+
+def encode_flac_quick(pcm, rate=16000, blocksize=4096, constant=None):
+    """16-bit mono stream for corpus-sized test data, built with array operations instead of per-sample bit writes:
+    VERBATIM subframes (byte aligned for 16-bit samples) or, with `constant` = (value, total_samples), CONSTANT
+    subframes (a whole file in a few hundred bytes)."""
+    if constant is not None:
+        value, total = constant
+        pcm = None
+    else:
+        pcm = np.asarray(pcm).astype(np.int64)
+        total = len(pcm)
+    frames = []
+    start = 0
+    number = 0
+    while start < total:
+        n = min(blocksize, total - start)
+        w = BitWriter()
+        w.put(0x7ffc, 15)
+        w.put(0, 1)
+        bs_code = _BLOCK_CODES.get(n, 6 if n <= 256 else 7)
+        w.put(bs_code, 4)
+        w.put(_RATE_CODES[rate], 4)
+        w.put(0, 4)
+        w.put(_BITS_CODES[16], 3)
+        w.put(0, 1)
+        for byte in _utf8_number(number):
+            w.put(byte, 8)
+        if bs_code == 6:
+            w.put(n - 1, 8)
+        elif bs_code == 7:
+            w.put(n - 1, 16)
+        w.put(crc8(w.bytes()), 8)
+        if pcm is None:
+            body = w.bytes() + bytes([0x00]) + int(value).to_bytes(2, "big", signed=True)
+        else:
+            body = w.bytes() + bytes([0x02]) + pcm[start:start + n].astype(">i2").tobytes()
+        frames.append(body + _crc16_fast(body).to_bytes(2, "big"))
+        start += n
+        number += 1
+    if pcm is None:
+        md5 = bytes(16)
+    else:
+        md5 = hashlib.md5(pcm.astype("<i2").tobytes()).digest()
+    info = BitWriter()
+    info.put(blocksize, 16)
+    info.put(blocksize, 16)
+    info.put(min(map(len, frames)), 24)
+    info.put(max(map(len, frames)), 24)
+    info.put(rate, 20)
+    info.put(0, 3)
+    info.put(15, 5)
+    info.put(total, 36)
+    return b"fLaC" + bytes([0x80]) + (34).to_bytes(3, "big") + info.bytes() + md5 + b"".join(frames)
