@@ -83,7 +83,9 @@ def test_reference_test_file_passes_against_the_drop_in(tmp_path):
 def test_items_equal_the_reference_batchers_items(tmp_path):
     """voicemap/librispeech.py itself, imported unchanged, against ours on the same FLAC tree: identical index tables,
     identical clips and labels for every item in every (stochastic, pad, label) mode, and identical consumption of the
-    numpy random stream -- including through our fragment-only, threaded batch path."""
+    numpy random stream -- including through our fragment-only, threaded batch path; and, seed by seed, the very same
+    alike / differing pairs and k-way n-shot tasks (our array-based draws make the calls on numpy's global RandomState
+    that pandas' DataFrame.sample makes for the reference)."""
     _write_corpus(str(tmp_path))
     script = os.path.join(ROOT, "tests", "golden", "run_reference_batcher.py")
     run = subprocess.run([sys.executable, "-W", "ignore", script, str(tmp_path)], cwd=str(tmp_path),
@@ -91,4 +93,4 @@ def test_items_equal_the_reference_batchers_items(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     verdict = json.loads(run.stdout.strip().splitlines()[-1])
-    assert verdict["mismatches"] == [] and verdict["items"] == 5 * 126, verdict
+    assert verdict["mismatches"] == [] and verdict["items"] == 5 * 126 and verdict["draws"] == 40, verdict
