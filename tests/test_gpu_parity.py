@@ -260,6 +260,30 @@ def test_predict_pipelined_host_batch_is_bit_identical(stress_params):
     assert np.array_equal(enc.predict(x), whole)                # buffer reuse across calls
 
 
+def test_predict_numpy_float64_is_staged_and_bit_identical(stress_params, monkeypatch):
+    """predict() of a numpy float64 batch (what the batcher and the reference's preprocessing hand over) casts chunk by
+    chunk on worker threads into pinned slots (models._HostStage): same bits as the float32 batch embedded in one
+    launch, with slot recycling, with a staging buffer smaller than the batch, and through the siamese model."""
+    from voicemap_b200 import models as M
+    enc = M.get_baseline_convolutional_encoder(128, 64, dropout=0.0)
+    enc.set_named_weights(stress_params)
+    rng = np.random.default_rng(5)
+    x = O.WHITEN_RMS * rng.standard_normal((700, 2000, 1))       # float64; 700 clips = 6 chunks of 128 > 4 slots
+    eng = enc._get_engine()
+    whole = eng.forward(torch.from_numpy(x[:, :, 0].astype(np.float32)).cuda()).cpu().numpy()
+    assert np.array_equal(enc.predict(x), whole)
+    assert np.array_equal(enc.predict(x[::-1][::-1]), whole)     # non-contiguous view, second call (slots reused)
+    assert np.array_equal(enc.predict(x[:5]), whole[:5])         # n-shot sized batch: a single chunk
+    monkeypatch.setattr(M, "_PIPELINE_BUFFER_BYTES", 4 * 2000 * 256)   # device staging buffer of 256 clips: 3 passes
+    enc._copy_buf = None
+    assert np.array_equal(enc.predict(x), whole)
+    monkeypatch.undo()
+    sia = M.build_siamese_net(enc, (2000, 1))
+    from_numpy = sia.predict([x[:350], x[350:]])
+    from_tensor = sia.predict([torch.from_numpy(x[:350].astype(np.float32)), torch.from_numpy(x[350:].astype(np.float32))])
+    assert from_numpy.shape == (350, 1) and np.array_equal(from_numpy, from_tensor)
+
+
 @pytest.mark.parametrize("precision", [2, 3])
 def test_full_batch_properties(stress_params, precision):
     """BASELINE config[1] size (256 clips x 12000): batch-composition independence (bit-exact), permutation

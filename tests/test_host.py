@@ -507,3 +507,42 @@ def test_precision_is_validated_and_survives_clone():
     assert clone_model(enc).precision == 3
     with pytest.raises(ValueError):
         enc.precision = 4
+
+
+def test_host_stage_casts_in_order_and_recycles_slots(monkeypatch):
+    """_HostStage (predict() on numpy batches): every chunk is the float32 cast of its rows, chunks come in order, and
+    a slot is only reused after its consumer's copy event -- checked with pinning stubbed out (no CUDA here)."""
+    import torch
+    from voicemap_b200 import models as M
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    assert M._cast_plan(256) == [(0, 64), (64, 128), (128, 192), (192, 256)]
+    assert M._cast_plan(5) == [(0, 5)] and M._cast_plan(40) == [(0, 16), (16, 32), (32, 40)]
+    for n in (1, 7, 63, 64, 300, 5000):
+        plan = M._cast_plan(n)
+        assert plan[0][0] == 0 and plan[-1][1] == n and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+        assert all(0 < hi - lo <= 128 for lo, hi in plan)
+
+    class Event:
+        def __init__(self, log, tag):
+            self.log, self.tag = log, tag
+
+        def synchronize(self):
+            self.log.append(self.tag)
+
+    stage = M._HostStage()
+    rng = np.random.default_rng(0)
+    batch = rng.normal(size=(1200, 37, 1))  # float64, 10 chunks of 128 rows (the cap) over 4 slots, last one ragged
+    waited, seen = [], []
+    out = np.zeros((1200, 37), dtype=np.float32)
+    for lo, hi, view, slot in stage.chunks(batch[:, :, 0]):
+        assert slot[1] is None               # the previous user's event was awaited and cleared before the cast
+        out[lo:hi] = view.numpy()
+        seen.append((lo, hi))
+        slot[1] = Event(waited, lo)
+    assert seen == [(lo, min(lo + 128, 1200)) for lo in range(0, 1200, 128)]
+    np.testing.assert_array_equal(out, batch[:, :, 0].astype(np.float32))
+    assert waited == [lo for lo, _ in seen[:len(seen) - 4]]      # each recycled slot waited for exactly its own copy
+    # integer and float32 inputs, second call on the same stage (left-over events are awaited first)
+    ints = rng.integers(-5, 5, size=(9, 4))
+    got = np.concatenate([view.numpy().copy() for _, _, view, _ in stage.chunks(ints)])
+    np.testing.assert_array_equal(got, ints.astype(np.float32))

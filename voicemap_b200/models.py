@@ -5,7 +5,9 @@
 from __future__ import annotations
 
 import json
+import os
 from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -36,6 +38,71 @@ def _pipeline_plan(n, pinned=True):
         plan.append((lo, hi))
         lo = hi
     return plan
+
+
+def _cast_plan(n):
+    """[(lo, hi), ...]: staging chunks of a numpy batch of n clips -- a quarter of the batch each, 16 .. 128 clips.
+    Every chunk costs the encoder its fixed ~0.06 ms of launches and prologues, so chunks are large; up to four are
+    cast at the same time, one worker thread each.  Measured on the B200 box for 256 x 12000 doubles
+    (tools/predict_numpy_bench.py, profiles/r01_predict_numpy.log): 16 chunks of 16 clips 2.8 ms, 4 chunks of 64 clips
+    1.7 ms, a small first chunk then doubling 1.65 - 1.95 ms, pieces of a chunk on several threads 1.8 - 2.0 ms;
+    the host-side cast alone is 1.5 ms on one thread and a batch that is already float32 and pinned takes 1.05 ms."""
+    rows = int(min(n, 128, max(16, -(-n // 4))))
+    return [(lo, min(n, lo + rows)) for lo in range(0, n, rows)]
+
+
+class _HostStage:
+    """numpy batches (the batcher and the reference's preprocessing hand out float64, voicemap/librispeech.py:103) ->
+    float32 chunks in pinned memory.  The cast is the expensive part of ``predict(numpy)`` -- 1.5 ms (B200 box) to 15 ms
+    (build container) on one host thread for 256 x 12000 doubles, against 0.9 ms of kernels -- so it runs chunk by chunk on worker threads (numpy releases the
+    GIL while it converts), a few chunks ahead of the copy engine, and every chunk is copied and embedded as soon as it
+    is ready.  Slots are pinned once and reused; a slot is recycled after the copy that read it has finished."""
+
+    def __init__(self):
+        try:
+            cpus = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cpus = os.cpu_count() or 1
+        self.workers = max(1, min(4, cpus))
+        self.pool = ThreadPoolExecutor(max_workers=self.workers)
+        self.slots = []          # [pinned float32 tensor, copy-done event or None]
+
+    def _slot(self, k, elems):
+        import torch
+        while len(self.slots) <= k:
+            self.slots.append([None, None])
+        slot = self.slots[k]
+        if slot[1] is not None:
+            slot[1].synchronize()
+            slot[1] = None
+        if slot[0] is None or slot[0].numel() < elems:
+            slot[0] = torch.empty(elems, dtype=torch.float32).pin_memory()
+        return slot
+
+    def chunks(self, src):
+        """src: numpy (n, length) view of any dtype, any strides.  Yields (lo, hi, pinned float32 (hi-lo, length), slot)
+        in order; the consumer stores the event of its copy in ``slot[1]``."""
+        n, length = src.shape
+        plan = _cast_plan(n)
+        count = len(plan)
+        rows = max(hi - lo for lo, hi in plan)
+        depth = min(count, 4)
+        pending = {}
+
+        def submit(i):
+            lo, hi = plan[i]
+            slot = self._slot(i % depth, rows * length)
+            view = slot[0][:(hi - lo) * length].view(hi - lo, length)
+            pending[i] = (self.pool.submit(np.copyto, view.numpy(), src[lo:hi], casting='unsafe'), lo, hi, view, slot)
+
+        for i in range(depth):
+            submit(i)
+        for i in range(count):
+            done, lo, hi, view, slot = pending.pop(i)
+            done.result()
+            yield lo, hi, view, slot
+            if i + depth < count:
+                submit(i + depth)
 
 
 def _glorot_uniform(shape, rng):
@@ -344,6 +411,14 @@ class EncoderModel(_ModelBase):
         """x_dev: CUDA fp32 (N, L[, 1]) -> CUDA (N, embedding_dimension)."""
         return self._get_engine().forward(x_dev)
 
+    def _check_input_shape(self, shape):
+        if len(shape) != 3 or shape[2] != 1:
+            raise ValueError(f"Error when checking input: expected input to have shape (N, L, 1) but got array "
+                             f"with shape {shape}")
+        if self.input_shape is not None and tuple(shape[1:]) != tuple(self.input_shape):
+            raise ValueError(f"Error when checking input: expected conv1d_1_input to have shape "
+                             f"{self.input_shape} but got array with shape {shape[1:]}")
+
     def _host_batch(self, x):
         """numpy (N, L, 1) of any float dtype, or a torch CPU tensor (N, L[, 1]) (pinned memory makes the
         host->device copy asynchronous) -> contiguous float32 torch CPU tensor (N, L)."""
@@ -357,12 +432,7 @@ class EncoderModel(_ModelBase):
         else:
             x = np.asarray(x)
             shape = x.shape
-        if len(shape) != 3 or shape[2] != 1:
-            raise ValueError(f"Error when checking input: expected input to have shape (N, L, 1) but got array "
-                             f"with shape {shape}")
-        if self.input_shape is not None and tuple(shape[1:]) != tuple(self.input_shape):
-            raise ValueError(f"Error when checking input: expected conv1d_1_input to have shape "
-                             f"{self.input_shape} but got array with shape {shape[1:]}")
+        self._check_input_shape(shape)
         if isinstance(x, torch.Tensor):
             xt = x.reshape(shape[0], shape[1])
             return xt if (xt.dtype == torch.float32 and xt.is_contiguous()) else xt.float().contiguous()
@@ -373,12 +443,23 @@ class EncoderModel(_ModelBase):
         dtype (cast to float32 like Keras' floatx) or a torch CPU tensor.  Returns numpy float32.  ``batch_size``
         is accepted for compatibility; results do not depend on it."""
         import torch
-        xt = self._host_batch(x)
-        if xt.shape[0] == 0:     # an empty batch yields an empty result (as numpy-style APIs do); nothing to launch
+        if isinstance(x, torch.Tensor):
+            xt = self._host_batch(x)
+            count = xt.shape[0]
+        else:
+            x = np.asarray(x)
+            self._check_input_shape(x.shape)
+            count = x.shape[0]
+        if count == 0:           # an empty batch yields an empty result (as numpy-style APIs do); nothing to launch
             units = self._head["units"] if self._head is not None else self.embedding_dimension
             return np.zeros((0, units), dtype=np.float32)
         eng = self._get_engine()
-        emb = self._embed_pipelined(xt, eng)
+        if isinstance(x, torch.Tensor):
+            emb = self._embed_pipelined(xt, eng)
+        else:
+            emb = torch.empty((count, self.embedding_dimension), dtype=torch.float32, device=eng.device)
+            self._stage_numpy(x[:, :, 0], eng,
+                              lambda xin, lo, hi, base: eng.forward(xin[lo:hi], out=emb[base + lo:base + hi]))
         if self._head is not None:
             emb = self._apply_head(emb)
         return emb.cpu().numpy()
@@ -413,6 +494,48 @@ class EncoderModel(_ModelBase):
                 main.wait_event(copied)
                 eng.forward(xin[lo:hi], out=out[base + lo:base + hi])
         return out
+
+    def _device_input(self, eng, rows, length):
+        import torch
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=eng.device)
+            self._copy_buf = None
+        if self._copy_buf is None or self._copy_buf.numel() < rows * length:
+            self._copy_buf = torch.empty(rows * length, dtype=torch.float32, device=eng.device)
+        return self._copy_buf[:rows * length].view(rows, length)
+
+    def _stage_numpy(self, src, eng, on_chunk=None, xin=None):
+        """numpy (n, length), any dtype -> float32 on the device, through ``_HostStage``: cast on worker threads into
+        pinned chunks, asynchronous copies on the side stream.  ``on_chunk(xin, lo, hi, base)`` is called once rows
+        [lo, hi) of the device buffer ``xin`` -- batch rows [base + lo, base + hi) -- are ordered before the main
+        stream; a batch larger than the staging buffer goes through it in passes (``base`` > 0).  With a caller-owned
+        ``xin`` (n rows) and no callback the main stream just waits for the whole batch."""
+        import torch
+        n, length = src.shape
+        if getattr(self, "_host_stage", None) is None:
+            self._host_stage = _HostStage()
+        if xin is None:
+            rows = max(1, min(n, _PIPELINE_BUFFER_BYTES // (4 * length)))
+            xin = self._device_input(eng, rows, length)
+        else:
+            rows = n
+            self._device_input(eng, 1, 1)               # makes sure the copy stream exists
+        main = torch.cuda.current_stream(eng.device)
+        for base in range(0, n, rows):
+            m = min(rows, n - base)
+            self._copy_stream.wait_stream(main)         # earlier kernels that read the buffer are done
+            for lo, hi, view, slot in self._host_stage.chunks(src[base:base + m]):
+                with torch.cuda.stream(self._copy_stream):
+                    xin[lo:hi].copy_(view, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(self._copy_stream)
+                slot[1] = copied
+                if on_chunk is not None:
+                    main.wait_event(copied)
+                    on_chunk(xin, lo, hi, base)
+            if on_chunk is None:
+                main.wait_stream(self._copy_stream)
+        return xin
 
     def predict_raw(self, x, downsampling=4, whitening=True):
         """Embeddings of RAW clips (N, T, 1) (e.g. 48000 samples of 16 kHz audio): equivalent to
@@ -539,9 +662,16 @@ class SiameseModel(_ModelBase):
         from .engine import pair_head_loss
         if not isinstance(x, (list, tuple)) or len(x) != 2:
             raise ValueError("Error when checking model input: the siamese network expects a list of 2 arrays")
-        x1 = self.encoder._host_batch(x[0])
-        x2 = self.encoder._host_batch(x[1])
-        if x1.shape != x2.shape:
+        sides = []
+        for side in x:          # torch CPU tensors go through _host_batch; numpy batches are cast while they are staged
+            if isinstance(side, torch.Tensor):
+                sides.append(self.encoder._host_batch(side))
+            else:
+                side = np.asarray(side)
+                self.encoder._check_input_shape(side.shape)
+                sides.append(side[:, :, 0])
+        x1, x2 = sides
+        if tuple(x1.shape) != tuple(x2.shape):
             raise ValueError(f"siamese inputs must have the same shape, got {tuple(x1.shape)} and {tuple(x2.shape)}")
         if (x1.shape[1], 1) != self.input_shape:
             raise ValueError(f"Error when checking input: expected input_1 to have shape {self.input_shape} but got "
@@ -556,8 +686,11 @@ class SiameseModel(_ModelBase):
             n = min(half, x1.shape[0] - i)
             # both branches share weights and eval-mode BN: run them as one 2n-clip batch
             xb = torch.empty((2 * n, x1.shape[1]), dtype=torch.float32, device=eng.device)
-            xb[:n].copy_(x1[i:i + n], non_blocking=True)
-            xb[n:].copy_(x2[i:i + n], non_blocking=True)
+            for part, dst in ((x1, xb[:n]), (x2, xb[n:])):
+                if isinstance(part, torch.Tensor):
+                    dst.copy_(part[i:i + n], non_blocking=True)
+                else:
+                    self.encoder._stage_numpy(part[i:i + n], eng, xin=dst)
             emb = eng.forward(xb)
             prob, _, _ = pair_head_loss(emb[:n], emb[n:], w, b, self.distance_metric)
             outs.append(prob)
