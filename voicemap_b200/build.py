@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libvoicemap_b200.so")
 IO_LIB_PATH = os.path.join(HERE, "libvoicemap_io.so")
 IO_SOURCES = ["vm_flac.c"]
 IO_HEADERS = [os.path.join("..", "..", "include", "voicemap_io.h")]
-CC_FLAGS = ["-O3", "-std=c99", "-Wall", "-Wextra", "-fPIC", "-shared"]
+CC_FLAGS = ["-O3", "-std=c99", "-Wall", "-Wextra", "-fwrapv", "-fPIC", "-shared"]  # -fwrapv: hostile streams may overflow the predictor
 SOURCES = ["vm_api.cu", "vm_conv1.cu", "vm_conv3.cu", "vm_head.cu", "vm_train.cu", "vm_wgrad.cu"]
 HEADERS = ["vm_common.cuh", "vm_kernels.h", os.path.join("..", "..", "include", "voicemap_b200.h")]
 NVCC_FLAGS = [
