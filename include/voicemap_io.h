@@ -33,7 +33,8 @@ extern "C" {
 #define VMIO_ERR_CAPACITY (-9)    /* output buffer too small for the decoded stream */
 #define VMIO_ERR_RESIDUAL (-10)   /* residual partitioning inconsistent with the block size / predictor order */
 #define VMIO_ERR_NOMEM (-11)      /* scratch allocation failed */
-#define VMIO_ERR_IO (-12)         /* file could not be opened / read (vmio_flac_read_file only) */
+#define VMIO_ERR_IO (-12)         /* file could not be opened / read */
+#define VMIO_ERR_SHORT (-13)      /* a file holds fewer samples than the caller's index promised */
 
 typedef struct vmio_flac_info {
     uint32_t sample_rate;
@@ -70,6 +71,16 @@ int64_t vmio_flac_decode(const uint8_t* data, size_t len, int32_t* out_i32, doub
  * first) or a negative VMIO_ERR_* code. */
 int64_t vmio_flac_decode_range(const uint8_t* data, size_t len, uint64_t start, uint64_t count, int32_t* out_i32,
                                double* out_f64, vmio_flac_info* info);
+
+/* One batch of training clips in one call: row i of `out` (n rows of `want` doubles, the (B, T) array of
+ * voicemap/librispeech.py:179-186 before its channel axis is added) becomes `lead[i]` zeros, samples
+ * [start[i], start[i] + count[i]) of the mono file paths[i] scaled like vmio_flac_decode's f64 output, and zeros up to
+ * `want` -- i.e. `__getitem__`'s crop and padding (voicemap/librispeech.py:105-124) with the random offsets chosen by the
+ * caller.  `lead` may be NULL (no leading zeros).  Files are read and decoded on up to `threads` threads (the calling
+ * thread included), each decoding only the frames under its fragment.  Returns 0, or the first error with its row in
+ * *failed_row (optional); VMIO_ERR_SHORT when a file ends before start + count. */
+int vmio_flac_read_fragments(const char* const* paths, const uint64_t* start, const uint64_t* count, const uint64_t* lead,
+                             size_t n, double* out, size_t want, int threads, int64_t* failed_row);
 
 /* Same as vmio_flac_decode for a file on disk (read fully into scratch memory first). */
 int64_t vmio_flac_read_file(const char* path, int32_t* out_i32, double* out_f64, uint64_t capacity_frames,

@@ -57,7 +57,7 @@ def test_header_symbols_exported_and_bound(io_library):
     text = open(os.path.join(ROOT, "include", "voicemap_io.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     declared = sorted(set(re.findall(r"\b(vmio_[a-z0-9_]+)\s*\(", text)))
-    assert declared == sorted(audio_io.SIGNATURES) and len(declared) == 7
+    assert declared == sorted(audio_io.SIGNATURES) and len(declared) == 8
     lib = ctypes.CDLL(io_library)
     for name in declared:
         assert hasattr(lib, name)
@@ -392,6 +392,43 @@ def test_batcher_reads_a_real_flac_corpus(tmp_path):
         batches.append((left, right, query, support))
     for a, b in zip(*batches):
         np.testing.assert_array_equal(a, b)
+
+
+def test_read_fragments_batch_call(tmp_path):
+    """The native batch reader: crop, leading / trailing zeros, thread counts, and its error reports."""
+    paths, pcms = [], []
+    for i in range(9):
+        pcm = _speechlike(5000 + 300 * i, seed=40 + i)[:, 0]
+        path = tmp_path / f"{i}.flac"
+        path.write_bytes(encode_flac(pcm, 16000, 16, 1024, kind="fixed", fixed_order=2))
+        paths.append(str(path))
+        pcms.append(pcm)
+    rng = np.random.default_rng(3)
+    want = 4000
+    starts = [int(rng.integers(0, len(p) - 3000)) for p in pcms]
+    counts = [int(rng.integers(0, 3000)) for _ in pcms]
+    counts[0], counts[1] = 0, want                 # an empty fragment and one that fills the clip
+    starts[1] = 17
+    leads = [int(rng.integers(0, want - c + 1)) for c in counts]
+    expect = np.zeros((9, want))
+    for i, pcm in enumerate(pcms):
+        expect[i, leads[i]:leads[i] + counts[i]] = pcm[starts[i]:starts[i] + counts[i]] / 32768.0
+    for workers in (1, 3, 16):
+        np.testing.assert_array_equal(audio_io.read_fragments(paths, starts, counts, want, leads, workers=workers), expect)
+    no_lead = audio_io.read_fragments(paths[:2], [5, 6], [10, 20], 25)
+    np.testing.assert_array_equal(no_lead[1, :20], pcms[1][6:26] / 32768.0)
+    assert not no_lead[0, 10:].any() and audio_io.read_fragments([], [], [], 10).shape == (0, 10)
+
+    with pytest.raises(audio_io.AudioDecodeError, match="3.flac.*fewer samples"):     # row 3 asks past its file's end
+        audio_io.read_fragments(paths, [0, 0, 0, len(pcms[3]) - 50, 0, 0, 0, 0, 0], [100] * 9, want, [0] * 9, workers=2)
+    with pytest.raises(audio_io.AudioDecodeError, match="could not be read"):
+        audio_io.read_fragments(paths[:2] + [str(tmp_path / "nope.flac")], [0] * 3, [10] * 3, want)
+    with pytest.raises(audio_io.AudioDecodeError, match="exceeds"):
+        audio_io.read_fragments(paths[:1], [0], [want], want, [1])
+    stereo = tmp_path / "stereo.flac"
+    stereo.write_bytes(encode_flac(_speechlike(2048, channels=2), 16000, 16, 1024, kind="fixed"))
+    with pytest.raises(audio_io.AudioDecodeError, match="unsupported"):
+        audio_io.read_fragments([str(stereo)], [0], [10], want)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -39,6 +39,8 @@ SIGNATURES = {
     "vmio_flac_probe": (C.c_int, [_u8p, C.c_size_t, _infop]),
     "vmio_flac_decode": (C.c_int64, [_u8p, C.c_size_t, _i32p, _f64p, C.c_uint64, _infop]),
     "vmio_flac_decode_range": (C.c_int64, [_u8p, C.c_size_t, C.c_uint64, C.c_uint64, _i32p, _f64p, _infop]),
+    "vmio_flac_read_fragments": (C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_int64)]),
     "vmio_flac_read_file": (C.c_int64, [C.c_char_p, _i32p, _f64p, C.c_uint64, _infop]),
     "vmio_flac_probe_file": (C.c_int, [C.c_char_p, _infop]),
 }
@@ -145,6 +147,35 @@ def read_flac_range(path, start, count, dtype="float64"):
         return decode_flac_range(data, start, count, dtype)
     except AudioDecodeError as exc:
         raise AudioDecodeError(f"{path}: {exc}") from None
+
+
+def read_fragments(paths, starts, counts, want, leads=None, workers=None):
+    """One batch of clips in one native call: row i of the returned float64 (n, want) array is ``leads[i]`` zeros,
+    samples [starts[i], starts[i] + counts[i]) of the mono FLAC file ``paths[i]`` and zeros up to ``want``.  Files are
+    read and decoded (only the frames under each fragment) on ``workers`` threads inside the library."""
+    lib = load()
+    n = len(paths)
+    out = np.empty((n, int(want)), dtype=np.float64)
+    if n == 0:
+        return out
+    if workers is None:
+        workers = min(n, os.cpu_count() or 1, 16)
+    encoded = [os.fsencode(p) for p in paths]
+    c_paths = (C.c_char_p * n)(*encoded)
+    c_start = np.ascontiguousarray(starts, dtype=np.uint64)
+    c_count = np.ascontiguousarray(counts, dtype=np.uint64)
+    c_lead = np.ascontiguousarray(leads if leads is not None else np.zeros(n), dtype=np.uint64)
+    if not (len(c_start) == len(c_count) == len(c_lead) == n):
+        raise AudioDecodeError("read_fragments: paths, starts, counts and leads must have the same length")
+    if n and int((c_lead + c_count).max()) > int(want):
+        raise AudioDecodeError("read_fragments: lead + count exceeds the clip length")
+    failed = C.c_int64(-1)
+    rc = lib.vmio_flac_read_fragments(c_paths, c_start.ctypes.data, c_count.ctypes.data, c_lead.ctypes.data, n,
+                                      out.ctypes.data, int(want), max(1, int(workers)), C.byref(failed))
+    if rc != 0:
+        where = paths[failed.value] if 0 <= failed.value < n else "<batch>"
+        _fail(rc, f"read_fragments({where})")
+    return out
 
 
 def read_flac(path, dtype="float64"):

@@ -50,7 +50,7 @@ def build_io_library(force: bool = False) -> str:
         raise RuntimeError("gcc not found: cannot build libvoicemap_io.so")
     srcs = [os.path.join(CSRC, s) for s in IO_SOURCES]
     if force or _stale(IO_LIB_PATH, srcs + [os.path.join(CSRC, h) for h in IO_HEADERS]):
-        r = subprocess.run([cc, *CC_FLAGS, "-o", IO_LIB_PATH, *srcs], capture_output=True, text=True)
+        r = subprocess.run([cc, *CC_FLAGS, "-o", IO_LIB_PATH, *srcs, "-lpthread"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("gcc failed:\n" + r.stdout + r.stderr)
     return IO_LIB_PATH

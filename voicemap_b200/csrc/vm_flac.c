@@ -7,6 +7,7 @@
  */
 #include "../../include/voicemap_io.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -416,6 +417,7 @@ const char* vmio_error_string(int code) {
         case VMIO_ERR_RESIDUAL: return "inconsistent residual partitioning";
         case VMIO_ERR_NOMEM: return "out of memory";
         case VMIO_ERR_IO: return "file could not be read";
+        case VMIO_ERR_SHORT: return "file holds fewer samples than requested (stale index?)";
         default: return "unknown error";
     }
 }
@@ -594,3 +596,69 @@ int vmio_flac_probe_file(const char* path, vmio_flac_info* info) {
     }
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------- batch of fragments */
+typedef struct {
+    const char* const* paths;
+    const uint64_t* start;
+    const uint64_t* count;
+    const uint64_t* lead;
+    size_t n, want;
+    double* out;
+    size_t next;         /* next row to claim (atomic) */
+    int error;           /* first error, 0 while none (atomic) */
+    int64_t failed;      /* row of the first error */
+} batch_t;
+
+static int read_fragment(const batch_t* b, size_t i) {
+    double* row = b->out + i * b->want;
+    const uint64_t lead = b->lead ? b->lead[i] : 0, count = b->count[i];
+    if (lead + count > b->want) return VMIO_ERR_ARG;
+    memset(row, 0, sizeof(double) * lead);
+    memset(row + lead + count, 0, sizeof(double) * (b->want - lead - count));
+    if (count == 0) return VMIO_OK;
+    uint8_t* buf = NULL;
+    const int64_t size = slurp(b->paths[i], 0, &buf);
+    if (size < 0) return (int)size;
+    vmio_flac_info info;
+    int64_t got = size == 0 ? VMIO_ERR_NOT_FLAC : vmio_flac_probe(buf, (size_t)size, &info);
+    if (got == VMIO_OK) got = info.channels == 1 ? vmio_flac_decode_range(buf, (size_t)size, b->start[i], count, NULL, row + lead, NULL)
+                                                 : VMIO_ERR_UNSUPPORTED;
+    free(buf);
+    if (got < 0) return (int)got;
+    return (uint64_t)got == count ? VMIO_OK : VMIO_ERR_SHORT;
+}
+
+static void* batch_worker(void* arg) {
+    batch_t* b = (batch_t*)arg;
+    for (;;) {
+        const size_t i = __atomic_fetch_add(&b->next, 1, __ATOMIC_RELAXED);
+        if (i >= b->n || __atomic_load_n(&b->error, __ATOMIC_RELAXED)) break;
+        const int rc = read_fragment(b, i);
+        if (rc) {
+            int none = 0;
+            if (__atomic_compare_exchange_n(&b->error, &none, rc, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+                __atomic_store_n(&b->failed, (int64_t)i, __ATOMIC_RELAXED);
+        }
+    }
+    return NULL;
+}
+
+int vmio_flac_read_fragments(const char* const* paths, const uint64_t* start, const uint64_t* count, const uint64_t* lead,
+                             size_t n, double* out, size_t want, int threads, int64_t* failed_row) {
+    if (failed_row) *failed_row = -1;
+    if (n == 0) return VMIO_OK;
+    if (!paths || !start || !count || !out) return VMIO_ERR_ARG;
+    batch_t b = {paths, start, count, lead, n, want, out, 0, 0, -1};
+    if (threads > 64) threads = 64;
+    if ((size_t)threads > n) threads = (int)n;
+    pthread_t ids[64];
+    int started = 0;
+    for (int t = 1; t < threads; ++t) /* the calling thread is worker 0 */
+        if (pthread_create(&ids[started], NULL, batch_worker, &b) == 0) ++started;
+    batch_worker(&b);
+    for (int t = 0; t < started; ++t) pthread_join(ids[t], NULL);
+    if (b.error && failed_row) *failed_row = b.failed;
+    return b.error;
+}
+

@@ -226,11 +226,35 @@ class LibriSpeechDataset(Sequence):
         samples, _ = self.reader(self._paths[index])
         return self._fragment(samples), self._label(index)
 
+    def _native_clips(self, rows):
+        """(len(rows), fragment_length) float64 batch straight from the decoder library, or None when this dataset
+        cannot use it (custom reader, non-FLAC files, or clips that come out shorter than the fragment length).  The
+        crop offsets and padding splits are drawn here, in row order, exactly as ``__getitem__`` draws them."""
+        if not all(self._native_flac(r) for r in rows):
+            return None
+        state = np.random.get_state()
+        plans = [self._draw_fragment(int(self._weight[r])) for r in rows]
+        if not self.pad and any(take != self.fragment_length for _, take, _ in plans):
+            np.random.set_state(state)           # ragged clips: the per-item path handles them (and redraws)
+            return None
+        starts, takes, leads = zip(*plans) if plans else ((), (), ())
+        try:
+            return audio_io.read_fragments([self._paths[r] for r in rows], starts, takes, self.fragment_length, leads,
+                                           workers=self.decode_workers)
+        except audio_io.AudioDecodeError as exc:
+            if 'fewer samples' in str(exc):
+                raise ValueError('{}; delete the cached *.index.csv and re-index'.format(exc)) from None
+            raise
+
     def _items(self, rows):
         """``[self[r] for r in rows]`` with the files decoded concurrently.  Every random draw happens on the calling
         thread in row order -- before decoding when the file lengths are known from the index (FLAC + our decoder: only
-        the fragment is decoded), after it otherwise -- so the random stream is the one the serial loop consumes."""
+        the fragment is decoded, by the library's own threads), after it otherwise -- so the random stream is the one
+        the serial loop consumes."""
         rows = [int(r) for r in rows]
+        batch = self._native_clips(rows)
+        if batch is not None:
+            return [(batch[i], self._label(r)) for i, r in enumerate(rows)]
         workers = self.decode_workers
         if all(self._native_flac(r) for r in rows):
             plans = [self._draw_fragment(int(self._weight[r])) for r in rows]
@@ -244,6 +268,10 @@ class LibriSpeechDataset(Sequence):
         return [(self._fragment(samples), self._label(r)) for r, (samples, _) in zip(rows, decoded)]
 
     def _clips(self, rows):
+        rows = [int(r) for r in rows]
+        batch = self._native_clips(rows)
+        if batch is not None:
+            return batch
         return np.stack([clip for clip, _ in self._items(rows)])
 
     # ------------------------------------------------------------------------------------------------ draws
