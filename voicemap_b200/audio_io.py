@@ -46,6 +46,7 @@ SIGNATURES = {
 }
 
 _lib = None
+DEFAULT_WORKERS = None   # decoder threads when a call does not say; None = min(items, cores, 16)
 
 
 def load():
@@ -159,7 +160,7 @@ def read_fragments(paths, starts, counts, want, leads=None, workers=None):
     if n == 0:
         return out
     if workers is None:
-        workers = min(n, os.cpu_count() or 1, 16)
+        workers = DEFAULT_WORKERS if DEFAULT_WORKERS is not None else min(n, os.cpu_count() or 1, 16)
     encoded = [os.fsencode(p) for p in paths]
     c_paths = (C.c_char_p * n)(*encoded)
     c_start = np.ascontiguousarray(starts, dtype=np.uint64)
@@ -233,7 +234,7 @@ def read_many(paths, reader=read, workers=None):
     are unpacked (``reader(*p)``).  The FLAC decoder runs outside the GIL, so threads scale with cores."""
     jobs = [p if isinstance(p, tuple) else (p,) for p in paths]
     if workers is None:
-        workers = min(len(jobs), os.cpu_count() or 1, 16)
+        workers = DEFAULT_WORKERS if DEFAULT_WORKERS is not None else min(len(jobs), os.cpu_count() or 1, 16)
     if workers <= 1 or len(jobs) <= 1:
         return [reader(*job) for job in jobs]
     with ThreadPoolExecutor(max_workers=workers) as pool:

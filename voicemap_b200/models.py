@@ -156,7 +156,8 @@ class _ModelBase:
         from .training import fit_generator
         return fit_generator(self, generator, steps_per_epoch=steps_per_epoch, epochs=epochs, verbose=verbose,
                              callbacks=callbacks, validation_data=validation_data,
-                             validation_steps=validation_steps, initial_epoch=initial_epoch)
+                             validation_steps=validation_steps, initial_epoch=initial_epoch, workers=workers,
+                             use_multiprocessing=use_multiprocessing)
 
     def summary(self, print_fn=None):
         lines = ["_" * 65, f"{'Layer (type)':<40}{'Param #':>25}", "=" * 65]

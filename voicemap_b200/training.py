@@ -16,6 +16,7 @@ buffers: the host issues a step in ~0.4 ms and never waits for the device inside
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -555,9 +556,24 @@ def _dist_info():
     return None, 1
 
 
+def _producer_processes(workers, use_multiprocessing):
+    """How many batch-producer processes to fork: Keras' ``workers`` when ``use_multiprocessing`` is set (the reference
+    passes ``multiprocessing.cpu_count()``), capped by the cores this process may use; 0 = stay on the background
+    thread."""
+    import multiprocessing as mp
+    if not use_multiprocessing or not workers or int(workers) <= 1 or 'fork' not in mp.get_all_start_methods():
+        return 0
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(0, min(int(workers), cores, 16)) if cores > 1 else 0
+
+
 def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
-                  validation_steps=None, initial_epoch=0):
-    """model.fit_generator(...) of experiments/train_siamese.py:65-94 / train_classifier.py:120-150."""
+                  validation_steps=None, initial_epoch=0, workers=1, use_multiprocessing=False):
+    """model.fit_generator(...) of experiments/train_siamese.py:65-94 / train_classifier.py:120-150.  ``workers`` > 1
+    with ``use_multiprocessing=True`` (what both scripts pass) forks that many batch producers (``prefetch.py``)."""
     if model.loss is None or model.optimizer is None:
         raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
     is_seq = hasattr(generator, "__getitem__") and hasattr(generator, "__len__")
@@ -579,7 +595,14 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
         cb.set_model(model)
         cb.set_params(dict(epochs=epochs, steps=steps_per_epoch, verbose=verbose))
         cb.on_train_begin()
-    prefetch = _Prefetcher(generator) if not is_seq else None   # Sequences are indexed (and reshuffled) per epoch
+    producers = _producer_processes(workers, use_multiprocessing)
+    if is_seq:
+        prefetch = None                    # Sequences are indexed (and reshuffled) per epoch
+    elif producers:
+        from .prefetch import ProcessPrefetcher
+        prefetch = ProcessPrefetcher(generator, producers)
+    else:
+        prefetch = _Prefetcher(generator)
     val_iter = None
     if validation_data is not None and not isinstance(validation_data, (tuple, list)):
         val_iter = iter(validation_data)
@@ -588,8 +611,15 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
         for cb in callbacks:
             cb.on_epoch_begin(epoch)
         losses, accs = [], []
+        ordered = None
+        if is_seq and producers and steps_per_epoch > 1:
+            from .prefetch import SequencePrefetcher
+            ordered = SequencePrefetcher(generator, [s % len(generator) for s in range(steps_per_epoch)], producers)
         for step in range(steps_per_epoch):
-            batch = prefetch.next() if prefetch is not None else generator[step % len(generator)]
+            if ordered is not None:
+                batch = ordered.next()
+            else:
+                batch = prefetch.next() if prefetch is not None else generator[step % len(generator)]
             x, y = batch[0], batch[1]
             if trainer.kind == "siamese":
                 lv, acc = trainer.siamese_step(x[0], x[1], y, allreduce=allreduce, world=world)
@@ -597,6 +627,8 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
                 lv, acc = trainer.classifier_step(x, y, allreduce=allreduce, world=world)
             losses.append(lv)
             accs.append(acc)
+        if ordered is not None:
+            ordered.close()
         logs = {"loss": float(torch.stack(losses).mean().item())}
         if "accuracy" in (model.metrics or []) or "acc" in (model.metrics or []):
             logs["acc"] = float(torch.stack(accs).mean().item())
