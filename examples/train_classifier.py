@@ -47,6 +47,9 @@ def main():
     ap.add_argument("--batchsize", type=int, default=64)
     ap.add_argument("--filters", type=int, default=128)
     ap.add_argument("--embedding", type=int, default=64)
+    ap.add_argument("--workers", type=int, default=1,
+                    help="batch producer processes (the reference passes multiprocessing.cpu_count(), "
+                         "experiments/train_siamese.py:71); 1 = one background thread")
     ap.add_argument("--epochs", type=int, default=50)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--eval-tasks", type=int, default=500)
@@ -76,6 +79,7 @@ def main():
     batches = ShuffledBatches(train, pre, args.batchsize)
     classifier.fit_generator(
         batches, steps_per_epoch=min(args.steps, len(batches)), epochs=args.epochs,
+        workers=args.workers, use_multiprocessing=args.workers > 1,
         callbacks=[NShotEvaluationCallback(args.eval_tasks, 1, 5, valid, preprocessor=pre, mode="classifier"),
                    CSVLogger(os.path.join(args.out, "logs", "classifier.csv"))])
 

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--filters", type=int, default=128)
     ap.add_argument("--embedding", type=int, default=64)
     ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--workers", type=int, default=1,
+                    help="batch producer processes (the reference passes multiprocessing.cpu_count(), "
+                         "experiments/train_siamese.py:71); 1 = one background thread")
     ap.add_argument("--epochs", type=int, default=50)
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--eval-tasks", type=int, default=500)
@@ -64,6 +67,7 @@ def main():
     siamese.fit_generator(
         train_batches, steps_per_epoch=args.steps, epochs=args.epochs,
         validation_data=valid_batches, validation_steps=max(1, args.steps // 5),
+        workers=args.workers, use_multiprocessing=args.workers > 1,
         callbacks=[
             NShotEvaluationCallback(args.eval_tasks, 1, args.k_way, valid, preprocessor=pre),
             CSVLogger(os.path.join(args.out, "logs", tag + ".csv")),
