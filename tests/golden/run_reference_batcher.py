@@ -88,6 +88,28 @@ def main():
             if not (np.array_equal(q1, q2) and l1 == l2 and np.array_equal(s1, s2) and np.array_equal(sl1, sl2)):
                 verdict["mismatches"].append("{}-way {}-shot task, seed {}".format(k, n, seed))
         verdict["draws"] += 1
+    # a reduced index assigned from outside, as experiments/wide_vs_tall.py:55-78 does (fewer speakers, fewer files, the
+    # original ids, a shuffled row order): both batchers must keep drawing the same pairs and tasks from the subset
+    verdict["reduced"] = 0
+    keep = theirs.df[theirs.df["speaker_id"].isin(sorted(theirs.df["speaker_id"].unique())[::2])]
+    keep = keep[keep["id"] % 5 != 0].sample(frac=1.0, random_state=3)
+    theirs.df = keep
+    ours.df = ours.df.loc[keep.index]
+    if len(theirs) != len(ours) or theirs.num_classes() != ours.num_classes():
+        verdict["mismatches"].append("reduced index: sizes")
+    for seed in range(20):
+        np.random.seed(seed)
+        a = [(int(i), int(j)) for i, j in theirs.get_alike_pairs(8)]
+        d = [(int(i), int(j)) for i, j in theirs.get_differing_pairs(8)]
+        (q1, l1), (s1, sl1) = theirs.build_n_shot_task(4, 2)
+        np.random.seed(seed)
+        same = a == ours.get_alike_pairs(8) and d == ours.get_differing_pairs(8)
+        (q2, l2), (s2, sl2) = ours.build_n_shot_task(4, 2)
+        if not (same and np.array_equal(q1, q2) and l1 == l2 and np.array_equal(s1, s2) and np.array_equal(sl1, sl2)):
+            verdict["mismatches"].append("reduced index, seed {}".format(seed))
+        if not set(i for pair in a + d for i in pair) <= set(keep["id"]):
+            verdict["mismatches"].append("reduced index: a draw left the subset")
+        verdict["reduced"] += 1
     print(json.dumps(verdict))
 
 

@@ -120,17 +120,13 @@ class LibriSpeechDataset(Sequence):
         # row number == dataset id; the speaker's LibriVox id moves to `speaker_id` (voicemap/librispeech.py:88-96)
         table = table.rename(columns={'id': 'speaker_id', 'minutes': 'speaker_minutes'}).reset_index(drop=True)
         table['id'] = np.arange(len(table))
-        self.df = table
 
+        # per-file facts, indexed by dataset id for the lifetime of the object
         self._paths = table['filepath'].tolist()
         self._speaker = table['speaker_id'].to_numpy()
         self._weight = table['length'].to_numpy(dtype=np.float64)
         self._sex = table['sex'].tolist()
-        members = defaultdict(list)
-        for row, speaker in enumerate(self._speaker):
-            members[speaker].append(row)
-        self._members = {speaker: np.asarray(rows) for speaker, rows in members.items()}
-        self._group_size = np.asarray([len(self._members[s]) for s in self._speaker], dtype=np.int64)
+        self.df = table          # property: also derives the sampling structures from the rows of the frame
         # the reference's lookup tables, kept for code that pokes at them
         self.datasetid_to_filepath = dict(enumerate(self._paths))
         self.datasetid_to_speaker_id = dict(enumerate(self._speaker.tolist()))
@@ -165,8 +161,26 @@ class LibriSpeechDataset(Sequence):
         return records
 
     # ------------------------------------------------------------------------------------------------ items
+    @property
+    def df(self):
+        """The index table the reference's callers read -- and replace: experiments/wide_vs_tall.py:55-78 deep-copies
+        a dataset and assigns a frame with fewer rows (same ``id`` values) to train on fewer speakers.  Assigning
+        restricts every draw to the rows of the new frame, in its row order, as ``self.df.sample`` does there."""
+        return self._df
+
+    @df.setter
+    def df(self, frame):
+        self._df = frame
+        self._active = frame['id'].to_numpy(dtype=np.int64)
+        members = defaultdict(list)
+        for row in self._active:
+            members[self._speaker[row]].append(row)
+        self._members = {speaker: np.asarray(rows) for speaker, rows in members.items()}
+        self._group_size = np.zeros(len(self._paths), dtype=np.int64)
+        self._group_size[self._active] = [len(self._members[self._speaker[row]]) for row in self._active]
+
     def __len__(self):
-        return len(self._paths)
+        return len(self._active)
 
     def num_classes(self):
         return len(self._members)
@@ -280,7 +294,7 @@ class LibriSpeechDataset(Sequence):
         array ``among``.  (numpy's weighted choice without replacement is what the pandas 0.23 pinned by the reference
         calls; pandas >= 2.2 refuses the same request when count * max(weight) > sum(weights), which small corpora
         hit at the reference's batch sizes.)"""
-        pool = np.arange(len(self)) if among is None else np.asarray(among)
+        pool = self._active if among is None else np.asarray(among)
         w = self._weight[pool]
         return pool[np.random.choice(len(pool), size=count, replace=False, p=w / w.sum())]
 
@@ -298,7 +312,7 @@ class LibriSpeechDataset(Sequence):
     def get_differing_pairs(self, num_pairs):
         """``num_pairs`` (id, id) tuples from different speakers (voicemap/librispeech.py:155-167)."""
         first = self._draw(num_pairs)
-        others = np.flatnonzero(~np.isin(self._speaker, self._speaker[first]))
+        others = self._active[~np.isin(self._speaker[self._active], self._speaker[first])]
         second = self._draw(num_pairs, among=others)
         return list(zip(first.tolist(), second.tolist()))
 

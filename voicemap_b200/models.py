@@ -159,6 +159,10 @@ class _ModelBase:
                              validation_steps=validation_steps, initial_epoch=initial_epoch, workers=workers,
                              use_multiprocessing=use_multiprocessing)
 
+    def _non_trainable_params(self):
+        encoder = getattr(self, "encoder", self)
+        return int(sum(w.size for name, w in encoder.weights.items() if name.endswith(("_mean", "_var"))))
+
     def summary(self, print_fn=None):
         lines = ["_" * 65, f"{'Layer (type)':<40}{'Param #':>25}", "=" * 65]
         total = 0
@@ -170,7 +174,9 @@ class _ModelBase:
                 n = int(sum(np.prod(self._weight(w).shape) for w in layer.weight_names))
                 lines.append(f"{layer.name + ' (' + layer.class_name + ')':<40}{n:>25}")
             total += n
-        lines += ["=" * 65, f"Total params: {total:,}", "_" * 65]
+        frozen = self._non_trainable_params()     # BatchNormalization moving statistics
+        lines += ["=" * 65, f"Total params: {total:,}", f"Trainable params: {total - frozen:,}",
+                  f"Non-trainable params: {frozen:,}", "_" * 65]
         text = "\n".join(lines)
         (print_fn or print)(text)
         return None
