@@ -41,6 +41,24 @@ sys.exit(0 if result.wasSuccessful() and result.testsRun == 3 else 1)
 """
 
 
+def _write_irregular_corpus(root):
+    """30 speakers with 1 - 7 utterances of 1 - 6 s each: files shorter than the fragment, speakers with a single
+    usable file, speakers with none."""
+    rng = np.random.default_rng(11)
+    lines = ["; irregular miniature LibriSpeech", ";ID  |SEX| SUBSET           |MINUTES| NAME"]
+    for s in range(30):
+        speaker, chapter = 700 + s, 40 + s
+        folder = os.path.join(root, "data", "LibriSpeech", "dev-clean", str(speaker), str(chapter))
+        os.makedirs(folder)
+        lines.append("{:<5}| {} | dev-clean        | 9.{:02d} | Reader {}".format(speaker, "MF"[s % 2], s, s))
+        for u in range(int(rng.integers(1, 8))):
+            samples = int(rng.integers(16000, 96000))
+            with open(os.path.join(folder, "{}-{}-{:04d}.flac".format(speaker, chapter, u)), "wb") as handle:
+                handle.write(encode_flac_quick(None, constant=(13 * (s + 1), samples)))
+    with open(os.path.join(root, "data", "LibriSpeech", "SPEAKERS.TXT"), "w") as handle:
+        handle.write("\n".join(lines) + "\n")
+
+
 def _write_corpus(root):
     rng = np.random.default_rng(0)
     lines = ["; miniature LibriSpeech for the reference's tests", ";ID  |SEX| SUBSET           |MINUTES| NAME"]
@@ -94,7 +112,22 @@ def test_items_equal_the_reference_batchers_items(tmp_path):
     assert run.returncode == 0, run.stdout + run.stderr
     verdict = json.loads(run.stdout.strip().splitlines()[-1])
     assert verdict["mismatches"] == [] and verdict["items"] == 5 * 126 and verdict["draws"] == 40, verdict
-    assert verdict["reduced"] == 20, verdict
+    assert verdict["reduced"] == 20 and verdict.get("skipped", 0) == 0 and verdict.get("both_failed", 0) == 0, verdict
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_TESTS), reason="the reference tree is only present in the build container")
+def test_items_and_draws_equal_the_reference_on_an_irregular_corpus(tmp_path):
+    """Same side-by-side run on a ragged tree (files shorter than the fragment, speakers with one usable file or none):
+    items in all modes, pair draws and n-shot tasks agree -- including the draws neither batcher can make."""
+    _write_irregular_corpus(str(tmp_path))
+    script = os.path.join(ROOT, "tests", "golden", "run_reference_batcher.py")
+    run = subprocess.run([sys.executable, "-W", "ignore", script, str(tmp_path)], cwd=str(tmp_path),
+                         env=dict(os.environ, VOICEMAP_PATH=str(tmp_path), PYTHONPATH=ROOT),
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    verdict = json.loads(run.stdout.strip().splitlines()[-1])
+    assert verdict["mismatches"] == [] and verdict["items"] > 300 and verdict["draws"] == 40, verdict
+    assert verdict["reduced"] == 20 and verdict.get("both_failed", 0) > 0, verdict
 
 
 SCRIPT_RUNNER = r"""
