@@ -164,6 +164,28 @@ def test_fit_generator_uses_the_producers(monkeypatch):
         def on_epoch_end(self):
             pass
 
+    # default arguments: the single background thread (generator) / in-line indexing (Sequence), same loop
+    del steps[:]
+    model.fit_generator(_siamese_batches(), steps_per_epoch=3, epochs=2, verbose=0)
+    model.fit_generator(Seq(), epochs=1, verbose=0)
+    assert len(steps) == 6 + 5
+
+    # a failing step closes the producers on its way out
+    def boom(self, x1, x2, y, allreduce=None, world=1):
+        raise RuntimeError("device lost")
+    monkeypatch.setattr(StubEngine, "siamese_step", boom)
+    model._trainer = None
+    import multiprocessing
+    before = len(multiprocessing.active_children())
+    with pytest.raises(RuntimeError, match="device lost"):
+        model.fit_generator(_siamese_batches(), steps_per_epoch=3, epochs=1, verbose=0, workers=4, use_multiprocessing=True)
+    time.sleep(0.2)
+    assert len(multiprocessing.active_children()) <= before
+    monkeypatch.undo()
+    monkeypatch.setattr(training, "TrainEngine", StubEngine)
+    monkeypatch.setattr(training, "_producer_processes", lambda workers, multi: 3 if multi and workers > 1 else 0)
+    model._trainer = None
+
     del steps[:]
     model.fit_generator(Seq(), epochs=2, verbose=0, workers=4, use_multiprocessing=True)
     assert len(steps) == 10 and steps[:5] == steps[5:]          # index order, both epochs

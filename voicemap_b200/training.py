@@ -607,46 +607,50 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
     if validation_data is not None and not isinstance(validation_data, (tuple, list)):
         val_iter = iter(validation_data)
     history = []
-    for epoch in range(initial_epoch, epochs):
-        for cb in callbacks:
-            cb.on_epoch_begin(epoch)
-        losses, accs = [], []
-        ordered = None
-        if is_seq and producers and steps_per_epoch > 1:
-            from .prefetch import SequencePrefetcher
-            ordered = SequencePrefetcher(generator, [s % len(generator) for s in range(steps_per_epoch)], producers)
-        for step in range(steps_per_epoch):
-            if ordered is not None:
-                batch = ordered.next()
-            else:
-                batch = prefetch.next() if prefetch is not None else generator[step % len(generator)]
-            x, y = batch[0], batch[1]
-            if trainer.kind == "siamese":
-                lv, acc = trainer.siamese_step(x[0], x[1], y, allreduce=allreduce, world=world)
-            else:
-                lv, acc = trainer.classifier_step(x, y, allreduce=allreduce, world=world)
-            losses.append(lv)
-            accs.append(acc)
-        if ordered is not None:
-            ordered.close()
-        logs = {"loss": float(torch.stack(losses).mean().item())}
-        if "accuracy" in (model.metrics or []) or "acc" in (model.metrics or []):
-            logs["acc"] = float(torch.stack(accs).mean().item())
-        trainer.sync_to_model()
-        if validation_data is not None:
-            vl, va = _validate(model, trainer, validation_data, val_iter, validation_steps)
-            logs["val_loss"] = vl
-            if "acc" in logs:
-                logs["val_acc"] = va
-        if is_seq:
-            generator.on_epoch_end()
-        for cb in callbacks:
-            cb.on_epoch_end(epoch, logs)
-        if verbose:
-            print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
-        history.append(dict(logs))
-    if prefetch is not None:
-        prefetch.close()
+    try:
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch)
+            losses, accs = [], []
+            ordered = None
+            if is_seq and producers and steps_per_epoch > 1:
+                from .prefetch import SequencePrefetcher
+                ordered = SequencePrefetcher(generator, [s % len(generator) for s in range(steps_per_epoch)], producers)
+            try:
+                for step in range(steps_per_epoch):
+                    if ordered is not None:
+                        batch = ordered.next()
+                    else:
+                        batch = prefetch.next() if prefetch is not None else generator[step % len(generator)]
+                    x, y = batch[0], batch[1]
+                    if trainer.kind == "siamese":
+                        lv, acc = trainer.siamese_step(x[0], x[1], y, allreduce=allreduce, world=world)
+                    else:
+                        lv, acc = trainer.classifier_step(x, y, allreduce=allreduce, world=world)
+                    losses.append(lv)
+                    accs.append(acc)
+            finally:
+                if ordered is not None:
+                    ordered.close()
+            logs = {"loss": float(torch.stack(losses).mean().item())}
+            if "accuracy" in (model.metrics or []) or "acc" in (model.metrics or []):
+                logs["acc"] = float(torch.stack(accs).mean().item())
+            trainer.sync_to_model()
+            if validation_data is not None:
+                vl, va = _validate(model, trainer, validation_data, val_iter, validation_steps)
+                logs["val_loss"] = vl
+                if "acc" in logs:
+                    logs["val_acc"] = va
+            if is_seq:
+                generator.on_epoch_end()
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()))
+            history.append(dict(logs))
+    finally:
+        if prefetch is not None:    # producers (thread or processes) stop even when a step raised
+            prefetch.close()
     for cb in callbacks:
         cb.on_train_end()
     return history
