@@ -198,3 +198,39 @@ def test_producer_count_policy():
     cores = len(os.sched_getaffinity(0))
     if cores > 1:
         assert _producer_processes(64, True) == min(64, cores, 16)
+
+
+def test_producers_run_the_real_batcher_on_flac_files(tmp_path):
+    """Forked producers running the reference-style generator expression over LibriSpeechDataset: FLAC files on disk,
+    the decoder library's own threads inside each child, preprocessing, shared-memory hand-over."""
+    from flac_writer import encode_flac_quick
+    from voicemap_b200 import utils
+    from voicemap_b200.librispeech import LibriSpeechDataset
+    root = tmp_path / "data" / "LibriSpeech"
+    lines = ["; tiny"]
+    rng = np.random.default_rng(0)
+    for s in range(40):
+        folder = root / "dev-clean" / str(100 + s) / "1"
+        folder.mkdir(parents=True)
+        lines.append("{} | {} | dev-clean | 9.0 | R{}".format(100 + s, "FM"[s % 2], s))
+        for u in range(3):
+            pcm = np.round(1000 * rng.standard_normal(17000 + 100 * u) + 40 * s).astype(np.int64)
+            (folder / "{}-1-{:04d}.flac".format(100 + s, u)).write_bytes(encode_flac_quick(pcm))
+    (root / "SPEAKERS.TXT").write_text("\n".join(lines) + "\n")
+    dataset = LibriSpeechDataset("dev-clean", 1, data_path=str(tmp_path), cache=False)
+    pre = utils.BatchPreProcessor("siamese", utils.preprocess_instances(4))
+    batches = (pre(batch) for batch in dataset.yield_verification_batches(16))
+    producers = prefetch.ProcessPrefetcher(batches, workers=2)
+    try:
+        firsts = []
+        for _ in range(7):
+            (left, right), labels = producers.next()
+            assert left.shape == right.shape == (16, 4000, 1) and left.dtype == np.float64
+            assert labels[:, 0].tolist() == [0.0] * 8 + [1.0] * 8
+            # whitened: the gain comes from the un-centred batch (reference quirk), so DC offsets leave the RMS below 0.038
+            assert 0.01 < float(np.sqrt(np.mean(np.square(left)))) <= 0.038021 + 1e-9
+            assert abs(float(left.mean(axis=1).max())) < 1e-12
+            firsts.append(float(left[0, 0, 0]))
+        assert len(set(firsts)) == 7
+    finally:
+        producers.close()
