@@ -63,3 +63,42 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         assert "no CPU or PyTorch fallback" in str(exc)
     else:
         raise AssertionError("load() must raise when the CUDA library is missing")
+
+
+def test_headers_are_plain_c_and_a_c_program_links(built_library, tmp_path):
+    """The boundary is a C ABI: both headers compile as strict C99 (no C++-isms, no torch types), and a C program linked
+    against the two libraries calls their host-only entry points."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    from voicemap_b200.build import IO_LIB_PATH, build_io_library
+    build_io_library()
+    source = tmp_path / "client.c"
+    source.write_text(r'''
+#include <stdio.h>
+#include "voicemap_b200.h"
+#include "voicemap_io.h"
+int main(void) {
+    vmio_flac_info info;
+    const unsigned char junk[8] = {'R', 'I', 'F', 'F', 0, 0, 0, 0};
+    int rc = vmio_flac_probe(junk, sizeof junk, &info);
+    printf("%d %d %d %s|%d %lu %d\n", vm_version(), vmio_version(), rc, vmio_error_string(rc),
+           vm_padded_channels(192), (unsigned long)vm_conv1_wpack_bytes(128), vm_conv3_num_position_tiles(3000));
+    return 0;
+}
+''')
+    include = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(built_library)
+    syntax = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", include,
+                             str(source)], capture_output=True, text=True)
+    assert syntax.returncode == 0, syntax.stderr
+    exe = tmp_path / "client"
+    link = subprocess.run([gcc, "-std=c99", "-I", include, str(source), "-o", str(exe), built_library, IO_LIB_PATH,
+                           "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert link.returncode == 0, link.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    assert run.stdout.strip() == "100 100 -2 not a FLAC stream (no fLaC marker / STREAMINFO)|256 16384 24"
