@@ -37,8 +37,14 @@ def _worker(rank, world_size, port, out_dir):
     t_max = parallel.max_over_ranks(1.0 + rank)
     mean = parallel.global_mean(float(np.arange(lo, hi).sum()), hi - lo)
     rows = parallel.gather_rows(torch.full((hi - lo, 2), float(rank)))
+    # the reference's builders take no seed: ranks start from different weights until rank 0's are broadcast
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    model = build_siamese_net(get_baseline_convolutional_encoder(16, 8), (1024, 1))
+    before = np.concatenate([w.reshape(-1) for w in model.get_weights()])
+    parallel.broadcast_weights_(model)
+    after = np.concatenate([w.reshape(-1) for w in model.get_weights()])
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, hi=hi, flat=flat.numpy(), full=full, w=p["w"], t_max=t_max,
-             mean=mean, rows=rows.numpy())
+             mean=mean, rows=rows.numpy(), before=before, after=after)
     dist.destroy_process_group()
 
 
@@ -53,6 +59,9 @@ def test_two_rank_gloo(tmp_path):
     assert r0["t_max"] == r1["t_max"] == 2.0                  # slowest rank defines the step time
     assert abs(float(r0["mean"]) - 3.0) < 1e-12               # mean over the global batch, uneven shards
     assert r0["rows"].shape == (7, 2) and r0["rows"][:4].sum() == 0 and r0["rows"][4:].sum() == 6
+    assert not np.array_equal(r0["before"], r1["before"])     # independently initialised ranks differ ...
+    np.testing.assert_array_equal(r0["after"], r0["before"])  # ... rank 0 keeps its weights ...
+    np.testing.assert_array_equal(r1["after"], r0["before"])  # ... and rank 1 receives them, bit for bit
 
 
 def test_single_process_defaults():
@@ -61,3 +70,5 @@ def test_single_process_defaults():
     assert parallel.shard_bounds(10, 1, 4) == (3, 6) and parallel.shard_bounds(10, 3, 4) == (8, 10)
     t = torch.ones(3)
     assert parallel.allreduce_sum_(t) is t and parallel.max_over_ranks(2.5) == 2.5
+    marker = object()
+    assert parallel.broadcast_weights_(marker) is marker       # one process: nothing to do

@@ -48,6 +48,29 @@ def allreduce_sum_(flat):
     return flat
 
 
+def broadcast_weights_(model, src=0):
+    """Every rank takes rank ``src``'s weights (``model.get_weights()`` / ``set_weights``).  The reference's builders
+    have no seed argument (voicemap/models.py:6,44), so independently launched ranks would start data-parallel
+    training from different random initialisations and -- sharing gradients but not weights -- never agree.  One flat
+    float32 buffer, one broadcast; a no-op for one process.  With NCCL the buffer travels through the current CUDA
+    device, with gloo through host memory."""
+    if world()[1] <= 1:
+        return model
+    import numpy as np
+    weights = model.get_weights()
+    flat = torch.from_numpy(np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights]))
+    if dist.get_backend() == "nccl":
+        flat = flat.cuda()
+    dist.broadcast(flat, src=src)
+    flat = flat.cpu().numpy()
+    out, at = [], 0
+    for w in weights:
+        out.append(flat[at:at + w.size].reshape(w.shape).copy())
+        at += w.size
+    model.set_weights(out)
+    return model
+
+
 def max_over_ranks(value, device="cpu"):
     """Timing reduction of the bench: the slowest rank defines the step time."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

@@ -582,6 +582,9 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
             raise ValueError("`steps_per_epoch=None` is only valid for a generator based on the `Sequence` class.")
         steps_per_epoch = len(generator)
     trainer = getattr(model, "_trainer", None)
+    if _dist_info()[1] > 1 and trainer is None:
+        from .parallel import broadcast_weights_
+        broadcast_weights_(model)            # ranks were initialised independently: start from rank 0's weights
     if trainer is None or trainer.optimizer is not model.optimizer or trainer.loss != model.loss:
         trainer = TrainEngine(model, model.optimizer, model.loss)
         model._trainer = trainer
