@@ -38,6 +38,17 @@ def main():
     ap.add_argument("--out", default=PATH)
     args = ap.parse_args()
 
+    # data parallel: `python -m torch.distributed.run --nproc-per-node N examples/train_siamese.py ...` gives every rank
+    # 1/N of each batch; fit_generator then shares BatchNorm statistics and gradients and starts from rank 0's weights
+    rank, world = 0, 1
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        from voicemap_b200 import parallel
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        rank, world = parallel.init_from_env("nccl", torch.device("cuda", local))
+        args.batchsize = max(2, args.batchsize // world // 2 * 2)
+
     if args.synthetic:
         from synthetic_speakers import SyntheticCorpus
         # the reference's differing-pair draw excludes every speaker of its first draw: keep speakers >> batchsize / 2
@@ -68,13 +79,13 @@ def main():
         train_batches, steps_per_epoch=args.steps, epochs=args.epochs,
         validation_data=valid_batches, validation_steps=max(1, args.steps // 5),
         workers=args.workers, use_multiprocessing=args.workers > 1,
-        callbacks=[
-            NShotEvaluationCallback(args.eval_tasks, 1, args.k_way, valid, preprocessor=pre),
+        verbose=1 if rank == 0 else 0,
+        callbacks=[NShotEvaluationCallback(max(1, args.eval_tasks // world), 1, args.k_way, valid, preprocessor=pre)] + ([
+            # files are written by rank 0 only; the metric they follow is pooled over ranks by the callback above
             CSVLogger(os.path.join(args.out, "logs", tag + ".csv")),
             ModelCheckpoint(os.path.join(args.out, "models", tag + ".hdf5"), monitor=monitor, mode="max",
                             save_best_only=True, verbose=True),
-            ReduceLROnPlateau(monitor=monitor, mode="max", verbose=1),
-        ])
+        ] if rank == 0 else []) + [ReduceLROnPlateau(monitor=monitor, mode="max", verbose=1 if rank == 0 else 0)])
 
 
 if __name__ == "__main__":

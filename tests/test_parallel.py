@@ -43,8 +43,29 @@ def _worker(rank, world_size, port, out_dir):
     before = np.concatenate([w.reshape(-1) for w in model.get_weights()])
     parallel.broadcast_weights_(model)
     after = np.concatenate([w.reshape(-1) for w in model.get_weights()])
+    # the n-shot callback pools its accuracy over ranks: rank 0 solves every task, rank 1 none -> 0.5 on both
+    from voicemap_b200 import utils
+
+    class Tasks:
+        def build_n_shot_task(self, k, n=1):
+            query = np.full(64, 1.0)
+            support = np.stack([np.full(64, 1.0 if (c == 0) == (rank == 0) else 5.0) for c in range(k) for _ in range(n)])
+            return (query, 0), (support, np.repeat(np.arange(k), n))
+
+    class Siamese:
+        layers = [None, None, None]
+
+        def predict(self, x):
+            return np.abs(x[0] - x[1]).mean(axis=(1, 2))[:, None]
+
+    callback = utils.NShotEvaluationCallback(6, 1, 3, Tasks(), preprocessor=utils.BatchPreProcessor(
+        "siamese", utils.preprocess_instances(1, whitening=False)))
+    callback.set_model(Siamese())
+    logs = {}
+    callback.on_epoch_end(0, logs)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, hi=hi, flat=flat.numpy(), full=full, w=p["w"], t_max=t_max,
-             mean=mean, rows=rows.numpy(), before=before, after=after)
+             mean=mean, rows=rows.numpy(), before=before, after=after,
+             pooled=logs["val_1-shot_acc"])
     dist.destroy_process_group()
 
 
@@ -62,6 +83,7 @@ def test_two_rank_gloo(tmp_path):
     assert not np.array_equal(r0["before"], r1["before"])     # independently initialised ranks differ ...
     np.testing.assert_array_equal(r0["after"], r0["before"])  # ... rank 0 keeps its weights ...
     np.testing.assert_array_equal(r1["after"], r0["before"])  # ... and rank 1 receives them, bit for bit
+    assert float(r0["pooled"]) == float(r1["pooled"]) == 0.5   # pooled n-shot accuracy, identical on both ranks
 
 
 def test_single_process_defaults():

@@ -71,17 +71,28 @@ def broadcast_weights_(model, src=0):
     return model
 
 
-def max_over_ranks(value, device="cpu"):
+def _scalar_device(device):
+    """Where small host-side scalars travel: NCCL only moves CUDA tensors, gloo host ones."""
+    if device is not None:
+        return device
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return "cpu"
+
+
+def max_over_ranks(value, device=None):
     """Timing reduction of the bench: the slowest rank defines the step time."""
+    device = _scalar_device(device)
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
 
-def global_mean(local_sum, local_count, device="cpu"):
+def global_mean(local_sum, local_count, device=None):
     """Mean of a per-sample quantity over the GLOBAL batch (the loss mean must not be a mean of rank means when
     shards are uneven)."""
+    device = _scalar_device(device)
     t = torch.tensor([float(local_sum), float(local_count)], dtype=torch.float64, device=device)
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

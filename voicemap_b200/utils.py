@@ -237,7 +237,10 @@ class NShotEvaluationCallback(Callback):
                                         self.k_way, network_type=self.mode,
                                         tasks_per_launch=max(1, self.batch_tasks))
         key = 'val_{}-shot_acc'.format(self.n_shot)
-        accuracy = solved / float(self.num_tasks)
+        # data-parallel training: every rank has solved its own random tasks; the metric is their pooled accuracy, the
+        # same number on every rank, so that callbacks steered by it (ReduceLROnPlateau, ModelCheckpoint) stay in step
+        from .parallel import global_mean
+        accuracy = global_mean(solved, self.num_tasks)
         if logs is not None:
             logs[key] = accuracy
         print('{}: {:.4f}'.format(key, accuracy))
