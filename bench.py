@@ -372,6 +372,8 @@ def run_b200(args):
             # 738 + 651 + 304 MB at batch 256, the same for precision 2 and 3: both move 4 bytes per activation)
             # averaged per launch; algorithmic bytes per launch average 590 MB
             traffic=(5.64e8 if (n, length) == (256, 12000) and args.precision in (2, 3) else None),
+            traffic_source="ncu --set full capture of the same kernels at this batch, profiles/r01_ncu_summary.md "
+                           "(dram__bytes_read.sum + dram__bytes_write.sum, mean of the three conv3 launches)",
             blocks=blocks,
             network=dict(us_per_clip=round(us_per_clip, 3),
                          frac_of_tf32_roofline=round(bound_us(peaks["bf16_tflops"] / 2) / us_per_clip, 4),
