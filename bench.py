@@ -381,7 +381,7 @@ def run_b200(args):
                          note="BASELINE.md section 3 bounds: sum over blocks of max(bytes/HBM, flops/peak); "
                               "TF32 peak taken as bf16/2"))
         cpu_baseline = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # the CPU leg is timed at N = 1 only (rank 0's host cores, alone)
             cpu_baseline, _ = time_oracle(length, 8, budget_s=args.cpu_baseline_seconds)
         line = dict(
             metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
