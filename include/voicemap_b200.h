@@ -100,6 +100,18 @@ int vm_pair_head_loss_fwd(const float* e1, const float* e2, int N, int E, int me
                           const float* head_b, const float* y_true, int loss_kind, float* dist, float* prob,
                           float* loss, void* stream);
 
+/* ---- k-way n-shot scoring on embeddings ---------------------------------------------------------------------
+ * voicemap/utils.py:156-212: query (T, E); support (T, k*n, E) ordered [class 0]*n + ... + [class k-1]*n
+ * (voicemap/librispeech.py:204-240).  Per task: mean embedding of each class, `distance` to the query
+ * (VM_DISTANCE_EUCLIDEAN: |mean - q|; VM_DISTANCE_COSINE: 1 - cos(mean of unit vectors, q), scipy cdist 'cosine';
+ * VM_DISTANCE_DOT: -(mean unit vector * mean norm) . q), then best[t] = arg-min class (first minimum): the task is
+ * solved when best[t] == 0.  scores (T, k) optional.  Sums in double, like the reference's numpy / scipy. */
+#define VM_DISTANCE_EUCLIDEAN 0
+#define VM_DISTANCE_COSINE 1
+#define VM_DISTANCE_DOT 2
+int vm_nshot_score(const float* query, const float* support, int T, int k, int n, int E, int distance, float* scores,
+                   int32_t* best, void* stream);
+
 /* ---- plane conversion (per-block fp32 views for callers and tests) ---------------------------------------- */
 int vm_split_planes(const float* x, size_t n, uint16_t* hi, uint16_t* lo, void* stream);
 int vm_merge_planes(const uint16_t* hi, const uint16_t* lo, size_t n, float* x, void* stream);
@@ -143,20 +155,31 @@ int vm_encoder_fwd_raw(const float* x, int N, int T, int downsampling, int white
 int vm_pack_conv1_raw(const float* kernel, const float* bias, int cout, void* wpack, float* epi, void* stream);
 int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout, void* wpack, float* epi,
                       void* stream);
-/* dgrad operand: tap-flipped, channel-transposed kernel (bf16 planes) in the conv3 layout with (cin' = Cout, cout' = Cin);
- * wpack holds vm_conv3_wpack_bytes(cout, cin) bytes, epi vm_epi_bytes(cin). */
+/* dgrad operand: tap-flipped, channel-transposed kernel (fp16 hi/lo planes) in the conv3 layout with
+ * (cin' = Cout, cout' = Cin); wpack holds vm_conv3_wpack_bytes(cout, cin) bytes, epi vm_epi_bytes(cin). */
 int vm_pack_conv3_dgrad(const float* kernel /* (3, Cin, Cout) */, int cin, int cout, void* wpack, float* epi,
                         void* stream);
 
-/* Train-mode conv forward: u = relu(conv(x) + bias), un-pooled fp32 (N, L, Cout), plus per-channel {sum, sumsq}
- * partial rows stat_partial (N * 2*ceil(L/256), Cpad) float2 (may be NULL). */
-int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
-                     float* stat_partial, int precision, void* stream);
-/* linear = 0: as above for blocks 2-4.  linear = 1: plain convolution output (dgrad: in = dU bf16 planes, wpack from
- * vm_pack_conv3_dgrad, out = dX fp32 (N, L, Cin)). */
-int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
-                     const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
-                     void* stream);
+/* Train-mode conv forward of one block: u = relu(conv(x) + bias) at every position, of which the call keeps
+ *   u16 (N, L, Cout)       16 bits per element: fp16(u) in bits 0-14, bit 15 = "arg-max of its MaxPool window" (first
+ *                          winner on ties; the arg-MIN of u where gamma[c] < 0, i.e. the arg-max after BatchNorm);
+ *   ext (N, L/pool, Cout)  fp32 extreme of u per window (max, or min where gamma[c] < 0): the forward pass continues
+ *                          from these exact values, BatchNorm being monotone per channel;
+ *   stat_partial           per-channel {sum, sumsq} rows (N * 2*ceil(L/256), Cpad) float2 for the batch statistics.
+ * gamma (Cout) supplies the signs only (NULL = all maxima).  pool: 4 or 2 for block 1, always 2 for blocks 2-4.
+ * precision 2 (blocks 2-4): in_lo is the e5m2x2 Q plane; 3: the fp16 residual plane. */
+int vm_conv1_train_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,
+                       const float* gamma, uint16_t* u16, float* ext, float* stat_partial, int precision, void* stream);
+int vm_conv3_train_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
+                       const void* wpack, const float* epi, const float* gamma, uint16_t* u16, float* ext,
+                       float* stat_partial, int precision, void* stream);
+/* Data gradient of a block's convolution: dX (N, L, Cin) fp32 = conv3(dU, flipped/transposed kernel).  du_hi / du_lo
+ * (N, L, Cout): the scaled fp16 gradient planes vm_bn_bwd wrote, grad_absmax the word it derived their power-of-two
+ * scale from (the epilogue takes the scale out again).  precision 3: dUh*Wh + dUl*Wh + dUh*Wl; 2: one-plane gradient
+ * (du_lo NULL), dUh*Wh + dUh*Wl; 1: dUh*Wh. */
+int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int cin,
+                   const void* wpack_dgrad, const float* epi_dgrad, const uint32_t* grad_absmax, float* dx,
+                   int precision, void* stream);
 int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
 /* bytes of the `red_scratch` buffer the two-stage (deterministic, atomics-free) channel reductions need */
 size_t vm_reduce_scratch_bytes(int G, int C);
@@ -166,14 +189,15 @@ size_t vm_reduce_scratch_bytes(int G, int C);
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
                          float* moving_var, float* bn_const, double* red_scratch, void* stream);
-/* y = bn(u) * mask -> MaxPool1D(pool) -> fp16 planes (N, L/pool, C) for the next block's forward conv, and
- * (optional, both or neither) the same values as bf16 planes for vm_wgrad3 (the tensor core cannot mix fp16 with
- * bf16 operands).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
-int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* bf_hi, uint16_t* bf_lo, void* stream);
-/* block 4: bn -> MaxPool1D(2) -> GlobalMaxPool1D merged; gmax (N, C), argmax (N, C) un-pooled position. */
-int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
-                   int32_t* argmax, void* stream);
+/* y = (s * ext + t) * mask on the window extremes = MaxPool1D(pool)(SpatialDropout(BatchNorm(u))) -> planes
+ * (N, Lout, C) of the next block: out_hi fp16 always; out_lo the fp16 residual plane (forward precision 3, and the
+ * second activation plane of vm_wgrad3) and / or out_q the e5m2x2 Q plane (forward precision 2), each optional
+ * (NULL).  mask (N, C) = SpatialDropout1D keep/(1-p), or NULL. */
+int vm_bn_pool_fwd(const float* ext, int N, int Lout, int C, int G, const float* bn_const, const float* mask,
+                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* out_q, void* stream);
+/* block 4: bn on the MaxPool1D(2) window extremes -> GlobalMaxPool1D; gmax (N, C), jstar (N, C) the winning window. */
+int vm_bn_gmax_fwd(const float* ext, int N, int Lout, int C, int G, const float* bn_const, const float* mask,
+                   float* gmax, int32_t* jstar, void* stream);
 int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, void* stream);
 
 /* Backward of the siamese head + loss (emb (2N, E): branch 1 rows then branch 2 rows). */
@@ -182,14 +206,16 @@ int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const floa
                           float* d_head_b, void* stream);
 int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
                  void* stream);
-/* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax + argmax
- * (block 4).  Outputs: dgamma, dbeta, dbias (C), dU as bf16 (hi, lo) planes (N, L, C) -- gradients are carried in
- * bf16 pairs (fp32 exponent range, ~16 significant bits), so no loss scaling is required.  scratch_f2 / scratch_f hold
- * N * chunks * max(1, 512/C) rows of C float2 / float; bwd_const (G, C) float4. */
-int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
-              int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
-              float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
-              float* dbias, double* red_scratch, void* stream);
+/* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax (N, C) + jstar
+ * (block 4: the gradient sits in window jstar[n][c]).  Outputs: dgamma, dbeta, dbias (C) and dU (N, L, C) as fp16
+ * planes scaled by a power of two that is derived from the largest |s * dy| of the block (stored as float bits in
+ * *grad_absmax; vm_wgrad* / vm_conv3_dgrad take the scale out again): du_hi always, du_lo = fp16 residual when not
+ * NULL.  scratch_f2 / scratch_f: vm_bn_bwd_scratch_elems(N) float2 / float entries; bwd_const (G, C) float4. */
+size_t vm_bn_bwd_scratch_elems(int N);
+int vm_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
+              int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
+              float* bwd_const, float* dgamma, float* dbeta, uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
+              float* scratch_f, float* dbias, double* red_scratch, void* stream);
 /* Synchronised BatchNorm across data-parallel ranks (the reference's BN sees the whole batch on one
  * device).  The two calls above are split at the point where the per-(group, channel) sums exist, so that the caller
  * can all-reduce them (torch.distributed / NCCL) in between:
@@ -203,22 +229,25 @@ int vm_bn_stats_sums(const float* stat_partial, int rows_per_clip, int N, int G,
 int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
                           float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
                           void* stream);
-int vm_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L,
-                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
-                   double* red_scratch, double* sums, void* stream);
-int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
-                        const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C, int G,
-                        int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
-                        float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f, float* dbias,
-                        double* red_scratch, void* stream);
-/* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores; x_* and du_* are bf16 planes;
- * partial: scratch. */
+int vm_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L,
+                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
+                   uint32_t* grad_absmax, double* red_scratch, double* sums, void* stream);
+int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
+                        const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L, int C, int G,
+                        int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
+                        float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
+                        float* dbias, double* red_scratch, void* stream);
+/* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores.  x_hi / x_lo: the fp16 planes the
+ * forward conv of the block consumed (x_lo = fp16 residual plane: training keeps precision-3 planes for this);
+ * du_*: the scaled gradient planes of vm_bn_bwd, grad_absmax their scale word.  precision 3: Xh*Uh + Xl*Uh + Xh*Ul;
+ * 2: one-plane gradient (du_lo NULL), Xh*Uh + Xl*Uh; 1: Xh*Uh.  partial: scratch. */
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
-              int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream);
-/* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co].  precision 3 / 1: tensor cores (bf16 Toeplitz operand
- * built in shared memory, 3 or 1 MMAs per K step); precision 0: fp32 CUDA-core reference kernel. */
+              int cin, int cout, int precision, const uint32_t* grad_absmax, float* partial, size_t partial_bytes,
+              float* dw, void* stream);
+/* dW1 (32, 1, Cout) = sum_{n,p} x[n][p+k-15] * dU1[n][p][co] on tensor cores (fp16 Toeplitz operand of the waveform
+ * built in shared memory).  precision 3: Uh*Th + Ul*Th + Uh*Tl; 2: one-plane gradient, Uh*Th + Uh*Tl; 1: Uh*Th. */
 int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int precision,
-              float* partial, size_t partial_bytes, float* dw, void* stream);
+              const uint32_t* grad_absmax, float* partial, size_t partial_bytes, float* dw, void* stream);
 /* keras.optimizers.Adam update with global-norm clipping on a flat parameter buffer:
  * g' = g * inv_scale * min(1, clipnorm / ||g * inv_scale||) (clipnorm <= 0: off); m, v, p updated in place with
  * p -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller. */

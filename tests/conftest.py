@@ -12,6 +12,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU-marked tests are skipped, not failed, on a machine without CUDA (a plain `pytest tests` in the build
+    container).  On the GPU box nothing is skipped: a missing device or library there must fail loudly."""
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); run with -m gpu on the GPU box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def built_library():
     """Path of libvoicemap_b200.so; builds it with nvcc when absent (cross-compiles without a GPU)."""

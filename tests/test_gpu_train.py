@@ -23,7 +23,7 @@ def _grad_errors(grads, ref_grads):
             max(np.abs(g).max(), floor) for k, g in ref_grads.items()}
 
 
-def _make(filters, emb, loss, metric="uniform_euclidean", seed=0, dropout=0.0):
+def _make(filters, emb, loss, metric="uniform_euclidean", seed=0, dropout=0.0, precision=3, bwd_precision=3):
     from voicemap_b200.keras_compat import Adam
     from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
     from voicemap_b200.training import TrainEngine
@@ -40,15 +40,25 @@ def _make(filters, emb, loss, metric="uniform_euclidean", seed=0, dropout=0.0):
         sia.head_weights["head_bias"][:] = -0.3
     opt = Adam(clipnorm=1.0)
     sia.compile(loss=loss, optimizer=opt)
-    tr = TrainEngine(sia, opt, sia.loss)
+    tr = TrainEngine(sia, opt, sia.loss, precision=precision, bwd_precision=bwd_precision)
     return params, sia, tr
 
 
+# gradient tolerance per backward arithmetic (max |error| of a tensor relative to its largest entry, fp64 autograd
+# oracle; measured <= 2.2e-4 / 6.5e-4 / 8e-4 at this size, tools/train_parity_probe.py): 3 = two-plane fp16 gradients, three
+# MMAs per step; 2 = one-plane gradients (every dU element rounded to 11 significant bits, unbiased) against two-plane
+# activations / weights; 1 = one plane each.  The forward pass is precision 3 throughout: the siamese head
+# differentiates through e1 - e2, which amplifies the fp16 + fp8 forward's 1e-5 embedding error to 1e-2 in the gradients
+# of an untrained net (the loss itself stays within 1e-5).
+GRAD_TOL = {3: 5e-4, 2: 2e-3, 1: 2e-3}
+
+
+@pytest.mark.parametrize("precision,bwd_precision", [(3, 3), (3, 2), (3, 1)])
 @pytest.mark.parametrize("filters,emb,loss,metric", [(32, 16, "binary_crossentropy", "uniform_euclidean"),
                                                      (128, 64, "contrastive_loss", "uniform_euclidean"),
                                                      (64, 32, "binary_crossentropy", "weighted_l1")])
-def test_siamese_step_forward_and_gradients(filters, emb, loss, metric):
-    params, sia, tr = _make(filters, emb, loss, metric)
+def test_siamese_step_forward_and_gradients(filters, emb, loss, metric, precision, bwd_precision):
+    params, sia, tr = _make(filters, emb, loss, metric, precision=precision, bwd_precision=bwd_precision)
     n, length = 4, 1024
     x1 = O.synthetic_clips(n, length, seed=11)
     x2 = O.synthetic_clips(n, length, seed=12)
@@ -57,7 +67,8 @@ def test_siamese_step_forward_and_gradients(filters, emb, loss, metric):
     lv, acc = tr.siamese_step(x1, x2, y, apply=False)
     torch.cuda.synchronize()
     # the oracle takes the device's ReLU pattern (see conv1d_same_relu): branch 1 = rows [0, n), branch 2 = [n, 2n)
-    masks = [[(tr.U[b][br * n:(br + 1) * n] > 0).cpu().numpy().astype(np.float64) for b in range(4)] for br in range(2)]
+    masks = [[tr.relu_pattern(b)[br * n:(br + 1) * n].cpu().numpy().astype(np.float64) for b in range(4)]
+             for br in range(2)]
     ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=loss, distance_metric=metric, relu_masks=masks)
     # train-mode forward
     emb_gpu = tr.embv.cpu().numpy()
@@ -72,11 +83,9 @@ def test_siamese_step_forward_and_gradients(filters, emb, loss, metric):
             assert _rel(1.0 / np.square(bnc[:, 3]) - O.BN_EPS, v) < 1e-3
     # gradients
     # kernel-level diagnostics: block-1 activations and their gradients (the last dU left in the buffer is block 1's)
-    u1 = tr.U[0].cpu().numpy()
+    u1 = tr.activation(0).cpu().numpy()            # fp16 copy kept for the backward pass: 2^-11 relative
     u1_ref = np.concatenate([ref["u"][0][0], ref["u"][1][0]], axis=0)
-    nu = u1.size
-    bits = tr.dU[:, :nu].cpu().numpy().view(np.uint16).astype(np.uint32) << 16
-    du1 = (bits[0].view(np.float32) + bits[1].view(np.float32)).reshape(u1.shape) / tr.loss_scale
+    du1 = tr.block_gradient(0).cpu().numpy()
     # the oracle keeps d loss / d u of the post-ReLU tensor; the kernel stores the gradient of the conv output
     du1_ref = np.concatenate([ref["du"][0][0], ref["du"][1][0]], axis=0) * (u1 > 0)
     err = np.abs(du1 - du1_ref)
@@ -92,7 +101,7 @@ def test_siamese_step_forward_and_gradients(filters, emb, loss, metric):
     refg = dict(ref["grads"], head_kernel=ref["head_w_grad"], head_bias=ref["head_b_grad"])
     worst = _grad_errors(grads, refg)
     print({k: f"{v:.2e}" for k, v in worst.items()})
-    assert max(worst.values()) < 2e-3, worst
+    assert max(worst.values()) < GRAD_TOL[bwd_precision], worst
 
 
 def test_moving_statistics_and_adam_update():
@@ -154,7 +163,7 @@ def test_classifier_step_gradients():
     y = np.eye(classes, dtype=np.float32)[np.arange(n) % classes]
     lv, acc = tr.classifier_step(x, y, apply=False)
     torch.cuda.synchronize()
-    masks = [(tr.U[b] > 0).cpu().numpy().astype(np.float64) for b in range(4)]
+    masks = [tr.relu_pattern(b).cpu().numpy().astype(np.float64) for b in range(4)]
     ref = O.classifier_train_step_grads(params, clf.weights["head_kernel"], clf.weights["head_bias"], x, y,
                                         relu_masks=masks)
     assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
@@ -179,7 +188,8 @@ def test_dropout_mask_semantics():
     hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
     lv, _ = tr.siamese_step(x1, x2, y, apply=False, masks=dm)
     torch.cuda.synchronize()
-    rmasks = [[(tr.U[b][br * n:(br + 1) * n] > 0).cpu().numpy().astype(np.float64) for b in range(4)] for br in range(2)]
+    rmasks = [[tr.relu_pattern(b)[br * n:(br + 1) * n].cpu().numpy().astype(np.float64) for b in range(4)]
+              for br in range(2)]
     ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, dropout_masks=(om1, om2), relu_masks=rmasks)
     assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
     assert max(_grad_errors(tr.gradients(), ref["grads"]).values()) < 2e-3

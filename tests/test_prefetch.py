@@ -234,3 +234,23 @@ def test_producers_run_the_real_batcher_on_flac_files(tmp_path):
         assert len(set(firsts)) == 7
     finally:
         producers.close()
+
+
+def test_batch_kept_past_close_stays_mapped():
+    """A batch handed out by a prefetcher is a view of a shared-memory slot; closing the pool (end of an epoch, an
+    error, fit's end) must not unmap it under a caller who still holds it -- the block lingers and is released when the
+    view is gone."""
+    np.random.seed(11)
+    pre = prefetch.ProcessPrefetcher(_siamese_batches(), workers=2)
+    pre.next()                                   # the parent's own first batch
+    kept = pre.next()                            # a slot view
+    snapshot = [a.copy() for a in kept[0]] + [kept[1].copy()]
+    blocks = list(pre.pool.blocks)
+    pre.close()
+    assert any(b in prefetch._LINGERING for b in blocks)            # deferred, not unmapped
+    _check(kept)                                                    # would segfault on a dangling mapping
+    np.testing.assert_array_equal(kept[0][0], snapshot[0])
+    np.testing.assert_array_equal(kept[1], snapshot[2])
+    del kept
+    prefetch._release([])                                           # the next close retries the lingering blocks
+    assert not any(b in prefetch._LINGERING for b in blocks)

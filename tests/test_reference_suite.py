@@ -164,13 +164,13 @@ print("RECORD " + json.dumps(record))
 """
 
 
-def _tiny_subset(root, subset, speakers, lines, base=40000):
+def _tiny_subset(root, subset, speakers, lines, base=40000, files=3):
     for s in speakers:
         folder = os.path.join(root, "data", "LibriSpeech", subset, str(s), "1")
         os.makedirs(folder)
         lines.append("{:<5}| {} | {:<16} | 30.00 | Reader {}".format(s, "FM"[s % 2], subset, s))
-        for u in range(3):
-            samples = base + 4000 * u + s % 97                  # 2.5 - 3.0 s by default: padded to 3 s by pad=True
+        for u in range(files):
+            samples = base + 4000 * (u % 3) + s % 97                  # 2.5 - 3.0 s by default: padded to 3 s by pad=True
             with open(os.path.join(folder, "{}-1-{:04d}.flac".format(s, u)), "wb") as handle:
                 handle.write(encode_flac_quick(None, constant=(11 * (s % 50 + 1), samples)))
 
@@ -184,7 +184,9 @@ def three_subset_corpus(tmp_path_factory):
     lines = ["; miniature corpus", ";ID  |SEX| SUBSET           |MINUTES| NAME"]
     _tiny_subset(root, "train-clean-100", range(1000, 1420), lines)
     _tiny_subset(root, "train-clean-360", range(3000, 3420), lines)
-    _tiny_subset(root, "dev-clean", range(500, 540), lines, base=49000)
+    # 5 files per dev speaker: a 32-pair differing draw may cover 32 of the 40 speakers and must still find 32 files of
+    # the other 8 (with 3 files it failed once in a few runs: "Cannot take a larger sample than population")
+    _tiny_subset(root, "dev-clean", range(500, 540), lines, base=49000, files=5)
     with open(os.path.join(root, "data", "LibriSpeech", "SPEAKERS.TXT"), "w") as handle:
         handle.write("\n".join(lines) + "\n")
     return root

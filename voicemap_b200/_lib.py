@@ -39,6 +39,7 @@ SIGNATURES = {
     "vm_conv3_relu_bn_pool2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_gmax_dense_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "vm_pair_head_loss_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "vm_nshot_score": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "vm_split_planes": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "vm_merge_planes": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "vm_split_planes_q": (_i, [_vp, _sz, _vp, _vp, _vp]),
@@ -54,25 +55,27 @@ SIGNATURES = {
     "vm_pack_conv1_raw": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "vm_pack_conv3_raw": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "vm_pack_conv3_dgrad": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
-    "vm_conv1_raw_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
-    "vm_conv3_raw_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "vm_conv1_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vm_conv3_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vm_conv3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_stat_rows_per_clip": (_i, [_i]),
     "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "vm_reduce_scratch_bytes": (_sz, [_i, _i]),
-    "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_gmax_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp]),
+    "vm_bn_bwd_scratch_elems": (_sz, [_i]),
+    "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                       _vp, _vp, _vp]),
     "vm_bn_stats_sums": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "vm_bn_stats_from_sums": (_i, [_vp, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
-    "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
-    "vm_bn_bwd_from_sums": (_i, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp,
-                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
-    "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vm_bn_bwd_from_sums": (_i, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
+    "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "vm_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _f, _vp]),
 }
 

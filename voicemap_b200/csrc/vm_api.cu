@@ -144,7 +144,7 @@ int vm_conv1_relu_bn_pool_fwd(const float* x, int N, int L, int cout, int pool, 
     return set_error(VM_ERR_SHAPE, "conv1: null pointer");
   if (precision >= 2 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for precision 2 / 3");
   return launch_conv1(x, N, L, cout, wpack, epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), nullptr, nullptr, precision, g_max_ctas,
+                      reinterpret_cast<__half*>(out_lo), nullptr, nullptr, nullptr, nullptr, precision, g_max_ctas,
                       (cudaStream_t)stream, 1, 0, nullptr, nullptr, pool);
 }
 
@@ -156,7 +156,7 @@ int vm_conv3_relu_bn_pool2_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int
     return set_error(VM_ERR_SHAPE, "conv3: out_lo required for precision 2 / 3");
   return launch_conv3(reinterpret_cast<const __half*>(in_hi), reinterpret_cast<const __half*>(in_lo), N, L, cin, cout,
                       static_cast<const __half*>(wpack), epi, reinterpret_cast<__half*>(out_hi),
-                      reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, 0, precision, g_max_ctas,
+                      reinterpret_cast<__half*>(out_lo), gmax_partial, nullptr, nullptr, 0, precision, g_max_ctas,
                       (cudaStream_t)stream);
 }
 
@@ -174,6 +174,11 @@ int vm_pair_head_loss_fwd(const float* e1, const float* e2, int N, int E, int me
     return set_error(VM_ERR_SHAPE, "pair_head_loss: null pointer");
   return launch_pair_head_loss(e1, e2, N, E, metric, head_w, head_b, y_true, loss_kind, dist, prob, loss,
                                (cudaStream_t)stream);
+}
+
+int vm_nshot_score(const float* query, const float* support, int T, int k, int n, int E, int distance, float* scores,
+                   int32_t* best, void* stream) {
+  return launch_nshot_score(query, support, T, k, n, E, distance, scores, best, (cudaStream_t)stream);
 }
 
 int vm_split_planes(const float* x, size_t n, uint16_t* hi, uint16_t* lo, void* stream) {
@@ -216,19 +221,36 @@ int vm_pack_conv3_dgrad(const float* kernel, int cin, int cout, void* wpack, flo
 int vm_stat_rows_per_clip(int L) { return 2 * ((L + 255) / 256); }
 size_t vm_reduce_scratch_bytes(int G, int C) { return size_t(G > 0 ? G : 1) * 32 * size_t(C) * 16; }
 
-int vm_conv1_raw_fwd(const float* x, int N, int L, int cout, const void* wpack, const float* epi, float* u,
-                     float* stat_partial, int precision, void* stream) {
-  if (x == nullptr || wpack == nullptr || epi == nullptr || u == nullptr)
-    return set_error(VM_ERR_SHAPE, "conv1_raw: null pointer");
-  return launch_conv1(x, N, L, cout, wpack, epi, nullptr, nullptr, u, stat_partial, precision, g_max_ctas, ST);
+int vm_conv1_train_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,
+                       const float* gamma, uint16_t* u16, float* ext, float* stat_partial, int precision, void* stream) {
+  if (x == nullptr || wpack == nullptr || epi == nullptr || u16 == nullptr || ext == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv1_train: null pointer");
+  return launch_conv1(x, N, L, cout, wpack, epi, nullptr, nullptr, u16, ext, gamma, stat_partial, precision,
+                      g_max_ctas, ST, 1, 0, nullptr, nullptr, pool);
 }
-int vm_conv3_raw_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
-                     const void* wpack, const float* epi, float* out, float* stat_partial, int linear, int precision,
-                     void* stream) {
-  if (in_hi == nullptr || wpack == nullptr || epi == nullptr || out == nullptr)
-    return set_error(VM_ERR_SHAPE, "conv3_raw: null pointer");
+int vm_conv3_train_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int L, int cin, int cout,
+                       const void* wpack, const float* epi, const float* gamma, uint16_t* u16, float* ext,
+                       float* stat_partial, int precision, void* stream) {
+  if (in_hi == nullptr || wpack == nullptr || epi == nullptr || u16 == nullptr || ext == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3_train: null pointer");
+  Conv3Extra ex;
+  ex.out_u16 = u16; ex.out_ext = ext; ex.sign_src = gamma;
   return launch_conv3(CH16(in_hi), CH16(in_lo), N, L, cin, cout, static_cast<const __half*>(wpack), epi, nullptr,
-                      nullptr, nullptr, out, stat_partial, linear, /*in_bf16=*/linear, precision, g_max_ctas, ST);
+                      nullptr, nullptr, nullptr, stat_partial, 0, precision, g_max_ctas, ST, ex);
+}
+int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int cin,
+                   const void* wpack_dgrad, const float* epi_dgrad, const uint32_t* grad_absmax, float* dx,
+                   int precision, void* stream) {
+  if (du_hi == nullptr || wpack_dgrad == nullptr || epi_dgrad == nullptr || dx == nullptr)
+    return set_error(VM_ERR_SHAPE, "conv3_dgrad: null pointer");
+  if (precision < 1 || precision > 3) return set_error(VM_ERR_SHAPE, "conv3_dgrad: precision must be 1, 2 or 3");
+  if (precision == 3 && du_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3_dgrad: du_lo required for precision 3");
+  Conv3Extra ex;
+  ex.grad_absmax = grad_absmax;
+  ex.x_single = (precision == 2) ? 1 : 0;
+  // the gradient is the "input" operand of this convolution (channels = Cout of the forward conv), the output has Cin
+  return launch_conv3(CH16(du_hi), CH16(du_lo), N, L, cout, cin, static_cast<const __half*>(wpack_dgrad), epi_dgrad,
+                      nullptr, nullptr, nullptr, dx, nullptr, /*linear=*/1, precision == 1 ? 1 : 3, g_max_ctas, ST, ex);
 }
 int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, int G, int L, int C,
                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
@@ -236,14 +258,14 @@ int vm_bn_stats_finalize(const float* stat_partial, int rows_per_clip, int N, in
   return launch_bn_stats_finalize(stat_partial, rows_per_clip, vm_padded_channels(C), N, G, L, C, gamma, beta, eps,
                                   momentum, moving_mean, moving_var, bn_const, red_scratch, ST);
 }
-int vm_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* bf_hi, uint16_t* bf_lo, void* stream) {
-  if ((bf_hi == nullptr) != (bf_lo == nullptr)) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: give both bf16 planes");
-  return launch_bn_pool_fwd(u, N, L, C, G, pool, bn_const, mask, H16(out_hi), H16(out_lo), bf_hi, bf_lo, ST);
+int vm_bn_pool_fwd(const float* ext, int N, int Lout, int C, int G, const float* bn_const, const float* mask,
+                   uint16_t* out_hi, uint16_t* out_lo, uint16_t* out_q, void* stream) {
+  if (ext == nullptr || bn_const == nullptr || out_hi == nullptr) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: null pointer");
+  return launch_bn_pool_fwd(ext, N, Lout, C, G, bn_const, mask, H16(out_hi), H16(out_lo), out_q, ST);
 }
-int vm_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask, float* gmax,
-                   int32_t* argmax, void* stream) {
-  return launch_bn_gmax_fwd(u, N, L, C, G, bn_const, mask, gmax, argmax, ST);
+int vm_bn_gmax_fwd(const float* ext, int N, int Lout, int C, int G, const float* bn_const, const float* mask,
+                   float* gmax, int32_t* jstar, void* stream) {
+  return launch_bn_gmax_fwd(ext, N, Lout, C, G, bn_const, mask, gmax, jstar, ST);
 }
 int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, void* stream) {
   return launch_dense_fwd(x, N, C, w, b, E, y, ST);
@@ -258,12 +280,13 @@ int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, 
                  void* stream) {
   return launch_dense_bwd(x, dy, w, N, C, E, dw, db, dx, ST);
 }
-int vm_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C,
-              int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
-              float* bwd_const, float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
-              float* dbias, double* red_scratch, void* stream) {
-  return launch_bn_bwd(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks, bwd_const,
-                       dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch, ST);
+size_t vm_bn_bwd_scratch_elems(int N) { return bn_bwd_scratch_elems(N); }
+int vm_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
+              int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
+              float* bwd_const, float* dgamma, float* dbeta, uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
+              float* scratch_f, float* dbias, double* red_scratch, void* stream) {
+  return launch_bn_bwd(u16, ext, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, scratch_f2, bwd_const,
+                       dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch, ST);
 }
 int vm_bn_stats_sums(const float* stat_partial, int rows_per_clip, int N, int G, int C, double* red_scratch,
                      double* sums, void* stream) {
@@ -274,30 +297,30 @@ int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const 
                           void* stream) {
   return launch_bn_stats_from_sums(sums, count, G, C, gamma, beta, eps, momentum, moving_mean, moving_var, bn_const, ST);
 }
-int vm_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L,
-                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2, int chunks,
-                   double* red_scratch, double* sums, void* stream) {
-  return launch_bn_bwd_sums(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, scratch_f2, chunks,
+int vm_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L,
+                   int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
+                   uint32_t* grad_absmax, double* red_scratch, double* sums, void* stream) {
+  return launch_bn_bwd_sums(ext, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, scratch_f2, grad_absmax,
                             red_scratch, sums, ST);
 }
-int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
-                        const float* dy_pooled, const float* d_gmax, const int32_t* argmax, int N, int L, int C, int G,
-                        int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
-                        float* dgamma, float* dbeta, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f, float* dbias,
-                        double* red_scratch, void* stream) {
-  return launch_bn_bwd_from_sums(local_sums, global_sums, count, u, dy_pooled, d_gmax, argmax, N, L, C, G, pool,
-                                 bn_const, mask, chunks, bwd_const, dgamma, dbeta, H16(du_hi), H16(du_lo), scratch_f,
-                                 dbias, red_scratch, ST);
+int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
+                        const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L, int C, int G,
+                        int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
+                        float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
+                        float* dbias, double* red_scratch, void* stream) {
+  return launch_bn_bwd_from_sums(local_sums, global_sums, count, u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool,
+                                 bn_const, mask, bwd_const, dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo),
+                                 scratch_f, dbias, red_scratch, ST);
 }
 int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L,
-              int cin, int cout, int precision, float* partial, size_t partial_bytes, float* dw, void* stream) {
+              int cin, int cout, int precision, const uint32_t* grad_absmax, float* partial, size_t partial_bytes,
+              float* dw, void* stream) {
   return launch_wgrad3(CH16(x_hi), CH16(x_lo), CH16(du_hi), CH16(du_lo), N, L, cin, cout, precision, partial,
-                       partial_bytes, dw, ST);
+                       partial_bytes, dw, grad_absmax, ST);
 }
 int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int precision,
-              float* partial, size_t partial_bytes, float* dw, void* stream) {
-  if (precision != 0 && precision != 1 && precision != 3) return set_error(VM_ERR_SHAPE, "wgrad1: bad precision");
-  return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, ST, precision);
+              const uint32_t* grad_absmax, float* partial, size_t partial_bytes, float* dw, void* stream) {
+  return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, grad_absmax, ST, precision);
 }
 int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* scratch, float inv_scale,
                  float clipnorm, float lr_t, float beta1, float beta2, float eps, void* stream) {
@@ -327,17 +350,17 @@ static int encoder_fwd_impl(const float* x, int N, int L, int filters, int first
   float* part = reinterpret_cast<float*>(ws + 2 * pl.a1 + 2 * pl.a2 + 2 * pl.a3);
   const int f = filters;
   int rc;
-  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, precision, g_max_ctas, st, x_stride,
+  if ((rc = launch_conv1(x, N, L, f, wpack[0], epi[0], a1h, a1l, nullptr, nullptr, nullptr, nullptr, precision, g_max_ctas, st, x_stride,
                          x_clip_stride, pre_mean, pre_scale, first_pool)))
     return rc;
   if ((rc = launch_conv3(a1h, a1l, N, pl.l1, f, 2 * f, static_cast<const __half*>(wpack[1]), epi[1], a2h, a2l,
-                         nullptr, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a2h, a2l, N, pl.l2, 2 * f, 3 * f, static_cast<const __half*>(wpack[2]), epi[2], a3h, a3l,
-                         nullptr, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
+                         nullptr, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   if ((rc = launch_conv3(a3h, a3l, N, pl.l3, 3 * f, 4 * f, static_cast<const __half*>(wpack[3]), epi[3], nullptr,
-                         nullptr, part, nullptr, nullptr, 0, 0, precision, g_max_ctas, st)))
+                         nullptr, part, nullptr, nullptr, 0, precision, g_max_ctas, st)))
     return rc;
   return launch_gmax_dense(part, N, pl.t4, 4 * f, pl.c4_pad, epi[3], dense_w, dense_b, E, nullptr, emb, st);
 }

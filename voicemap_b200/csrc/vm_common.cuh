@@ -329,6 +329,19 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
                :
                : "memory");
 }
+// split form of the 8-column load
+__device__ __forceinline__ void tmem_ld_32x8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile(
@@ -391,5 +404,32 @@ __device__ __forceinline__ void sts_b16(uint32_t addr, uint16_t v) {
 }
 
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(uint32_t(b) << 16); }
+
+// ---------------------------------------------------------------------------------------------
+// Training: the un-pooled activation u = relu(conv + bias) is kept for the backward pass as ONE 16-bit word per
+// element: fp16(u) in bits 0-14 (u >= 0, so the sign bit is free) and, in bit 15, "this element is the arg-max of its
+// MaxPool window" (first winner on ties; for channels with a negative BatchNorm scale the arg-MIN of u, which is the
+// arg-max of the normalised value).  The forward pass itself continues from the fp32 window extremes (see
+// vm_train.cu), so the rounding to fp16 only enters the backward pass through xhat = (u - mean) * rstd.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t encode_u(float u, bool is_argmax) {
+  return uint16_t(__half_as_ushort(__float2half_rn(u)) | (is_argmax ? 0x8000u : 0u));
+}
+__device__ __forceinline__ float decode_u(uint32_t bits) { return __half2float(__ushort_as_half(uint16_t(bits & 0x7FFFu))); }
+
+// Gradients travel between the backward kernels as fp16 planes scaled by a power of two chosen per block from the
+// largest |s * dy| the BatchNorm-backward reduction saw (a float's bits, kept in a device word and raised with
+// atomicMax: non-negative floats order like unsigned integers).  Every kernel that writes or reads the scaled planes
+// derives the scale from that word with this function, so producer and consumers agree exactly; powers of two make the
+// scaling itself exact.  Target: the largest routed gradient lands in [32, 64) -- 2^10 of head room below fp16's
+// maximum for the batch-statistics terms, 2^19 of normal range below.
+__host__ __device__ __forceinline__ float grad_scale_from_absmax(float a) {
+  if (!(a > 0.f) || !(a < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(a, &e);                 // a = m * 2^e, m in [0.5, 1)
+  e = 6 - e;
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return ldexpf(1.f, e);
+}
 
 }  // namespace vm

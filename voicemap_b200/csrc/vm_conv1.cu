@@ -336,15 +336,23 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
         const int co = slab * kTileM + ch;
         const float4 ep = p.epi[co];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
-        if (p.out_f32 != nullptr) {
-          // train-mode forward: un-pooled u = relu(acc + bias) as fp32 + per-channel {sum, sum of squares}
-          // partials.  Granule = 64 positions x 128 channels fp32 = the group's staging buffer (4 TMA boxes of 32
-          // channels); the two warps of a lane quarter take 32 columns each.
+        if (p.out_u16 != nullptr) {
+          // train-mode forward: per position u = relu(acc + bias) -> {sum, sum of squares} partials for the batch
+          // statistics, the encoded un-pooled activation (fp16 + arg-max flag, encode_u) and the fp32 extreme of every
+          // MaxPool(kPool) window (max, or min where the BatchNorm scale is negative).  Granule = 64 positions x 128
+          // channels = the group's staging buffer: [u16: 2 boxes of 64 pos x 64 ch][extremes: 4 boxes of 64/kPool
+          // windows x 32 ch fp32]; the two warps of a lane quarter take 32 columns each.
           if (wg == 0) mbar_wait(&bars->tfull[buf], it & 1);  // one polling warp per group; the rest block in bar.sync
+          constexpr int kWin = 32 / kPool;                     // windows per warp and granule
+          constexpr int kExtRows = 64 / kPool;
+          const bool neg = (p.sign_src != nullptr && co < p.cout) ? (p.sign_src[co] < 0.f) : false;
+          const int lvalid = p.lout * kPool;
           float s1 = 0.f, s2 = 0.f;
+          const uint32_t st_u = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (chalf * 32) * 128 + (ch & 63) * 2;
+          const uint32_t st_m = smem_u32(ob) + 2 * kOutBoxBytes + (ch >> 5) * (kExtRows * 128) + (chalf * kWin) * 128 +
+                                (ch & 31) * 4;
 #pragma unroll 1
           for (int gr = 0; gr < kTileN / 64; ++gr) {
-            const uint32_t st = smem_u32(ob) + (ch >> 5) * 8192 + (ch & 31) * 4 + chalf * 32 * 128;
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(bar_id, 256);
             tc_fence_after_sync();
@@ -356,10 +364,23 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
             }
             const int pos0 = p0 + gr * 64 + chalf * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float y = apply_epi(ep, v[j]);
-              if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
-              sts_f32(st + j * 128, y);
+            for (int w = 0; w < kWin; ++w) {
+              float y[kPool];
+              int best = 0;
+#pragma unroll
+              for (int i = 0; i < kPool; ++i) {
+                y[i] = apply_epi(ep, v[kPool * w + i]);
+                if (pos0 + kPool * w + i < p.L) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
+              }
+              float ext = y[0];
+#pragma unroll
+              for (int i = 1; i < kPool; ++i)
+                if (neg ? (y[i] < ext) : (y[i] > ext)) { ext = y[i]; best = i; }   // first winner on ties
+              const bool win = pos0 + kPool * w + kPool - 1 < lvalid;              // 'valid' pooling drops the tail
+#pragma unroll
+              for (int i = 0; i < kPool; ++i)
+                sts_b16(st_u + (kPool * w + i) * 128, encode_u(y[i], win && best == i));
+              sts_f32(st_m + w * 128, ext);
             }
             fence_proxy_async_smem();
             named_bar_sync(bar_id, 256);
@@ -367,9 +388,17 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
               const int pos = p0 + gr * 64;
               if (pos < p.L) {
 #pragma unroll
-                for (int b4 = 0; b4 < 4; ++b4) {
-                  const int c0 = slab * kTileM + b4 * 32;
-                  if (c0 < p.cout) tma_store_3d(&tm_oh, ob + b4 * 8192, c0, pos, n);
+                for (int half = 0; half < 2; ++half) {
+                  const int c0 = slab * kTileM + half * 64;
+                  if (c0 < p.cout) tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+                }
+                if (pos / kPool < p.lout) {
+#pragma unroll
+                  for (int b4 = 0; b4 < 4; ++b4) {
+                    const int c0 = slab * kTileM + b4 * 32;
+                    if (c0 < p.cout)
+                      tma_store_3d(&tm_ol, ob + 2 * kOutBoxBytes + b4 * (kExtRows * 128), c0, pos / kPool, n);
+                  }
                 }
               }
               tma_store_commit();
@@ -459,15 +488,17 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
 }
 
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
-                 __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
-                 cudaStream_t stream, int x_stride, long long x_clip_stride, const float* pre_mean,
-                 const float* pre_scale, int pool) {
+                 __half* out_lo, uint16_t* out_u16, float* out_ext, const float* sign_src, float* stat_partial,
+                 int products, int max_ctas, cudaStream_t stream, int x_stride, long long x_clip_stride,
+                 const float* pre_mean, const float* pre_scale, int pool) {
   using namespace c1;
   if (pool != 2 && pool != 4) return set_error(VM_ERR_UNSUPPORTED, "conv1: first MaxPool1D size must be 2 or 4");
   if (N <= 0 || L < pool) return set_error(VM_ERR_SHAPE, "conv1: need N > 0 and L >= pool size");
   if (cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout must be a positive multiple of 8");
   if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "conv1: products must be 1, 2 or 3");
-  if (products == 2 && out_f32 != nullptr) products = 3;   // the un-pooled fp32 output has no second plane
+  if ((out_u16 != nullptr) != (out_ext != nullptr))
+    return set_error(VM_ERR_SHAPE, "conv1: the train-mode forward needs both out_u16 and out_ext");
+  if (products == 2 && out_u16 != nullptr) products = 3;   // block 1 itself always runs fp16 x 3 for products >= 2
   const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
   const int nslab = cout_pad / kTileM;
   if (nslab > kMaxSlabs) return set_error(VM_ERR_UNSUPPORTED, "conv1: Cout > 512 not supported");
@@ -483,16 +514,19 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo;
   p.nstages = kMaxStages;
-  p.out_f32 = out_f32;
+  p.out_u16 = out_u16; p.out_ext = out_ext; p.sign_src = sign_src;
   p.stat_partial = reinterpret_cast<float2*>(stat_partial);
   CUtensorMap oh, ol;
-  if (out_f32 != nullptr) {
-    const uint64_t odims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
-    const uint64_t ostr[2] = {uint64_t(cout) * 4, uint64_t(L) * cout * 4};
-    const uint32_t obox[3] = {32, 64, 1};
+  if (out_u16 != nullptr) {
+    const uint64_t udims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+    const uint64_t ustr[2] = {uint64_t(cout) * 2, uint64_t(L) * cout * 2};
+    const uint32_t ubox[3] = {64, 64, 1};
+    const uint64_t mdims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
+    const uint64_t mstr[2] = {uint64_t(cout) * 4, uint64_t(p.lout) * cout * 4};
+    const uint32_t mbox[3] = {32, uint32_t(64 / pool), 1};
     int rc;
-    if ((rc = make_tensor_map(&oh, out_f32, 3, odims, ostr, obox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
-    ol = oh;
+    if ((rc = make_tensor_map(&oh, out_u16, 3, udims, ustr, ubox, VM_SWIZZLE_NONE))) return rc;
+    if ((rc = make_tensor_map(&ol, out_ext, 3, mdims, mstr, mbox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
   } else {
     if (out_hi == nullptr) return set_error(VM_ERR_SHAPE, "conv1: no output given");
     if (products >= 2 && out_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv1: out_lo required for products>=2");
@@ -565,7 +599,9 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
   uint8_t* tring = smem + kUStages * kUStageBytes;
   Wgrad1Barriers* bars = reinterpret_cast<Wgrad1Barriers*>(tring + kTStages * kTStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nplanes = (p.products == 3) ? 2 : 1;
+  // products 3: Uh*Th + Ul*Th + Uh*Tl;  2: Uh*Th + Uh*Tl (one-plane gradient);  1: Uh*Th
+  const int tplanes = (p.products >= 2) ? 2 : 1;
+  const int uplanes = (p.products == 3) ? 2 : 1;
   const int ntiles = p.N * p.nptile;
   const int co0 = blockIdx.y * 128;
 
@@ -582,7 +618,7 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp < kTStages) {
-    // Toeplitz producers (bf16 planes): warp q fills stage q for local tiles q, q + 2, ...
+    // Toeplitz producers (fp16 planes of the waveform): warp q fills stage q for local tiles q, q + 2, ...
     const int q = warp;
     uint32_t i = q;
     for (int tile = blockIdx.x + q * gridDim.x; tile < ntiles; tile += kTStages * gridDim.x, i += kTStages) {
@@ -591,7 +627,7 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
       float xv[39];
       toeplitz_load_strip(p.x + size_t(n) * p.L, 1, 0.f, 1.f, p0 - 15 + 8 * lane, p.L, xv);
       mbar_wait(&bars->tempty[q], ((i / kTStages) & 1) ^ 1);
-      toeplitz_store<true>(xv, smem_u32(tring + q * kTStageBytes + lane * kGroupStride), nplanes, kTPlaneBytes);
+      toeplitz_store<false>(xv, smem_u32(tring + q * kTStageBytes + lane * kGroupStride), tplanes, kTPlaneBytes);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tfull[q]);
@@ -607,8 +643,8 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
           const int s = it % kUStages;
           mbar_wait(&bars->uempty[s], ((it / kUStages) & 1) ^ 1);
           uint8_t* base = uring + s * kUStageBytes;
-          mbar_arrive_expect_tx(&bars->ufull[s], nplanes * kUPlaneBytes);
-          for (int pl = 0; pl < nplanes; ++pl) {
+          mbar_arrive_expect_tx(&bars->ufull[s], uplanes * kUPlaneBytes);
+          for (int pl = 0; pl < uplanes; ++pl) {
             const CUtensorMap* m = pl ? &tm_ul : &tm_uh;
             tma_load_3d(base + pl * kUPlaneBytes, m, &bars->ufull[s], co0, p0 + j * kSub, n);
             tma_load_3d(base + pl * kUPlaneBytes + kUHalfBytes, m, &bars->ufull[s], co0 + 64, p0 + j * kSub, n);
@@ -619,8 +655,8 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
   } else if (warp == 5) {
     {
       const bool elected = elect_one_sync();   // whole warp runs the loop (uniform descriptor math), one lane issues
-      // M = 128 (co), N = 32 (taps), both operands MN-major, both bf16
-      const uint32_t idesc = make_idesc_f16(128, 32, 1, 1) | (1u << 15) | (1u << 16);
+      // M = 128 (co), N = 32 (taps), both operands MN-major, both fp16
+      const uint32_t idesc = make_idesc_f16(128, 32) | (1u << 15) | (1u << 16);
       uint32_t i = 0, uit = 0, first = 1;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
         const int ts = i % kTStages;
@@ -639,12 +675,12 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
             if (elected) umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
                      make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, first ? 0u : 1u);
             first = 0;
-            if (nplanes == 2) {
-              if (elected) umma_f16(tmem_base, make_smem_desc(ul + arow, kUHalfBytes, 1024, kLayoutSW128),
+            if (uplanes == 2 && elected)
+              umma_f16(tmem_base, make_smem_desc(ul + arow, kUHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(th + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
-              if (elected) umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
+            if (tplanes == 2 && elected)
+              umma_f16(tmem_base, make_smem_desc(uh + arow, kUHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(tl + brow, kGroupStride, 128, kLayoutNone), idesc, 1);
-            }
           }
           if (elected) umma_commit(&bars->uempty[us]);
         }
@@ -679,7 +715,7 @@ int launch_wgrad1_tc(const float* x, const __half* du_hi, const __half* du_lo, i
                      float* partial, size_t partial_bytes, int* nsplit_out, cudaStream_t stream) {
   using namespace w1;
   if (N <= 0 || L <= 0 || cout <= 0 || cout % 8 != 0) return set_error(VM_ERR_SHAPE, "wgrad1: bad shape");
-  if (products == 3 && du_lo == nullptr) return set_error(VM_ERR_SHAPE, "wgrad1: lo plane required");
+  if (products == 3 && du_lo == nullptr) return set_error(VM_ERR_SHAPE, "wgrad1: lo plane required for products = 3");
   Wgrad1Params p{};
   p.x = x; p.N = N; p.L = L; p.cout = cout; p.products = products;
   p.nptile = (L + kTileN - 1) / kTileN;

@@ -126,6 +126,57 @@ __device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, ui
   }
 }
 
+// Train-mode epilogue of one accumulator tile for one warp (the two warps of a lane quarter take 8 of every 16
+// columns): u = relu(acc + bias) per position -> per-channel {sum, sum of squares} for the batch statistics, the
+// un-pooled activation as fp16 + arg-max flag (encode_u) and the fp32 extreme of every MaxPool(2) window (max, or
+// min for channels whose BatchNorm scale is negative: the value the normalised maximum comes from).  Granule = 16
+// positions: staging buffer = [u16: 2 boxes of 16 pos x 64 ch][extremes: 4 boxes of 8 windows x 32 ch fp32] = 8 KB,
+// handed to the store warp like the pooled granules.
+__device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t taddr, uint8_t* stage, int ch, int chalf,
+                                          Conv3Barriers* bars, int buf, uint32_t& gcount, int pos_base, int L,
+                                          int lvalid, float& s1, float& s2) {
+  using namespace c3;
+  const uint32_t off_u = (ch >> 6) * 2048 + (chalf * 8) * 128 + (ch & 63) * 2;
+  const uint32_t off_m = 4096 + (ch >> 5) * 1024 + (chalf * 4) * 128 + (ch & 31) * 4;
+  auto granule = [&](const uint32_t (&r)[8], int gr) {
+    const int sb = gcount & 1;
+    const uint32_t st = smem_u32(stage + sb * kStageBufBytes);
+    if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+    const int pos0 = pos_base + gr * 16 + chalf * 8;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float a = apply_epi(ep, __uint_as_float(r[2 * w]));
+      const float b = apply_epi(ep, __uint_as_float(r[2 * w + 1]));
+      if (pos0 + 2 * w < L) { s1 += a; s2 = fmaf(a, a, s2); }
+      if (pos0 + 2 * w + 1 < L) { s1 += b; s2 = fmaf(b, b, s2); }
+      const bool second = neg ? (b < a) : (b > a);          // first winner on ties
+      const bool win = pos0 + 2 * w + 1 < lvalid;           // the window exists ('valid' pooling drops an odd tail)
+      sts_b16(st + off_u + (2 * w) * 128, encode_u(a, win && !second));
+      sts_b16(st + off_u + (2 * w + 1) * 128, encode_u(b, win && second));
+      sts_f32(st + off_m + w * 128, second ? b : a);
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(&bars->sfull[sb]);
+    ++gcount;
+  };
+  uint32_t ra[8], rb[8];
+  tmem_ld_32x8_issue(taddr + chalf * 8, ra);
+#pragma unroll 1
+  for (int gr = 0; gr < kTileN / 16; gr += 2) {
+    tmem_ld_wait(ra);
+    tmem_ld_32x8_issue(taddr + (gr + 1) * 16 + chalf * 8, rb);
+    granule(ra, gr);
+    tmem_ld_wait(rb);
+    if (gr + 2 < kTileN / 16) {
+      tmem_ld_32x8_issue(taddr + (gr + 2) * 16 + chalf * 8, ra);
+    } else {
+      tc_fence_before_sync();
+      mbar_arrive(&bars->tempty[buf]);
+    }
+    granule(rb, gr + 1);
+  }
+}
+
 __global__ void __launch_bounds__(c3::kThreads, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
@@ -175,10 +226,11 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
           const int s = it % kXStages;
           mbar_wait(&bars->xempty[s], ((it / kXStages) & 1) ^ 1);
           uint8_t* dst = xring + s * kXSlotBytes;
-          mbar_arrive_expect_tx(&bars->xfull[s], wplanes * kXPlaneBytes);
+          const int xplanes = p.x_single ? 1 : wplanes;
+          mbar_arrive_expect_tx(&bars->xfull[s], xplanes * kXPlaneBytes);
           tma_load_3d(dst, &tm_xh_main, &bars->xfull[s], c * kKC, p0 - 1, n);
           tma_load_3d(dst + kXMainBytes, &tm_xh_halo, &bars->xfull[s], c * kKC, p0 + 255, n);
-          if (wplanes == 2) {
+          if (xplanes == 2) {
             tma_load_3d(dst + kXPlaneBytes, &tm_xl_main, &bars->xfull[s], c * kKC, p0 - 1, n);
             tma_load_3d(dst + kXPlaneBytes + kXMainBytes, &tm_xl_halo, &bars->xfull[s], c * kKC, p0 + 255, n);
           }
@@ -217,7 +269,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         // there are positions left -- the tensor pipe is the bound, so unused columns are pure waste
         const int p0 = ((tile / p.nslab) % p.nptile) * kTileN;
         const int ncols = min(kTileN, (p.L - p0 + 15) & ~15);
-        const uint32_t idesc = make_idesc_f16(kTileM, ncols, p.in_bf16, p.in_bf16);  // dgrad: both operands bf16
+        const uint32_t idesc = make_idesc_f16(kTileM, ncols);
         const uint32_t idesc8 = make_idesc_f8(kTileM, ncols);
         mbar_wait(&bars->tempty[buf], ((tit >> 1) & 1) ^ 1);
         tc_fence_after_sync();
@@ -246,7 +298,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
                            make_smem_desc(bh + k * 32, 16, 1024, kLayoutSW128), idesc, acc);
                 acc = 1;
               }
-              if (wplanes == 2 && !mixed) {
+              if (wplanes == 2 && !mixed && !p.x_single) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   if (elected)
@@ -289,7 +341,41 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     // The epilogue warps hand over each 8 KB output granule through an mbarrier pair per staging buffer instead of
     // meeting in a CTA-wide named barrier: no epilogue warp waits for another one or for the store issue, they only
     // wait (rarely) for a staging buffer whose previous store has not been read out of shared memory yet.
-    if (lane == 0 && p.gmax_partial == nullptr && p.out_f32 == nullptr) {
+    if (lane == 0 && p.out_u16 != nullptr) {
+      // train-mode forward: 16 granules per tile, each 2 boxes of encoded activations + 4 boxes of window extremes
+      uint32_t g = 0;
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
+        const int tile = ti.tile();
+        const int slab = tile % p.nslab;
+        const int pt_lin = tile / p.nslab;
+        const int n = pt_lin / p.nptile;
+        const int p0 = (pt_lin % p.nptile) * kTileN;
+        for (int gr = 0; gr < kTileN / 16; ++gr, ++g) {
+          const int b = g & 1;
+          mbar_wait(&bars->sfull[b], (g >> 1) & 1);
+          const uint8_t* sbuf = stage + b * kStageBufBytes;
+          const int pos = p0 + gr * 16;
+          if (pos < p.L) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = slab * kTileM + half * 64;
+              if (c0 < p.cout) tma_store_3d(&tm_oh, sbuf + half * 2048, c0, pos, n);
+            }
+            if ((pos >> 1) < p.lout) {
+#pragma unroll
+              for (int b4 = 0; b4 < 4; ++b4) {
+                const int c0 = slab * kTileM + b4 * 32;
+                if (c0 < p.cout) tma_store_3d(&tm_ol, sbuf + 4096 + b4 * 1024, c0, pos >> 1, n);
+              }
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&bars->sempty[b]);
+        }
+      }
+      tma_store_wait_all<0>();
+    } else if (lane == 0 && p.gmax_partial == nullptr && p.out_f32 == nullptr) {
       uint32_t g = 0;
       for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
         const int tile = ti.tile();
@@ -347,7 +433,13 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       named_bar_sync(1, kEpiWarps * 32);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
-      if (p.gmax_partial != nullptr) {
+      if (p.out_u16 != nullptr) {
+        const bool neg = (p.sign_src != nullptr && co < p.cout) ? (p.sign_src[co] < 0.f) : false;
+        float s1 = 0.f, s2 = 0.f;
+        raw2_tile(ep, neg, taddr, stage, ch, chalf, bars, buf, gcount, p0, p.L, lvalid, s1, s2);
+        if (p.stat_partial != nullptr)
+          p.stat_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+      } else if (p.gmax_partial != nullptr) {
         float m = -INFINITY;
 #pragma unroll 1
         for (int gg = 0; gg < kTileN / 64; ++gg) {
@@ -373,6 +465,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         // partials; dgrad: y = acc).  Granule = 16 positions x 128 channels fp32 (4 TMA boxes of 32 channels);
         // the two warps of a lane quarter take 8 columns each.
         float s1 = 0.f, s2 = 0.f;
+        // dgrad: the incoming gradient planes carry a power-of-two scale (vm_common.cuh); undo it here
+        const float unscale = (p.linear && p.grad_absmax != nullptr)
+                                  ? 1.0f / grad_scale_from_absmax(__uint_as_float(*p.grad_absmax)) : 1.0f;
 #pragma unroll 1
         for (int gr = 0; gr < kTileN / 16; ++gr, ++gcount) {
           uint8_t* sbuf = stage + (gcount & 1) * kStageBufBytes;
@@ -386,7 +481,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
           const int pos0 = p0 + gr * 16 + chalf * 8;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float y = p.linear ? v[j] : apply_epi(ep, v[j]);
+            const float y = p.linear ? v[j] * unscale : apply_epi(ep, v[j]);
             if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
             sts_f32(st + j * 128, y);
           }
@@ -441,16 +536,20 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
-                 float* stat_partial, int linear, int in_bf16, int products, int max_ctas, cudaStream_t stream) {
+                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream,
+                 const Conv3Extra& extra) {
   using namespace c3;
   if (N <= 0 || L <= 0) return set_error(VM_ERR_SHAPE, "conv3: N and L must be positive");
   // K chunks are 64 channels wide; a ragged last chunk is zero-filled by TMA in both operands
   if (cin % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cin must be a multiple of 8");
   if (cout % 8 != 0) return set_error(VM_ERR_UNSUPPORTED, "conv3: Cout must be a multiple of 8");
   if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "conv3: products must be 1, 2 or 3");
-  if (products == 2 && (out_f32 != nullptr || in_bf16))
-    return set_error(VM_ERR_UNSUPPORTED, "conv3: products=2 (e5m2 correction planes) is an eval-forward mode");
-  if (gmax_partial == nullptr && out_hi == nullptr && out_f32 == nullptr)
+  if (products == 2 && (out_f32 != nullptr || extra.x_single))
+    return set_error(VM_ERR_UNSUPPORTED, "conv3: products=2 (e5m2 correction planes) is a forward mode");
+  if (extra.x_single && products != 3) return set_error(VM_ERR_SHAPE, "conv3: x_single goes with products=3");
+  if ((extra.out_u16 != nullptr) != (extra.out_ext != nullptr))
+    return set_error(VM_ERR_SHAPE, "conv3: the train-mode forward needs both out_u16 and out_ext");
+  if (gmax_partial == nullptr && out_hi == nullptr && out_f32 == nullptr && extra.out_u16 == nullptr)
     return set_error(VM_ERR_SHAPE, "conv3: no output given");
   if (L / 2 <= 0) return set_error(VM_ERR_SHAPE, "conv3: L must be >= 2");
   const int cout_pad = (cout + kTileM - 1) / kTileM * kTileM;
@@ -465,7 +564,9 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   p.epi = reinterpret_cast<const float4*>(epi);
   p.out_hi = out_hi; p.out_lo = out_lo; p.gmax_partial = gmax_partial;
   p.out_f32 = out_f32; p.stat_partial = reinterpret_cast<float2*>(stat_partial); p.linear = linear;
-  p.in_bf16 = in_bf16;
+  p.x_single = extra.x_single;
+  p.out_u16 = extra.out_u16; p.out_ext = extra.out_ext; p.sign_src = extra.sign_src;
+  p.grad_absmax = extra.grad_absmax;
 
   CUtensorMap xh_main, xh_halo, xl_main, xl_halo, wh, wl;
   // X planes: (N, L, Cin) fp16, dims fastest-first {Cin, L, N}
@@ -475,8 +576,9 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   int rc;
   if ((rc = make_tensor_map(&xh_main, in_hi, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&xh_halo, in_hi, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
-  const __half* lo_src = (products >= 2) ? in_lo : in_hi;
-  if (products >= 2 && in_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: second plane required for products>=2");
+  const bool need_lo = products >= 2 && !extra.x_single;
+  const __half* lo_src = need_lo ? in_lo : in_hi;
+  if (need_lo && in_lo == nullptr) return set_error(VM_ERR_SHAPE, "conv3: second plane required for products>=2");
   if ((rc = make_tensor_map(&xl_main, lo_src, 3, xdims, xstr, box_main, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&xl_halo, lo_src, 3, xdims, xstr, box_halo, VM_SWIZZLE_128B))) return rc;
   // W planes: [plane][tap*cout_pad + cout][cin] fp16
@@ -491,7 +593,18 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
 
   // pooled output planes (N, lout, cout) fp16 -- TMA store boxes of 64 channels x 16 positions
   CUtensorMap oh, ol;
-  if (out_f32 != nullptr) {
+  if (extra.out_u16 != nullptr) {
+    // encoded activations (N, L, cout) 16-bit: boxes of 64 channels x 16 positions; window extremes (N, lout, cout)
+    // fp32: boxes of 32 channels x 8 windows
+    const uint64_t udims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
+    const uint64_t ustr[2] = {uint64_t(cout) * 2, uint64_t(L) * cout * 2};
+    const uint32_t ubox[3] = {64, kStagePos, 1};
+    if ((rc = make_tensor_map(&oh, extra.out_u16, 3, udims, ustr, ubox, VM_SWIZZLE_NONE))) return rc;
+    const uint64_t mdims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
+    const uint64_t mstr[2] = {uint64_t(cout) * 4, uint64_t(p.lout) * cout * 4};
+    const uint32_t mbox[3] = {32, 8, 1};
+    if ((rc = make_tensor_map(&ol, extra.out_ext, 3, mdims, mstr, mbox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;
+  } else if (out_f32 != nullptr) {
     // un-pooled fp32 output (N, L, cout): TMA store boxes of 32 channels x 16 positions
     const uint64_t odims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
     const uint64_t ostr[2] = {uint64_t(cout) * 4, uint64_t(L) * cout * 4};

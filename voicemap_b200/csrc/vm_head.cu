@@ -97,7 +97,7 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
 // ---------------------------------------------------------------------------------------------
 // dgrad weights: dX[p][ci] = sum_t sum_co dU[p + t - 1][co] * W[2 - t][ci][co] is a k=3 'same' convolution of dU with
 // the tap-flipped, channel-transposed kernel.  w (3, cin, cout) -> wpack [plane][tap][cin_pad][cout] fp16, i.e. the
-// conv3 operand layout with the roles (cin' = cout, cout' = cin), as bf16 (hi, lo) planes.
+// conv3 operand layout with the roles (cin' = cout, cout' = cin), as fp16 (hi, lo) planes.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad,
                                         __half* __restrict__ wpack, float4* __restrict__ epi) {
@@ -109,10 +109,10 @@ __global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, in
   const int ci = int((idx / cout) % cin_pad);
   const int tap = int(idx / (size_t(cout) * cin_pad));
   const float v = (ci < cin) ? w[(size_t(2 - tap) * cin + ci) * cout + co] : 0.f;
-  uint16_t h, l;  // bf16 planes: the dgrad MMA runs bf16 x bf16 (its other operand, dU, is bf16)
-  split_bf16(v, h, l);
-  wpack[idx] = __ushort_as_half(h);
-  wpack[total + idx] = __ushort_as_half(l);
+  __half h, l;    // fp16 (hi, lo) planes, like the forward weights; the other operand is the scaled fp16 gradient
+  split_f32(v, h, l);
+  wpack[idx] = h;
+  wpack[total + idx] = l;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -245,6 +245,70 @@ __global__ void pair_head_loss_kernel(const float* __restrict__ e1, const float*
     float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (threadIdx.x == 0) loss[0] = v / float(N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-way n-shot scoring on embeddings (voicemap/utils.py:156-212): class means over the n shots of each of the k
+// support classes, distance to the query (0 euclidean, 1 cosine, 2 dot product, as the reference defines them), and
+// the arg-min class (first minimum, like np.argmin).  One block per task, one warp per class (round robin); sums are
+// taken in double like scipy's cdist / the float64 numpy of the reference, so near-ties resolve the same way.
+//   cosine:      centre = mean_i s_i / |s_i|;                 score = 1 - centre.q / (|centre| |q|)
+//   dot product: centre = (mean_i s_i / |s_i|) * mean_i |s_i|; score = -centre.q
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void nshot_score_kernel(const float* __restrict__ query, const float* __restrict__ support, int T, int k,
+                                   int n, int E, int distance, float* __restrict__ scores, int* __restrict__ best) {
+  extern __shared__ double sc[];   // [k] scores of this task
+  const int t = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* q = query + size_t(t) * E;
+  for (int c = warp; c < k; c += nwarps) {
+    const float* s = support + (size_t(t) * k + c) * size_t(n) * E;
+    double score;
+    if (distance == 0) {
+      double ss = 0.0;
+      for (int j = lane; j < E; j += 32) {
+        double m = 0.0;
+        for (int i = 0; i < n; ++i) m += double(s[size_t(i) * E + j]);
+        const double d = m / double(n) - double(q[j]);
+        ss += d * d;
+      }
+      score = sqrt(warp_sum(ss));
+    } else {
+      // unit vectors of the shots: 1 / |s_i| per shot first (n is small: 1 or 5 in the reference's scripts)
+      double cq = 0.0, cc = 0.0, qq = 0.0, mean_norm = 0.0;
+      for (int j0 = 0; j0 < E; j0 += 32) {   // centre_j needs every shot's norm: recomputed per j block (n*E is tiny)
+        const int j = j0 + lane;
+        double cj = 0.0;
+        for (int i = 0; i < n; ++i) {
+          double nn = 0.0;
+          for (int jj = lane; jj < E; jj += 32) { const double v = double(s[size_t(i) * E + jj]); nn += v * v; }
+          const double norm = sqrt(warp_sum(nn));
+          if (j < E) cj += double(s[size_t(i) * E + j]) / norm;
+          if (j0 == 0) mean_norm += norm;
+        }
+        cj /= double(n);
+        if (j < E) { const double qj = double(q[j]); cq += cj * qj; cc += cj * cj; qq += qj * qj; }
+      }
+      cq = warp_sum(cq); cc = warp_sum(cc); qq = warp_sum(qq);
+      mean_norm /= double(n);
+      score = (distance == 1) ? 1.0 - cq / (sqrt(cc) * sqrt(qq)) : -(cq * mean_norm);
+    }
+    if (lane == 0) {
+      sc[c] = score;
+      if (scores != nullptr) scores[size_t(t) * k + c] = float(score);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0;
+    for (int c = 1; c < k; ++c)
+      if (sc[c] < sc[b]) b = c;
+    best[t] = b;
   }
 }
 
@@ -392,6 +456,16 @@ int launch_pair_head_loss(const float* e1, const float* e2, int N, int E, int me
   pair_head_loss_kernel<<<1, 256, 0, stream>>>(e1, e2, N, E, metric, head_w, head_b, y_true, loss_kind, dist, prob,
                                                loss);
   return check_launch("pair_head_loss");
+}
+
+int launch_nshot_score(const float* query, const float* support, int T, int k, int n, int E, int distance,
+                       float* scores, int* best, cudaStream_t stream) {
+  if (T <= 0 || k <= 0 || n <= 0 || E <= 0) return set_error(VM_ERR_SHAPE, "nshot_score: bad shape");
+  if (distance < 0 || distance > 2) return set_error(VM_ERR_UNSUPPORTED, "nshot_score: distance must be 0, 1 or 2");
+  if (size_t(k) * sizeof(double) > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "nshot_score: k too large");
+  if (query == nullptr || support == nullptr || best == nullptr) return set_error(VM_ERR_SHAPE, "nshot_score: null pointer");
+  nshot_score_kernel<<<T, 128, k * sizeof(double), stream>>>(query, support, T, k, n, E, distance, scores, best);
+  return check_launch("nshot_score");
 }
 
 }  // namespace vm

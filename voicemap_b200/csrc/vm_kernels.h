@@ -38,12 +38,16 @@ struct Conv1Params {
   const float4* epi;     // [cout_pad] {sigma, bias, s, t}
   __half* out_hi;        // (N, lout, cout)
   __half* out_lo;
-  float* out_f32;        // (N, L, cout) un-pooled fp32 output (train-mode forward), or null
+  // train-mode forward (out_u16 != null): encoded un-pooled activations (N, L, cout) (encode_u, vm_common.cuh) and
+  // the fp32 extreme of every pool window (N, lout, cout); sign_src[cout] < 0 selects the minimum, null = maxima
+  uint16_t* out_u16;
+  float* out_ext;
+  const float* sign_src;
   float2* stat_partial;  // (N*nptile*2, cout_pad) {sum, sum of squares} over valid positions, or null
 };
 int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, const float* epi, __half* out_hi,
-                 __half* out_lo, float* out_f32, float* stat_partial, int products, int max_ctas,
-                 cudaStream_t stream, int x_stride = 1, long long x_clip_stride = 0,
+                 __half* out_lo, uint16_t* out_u16, float* out_ext, const float* sign_src, float* stat_partial,
+                 int products, int max_ctas, cudaStream_t stream, int x_stride = 1, long long x_clip_stride = 0,
                  const float* pre_mean = nullptr, const float* pre_scale = nullptr, int pool = 4);
 int launch_preprocess_stats(const float* x, int N, int T, int stride, int G, float rms, float* mean, float* scale,
                             cudaStream_t stream);
@@ -63,12 +67,26 @@ struct Conv3Params {
   float* out_f32;        // (N, L, cout) un-pooled fp32 output (train-mode forward / dgrad), or null
   float2* stat_partial;  // (N, 2*nptile, cout_pad) {sum, sum of squares} of out_f32 over valid positions, or null
   int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
-  int in_bf16;           // input AND weight planes are bf16 (dgrad) instead of fp16 (kind::f16 cannot mix the two)
+  int x_single;          // products 3 with a single input plane: Xh*Wh + Xh*Wl (dgrad of a one-plane gradient)
   int slabs_per_unit;    // tile schedule: 1, or nslab when the X tile stays in shared memory for all cout slabs
+  // train-mode forward (out_u16 != null): encoded un-pooled activations (N, L, cout) (encode_u) + fp32 window
+  // extremes (N, lout, cout); sign_src[cout] < 0 selects the minimum (negative BatchNorm scale), null = all maxima
+  uint16_t* out_u16;
+  float* out_ext;
+  const float* sign_src;
+  const uint32_t* grad_absmax;  // dgrad: bits of the largest |s * dy| of the block -> power-of-two unscale, or null
+};
+struct Conv3Extra {            // optional arguments of launch_conv3 beyond the eval-forward set
+  uint16_t* out_u16 = nullptr;
+  float* out_ext = nullptr;
+  const float* sign_src = nullptr;
+  const uint32_t* grad_absmax = nullptr;
+  int x_single = 0;
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
-                 float* stat_partial, int linear, int in_bf16, int products, int max_ctas, cudaStream_t stream);
+                 float* stat_partial, int linear, int products, int max_ctas, cudaStream_t stream,
+                 const Conv3Extra& extra = Conv3Extra());
 
 // ---- weight gradients (vm_wgrad.cu) ----
 struct Wgrad3Params {
@@ -80,9 +98,10 @@ struct Wgrad3Params {
 };
 int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, const __half* du_lo, int N, int L,
                   int cin, int cout, int products, float* partial, size_t partial_bytes, float* dw,
-                  cudaStream_t stream);
+                  const unsigned int* grad_absmax, cudaStream_t stream);
 int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
-                  size_t partial_bytes, float* dw, cudaStream_t stream, int products = 3);
+                  size_t partial_bytes, float* dw, const unsigned int* grad_absmax, cudaStream_t stream,
+                  int products = 3);
 int launch_wgrad1_tc(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, int products,
                      float* partial, size_t partial_bytes, int* nsplit_out, cudaStream_t stream);
 
@@ -90,35 +109,35 @@ int launch_wgrad1_tc(const float* x, const __half* du_hi, const __half* du_lo, i
 int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad, int N, int G, int L, int C,
                              const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
                              float* moving_var, float* bn_const, double* red_scratch, cudaStream_t st);
-int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
-                       const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
-                       cudaStream_t st);
-int launch_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask,
-                       float* gmax, int* argmax, cudaStream_t st);
+int launch_bn_pool_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
+                       __half* out_hi, __half* out_lo, uint16_t* out_q, cudaStream_t st);
+int launch_bn_gmax_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
+                       float* gmax, int* jstar, cudaStream_t st);
 int launch_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, cudaStream_t st);
 int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db,
                      float* dx, cudaStream_t st);
 int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                               const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
                               float* d_head_b, cudaStream_t st);
-int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
-                  int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
-                  float* bwd_const, float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
-                  float* dbias, double* red_scratch, cudaStream_t st);
+size_t bn_bwd_scratch_elems(int N);
+int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
+                  int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
+                  float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax, __half* du_hi, __half* du_lo,
+                  float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st);
 // split forms for synchronised BatchNorm (sums -> caller's all-reduce -> constants)
 int launch_bn_stats_sums(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C, double* red_scratch,
                          double* sums, cudaStream_t st);
 int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, const float* gamma, const float* beta,
                               float eps, float momentum, float* moving_mean, float* moving_var, float* bn_const,
                               cudaStream_t st);
-int launch_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
-                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
-                       double* red_scratch, double* sums, cudaStream_t st);
-int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
-                            const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C, int G,
-                            int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
-                            float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
-                            float* dbias, double* red_scratch, cudaStream_t st);
+int launch_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L,
+                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
+                       unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st);
+int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
+                            const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L, int C, int G,
+                            int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
+                            float* dbeta, const unsigned int* absmax, __half* du_hi, __half* du_lo,
+                            float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st);
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
                      float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
 int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);
@@ -137,5 +156,7 @@ int launch_gmax_dense(const float* partial, int N, int T, int C, int c_pad, cons
 int launch_pair_head_loss(const float* e1, const float* e2, int N, int E, int metric, const float* head_w,
                           const float* head_b, const float* y_true, int loss_kind, float* dist, float* prob,
                           float* loss, cudaStream_t stream);
+int launch_nshot_score(const float* query, const float* support, int T, int k, int n, int E, int distance,
+                       float* scores, int* best, cudaStream_t stream);
 
 }  // namespace vm

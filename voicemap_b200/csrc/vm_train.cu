@@ -1,13 +1,23 @@
 // Training-mode kernels around the tensor-core convolutions (CUDA cores; all HBM-bound elementwise / reduction work).
 //
-// Forward (train):  conv (RAW mode: u = relu(acc + bias), fp32, un-pooled, + {sum, sumsq} partials)
-//                   -> bn_stats_finalize (batch moments per BN group, Keras moving-average update)
-//                   -> bn_pool_fwd (y = s*u + t, SpatialDropout mask, MaxPool -> fp16 (hi, lo) planes)
-//                      / bn_gmax_fwd for block 4 (MaxPool(2) + GlobalMaxPool1D merged, with argmax)
+// What a block keeps from its forward pass (written by the conv kernels' train-mode epilogues, vm_conv1/3.cu):
+//   u16 (N, L, C)      the un-pooled activation u = relu(conv + bias) as fp16 + an arg-max flag in the sign bit
+//                      (encode_u, vm_common.cuh) -- 2 bytes per element, the only full-resolution tensor of the block;
+//   ext (N, L/p, C)    the fp32 extreme of u in every MaxPool window: the maximum, or the minimum where the BatchNorm
+//                      scale is negative (sign(gamma) is known before the batch statistics are).  BatchNorm is
+//                      monotone per channel, so the pooled output is s * ext + t exactly as if the affine had been
+//                      applied before the pool (voicemap/models.py:17-19);
+//   {sum, sumsq}       per-channel partials of u for the batch statistics.
+// Forward (train):  conv -> bn_stats_finalize (batch moments per BN group, Keras moving-average update)
+//                   -> bn_pool_fwd (y = s*ext + t, SpatialDropout mask -> fp16 planes (hi, lo | Q) of the next conv)
+//                      / bn_gmax_fwd for block 4 (GlobalMaxPool1D over the windows, with the winning window)
 //                   -> dense_fwd -> pair head + loss (vm_head.cu)
 // Backward:         pair_head_loss_bwd -> dense_bwd -> per block (4..1):
-//                   bn_bwd_reduce (sum dy, sum dy*xhat) -> bn_bwd_finalize (+ dgamma, dbeta)
-//                   -> bn_relu_bwd (dU as fp16 planes, + conv-bias gradient partials)
+//                   bn_bwd_reduce (sum dy, sum dy*xhat: dy is non-zero at the window arg-max only, where u == ext, so
+//                   this pass reads pooled tensors only; also the largest |s*dy| -> gradient scale)
+//                   -> bn_bwd_finalize (+ dgamma, dbeta)
+//                   -> bn_relu_bwd (u16 + dy -> dU = relu'(u) * s * (dy - mean_dy - xhat*mean_dyxhat) as scaled fp16
+//                      planes, + conv-bias gradient partials)
 //                   -> wgrad (vm_wgrad.cu) and dgrad (conv3_kernel on flipped/transposed weights).
 // Reference semantics: keras BatchNormalization / SpatialDropout1D / MaxPool1D / GlobalMaxPool1D / Dense in training
 // mode as used by voicemap/models.py:6-81; losses voicemap/utils.py:77-85 and keras binary_crossentropy.
@@ -160,97 +170,104 @@ __global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// BN affine (+ dropout mask) + MaxPool -> (hi, lo) planes.  One thread = 4 channels of one pooled position.
+// Thread layout of the elementwise passes: grid (clip, position chunk); inside a block of 256 threads, thread
+// (channel group cg, stream) owns kPer adjacent channels for the whole launch -- its BatchNorm constants live in
+// registers -- and walks the positions stream, stream + streams, ... of the chunk.
 // ---------------------------------------------------------------------------------------------
+constexpr int kEwThreads = 256;
+__host__ __device__ constexpr int ew_streams(int C, int per) { return (kEwThreads / (C / per)) > 0 ? kEwThreads / (C / per) : 1; }
+static int ew_chunks(int N, int items, int streams) {
+  // ~8 blocks per SM, but no more chunks than there are stream passes to hand out
+  int chunks = (kNumSMs * 8 + N - 1) / N;
+  const int most = (items + streams - 1) / streams;
+  if (chunks > most) chunks = most;
+  return chunks < 1 ? 1 : chunks;
+}
 __device__ __forceinline__ float f4get(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
-__global__ void bn_pool_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G, int pool,
-                                   const float4* __restrict__ bn_const, const float* __restrict__ mask,
-                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                   uint16_t* __restrict__ bf_hi, uint16_t* __restrict__ bf_lo) {
-  const int lout = L / pool;
-  const int c4n = C >> 2;
-  const size_t total = size_t(N) * lout * c4n;
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  // One item = one pooled output of 4 adjacent channels (pool <= 4 rows of 16 bytes).  Two items per iteration: the rows
-  // of both are loaded before either is reduced (with pool = 2 one item keeps only 32 bytes per thread in flight).
-  struct Item {
-    float4 x[4];
-    int c4, j, n;
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
+}
+
+// BN affine (+ dropout mask) on the window extremes -> planes of the next conv: fp16 hi always, the fp16 residual
+// plane (kLo: forward precision 3, and the weight gradient's second activation plane) and / or the e5m2x2 Q plane
+// (kQ: forward precision 2).
+template <bool kLo, bool kQ>
+__global__ void __launch_bounds__(kEwThreads)
+bn_pool_fwd_kernel(const float* __restrict__ ext, int N, int lout, int C, int G, const float4* __restrict__ bn_const,
+                   const float* __restrict__ mask, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                   uint16_t* __restrict__ out_q) {
+  const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+  const int groups = C >> 3, streams = ew_streams(C, 8);
+  if (int(threadIdx.x) >= groups * streams) return;
+  const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 8 * cg;
+  const int g = n / (N / G);
+  float sv[8], tv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 bc = bn_const[size_t(g) * C + c + k];
+    const float mk = mask ? mask[size_t(n) * C + c + k] : 1.f;
+    sv[k] = bc.x * mk;
+    tv[k] = bc.y * mk;
+  }
+  const int per = (lout + chunks - 1) / chunks;
+  const int j0 = chunk * per, j1 = min(lout, j0 + per);
+  auto finish = [&](int j, const float4& a, const float4& b) {
+    __half h[8], l[8];
+    uint16_t q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float y = fmaf(sv[k], k < 4 ? f4get(a, k) : f4get(b, k - 4), tv[k]);
+      split_f32(y, h[k], l[k]);
+      if (kQ) split_f16_q(y, h[k], q[k]);   // same hi
+    }
+    const size_t o = (size_t(n) * lout + j) * C + c;
+    *reinterpret_cast<uint4*>(out_hi + o) =
+        make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+    if (kLo)
+      *reinterpret_cast<uint4*>(out_lo + o) =
+          make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+    if (kQ)
+      *reinterpret_cast<uint4*>(out_q + o) =
+          make_uint4(uint32_t(q[0]) | (uint32_t(q[1]) << 16), uint32_t(q[2]) | (uint32_t(q[3]) << 16),
+                     uint32_t(q[4]) | (uint32_t(q[5]) << 16), uint32_t(q[6]) | (uint32_t(q[7]) << 16));
   };
-  auto load_item = [&](size_t idx, Item& it) {
-    it.c4 = int(idx % c4n);
-    const size_t nj = idx / c4n;
-    it.j = int(nj % lout);
-    it.n = int(nj / lout);
-    const float* up = u + (size_t(it.n) * L + size_t(it.j) * pool) * C + 4 * it.c4;
+  // four positions in flight per thread (32 bytes each)
+  for (int j = j0 + stream; j < j1; j += 4 * streams) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int jj = j + i * streams;
+      if (jj < j1) {
+        const float4* src = reinterpret_cast<const float4*>(ext + (size_t(n) * lout + jj) * C + c);
+        a[i] = __ldcs(src);
+        b[i] = __ldcs(src + 1);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      it.x[i] = (i < pool) ? *reinterpret_cast<const float4*>(up + size_t(i) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  auto finish_item = [&](const Item& it) {
-    const int g = it.n / (N / G);
-    float best[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 bc = bn_const[size_t(g) * C + 4 * it.c4 + k];
-      const float mk = mask ? mask[size_t(it.n) * C + 4 * it.c4 + k] : 1.f;
-      const float sv = bc.x * mk, tv = bc.y * mk;
-      float m = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < pool) m = fmaxf(m, fmaf(sv, f4get(it.x[i], k), tv));
-      best[k] = m;
-    }
-    __half h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) split_f32(best[k], h[k], l[k]);
-    const size_t o = (size_t(it.n) * lout + it.j) * C + 4 * it.c4;
-    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(
-        uint32_t(__half_as_ushort(h[0])) | (uint32_t(__half_as_ushort(h[1])) << 16),
-        uint32_t(__half_as_ushort(h[2])) | (uint32_t(__half_as_ushort(h[3])) << 16));
-    *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(
-        uint32_t(__half_as_ushort(l[0])) | (uint32_t(__half_as_ushort(l[1])) << 16),
-        uint32_t(__half_as_ushort(l[2])) | (uint32_t(__half_as_ushort(l[3])) << 16));
-    if (bf_hi != nullptr) {  // bf16 copy of the same activations: the wgrad MMA needs X in dU's format
-      uint16_t bh[4], bl[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) split_bf16(best[k], bh[k], bl[k]);
-      *reinterpret_cast<uint2*>(bf_hi + o) = make_uint2(uint32_t(bh[0]) | (uint32_t(bh[1]) << 16),
-                                                        uint32_t(bh[2]) | (uint32_t(bh[3]) << 16));
-      *reinterpret_cast<uint2*>(bf_lo + o) = make_uint2(uint32_t(bl[0]) | (uint32_t(bl[1]) << 16),
-                                                        uint32_t(bl[2]) | (uint32_t(bl[3]) << 16));
-    }
-  };
-  for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += 2 * stride) {
-    Item a, b;
-    const bool two = (idx + stride < total);
-    load_item(idx, a);
-    if (two) load_item(idx + stride, b);
-    finish_item(a);
-    if (two) finish_item(b);
+      if (j + i * streams < j1) finish(j + i * streams, a[i], b[i]);
   }
 }
 
-// Block 4: BN affine (+ mask) -> MaxPool(2,'valid') -> GlobalMaxPool1D == max over positions l < 2*floor(L/2).
-// grid (N, ceil(C/32)); block (32 channels, 8 position lanes).  Writes the max and the un-pooled argmax position.
-__global__ void bn_gmax_fwd_kernel(const float* __restrict__ u, int N, int L, int C, int G,
+// Block 4: BN affine (+ mask) on the MaxPool(2) window extremes -> GlobalMaxPool1D over the windows.
+// grid (N, ceil(C/32)); block (32 channels, 8 window lanes).  Writes the max and the winning window (first on ties).
+__global__ void bn_gmax_fwd_kernel(const float* __restrict__ ext, int N, int lout, int C, int G,
                                    const float4* __restrict__ bn_const, const float* __restrict__ mask,
-                                   float* __restrict__ gmax, int* __restrict__ argmax) {
+                                   float* __restrict__ gmax, int* __restrict__ jstar) {
   __shared__ float smax[8][32];
   __shared__ int sidx[8][32];
   const int n = blockIdx.x;
   const int c = blockIdx.y * 32 + threadIdx.x;
   const int g = n / (N / G);
-  const int lvalid = (L / 2) * 2;
   float best = -INFINITY;
   int bi = 0;
   if (c < C) {
     const float4 bc = bn_const[size_t(g) * C + c];
     const float mk = mask ? mask[size_t(n) * C + c] : 1.f;
     const float s = bc.x * mk, t = bc.y * mk;
-    for (int l = threadIdx.y; l < lvalid; l += 8) {
-      const float y = fmaf(s, u[(size_t(n) * L + l) * C + c], t);
-      if (y > best) { best = y; bi = l; }
+    for (int j = threadIdx.y; j < lout; j += 8) {
+      const float y = fmaf(s, ext[(size_t(n) * lout + j) * C + c], t);
+      if (y > best) { best = y; bi = j; }
     }
   }
   smax[threadIdx.y][threadIdx.x] = best;
@@ -263,7 +280,7 @@ __global__ void bn_gmax_fwd_kernel(const float* __restrict__ u, int N, int L, in
       if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
     gmax[size_t(n) * C + c] = best;
-    argmax[size_t(n) * C + c] = bi;
+    jstar[size_t(n) * C + c] = bi;
   }
 }
 
@@ -411,99 +428,76 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// BN backward, pass 1: per-channel sums of dy and dy * xhat over the batch.
-//   dense  (dy_pooled != null): gradient arrives on the pooled tensor (N, L/pool, C) and is routed to the
-//                               arg-max of each window (recomputed from u);
-//   sparse (dy_pooled == null): block 4, gradient d_gmax (N, C) sits at position argmax[n][c].
-// grid (N, chunks), block = 128 threads over channels; partial rows [(n*chunks + chunk)][C] float2.
+// BN backward, pass 1: per-channel sums of dy and dy * xhat over the batch, and the largest |s * dy|.
+// The gradient of a pooled output lands on the window's arg-max, where u equals the stored extreme, so
+//   sum dy        = sum over windows of dy,      sum dy * xhat = sum over windows of dy * (ext - mean) * rstd
+// and this pass reads the two POOLED tensors only.
+//   dense  (dy_pooled != null): gradient on the pooled tensor (N, lout, C);
+//   sparse (dy_pooled == null): block 4, gradient d_gmax (N, C) sits in window jstar[n][c].
+// grid (N, chunks); thread = 4 adjacent channels; partial rows [((n*chunks + chunk)*streams + stream)][C] float2.
 // ---------------------------------------------------------------------------------------------
-// Thread layout of the two big elementwise passes: one thread owns 4 adjacent channels (float4 loads, 8-byte plane
-// stores); a block of 128 threads covers C/4 channel groups x (512/C) interleaved position streams.
-
-// arg-max of s*u + t over a pool window == arg-max of u (s >= 0) or arg-min of u (s < 0); first winner on ties
-__device__ __forceinline__ void window_argmax4(const float* __restrict__ up, int C, int pool, const float (&s)[4],
-                                               int (&bi)[4], float (&bu)[4]) {
-  const float4 v0 = *reinterpret_cast<const float4*>(up);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { bi[k] = 0; bu[k] = f4get(v0, k); }
-  for (int i = 1; i < pool; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(up + size_t(i) * C);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float x = f4get(v, k);
-      if ((s[k] >= 0.f) ? (x > bu[k]) : (x < bu[k])) { bu[k] = x; bi[k] = i; }
-    }
-  }
-}
-
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
-                                     const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
-                                     int C, int G, int pool, const float4* __restrict__ bn_const,
-                                     const float* __restrict__ mask, float2* __restrict__ partial) {
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_kernel(const float* __restrict__ ext, const float* __restrict__ dy_pooled,
+                     const float* __restrict__ d_gmax, const int* __restrict__ jstar, int N, int lout, int C, int G,
+                     const float4* __restrict__ bn_const, const float* __restrict__ mask,
+                     float2* __restrict__ partial, unsigned int* __restrict__ absmax) {
   const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
-  const int g = n / (N / G);
-  const int groups = C >> 2;
-  const int nstream = max(1, int(blockDim.x) / groups);
-  for (int item = threadIdx.x; item < groups * nstream; item += blockDim.x) {
-    const int cg = item % groups, stream = item / groups;
-    const int c = 4 * cg;
-    float sc[4], mean[4], rstd[4], mk[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const int groups = C >> 2, streams = ew_streams(C, 4);
+  float amax = 0.f;
+  if (int(threadIdx.x) < groups * streams) {
+    const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 4 * cg;
+    const int g = n / (N / G);
+    float sabs[4], mean[4], rstd[4], mk[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 bc = bn_const[size_t(g) * C + c + k];
       mk[k] = mask ? mask[size_t(n) * C + c + k] : 1.f;
-      sc[k] = bc.x * mk[k]; mean[k] = bc.z; rstd[k] = bc.w;
+      sabs[k] = fabsf(bc.x); mean[k] = bc.z; rstd[k] = bc.w;
     }
     if (dy_pooled != nullptr) {
-      const int lout = L / pool;
       const int per = (lout + chunks - 1) / chunks;
       const int j0 = chunk * per, j1 = min(lout, j0 + per);
-      // two windows in flight per thread (see bn_relu_bwd_kernel); sums are still taken in window order
-      struct Window {
-        float4 ur[4], dv;
-      };
-      auto load_window = [&](int j, Window& W) {
-        const float* up = u + (size_t(n) * L + size_t(j) * pool) * C + c;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          W.ur[i] = (i < pool) ? *reinterpret_cast<const float4*>(up + size_t(i) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-        W.dv = *reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + j) * C + c);
-      };
-      auto add_window = [&](const Window& W) {
+      auto add = [&](const float4& e, const float4& d) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float bu = f4get(W.ur[0], k);   // arg-max of s*u + t == arg-max (s >= 0) / arg-min (s < 0) of u, first on ties
-#pragma unroll
-          for (int i = 1; i < 4; ++i) {
-            const float x = f4get(W.ur[i], k);
-            if (i < pool && ((sc[k] >= 0.f) ? (x > bu) : (x < bu))) bu = x;
-          }
-          const float dy = f4get(W.dv, k) * mk[k];
+          const float dy = f4get(d, k) * mk[k];
           s1[k] += dy;
-          s2[k] = fmaf(dy, (bu - mean[k]) * rstd[k], s2[k]);
+          s2[k] = fmaf(dy, (f4get(e, k) - mean[k]) * rstd[k], s2[k]);
+          amax = fmaxf(amax, fabsf(dy) * sabs[k]);
         }
       };
-      for (int j = j0 + stream; j < j1; j += 2 * nstream) {
-        Window A, B;
-        const bool two = (j + nstream < j1);
-        load_window(j, A);
-        if (two) load_window(j + nstream, B);
-        add_window(A);
-        if (two) add_window(B);
+      // four windows in flight per thread; the sums are still taken in window order
+      for (int j = j0 + stream; j < j1; j += 4 * streams) {
+        float4 e[4], d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int jj = j + i * streams;
+          if (jj < j1) {
+            const size_t o = (size_t(n) * lout + jj) * C + c;
+            e[i] = *reinterpret_cast<const float4*>(ext + o);
+            d[i] = __ldcs(reinterpret_cast<const float4*>(dy_pooled + o));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (j + i * streams < j1) add(e[i], d[i]);
       }
     } else if (chunk == 0 && stream == 0) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int l = argmax[size_t(n) * C + c + k];
+        const int j = jstar[size_t(n) * C + c + k];
         const float dy = d_gmax[size_t(n) * C + c + k] * mk[k];
         s1[k] = dy;
-        s2[k] = dy * (u[(size_t(n) * L + l) * C + c + k] - mean[k]) * rstd[k];
+        s2[k] = dy * (ext[(size_t(n) * lout + j) * C + c + k] - mean[k]) * rstd[k];
+        amax = fmaxf(amax, fabsf(dy) * sabs[k]);
       }
     }
-    float2* row = partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;
+    float2* row = partial + ((size_t(n) * chunks + chunk) * streams + stream) * C + c;
 #pragma unroll
     for (int k = 0; k < 4; ++k) row[k] = make_float2(s1[k], s2[k]);
   }
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(absmax, __float_as_uint(amax));
 }
 
 // pass 2: per (group, channel) means -> bwd constants {s, mean_dy, mean_dyxhat, 0}; dgamma/dbeta summed over groups.
@@ -526,109 +520,109 @@ __global__ void bn_bwd_finalize_kernel(const double2* __restrict__ tmp, int N, i
   dbeta[c] = float(tb);
 }
 
-// pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) as bf16 (hi, lo) planes; conv-bias gradient
-// partials sum_positions dU per channel.  grid (N, chunks) over pool windows (incl. the 'valid' tail window, which
-// receives no dy but still the batch-statistics terms).
-__device__ __forceinline__ uint2 pack4u(const uint16_t (&h)[4]) {
-  return make_uint2(uint32_t(h[0]) | (uint32_t(h[1]) << 16), uint32_t(h[2]) | (uint32_t(h[3]) << 16));
-}
-__global__ void __launch_bounds__(128, 5)
-bn_relu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy_pooled,
-                                   const float* __restrict__ d_gmax, const int* __restrict__ argmax, int N, int L,
-                                   int C, int G, int pool, const float4* __restrict__ bn_const,
-                                   const float4* __restrict__ bwd_const, const float* __restrict__ mask,
-                                   __half* __restrict__ du_hi, __half* __restrict__ du_lo,
-                                   float* __restrict__ dbias_partial) {
+// pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) at every un-pooled position (incl. the 'valid'
+// tail, which receives no dy but still the batch-statistics terms), written as fp16 planes scaled by the block's
+// power-of-two gradient scale (hi, and lo = fp16(residual) when kPlanes == 2); conv-bias gradient partials
+// sum_positions dU per channel (un-scaled).  Per channel the expression is affine in u and dy:
+//   dU = A*dy + B + Cc*u,  A = s*mk,  B = s*(mean*rstd*mean_dyxhat - mean_dy),  Cc = -s*rstd*mean_dyxhat
+// with u and the arg-max flag decoded from the 16-bit activation word.  grid (N, chunks) over pool windows.
+template <bool kSparse, int kPlanes>
+__global__ void __launch_bounds__(kEwThreads)
+bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ dy_pooled,
+                   const float* __restrict__ d_gmax, const int* __restrict__ jstar, int N, int L, int C, int G,
+                   int pool, const float4* __restrict__ bn_const, const float4* __restrict__ bwd_const,
+                   const float* __restrict__ mask, const unsigned int* __restrict__ absmax,
+                   __half* __restrict__ du_hi, __half* __restrict__ du_lo, float* __restrict__ dbias_partial) {
   const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+  const int groups = C >> 3, streams = ew_streams(C, 8);
+  if (int(threadIdx.x) >= groups * streams) return;
+  const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 8 * cg;
   const int g = n / (N / G);
   const int lout = L / pool;
   const int wins = (L + pool - 1) / pool;
   const int per = (wins + chunks - 1) / chunks;
   const int w0 = chunk * per, w1 = min(wins, w0 + per);
-  const int groups = C >> 2;
-  const int nstream = max(1, int(blockDim.x) / groups);
-  for (int item = threadIdx.x; item < groups * nstream; item += blockDim.x) {
-    const int cg = item % groups, stream = item / groups;
-    const int c = 4 * cg;
-    float sc[4], mean[4], rstd[4], mk[4], bs[4], mdy[4], mdx[4], dg[4], sb[4] = {0, 0, 0, 0};
-    int am[4];
+  const float scale = grad_scale_from_absmax(__uint_as_float(*absmax));
+  float A[8], B[8], Cc[8], sb[8];
+  int js[kSparse ? 8 : 1];
+  float dg[kSparse ? 8 : 1];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 bc = bn_const[size_t(g) * C + c + k];
-      const float4 bw = bwd_const[size_t(g) * C + c + k];
-      mk[k] = mask ? mask[size_t(n) * C + c + k] : 1.f;
-      sc[k] = bc.x * mk[k]; mean[k] = bc.z; rstd[k] = bc.w;
-      bs[k] = bw.x; mdy[k] = bw.y; mdx[k] = bw.z;
-      am[k] = (dy_pooled == nullptr) ? argmax[size_t(n) * C + c + k] : -1;
-      dg[k] = (dy_pooled == nullptr) ? d_gmax[size_t(n) * C + c + k] * mk[k] : 0.f;
+  for (int k = 0; k < 8; ++k) {
+    const float4 bc = bn_const[size_t(g) * C + c + k];
+    const float4 bw = bwd_const[size_t(g) * C + c + k];
+    const float mk = mask ? mask[size_t(n) * C + c + k] : 1.f;
+    A[k] = bw.x * mk * scale;
+    B[k] = bw.x * (bc.z * bc.w * bw.z - bw.y) * scale;
+    Cc[k] = -bw.x * bc.w * bw.z * scale;
+    sb[k] = 0.f;
+    if (kSparse) {
+      js[k] = jstar[size_t(n) * C + c + k];
+      dg[k] = d_gmax[size_t(n) * C + c + k];
     }
-    // Two windows per iteration: all global loads of both are issued before the first one is processed.  With
-    // pool = 2 (blocks 2-4) a window is only 2 x 16 bytes per thread, and one window at a time left the kernel at
-    // 2.7 - 3.0 TB/s (block 1, pool = 4: 4.6 TB/s).  The windows are still applied in order, so dbias sums are unchanged.
-    struct Window {
-      float4 ur[4];   // the window's rows (pool <= 4)
-      float4 dv;      // its pooled gradient
-      int l0, wl;
-      bool has_dy;
-    };
-    auto load_window = [&](int w, Window& W) {
-      W.l0 = w * pool;
-      W.wl = min(pool, L - W.l0);
-      const float* up = u + (size_t(n) * L + W.l0) * C + c;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        W.ur[i] = (i < W.wl) ? __ldcs(reinterpret_cast<const float4*>(up + size_t(i) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      W.has_dy = (dy_pooled != nullptr && w < lout);
-      W.dv = W.has_dy ? __ldcs(reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    auto apply_window = [&](const Window& W) {
-      int bi[4] = {-1, -1, -1, -1};
-      float dyw[4] = {0, 0, 0, 0};
-      if (W.has_dy) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float bu = f4get(W.ur[0], k);
-          bi[k] = 0;
-#pragma unroll
-          for (int i = 1; i < 4; ++i) {
-            const float x = f4get(W.ur[i], k);
-            if (i < pool && ((sc[k] >= 0.f) ? (x > bu) : (x < bu))) { bu = x; bi[k] = i; }
-          }
-          dyw[k] = f4get(W.dv, k) * mk[k];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < W.wl) {
-          uint16_t h[4], lw[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float uv = f4get(W.ur[i], k);
-            const float dy = (dy_pooled != nullptr) ? ((i == bi[k]) ? dyw[k] : 0.f) : ((W.l0 + i == am[k]) ? dg[k] : 0.f);
-            const float xhat = (uv - mean[k]) * rstd[k];
-            const float du = (uv > 0.f) ? bs[k] * (dy - mdy[k] - xhat * mdx[k]) : 0.f;
-            sb[k] += du;
-            split_bf16(du, h[k], lw[k]);
-          }
-          const size_t o = (size_t(n) * L + W.l0 + i) * C + c;
-          __stcs(reinterpret_cast<uint2*>(du_hi + o), pack4u(h));
-          if (du_lo != nullptr) __stcs(reinterpret_cast<uint2*>(du_lo + o), pack4u(lw));
-        }
-      }
-    };
-    for (int w = w0 + stream; w < w1; w += 2 * nstream) {
-      Window A, B;
-      const bool two = (w + nstream < w1);
-      load_window(w, A);
-      if (two) load_window(w + nstream, B);
-      apply_window(A);
-      if (two) apply_window(B);
-    }
-    float* row = dbias_partial + ((size_t(n) * chunks + chunk) * nstream + stream) * C + c;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) row[k] = sb[k];
   }
+  struct Window {
+    uint4 ur[4];    // the window's rows of 8 encoded activations (pool <= 4)
+    float4 d0, d1;  // its pooled gradient
+  };
+  auto load_window = [&](int w, Window& W) {
+    const int l0 = w * pool, wl = min(pool, L - l0);
+    const uint16_t* up = u16 + (size_t(n) * L + l0) * C + c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      W.ur[i] = (i < wl) ? __ldcs(reinterpret_cast<const uint4*>(up + size_t(i) * C)) : make_uint4(0u, 0u, 0u, 0u);
+    if (!kSparse && w < lout) {
+      const float4* dp = reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c);
+      W.d0 = __ldcs(dp);
+      W.d1 = __ldcs(dp + 1);
+    } else {
+      W.d0 = W.d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto apply_window = [&](int w, const Window& W) {
+    const int l0 = w * pool, wl = min(pool, L - l0);
+    float add[8];   // A * dy of this window: what the flagged element receives on top of the statistics terms
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float dy = kSparse ? ((w == js[k]) ? dg[k] : 0.f) : (k < 4 ? f4get(W.d0, k) : f4get(W.d1, k - 4));
+      add[k] = A[k] * dy;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < wl) {
+        const uint32_t wd[4] = {W.ur[i].x, W.ur[i].y, W.ur[i].z, W.ur[i].w};
+        __half h[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t bits = (wd[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+          const float u = decode_u(bits);
+          float du = fmaf(Cc[k], u, (bits & 0x8000u) ? B[k] + add[k] : B[k]);
+          if ((bits & 0x7FFFu) == 0u) du = 0.f;      // relu'(u)
+          sb[k] += du;
+          h[k] = __float2half_rn(du);
+          if (kPlanes == 2) lo[k] = __float2half_rn(du - __half2float(h[k]));
+        }
+        const size_t o = (size_t(n) * L + l0 + i) * C + c;
+        __stcs(reinterpret_cast<uint4*>(du_hi + o),
+               make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
+        if (kPlanes == 2)
+          __stcs(reinterpret_cast<uint4*>(du_lo + o),
+                 make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7])));
+      }
+    }
+  };
+  // two windows in flight per thread
+  for (int w = w0 + stream; w < w1; w += 2 * streams) {
+    Window Wa, Wb;
+    const bool two = (w + streams < w1);
+    load_window(w, Wa);
+    if (two) load_window(w + streams, Wb);
+    apply_window(w, Wa);
+    if (two) apply_window(w + streams, Wb);
+  }
+  const float inv = 1.0f / scale;
+  float* row = dbias_partial + ((size_t(n) * chunks + chunk) * streams + stream) * C + c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) row[k] = sb[k] * inv;
 }
 
 // second stage of a plain column sum -> out[C]
@@ -712,23 +706,27 @@ int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, co
   return check_launch_t("bn_stats_from_sums");
 }
 
-int launch_bn_pool_fwd(const float* u, int N, int L, int C, int G, int pool, const float* bn_const,
-                       const float* mask, __half* out_hi, __half* out_lo, uint16_t* bf_hi, uint16_t* bf_lo,
-                       cudaStream_t st) {
-  if (C % 4 != 0 || N % G != 0 || pool <= 0 || L / pool <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
-  const size_t total = size_t(N) * (L / pool) * (C / 4);
-  const unsigned blocks = unsigned(min(size_t(148 * 32), (total + 255) / 256));
-  bn_pool_fwd_kernel<<<blocks, 256, 0, st>>>(u, N, L, C, G, pool, reinterpret_cast<const float4*>(bn_const), mask,
-                                            out_hi, out_lo, bf_hi, bf_lo);
+int launch_bn_pool_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
+                       __half* out_hi, __half* out_lo, uint16_t* out_q, cudaStream_t st) {
+  if (C % 8 != 0 || N <= 0 || G <= 0 || N % G != 0 || lout <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
+  const dim3 grid(N, ew_chunks(N, lout, ew_streams(C, 8)));
+  const float4* bc = reinterpret_cast<const float4*>(bn_const);
+#define VM_POOL_FWD(LO, Q) \
+  bn_pool_fwd_kernel<LO, Q><<<grid, kEwThreads, 0, st>>>(ext, N, lout, C, G, bc, mask, out_hi, out_lo, out_q)
+  if (out_lo != nullptr && out_q != nullptr) VM_POOL_FWD(true, true);
+  else if (out_lo != nullptr) VM_POOL_FWD(true, false);
+  else if (out_q != nullptr) VM_POOL_FWD(false, true);
+  else VM_POOL_FWD(false, false);
+#undef VM_POOL_FWD
   return check_launch_t("bn_pool_fwd");
 }
 
-int launch_bn_gmax_fwd(const float* u, int N, int L, int C, int G, const float* bn_const, const float* mask,
-                       float* gmax, int* argmax, cudaStream_t st) {
-  if (N % G != 0 || L < 2) return set_error(VM_ERR_SHAPE, "bn_gmax_fwd: bad shape");
-  bn_gmax_fwd_kernel<<<dim3(N, (C + 31) / 32), dim3(32, 8), 0, st>>>(u, N, L, C, G,
+int launch_bn_gmax_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
+                       float* gmax, int* jstar, cudaStream_t st) {
+  if (N <= 0 || G <= 0 || N % G != 0 || lout < 1) return set_error(VM_ERR_SHAPE, "bn_gmax_fwd: bad shape");
+  bn_gmax_fwd_kernel<<<dim3(N, (C + 31) / 32), dim3(32, 8), 0, st>>>(ext, N, lout, C, G,
                                                                     reinterpret_cast<const float4*>(bn_const), mask,
-                                                                    gmax, argmax);
+                                                                    gmax, jstar);
   return check_launch_t("bn_gmax_fwd");
 }
 
@@ -756,80 +754,97 @@ int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const 
   return check_launch_t("pair_head_loss_bwd");
 }
 
-static int bn_bwd_check(const double* red_scratch, int N, int G, int C, int chunks, const void* dy_pooled,
-                        const void* d_gmax) {
+static int bn_bwd_check(const double* red_scratch, int N, int G, int C, const void* dy_pooled, const void* d_gmax,
+                        const void* absmax) {
   if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd: reduction scratch missing");
-  if (N % G != 0 || chunks <= 0) return set_error(VM_ERR_SHAPE, "bn_bwd: bad shape");
+  if (absmax == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd: gradient-scale word missing");
+  if (N <= 0 || G <= 0 || N % G != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: bad shape");
   if ((dy_pooled == nullptr) == (d_gmax == nullptr)) return set_error(VM_ERR_SHAPE, "bn_bwd: give dy_pooled xor d_gmax");
-  if (C % 4 != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: C must be a multiple of 4");
+  if (C % 8 != 0) return set_error(VM_ERR_SHAPE, "bn_bwd: C must be a multiple of 8");
   return VM_OK;
+}
+// scratch contract of the two partial buffers: vm_bn_bwd_scratch_elems(N) entries each (float2 / float)
+size_t bn_bwd_scratch_elems(int N) {
+  if (N <= 0) return 0;
+  return size_t(N) * size_t((kNumSMs * 8 + N - 1) / N) * 2048;
 }
 
 // passes 1-2: per-(group, channel) sums of dy and dy*xhat over this rank's clips -> tmp (and, if asked, `sums`)
-static int bn_bwd_reduce(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
-                         int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
-                         double* red_scratch, double* sums, cudaStream_t st) {
+static int bn_bwd_reduce(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N,
+                         int lout, int C, int G, const float* bn_const, const float* mask, float* partial,
+                         unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st) {
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  const float4* bc = reinterpret_cast<const float4*>(bn_const);
-  const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;  // must match the kernels' thread layout
-  bn_bwd_reduce_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bc, mask,
-                                                        reinterpret_cast<float2*>(partial));
+  cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd: memset");
+  const int streams = ew_streams(C, 4);
+  const int chunks = dy_pooled != nullptr ? ew_chunks(N, lout, streams) : 1;
+  bn_bwd_reduce_kernel<<<dim3(N, chunks), kEwThreads, 0, st>>>(ext, dy_pooled, d_gmax, jstar, N, lout, C, G,
+                                                               reinterpret_cast<const float4*>(bn_const), mask,
+                                                               reinterpret_cast<float2*>(partial), absmax);
   rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
-      partial, size_t(N / G) * chunks * nstream, C, C, tmp);
+      partial, size_t(N / G) * chunks * streams, C, C, tmp);
   if (sums != nullptr) stage2_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, G, C, reinterpret_cast<double2*>(sums));
   return VM_OK;
 }
 
 // pass 3 + conv-bias gradient, given bwd_const
-static int bn_bwd_apply(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
-                        int C, int G, int pool, const float* bn_const, const float* mask, int chunks,
-                        const float* bwd_const, __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias,
+static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L,
+                        int C, int G, int pool, const float* bn_const, const float* mask, const float* bwd_const,
+                        const unsigned int* absmax, __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias,
                         double* red_scratch, cudaStream_t st) {
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  const int nstream = (128 / (C / 4)) > 0 ? 128 / (C / 4) : 1;
-  bn_relu_bwd_kernel<<<dim3(N, chunks), 128, 0, st>>>(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool,
-                                                      reinterpret_cast<const float4*>(bn_const),
-                                                      reinterpret_cast<const float4*>(bwd_const), mask, du_hi, du_lo,
-                                                      dbias_partial);
+  const int streams = ew_streams(C, 8);
+  const int chunks = ew_chunks(N, (L + pool - 1) / pool, streams);
+  const dim3 grid(N, chunks);
+  const float4* bc = reinterpret_cast<const float4*>(bn_const);
+  const float4* bw = reinterpret_cast<const float4*>(bwd_const);
+#define VM_RELU_BWD(SPARSE, PLANES)                                                                                 \
+  bn_relu_bwd_kernel<SPARSE, PLANES><<<grid, kEwThreads, 0, st>>>(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bc, \
+                                                                  bw, mask, absmax, du_hi, du_lo, dbias_partial)
+  if (dy_pooled == nullptr) { if (du_lo) VM_RELU_BWD(true, 2); else VM_RELU_BWD(true, 1); }
+  else { if (du_lo) VM_RELU_BWD(false, 2); else VM_RELU_BWD(false, 1); }
+#undef VM_RELU_BWD
   rowsum_stage1_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial,
-                                                                           size_t(N) * chunks * nstream, C, C, tmp);
+                                                                           size_t(N) * chunks * streams, C, C, tmp);
   colsum_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, C, dbias);
   return VM_OK;
 }
 
-int launch_bn_bwd(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C,
-                  int G, int pool, const float* bn_const, const float* mask, float* partial /* N*chunks*C float2 */,
-                  int chunks /* partial buffers hold N*chunks*max(1,512/C) rows */, float* bwd_const, float* dgamma,
-                  float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial /* N*chunks*C */, float* dbias,
-                  double* red_scratch, cudaStream_t st) {
-  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
+                  int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
+                  float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax, __half* du_hi, __half* du_lo,
+                  float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
-  bn_bwd_reduce(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, partial, chunks, red_scratch, nullptr,
-                st);
+  if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
+                          red_scratch, nullptr, st)))
+    return rc;
   bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<double2*>(red_scratch), N, G, L, C,
                                                       reinterpret_cast<const float4*>(bn_const),
                                                       reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
-  bn_bwd_apply(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, chunks, bwd_const, du_hi, du_lo,
+  bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd");
 }
 
-int launch_bn_bwd_sums(const float* u, const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L,
-                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial, int chunks,
-                       double* red_scratch, double* sums, cudaStream_t st) {
-  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+int launch_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L,
+                       int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
+                       unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
   if (sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd_sums: null sums");
-  bn_bwd_reduce(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, partial, chunks, red_scratch, sums, st);
+  if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
+                          red_scratch, sums, st)))
+    return rc;
   return check_launch_t("bn_bwd_sums");
 }
 
-int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const float* u,
-                            const float* dy_pooled, const float* d_gmax, const int* argmax, int N, int L, int C, int G,
-                            int pool, const float* bn_const, const float* mask, int chunks, float* bwd_const,
-                            float* dgamma, float* dbeta, __half* du_hi, __half* du_lo, float* dbias_partial,
-                            float* dbias, double* red_scratch, cudaStream_t st) {
-  int rc = bn_bwd_check(red_scratch, N, G, C, chunks, dy_pooled, d_gmax);
+int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
+                            const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L, int C, int G,
+                            int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
+                            float* dbeta, const unsigned int* absmax, __half* du_hi, __half* du_lo,
+                            float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
   if (local_sums == nullptr || global_sums == nullptr || !(count > 0.0))
     return set_error(VM_ERR_SHAPE, "bn_bwd_from_sums: bad sums / count");
@@ -837,7 +852,7 @@ int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums,
                                                        reinterpret_cast<const double2*>(global_sums), count, G, C,
                                                        reinterpret_cast<const float4*>(bn_const),
                                                        reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
-  bn_bwd_apply(u, dy_pooled, d_gmax, argmax, N, L, C, G, pool, bn_const, mask, chunks, bwd_const, du_hi, du_lo,
+  bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd_from_sums");
 }

@@ -8,11 +8,13 @@
 //   by `tap` rows.  D[tap] = 128 ci lanes x 128 co columns fp32 in TMEM (3 x 128 columns), accumulated over the
 //   CTA's slice of (clip, 64-position chunk) steps, then written to a per-split partial buffer that
 //   wgrad_reduce sums deterministically (no atomics).
-//   Both operands are bf16 (hi, lo) planes: gradients keep the fp32 exponent range (no loss scaling) and kind::f16
-//   cannot mix fp16 with bf16, so bn_pool_fwd also emits a bf16 copy of the activations for this kernel.
-//   products = 3 gives ~2^-16 relative gradients, products = 1 plain bf16.
+//   Both operands are fp16 planes: X is read from the very planes the forward convolution consumed (no copy in
+//   another format), dU arrives scaled by the block's power-of-two gradient scale (vm_common.cuh) which
+//   wgrad_reduce takes out again.  products = 3: Xh*Uh + Xl*Uh + Xh*Ul (two-plane gradient, ~2^-21);
+//   products = 2: Xh*Uh + Xl*Uh (one-plane gradient: dU rounded to fp16, 2^-12 relative per element, unbiased);
+//   products = 1: Xh*Uh.
 //
-// wgrad1 (block 1):  dW1[k][co] = sum_{n,p} x[n][p + k - 15] * dU1[n][p][co]   (CUDA cores, fp32; 4% of the FLOPs)
+// wgrad1 (block 1):  dW1[k][co] = sum_{n,p} x[n][p + k - 15] * dU1[n][p][co]   (tensor cores too: vm_conv1.cu)
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 
@@ -40,7 +42,7 @@ struct __align__(8) WgradBarriers {
 
 // instruction descriptor with both operands MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
-  return make_idesc_f16(M, N, /*A = X bf16*/ 1, /*B = dU bf16*/ 1) | (1u << 15) | (1u << 16);
+  return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);   // both operands fp16
 }
 
 __global__ void __launch_bounds__(wg::kThreads, 1)
@@ -52,7 +54,9 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nplanes = (p.products == 3) ? 2 : 1;
+  // products 3: Xh*Uh + Xl*Uh + Xh*Ul;  2: Xh*Uh + Xl*Uh (one-plane gradient);  1: Xh*Uh
+  const int xplanes = (p.products >= 2) ? 2 : 1;
+  const int uplanes = (p.products == 3) ? 2 : 1;
 
   // work item: (ci slab, co tile, split)
   const int combo = blockIdx.x % p.ncombo;
@@ -83,14 +87,16 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
         const int s = it % kStages;
         mbar_wait(&bars->empty[s], ((it / kStages) & 1) ^ 1);
         uint8_t* base = smem + s * kStageBytes;
-        mbar_arrive_expect_tx(&bars->full[s], nplanes * (kXPlaneBytes + kUPlaneBytes));
-        for (int pl = 0; pl < nplanes; ++pl) {
+        mbar_arrive_expect_tx(&bars->full[s], xplanes * kXPlaneBytes + uplanes * kUPlaneBytes);
+        for (int pl = 0; pl < xplanes; ++pl) {
           uint8_t* xb = base + pl * kXPlaneBytes;
-          uint8_t* ub = base + 2 * kXPlaneBytes + pl * kUPlaneBytes;
           const CUtensorMap* mx = pl ? &tm_xl : &tm_xh;
-          const CUtensorMap* mu = pl ? &tm_ul : &tm_uh;
           tma_load_3d(xb, mx, &bars->full[s], ci0, p0 - 1, n);
           tma_load_3d(xb + kXHalfBytes, mx, &bars->full[s], ci0 + 64, p0 - 1, n);
+        }
+        for (int pl = 0; pl < uplanes; ++pl) {
+          uint8_t* ub = base + 2 * kXPlaneBytes + pl * kUPlaneBytes;
+          const CUtensorMap* mu = pl ? &tm_ul : &tm_uh;
           tma_load_3d(ub, mu, &bars->full[s], co0, p0, n);
           tma_load_3d(ub + kUHalfBytes, mu, &bars->full[s], co0 + 64, p0, n);
         }
@@ -116,12 +122,12 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
             const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
             if (elected) umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
                      make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, acc);
-            if (nplanes == 2) {
-              if (elected) umma_f16(d, make_smem_desc(xl + arow, kXHalfBytes, 1024, kLayoutSW128),
+            if (xplanes == 2 && elected)
+              umma_f16(d, make_smem_desc(xl + arow, kXHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(uh + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
-              if (elected) umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
+            if (uplanes == 2 && elected)
+              umma_f16(d, make_smem_desc(xh + arow, kXHalfBytes, 1024, kLayoutSW128),
                        make_smem_desc(ul + brow, kUHalfBytes, 1024, kLayoutSW128), idesc, 1);
-            }
           }
         }
         if (elected) umma_commit(&bars->empty[s]);
@@ -162,22 +168,25 @@ wgrad3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__
   }
 }
 
-// dW[i] = scale * sum_s partial[s][i]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, size_t n, float scale,
-                                    float* __restrict__ out) {
+// dW[i] = sum_s partial[s][i] / (the block's power-of-two gradient scale, vm_common.cuh)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, size_t n,
+                                    const unsigned int* __restrict__ grad_absmax, float* __restrict__ out) {
+  const float unscale = grad_absmax ? 1.0f / grad_scale_from_absmax(__uint_as_float(*grad_absmax)) : 1.0f;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < nsplit; ++k) s += partial[size_t(k) * n + i];
-    out[i] = s * scale;
+    out[i] = s * unscale;
   }
 }
 
 int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, const __half* du_lo, int N, int L,
                   int cin, int cout, int products, float* partial, size_t partial_bytes, float* dw,
-                  cudaStream_t stream) {
+                  const unsigned int* grad_absmax, cudaStream_t stream) {
   using namespace wg;
   if (N <= 0 || L <= 0 || cin % 8 != 0 || cout % 8 != 0) return set_error(VM_ERR_SHAPE, "wgrad3: bad shape");
-  if (products == 3 && (x_lo == nullptr || du_lo == nullptr)) return set_error(VM_ERR_SHAPE, "wgrad3: lo planes required");
+  if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "wgrad3: products must be 1, 2 or 3");
+  if ((products >= 2 && x_lo == nullptr) || (products == 3 && du_lo == nullptr))
+    return set_error(VM_ERR_SHAPE, "wgrad3: lo planes required");
   Wgrad3Params p{};
   p.N = N; p.L = L; p.cin = cin; p.cout = cout; p.products = products;
   p.nchunk = (L + kPosChunk - 1) / kPosChunk;
@@ -200,7 +209,7 @@ int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, c
   const uint32_t ubox[3] = {64, kPosChunk, 1};
   int rc;
   if ((rc = make_tensor_map(&xh, x_hi, 3, xdims, xstr, xbox, VM_SWIZZLE_128B))) return rc;
-  if ((rc = make_tensor_map(&xl, products == 3 ? x_lo : x_hi, 3, xdims, xstr, xbox, VM_SWIZZLE_128B))) return rc;
+  if ((rc = make_tensor_map(&xl, products >= 2 ? x_lo : x_hi, 3, xdims, xstr, xbox, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&uh, du_hi, 3, udims, ustr, ubox, VM_SWIZZLE_128B))) return rc;
   if ((rc = make_tensor_map(&ul, products == 3 ? du_lo : du_hi, 3, udims, ustr, ubox, VM_SWIZZLE_128B))) return rc;
 
@@ -210,104 +219,23 @@ int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, c
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad3: launch");
   const unsigned blocks = unsigned(min(size_t(148 * 8), (wsize + 255) / 256));
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, nsplit, wsize, 1.0f, dw);
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, nsplit, wsize, grad_absmax, dw);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "wgrad3: reduce launch");
   return VM_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// wgrad1: block = 128 threads; thread (k8 = tid / 32, c4 = tid % 32) accumulates taps 8*k8..+7 x channels 4*c4..+3.
-// grid (N, position chunks); per-CTA partial [32][cout] -> deterministic reduce.
-// ---------------------------------------------------------------------------------------------
-constexpr int kW1Chunk = 1024;  // positions per CTA
-constexpr int kW1Sub = 64;      // positions per shared-memory sub-tile
-
-__global__ void __launch_bounds__(128)
-wgrad1_kernel(const float* __restrict__ x, const __half* __restrict__ du_hi, const __half* __restrict__ du_lo, int N,
-              int L, int cout, int co_base, float* __restrict__ partial) {
-  __shared__ float xs[kW1Chunk + 32];
-  __shared__ __align__(16) float us[kW1Sub][128];
-  const int n = blockIdx.x, chunk = blockIdx.y;
-  const int p0 = chunk * kW1Chunk;
-  const int plen = min(kW1Chunk, L - p0);
-  const int k8 = threadIdx.x >> 5, c4 = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kW1Chunk + 31; i += 128) {
-    const int e = p0 - 15 + i;
-    xs[i] = (e >= 0 && e < L) ? x[size_t(n) * L + e] : 0.f;
-  }
-  float acc[8][4];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-
-  for (int sp = 0; sp < plen; sp += kW1Sub) {
-    __syncthreads();
-    const int sl = min(kW1Sub, plen - sp);
-    for (int i = threadIdx.x; i < kW1Sub * 128; i += 128) {
-      const int r = i >> 7, c = i & 127;
-      float v = 0.f;
-      if (r < sl && co_base + c < cout) {
-        const size_t o = (size_t(n) * L + p0 + sp + r) * cout + co_base + c;
-        v = bf16_bits_to_float(__half_as_ushort(du_hi[o])) +
-            (du_lo ? bf16_bits_to_float(__half_as_ushort(du_lo[o])) : 0.f);
-      }
-      us[r][c] = v;
-    }
-    __syncthreads();
-    // sliding window of 8 samples: position r uses x[p + 8*k8 + a - 15], a = 0..7  ->  xs[sp + r + 8*k8 + a]
-    float xr[8];
-#pragma unroll
-    for (int a = 0; a < 7; ++a) xr[a + 1] = xs[sp + 8 * k8 + a];
-    for (int r = 0; r < sl; ++r) {
-#pragma unroll
-      for (int a = 0; a < 7; ++a) xr[a] = xr[a + 1];
-      xr[7] = xs[sp + r + 8 * k8 + 7];
-      const float4 d = *reinterpret_cast<const float4*>(&us[r][4 * c4]);
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        acc[a][0] = fmaf(xr[a], d.x, acc[a][0]);
-        acc[a][1] = fmaf(xr[a], d.y, acc[a][1]);
-        acc[a][2] = fmaf(xr[a], d.z, acc[a][2]);
-        acc[a][3] = fmaf(xr[a], d.w, acc[a][3]);
-      }
-    }
-  }
-  float* out = partial + (size_t(n) * gridDim.y + chunk) * 32 * cout;
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int co = co_base + 4 * c4 + b;
-      if (co < cout) out[size_t(8 * k8 + a) * cout + co] = acc[a][b];
-    }
-}
-
 int launch_wgrad1(const float* x, const __half* du_hi, const __half* du_lo, int N, int L, int cout, float* partial,
-                  size_t partial_bytes, float* dw, cudaStream_t stream, int products) {
+                  size_t partial_bytes, float* dw, const unsigned int* grad_absmax, cudaStream_t stream, int products) {
   if (N <= 0 || L <= 0 || cout <= 0) return set_error(VM_ERR_SHAPE, "wgrad1: bad shape");
-  if (products != 0) {  // tensor-core path (vm_conv1.cu); products == 0 keeps the CUDA-core reference kernel below
-    int nsplit = 0;
-    int rc = launch_wgrad1_tc(x, du_hi, du_lo, N, L, cout, products, partial, partial_bytes, &nsplit, stream);
-    if (rc) return rc;
-    const size_t wsz = size_t(32) * cout;
-    wgrad_reduce_kernel<<<unsigned((wsz + 255) / 256), 256, 0, stream>>>(partial, nsplit, wsz, 1.0f, dw);
-    cudaError_t e2 = cudaGetLastError();
-    if (e2 != cudaSuccess) return set_cuda_error(e2, "wgrad1: reduce launch");
-    return VM_OK;
-  }
-  const int chunks = (L + kW1Chunk - 1) / kW1Chunk;
-  const size_t wsize = size_t(32) * cout;
-  if (size_t(N) * chunks * wsize * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad1: partial buffer too small");
-  for (int co_base = 0; co_base < cout; co_base += 128)
-    wgrad1_kernel<<<dim3(N, chunks), 128, 0, stream>>>(x, du_hi, du_lo, N, L, cout, co_base, partial);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: launch");
-  const unsigned blocks = unsigned((wsize + 255) / 256);
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, N * chunks, wsize, 1.0f, dw);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error(e, "wgrad1: reduce launch");
+  if (products < 1 || products > 3) return set_error(VM_ERR_SHAPE, "wgrad1: products must be 1, 2 or 3");
+  int nsplit = 0;
+  int rc = launch_wgrad1_tc(x, du_hi, du_lo, N, L, cout, products, partial, partial_bytes, &nsplit, stream);
+  if (rc) return rc;
+  const size_t wsz = size_t(32) * cout;
+  wgrad_reduce_kernel<<<unsigned((wsz + 255) / 256), 256, 0, stream>>>(partial, nsplit, wsz, grad_absmax, dw);
+  cudaError_t e2 = cudaGetLastError();
+  if (e2 != cudaSuccess) return set_cuda_error(e2, "wgrad1: reduce launch");
   return VM_OK;
 }
 

@@ -126,10 +126,12 @@ class EncoderEngine:
         base = self._workspace.data_ptr()
         return C.c_void_p((base + 1023) // 1024 * 1024)
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, precision=None):
         """x: contiguous fp32 tensor (N, L) or (N, L, 1), on the device or in PINNED host memory (block 1 then reads
         the waveform over PCIe/C2C directly -- pinned allocations are device-mapped under unified addressing; the
-        caller keeps the tensor alive and unchanged until the stream has run).  Returns (N, E) fp32 (CUDA)."""
+        caller keeps the tensor alive and unchanged until the stream has run).  Returns (N, E) fp32 (CUDA).
+        ``precision`` overrides the engine's arithmetic for this call (the packed weights carry the planes of every
+        mode and the workspace layout is the same)."""
         if x.dim() == 3:
             if x.shape[2] != 1:
                 raise ValueError("encoder input must have one channel: (N, L, 1)")
@@ -147,7 +149,7 @@ class EncoderEngine:
             ep = (C.c_void_p * 4)(*[t.data_ptr() for t in self.epi])
             rc = self.lib.vm_encoder_fwd(_ptr(x), n, length, self.filters, self.first_pool, wp, ep, _ptr(self.params["dense_kernel"]),
                                          _ptr(self.params["dense_bias"]), self.embedding_dimension, ws, _ptr(out),
-                                         self.precision, _stream())
+                                         int(precision) if precision is not None else self.precision, _stream())
         _lib.check(rc, "vm_encoder_fwd")
         return out
 

@@ -598,6 +598,11 @@ class SiameseModel(_ModelBase):
                        LayerInfo("dense_2", "Dense", dict(units=1, activation="sigmoid"),
                                  ("head_kernel", "head_bias"), self)]
         self._head_dev = None
+        # The head works on DIFFERENCES of embeddings: e1 - e2 cancels most of their magnitude, which amplifies the
+        # encoder's rounding error by |e| / |e1 - e2| before the sigmoid.  Pair probabilities and the losses computed
+        # from them are held to 1e-4 of the reference, which the fp16 x 3 arithmetic meets and the
+        # fp16 + fp8 mode (the encoder's default for embeddings) does not always: the siamese eval path runs precision 3.
+        self.precision = 3
 
     def _weight(self, name):
         return self.head_weights[name]
@@ -698,11 +703,52 @@ class SiameseModel(_ModelBase):
                     dst.copy_(part[i:i + n], non_blocking=True)
                 else:
                     self.encoder._stage_numpy(part[i:i + n], eng, xin=dst)
-            emb = eng.forward(xb)
+            emb = eng.forward(xb, precision=self.precision)
             prob, _, _ = pair_head_loss(emb[:n], emb[n:], w, b, self.distance_metric)
             outs.append(prob)
         out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         return out.cpu().numpy()
+
+    def test_on_batch(self, x, y, sample_weight=None):
+        """keras ``Model.test_on_batch``: eval-mode loss of the compiled model on one batch of pairs (and accuracy when
+        compiled with ``metrics=['accuracy']``).  Encoder, head and loss run on the device: both branches as one
+        2N-clip launch, then ONE launch of the fused head + loss kernel (``vm_pair_head_loss_fwd``), which is the
+        arithmetic the training step uses.  Reference: voicemap/models.py:64-69, voicemap/utils.py:77-85, keras
+        binary_crossentropy (experiments/train_siamese.py:57)."""
+        import torch
+        from .engine import pair_head_loss
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is not used by voicemap's scripts")
+        if self.loss is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        loss = {"contrastive_loss": "contrastive", "binary_crossentropy": "binary_crossentropy"}.get(self.loss)
+        if loss is None:
+            raise NotImplementedError(f"siamese evaluation with loss {self.loss!r}")
+        if not isinstance(x, (list, tuple)) or len(x) != 2:
+            raise ValueError("Error when checking model input: the siamese network expects a list of 2 arrays")
+        sides = []
+        for side in x:
+            side = np.asarray(side)
+            self.encoder._check_input_shape(side.shape)
+            sides.append(side[:, :, 0])
+        n, length = sides[0].shape
+        if sides[1].shape != (n, length):
+            raise ValueError("siamese inputs must have the same shape")
+        labels = np.asarray(y, dtype=np.float32).reshape(-1)
+        if labels.shape[0] != n:
+            raise ValueError(f"expected {n} labels, got {labels.shape[0]}")
+        eng = self.encoder._get_engine()
+        w, b = self._head_device(eng.device)
+        xb = torch.empty((2 * n, length), dtype=torch.float32, device=eng.device)
+        for part, dst in zip(sides, (xb[:n], xb[n:])):
+            self.encoder._stage_numpy(part, eng, xin=dst)
+        yt = torch.from_numpy(labels).to(eng.device, non_blocking=True)
+        emb = eng.forward(xb, precision=self.precision)
+        prob, _, lossv = pair_head_loss(emb[:n], emb[n:], w, b, self.distance_metric, y_true=yt, loss=loss)
+        out = [float(lossv.item())]
+        if any(m in ("accuracy", "acc") for m in (self.metrics or [])):
+            out.append(float(((prob.reshape(-1) > 0.5).to(torch.float32) == yt).to(torch.float32).mean().item()))
+        return out[0] if len(out) == 1 else out
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -812,7 +858,23 @@ def _load_keras_hdf5(filepath):
             enc.set_named_weights({"head_kernel": find("dense_2/kernel"), "head_bias": find("dense_2/bias")})
         return enc
     head_k = find("dense_2/kernel")
-    metric = "weighted_l1" if head_k.shape[0] == emb and emb != 1 else "uniform_euclidean"
+    stored = []
+
+    def walk_metric(o):
+        if isinstance(o, dict):
+            if "voicemap_distance_metric" in o:
+                stored.append(o["voicemap_distance_metric"])
+            for v in o.values():
+                walk_metric(v)
+        elif isinstance(o, list):
+            for v in o:
+                walk_metric(v)
+
+    walk_metric(cfg)
+    if stored and stored[0] in ("weighted_l1", "uniform_euclidean"):
+        metric = stored[0]               # written by this package's save(); Keras' own files carry only the lambda
+    else:                                # a Keras checkpoint: the head kernel's shape tells the two apart (emb > 1)
+        metric = "weighted_l1" if head_k.shape[0] == emb and emb != 1 else "uniform_euclidean"
     m = SiameseModel(enc, lshape if lshape else (12000, 1), metric)
     m.head_weights["head_kernel"] = head_k.reshape(m.head_weights["head_kernel"].shape).copy()
     m.head_weights["head_bias"] = find("dense_2/bias").copy()

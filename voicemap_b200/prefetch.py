@@ -114,6 +114,27 @@ def _worker(index, count, seed, source, blocks, free_q, ready_q, task_q, stop):
         os._exit(code)
 
 
+_LINGERING = []   # blocks whose mapping outlives their pool because a handed-out batch still views them
+
+
+def _release(blocks):
+    """Unlink the blocks' names now; unmap each block as soon as no numpy view of it is left.  A block that is still
+    viewed (the last batch of an epoch, a batch kept by the caller, one shown in a traceback) stays mapped and is
+    retried whenever another pool closes -- never unmapped under a live array."""
+    for block in blocks:
+        try:
+            block.unlink()
+        except FileNotFoundError:
+            pass
+    pending = _LINGERING + list(blocks)
+    del _LINGERING[:]
+    for block in pending:
+        try:
+            block.close()
+        except BufferError:                                # exported pointers exist: a batch still views the block
+            _LINGERING.append(block)
+
+
 class _Pool:
     """Shared-memory slots, the queues and the forked children; the two prefetchers below differ in what they ask of
     them."""
@@ -166,7 +187,10 @@ class _Pool:
     def batch(self, message):
         _, _, slot, tree, entries, _ = message
         block = self.blocks[slot]
-        arrays = [np.ndarray(shape, dtype=dtype, buffer=block.buf, offset=offset) for offset, shape, dtype in entries]
+        # np.frombuffer (unlike np.ndarray(buffer=...)) keeps a buffer export of the mapping for as long as the array
+        # lives, so close() cannot unmap a block under a batch somebody still holds (it defers, see _release)
+        arrays = [np.frombuffer(block.buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64)), offset=offset)
+                  .reshape(shape) for offset, shape, dtype in entries]
         return _rebuild(tree, arrays)
 
     def close(self):
@@ -187,15 +211,7 @@ class _Pool:
             if q is not None:
                 q.cancel_join_thread()
                 q.close()
-        for block in self.blocks:
-            try:
-                block.close()
-            except BufferError:                            # a batch handed out earlier still views the block
-                pass
-            try:
-                block.unlink()
-            except FileNotFoundError:
-                pass
+        _release(self.blocks)
 
     def __del__(self):
         try:

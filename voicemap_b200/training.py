@@ -27,7 +27,6 @@ from .engine import BN_EPS, PRECISION_FP32_GRADE, EncoderEngine, _ptr, _stream
 
 BN_MOMENTUM = 0.99
 POOLS = (4, 2, 2, 2)
-_BWD_CHUNKS = 32
 
 
 def _check(rc, what):
@@ -66,6 +65,10 @@ class TrainEngine:
 
     def __init__(self, model, optimizer, loss, loss_scale=1.0, precision=PRECISION_FP32_GRADE, bwd_precision=None,
                  seed=0):
+        """precision: arithmetic of the train-mode forward convolutions of blocks 2-4 -- 3 = fp16 x 3, 2 = fp16 + fp8
+        correction product; block 1 always runs fp16 x 3.  bwd_precision: 3 = two-plane fp16
+        gradients, three MMAs per step; 2 = one-plane fp16 gradients (each dU element rounded to 11 significant bits,
+        unbiased) against two-plane activations / weights, two MMAs; 1 = one plane each."""
         from .models import EncoderModel, SiameseModel
         self.lib = _lib.load()
         self.model = model
@@ -161,17 +164,26 @@ class TrainEngine:
         key = (nb, length, groups)
         if self._buf_key == key:
             return
+        self.U16 = self.EXT = self.X = self.XL = self.XQ = self.dU = self.dX = self.scr1 = self.scr2 = None   # free before regrowing
         dev, f32, f16 = self.device, torch.float32, torch.float16
         ls = [length]
         for p in self.pools:
             ls.append(ls[-1] // p)
         if ls[4] < 1:
             raise ValueError("clips are too short for the encoder")
-        self.ls = ls  # ls[b] = input length of block b+1 = un-pooled length of block b+1's conv
+        self.ls = ls  # ls[b] = un-pooled length of block b+1's conv; ls[b + 1] = its pooled length
         c = self.channels
-        self.U = [torch.empty((nb, ls[b], c[b]), dtype=f32, device=dev) for b in range(4)]
-        self.X = [torch.empty((2, nb, ls[b + 1], c[b]), dtype=f16, device=dev) for b in range(3)]  # fp16 [hi/lo]
-        self.XB = [torch.empty((2, nb, ls[b + 1], c[b]), dtype=torch.int16, device=dev) for b in range(3)]  # bf16
+        # per block: encoded un-pooled activations (fp16 + arg-max flag) and the fp32 extreme of every pool window
+        self.U16 = [torch.empty((nb, ls[b], c[b]), dtype=torch.int16, device=dev) for b in range(4)]
+        self.EXT = [torch.empty((nb, ls[b + 1], c[b]), dtype=f32, device=dev) for b in range(4)]
+        # pooled, normalised activations = inputs of the next block's conv: fp16 hi plane, fp16 residual plane (forward
+        # precision 3; the weight gradient's second plane whenever bwd_precision >= 2) and / or e5m2x2 Q plane (forward
+        # precision 2)
+        want_lo = self.precision == 3 or (self.precision == 2 and self.bwd_precision >= 2)
+        self.X = [torch.empty((nb, ls[b + 1], c[b]), dtype=f16, device=dev) for b in range(3)]
+        self.XL = [torch.empty((nb, ls[b + 1], c[b]), dtype=f16, device=dev) if want_lo else None for b in range(3)]
+        self.XQ = [torch.empty((nb, ls[b + 1], c[b]), dtype=f16, device=dev) if self.precision == 2 else None
+                   for b in range(3)]
         rows = [self.lib.vm_stat_rows_per_clip(ls[b]) for b in range(4)]
         self.stat = [torch.empty((nb * rows[b], self.lib.vm_padded_channels(c[b]), 2), dtype=f32, device=dev)
                      for b in range(4)]
@@ -179,16 +191,16 @@ class TrainEngine:
         self.bnc = [torch.empty((groups, c[b], 4), dtype=f32, device=dev) for b in range(4)]
         self.bwc = [torch.empty((groups, c[b], 4), dtype=f32, device=dev) for b in range(4)]
         self.gmax = torch.empty((nb, c[3]), dtype=f32, device=dev)
-        self.argmax = torch.empty((nb, c[3]), dtype=torch.int32, device=dev)
+        self.jstar = torch.empty((nb, c[3]), dtype=torch.int32, device=dev)
         self.embv = torch.empty((nb, self.emb), dtype=f32, device=dev)
         self.d_emb = torch.empty((nb, self.emb), dtype=f32, device=dev)
         self.d_gmax = torch.empty((nb, c[3]), dtype=f32, device=dev)
         max_u = max(ls[b] * c[b] for b in range(4))
-        self.dU = torch.empty((2, nb * max_u), dtype=f16, device=dev)
+        self.dU = torch.empty((2 if self.bwd_precision == 3 else 1, nb * max_u), dtype=f16, device=dev)
+        self.gabs = torch.zeros((4,), dtype=torch.int32, device=dev)   # per block: bits of max |s * dy| -> gradient scale
         max_x = max(ls[b + 1] * c[b] for b in range(3))
         self.dX = torch.empty(nb * max_x, dtype=f32, device=dev)
-        # BN-backward partial rows: N * chunks * nstream rows of C entries with nstream * C == max(512, C)
-        scr_elems = nb * _BWD_CHUNKS * max(512, max(c))
+        scr_elems = self.lib.vm_bn_bwd_scratch_elems(nb)
         self.scr2 = torch.empty((scr_elems, 2), dtype=f32, device=dev)
         self.scr1 = torch.empty((scr_elems,), dtype=f32, device=dev)
         self.red = torch.empty(self.lib.vm_reduce_scratch_bytes(groups, max(c)) // 8, dtype=torch.float64, device=dev)
@@ -263,17 +275,18 @@ class TrainEngine:
         c, ls = self.channels, self.ls
         eps, mom = C.c_float(BN_EPS), C.c_float(BN_MOMENTUM)
         for b in range(4):
+            gamma, beta = _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"])
             if b == 0:
-                plan.launch(lib.vm_conv1_raw_fwd, "train conv block 1", _ptr(self.xin), nb, length, c[0],
-                            _ptr(self.wraw[0]), _ptr(self.eraw[0]), _ptr(self.U[0]), _ptr(self.stat[0]), self.precision,
-                            st)
+                plan.launch(lib.vm_conv1_train_fwd, "train conv block 1", _ptr(self.xin), nb, length, c[0], self.pools[0],
+                            _ptr(self.wraw[0]), _ptr(self.eraw[0]), gamma, _ptr(self.U16[0]), _ptr(self.EXT[0]),
+                            _ptr(self.stat[0]), self.precision, st)
             else:
-                plan.launch(lib.vm_conv3_raw_fwd, f"train conv block {b + 1}", _ptr(self.X[b - 1][0]),
-                            _ptr(self.X[b - 1][1]), nb, ls[b], c[b - 1], c[b], _ptr(self.wraw[b]), _ptr(self.eraw[b]),
-                            _ptr(self.U[b]), _ptr(self.stat[b]), 0, self.precision, st)
+                second = self.XQ[b - 1] if self.precision == 2 else self.XL[b - 1]
+                plan.launch(lib.vm_conv3_train_fwd, f"train conv block {b + 1}", _ptr(self.X[b - 1]),
+                            _ptr(second), nb, ls[b], c[b - 1], c[b], _ptr(self.wraw[b]), _ptr(self.eraw[b]),
+                            gamma, _ptr(self.U16[b]), _ptr(self.EXT[b]), _ptr(self.stat[b]), self.precision, st)
             mm = self.moving[f"bn{b + 1}_mean"] if update_moving else None
             mv = self.moving[f"bn{b + 1}_var"] if update_moving else None
-            gamma, beta = _ptr(self.p[f"bn{b + 1}_gamma"]), _ptr(self.p[f"bn{b + 1}_beta"])
             if self.sync_allreduce is None:
                 plan.launch(lib.vm_bn_stats_finalize, "vm_bn_stats_finalize", _ptr(self.stat[b]), self.stat_rows[b], nb,
                             groups, ls[b], c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]),
@@ -287,12 +300,12 @@ class TrainEngine:
                 plan.launch(lib.vm_bn_stats_from_sums, "vm_bn_stats_from_sums", _ptr(sums), C.c_double(count), groups,
                             c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]), st)
             if b < 3:
-                plan.launch(lib.vm_bn_pool_fwd, "vm_bn_pool_fwd", _ptr(self.U[b]), nb, ls[b], c[b], groups, self.pools[b],
-                            _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.X[b][0]), _ptr(self.X[b][1]),
-                            _ptr(self.XB[b][0]), _ptr(self.XB[b][1]), st)
+                plan.launch(lib.vm_bn_pool_fwd, "vm_bn_pool_fwd", _ptr(self.EXT[b]), nb, ls[b + 1], c[b], groups,
+                            _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.X[b]), _ptr(self.XL[b]), _ptr(self.XQ[b]),
+                            st)
             else:
-                plan.launch(lib.vm_bn_gmax_fwd, "vm_bn_gmax_fwd", _ptr(self.U[3]), nb, ls[3], c[3], groups,
-                            _ptr(self.bnc[3]), _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.argmax), st)
+                plan.launch(lib.vm_bn_gmax_fwd, "vm_bn_gmax_fwd", _ptr(self.EXT[3]), nb, ls[4], c[3], groups,
+                            _ptr(self.bnc[3]), _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.jstar), st)
         plan.launch(lib.vm_dense_fwd, "vm_dense_fwd", _ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]),
                     _ptr(self.p["dense_bias"]), self.emb, _ptr(self.embv), st)
         return plan
@@ -323,23 +336,25 @@ class TrainEngine:
         bp = self.bwd_precision
         for b in (3, 2, 1, 0):
             n_u = nb * ls[b] * c[b]
-            du_hi, du_lo = self.dU[0][:n_u], self.dU[1][:n_u]
+            du_hi = self.dU[0][:n_u]
+            du_lo = self.dU[1][:n_u] if bp == 3 else None
+            gabs = _ptr(self.gabs[b:b + 1])
             if b == 3:
-                dy, dg, am = None, self.d_gmax, self.argmax
+                dy, dg, js = None, self.d_gmax, self.jstar
             else:
-                dy, dg, am = self.dX, None, None
+                dy, dg, js = self.dX, None, None
             grads = (_ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]))
             if self.sync_allreduce is None:
-                plan.launch(lib.vm_bn_bwd, f"vm_bn_bwd block {b + 1}", _ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb,
-                            ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.scr2),
-                            _BWD_CHUNKS, _ptr(self.bwc[b]), *grads, _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1),
-                            _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
+                plan.launch(lib.vm_bn_bwd, f"vm_bn_bwd block {b + 1}", _ptr(self.U16[b]), _ptr(self.EXT[b]), _ptr(dy),
+                            _ptr(dg), _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
+                            _ptr(self.masks[b]), _ptr(self.scr2), _ptr(self.bwc[b]), *grads, gabs, _ptr(du_hi),
+                            _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
             else:
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
-                plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.U[b]), _ptr(dy), _ptr(dg),
-                            _ptr(am), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
-                            _ptr(self.scr2), _BWD_CHUNKS, _ptr(self.red), _ptr(loc), st)
+                plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.EXT[b]), _ptr(dy), _ptr(dg),
+                            _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
+                            _ptr(self.scr2), gabs, _ptr(self.red), _ptr(loc), st)
 
                 def share(loc=loc, glo=glo):
                     glo.copy_(loc)
@@ -347,19 +362,21 @@ class TrainEngine:
                 plan.host(share)
                 count = float(self.sync_world) * (nb // groups) * ls[b]
                 plan.launch(lib.vm_bn_bwd_from_sums, f"vm_bn_bwd_from_sums block {b + 1}", _ptr(loc), _ptr(glo),
-                            C.c_double(count), _ptr(self.U[b]), _ptr(dy), _ptr(dg), _ptr(am), nb, ls[b], c[b], groups,
-                            self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _BWD_CHUNKS, _ptr(self.bwc[b]), *grads,
+                            C.c_double(count), _ptr(self.U16[b]), _ptr(dy), _ptr(dg), _ptr(js), nb, ls[b], c[b], groups,
+                            self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.bwc[b]), *grads, gabs,
                             _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
             if b == 0:
                 plan.launch(lib.vm_wgrad1, "vm_wgrad1", _ptr(self.xin), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp,
-                            _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
+                            gabs, _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
             else:
-                plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.XB[b - 1][0]), _ptr(self.XB[b - 1][1]),
-                            _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b - 1], c[b], bp, _ptr(self.wpart),
+                x_lo = self.XL[b - 1]
+                wp = bp if x_lo is not None else 1      # forward precision 1 keeps no second activation plane
+                plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.X[b - 1]), _ptr(x_lo), _ptr(du_hi),
+                            _ptr(du_lo if wp == 3 else None), nb, ls[b], c[b - 1], c[b], wp, gabs, _ptr(self.wpart),
                             self.wpart.numel() * 4, _ptr(g[f"conv{b + 1}_kernel"]), st)
                 # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
-                plan.launch(lib.vm_conv3_raw_fwd, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
-                            c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), _ptr(self.dX), None, 1, bp, st)
+                plan.launch(lib.vm_conv3_dgrad, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
+                            c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), gabs, _ptr(self.dX), bp, st)
         return plan
 
     # ------------------------------------------------------------------ optimizer
@@ -490,6 +507,30 @@ class TrainEngine:
             target[name] = self.p[name].detach().cpu().numpy().copy()
         if self.kind == "siamese":
             self.model._head_dev = None
+
+    # ------------------------------------------------------------------ views for tests / diagnostics
+    def relu_pattern(self, b):
+        """(NB, L_b, C_b) bool: where block b+1's un-pooled activation of the last step was positive."""
+        return (self.U16[b] & 0x7FFF) != 0
+
+    def activation(self, b):
+        """(NB, L_b, C_b) fp32: block b+1's un-pooled u = relu(conv + bias) as kept for the backward pass (fp16)."""
+        return (self.U16[b] & 0x7FFF).view(torch.float16).to(torch.float32)
+
+    def argmax_flags(self, b):
+        return self.U16[b] < 0          # bit 15 of the int16 word
+
+    def block_gradient(self, b):
+        """(NB, L_b, C_b) fp32: dLoss/d(conv output) of block b+1 as the backward kernels consumed it (planes summed,
+        gradient scale and loss scale taken out).  Only the block written last is still in the buffer (block 1 after
+        a full backward)."""
+        n_u = self.U16[b].numel()
+        planes = self.dU[:, :n_u].to(torch.float32).sum(dim=0)
+        absmax = self.gabs[b:b + 1].view(torch.float32).item()
+        if absmax > 0:
+            import math
+            planes = planes / math.ldexp(1.0, 6 - math.frexp(absmax)[1])
+        return (planes / self.loss_scale).view(self.U16[b].shape)
 
     def gradients(self):
         """Unscaled gradients as numpy arrays (tests)."""
@@ -661,7 +702,9 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
 
 def _validate(model, trainer, validation_data, val_iter, validation_steps):
     """Eval-mode loss / accuracy (moving BN statistics, no dropout) over the validation batches, Keras-style
-    sample-weighted means.  Predictions come from the CUDA eval path; the scalar loss formulas run on the host."""
+    sample-weighted means.  Siamese: ``model.test_on_batch`` (encoder + fused head/loss kernel on the device).
+    Classifier: softmax probabilities from the device, the cross-entropy of the (N, classes) matrix on the host (the
+    classifier head is adjacent to the path)."""
     if val_iter is None:
         batches = [validation_data]
     else:
@@ -671,17 +714,17 @@ def _validate(model, trainer, validation_data, val_iter, validation_steps):
     tot, tl, ta = 0, 0.0, 0.0
     for batch in batches:
         x, y = batch[0], np.asarray(batch[1], dtype=np.float32)
-        pred = model.predict(x).astype(np.float32)
-        n = pred.shape[0]
         if trainer.kind == "siamese":
-            y = y.reshape(-1, 1)
-            if model.loss == "contrastive_loss":
-                lv = float(np.mean((1 - y) * np.square(pred) + y * np.square(np.maximum(1 - pred, 0))))
-            else:
-                pc = np.clip(pred, np.float32(1e-7), np.float32(1 - 1e-7))
-                lv = float(np.mean(-y * np.log(pc) - (1 - y) * np.log(1 - pc)))
-            acc = float(np.mean((pred > 0.5).astype(np.float32) == y))
+            # encoder, head and loss on the device: one 2N-clip launch + the fused head/loss kernel of the train step
+            metrics, model.metrics = model.metrics, ["accuracy"]
+            try:
+                lv, acc = model.test_on_batch(x, y)
+            finally:
+                model.metrics = metrics
+            n = y.reshape(-1).shape[0]
         else:
+            pred = model.predict(x).astype(np.float32)
+            n = pred.shape[0]
             pc = np.clip(pred / pred.sum(axis=-1, keepdims=True), 1e-7, 1 - 1e-7)
             lv = float(np.mean(-(y * np.log(pc)).sum(axis=-1)))
             acc = float(np.mean(pred.argmax(axis=-1) == y.argmax(axis=-1)))

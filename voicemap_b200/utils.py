@@ -150,7 +150,8 @@ def _solved_pairwise(model, tasks, k):
     engine = encoder._get_engine()
     # eval-mode embeddings are independent of batch composition, so the query is embedded once per task
     clips = np.concatenate([left[:1] for left, _ in tasks] + [right for _, right in tasks], axis=0)
-    emb = engine.forward(encoder._host_batch(clips).to(engine.device, non_blocking=True))
+    emb = engine.forward(encoder._host_batch(clips).to(engine.device, non_blocking=True),
+                         precision=getattr(model, 'precision', None))
     width = emb.shape[1]
     queries = emb[:t, None, :].expand(t, k, width).reshape(t * k, width).contiguous()
     kernel, bias = model._head_device(engine.device)
@@ -158,18 +159,52 @@ def _solved_pairwise(model, tasks, k):
     return int((prob.reshape(t, k).argmin(dim=1) == 0).sum().item())
 
 
-def _solved_by_embedding(encoder, tasks, k, n, score):
-    """Tasks whose nearest class (under ``score``) is class 0."""
-    if len(tasks) == 1:
-        query, support = tasks[0]
-        embedded = [(encoder.predict(query), encoder.predict(support))]
-    else:
-        t = len(tasks)
-        clips = np.concatenate([q for q, _ in tasks] + [s for _, s in tasks], axis=0)
-        emb = encoder.predict(clips)
+_DISTANCE_IDS = {'euclidean': 0, 'cosine': 1, 'dot_product': 2}   # VM_DISTANCE_* of include/voicemap_b200.h
+
+
+def nshot_best_class_device(query_emb, support_emb, k, n, distance):
+    """Device-side decision rule of voicemap/utils.py:156-212 for T tasks at once: ``query_emb`` CUDA (T, E),
+    ``support_emb`` CUDA (T*k*n, E) ordered task by task, class by class.  Class means, the chosen distance and the
+    arg-min all run in ``vm_nshot_score``; returns a CUDA int32 (T,) tensor of winning classes (0 = solved)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    t, width = query_emb.shape
+    if support_emb.shape != (t * k * n, width):
+        raise ValueError('support embeddings must have shape (tasks * k * n, embedding_dimension)')
+    query_emb, support_emb = query_emb.contiguous(), support_emb.contiguous()
+    best = torch.empty((t,), dtype=torch.int32, device=query_emb.device)
+    with torch.cuda.device(query_emb.device):
+        rc = lib.vm_nshot_score(C.c_void_p(query_emb.data_ptr()), C.c_void_p(support_emb.data_ptr()), t, k, n, width,
+                                _DISTANCE_IDS[distance], None, C.c_void_p(best.data_ptr()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, 'vm_nshot_score')
+    return best
+
+
+def _solved_by_embedding(encoder, tasks, k, n, distance):
+    """Tasks whose nearest class (under ``distance``) is class 0.  Queries and supports of all tasks of the list are
+    embedded by one encoder launch; class means, distances and the arg-min run on the device (``vm_nshot_score``) and
+    only the count comes back.  (The numpy ``_SCORES`` above state the same rule on the host; tests hold the two
+    together.)"""
+    t = len(tasks)
+    clips = np.concatenate([q for q, _ in tasks] + [s for _, s in tasks], axis=0)
+    if not hasattr(encoder, '_get_engine'):
+        # a foreign model object that only offers ``predict`` (duck-typed stand-ins in the host tests): its embeddings
+        # are host arrays it computed itself; the rule is applied with the numpy statement above.  Models built by
+        # this package never come here -- they have no host arithmetic to fall back to.
+        emb = np.asarray(encoder.predict(clips))
         shots = emb[t:].reshape(t, k * n, -1)
-        embedded = [(emb[i:i + 1], shots[i]) for i in range(t)]
-    return sum(int(np.argmin(score(q[0], s, k, n)) == 0) for q, s in embedded)
+        return sum(int(np.argmin(_SCORES[distance](emb[i], shots[i], k, n)) == 0) for i in range(t))
+    import torch
+    encoder._check_input_shape(clips.shape)
+    engine = encoder._get_engine()
+    emb = torch.empty((clips.shape[0], encoder.embedding_dimension), dtype=torch.float32, device=engine.device)
+    encoder._stage_numpy(clips[:, :, 0], engine,
+                         lambda xin, lo, hi, base: engine.forward(xin[lo:hi], out=emb[base + lo:base + hi]))
+    best = nshot_best_class_device(emb[:t], emb[t:], k, n, distance)
+    return int((best == 0).sum().item())
 
 
 def n_shot_task_evaluation(model, dataset, preprocessor, num_tasks, n, k, network_type='siamese',
@@ -193,7 +228,7 @@ def n_shot_task_evaluation(model, dataset, preprocessor, num_tasks, n, k, networ
         encoder = _embedding_network(model, network_type)
         if distance not in _SCORES:
             raise ValueError('Distance must be in (euclidean, cosine, dot_product)')
-        score = _SCORES[distance]
+        score = distance
 
     from tqdm import tqdm
     n_correct = 0
