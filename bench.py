@@ -44,6 +44,10 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
                     help="2: fp16 product + fp8 (e5m2 pairs) correction product (parity mode, default); 3: fp16x3 split "
                          "(parity mode, tighter); 1: fp16x1 (throughput mode, not parity)")
+    ap.add_argument("--train-pairs", type=int, default=128,
+                    help="GLOBAL pairs per training step (BASELINE config[2]: 128), sharded over the ranks")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step record")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -206,6 +210,101 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# training step (BASELINE config[2]): siamese encoder + contrastive loss, 128 pairs per step, data parallel
+# ------------------------------------------------------------------------------------------------------------
+def bench_train(args, dev, rank, world, peaks):
+    """One record per backward arithmetic: forward (train-mode BatchNorm over the GLOBAL batch), backward, per-block
+    gradient all-reduce overlapped with the rest of backward, Keras-Adam(clipnorm=1).  STRONG scaling: the global batch
+    of ``--train-pairs`` pairs (experiments/siamese_contrastive_loss.py:70,76-83 trains 64-pair batches; BASELINE
+    config[2] names 128) is split over the ranks, so N ranks x 128/N pairs compute the single-device step.  Device timed
+    (CUDA events around ``--train-steps`` steps, max over ranks); ``e2e`` feeds float32 numpy batches from host memory
+    through the pinned staging ring every step, as ``fit_generator`` does."""
+    import torch
+    import torch.distributed as dist
+    from voicemap_b200 import parallel
+    from voicemap_b200.keras_compat import Adam
+    from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
+    from voicemap_b200.training import TrainEngine
+    from voicemap_b200.utils import contrastive_loss
+
+    length, steps = args.length, max(args.train_steps, 1)
+    if args.train_pairs % world != 0:
+        return dict(skipped=f"{args.train_pairs} pairs do not split evenly over {world} ranks")
+    pairs = args.train_pairs // world
+    g = torch.Generator().manual_seed(4321 + rank)
+    x1h = (0.038021 * torch.randn(pairs, length, generator=g)).numpy()
+    x2h = (0.038021 * torch.randn(pairs, length, generator=g)).numpy()
+    x1, x2 = torch.from_numpy(x1h).to(dev), torch.from_numpy(x2h).to(dev)
+    y = np.concatenate([np.zeros(pairs // 2), np.ones(pairs - pairs // 2)]).astype(np.float32)
+    yd = torch.from_numpy(y).to(dev)
+    allreduce = parallel.allreduce_sum_ if world > 1 else None
+    flops_fwd = sum(b["flop"] for b in block_work(length)) * 2 * args.train_pairs      # whole job, all ranks
+    out = dict(metric="siamese_train_pairs_per_sec", unit="pairs/s", scaling="strong",
+               config=dict(workload=f"siamese encoder + contrastive loss train step (fwd, bwd, all-reduce, Adam), "
+                                    f"{args.train_pairs} pairs/step global = {pairs} pairs/GPU x {length} samples, "
+                                    f"filters={FILTERS}, emb={EMB}, train-mode BatchNorm synchronised over the ranks",
+                           parallelism=f"dp{world}: per-block gradient all-reduce (5 buckets, "
+                                       f"{(1023808 + 2) * 4 / 1e6:.1f} MB fp32 per step) overlapped with backward + 8 "
+                                       f"BatchNorm statistics all-reduces (<= 16 KB each)" if world > 1 else "dp1"),
+               modes={})
+    for name, bwd in (("bwd1", 1), ("bwd3", 3)):
+        enc = get_baseline_convolutional_encoder(FILTERS, EMB, dropout=0.0)
+        sia = build_siamese_net(enc, (length, 1))
+        parallel.broadcast_weights_(sia)
+        opt = Adam(clipnorm=1.0)
+        sia.compile(loss=contrastive_loss, optimizer=opt)
+        tr = TrainEngine(sia, opt, sia.loss, precision=3, bwd_precision=bwd)
+        tr.set_sync_bn(allreduce, world)
+        tr.set_gradient_buckets(world > 1)
+        for _ in range(3):
+            tr.siamese_step(x1, x2, yd, world=world)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            lv, _ = tr.siamese_step(x1, x2, yd, world=world)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+        # end to end: host numpy batches -> pinned staging -> H2D -> step -> loss read back, every step
+        for _ in range(2):
+            tr.siamese_step(x1h, x2h, y, world=world)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            lv, _ = tr.siamese_step(x1h, x2h, y, world=world)
+            loss_host = float(lv.item())
+        t_e2e = parallel.max_over_ranks((time.perf_counter() - t0) / steps * 1e3, dev)
+        launches = sum(1 for k, pl in tr._plans.items() for fn, _, _ in pl.ops if fn is not None) + 2   # + Adam (2 kernels)
+        out["modes"][name] = dict(
+            ms_per_step=round(ms, 4), value=round(args.train_pairs / (ms * 1e-3), 1),
+            audio_seconds_per_sec=round(args.train_pairs * 2 * CLIP_SECONDS / (ms * 1e-3), 1),
+            e2e=dict(ms_per_step=round(t_e2e, 4), value=round(args.train_pairs / (t_e2e * 1e-3), 1), unit="pairs/s",
+                     h2d_bytes_per_step=2 * pairs * length * 4 + pairs * 4, d2h_bytes_per_step=4),
+            backward={1: "one-plane fp16 gradients and operands, 1 MMA per MAC, per-block power-of-two scaling; "
+                         "gradient tolerance 2e-3 (tests/test_gpu_train.py)",
+                      3: "two-plane fp16 gradients and operands, 3 MMAs per MAC; gradient tolerance 5e-4"}[bwd],
+            forward="fp16 x 3 (train-mode loss within 1e-4 of the oracle)",
+            c_abi_calls_per_step=launches, final_loss=loss_host,
+            roofline=dict(bound="tensor", achieved=round(3 * flops_fwd / (ms * 1e-3) / 1e12 / world, 1),
+                          peak=peaks["bf16_tflops"], unit="TFLOP/s per GPU",
+                          frac=round(3 * flops_fwd / (ms * 1e-3) / 1e12 / world / peaks["bf16_tflops"], 4),
+                          note="ALGORITHMIC flops: 3 x forward (fwd + dgrad + wgrad) of 2 x pairs clips, counted once; "
+                               f"forward issues 3 MMAs per MAC, backward {bwd}"))
+        del tr, sia, enc
+        torch.cuda.empty_cache()
+    out.update(ms_per_step=out["modes"]["bwd1"]["ms_per_step"], value=out["modes"]["bwd1"]["value"], mode="bwd1",
+               n_gpus=world, steps=steps, nccl_bytes_per_step=(1023808 + 2) * 4 if world > 1 else 0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -339,8 +438,10 @@ def run_b200(args):
                            "voicemap/utils.py:29; SURVEY.md F3); rank 0's timing x n_gpus, informational")
         del xr, outr
 
+    peaks = load_peaks()
+    train = None if args.no_train else bench_train(args, dev, rank, world, peaks)
+
     if rank == 0:
-        peaks = load_peaks()
         work = block_work(length)
         conv3_ms = kern_ms["conv3_b2"] + kern_ms["conv3_b3"] + kern_ms["conv3_b4"]
         conv3_flop = sum(b["flop"] for b in work[1:]) * n
@@ -405,6 +506,7 @@ def run_b200(args):
             raw16k=raw16k,
             roofline=roofline,
             cpu_baseline=cpu_baseline,
+            train=train,
         )
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -200,12 +200,27 @@ def batchnorm_train(x, gamma, beta, eps=BN_EPS):
     return x * s + (beta - mean * s), mean, var
 
 
-def maxpool1d_valid(x, pool):
+def maxpool1d_valid(x, pool, select=None, slack=None):
     """keras MaxPool1D(pool, pool), padding 'valid': L_out = floor(L/pool), the
-    tail is dropped (voicemap/models.py:19,25,30,35)."""
+    tail is dropped (voicemap/models.py:19,25,30,35).
+    ``select`` (N, L, C) bool, optional: take the flagged element of every window (exactly one per window) instead of
+    the maximum.  Gradient tests pass the device's own arg-max pattern: where two values of a window agree to within
+    rounding, fp32 and fp64 legitimately pick different winners, and the gradient of the pool -- which lands on the
+    winner only -- would differ by a whole entry without either side being wrong.  ``slack`` (a list) receives
+    max((window maximum - selected value) / max|x|), so that a caller can check that every selection IS a maximum up
+    to rounding."""
     n, l, c = x.shape
     lo = l // pool
-    return x[:, :lo * pool, :].reshape(n, lo, pool, c).amax(dim=2)
+    win = x[:, :lo * pool, :].reshape(n, lo, pool, c)
+    if select is None:
+        return win.amax(dim=2)
+    sel = select[:, :lo * pool, :].reshape(n, lo, pool, c)
+    if not bool((sel.sum(dim=2) == 1).all()):
+        raise ValueError("maxpool1d_valid: `select` must flag exactly one element per window")
+    picked = (win * sel.to(win.dtype)).sum(dim=2)
+    if slack is not None:
+        slack.append(float(((win.amax(dim=2) - picked).max() / x.abs().max()).item()))
+    return picked
 
 
 POOLS = (4, 2, 2, 2)  # voicemap/models.py:19,25,30,35
@@ -349,10 +364,13 @@ def bn_moving_update(moving_mean, moving_var, mean, var, n, momentum=BN_MOMENTUM
             moving_var * momentum + var_unbiased * (1.0 - momentum))
 
 
-def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=None, relu_masks=None):
+def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=None, relu_masks=None, pool_selects=None,
+                                 gmax_select=None, slack=None):
     """Train-mode encoder on torch tensors (autograd-capable).  x (N, L, 1); P: dict name -> tensor.
     dropout_masks: optional list of 4 keep-masks (N, 1, C) already scaled by 1/(1-p) (SpatialDropout1D,
-    voicemap/models.py:18,24,29,34).  Returns emb and per-block (mean, var, count)."""
+    voicemap/models.py:18,24,29,34).  pool_selects: optional list of 4 bool arrays (N, L_b, C_b), the winner of every
+    MaxPool window (see maxpool1d_valid); gmax_select (N, C4) int, the winning window of GlobalMaxPool1D.  Returns emb
+    and per-block (mean, var, count)."""
     h = x
     stats = []
     for i in range(1, 5):
@@ -366,8 +384,13 @@ def _encoder_forward_train_torch(x, P, pools=POOLS, dropout_masks=None, keep=Non
         stats.append((m.detach(), v.detach(), n_red))
         if dropout_masks is not None and dropout_masks[i - 1] is not None:
             h = h * dropout_masks[i - 1]
-        h = maxpool1d_valid(h, pools[i - 1])
-    gmax = h.amax(dim=1)
+        h = maxpool1d_valid(h, pools[i - 1], None if pool_selects is None else pool_selects[i - 1], slack)
+    if gmax_select is None:
+        gmax = h.amax(dim=1)
+    else:
+        gmax = torch.gather(h, 1, gmax_select.to(torch.int64)[:, None, :])[:, 0, :]
+        if slack is not None:
+            slack.append(float(((h.amax(dim=1) - gmax).max() / h.abs().max()).item()))
     return gmax @ P["dense_kernel"] + P["dense_bias"], stats
 
 
@@ -376,19 +399,26 @@ TRAINABLE_SUFFIXES = ("kernel", "bias", "gamma", "beta")
 
 def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_crossentropy",
                              distance_metric="uniform_euclidean", dtype=torch.float64, dropout_masks=(None, None),
-                             relu_masks=(None, None)):
+                             relu_masks=(None, None), pool_selects=(None, None), gmax_selects=(None, None)):
     """One training-mode forward/backward of build_siamese_net (voicemap/models.py:49-79) with the loss of
     experiments/train_siamese.py:57 ('binary_crossentropy') or siamese_contrastive_loss.py:70 (contrastive_loss).
     The shared encoder is applied once per branch, so BN batch statistics are per branch.
+    pool_selects / gmax_selects: per branch, the device's own pool winners (see maxpool1d_valid); ``select_slack`` in
+    the result is how far any of them is from the true maximum, relative to the tensor's largest entry.
     Returns dict(loss, prob, grads {name: array}, head grads, stats [branch][block] -> (mean, var, n))."""
     P = {k: _t(v, dtype).clone().requires_grad_(any(k.endswith(s) for s in TRAINABLE_SUFFIXES))
          for k, v in params.items()}
     hw = _t(np.asarray(head_w, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
     hb = _t(np.asarray(head_b, dtype=np.float64).reshape(-1), dtype).clone().requires_grad_(True)
     k1, k2 = [], []
+    slack = []
     rm = [None if m is None else [_t(a, dtype) for a in m] for m in relu_masks]
-    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0], keep=k1, relu_masks=rm[0])
-    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1], keep=k2, relu_masks=rm[1])
+    ps = [None if m is None else [torch.as_tensor(np.asarray(a)).to(torch.bool) for a in m] for m in pool_selects]
+    gs = [None if m is None else torch.as_tensor(np.asarray(m)) for m in gmax_selects]
+    e1, s1 = _encoder_forward_train_torch(_t(x1, dtype), P, dropout_masks=dropout_masks[0], keep=k1, relu_masks=rm[0],
+                                          pool_selects=ps[0], gmax_select=gs[0], slack=slack)
+    e2, s2 = _encoder_forward_train_torch(_t(x2, dtype), P, dropout_masks=dropout_masks[1], keep=k2, relu_masks=rm[1],
+                                          pool_selects=ps[1], gmax_select=gs[1], slack=slack)
     diff = e1 - e2
     if distance_metric == "uniform_euclidean":
         d = torch.sqrt(torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=0.0))
@@ -411,13 +441,13 @@ def siamese_train_step_grads(params, head_w, head_b, x1, x2, y, loss="binary_cro
     return dict(loss=float(lv.item()), prob=p.detach().numpy(), grads=grads,
                 head_w_grad=hw.grad.numpy().copy(), head_b_grad=hb.grad.numpy().copy(),
                 stats=[[(m.numpy(), v.numpy(), n) for (m, v, n) in s] for s in (s1, s2)],
-                e1=e1.detach().numpy(), e2=e2.detach().numpy(),
+                e1=e1.detach().numpy(), e2=e2.detach().numpy(), select_slack=max(slack) if slack else 0.0,
                 u=[[h.detach().numpy() for h in k] for k in (k1, k2)],
                 du=[[h.grad.numpy().copy() for h in k] for k in (k1, k2)])
 
 
 def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dtype=torch.float64,
-                                dropout_masks=None, relu_masks=None):
+                                dropout_masks=None, relu_masks=None, pool_selects=None, gmax_select=None):
     """Encoder + Dense(num_classes, softmax) + categorical_crossentropy
     (experiments/train_classifier.py:110-115), training mode."""
     P = {k: _t(v, dtype).clone().requires_grad_(any(k.endswith(s) for s in TRAINABLE_SUFFIXES))
@@ -425,7 +455,11 @@ def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dty
     hk = _t(head_kernel, dtype).clone().requires_grad_(True)
     hb = _t(head_bias, dtype).clone().requires_grad_(True)
     rm = None if relu_masks is None else [_t(a, dtype) for a in relu_masks]
-    emb, stats = _encoder_forward_train_torch(_t(x, dtype), P, dropout_masks=dropout_masks, relu_masks=rm)
+    ps = None if pool_selects is None else [torch.as_tensor(np.asarray(a)).to(torch.bool) for a in pool_selects]
+    gs = None if gmax_select is None else torch.as_tensor(np.asarray(gmax_select))
+    slack = []
+    emb, stats = _encoder_forward_train_torch(_t(x, dtype), P, dropout_masks=dropout_masks, relu_masks=rm,
+                                              pool_selects=ps, gmax_select=gs, slack=slack)
     logits = emb @ hk + hb
     logp = torch.log_softmax(logits, dim=-1)
     lv = -(_t(y_onehot, dtype) * logp).sum(dim=-1).mean()
@@ -433,4 +467,5 @@ def classifier_train_step_grads(params, head_kernel, head_bias, x, y_onehot, dty
     grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad}
     return dict(loss=float(lv.item()), grads=grads, head_kernel_grad=hk.grad.numpy().copy(),
                 head_bias_grad=hb.grad.numpy().copy(), stats=[(m.numpy(), v.numpy(), n) for (m, v, n) in stats],
+                select_slack=max(slack) if slack else 0.0,
                 probs=torch.softmax(logits, dim=-1).detach().numpy())

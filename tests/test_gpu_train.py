@@ -23,6 +23,19 @@ def _grad_errors(grads, ref_grads):
             max(np.abs(g).max(), floor) for k, g in ref_grads.items()}
 
 
+def _patterns(tr, n, branches=2):
+    """The device's own discrete decisions of the last step, per branch, for the oracle: ReLU pattern, the winner of
+    every MaxPool window and the winning window of GlobalMaxPool1D.  Where two candidates agree to within rounding, fp32
+    and fp64 legitimately decide differently and the gradient -- which follows the winner -- differs by a whole entry
+    without either side being wrong; the oracle therefore differentiates along the device's decisions and reports
+    (``select_slack``) how far any of them is from a true maximum."""
+    rows = [slice(br * n, (br + 1) * n) for br in range(branches)]
+    relu = [[tr.relu_pattern(b)[r].cpu().numpy().astype(np.float64) for b in range(4)] for r in rows]
+    pool = [[tr.argmax_flags(b)[r].cpu().numpy() for b in range(4)] for r in rows]
+    gmax = [tr.jstar[r].cpu().numpy() for r in rows]
+    return relu, pool, gmax
+
+
 def _make(filters, emb, loss, metric="uniform_euclidean", seed=0, dropout=0.0, precision=3, bwd_precision=3):
     from voicemap_b200.keras_compat import Adam
     from voicemap_b200.models import build_siamese_net, get_baseline_convolutional_encoder
@@ -66,10 +79,11 @@ def test_siamese_step_forward_and_gradients(filters, emb, loss, metric, precisio
     hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
     lv, acc = tr.siamese_step(x1, x2, y, apply=False)
     torch.cuda.synchronize()
-    # the oracle takes the device's ReLU pattern (see conv1d_same_relu): branch 1 = rows [0, n), branch 2 = [n, 2n)
-    masks = [[tr.relu_pattern(b)[br * n:(br + 1) * n].cpu().numpy().astype(np.float64) for b in range(4)]
-             for br in range(2)]
-    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=loss, distance_metric=metric, relu_masks=masks)
+    # the oracle takes the device's discrete decisions (see _patterns): branch 1 = rows [0, n), branch 2 = [n, 2n)
+    masks, pool, gmax = _patterns(tr, n)
+    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=loss, distance_metric=metric, relu_masks=masks,
+                                     pool_selects=pool, gmax_selects=gmax)
+    assert ref["select_slack"] < 1e-5
     # train-mode forward
     emb_gpu = tr.embv.cpu().numpy()
     assert _rel(emb_gpu[:n], ref["e1"]) < 1e-4 and _rel(emb_gpu[n:], ref["e2"]) < 1e-4
@@ -163,9 +177,10 @@ def test_classifier_step_gradients():
     y = np.eye(classes, dtype=np.float32)[np.arange(n) % classes]
     lv, acc = tr.classifier_step(x, y, apply=False)
     torch.cuda.synchronize()
-    masks = [tr.relu_pattern(b).cpu().numpy().astype(np.float64) for b in range(4)]
+    masks, pool, gmax = _patterns(tr, n, branches=1)
     ref = O.classifier_train_step_grads(params, clf.weights["head_kernel"], clf.weights["head_bias"], x, y,
-                                        relu_masks=masks)
+                                        relu_masks=masks[0], pool_selects=pool[0], gmax_select=gmax[0])
+    assert ref["select_slack"] < 1e-5
     assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
     grads = tr.gradients()
     worst = _grad_errors(grads, dict(ref["grads"], head_kernel=ref["head_kernel_grad"], head_bias=ref["head_bias_grad"]))
@@ -188,9 +203,10 @@ def test_dropout_mask_semantics():
     hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
     lv, _ = tr.siamese_step(x1, x2, y, apply=False, masks=dm)
     torch.cuda.synchronize()
-    rmasks = [[tr.relu_pattern(b)[br * n:(br + 1) * n].cpu().numpy().astype(np.float64) for b in range(4)]
-              for br in range(2)]
-    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, dropout_masks=(om1, om2), relu_masks=rmasks)
+    rmasks, pool, gmax = _patterns(tr, n)
+    ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, dropout_masks=(om1, om2), relu_masks=rmasks,
+                                     pool_selects=pool, gmax_selects=gmax)
+    assert ref["select_slack"] < 1e-5
     assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
     assert max(_grad_errors(tr.gradients(), ref["grads"]).values()) < 2e-3
     assert tr._set_masks(8, None)
@@ -249,3 +265,47 @@ def test_sync_bn_split_path_equals_fused_path_on_one_rank():
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
     for k in out[0][2]:
         assert torch.equal(out[0][2][k], out[1][2][k]), k
+
+
+def test_train_step_at_baseline_shape_64_pairs_12000():
+    """BASELINE config[2]'s per-step shape on one GPU: 64 pairs (128 clips) x 12000 samples, filters 128, embedding 64,
+    contrastive loss (experiments/siamese_contrastive_loss.py:70,76-83) against the fp64 autograd oracle: train-mode
+    embeddings and loss at 1e-4, batch statistics, and every gradient tensor at the tolerance of its backward
+    arithmetic (GRAD_TOL).  Both backward modes share one oracle evaluation: they run the same forward pass, so the
+    discrete decisions handed to the oracle (ReLU pattern, pool winners) are the same (checked)."""
+    n, length, filters, emb = 64, 12000, 128, 64
+    x1 = O.synthetic_clips(n, length, seed=111)
+    x2 = O.synthetic_clips(n, length, seed=112)
+    y = (np.arange(n) >= n // 2).astype(np.float32)
+    ref, pattern = None, None
+    for bwd in (1, 3):
+        params, sia, tr = _make(filters, emb, "contrastive_loss", seed=7, bwd_precision=bwd)
+        hw, hb = sia.head_weights["head_kernel"].reshape(-1).copy(), sia.head_weights["head_bias"].copy()
+        lv, _ = tr.siamese_step(x1, x2, y, apply=False)
+        torch.cuda.synchronize()
+        masks, pool, gmax = _patterns(tr, n)
+        if ref is None:
+            pattern = (masks, pool, gmax)
+            ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss="contrastive_loss", relu_masks=masks,
+                                             pool_selects=pool, gmax_selects=gmax)
+            assert ref["select_slack"] < 1e-5      # every device winner is a maximum up to rounding
+        else:
+            for got, first in zip((masks, pool), pattern[:2]):
+                assert all(np.array_equal(a, b) for sa, sb in zip(got, first) for a, b in zip(sa, sb))
+            assert all(np.array_equal(a, b) for a, b in zip(gmax, pattern[2]))
+        emb_gpu = tr.embv.cpu().numpy()
+        assert _rel(emb_gpu[:n], ref["e1"]) < 1e-4 and _rel(emb_gpu[n:], ref["e2"]) < 1e-4
+        assert abs(lv.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+        for branch in range(2):
+            for b in range(4):
+                m, v, _ = ref["stats"][branch][b]
+                bnc = tr.bnc[b][branch].cpu().numpy()
+                assert _rel(bnc[:, 2], m) < 1e-4
+                assert _rel(1.0 / np.square(bnc[:, 3]) - O.BN_EPS, v) < 1e-3
+        refg = dict(ref["grads"], head_kernel=ref["head_w_grad"], head_bias=ref["head_b_grad"])
+        worst = _grad_errors(tr.gradients(), refg)
+        print(f"64 pairs x 12000, bwd_precision {bwd}: loss rel err {abs(lv.item() - ref['loss']) / abs(ref['loss']):.2e}",
+              {k: f"{v:.2e}" for k, v in worst.items()})
+        assert max(worst.values()) < GRAD_TOL[bwd], (bwd, worst)
+        del tr, sia
+        torch.cuda.empty_cache()

@@ -168,3 +168,37 @@ def test_keras_adam_step_matches_closed_form():
     lr_t = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
     expect = np.array([1.0, -2.0]) - lr_t * (0.1 * gc) / (np.sqrt(0.001 * gc ** 2) + 1e-7)
     np.testing.assert_allclose(p["w"], expect, rtol=1e-12)
+
+
+def test_pool_winner_selection_reproduces_the_plain_gradient():
+    """Gradient tests hand the device's pool winners to the oracle (maxpool1d_valid ``select``, GlobalMaxPool
+    ``gmax_select``).  With the oracle's OWN winners the selected forward/backward must equal the plain one, the slack
+    must be zero, and a selection that is not a maximum must show up in the slack."""
+    params = O.init_encoder_params(16, 8, seed=0, random_bias=True)
+    rng = np.random.default_rng(3)
+    for i in range(1, 5):
+        params[f"bn{i}_gamma"] = rng.uniform(-1.2, 1.5, params[f"bn{i}_gamma"].shape).astype(np.float32)
+    x1, x2 = O.synthetic_clips(2, 512, seed=1), O.synthetic_clips(2, 512, seed=2)
+    y = np.array([0.0, 1.0])
+    plain = O.siamese_train_step_grads(params, np.array([0.05]), np.array([-0.3]), x1, x2, y)
+    selects = []
+    for branch in range(2):
+        flags = []
+        for b, (u, pool) in enumerate(zip(plain["u"][branch], O.POOLS)):
+            lo = u.shape[1] // pool
+            win = u[:, :lo * pool].reshape(u.shape[0], lo, pool, -1)
+            pick = np.where(params[f"bn{b + 1}_gamma"][None, None, :] < 0, win.argmin(2), win.argmax(2))
+            f = np.zeros_like(win, dtype=bool)
+            np.put_along_axis(f, pick[:, :, None, :], True, 2)
+            full = np.zeros(u.shape, bool)
+            full[:, :lo * pool] = f.reshape(u.shape[0], lo * pool, -1)
+            flags.append(full)
+        selects.append(flags)
+    chosen = O.siamese_train_step_grads(params, np.array([0.05]), np.array([-0.3]), x1, x2, y, pool_selects=selects)
+    assert chosen["select_slack"] == 0.0 and abs(chosen["loss"] - plain["loss"]) < 1e-14
+    for k in plain["grads"]:
+        np.testing.assert_allclose(chosen["grads"][k], plain["grads"][k], rtol=0, atol=1e-13)
+    wrong = [[f.copy() for f in side] for side in selects]
+    wrong[0][0][:, :4, :] = np.roll(wrong[0][0][:, :4, :], 1, axis=1)       # first window of block 1: another element
+    moved = O.siamese_train_step_grads(params, np.array([0.05]), np.array([-0.3]), x1, x2, y, pool_selects=wrong)
+    assert moved["select_slack"] > 1e-3

@@ -34,6 +34,18 @@ def _worker(rank, world_size, port, out_dir):
     full = (data * (data @ w)[:, None]).sum(axis=0)
     p = {"w": w.copy()}
     O.keras_adam_step(p, {"w": flat.numpy() / 7.0}, {"w": np.zeros(5)}, {"w": np.zeros(5)}, t=1, clipnorm=1.0)
+    # bucketed asynchronous all-reduce of a flat buffer: same result as one all-reduce, buckets issued out of order
+    flat2 = torch.arange(10, dtype=torch.float64) * (rank + 1)
+    buckets = parallel.GradientBuckets(flat2, [(6, 10), (3, 6), (0, 3)])
+    for i in range(3):
+        buckets.launch(i)
+    buckets.wait()
+    assert torch.equal(flat2, torch.arange(10, dtype=torch.float64) * 3) and not buckets.works
+    try:
+        parallel.GradientBuckets(flat2, [(0, 3), (4, 10)])
+        raise AssertionError("a gap between buckets must be rejected")
+    except ValueError:
+        pass
     t_max = parallel.max_over_ranks(1.0 + rank)
     mean = parallel.global_mean(float(np.arange(lo, hi).sum()), hi - lo)
     rows = parallel.gather_rows(torch.full((hi - lo, 2), float(rank)))

@@ -49,7 +49,7 @@ def main():
         torch.cuda.synchronize()
         masks = [[tr.relu_pattern(b)[br * n:(br + 1) * n].cpu().numpy().astype(np.float64) for b in range(4)]
                  for br in range(2)]
-        ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=args.loss, relu_masks=masks)
+        ref = O.siamese_train_step_grads(params, hw, hb, x1, x2, y, loss=args.loss, relu_masks=masks, pool_selects=[[tr.argmax_flags(b)[br * n:(br + 1) * n].cpu().numpy() for b in range(4)] for br in range(2)], gmax_selects=[tr.jstar[br * n:(br + 1) * n].cpu().numpy() for br in range(2)])
         refg = dict(ref["grads"], head_kernel=ref["head_w_grad"], head_bias=ref["head_b_grad"])
         floor = 1e-3 * max(np.abs(np.asarray(g)).max() for g in refg.values())
         grads = tr.gradients()

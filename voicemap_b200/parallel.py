@@ -48,6 +48,35 @@ def allreduce_sum_(flat):
     return flat
 
 
+class GradientBuckets:
+    """The flat gradient buffer cut into contiguous buckets, each all-reduced (sum) as soon as the backward pass has
+    finished writing it, while the rest of the backward pass keeps running (one flat buffer,
+    overlapped with the tail of backward).  ``bounds`` = [(lo, hi), ...] element ranges in the order in which they become
+    complete (the encoder's blocks finish last-layer-first).  ``launch(i)`` issues bucket i asynchronously: with NCCL
+    the collective runs on the process group's own stream, ordered after everything already enqueued on the current
+    stream; ``wait()`` orders the current stream after all outstanding buckets (no host block with NCCL) -- call it
+    before the optimizer reads the buffer.  One process: both are no-ops."""
+
+    def __init__(self, flat, bounds):
+        self.flat = flat
+        self.bounds = [(int(lo), int(hi)) for lo, hi in bounds]
+        covered = sorted(self.bounds)
+        if covered[0][0] != 0 or covered[-1][1] != flat.numel() or any(a[1] != b[0] for a, b in zip(covered, covered[1:])):
+            raise ValueError("gradient buckets must tile the flat buffer exactly once")
+        self.views = [flat[lo:hi] for lo, hi in self.bounds]
+        self.works = []
+        self.bytes_per_step = flat.numel() * flat.element_size()
+
+    def launch(self, i):
+        if world()[1] > 1:
+            self.works.append(dist.all_reduce(self.views[i], op=dist.ReduceOp.SUM, async_op=True))
+
+    def wait(self):
+        for work in self.works:
+            work.wait()
+        self.works = []
+
+
 def broadcast_weights_(model, src=0):
     """Every rank takes rank ``src``'s weights (``model.get_weights()`` / ``set_weights``).  The reference's builders
     have no seed argument (voicemap/models.py:6,44), so independently launched ranks would start data-parallel

@@ -81,6 +81,7 @@ class TrainEngine:
         # the GLOBAL batch, as on the reference's single device; None = per-rank statistics
         self.sync_allreduce = None
         self.sync_world = 1
+        self.grad_buckets = None   # parallel.GradientBuckets: per-block asynchronous gradient all-reduce (data parallel)
         if isinstance(model, SiameseModel):
             self.kind = "siamese"
             self.encoder_model = model.encoder
@@ -310,6 +311,24 @@ class TrainEngine:
                     _ptr(self.p["dense_bias"]), self.emb, _ptr(self.embv), st)
         return plan
 
+    def bucket_bounds(self):
+        """Element ranges of the flat gradient buffer in the order the backward pass completes them: the embedding
+        Dense + head, then blocks 4, 3, 2, 1 (conv kernel, conv bias, BN gamma, BN beta are adjacent in Keras order)."""
+        first = {i: self.layout[f"conv{i}_kernel"][0] for i in range(1, 5)}
+        dense = self.layout["dense_kernel"][0]
+        return [(dense, self.nparams), (first[4], dense), (first[3], first[4]), (first[2], first[3]), (0, first[2])]
+
+    def set_gradient_buckets(self, enabled=True):
+        """Data parallel: all-reduce the gradient per block, as soon as that block's weight gradient is written, on the
+        process group's stream while the backward pass continues; ``siamese_step`` / ``classifier_step`` wait for the
+        buckets before the optimizer step.  Replaces the single all-reduce after backward (``allreduce=`` of the steps)."""
+        if enabled:
+            from .parallel import GradientBuckets
+            self.grad_buckets = GradientBuckets(self.grad, self.bucket_bounds())
+        else:
+            self.grad_buckets = None
+        self._plans = {k: v for k, v in self._plans.items() if k[0] != "bwd"}
+
     def set_sync_bn(self, allreduce, world):
         """allreduce(tensor): in-place SUM over ranks (torch.distributed.all_reduce); world: number of ranks, each
         feeding the same number of clips per step.  allreduce=None restores per-rank statistics."""
@@ -321,7 +340,7 @@ class TrainEngine:
         """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters."""
         if d_emb.data_ptr() != self.d_emb.data_ptr():
             self.d_emb.copy_(d_emb)
-        key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None,
+        key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None, self.grad_buckets is not None,
                torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
@@ -333,6 +352,9 @@ class TrainEngine:
         c, ls, g, groups = self.channels, self.ls, self.g, self.groups
         plan.launch(lib.vm_dense_bwd, "vm_dense_bwd", _ptr(self.gmax), _ptr(self.d_emb), _ptr(self.p["dense_kernel"]), nb,
                     c[3], self.emb, _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
+        buckets = self.grad_buckets
+        if buckets is not None:    # Dense + head gradients are complete (the head's were written before this plan)
+            plan.host(lambda: buckets.launch(0))
         bp = self.bwd_precision
         for b in (3, 2, 1, 0):
             n_u = nb * ls[b] * c[b]
@@ -368,12 +390,16 @@ class TrainEngine:
             if b == 0:
                 plan.launch(lib.vm_wgrad1, "vm_wgrad1", _ptr(self.xin), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp,
                             gabs, _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
+                if buckets is not None:
+                    plan.host(lambda: buckets.launch(4))
             else:
                 x_lo = self.XL[b - 1]
                 wp = bp if x_lo is not None else 1      # forward precision 1 keeps no second activation plane
                 plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.X[b - 1]), _ptr(x_lo), _ptr(du_hi),
                             _ptr(du_lo if wp == 3 else None), nb, ls[b], c[b - 1], c[b], wp, gabs, _ptr(self.wpart),
                             self.wpart.numel() * 4, _ptr(g[f"conv{b + 1}_kernel"]), st)
+                if buckets is not None:    # block b+1's gradients are complete: share them while dgrad and the
+                    plan.host(lambda i=4 - b: buckets.launch(i))   # blocks below keep the device busy
                 # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
                 plan.launch(lib.vm_conv3_dgrad, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
                             c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), gabs, _ptr(self.dX), bp, st)
@@ -448,12 +474,17 @@ class TrainEngine:
             plan = self._plans[key] = self._build_siamese_head_plan(n)
         plan.run()
         self.backward_encoder(self.d_emb)
-        if allreduce is not None:
-            allreduce(self.grad)
+        self._share_gradients(allreduce)
         if apply:
             self.apply_gradients(world)
         acc = ((self.prob.reshape(-1) > 0.5).to(torch.float32) == self.yin).to(torch.float32).mean()
         return self.lossv.clone().reshape(()), acc
+
+    def _share_gradients(self, allreduce):
+        if self.grad_buckets is not None:
+            self.grad_buckets.wait()          # issued per block inside the backward plan
+        elif allreduce is not None:
+            allreduce(self.grad)
 
     def _build_siamese_head_plan(self, n):
         lib, plan, st = self.lib, _Plan(), _stream()
@@ -487,8 +518,7 @@ class TrainEngine:
         self.g["head_bias"].copy_(dlogits.sum(dim=0))
         self.d_emb.copy_(dlogits @ hk.t())
         self.backward_encoder(self.d_emb)
-        if allreduce is not None:
-            allreduce(self.grad)
+        self._share_gradients(allreduce)
         if apply:
             self.apply_gradients(world)
         acc = (logits.argmax(dim=-1) == yt.argmax(dim=-1)).to(torch.float32).mean()
@@ -634,6 +664,7 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
     # BatchNorm sees the whole batch in the reference (one device); data-parallel ranks therefore share their batch
     # statistics unless the model opts out with ``model.sync_batchnorm = False``
     trainer.set_sync_bn(allreduce if getattr(model, "sync_batchnorm", True) else None, world)
+    trainer.set_gradient_buckets(world > 1)     # per-block asynchronous gradient all-reduce inside the backward pass
     callbacks = list(callbacks or [])
     for cb in callbacks:
         cb.set_model(model)
