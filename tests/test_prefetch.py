@@ -136,6 +136,9 @@ def test_fit_generator_uses_the_producers(monkeypatch):
         def set_sync_bn(self, allreduce, world):
             pass
 
+        def set_gradient_buckets(self, enabled=True):
+            pass
+
         def siamese_step(self, x1, x2, y, allreduce=None, world=1):
             _check(([x1, x2], y))
             steps.append(float(y[0, 0]))
