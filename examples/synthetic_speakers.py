@@ -11,6 +11,7 @@ class SyntheticCorpus:
     def __init__(self, n_speakers=40, files_per_speaker=6, seconds=(3.5, 5.0), subset="synthetic", seed=0):
         self.rng = np.random.default_rng(seed)
         self.voices = {}
+        self._cache = {}
         rows = []
         for s in range(n_speakers):
             f0 = self.rng.uniform(90, 260)
@@ -24,6 +25,14 @@ class SyntheticCorpus:
         self.index = pd.DataFrame(rows)
 
     def reader(self, path):
+        if path in self._cache:
+            return self._cache[path], RATE
+        audio, _ = self._synthesise(path)
+        if len(self._cache) < 4096:          # a few hundred MB at most: evaluation loops re-read the same files
+            self._cache[path] = audio
+        return audio, RATE
+
+    def _synthesise(self, path):
         _, _, spk, j, length = path.split("/")
         spk, j, length = int(spk), int(j), int(length)
         rng = np.random.default_rng(spk * 1000 + j)

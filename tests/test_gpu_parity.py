@@ -286,8 +286,8 @@ def test_predict_numpy_float64_is_staged_and_bit_identical(stress_params, monkey
 
 @pytest.mark.parametrize("precision", [2, 3])
 def test_full_batch_properties(stress_params, precision):
-    """BASELINE config[1] size (256 clips x 12000): batch-composition independence (bit-exact), permutation
-    equivariance, and spot parity of a few clips against the oracle."""
+    """BASELINE config[1] size (256 clips x 12000): every one of the 256 clips against the oracle at the north-star
+    tolerance, batch-composition independence (bit-exact), permutation equivariance, run-to-run determinism."""
     eng = _engine(128, 64, stress_params, precision)
     g = torch.Generator().manual_seed(5)
     x = (O.WHITEN_RMS * torch.randn(256, 12000, generator=g)).cuda()
@@ -297,9 +297,8 @@ def test_full_batch_properties(stress_params, precision):
     assert torch.equal(sub, full[100:108])                      # a clip's embedding does not depend on its batch
     perm = torch.randperm(256, generator=g).cuda()
     assert torch.equal(eng.forward(x[perm].contiguous()), full[perm])
-    idx = [0, 17, 255]
-    ref = O.encoder_forward(x[idx].cpu().numpy()[:, :, None], stress_params, torch.float32)
-    assert _per_clip(full[idx].cpu().numpy(), ref) <= TOL
+    ref = O.encoder_forward(x.cpu().numpy()[:, :, None], stress_params, torch.float32)      # all 256 clips
+    assert ref.shape == (256, 64) and _per_clip(full.cpu().numpy(), ref) <= TOL
     # 'same' zero padding: appending zeros after the global-max winner cannot lower any channel of the raw max;
     # the embedding of a clip equals the embedding of the same clip computed alone (already checked) and the
     # encoder is deterministic run to run
@@ -444,3 +443,51 @@ def test_large_batch_of_short_clips(stress_params, precision):
     ref = O.encoder_forward(x[idx].cpu().numpy()[:, :, None], stress_params, torch.float32)
     assert _per_clip(full[idx].cpu().numpy(), ref) <= TOL
     assert torch.equal(eng.forward(x[700:800].contiguous()), full[700:800])
+
+
+@pytest.mark.parametrize("distance", ["euclidean", "cosine", "dot_product"])
+@pytest.mark.parametrize("k,n,width", [(5, 1, 64), (5, 5, 64), (20, 5, 128), (3, 2, 33)])
+def test_nshot_scoring_on_device_equals_reference_rule(distance, k, n, width):
+    """vm_nshot_score (class means, distance, arg-min on the device) against the numpy statement of
+    voicemap/utils.py:156-212 (utils._SCORES), incl. an exact tie (first minimum wins, as np.argmin)."""
+    from voicemap_b200 import utils
+    rng = np.random.default_rng(k * 100 + n)
+    tasks = 37
+    query = rng.normal(size=(tasks, width)).astype(np.float32)
+    support = rng.normal(size=(tasks, k * n, width)).astype(np.float32)
+    support[0, n:2 * n] = support[0, :n]                      # task 0: classes 0 and 1 coincide and are nearest:
+    query[0] = support[0, :n].mean(axis=0)                    # an exact tie that the first class must win
+    best = utils.nshot_best_class_device(torch.from_numpy(query).cuda(),
+                                         torch.from_numpy(support.reshape(tasks * k * n, width)).cuda(), k, n, distance)
+    want = [int(np.argmin(utils._SCORES[distance](query[t].astype(np.float64), support[t].astype(np.float64), k, n)))
+            for t in range(tasks)]
+    assert best.cpu().tolist() == want
+    if distance != "dot_product":     # (a longer vector elsewhere can out-project the coinciding pair)
+        assert want[0] == 0
+
+
+@pytest.mark.parametrize("loss", ["contrastive_loss", "binary_crossentropy"])
+def test_siamese_probability_and_loss_at_config3_shape(stress_params, loss):
+    """BASELINE config[2]'s shape in eval mode: 128 pairs x 12000, filters 128 -- CUDA encoder (both branches as one
+    256-clip launch) -> fused head + loss kernel, against the fp64 oracle at |d| / |ref| <= 1e-4 for the probabilities
+    and the loss (voicemap/models.py:64-69, voicemap/utils.py:77-85)."""
+    from voicemap_b200.keras_compat import Adam
+    from voicemap_b200 import utils
+    pairs, length = 128, 12000
+    enc = M.get_baseline_convolutional_encoder(128, 64, dropout=0.0)
+    enc.set_named_weights(stress_params)
+    sia = M.build_siamese_net(enc, (length, 1))
+    x = O.synthetic_clips(2 * pairs, length, seed=77)
+    y = (np.arange(pairs) >= pairs // 2).astype(np.float64)[:, None]
+    ref_emb = O.encoder_forward(x, stress_params, torch.float64)
+    spread = float(np.median(np.linalg.norm(ref_emb[:pairs] - ref_emb[pairs:], axis=1)))
+    w, b = np.array([[2.0 / spread]], np.float32), np.array([-1.5], np.float32)     # un-saturated sigmoid
+    sia.set_weights(enc.get_weights() + [w, b])
+    ref_prob, _ = O.siamese_head(ref_emb[:pairs], ref_emb[pairs:], float(w[0, 0]), float(b[0]))
+    assert 0.02 < ref_prob.min() and ref_prob.max() < 0.98
+    prob = sia.predict([x[:pairs], x[pairs:]])
+    assert np.abs(prob - ref_prob).max() <= 1e-4 * np.abs(ref_prob).max()
+    sia.compile(loss=utils.contrastive_loss if loss == "contrastive_loss" else loss, optimizer=Adam())
+    got = sia.test_on_batch([x[:pairs], x[pairs:]], y)
+    want = O.contrastive_loss(y, ref_prob) if loss == "contrastive_loss" else O.binary_crossentropy(y, ref_prob)
+    assert abs(got - float(want)) <= 1e-4 * abs(float(want)), (got, float(want))
