@@ -29,6 +29,7 @@ class SyntheticCorpus:
             return self._cache[path], RATE
         audio, _ = self._synthesise(path)
         if len(self._cache) < 4096:          # a few hundred MB at most: evaluation loops re-read the same files
+            audio.setflags(write=False)      # shared between readers from now on
             self._cache[path] = audio
         return audio, RATE
 

@@ -160,6 +160,12 @@ int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout,
 int vm_pack_conv3_dgrad(const float* kernel /* (3, Cin, Cout) */, int cin, int cout, void* wpack, float* epi,
                         void* stream);
 
+/* The three calls above for all four blocks in ONE launch (the weights change once per training step): kernels[4],
+ * biases[4] in Keras layout for blocks 1-4 with Cout = filters * (1, 2, 3, 4); wraw[4] / eraw[4] receive the "raw"
+ * forward operands, wdg[4] / edg[4] (entries 1-3 used; entry 0 ignored) the dgrad operands. */
+int vm_pack_train(const float* const* kernels, const float* const* biases, int filters, void* const* wraw,
+                  float* const* eraw, void* const* wdg, float* const* edg, void* stream);
+
 /* Train-mode conv forward of one block: u = relu(conv(x) + bias) at every position, of which the call keeps
  *   u16 (N, L, Cout)       16 bits per element: fp16(u) in bits 0-14, bit 15 = "arg-max of its MaxPool window" (first
  *                          winner on ties; the arg-MIN of u where gamma[c] < 0, i.e. the arg-max after BatchNorm);
@@ -200,10 +206,11 @@ int vm_bn_gmax_fwd(const float* ext, int N, int Lout, int C, int G, const float*
                    float* gmax, int32_t* jstar, void* stream);
 int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, int E, float* y, void* stream);
 
-/* Backward of the siamese head + loss (emb (2N, E): branch 1 rows then branch 2 rows). */
+/* Backward of the siamese head + loss (emb (2N, E): branch 1 rows then branch 2 rows).  accuracy (1 float, optional):
+ * keras' 'accuracy' metric of the batch, mean(round(p) == y). */
 int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                           const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
-                          float* d_head_b, void* stream);
+                          float* d_head_b, float* accuracy, void* stream);
 int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
                  void* stream);
 /* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax (N, C) + jstar

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--bwd-precision", type=int, default=3)
     ap.add_argument("--local-bn", action="store_true", help="per-rank BatchNorm statistics instead of synchronised")
+    ap.add_argument("--timeline", action="store_true", help="print live per-launch durations of a step (one rank)")
     args = ap.parse_args()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -74,6 +75,12 @@ def main():
         tr.siamese_step(x1, x2, y, allreduce=allreduce, world=world)
     t_host = (time.perf_counter() - t_host) / 4 * 1e3
     torch.cuda.synchronize()
+    if args.timeline and world == 1:
+        total = 0.0
+        for what, t in tr.time_siamese_step(x1, x2, y):
+            total += t
+            print(f"{t * 1e3:9.1f} us  {what}")
+        print(f"{total * 1e3:9.1f} us  sum (events between launches; step above {ms * 1e3:.1f} us)")
     if rank == 0:
         print(json.dumps(dict(metric="siamese_train_pairs_per_sec", value=round(world * pairs / (ms * 1e-3), 1),
                               unit="pairs/s", audio_seconds_per_sec=round(world * pairs * 2 * 3.0 / (ms * 1e-3), 1),
@@ -81,7 +88,7 @@ def main():
                               args.pairs_per_gpu is None else "weak",
                               config=dict(workload=f"siamese train step (fwd+bwd+Adam), contrastive loss, "
                                                    f"{pairs} pairs/GPU x {args.length} samples, filters={args.filters}, "
-                                                   f"fwd fp16x3, bwd bf16x{args.bwd_precision}",
+                                                   f"fwd fp16x3, bwd fp16 mode {args.bwd_precision}",
                                           parallelism=f"dp{world}, one flat fp32 gradient all-reduce "
                                                       f"({tr.nparams * 4 / 1e6:.1f} MB) per step, BatchNorm "
                                                       f"{'per rank' if (args.local_bn or world == 1) else 'synchronised (8 small all-reduces)'}"),

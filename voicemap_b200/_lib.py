@@ -55,6 +55,8 @@ SIGNATURES = {
     "vm_pack_conv1_raw": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "vm_pack_conv3_raw": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "vm_pack_conv3_dgrad": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "vm_pack_train": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                           C.POINTER(_vp), _vp]),
     "vm_conv1_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -64,7 +66,7 @@ SIGNATURES = {
     "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_gmax_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd_scratch_elems": (_sz, [_i]),
     "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

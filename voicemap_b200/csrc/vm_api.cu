@@ -218,6 +218,10 @@ int vm_pack_conv3_raw(const float* kernel, const float* bias, int cin, int cout,
 int vm_pack_conv3_dgrad(const float* kernel, int cin, int cout, void* wpack, float* epi, void* stream) {
   return launch_pack_conv3_dgrad(kernel, cin, cout, wpack, epi, ST);
 }
+int vm_pack_train(const float* const* kernels, const float* const* biases, int filters, void* const* wraw,
+                  float* const* eraw, void* const* wdg, float* const* edg, void* stream) {
+  return launch_pack_train(kernels, biases, filters, wraw, eraw, wdg, edg, ST);
+}
 int vm_stat_rows_per_clip(int L) { return 2 * ((L + 255) / 256); }
 size_t vm_reduce_scratch_bytes(int G, int C) { return size_t(G > 0 ? G : 1) * 32 * size_t(C) * 16; }
 
@@ -272,9 +276,9 @@ int vm_dense_fwd(const float* x, int N, int C, const float* w, const float* b, i
 }
 int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                           const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
-                          float* d_head_b, void* stream) {
+                          float* d_head_b, float* accuracy, void* stream) {
   return launch_pair_head_loss_bwd(emb, N, E, metric, head_w, head_b, y_true, loss_kind, loss_scale, d_emb, d_head_w,
-                                   d_head_b, ST);
+                                   d_head_b, accuracy, ST);
 }
 int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
                  void* stream) {

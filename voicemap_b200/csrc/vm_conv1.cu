@@ -322,6 +322,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
     const int ch = q * 32 + lane;
     uint8_t* ob = outbuf + grp * kOutBufBytes;
     const int buf = grp;
+    uint32_t t_gcount = 0;   // train-mode forward: granules staged so far by this group (selects the staging half)
     // this group's accumulators are ait = grp, grp + 2, ...; (tile, slab, n, p0) advance incrementally
     const int dn = int(gridDim.x) / p.nptile, dpt = int(gridDim.x) % p.nptile;
     int tile = blockIdx.x, n = tile / p.nptile, pt = tile % p.nptile, slab = grp;
@@ -339,71 +340,101 @@ conv1_kernel(const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ 
         if (p.out_u16 != nullptr) {
           // train-mode forward: per position u = relu(acc + bias) -> {sum, sum of squares} partials for the batch
           // statistics, the encoded un-pooled activation (fp16 + arg-max flag, encode_u) and the fp32 extreme of every
-          // MaxPool(kPool) window (max, or min where the BatchNorm scale is negative).  Granule = 64 positions x 128
-          // channels = the group's staging buffer: [u16: 2 boxes of 64 pos x 64 ch][extremes: 4 boxes of 64/kPool
-          // windows x 32 ch fp32]; the two warps of a lane quarter take 32 columns each.
+          // MaxPool(kPool) window (max, or min where the BatchNorm scale is negative).  Granule = 32 positions x 128
+          // channels; the group's staging buffer is used as two halves of 16 KB, each
+          // [u16: 2 boxes of 32 pos x 64 ch][extremes: 4 boxes of 32/kPool windows x 32 ch fp32], so that the TMA
+          // store of one granule drains while the next one is computed: ONE named barrier per granule (before it the
+          // leader waits for the store issued a granule earlier, i.e. for the half that is written next).  The two
+          // warps of a lane quarter take 16 columns each; TMEM loads are software-pipelined.
           if (wg == 0) mbar_wait(&bars->tfull[buf], it & 1);  // one polling warp per group; the rest block in bar.sync
-          constexpr int kWin = 32 / kPool;                     // windows per warp and granule
-          constexpr int kExtRows = 64 / kPool;
+          named_bar_sync(bar_id, 256);
+          tc_fence_after_sync();
+          constexpr int kWin = 16 / kPool;                     // windows per warp and granule
+          constexpr int kExtBox = (32 / kPool) * 128;          // bytes of one extremes box
           const bool neg = (p.sign_src != nullptr && co < p.cout) ? (p.sign_src[co] < 0.f) : false;
+          const uint32_t sgn = neg ? 0x80000000u : 0u;         // compare -u where the minimum is wanted (u >= 0)
           const int lvalid = p.lout * kPool;
+          const bool interior = (p0 + kTileN <= p.L) && (p0 + kTileN <= lvalid);
           float s1 = 0.f, s2 = 0.f;
-          const uint32_t st_u = smem_u32(ob) + (ch >> 6) * kOutBoxBytes + (chalf * 32) * 128 + (ch & 63) * 2;
-          const uint32_t st_m = smem_u32(ob) + 2 * kOutBoxBytes + (ch >> 5) * (kExtRows * 128) + (chalf * kWin) * 128 +
-                                (ch & 31) * 4;
-#pragma unroll 1
-          for (int gr = 0; gr < kTileN / 64; ++gr) {
-            if (leader) tma_store_wait_read<0>();
-            named_bar_sync(bar_id, 256);
-            tc_fence_after_sync();
-            float v[32];
-            tmem_ld_32x32(taddr + gr * 64 + chalf * 32, v);
-            if (gr == kTileN / 64 - 1) {
-              tc_fence_before_sync();
-              mbar_arrive(&bars->tempty[buf]);
-            }
-            const int pos0 = p0 + gr * 64 + chalf * 32;
+          const uint32_t off_u = (ch >> 6) * 4096 + (chalf * 16) * 128 + (ch & 63) * 2;
+          const uint32_t off_m = 8192 + (ch >> 5) * kExtBox + (chalf * kWin) * 128 + (ch & 31) * 4;
+          auto granule = [&](const uint32_t (&r)[16], int gr, auto interior_tag) {
+            constexpr bool kInterior = decltype(interior_tag)::value;
+            const uint32_t st = smem_u32(ob) + (t_gcount & 1) * 16384;
+            const int pos0 = p0 + gr * 32 + chalf * 16;
 #pragma unroll
             for (int w = 0; w < kWin; ++w) {
               float y[kPool];
-              int best = 0;
 #pragma unroll
               for (int i = 0; i < kPool; ++i) {
-                y[i] = apply_epi(ep, v[kPool * w + i]);
-                if (pos0 + kPool * w + i < p.L) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
+                y[i] = apply_epi(ep, __uint_as_float(r[kPool * w + i]));
+                if (kInterior || pos0 + kPool * w + i < p.L) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
               }
-              float ext = y[0];
+              // winner of the window, first on ties: a chain of strict comparisons on the (sign-adjusted) values
+              bool later[kPool];
+              float best = __uint_as_float(__float_as_uint(y[0]) ^ sgn), ext = y[0];
 #pragma unroll
-              for (int i = 1; i < kPool; ++i)
-                if (neg ? (y[i] < ext) : (y[i] > ext)) { ext = y[i]; best = i; }   // first winner on ties
-              const bool win = pos0 + kPool * w + kPool - 1 < lvalid;              // 'valid' pooling drops the tail
+              for (int i = 1; i < kPool; ++i) {
+                const float key = __uint_as_float(__float_as_uint(y[i]) ^ sgn);
+                later[i] = key > best;
+                best = later[i] ? key : best;
+                ext = later[i] ? y[i] : ext;
+              }
+              const bool win = kInterior || (pos0 + kPool * w + kPool - 1 < lvalid);   // 'valid' pooling drops the tail
 #pragma unroll
-              for (int i = 0; i < kPool; ++i)
-                sts_b16(st_u + (kPool * w + i) * 128, encode_u(y[i], win && best == i));
-              sts_f32(st_m + w * 128, ext);
+              for (int i = 0; i < kPool; ++i) {
+                bool flag = (i == 0) ? true : later[i];
+#pragma unroll
+                for (int k = i + 1; k < kPool; ++k) flag = flag && !later[k];
+                sts_b16(st + off_u + (kPool * w + i) * 128, encode_u(y[i], flag && win));
+              }
+              sts_f32(st + off_m + w * 128, ext);
             }
             fence_proxy_async_smem();
+            if (leader) tma_store_wait_read<0>();   // the store of the previous granule (other half) has drained
             named_bar_sync(bar_id, 256);
             if (leader) {
-              const int pos = p0 + gr * 64;
+              const uint8_t* sb = ob + (t_gcount & 1) * 16384;
+              const int pos = p0 + gr * 32;
               if (pos < p.L) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                   const int c0 = slab * kTileM + half * 64;
-                  if (c0 < p.cout) tma_store_3d(&tm_oh, ob + half * kOutBoxBytes, c0, pos, n);
+                  if (c0 < p.cout) tma_store_3d(&tm_oh, sb + half * 4096, c0, pos, n);
                 }
                 if (pos / kPool < p.lout) {
 #pragma unroll
                   for (int b4 = 0; b4 < 4; ++b4) {
                     const int c0 = slab * kTileM + b4 * 32;
-                    if (c0 < p.cout)
-                      tma_store_3d(&tm_ol, ob + 2 * kOutBoxBytes + b4 * (kExtRows * 128), c0, pos / kPool, n);
+                    if (c0 < p.cout) tma_store_3d(&tm_ol, sb + 8192 + b4 * kExtBox, c0, pos / kPool, n);
                   }
                 }
               }
               tma_store_commit();
             }
-          }
+            ++t_gcount;
+          };
+          auto tile_loop = [&](auto interior_tag) {
+            uint32_t ra[16], rb[16];
+            const uint32_t tcol = taddr + chalf * 16;
+            tmem_ld_32x16_issue(tcol, ra);
+#pragma unroll 1
+            for (int gr = 0; gr < kTileN / 32; gr += 2) {
+              tmem_ld_wait(ra);
+              tmem_ld_32x16_issue(tcol + (gr + 1) * 32, rb);
+              granule(ra, gr, interior_tag);
+              tmem_ld_wait(rb);
+              if (gr + 2 < kTileN / 32) {
+                tmem_ld_32x16_issue(tcol + (gr + 2) * 32, ra);
+              } else {  // all TMEM reads of this accumulator are done
+                tc_fence_before_sync();
+                mbar_arrive(&bars->tempty[buf]);
+              }
+              granule(rb, gr + 1, interior_tag);
+            }
+          };
+          if (interior) tile_loop(std::true_type{});
+          else tile_loop(std::false_type{});
           if (p.stat_partial != nullptr)
             p.stat_partial[(size_t(tile) * 2 + chalf) * p.cout_pad + co] = make_float2(s1, s2);
         } else {
@@ -520,10 +551,10 @@ int launch_conv1(const float* x, int N, int L, int cout, const void* wpack, cons
   if (out_u16 != nullptr) {
     const uint64_t udims[3] = {uint64_t(cout), uint64_t(L), uint64_t(N)};
     const uint64_t ustr[2] = {uint64_t(cout) * 2, uint64_t(L) * cout * 2};
-    const uint32_t ubox[3] = {64, 64, 1};
+    const uint32_t ubox[3] = {64, 32, 1};
     const uint64_t mdims[3] = {uint64_t(cout), uint64_t(p.lout), uint64_t(N)};
     const uint64_t mstr[2] = {uint64_t(cout) * 4, uint64_t(p.lout) * cout * 4};
-    const uint32_t mbox[3] = {32, uint32_t(64 / pool), 1};
+    const uint32_t mbox[3] = {32, uint32_t(32 / pool), 1};
     int rc;
     if ((rc = make_tensor_map(&oh, out_u16, 3, udims, ustr, ubox, VM_SWIZZLE_NONE))) return rc;
     if ((rc = make_tensor_map(&ol, out_ext, 3, mdims, mstr, mbox, VM_SWIZZLE_NONE, /*f32=*/1))) return rc;

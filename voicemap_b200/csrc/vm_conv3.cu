@@ -177,6 +177,40 @@ __device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t t
   }
 }
 
+// fp32 epilogue of one accumulator tile for one warp (dgrad): granule = 16 positions x 128 channels fp32 = 4 boxes of
+// 32 channels, pipelined TMEM loads, staging buffers handed to the store warp (see raw2_tile).
+__device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8_t* stage, int ch, int chalf,
+                                            Conv3Barriers* bars, int buf, uint32_t& gcount) {
+  using namespace c3;
+  const uint32_t off = (ch >> 5) * 2048 + (chalf * 8) * 128 + (ch & 31) * 4;
+  auto granule = [&](const uint32_t (&r)[8]) {
+    const int sb = gcount & 1;
+    const uint32_t st = smem_u32(stage + sb * kStageBufBytes) + off;
+    if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts_f32(st + j * 128, __uint_as_float(r[j]) * unscale);
+    fence_proxy_async_smem();
+    mbar_arrive(&bars->sfull[sb]);
+    ++gcount;
+  };
+  uint32_t ra[8], rb[8];
+  tmem_ld_32x8_issue(taddr + chalf * 8, ra);
+#pragma unroll 1
+  for (int gr = 0; gr < kTileN / 16; gr += 2) {
+    tmem_ld_wait(ra);
+    tmem_ld_32x8_issue(taddr + (gr + 1) * 16 + chalf * 8, rb);
+    granule(ra);
+    tmem_ld_wait(rb);
+    if (gr + 2 < kTileN / 16) {
+      tmem_ld_32x8_issue(taddr + (gr + 2) * 16 + chalf * 8, ra);
+    } else {
+      tc_fence_before_sync();
+      mbar_arrive(&bars->tempty[buf]);
+    }
+    granule(rb);
+  }
+}
+
 __global__ void __launch_bounds__(c3::kThreads, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
@@ -375,6 +409,33 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         }
       }
       tma_store_wait_all<0>();
+    } else if (lane == 0 && p.out_f32 != nullptr) {
+      // dgrad: 16 granules per tile, each 4 boxes of 16 positions x 32 channels fp32
+      uint32_t g = 0;
+      for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
+        const int tile = ti.tile();
+        const int slab = tile % p.nslab;
+        const int pt_lin = tile / p.nslab;
+        const int n = pt_lin / p.nptile;
+        const int p0 = (pt_lin % p.nptile) * kTileN;
+        for (int gr = 0; gr < kTileN / 16; ++gr, ++g) {
+          const int b = g & 1;
+          mbar_wait(&bars->sfull[b], (g >> 1) & 1);
+          const uint8_t* sbuf = stage + b * kStageBufBytes;
+          const int pos = p0 + gr * 16;
+          if (pos < p.L) {
+#pragma unroll
+            for (int b4 = 0; b4 < 4; ++b4) {
+              const int c0 = slab * kTileM + b4 * 32;
+              if (c0 < p.cout) tma_store_3d(&tm_oh, sbuf + b4 * 2048, c0, pos, n);
+            }
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&bars->sempty[b]);
+        }
+      }
+      tma_store_wait_all<0>();
     } else if (lane == 0 && p.gmax_partial == nullptr && p.out_f32 == nullptr) {
       uint32_t g = 0;
       for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next()) {
@@ -461,47 +522,11 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         // the two column halves keep separate partial rows: (N, 2*nptile, cout_pad), raw accumulator maxima
         p.gmax_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = m;
       } else if (p.out_f32 != nullptr) {
-        // un-pooled fp32 output (train-mode forward: u = relu(acc + bias) with per-channel sum / sum-of-squares
-        // partials; dgrad: y = acc).  Granule = 16 positions x 128 channels fp32 (4 TMA boxes of 32 channels);
-        // the two warps of a lane quarter take 8 columns each.
-        float s1 = 0.f, s2 = 0.f;
-        // dgrad: the incoming gradient planes carry a power-of-two scale (vm_common.cuh); undo it here
-        const float unscale = (p.linear && p.grad_absmax != nullptr)
+        // plain fp32 output of the accumulator (dgrad: dX = conv3(dU, flipped / transposed weights)); the incoming
+        // gradient planes carry a power-of-two scale (vm_common.cuh), taken out here
+        const float unscale = (p.grad_absmax != nullptr)
                                   ? 1.0f / grad_scale_from_absmax(__uint_as_float(*p.grad_absmax)) : 1.0f;
-#pragma unroll 1
-        for (int gr = 0; gr < kTileN / 16; ++gr, ++gcount) {
-          uint8_t* sbuf = stage + (gcount & 1) * kStageBufBytes;
-          const uint32_t st = smem_u32(sbuf) + (ch >> 5) * 2048 + (ch & 31) * 4 + chalf * 8 * 128;
-          float v[8];
-          tmem_ld_32x8(taddr + gr * 16 + chalf * 8, v);
-          if (gr == kTileN / 16 - 1) {
-            tc_fence_before_sync();
-            mbar_arrive(&bars->tempty[buf]);
-          }
-          const int pos0 = p0 + gr * 16 + chalf * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y = p.linear ? v[j] * unscale : apply_epi(ep, v[j]);
-            if (pos0 + j < p.L) { s1 += y; s2 = fmaf(y, y, s2); }
-            sts_f32(st + j * 128, y);
-          }
-          fence_proxy_async_smem();
-          if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, kEpiWarps * 32);
-          if (leader) {
-            const int pos = p0 + gr * 16;
-            if (pos < p.L) {
-#pragma unroll
-              for (int b4 = 0; b4 < 4; ++b4) {
-                const int c0 = slab * kTileM + b4 * 32;
-                if (c0 < p.cout) tma_store_3d(&tm_oh, sbuf + b4 * 2048, c0, pos, n);
-              }
-            }
-            tma_store_commit();
-          }
-        }
-        if (p.stat_partial != nullptr)
-          p.stat_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+        linear_tile(unscale, taddr, stage, ch, chalf, bars, buf, gcount);
       } else {
         // pooled outputs: granule = 16 pooled positions x 128 channels x 2 planes; the two warps of a lane quarter
         // take 16 raw columns (8 pooled positions) each.

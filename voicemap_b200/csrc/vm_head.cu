@@ -31,12 +31,12 @@ __device__ __forceinline__ float4 epi_relu_only(float bias) { return make_float4
 // conv3 weights: w (3, cin, cout) fp32 -> wpack [plane][tap][cout_pad][cin], 16 bits per entry; planes: fp16 hi, fp16 lo,
 // e5m2x2 Q (split_w_q: the operand of the single-MMA correction product of precision 2)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cin,
-                                  int cout, int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
+__device__ __forceinline__ void pack_conv3_body(size_t idx, const float* __restrict__ w, const float* __restrict__ bias,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ mean, const float* __restrict__ var,
+                                                float eps, int cin, int cout, int cout_pad,
+                                                __half* __restrict__ wpack, float4* __restrict__ epi) {
   const size_t total = size_t(3) * cout_pad * cin;
-  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx < size_t(cout_pad)) {
     const int co = int(idx);
     if (co >= cout) epi[co] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -61,16 +61,23 @@ __global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __re
   split_w_q(v, h, q);
   wpack[2 * total + idx] = __ushort_as_half(q);
 }
+__global__ void pack_conv3_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cin,
+                                  int cout, int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
+  pack_conv3_body(size_t(blockIdx.x) * blockDim.x + threadIdx.x, w, bias, gamma, beta, mean, var, eps, cin, cout,
+                  cout_pad, wpack, epi);
+}
 
 // ---------------------------------------------------------------------------------------------
 // conv1 weights: w (32, 1, cout) fp32 -> [slab][plane] 8 KB smem images (no-swizzle K-major core matrices:
 // byte offset of (row, tap) = (row/8)*512 + (tap/8)*128 + (row%8)*16 + (tap%8)*2)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
-                                  int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_conv1_body(int idx, const float* __restrict__ w, const float* __restrict__ bias,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ mean, const float* __restrict__ var,
+                                                float eps, int cout, int cout_pad, __half* __restrict__ wpack,
+                                                float4* __restrict__ epi) {
   if (idx < cout_pad) {
     if (idx >= cout) epi[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     else if (gamma == nullptr) epi[idx] = epi_relu_only(bias ? bias[idx] : 0.f);
@@ -93,16 +100,23 @@ __global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __re
   img[off] = h;
   img[4096 + off] = l;
 }
+__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout,
+                                  int cout_pad, __half* __restrict__ wpack, float4* __restrict__ epi) {
+  pack_conv1_body(blockIdx.x * blockDim.x + threadIdx.x, w, bias, gamma, beta, mean, var, eps, cout, cout_pad, wpack,
+                  epi);
+}
 
 // ---------------------------------------------------------------------------------------------
 // dgrad weights: dX[p][ci] = sum_t sum_co dU[p + t - 1][co] * W[2 - t][ci][co] is a k=3 'same' convolution of dU with
 // the tap-flipped, channel-transposed kernel.  w (3, cin, cout) -> wpack [plane][tap][cin_pad][cout] fp16, i.e. the
 // conv3 operand layout with the roles (cin' = cout, cout' = cin), as fp16 (hi, lo) planes.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad,
-                                        __half* __restrict__ wpack, float4* __restrict__ epi) {
+__device__ __forceinline__ void pack_conv3_dgrad_body(size_t idx, const float* __restrict__ w, int cin, int cout,
+                                                      int cin_pad, __half* __restrict__ wpack,
+                                                      float4* __restrict__ epi) {
   const size_t total = size_t(3) * cin_pad * cout;
-  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx < size_t(cin_pad)) epi[idx] = make_float4(0.f, 0.f, 0.f, 0.f);  // unused (linear epilogue)
   if (idx >= total) return;
   const int co = int(idx % cout);
@@ -113,6 +127,30 @@ __global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, in
   split_f32(v, h, l);
   wpack[idx] = h;
   wpack[total + idx] = l;
+}
+__global__ void pack_conv3_dgrad_kernel(const float* __restrict__ w, int cin, int cout, int cin_pad,
+                                        __half* __restrict__ wpack, float4* __restrict__ epi) {
+  pack_conv3_dgrad_body(size_t(blockIdx.x) * blockDim.x + threadIdx.x, w, cin, cout, cin_pad, wpack, epi);
+}
+
+// All operand packing of a training step in ONE launch (weights change once per step): block ranges select the task.
+__global__ void pack_train_kernel(const PackTrainArgs a) {
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < 7; ++i)
+    if (i < a.ntasks && blockIdx.x >= a.t[i].block0) t = i;
+  const PackTrainTask& k = a.t[t];
+  const size_t idx = size_t(blockIdx.x - k.block0) * blockDim.x + threadIdx.x;
+  if (k.kind == 0) {
+    pack_conv1_body(int(idx), k.w, k.bias, nullptr, nullptr, nullptr, nullptr, 0.f, k.cout, k.pad,
+                    static_cast<__half*>(k.wpack), reinterpret_cast<float4*>(k.epi));
+  } else if (k.kind == 1) {
+    pack_conv3_body(idx, k.w, k.bias, nullptr, nullptr, nullptr, nullptr, 0.f, k.cin, k.cout, k.pad,
+                    static_cast<__half*>(k.wpack), reinterpret_cast<float4*>(k.epi));
+  } else {
+    pack_conv3_dgrad_body(idx, k.w, k.cin, k.cout, k.pad, static_cast<__half*>(k.wpack),
+                          reinterpret_cast<float4*>(k.epi));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,6 +504,35 @@ int launch_nshot_score(const float* query, const float* support, int T, int k, i
   if (query == nullptr || support == nullptr || best == nullptr) return set_error(VM_ERR_SHAPE, "nshot_score: null pointer");
   nshot_score_kernel<<<T, 128, k * sizeof(double), stream>>>(query, support, T, k, n, E, distance, scores, best);
   return check_launch("nshot_score");
+}
+
+int launch_pack_train(const float* const* kernels, const float* const* biases, int filters, void* const* wraw,
+                      float* const* eraw, void* const* wdg, float* const* edg, cudaStream_t stream) {
+  if (filters <= 0 || kernels == nullptr || biases == nullptr || wraw == nullptr || eraw == nullptr || wdg == nullptr ||
+      edg == nullptr)
+    return set_error(VM_ERR_SHAPE, "pack_train: bad arguments");
+  PackTrainArgs a{};
+  unsigned blocks = 0;
+  int cin = 1;
+  for (int b = 0; b < 4; ++b) {
+    const int cout = filters * (b + 1);
+    const int cout_pad = (cout + 127) / 128 * 128;
+    PackTrainTask& f = a.t[a.ntasks++];
+    f.w = kernels[b]; f.bias = biases[b]; f.wpack = wraw[b]; f.epi = eraw[b];
+    f.cin = cin; f.cout = cout; f.pad = cout_pad; f.kind = (b == 0) ? 0 : 1; f.block0 = blocks;
+    const size_t total = (b == 0) ? size_t(cout_pad) * 32 : size_t(3) * cout_pad * cin;
+    blocks += unsigned((total + 255) / 256);
+    if (b > 0) {
+      PackTrainTask& d = a.t[a.ntasks++];
+      const int cin_pad = (cin + 127) / 128 * 128;
+      d.w = kernels[b]; d.bias = nullptr; d.wpack = wdg[b]; d.epi = edg[b];
+      d.cin = cin; d.cout = cout; d.pad = cin_pad; d.kind = 2; d.block0 = blocks;
+      blocks += unsigned((size_t(3) * cin_pad * cout + 255) / 256);
+    }
+    cin = cout;
+  }
+  pack_train_kernel<<<blocks, 256, 0, stream>>>(a);
+  return check_launch("pack_train");
 }
 
 }  // namespace vm

@@ -118,7 +118,7 @@ int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int
                      float* dx, cudaStream_t st);
 int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                               const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
-                              float* d_head_b, cudaStream_t st);
+                              float* d_head_b, float* accuracy, cudaStream_t st);
 size_t bn_bwd_scratch_elems(int N);
 int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
@@ -143,6 +143,20 @@ int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, dou
 int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);
 
 // ---- small kernels (vm_head.cu) ----
+struct PackTrainTask {
+  const float* w;
+  const float* bias;
+  void* wpack;
+  float* epi;
+  int cin, cout, pad, kind;   // kind 0: conv1 raw, 1: conv3 raw, 2: conv3 dgrad; pad = padded Cout (Cin for dgrad)
+  unsigned block0;            // first block of the task's range
+};
+struct PackTrainArgs {
+  PackTrainTask t[7];
+  int ntasks;
+};
+int launch_pack_train(const float* const* kernels, const float* const* biases, int filters, void* const* wraw,
+                      float* const* eraw, void* const* wdg, float* const* edg, cudaStream_t stream);
 int launch_pack_conv1(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
                       const float* var, float eps, int cout, void* wpack, float* epi, cudaStream_t stream);
 int launch_pack_conv3(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,

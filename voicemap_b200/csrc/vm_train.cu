@@ -39,14 +39,34 @@ static int check_launch_t(const char* what) {
 // ---------------------------------------------------------------------------------------------
 // Deterministic two-stage column reduction of a (rows, stride) fp32 matrix with NC interleaved components per entry
 // (NC = 2: float2 {a, b}; NC = 1: float).  Stage 1: grid (ceil(C/32), G*kRB), block (32, 8): row block rb of group
-// g -> tmp[(g*kRB + rb)][c] (double2).  Stage 2 (inside the finalize kernels): sum the kRB partials per (g, c).
+// g -> tmp[(g*kRB + rb)][c] (double2).  Stage 2 (the finishing functors): sum the kRB partials per (g, c).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRB = 32;
 
-template <int NC>
-__global__ void rowsum_stage1_kernel(const float* __restrict__ m, size_t rows_per_group, int stride, int C,
-                                     double2* __restrict__ tmp) {
+__device__ __forceinline__ double2 rowsum_stage2(const double2* __restrict__ tmp, int g, int C, int c) {
+  // all kRB loads are issued before the first add (the sum order stays rb = 0, 1, ...: deterministic)
+  double2 v[kRB];
+#pragma unroll
+  for (int rb = 0; rb < kRB; ++rb) v[rb] = tmp[(size_t(g) * kRB + rb) * C + c];
+  double a = 0.0, b = 0.0;
+#pragma unroll
+  for (int rb = 0; rb < kRB; ++rb) {
+    a += v[rb].x;
+    b += v[rb].y;
+  }
+  return make_double2(a, b);
+}
+
+// Both stages in ONE launch: the stage-1 grid as above, and the block that finishes last among the G*kRB blocks of a
+// channel column (a self-resetting ticket per column) runs the finishing functor `fin(tmp, c)` for its 32 channels.
+// The stage-2 sums are taken in the fixed order rb = 0, 1, ... whichever block comes last, so the result does not depend
+// on the schedule.  One training step runs at a time per device (the tickets are per device, not per stream).
+__device__ unsigned int g_rowsum_tickets[64];   // columns of 32 channels: C <= 2048
+template <int NC, class Fin>
+__global__ void rowsum_fused_kernel(const float* __restrict__ m, size_t rows_per_group, int stride, int C,
+                                    double2* __restrict__ tmp, const Fin fin) {
   __shared__ double2 sm[8][32];
+  __shared__ bool last;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int g = blockIdx.y / kRB, rb = blockIdx.y % kRB;
   const size_t per = (rows_per_group + kRB - 1) / kRB;
@@ -70,62 +90,66 @@ __global__ void rowsum_stage1_kernel(const float* __restrict__ m, size_t rows_pe
     for (int k = 1; k < 8; ++k) { a += sm[k][threadIdx.x].x; b += sm[k][threadIdx.x].y; }
     tmp[size_t(blockIdx.y) * C + c] = make_double2(a, b);
   }
-}
-__device__ __forceinline__ double2 rowsum_stage2(const double2* __restrict__ tmp, int g, int C, int c) {
-  // all kRB loads are issued before the first add (the sum order stays rb = 0, 1, ...: deterministic)
-  double2 v[kRB];
-#pragma unroll
-  for (int rb = 0; rb < kRB; ++rb) v[rb] = tmp[(size_t(g) * kRB + rb) * C + c];
-  double a = 0.0, b = 0.0;
-#pragma unroll
-  for (int rb = 0; rb < kRB; ++rb) {
-    a += v[rb].x;
-    b += v[rb].y;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();                                   // this block's partials before its ticket
+    const unsigned int t = atomicAdd(&g_rowsum_tickets[blockIdx.x], 1u);
+    last = (t == gridDim.y - 1);
+    if (last) g_rowsum_tickets[blockIdx.x] = 0u;       // ready for the next launch
   }
-  return make_double2(a, b);
+  __syncthreads();
+  if (last && threadIdx.y == 0 && c < C) {
+    __threadfence();                                   // the other blocks' partials after their tickets
+    fin(tmp, c);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // batch statistics -> BN constants {s, t, mean, rstd} per (group, channel); moving-average update
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_stats_finalize_kernel(const double2* __restrict__ tmp, int N,
-                                         int G, int L, int C, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float eps, float momentum,
-                                         float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                         float4* __restrict__ bn_const) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int clips = N / G;
-  const double cnt = double(clips) * double(L);
-  float mm = moving_mean ? moving_mean[c] : 0.f;
-  float mv = moving_var ? moving_var[c] : 0.f;
-  for (int g = 0; g < G; ++g) {
-    const double2 sums = rowsum_stage2(tmp, g, C, c);
-    const double s1 = sums.x, s2 = sums.y;
-    const double mean = s1 / cnt;
-    double var = s2 / cnt - mean * mean;  // biased batch variance (tf.nn.moments)
-    if (var < 0.0) var = 0.0;
-    const float rstd = float(1.0 / sqrt(var + double(eps)));
-    const float s = gamma[c] * rstd;
-    bn_const[size_t(g) * C + c] = make_float4(s, beta[c] - float(mean) * s, float(mean), rstd);
-    // keras: sample variance var * n / (n - (1 + eps)); moving <- moving * momentum + stat * (1 - momentum)
-    const float var_unbiased = float(var * (cnt / (cnt - (1.0 + double(eps)))));
-    mm = mm * momentum + float(mean) * (1.f - momentum);
-    mv = mv * momentum + var_unbiased * (1.f - momentum);
+struct BnStatsFin {
+  int N, G, L, C;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* moving_mean;
+  float* moving_var;
+  float4* bn_const;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const {
+    const int clips = N / G;
+    const double cnt = double(clips) * double(L);
+    float mm = moving_mean ? moving_mean[c] : 0.f;
+    float mv = moving_var ? moving_var[c] : 0.f;
+    for (int g = 0; g < G; ++g) {
+      const double2 sums = rowsum_stage2(tmp, g, C, c);
+      const double s1 = sums.x, s2 = sums.y;
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;  // biased batch variance (tf.nn.moments)
+      if (var < 0.0) var = 0.0;
+      const float rstd = float(1.0 / sqrt(var + double(eps)));
+      const float s = gamma[c] * rstd;
+      bn_const[size_t(g) * C + c] = make_float4(s, beta[c] - float(mean) * s, float(mean), rstd);
+      // keras: sample variance var * n / (n - (1 + eps)); moving <- moving * momentum + stat * (1 - momentum)
+      const float var_unbiased = float(var * (cnt / (cnt - (1.0 + double(eps)))));
+      mm = mm * momentum + float(mean) * (1.f - momentum);
+      mv = mv * momentum + var_unbiased * (1.f - momentum);
+    }
+    if (moving_mean) moving_mean[c] = mm;
+    if (moving_var) moving_var[c] = mv;
   }
-  if (moving_mean) moving_mean[c] = mm;
-  if (moving_var) moving_var[c] = mv;
-}
+};
 
 // ---------------------------------------------------------------------------------------------
 // Split form of the statistics for synchronised BatchNorm across ranks: (1) per-(group, channel) double sums,
 // (2) the caller all-reduces them, (3) constants from the global sums and the global count.
 // ---------------------------------------------------------------------------------------------
-__global__ void stage2_sums_kernel(const double2* __restrict__ tmp, int G, int C, double2* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  for (int g = 0; g < G; ++g) sums[size_t(g) * C + c] = rowsum_stage2(tmp, g, C, c);
-}
+struct SumsFin {
+  int G, C;
+  double2* sums;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const {
+    for (int g = 0; g < G; ++g) sums[size_t(g) * C + c] = rowsum_stage2(tmp, g, C, c);
+  }
+};
 __global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, double cnt, int G, int C,
                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                           float momentum, float* __restrict__ moving_mean,
@@ -322,19 +346,42 @@ dense_fwd_kernel(const float* __restrict__ x, int N, int C, const float* __restr
     __syncthreads();
   }
 }
-// dW[c][e] = sum_n x[n][c] * dy[n][e]  (grid C blocks, E threads);  db[e] = sum_n dy[n][e] (block 0)
-__global__ void dense_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, int N, int C, int E,
-                                   float* __restrict__ dw, float* __restrict__ db) {
-  const int c = blockIdx.x;
+// dW[c][e] = sum_n x[n][c] * dy[n][e];  db[e] = sum_n dy[n][e] (block 0).  Block = 8 channels x E outputs (one thread
+// per e, strided): a dy row is loaded once per clip for the 8 channels, four clips in flight (the first version ran one
+// serial chain of N dependent loads per output and took 47 us for 128 clips).
+__global__ void __launch_bounds__(64)
+dense_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, int N, int C, int E,
+                   float* __restrict__ dw, float* __restrict__ db) {
+  const int c0 = blockIdx.x * 8;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    float acc = 0.f, accb = 0.f;
-    for (int n = 0; n < N; ++n) {
-      const float d = dy[size_t(n) * E + e];
-      acc = fmaf(x[size_t(n) * C + c], d, acc);
-      accb += d;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      float d[4], xv[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        d[i] = dy[size_t(n + i) * E + e];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv[i][k] = (c0 + k < C) ? __ldg(x + size_t(n + i) * C + c0 + k) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {   // clips in order: the sums do not depend on the unrolling
+        accb += d[i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[i][k], d[i], acc[k]);
+      }
     }
-    dw[size_t(c) * E + e] = acc;
-    if (c == 0) db[e] = accb;
+    for (; n < N; ++n) {
+      const float d = dy[size_t(n) * E + e];
+      accb += d;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c0 + k < C) acc[k] = fmaf(x[size_t(n) * C + c0 + k], d, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c0 + k < C) dw[size_t(c0 + k) * E + e] = acc[k];
+    if (blockIdx.x == 0) db[e] = accb;
   }
 }
 // dx[n][c] = sum_e dy[n][e] * w[c][e]   (grid N blocks, C threads strided)
@@ -359,9 +406,13 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
                                           const float* __restrict__ head_w, const float* __restrict__ head_b,
                                           const float* __restrict__ y_true, int loss_kind, float loss_scale,
                                           float* __restrict__ d_emb, float* __restrict__ d_head_w,
-                                          float* __restrict__ d_head_b) {
+                                          float* __restrict__ d_head_b, float* __restrict__ accuracy) {
   extern __shared__ float dzs[];  // [N] dL/dz (scaled), then [N] distance
   float* dist = dzs + N;
+  __shared__ int hits;
+  if (threadIdx.x == 0) hits = 0;
+  __syncthreads();
+  int my_hits = 0;
   const float* e1 = emb;
   const float* e2 = emb + size_t(N) * E;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -380,6 +431,7 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
     }
     const float p = 1.0f / (1.0f + expf(-z));
     const float y = y_true[n];
+    my_hits += ((p > 0.5f ? 1.f : 0.f) == y) ? 1 : 0;     // keras 'accuracy' of a sigmoid output: round(p) == y
     float dp;
     if (loss_kind == 1) {  // contrastive: (1-y) p^2 + y max(1-p,0)^2
       dp = (1.f - y) * 2.f * p - y * 2.f * fmaxf(1.f - p, 0.f);
@@ -390,7 +442,9 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
     dzs[n] = dp * p * (1.f - p) * (loss_scale / float(N));
     dist[n] = d;
   }
+  if (accuracy != nullptr && my_hits) atomicAdd(&hits, my_hits);   // integer count: order does not matter
   __syncthreads();
+  if (accuracy != nullptr && threadIdx.x == 0) accuracy[0] = float(hits) / float(N);
   // d_emb
   for (int idx = threadIdx.x; idx < N * E; idx += blockDim.x) {
     const int n = idx / E, j = idx % E;
@@ -501,24 +555,27 @@ bn_bwd_reduce_kernel(const float* __restrict__ ext, const float* __restrict__ dy
 }
 
 // pass 2: per (group, channel) means -> bwd constants {s, mean_dy, mean_dyxhat, 0}; dgamma/dbeta summed over groups.
-__global__ void bn_bwd_finalize_kernel(const double2* __restrict__ tmp, int N, int G, int L,
-                                       int C, const float4* __restrict__ bn_const, float4* __restrict__ bwd_const,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int clips = N / G;
-  const double cnt = double(clips) * double(L);
-  double tg = 0.0, tb = 0.0;
-  for (int g = 0; g < G; ++g) {
-    const double2 sums = rowsum_stage2(tmp, g, C, c);
-    const double s1 = sums.x, s2 = sums.y;
-    bwd_const[size_t(g) * C + c] = make_float4(bn_const[size_t(g) * C + c].x, float(s1 / cnt), float(s2 / cnt), 0.f);
-    tb += s1;
-    tg += s2;
+struct BnBwdFin {
+  int N, G, L, C;
+  const float4* bn_const;
+  float4* bwd_const;
+  float* dgamma;
+  float* dbeta;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const {
+    const int clips = N / G;
+    const double cnt = double(clips) * double(L);
+    double tg = 0.0, tb = 0.0;
+    for (int g = 0; g < G; ++g) {
+      const double2 sums = rowsum_stage2(tmp, g, C, c);
+      const double s1 = sums.x, s2 = sums.y;
+      bwd_const[size_t(g) * C + c] = make_float4(bn_const[size_t(g) * C + c].x, float(s1 / cnt), float(s2 / cnt), 0.f);
+      tb += s1;
+      tg += s2;
+    }
+    dgamma[c] = float(tg);
+    dbeta[c] = float(tb);
   }
-  dgamma[c] = float(tg);
-  dbeta[c] = float(tb);
-}
+};
 
 // pass 3: dU = relu'(u) * s * (dy - mean_dy - xhat * mean_dyxhat) at every un-pooled position (incl. the 'valid'
 // tail, which receives no dy but still the batch-statistics terms), written as fp16 planes scaled by the block's
@@ -626,10 +683,11 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
 }
 
 // second stage of a plain column sum -> out[C]
-__global__ void colsum_finalize_kernel(const double2* __restrict__ tmp, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[c] = float(rowsum_stage2(tmp, 0, C, c).x);
-}
+struct ColsumFin {
+  int C;
+  float* out;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const { out[c] = float(rowsum_stage2(tmp, 0, C, c).x); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Keras Adam with global-norm clipping (keras.optimizers.Adam(clipnorm=...))
@@ -678,10 +736,10 @@ int launch_bn_stats_finalize(const float* partial, int rows_per_clip, int c_pad,
   if (N <= 0 || G <= 0 || N % G != 0 || C <= 0) return set_error(VM_ERR_SHAPE, "bn_stats_finalize: bad shape");
   if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_stats_finalize: reduction scratch missing");
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
-      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp);
-  bn_stats_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, N, G, L, C, gamma, beta, eps, momentum, moving_mean,
-                                                        moving_var, reinterpret_cast<float4*>(bn_const));
+  if (C > 2048) return set_error(VM_ERR_UNSUPPORTED, "bn_stats_finalize: C > 2048");
+  const BnStatsFin fin{N, G, L, C, gamma, beta, eps, momentum, moving_mean, moving_var, reinterpret_cast<float4*>(bn_const)};
+  rowsum_fused_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp, fin);
   return check_launch_t("bn_stats_finalize");
 }
 
@@ -690,9 +748,10 @@ int launch_bn_stats_sums(const float* partial, int rows_per_clip, int c_pad, int
   if (N <= 0 || G <= 0 || N % G != 0 || C <= 0) return set_error(VM_ERR_SHAPE, "bn_stats_sums: bad shape");
   if (red_scratch == nullptr || sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_stats_sums: null buffer");
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
-      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp);
-  stage2_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, G, C, reinterpret_cast<double2*>(sums));
+  if (C > 2048) return set_error(VM_ERR_UNSUPPORTED, "bn_stats_sums: C > 2048");
+  const SumsFin fin{G, C, reinterpret_cast<double2*>(sums)};
+  rowsum_fused_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * rows_per_clip, c_pad, C, tmp, fin);
   return check_launch_t("bn_stats_sums");
 }
 
@@ -738,19 +797,20 @@ int launch_dense_fwd(const float* x, int N, int C, const float* w, const float* 
 
 int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db,
                      float* dx, cudaStream_t st) {
-  dense_bwd_w_kernel<<<C, 64, 0, st>>>(x, dy, N, C, E, dw, db);
+  dense_bwd_w_kernel<<<(C + 7) / 8, 64, 0, st>>>(x, dy, N, C, E, dw, db);
   dense_bwd_x_kernel<<<N, 128, E * sizeof(float), st>>>(dy, w, N, C, E, dx);
   return check_launch_t("dense_bwd");
 }
 
 int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                               const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
-                              float* d_head_b, cudaStream_t st) {
+                              float* d_head_b, float* accuracy, cudaStream_t st) {
   if (N <= 0 || E <= 0 || (metric != 0 && metric != 1) || (loss_kind != 1 && loss_kind != 2))
     return set_error(VM_ERR_SHAPE, "pair_head_loss_bwd: bad arguments");
   if (size_t(N) * 8 > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "pair_head_loss_bwd: N too large");
   pair_head_loss_bwd_kernel<<<1, 256, 2 * N * sizeof(float), st>>>(emb, N, E, metric, head_w, head_b, y_true,
-                                                                   loss_kind, loss_scale, d_emb, d_head_w, d_head_b);
+                                                                   loss_kind, loss_scale, d_emb, d_head_w, d_head_b,
+                                                                   accuracy);
   return check_launch_t("pair_head_loss_bwd");
 }
 
@@ -770,9 +830,11 @@ size_t bn_bwd_scratch_elems(int N) {
 }
 
 // passes 1-2: per-(group, channel) sums of dy and dy*xhat over this rank's clips -> tmp (and, if asked, `sums`)
+template <class Fin>
 static int bn_bwd_reduce(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N,
                          int lout, int C, int G, const float* bn_const, const float* mask, float* partial,
-                         unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st) {
+                         unsigned int* absmax, double* red_scratch, const Fin& fin, cudaStream_t st) {
+  if (C > 2048) return set_error(VM_ERR_UNSUPPORTED, "bn_bwd: C > 2048");
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
   cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd: memset");
@@ -781,9 +843,8 @@ static int bn_bwd_reduce(const float* ext, const float* dy_pooled, const float* 
   bn_bwd_reduce_kernel<<<dim3(N, chunks), kEwThreads, 0, st>>>(ext, dy_pooled, d_gmax, jstar, N, lout, C, G,
                                                                reinterpret_cast<const float4*>(bn_const), mask,
                                                                reinterpret_cast<float2*>(partial), absmax);
-  rowsum_stage1_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
-      partial, size_t(N / G) * chunks * streams, C, C, tmp);
-  if (sums != nullptr) stage2_sums_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, G, C, reinterpret_cast<double2*>(sums));
+  rowsum_fused_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * chunks * streams, C, C, tmp, fin);
   return VM_OK;
 }
 
@@ -804,9 +865,9 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
   if (dy_pooled == nullptr) { if (du_lo) VM_RELU_BWD(true, 2); else VM_RELU_BWD(true, 1); }
   else { if (du_lo) VM_RELU_BWD(false, 2); else VM_RELU_BWD(false, 1); }
 #undef VM_RELU_BWD
-  rowsum_stage1_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial,
-                                                                           size_t(N) * chunks * streams, C, C, tmp);
-  colsum_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(tmp, C, dbias);
+  const ColsumFin fin{C, dbias};
+  rowsum_fused_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial, size_t(N) * chunks * streams,
+                                                                          C, C, tmp, fin);
   return VM_OK;
 }
 
@@ -816,12 +877,11 @@ int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled,
                   float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
   int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
+  const BnBwdFin fin{N, G, L, C, reinterpret_cast<const float4*>(bn_const), reinterpret_cast<float4*>(bwd_const),
+                     dgamma, dbeta};
   if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
-                          red_scratch, nullptr, st)))
+                          red_scratch, fin, st)))
     return rc;
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>(reinterpret_cast<double2*>(red_scratch), N, G, L, C,
-                                                      reinterpret_cast<const float4*>(bn_const),
-                                                      reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
   bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd");
@@ -833,8 +893,9 @@ int launch_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_
   int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
   if (sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd_sums: null sums");
+  const SumsFin fin{G, C, reinterpret_cast<double2*>(sums)};
   if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
-                          red_scratch, sums, st)))
+                          red_scratch, fin, st)))
     return rc;
   return check_launch_t("bn_bwd_sums");
 }

@@ -59,6 +59,24 @@ class _Plan:
                 if rc:
                     _lib.check(rc, what)
 
+    def run_timed(self, timings):
+        """The same launches with a CUDA event after every one (live timings of a step: ncu serialises the launches
+        and flushes caches between them, which inflates the small kernels).  ``timings``: list that receives
+        (what, event before, event after) triples."""
+        before = torch.cuda.Event(enable_timing=True)
+        before.record()
+        for fn, args, what in self.ops:
+            if fn is None:
+                args()
+                continue
+            rc = fn(*args)
+            if rc:
+                _lib.check(rc, what)
+            after = torch.cuda.Event(enable_timing=True)
+            after.record()
+            timings.append((what, before, after))
+            before = after
+
 
 class TrainEngine:
     """One training step of encoder (+ siamese head | classifier head) on the current CUDA device."""
@@ -213,25 +231,23 @@ class TrainEngine:
         self.yin = torch.empty((max(1, nb // groups),), dtype=f32, device=dev)   # siamese pair labels
         self.maskbuf = [torch.empty((nb, c[b]), dtype=f32, device=dev) for b in range(4)]
         self.prob = torch.empty((max(1, nb // groups), 1), dtype=f32, device=dev)
-        self.lossv = torch.zeros((1,), dtype=f32, device=dev)
+        self.lossv = torch.zeros((2,), dtype=f32, device=dev)      # [loss, accuracy] of the step
         self.masks = [None] * 4
         self._plans = {}
         self._buf_key = key
 
     def _plan_pack(self, plan, st):
+        """One launch packs the operands of all four blocks from the current weights: 'raw' forward planes (identity
+        BN, epilogue relu(acc + bias)) and the tap-flipped, channel-transposed dgrad planes of blocks 2-4."""
         p = self.p
-        lib = self.lib
-        cin = 1
-        for i, cout in enumerate(self.channels, start=1):
-            if i == 1:
-                plan.launch(lib.vm_pack_conv1_raw, "vm_pack_conv1_raw", _ptr(p["conv1_kernel"]), _ptr(p["conv1_bias"]),
-                            cout, _ptr(self.wraw[0]), _ptr(self.eraw[0]), st)
-            else:
-                plan.launch(lib.vm_pack_conv3_raw, "vm_pack_conv3_raw", _ptr(p[f"conv{i}_kernel"]),
-                            _ptr(p[f"conv{i}_bias"]), cin, cout, _ptr(self.wraw[i - 1]), _ptr(self.eraw[i - 1]), st)
-                plan.launch(lib.vm_pack_conv3_dgrad, "vm_pack_conv3_dgrad", _ptr(p[f"conv{i}_kernel"]), cin, cout,
-                            _ptr(self.wdg[i - 1]), _ptr(self.edg[i - 1]), st)
-            cin = cout
+        arr = C.c_void_p * 4
+        self._pack_args = (arr(*[p[f"conv{i}_kernel"].data_ptr() for i in range(1, 5)]),
+                           arr(*[p[f"conv{i}_bias"].data_ptr() for i in range(1, 5)]),
+                           arr(*[t.data_ptr() for t in self.wraw]), arr(*[t.data_ptr() for t in self.eraw]),
+                           arr(*[t.data_ptr() if t is not None else 0 for t in self.wdg]),
+                           arr(*[t.data_ptr() if t is not None else 0 for t in self.edg]))
+        k, bi, wr, er, wd, ed = self._pack_args
+        plan.launch(self.lib.vm_pack_train, "vm_pack_train", k, bi, self.filters, wr, er, wd, ed, st)
 
     def _set_masks(self, nb, masks):
         """Fill the static SpatialDropout1D mask buffers for this step; returns whether dropout is active.  One
@@ -477,8 +493,8 @@ class TrainEngine:
         self._share_gradients(allreduce)
         if apply:
             self.apply_gradients(world)
-        acc = ((self.prob.reshape(-1) > 0.5).to(torch.float32) == self.yin).to(torch.float32).mean()
-        return self.lossv.clone().reshape(()), acc
+        out = self.lossv.clone()        # one copy: the next step overwrites the buffer while callers still hold these
+        return out[0], out[1]
 
     def _share_gradients(self, allreduce):
         if self.grad_buckets is not None:
@@ -497,7 +513,7 @@ class TrainEngine:
                     _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, None, _ptr(self.prob), _ptr(self.lossv), st)
         plan.launch(lib.vm_pair_head_loss_bwd, "vm_pair_head_loss_bwd", _ptr(self.embv), n, self.emb, metric_id,
                     _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, C.c_float(self.loss_scale), _ptr(self.d_emb),
-                    _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), st)
+                    _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), _ptr(self.lossv[1:]), st)
         return plan
 
     def classifier_step(self, x, y_onehot, apply=True, masks=None, allreduce=None, world=1):
@@ -537,6 +553,29 @@ class TrainEngine:
             target[name] = self.p[name].detach().cpu().numpy().copy()
         if self.kind == "siamese":
             self.model._head_dev = None
+
+    def time_siamese_step(self, x1, x2, y, steps=10):
+        """Live per-launch durations of a siamese step (CUDA events between the C-ABI calls, averaged over ``steps``
+        steps after one warm-up step): [(what, ms), ...] in launch order, Adam last."""
+        self.siamese_step(x1, x2, y)
+        acc = None
+        for _ in range(steps):
+            timings = []
+            run, _Plan.run = _Plan.run, lambda plan: plan.run_timed(timings)
+            try:
+                self.siamese_step(x1, x2, y, apply=False)
+            finally:
+                _Plan.run = run
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            self.apply_gradients()
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record()
+            timings.append(("vm_adam_step", t0, t1))
+            torch.cuda.synchronize()
+            ms = [(w, a.elapsed_time(b)) for w, a, b in timings]
+            acc = ms if acc is None else [(w, t + u) for (w, t), (_, u) in zip(acc, ms)]
+        return [(w, t / steps) for w, t in acc]
 
     # ------------------------------------------------------------------ views for tests / diagnostics
     def relu_pattern(self, b):
