@@ -254,8 +254,10 @@ def bench_train(args, dev, rank, world, peaks):
                                     f"{args.train_pairs} pairs/step global = {pairs} pairs/GPU x {length} samples, "
                                     f"filters={FILTERS}, emb={EMB}, train-mode BatchNorm synchronised over the ranks",
                            parallelism=f"dp{world}: per-block gradient all-reduce (5 buckets, "
-                                       f"{(1023808 + 2) * 4 / 1e6:.1f} MB fp32 per step) overlapped with backward + 8 "
-                                       f"BatchNorm statistics all-reduces (<= 16 KB each)" if world > 1 else "dp1"),
+                                       f"{(1023808 + 2) * 4 / 1e6:.1f} MB fp32 per step, NCCL) overlapped with backward + 8 "
+                                       f"BatchNorm statistics sums (<= 16 KB each) "
+                                       f"{'inside the kernels over NVLink peer memory' if os.environ.get('VOICEMAP_SYNCBN', 'p2p').lower() != 'nccl' else 'as NCCL all-reduces'}"
+                           if world > 1 else "dp1"),
                modes={})
     for name, bwd in (("bwd1", 1), ("bwd3", 3)):
         enc = get_baseline_convolutional_encoder(FILTERS, EMB, dropout=0.0)
@@ -264,7 +266,9 @@ def bench_train(args, dev, rank, world, peaks):
         opt = Adam(clipnorm=1.0)
         sia.compile(loss=contrastive_loss, optimizer=opt)
         tr = TrainEngine(sia, opt, sia.loss, precision=3, bwd_precision=bwd)
-        tr.set_sync_bn(allreduce, world)
+        from voicemap_b200.training import sync_bn_peers
+        peers = sync_bn_peers() if world > 1 else None
+        tr.set_sync_bn(allreduce, world, peers=peers)
         tr.set_gradient_buckets(world > 1)
         for _ in range(3):
             tr.siamese_step(x1, x2, yd, world=world)

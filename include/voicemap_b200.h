@@ -244,6 +244,28 @@ int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, dou
                         int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
                         float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
                         float* dbias, double* red_scratch, void* stream);
+/* The same two pairs with the sum over the ranks INSIDE the consuming kernel, over NVLink peer memory instead of a
+ * collective call: every rank of the node (at most 8) owns one exchange buffer (vm_p2p_alloc) that all ranks have
+ * mapped through CUDA IPC (vm_p2p_export -> 64-byte handle -> vm_p2p_import on the peers).  A call pushes this rank's
+ * sums into every peer's buffer, raises a flag, waits for the peers' flags on its own buffer and adds the W vectors in
+ * rank order (bit-identical totals on every rank), then forms the constants -- one launch, no host involvement.
+ * peers: W buffer addresses as mapped in THIS process (peers[rank] = the local one); seq: 1, 2, 3, ... identical on
+ * every rank and incremented per call (all ranks must issue the same calls in the same order); total_sums receives the
+ * global sums (2*G*C doubles).  vm_bn_stats_sync follows vm_bn_stats_sums, vm_bn_bwd_sync follows vm_bn_bwd_sums. */
+size_t vm_p2p_buffer_bytes(void);
+int vm_p2p_alloc(void** ptr);
+int vm_p2p_free(void* ptr);
+int vm_p2p_export(void* ptr, unsigned char* handle64);
+int vm_p2p_import(const unsigned char* handle64, void** ptr);
+int vm_p2p_unimport(void* ptr);
+int vm_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
+                     uint32_t seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* moving_mean, float* moving_var, float* bn_const, void* stream);
+int vm_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world, uint32_t seq,
+                   double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
+                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* bwd_const,
+                   float* dgamma, float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
+                   float* scratch_f, float* dbias, double* red_scratch, void* stream);
 /* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores.  x_hi / x_lo: the fp16 planes the
  * forward conv of the block consumed (x_lo = fp16 residual plane: training keeps precision-3 planes for this);
  * du_*: the scaled gradient planes of vm_bn_bwd, grad_absmax their scale word.  precision 3: Xh*Uh + Xl*Uh + Xh*Ul;

@@ -133,7 +133,7 @@ def test_fit_generator_uses_the_producers(monkeypatch):
         def __init__(self, model, optimizer, loss):
             self.optimizer, self.loss = optimizer, loss
 
-        def set_sync_bn(self, allreduce, world):
+        def set_sync_bn(self, allreduce, world, peers=None):
             pass
 
         def set_gradient_buckets(self, enabled=True):

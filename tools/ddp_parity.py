@@ -53,11 +53,23 @@ def main():
     y = (np.arange(PAIRS) % 2).astype(np.float32)
     lo, hi = parallel.shard_bounds(PAIRS, rank, world)
 
+    from voicemap_b200.training import sync_bn_peers
     results = {}
-    for sync in (True, False):
+    # "p2p": sums cross the ranks inside the kernels (NVLink peer memory) + bucketed gradient all-reduce (the default of
+    # fit_generator); "nccl": 8 small all-reduce calls + one flat gradient all-reduce; False: per-rank statistics
+    for sync in ("p2p", "nccl", False):
         sia, tr = build(0)
         allreduce = parallel.allreduce_sum_ if world > 1 else None
-        tr.set_sync_bn(allreduce if sync else None, world)
+        peers = sync_bn_peers() if (sync == "p2p" and world > 1) else None
+        tr.set_sync_bn(allreduce if sync else None, world, peers=peers)
+        tr.set_gradient_buckets(sync == "p2p" and world > 1)
+        if sync == "p2p" and world > 1:    # a few steps on a throw-away model first: the exchange buffers' two slots and
+            _, warm = build(1)             # the sequence counter are then mid-stream when the compared step runs
+            warm.set_sync_bn(allreduce, world, peers=peers)
+            warm.set_gradient_buckets(True)
+            for _ in range(3):
+                warm.siamese_step(x1[lo:hi], x2[lo:hi], y[lo:hi], apply=True, allreduce=allreduce, world=world)
+            del warm
         lv, _ = tr.siamese_step(x1[lo:hi], x2[lo:hi], y[lo:hi], apply=True, allreduce=allreduce, world=world)
         loss = parallel.global_mean(float(lv.item()) * (hi - lo), hi - lo, dev)
         grads = {k: v / world for k, v in tr.gradients().items()}
@@ -69,7 +81,7 @@ def main():
         ref = (float(lv.item()), tr.gradients(), {k: v.cpu().numpy() for k, v in tr.moving.items()},
                {k: v.detach().cpu().numpy().copy() for k, v in tr.p.items()})
         ok = True
-        for sync in (True, False):
+        for sync in ("p2p", "nccl", False):
             loss, grads, moving, params = results[sync]
             floor = 1e-3 * max(np.abs(v).max() for v in ref[1].values())
             gerr = max(np.abs(grads[k] - ref[1][k]).max() / max(np.abs(ref[1][k]).max(), floor) for k in ref[1])

@@ -34,6 +34,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--bwd-precision", type=int, default=3)
     ap.add_argument("--local-bn", action="store_true", help="per-rank BatchNorm statistics instead of synchronised")
+    ap.add_argument("--nccl-bn", action="store_true", help="BatchNorm sums through NCCL all-reduce calls instead of the "
+                                                           "peer-memory kernels")
+    ap.add_argument("--flat-allreduce", action="store_true", help="one gradient all-reduce after backward instead of "
+                                                                  "per-block buckets inside it")
     ap.add_argument("--timeline", action="store_true", help="print live per-launch durations of a step (one rank)")
     args = ap.parse_args()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -52,7 +56,10 @@ def main():
     x2 = (0.038021 * torch.randn(pairs, args.length, generator=g)).to(dev)
     y = np.concatenate([np.zeros(pairs // 2), np.ones(pairs - pairs // 2)]).astype(np.float32)
     allreduce = parallel.allreduce_sum_ if world > 1 else None
-    tr.set_sync_bn(None if args.local_bn else allreduce, world)
+    from voicemap_b200.training import sync_bn_peers
+    peers = sync_bn_peers() if (world > 1 and not args.local_bn and not args.nccl_bn) else None
+    tr.set_sync_bn(None if args.local_bn else allreduce, world, peers=peers)
+    tr.set_gradient_buckets(world > 1 and not args.flat_allreduce)
 
     for _ in range(max(args.warmup, 3)):
         tr.siamese_step(x1, x2, y, allreduce=allreduce, world=world)
@@ -91,7 +98,7 @@ def main():
                                                    f"fwd fp16x3, bwd fp16 mode {args.bwd_precision}",
                                           parallelism=f"dp{world}, one flat fp32 gradient all-reduce "
                                                       f"({tr.nparams * 4 / 1e6:.1f} MB) per step, BatchNorm "
-                                                      f"{'per rank' if (args.local_bn or world == 1) else 'synchronised (8 small all-reduces)'}"),
+                                                      f"{'per rank' if (args.local_bn or world == 1) else ('synchronised: 8 NCCL all-reduces' if peers is None else 'synchronised: sums cross the ranks inside the kernels (NVLink peer memory)')}, gradients {'one flat all-reduce' if args.flat_allreduce else '5 buckets overlapped with backward'}"),
                               final_loss=float(lv.item()))), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

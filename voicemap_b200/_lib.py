@@ -76,6 +76,16 @@ SIGNATURES = {
     "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd_from_sums": (_i, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vm_p2p_buffer_bytes": (_sz, []),
+    "vm_p2p_alloc": (_i, [C.POINTER(_vp)]),
+    "vm_p2p_free": (_i, [_vp]),
+    "vm_p2p_export": (_i, [_vp, C.c_char_p]),
+    "vm_p2p_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "vm_p2p_unimport": (_i, [_vp]),
+    "vm_bn_stats_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp,
+                              _vp, _vp, _vp]),
+    "vm_bn_bwd_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                            _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "vm_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _f, _vp]),

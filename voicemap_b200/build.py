@@ -20,7 +20,7 @@ IO_SOURCES = ["vm_flac.c"]
 IO_HEADERS = [os.path.join("..", "..", "include", "voicemap_io.h")]
 CC_FLAGS = ["-O3", "-std=c99", "-Wall", "-Wextra", "-fwrapv", "-fPIC", "-shared"]  # -fwrapv: hostile streams may overflow the predictor
 SOURCES = ["vm_api.cu", "vm_conv1.cu", "vm_conv3.cu", "vm_head.cu", "vm_train.cu", "vm_wgrad.cu"]
-HEADERS = ["vm_common.cuh", "vm_kernels.h", os.path.join("..", "..", "include", "voicemap_b200.h")]
+HEADERS = ["vm_common.cuh", "vm_kernels.h", "vm_p2p.cuh", os.path.join("..", "..", "include", "voicemap_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include "vm_kernels.h"
+#include "vm_p2p.cuh"
+#include <string.h>
 
 namespace vm {
 
@@ -325,6 +327,57 @@ int vm_wgrad3(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* du_hi,
 int vm_wgrad1(const float* x, const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int precision,
               const uint32_t* grad_absmax, float* partial, size_t partial_bytes, float* dw, void* stream) {
   return launch_wgrad1(x, CH16(du_hi), CH16(du_lo), N, L, cout, partial, partial_bytes, dw, grad_absmax, ST, precision);
+}
+// ---- peer exchange buffers (CUDA IPC) and the BatchNorm calls that sum over the ranks inside the kernel -------------
+size_t vm_p2p_buffer_bytes(void) { return kP2PBufferBytes; }
+int vm_p2p_alloc(void** ptr) {
+  if (ptr == nullptr) return set_error(VM_ERR_SHAPE, "p2p_alloc: null pointer");
+  cudaError_t e = cudaMalloc(ptr, kP2PBufferBytes);        // own allocation: an IPC handle names a whole cudaMalloc block
+  if (e != cudaSuccess) return set_cuda_error(e, "p2p_alloc: cudaMalloc");
+  e = cudaMemset(*ptr, 0, kP2PBufferBytes);
+  if (e != cudaSuccess) return set_cuda_error(e, "p2p_alloc: cudaMemset");
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return set_cuda_error(e, "p2p_alloc: sync");
+  return VM_OK;
+}
+int vm_p2p_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? VM_OK : set_cuda_error(e, "p2p_free");
+}
+int vm_p2p_export(void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (ptr == nullptr || handle64 == nullptr) return set_error(VM_ERR_SHAPE, "p2p_export: null pointer");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) return set_cuda_error(e, "p2p_export: cudaIpcGetMemHandle");
+  memcpy(handle64, &h, 64);
+  return VM_OK;
+}
+int vm_p2p_import(const unsigned char* handle64, void** ptr) {
+  if (ptr == nullptr || handle64 == nullptr) return set_error(VM_ERR_SHAPE, "p2p_import: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? VM_OK : set_cuda_error(e, "p2p_import: cudaIpcOpenMemHandle (peer access over NVLink needed)");
+}
+int vm_p2p_unimport(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? VM_OK : set_cuda_error(e, "p2p_unimport");
+}
+int vm_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
+                     uint32_t seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* moving_mean, float* moving_var, float* bn_const, void* stream) {
+  return launch_bn_stats_sync(local_sums, total_sums, peers, rank, world, seq, count, G, C, gamma, beta, eps, momentum,
+                              moving_mean, moving_var, bn_const, ST);
+}
+int vm_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world, uint32_t seq,
+                   double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
+                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* bwd_const,
+                   float* dgamma, float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
+                   float* scratch_f, float* dbias, double* red_scratch, void* stream) {
+  return launch_bn_bwd_sync(local_sums, total_sums, peers, rank, world, seq, count, u16, dy_pooled, d_gmax, jstar, N, L,
+                            C, G, pool, bn_const, mask, bwd_const, dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo),
+                            scratch_f, dbias, red_scratch, ST);
 }
 int vm_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* scratch, float inv_scale,
                  float clipnorm, float lr_t, float beta1, float beta2, float eps, void* stream) {

@@ -27,6 +27,7 @@
 // All gradients flowing through these kernels carry the loss scale the caller folded into the loss gradient.
 #include "vm_common.cuh"
 #include "vm_kernels.h"
+#include "vm_p2p.cuh"
 
 namespace vm {
 
@@ -150,12 +151,12 @@ struct SumsFin {
     for (int g = 0; g < G; ++g) sums[size_t(g) * C + c] = rowsum_stage2(tmp, g, C, c);
   }
 };
-__global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, double cnt, int G, int C,
-                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                          float momentum, float* __restrict__ moving_mean,
-                                          float* __restrict__ moving_var, float4* __restrict__ bn_const) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__device__ __forceinline__ void bn_stats_from_sums_channel(int c, const double2* __restrict__ sums, double cnt, int G,
+                                                           int C, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, float momentum,
+                                                           float* __restrict__ moving_mean,
+                                                           float* __restrict__ moving_var,
+                                                           float4* __restrict__ bn_const) {
   float mm = moving_mean ? moving_mean[c] : 0.f;
   float mv = moving_var ? moving_var[c] : 0.f;
   for (int g = 0; g < G; ++g) {   // same arithmetic as bn_stats_finalize_kernel
@@ -173,14 +174,31 @@ __global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, doub
   if (moving_mean) moving_mean[c] = mm;
   if (moving_var) moving_var[c] = mv;
 }
+__global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, double cnt, int G, int C,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                          float momentum, float* __restrict__ moving_mean,
+                                          float* __restrict__ moving_var, float4* __restrict__ bn_const) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_stats_from_sums_channel(c, sums, cnt, G, C, gamma, beta, eps, momentum, moving_mean, moving_var, bn_const);
+}
+// The same with the cross-rank sum inside the kernel (vm_p2p.cuh): local sums -> peer exchange -> constants, one block.
+__global__ void __launch_bounds__(256)
+bn_stats_sync_kernel(const double* __restrict__ local, double* __restrict__ total, const P2PPeers peers,
+                     unsigned int seq, double cnt, int G, int C, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float momentum, float* __restrict__ moving_mean,
+                     float* __restrict__ moving_var, float4* __restrict__ bn_const) {
+  p2p_allreduce_block(local, 2 * G * C, peers, seq, total);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    bn_stats_from_sums_channel(c, reinterpret_cast<const double2*>(total), cnt, G, C, gamma, beta, eps, momentum,
+                               moving_mean, moving_var, bn_const);
+}
 // backward: the batch means of dy and dy*xhat come from the GLOBAL sums, dgamma / dbeta from this rank's own sums
 // (the gradient all-reduce adds the ranks' contributions)
-__global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const double2* __restrict__ global,
-                                        double cnt, int G, int C, const float4* __restrict__ bn_const,
-                                        float4* __restrict__ bwd_const, float* __restrict__ dgamma,
-                                        float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__device__ __forceinline__ void bn_bwd_from_sums_channel(int c, const double2* __restrict__ local,
+                                                         const double2* __restrict__ global, double cnt, int G, int C,
+                                                         const float4* __restrict__ bn_const,
+                                                         float4* __restrict__ bwd_const, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta) {
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
     const double2 gs = global[size_t(g) * C + c], ls = local[size_t(g) * C + c];
@@ -191,6 +209,22 @@ __global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const
   }
   dgamma[c] = float(tg);
   dbeta[c] = float(tb);
+}
+__global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const double2* __restrict__ global,
+                                        double cnt, int G, int C, const float4* __restrict__ bn_const,
+                                        float4* __restrict__ bwd_const, float* __restrict__ dgamma,
+                                        float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_bwd_from_sums_channel(c, local, global, cnt, G, C, bn_const, bwd_const, dgamma, dbeta);
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_sync_kernel(const double* __restrict__ local, double* __restrict__ total, const P2PPeers peers, unsigned int seq,
+                   double cnt, int G, int C, const float4* __restrict__ bn_const, float4* __restrict__ bwd_const,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  p2p_allreduce_block(local, 2 * G * C, peers, seq, total);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    bn_bwd_from_sums_channel(c, reinterpret_cast<const double2*>(local), reinterpret_cast<const double2*>(total), cnt, G,
+                             C, bn_const, bwd_const, dgamma, dbeta);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -765,6 +799,31 @@ int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, co
   return check_launch_t("bn_stats_from_sums");
 }
 
+static int p2p_check(void* const* peers, int rank, int world, int n, P2PPeers* out) {
+  if (peers == nullptr || world < 1 || world > kP2PMaxRanks || rank < 0 || rank >= world)
+    return set_error(VM_ERR_SHAPE, "p2p: bad rank / world (at most 8 ranks of one node)");
+  if (n > kP2PMaxDoubles) return set_error(VM_ERR_UNSUPPORTED, "p2p: vector too long for the exchange buffer");
+  for (int r = 0; r < world; ++r) {
+    if (peers[r] == nullptr) return set_error(VM_ERR_SHAPE, "p2p: null peer buffer");
+    out->buf[r] = peers[r];
+  }
+  out->rank = rank;
+  out->world = world;
+  return VM_OK;
+}
+
+int launch_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
+                         unsigned int seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* moving_mean, float* moving_var, float* bn_const, cudaStream_t st) {
+  if (G <= 0 || C <= 0 || !(count > 1.0)) return set_error(VM_ERR_SHAPE, "bn_stats_sync: bad shape");
+  P2PPeers pp{};
+  int rc = p2p_check(peers, rank, world, 2 * G * C, &pp);
+  if (rc) return rc;
+  bn_stats_sync_kernel<<<1, 256, 0, st>>>(local_sums, total_sums, pp, seq, count, G, C, gamma, beta, eps, momentum,
+                                          moving_mean, moving_var, reinterpret_cast<float4*>(bn_const));
+  return check_launch_t("bn_stats_sync");
+}
+
 int launch_bn_pool_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
                        __half* out_hi, __half* out_lo, uint16_t* out_q, cudaStream_t st) {
   if (C % 8 != 0 || N <= 0 || G <= 0 || N % G != 0 || lout <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
@@ -916,6 +975,25 @@ int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums,
   bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd_from_sums");
+}
+
+int launch_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
+                       unsigned int seq, double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax,
+                       const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                       float* bwd_const, float* dgamma, float* dbeta, const unsigned int* absmax, __half* du_hi,
+                       __half* du_lo, float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
+  if (rc) return rc;
+  if (local_sums == nullptr || total_sums == nullptr || !(count > 0.0))
+    return set_error(VM_ERR_SHAPE, "bn_bwd_sync: bad sums / count");
+  P2PPeers pp{};
+  if ((rc = p2p_check(peers, rank, world, 2 * G * C, &pp))) return rc;
+  bn_bwd_sync_kernel<<<1, 256, 0, st>>>(local_sums, total_sums, pp, seq, count, G, C,
+                                        reinterpret_cast<const float4*>(bn_const),
+                                        reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
+  bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
+               dbias_partial, dbias, red_scratch, st);
+  return check_launch_t("bn_bwd_sync");
 }
 
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,

@@ -223,6 +223,18 @@ def load_keras_weights(path):
     return cfg, layers
 
 
+def load_training_config(path):
+    """The ``training_config`` attribute of a full-model checkpoint (loss, metrics, optimizer_config), or None --
+    what keras.models.load_model uses to hand back a COMPILED model."""
+    import json
+    f = KerasH5(path)
+    try:
+        raw = f.attr("/", "training_config")
+    except (KeyError, ValueError):
+        return None
+    return json.loads(raw) if raw else None
+
+
 # ======================================================================================================================
 # Writer: the same subset of HDF5 the reader understands, laid out the way libhdf5 1.8/1.10 writes a Keras 2.2.x
 # ``model.save`` file (superblock v0, old-style groups = v1 B-tree + local heap + one symbol-table node, version-1 object

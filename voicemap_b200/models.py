@@ -307,6 +307,14 @@ class EncoderModel(_ModelBase):
                                  f"{new.shape} ({name})")
             self.weights[name] = new.copy()
         self._engine_dirty = True
+        self._drop_trainer()
+
+    def _drop_trainer(self):
+        """Weights set from the host supersede the device copies a TrainEngine holds (its parameter buffer, Adam
+        moments and recorded launch plans): the next fit / train step builds a fresh one from the new weights."""
+        for owner in (self, getattr(self, "_siamese_owner", None)):
+            if owner is not None and getattr(owner, "_trainer", None) is not None:
+                owner._trainer = None
 
     def set_named_weights(self, mapping):
         for name, value in mapping.items():
@@ -315,6 +323,7 @@ class EncoderModel(_ModelBase):
                 raise ValueError(f"{name}: expected {self.weights[name].shape}, got {value.shape}")
             self.weights[name] = value.copy()
         self._engine_dirty = True
+        self._drop_trainer()
 
     def get_config(self):
         return dict(kind="encoder", filters=self.filters, embedding_dimension=self.embedding_dimension,
@@ -333,7 +342,9 @@ class EncoderModel(_ModelBase):
             raise ValueError("precision must be 1, 2 or 3")
         if int(value) != self._precision:
             self._precision = int(value)
-            self._engine = None          # the engine is built for one arithmetic; the next predict() rebuilds it
+            if self._engine is not None:     # the packed weights carry the planes of every mode: the arithmetic is a
+                self._engine.precision = int(value)   # per-launch argument, so the engine (and a trainer's tensors
+                                                      # that live in it) stays
 
     def _clone(self):
         m = EncoderModel(self.filters, self.embedding_dimension, self.input_shape, self.dropout,
@@ -581,6 +592,7 @@ class SiameseModel(_ModelBase):
     def __init__(self, encoder, input_shape, distance_metric, seed=None):
         self.name = "model_1"
         self.encoder = encoder
+        encoder._siamese_owner = self        # host-side weight changes of the encoder invalidate this model's trainer
         self.input_shape = tuple(input_shape)
         self.distance_metric = distance_metric
         rng = np.random.default_rng(seed)
@@ -625,6 +637,7 @@ class SiameseModel(_ModelBase):
                 raise ValueError(f"{name}: expected {old.shape}, got {new.shape}")
             self.head_weights[name] = new.copy()
         self._head_dev = None
+        self._trainer = None
 
     def get_config(self):
         return dict(kind="siamese", encoder=self.encoder.get_config(), input_shape=self.input_shape,
@@ -881,13 +894,34 @@ def _load_keras_hdf5(filepath):
     return m
 
 
+def _compile_from_training_config(model, filepath):
+    """keras.models.load_model returns a compiled model when the file carries a training_config: same here, for the
+    losses / optimizer this package implements (anything else leaves the model un-compiled, with a warning)."""
+    import warnings
+    from .keras_hdf5 import load_training_config
+    tc = load_training_config(filepath)
+    if not tc:
+        return model
+    loss = tc.get("loss")
+    opt_cfg = (tc.get("optimizer_config") or {})
+    if opt_cfg.get("class_name") != "Adam" or loss not in ("binary_crossentropy", "categorical_crossentropy",
+                                                         "contrastive_loss"):
+        warnings.warn(f"checkpoint training_config (loss {loss!r}, optimizer {opt_cfg.get('class_name')!r}) is not "
+                      f"restored: compile the model before training")
+        return model
+    cfg = dict(opt_cfg.get("config") or {})
+    kwargs = {k: cfg[k] for k in ("lr", "beta_1", "beta_2", "epsilon", "decay", "clipnorm") if cfg.get(k) is not None}
+    model.compile(loss=loss, optimizer=Adam(**kwargs), metrics=list(tc.get("metrics") or []))
+    return model
+
+
 def load_model(filepath, custom_objects=None):
     """keras.models.load_model call site: experiments/k_way_accuracy.py:45.  Reads this package's npz container
     (counterpart of ``save``) and Keras 2.2.x HDF5 checkpoints (pure-Python reader, no h5py)."""
     with open(filepath, "rb") as fh:
         magic = fh.read(8)
     if magic == b"\x89HDF\r\n\x1a\n":
-        return _load_keras_hdf5(filepath)
+        return _compile_from_training_config(_load_keras_hdf5(filepath), filepath)
     with np.load(filepath) as z:
         cfg = json.loads(bytes(z["config"]).decode())
         weights = [z[f"w{i}"] for i in range(len(z.files) - 1)]

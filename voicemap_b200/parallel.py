@@ -77,6 +77,54 @@ class GradientBuckets:
         self.works = []
 
 
+class PeerExchange:
+    """Peer-memory exchange buffers for the cross-rank BatchNorm sums (``vm_bn_stats_sync`` / ``vm_bn_bwd_sync``,
+    csrc/vm_p2p.cuh): every rank of the node allocates one buffer in libvoicemap_b200.so, publishes its CUDA IPC handle
+    through ``torch.distributed`` (64 bytes per rank, once) and maps the others'.  The sums then travel over NVLink
+    inside the consuming kernel -- no collective call, no host involvement per step.  ``seq`` is the call counter every
+    rank advances in lockstep (``bump``) before each exchange; its ctypes object is handed to the launches, so recorded
+    launch plans see the current value.  At most 8 ranks, one node."""
+
+    def __init__(self):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        rank, ws = world()
+        if ws > 8:
+            raise _lib.VoicemapB200Error("peer-memory BatchNorm exchange supports at most 8 ranks of one node; set "
+                                         "VOICEMAP_SYNCBN=nccl for larger jobs")
+        own = C.c_void_p()
+        _lib.check(self.lib.vm_p2p_alloc(C.byref(own)), "vm_p2p_alloc")
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.vm_p2p_export(own, handle), "vm_p2p_export")
+        handles = [None] * ws
+        dist.all_gather_object(handles, handle.raw)
+        self.own, self.imported, ptrs = own, [], []
+        for r, h in enumerate(handles):
+            if r == rank:
+                ptrs.append(own.value)
+            else:
+                q = C.c_void_p()
+                _lib.check(self.lib.vm_p2p_import(h, C.byref(q)), f"vm_p2p_import (rank {r})")
+                self.imported.append(q)
+                ptrs.append(q.value)
+        self.peers = (C.c_void_p * ws)(*ptrs)
+        self.rank, self.world = rank, ws
+        self.seq = C.c_uint32(0)
+        dist.barrier()                       # every buffer is zeroed and mapped before the first exchange
+
+    def bump(self):
+        self.seq.value += 1
+
+    def close(self):
+        for q in self.imported:
+            self.lib.vm_p2p_unimport(q)
+        self.imported = []
+        if self.own is not None:
+            self.lib.vm_p2p_free(self.own)
+            self.own = None
+
+
 def broadcast_weights_(model, src=0):
     """Every rank takes rank ``src``'s weights (``model.get_weights()`` / ``set_weights``).  The reference's builders
     have no seed argument (voicemap/models.py:6,44), so independently launched ranks would start data-parallel

@@ -99,6 +99,7 @@ class TrainEngine:
         # the GLOBAL batch, as on the reference's single device; None = per-rank statistics
         self.sync_allreduce = None
         self.sync_world = 1
+        self.sync_peers = None     # parallel.PeerExchange: the BatchNorm sums cross the ranks inside the kernels (NVLink)
         self.grad_buckets = None   # parallel.GradientBuckets: per-block asynchronous gradient all-reduce (data parallel)
         if isinstance(model, SiameseModel):
             self.kind = "siamese"
@@ -278,7 +279,7 @@ class TrainEngine:
         self.x_in = self.xin
         self.groups = groups
         dropout_on = self._set_masks(nb, masks)
-        key = ("fwd", dropout_on, bool(update_moving), self.sync_allreduce is not None,
+        key = ("fwd", dropout_on, bool(update_moving), self.sync_allreduce is not None, self.sync_peers is not None,
                torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
@@ -308,6 +309,17 @@ class TrainEngine:
                 plan.launch(lib.vm_bn_stats_finalize, "vm_bn_stats_finalize", _ptr(self.stat[b]), self.stat_rows[b], nb,
                             groups, ls[b], c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]),
                             _ptr(self.red), st)
+            elif self.sync_peers is not None:
+                pe = self.sync_peers
+                k = groups * c[b] * 2
+                loc, glo = self.sums[0][:k], self.sums[1][:k]
+                plan.launch(lib.vm_bn_stats_sums, "vm_bn_stats_sums", _ptr(self.stat[b]), self.stat_rows[b], nb, groups,
+                            c[b], _ptr(self.red), _ptr(loc), st)
+                plan.host(pe.bump)
+                count = float(self.sync_world) * (nb // groups) * ls[b]   # equal shards on every rank
+                plan.launch(lib.vm_bn_stats_sync, "vm_bn_stats_sync", _ptr(loc), _ptr(glo), pe.peers, pe.rank, pe.world,
+                            pe.seq, C.c_double(count), groups, c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv),
+                            _ptr(self.bnc[b]), st)
             else:
                 sums = self.sums[1][:groups * c[b] * 2]
                 plan.launch(lib.vm_bn_stats_sums, "vm_bn_stats_sums", _ptr(self.stat[b]), self.stat_rows[b], nb, groups,
@@ -345,19 +357,22 @@ class TrainEngine:
             self.grad_buckets = None
         self._plans = {k: v for k, v in self._plans.items() if k[0] != "bwd"}
 
-    def set_sync_bn(self, allreduce, world):
+    def set_sync_bn(self, allreduce, world, peers=None):
         """allreduce(tensor): in-place SUM over ranks (torch.distributed.all_reduce); world: number of ranks, each
-        feeding the same number of clips per step.  allreduce=None restores per-rank statistics."""
+        feeding the same number of clips per step.  allreduce=None restores per-rank statistics.  ``peers``
+        (parallel.PeerExchange) replaces the collective calls by the kernels that sum over NVLink peer memory."""
         self.sync_allreduce = allreduce
         self.sync_world = int(world) if allreduce is not None else 1
+        self.sync_peers = peers if allreduce is not None else None
+        self._plans = {}
 
     # ------------------------------------------------------------------ backward of the encoder
     def backward_encoder(self, d_emb):
         """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters."""
         if d_emb.data_ptr() != self.d_emb.data_ptr():
             self.d_emb.copy_(d_emb)
-        key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None, self.grad_buckets is not None,
-               torch.cuda.current_stream().cuda_stream)
+        key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None, self.sync_peers is not None,
+               self.grad_buckets is not None, torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = self._build_backward_plan(self.d_emb.shape[0])
@@ -387,6 +402,20 @@ class TrainEngine:
                             _ptr(dg), _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
                             _ptr(self.masks[b]), _ptr(self.scr2), _ptr(self.bwc[b]), *grads, gabs, _ptr(du_hi),
                             _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
+            elif self.sync_peers is not None:
+                pe = self.sync_peers
+                k = groups * c[b] * 2
+                loc, glo = self.sums[0][:k], self.sums[1][:k]
+                plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.EXT[b]), _ptr(dy), _ptr(dg),
+                            _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
+                            _ptr(self.scr2), gabs, _ptr(self.red), _ptr(loc), st)
+                plan.host(pe.bump)
+                count = float(self.sync_world) * (nb // groups) * ls[b]
+                plan.launch(lib.vm_bn_bwd_sync, f"vm_bn_bwd_sync block {b + 1}", _ptr(loc), _ptr(glo), pe.peers, pe.rank,
+                            pe.world, pe.seq, C.c_double(count), _ptr(self.U16[b]), _ptr(dy), _ptr(dg), _ptr(js), nb,
+                            ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.bwc[b]),
+                            *grads, gabs, _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
+                            _ptr(self.red), st)
             else:
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
@@ -659,6 +688,24 @@ class _Prefetcher:
         self.stop = True
 
 
+def sync_bn_peers(trainer=None):
+    """The peer-memory exchange for synchronised BatchNorm (parallel.PeerExchange), created once per process --
+    or None when VOICEMAP_SYNCBN=nccl asks for the collective-call form (jobs beyond one node / 8 ranks)."""
+    if os.environ.get("VOICEMAP_SYNCBN", "p2p").lower() == "nccl":
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+        return None                          # gloo (CPU tests of the host logic): collective calls
+    global _PEERS
+    if _PEERS is None:
+        from .parallel import PeerExchange
+        _PEERS = PeerExchange()
+    return _PEERS
+
+
+_PEERS = None
+
+
 def _dist_info():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -702,7 +749,8 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
     allreduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
     # BatchNorm sees the whole batch in the reference (one device); data-parallel ranks therefore share their batch
     # statistics unless the model opts out with ``model.sync_batchnorm = False``
-    trainer.set_sync_bn(allreduce if getattr(model, "sync_batchnorm", True) else None, world)
+    want_sync = world > 1 and getattr(model, "sync_batchnorm", True)
+    trainer.set_sync_bn(allreduce if want_sync else None, world, peers=sync_bn_peers(trainer) if want_sync else None)
     trainer.set_gradient_buckets(world > 1)     # per-block asynchronous gradient all-reduce inside the backward pass
     callbacks = list(callbacks or [])
     for cb in callbacks:
@@ -746,9 +794,12 @@ def fit_generator(model, generator, steps_per_epoch=None, epochs=1, verbose=1, c
             finally:
                 if ordered is not None:
                     ordered.close()
-            logs = {"loss": float(torch.stack(losses).mean().item())}
+            # data parallel: every rank reports the mean over the GLOBAL batches, so that callbacks steered by the logs
+            # (ReduceLROnPlateau, ModelCheckpoint, EarlyStopping) take the same decisions on every rank
+            from .parallel import global_mean
+            logs = {"loss": global_mean(float(torch.stack(losses).sum().item()), len(losses))}
             if "accuracy" in (model.metrics or []) or "acc" in (model.metrics or []):
-                logs["acc"] = float(torch.stack(accs).mean().item())
+                logs["acc"] = global_mean(float(torch.stack(accs).sum().item()), len(accs))
             trainer.sync_to_model()
             if validation_data is not None:
                 vl, va = _validate(model, trainer, validation_data, val_iter, validation_steps)
@@ -801,4 +852,7 @@ def _validate(model, trainer, validation_data, val_iter, validation_steps):
         tot += n
         tl += lv * n
         ta += acc * n
+    if _dist_info()[1] > 1:
+        from .parallel import global_mean
+        return global_mean(tl, tot), global_mean(ta, tot)
     return tl / max(tot, 1), ta / max(tot, 1)
