@@ -182,10 +182,17 @@ int vm_conv3_train_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int 
 /* Data gradient of a block's convolution: dX (N, L, Cin) fp32 = conv3(dU, flipped/transposed kernel).  du_hi / du_lo
  * (N, L, Cout): the scaled fp16 gradient planes vm_bn_bwd wrote, grad_absmax the word it derived their power-of-two
  * scale from (the epilogue takes the scale out again).  precision 3: dUh*Wh + dUl*Wh + dUh*Wl; 2: one-plane gradient
- * (du_lo NULL), dUh*Wh + dUh*Wl; 1: dUh*Wh. */
+ * (du_lo NULL), dUh*Wh + dUh*Wl; 1: dUh*Wh.
+ * below_* (optional, below_partial NULL = off): the BatchNorm-backward reduction of the block BELOW, whose pooled
+ * gradient this call produces, taken in the epilogue while the values are in registers: below_ext (N, L, Cin) its
+ * window extremes, below_bn_const (G, Cin) x 4, below_mask (N, Cin) or NULL -> below_partial, vm_stat_rows_per_clip(L)
+ * rows of Cpad float2 {sum dy, sum dy * xhat} per clip, and *below_absmax (largest |s * dy|).  The following
+ * vm_bn_bwd of that block is then called with presummed_rows_per_clip = vm_stat_rows_per_clip(L), scratch_f2 =
+ * below_partial, grad_absmax = below_absmax, and skips its own pass over the pooled tensors. */
 int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int cin,
                    const void* wpack_dgrad, const float* epi_dgrad, const uint32_t* grad_absmax, float* dx,
-                   int precision, void* stream);
+                   int precision, const float* below_ext, const float* below_bn_const, const float* below_mask,
+                   int below_groups, float* below_partial, uint32_t* below_absmax, void* stream);
 int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
 /* bytes of the `red_scratch` buffer the two-stage (deterministic, atomics-free) channel reductions need */
 size_t vm_reduce_scratch_bytes(int G, int C);
@@ -222,7 +229,7 @@ size_t vm_bn_bwd_scratch_elems(int N);
 int vm_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
               int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
               float* bwd_const, float* dgamma, float* dbeta, uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
-              float* scratch_f, float* dbias, double* red_scratch, void* stream);
+              float* scratch_f, float* dbias, double* red_scratch, int presummed_rows_per_clip, void* stream);
 /* Synchronised BatchNorm across data-parallel ranks (the reference's BN sees the whole batch on one
  * device).  The two calls above are split at the point where the per-(group, channel) sums exist, so that the caller
  * can all-reduce them (torch.distributed / NCCL) in between:
@@ -238,7 +245,7 @@ int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const 
                           void* stream);
 int vm_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L,
                    int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
-                   uint32_t* grad_absmax, double* red_scratch, double* sums, void* stream);
+                   uint32_t* grad_absmax, double* red_scratch, double* sums, int presummed_rows_per_clip, void* stream);
 int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
                         const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L, int C, int G,
                         int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,

@@ -59,7 +59,7 @@ SIGNATURES = {
                            C.POINTER(_vp), _vp]),
     "vm_conv1_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "vm_conv3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "vm_conv3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "vm_stat_rows_per_clip": (_i, [_i]),
     "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "vm_reduce_scratch_bytes": (_sz, [_i, _i]),
@@ -70,10 +70,10 @@ SIGNATURES = {
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd_scratch_elems": (_sz, [_i]),
     "vm_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp, _vp]),
+                       _vp, _vp, _i, _vp]),
     "vm_bn_stats_sums": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "vm_bn_stats_from_sums": (_i, [_vp, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
-    "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vm_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_bn_bwd_from_sums": (_i, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_p2p_buffer_bytes": (_sz, []),

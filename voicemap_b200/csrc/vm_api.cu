@@ -246,7 +246,8 @@ int vm_conv3_train_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int 
 }
 int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int cin,
                    const void* wpack_dgrad, const float* epi_dgrad, const uint32_t* grad_absmax, float* dx,
-                   int precision, void* stream) {
+                   int precision, const float* below_ext, const float* below_bn_const, const float* below_mask,
+                   int below_groups, float* below_partial, uint32_t* below_absmax, void* stream) {
   if (du_hi == nullptr || wpack_dgrad == nullptr || epi_dgrad == nullptr || dx == nullptr)
     return set_error(VM_ERR_SHAPE, "conv3_dgrad: null pointer");
   if (precision < 1 || precision > 3) return set_error(VM_ERR_SHAPE, "conv3_dgrad: precision must be 1, 2 or 3");
@@ -254,6 +255,14 @@ int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, i
   Conv3Extra ex;
   ex.grad_absmax = grad_absmax;
   ex.x_single = (precision == 2) ? 1 : 0;
+  if (below_partial != nullptr) {
+    ex.red.ext = below_ext;
+    ex.red.bn_const = reinterpret_cast<const float4*>(below_bn_const);
+    ex.red.mask = below_mask;
+    ex.red.G = below_groups;
+    ex.red.partial = reinterpret_cast<float2*>(below_partial);
+    ex.red.absmax = below_absmax;
+  }
   // the gradient is the "input" operand of this convolution (channels = Cout of the forward conv), the output has Cin
   return launch_conv3(CH16(du_hi), CH16(du_lo), N, L, cout, cin, static_cast<const __half*>(wpack_dgrad), epi_dgrad,
                       nullptr, nullptr, nullptr, dx, nullptr, /*linear=*/1, precision == 1 ? 1 : 3, g_max_ctas, ST, ex);
@@ -290,9 +299,10 @@ size_t vm_bn_bwd_scratch_elems(int N) { return bn_bwd_scratch_elems(N); }
 int vm_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
               int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
               float* bwd_const, float* dgamma, float* dbeta, uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
-              float* scratch_f, float* dbias, double* red_scratch, void* stream) {
+              float* scratch_f, float* dbias, double* red_scratch, int presummed_rows_per_clip, void* stream) {
   return launch_bn_bwd(u16, ext, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, scratch_f2, bwd_const,
-                       dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch, ST);
+                       dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo), scratch_f, dbias, red_scratch,
+                       presummed_rows_per_clip, ST);
 }
 int vm_bn_stats_sums(const float* stat_partial, int rows_per_clip, int N, int G, int C, double* red_scratch,
                      double* sums, void* stream) {
@@ -305,9 +315,10 @@ int vm_bn_stats_from_sums(const double* sums, double count, int G, int C, const 
 }
 int vm_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L,
                    int C, int G, int pool, const float* bn_const, const float* mask, float* scratch_f2,
-                   uint32_t* grad_absmax, double* red_scratch, double* sums, void* stream) {
+                   uint32_t* grad_absmax, double* red_scratch, double* sums, int presummed_rows_per_clip,
+                   void* stream) {
   return launch_bn_bwd_sums(ext, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, scratch_f2, grad_absmax,
-                            red_scratch, sums, ST);
+                            red_scratch, sums, presummed_rows_per_clip, ST);
 }
 int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
                         const float* dy_pooled, const float* d_gmax, const int32_t* jstar, int N, int L, int C, int G,

@@ -179,27 +179,62 @@ __device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t t
 
 // fp32 epilogue of one accumulator tile for one warp (dgrad): granule = 16 positions x 128 channels fp32 = 4 boxes of
 // 32 channels, pipelined TMEM loads, staging buffers handed to the store warp (see raw2_tile).
+// kReduce: also accumulate, per channel, the BatchNorm-backward sums of the block below from the values in registers
+// (red_*: the thread's channel constants; erow: its column of the window extremes of this clip; lrem: valid positions
+// from this tile's first one).
+template <bool kReduce>
 __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8_t* stage, int ch, int chalf,
-                                            Conv3Barriers* bars, int buf, uint32_t& gcount) {
+                                            Conv3Barriers* bars, int buf, uint32_t& gcount, const float* erow,
+                                            size_t estride, int lrem, float mk, float mean, float rstd, float sabs,
+                                            float& s1, float& s2, float& amax) {
   using namespace c3;
   const uint32_t off = (ch >> 5) * 2048 + (chalf * 8) * 128 + (ch & 31) * 4;
-  auto granule = [&](const uint32_t (&r)[8]) {
+  int gr_pos = chalf * 8;   // first position (relative to the tile) of the granule being processed
+  auto load_ext = [&](float (&e)[8], int pos) {   // the thread's 8 window extremes of the granule starting at pos
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = (pos + j < lrem) ? __ldg(erow + size_t(pos + j) * estride) : mean;
+  };
+  // the extremes are fetched TWO granules ahead (registers ea / eb alternate like the TMEM loads): a global load has
+  // two granules of epilogue work to land, the first version (loads issued inside the granule that used them) exposed
+  // one DRAM latency per granule and doubled the kernel time.  (Also tried: prefetch.global.L2 of the next tile's
+  // extremes at tile start -- 8 % slower, the epilogue is issue-bound once the latency is covered.)
+  auto granule = [&](const uint32_t (&r)[8], float (&e)[8]) {
     const int sb = gcount & 1;
     const uint32_t st = smem_u32(stage + sb * kStageBufBytes) + off;
     if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+    float dy[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sts_f32(st + j * 128, __uint_as_float(r[j]) * unscale);
+    for (int j = 0; j < 8; ++j) {
+      dy[j] = __uint_as_float(r[j]) * unscale;
+      sts_f32(st + j * 128, dy[j]);
+    }
     fence_proxy_async_smem();
     mbar_arrive(&bars->sfull[sb]);
+    if (kReduce) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = (gr_pos + j < lrem) ? dy[j] * mk : 0.f;
+        s1 += d;
+        s2 = fmaf(d, (e[j] - mean) * rstd, s2);
+        amax = fmaxf(amax, fabsf(d) * sabs);
+      }
+      load_ext(e, gr_pos + 32);
+    }
+    gr_pos += 16;
     ++gcount;
   };
   uint32_t ra[8], rb[8];
+  float ea[8], eb[8];
+  if (kReduce) {
+    load_ext(ea, gr_pos);
+    load_ext(eb, gr_pos + 16);
+  }
   tmem_ld_32x8_issue(taddr + chalf * 8, ra);
 #pragma unroll 1
   for (int gr = 0; gr < kTileN / 16; gr += 2) {
     tmem_ld_wait(ra);
     tmem_ld_32x8_issue(taddr + (gr + 1) * 16 + chalf * 8, rb);
-    granule(ra);
+    granule(ra, ea);
     tmem_ld_wait(rb);
     if (gr + 2 < kTileN / 16) {
       tmem_ld_32x8_issue(taddr + (gr + 2) * 16 + chalf * 8, ra);
@@ -207,7 +242,7 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
       tc_fence_before_sync();
       mbar_arrive(&bars->tempty[buf]);
     }
-    granule(rb);
+    granule(rb, eb);
   }
 }
 
@@ -526,7 +561,23 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         // gradient planes carry a power-of-two scale (vm_common.cuh), taken out here
         const float unscale = (p.grad_absmax != nullptr)
                                   ? 1.0f / grad_scale_from_absmax(__uint_as_float(*p.grad_absmax)) : 1.0f;
-        linear_tile(unscale, taddr, stage, ch, chalf, bars, buf, gcount);
+        float s1 = 0.f, s2 = 0.f, amax = 0.f;
+        if (p.red.partial != nullptr) {
+          // BatchNorm-backward sums of the block below, from the gradient values this thread is about to store
+          const bool live = co < p.cout;
+          const int g = n / (p.N / p.red.G);
+          const float4 bc = live ? p.red.bn_const[size_t(g) * p.cout + co] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float mk = live ? (p.red.mask ? p.red.mask[size_t(n) * p.cout + co] : 1.f) : 0.f;
+          const float* erow = p.red.ext + (size_t(n) * p.L + p0) * p.cout + (live ? co : 0);
+          linear_tile<true>(unscale, taddr, stage, ch, chalf, bars, buf, gcount, erow, size_t(p.cout),
+                            live ? p.L - p0 : 0, mk, bc.z, bc.w, fabsf(bc.x), s1, s2, amax);
+          p.red.partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+          for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+          if (lane == 0 && amax > 0.f) atomicMax(p.red.absmax, __float_as_uint(amax));
+        } else {
+          linear_tile<false>(unscale, taddr, stage, ch, chalf, bars, buf, gcount, nullptr, 0, 0, 0.f, 0.f, 0.f, 0.f, s1,
+                             s2, amax);
+        }
       } else {
         // pooled outputs: granule = 16 pooled positions x 128 channels x 2 planes; the two warps of a lane quarter
         // take 16 raw columns (8 pooled positions) each.
@@ -592,6 +643,14 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
   p.x_single = extra.x_single;
   p.out_u16 = extra.out_u16; p.out_ext = extra.out_ext; p.sign_src = extra.sign_src;
   p.grad_absmax = extra.grad_absmax;
+  p.red = extra.red;
+  if (p.red.partial != nullptr) {
+    if (!linear || out_f32 == nullptr || p.red.ext == nullptr || p.red.bn_const == nullptr || p.red.absmax == nullptr ||
+        p.red.G <= 0 || N % p.red.G != 0)
+      return set_error(VM_ERR_SHAPE, "conv3: the fused BatchNorm-backward reduction goes with the dgrad output");
+    cudaError_t me = cudaMemsetAsync(p.red.absmax, 0, sizeof(unsigned int), stream);
+    if (me != cudaSuccess) return set_cuda_error(me, "conv3: memset");
+  }
 
   CUtensorMap xh_main, xh_halo, xl_main, xl_halo, wh, wl;
   // X planes: (N, L, Cin) fp16, dims fastest-first {Cin, L, N}

@@ -53,6 +53,14 @@ int launch_preprocess_stats(const float* x, int N, int T, int stride, int G, flo
                             cudaStream_t stream);
 
 // ---- blocks 2-4 ----
+struct Conv3Reduce {
+  const float* ext = nullptr;       // (N, L, cout) window extremes of the block below (its pooled positions = this L)
+  const float4* bn_const = nullptr; // (G, cout) {s, t, mean, rstd} of the block below
+  const float* mask = nullptr;      // (N, cout) dropout mask of the block below, or null
+  int G = 1;
+  float2* partial = nullptr;        // (N * 2 * nptile, cout_pad) {sum dy, sum dy * xhat} rows, one per (tile, column half)
+  unsigned int* absmax = nullptr;   // raised with atomicMax (float bits of max |s * dy|)
+};
 struct Conv3Params {
   int N, L, cin, cout, cout_pad;
   int lout;              // L / 2
@@ -75,6 +83,9 @@ struct Conv3Params {
   float* out_ext;
   const float* sign_src;
   const uint32_t* grad_absmax;  // dgrad: bits of the largest |s * dy| of the block -> power-of-two unscale, or null
+  // dgrad epilogue, optional: the BatchNorm-backward reduction of the block BELOW (whose pooled gradient this kernel
+  // writes) -- per-channel partial sums of dy and dy * xhat and the largest |s * dy|, taken while dy is in registers
+  Conv3Reduce red;
 };
 struct Conv3Extra {            // optional arguments of launch_conv3 beyond the eval-forward set
   uint16_t* out_u16 = nullptr;
@@ -82,6 +93,7 @@ struct Conv3Extra {            // optional arguments of launch_conv3 beyond the 
   const float* sign_src = nullptr;
   const uint32_t* grad_absmax = nullptr;
   int x_single = 0;
+  Conv3Reduce red = Conv3Reduce();
 };
 int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin, int cout, const __half* wpack,
                  const float* epi, __half* out_hi, __half* out_lo, float* gmax_partial, float* out_f32,
@@ -123,7 +135,7 @@ size_t bn_bwd_scratch_elems(int N);
 int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
                   float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax, __half* du_hi, __half* du_lo,
-                  float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st);
+                  float* dbias_partial, float* dbias, double* red_scratch, int presummed_rows, cudaStream_t st);
 // split forms for synchronised BatchNorm (sums -> caller's all-reduce -> constants)
 int launch_bn_stats_sums(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C, double* red_scratch,
                          double* sums, cudaStream_t st);
@@ -132,7 +144,7 @@ int launch_bn_stats_from_sums(const double* sums, double count, int G, int C, co
                               cudaStream_t st);
 int launch_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L,
                        int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
-                       unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st);
+                       unsigned int* absmax, double* red_scratch, double* sums, int presummed_rows, cudaStream_t st);
 int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums, double count, const uint16_t* u16,
                             const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L, int C, int G,
                             int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,

@@ -892,9 +892,18 @@ size_t bn_bwd_scratch_elems(int N) {
 template <class Fin>
 static int bn_bwd_reduce(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N,
                          int lout, int C, int G, const float* bn_const, const float* mask, float* partial,
-                         unsigned int* absmax, double* red_scratch, const Fin& fin, cudaStream_t st) {
+                         unsigned int* absmax, double* red_scratch, const Fin& fin, int presummed_rows,
+                         cudaStream_t st) {
   if (C > 2048) return set_error(VM_ERR_UNSUPPORTED, "bn_bwd: C > 2048");
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
+  if (presummed_rows > 0) {
+    // the dgrad kernel of the block above already left `presummed_rows` partial rows per clip (padded-channel stride)
+    // and the gradient-scale word: only the deterministic column reduction + finishing step remain
+    const int c_pad = (C + 127) / 128 * 128;
+    rowsum_fused_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+        partial, size_t(N / G) * presummed_rows, c_pad, C, tmp, fin);
+    return VM_OK;
+  }
   cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return set_cuda_error(e, "bn_bwd: memset");
   const int streams = ew_streams(C, 4);
@@ -933,13 +942,13 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
 int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
                   float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax, __half* du_hi, __half* du_lo,
-                  float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
+                  float* dbias_partial, float* dbias, double* red_scratch, int presummed_rows, cudaStream_t st) {
   int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
   const BnBwdFin fin{N, G, L, C, reinterpret_cast<const float4*>(bn_const), reinterpret_cast<float4*>(bwd_const),
                      dgamma, dbeta};
   if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
-                          red_scratch, fin, st)))
+                          red_scratch, fin, presummed_rows, st)))
     return rc;
   bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
@@ -948,13 +957,13 @@ int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled,
 
 int launch_bn_bwd_sums(const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar, int N, int L,
                        int C, int G, int pool, const float* bn_const, const float* mask, float* partial,
-                       unsigned int* absmax, double* red_scratch, double* sums, cudaStream_t st) {
+                       unsigned int* absmax, double* red_scratch, double* sums, int presummed_rows, cudaStream_t st) {
   int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
   if (rc) return rc;
   if (sums == nullptr) return set_error(VM_ERR_SHAPE, "bn_bwd_sums: null sums");
   const SumsFin fin{G, C, reinterpret_cast<double2*>(sums)};
   if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
-                          red_scratch, fin, st)))
+                          red_scratch, fin, presummed_rows, st)))
     return rc;
   return check_launch_t("bn_bwd_sums");
 }

@@ -184,7 +184,7 @@ class TrainEngine:
         key = (nb, length, groups)
         if self._buf_key == key:
             return
-        self.U16 = self.EXT = self.X = self.XL = self.XQ = self.dU = self.dX = self.scr1 = self.scr2 = None   # free before regrowing
+        self.U16 = self.EXT = self.X = self.XL = self.XQ = self.redp = self.dU = self.dX = self.scr1 = self.scr2 = None   # free before regrowing
         dev, f32, f16 = self.device, torch.float32, torch.float16
         ls = [length]
         for p in self.pools:
@@ -218,6 +218,9 @@ class TrainEngine:
         max_u = max(ls[b] * c[b] for b in range(4))
         self.dU = torch.empty((2 if self.bwd_precision == 3 else 1, nb * max_u), dtype=f16, device=dev)
         self.gabs = torch.zeros((4,), dtype=torch.int32, device=dev)   # per block: bits of max |s * dy| -> gradient scale
+        # blocks 1-3: partial rows of the BatchNorm-backward sums, written by the dgrad epilogue of the block above
+        self.redp = [torch.empty((nb * self.lib.vm_stat_rows_per_clip(ls[b + 1]), self.lib.vm_padded_channels(c[b]), 2),
+                                 dtype=f32, device=dev) for b in range(3)]
         max_x = max(ls[b + 1] * c[b] for b in range(3))
         self.dX = torch.empty(nb * max_x, dtype=f32, device=dev)
         scr_elems = self.lib.vm_bn_bwd_scratch_elems(nb)
@@ -397,18 +400,21 @@ class TrainEngine:
             else:
                 dy, dg, js = self.dX, None, None
             grads = (_ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]))
+            # blocks 1-3: the sums of dy and dy * xhat were taken by the dgrad epilogue of the block above
+            pre_rows = lib.vm_stat_rows_per_clip(ls[b + 1]) if b < 3 else 0
+            part = self.redp[b] if b < 3 else self.scr2
             if self.sync_allreduce is None:
                 plan.launch(lib.vm_bn_bwd, f"vm_bn_bwd block {b + 1}", _ptr(self.U16[b]), _ptr(self.EXT[b]), _ptr(dy),
                             _ptr(dg), _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
-                            _ptr(self.masks[b]), _ptr(self.scr2), _ptr(self.bwc[b]), *grads, gabs, _ptr(du_hi),
-                            _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
+                            _ptr(self.masks[b]), _ptr(part), _ptr(self.bwc[b]), *grads, gabs, _ptr(du_hi),
+                            _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), pre_rows, st)
             elif self.sync_peers is not None:
                 pe = self.sync_peers
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
                 plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.EXT[b]), _ptr(dy), _ptr(dg),
                             _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
-                            _ptr(self.scr2), gabs, _ptr(self.red), _ptr(loc), st)
+                            _ptr(part), gabs, _ptr(self.red), _ptr(loc), pre_rows, st)
                 plan.host(pe.bump)
                 count = float(self.sync_world) * (nb // groups) * ls[b]
                 plan.launch(lib.vm_bn_bwd_sync, f"vm_bn_bwd_sync block {b + 1}", _ptr(loc), _ptr(glo), pe.peers, pe.rank,
@@ -421,7 +427,7 @@ class TrainEngine:
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
                 plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.EXT[b]), _ptr(dy), _ptr(dg),
                             _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
-                            _ptr(self.scr2), gabs, _ptr(self.red), _ptr(loc), st)
+                            _ptr(part), gabs, _ptr(self.red), _ptr(loc), pre_rows, st)
 
                 def share(loc=loc, glo=glo):
                     glo.copy_(loc)
@@ -446,8 +452,11 @@ class TrainEngine:
                 if buckets is not None:    # block b+1's gradients are complete: share them while dgrad and the
                     plan.host(lambda i=4 - b: buckets.launch(i))   # blocks below keep the device busy
                 # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
+                # ... and, in its epilogue, the BatchNorm-backward sums of block b (dX is that block's pooled gradient)
                 plan.launch(lib.vm_conv3_dgrad, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
-                            c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), gabs, _ptr(self.dX), bp, st)
+                            c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), gabs, _ptr(self.dX), bp,
+                            _ptr(self.EXT[b - 1]), _ptr(self.bnc[b - 1]), _ptr(self.masks[b - 1]), groups,
+                            _ptr(self.redp[b - 1]), _ptr(self.gabs[b - 1:b]), st)
         return plan
 
     # ------------------------------------------------------------------ optimizer
