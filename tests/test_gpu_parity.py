@@ -472,6 +472,7 @@ def test_siamese_probability_and_loss_at_config3_shape(stress_params, loss):
     256-clip launch) -> fused head + loss kernel, against the fp64 oracle at |d| / |ref| <= 1e-4 for the probabilities
     and the loss (voicemap/models.py:64-69, voicemap/utils.py:77-85)."""
     from voicemap_b200.keras_compat import Adam
+    from voicemap_b200 import models as M
     from voicemap_b200 import utils
     pairs, length = 128, 12000
     enc = M.get_baseline_convolutional_encoder(128, 64, dropout=0.0)
