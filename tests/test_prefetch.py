@@ -129,6 +129,7 @@ def test_fit_generator_uses_the_producers(monkeypatch):
 
     class StubEngine:
         kind = "siamese"
+        bwd_precision = 1
 
         def __init__(self, model, optimizer, loss):
             self.optimizer, self.loss = optimizer, loss

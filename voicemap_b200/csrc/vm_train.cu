@@ -617,11 +617,11 @@ struct BnBwdFin {
 // sum_positions dU per channel (un-scaled).  Per channel the expression is affine in u and dy:
 //   dU = A*dy + B + Cc*u,  A = s*mk,  B = s*(mean*rstd*mean_dyxhat - mean_dy),  Cc = -s*rstd*mean_dyxhat
 // with u and the arg-max flag decoded from the 16-bit activation word.  grid (N, chunks) over pool windows.
-template <bool kSparse, int kPlanes>
-__global__ void __launch_bounds__(kEwThreads)
+template <bool kSparse, int kPlanes, int kPool>
+__global__ void __launch_bounds__(kEwThreads, 2)
 bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ dy_pooled,
                    const float* __restrict__ d_gmax, const int* __restrict__ jstar, int N, int L, int C, int G,
-                   int pool, const float4* __restrict__ bn_const, const float4* __restrict__ bwd_const,
+                   int /*pool == kPool*/, const float4* __restrict__ bn_const, const float4* __restrict__ bwd_const,
                    const float* __restrict__ mask, const unsigned int* __restrict__ absmax,
                    __half* __restrict__ du_hi, __half* __restrict__ du_lo, float* __restrict__ dbias_partial) {
   const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
@@ -629,6 +629,7 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
   if (int(threadIdx.x) >= groups * streams) return;
   const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 8 * cg;
   const int g = n / (N / G);
+  constexpr int pool = kPool;
   const int lout = L / pool;
   const int wins = (L + pool - 1) / pool;
   const int per = (wins + chunks - 1) / chunks;
@@ -652,14 +653,14 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
     }
   }
   struct Window {
-    uint4 ur[4];    // the window's rows of 8 encoded activations (pool <= 4)
-    float4 d0, d1;  // its pooled gradient
+    uint4 ur[kPool];  // the window's rows of 8 encoded activations
+    float4 d0, d1;    // its pooled gradient
   };
   auto load_window = [&](int w, Window& W) {
     const int l0 = w * pool, wl = min(pool, L - l0);
     const uint16_t* up = u16 + (size_t(n) * L + l0) * C + c;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kPool; ++i)
       W.ur[i] = (i < wl) ? __ldcs(reinterpret_cast<const uint4*>(up + size_t(i) * C)) : make_uint4(0u, 0u, 0u, 0u);
     if (!kSparse && w < lout) {
       const float4* dp = reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c);
@@ -671,44 +672,55 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
   };
   auto apply_window = [&](int w, const Window& W) {
     const int l0 = w * pool, wl = min(pool, L - l0);
-    float add[8];   // A * dy of this window: what the flagged element receives on top of the statistics terms
+    float Bf[8];   // B + A * dy of this window: what the flagged element receives instead of B
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float dy = kSparse ? ((w == js[k]) ? dg[k] : 0.f) : (k < 4 ? f4get(W.d0, k) : f4get(W.d1, k - 4));
-      add[k] = A[k] * dy;
+      Bf[k] = fmaf(A[k], dy, B[k]);
     }
+    __half* oh = du_hi + (size_t(n) * L + l0) * C + c;
+    __half* ol = (kPlanes == 2) ? du_lo + (size_t(n) * L + l0) * C + c : nullptr;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPool; ++i) {
       if (i < wl) {
         const uint32_t wd[4] = {W.ur[i].x, W.ur[i].y, W.ur[i].z, W.ur[i].w};
-        __half h[8], lo[8];
+        uint32_t ph[4], pl[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t bits = (wd[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-          const float u = decode_u(bits);
-          float du = fmaf(Cc[k], u, (bits & 0x8000u) ? B[k] + add[k] : B[k]);
-          if ((bits & 0x7FFFu) == 0u) du = 0.f;      // relu'(u)
-          sb[k] += du;
-          h[k] = __float2half_rn(du);
-          if (kPlanes == 2) lo[k] = __float2half_rn(du - __half2float(h[k]));
+        for (int q = 0; q < 4; ++q) {   // two channels per 32-bit word: paired conversions both ways
+          const uint32_t mag = wd[q] & 0x7FFF7FFFu;
+          const __half2 uh = *reinterpret_cast<const __half2*>(&mag);
+          const float2 u = __half22float2(uh);
+          const float b0 = (wd[q] & 0x8000u) ? Bf[2 * q] : B[2 * q];
+          const float b1 = (int(wd[q]) < 0) ? Bf[2 * q + 1] : B[2 * q + 1];
+          float d0 = fmaf(Cc[2 * q], u.x, b0), d1 = fmaf(Cc[2 * q + 1], u.y, b1);
+          d0 = (u.x > 0.f) ? d0 : 0.f;      // relu'(u)
+          d1 = (u.y > 0.f) ? d1 : 0.f;
+          sb[2 * q] += d0;
+          sb[2 * q + 1] += d1;
+          const __half2 h = __floats2half2_rn(d0, d1);
+          ph[q] = *reinterpret_cast<const uint32_t*>(&h);
+          if (kPlanes == 2) {
+            const float2 hf = __half22float2(h);
+            const __half2 lo = __floats2half2_rn(d0 - hf.x, d1 - hf.y);
+            pl[q] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
         }
-        const size_t o = (size_t(n) * L + l0 + i) * C + c;
-        __stcs(reinterpret_cast<uint4*>(du_hi + o),
-               make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7])));
-        if (kPlanes == 2)
-          __stcs(reinterpret_cast<uint4*>(du_lo + o),
-                 make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7])));
+        __stcs(reinterpret_cast<uint4*>(oh + size_t(i) * C), make_uint4(ph[0], ph[1], ph[2], ph[3]));
+        if (kPlanes == 2) __stcs(reinterpret_cast<uint4*>(ol + size_t(i) * C), make_uint4(pl[0], pl[1], pl[2], pl[3]));
       }
     }
   };
-  // two windows in flight per thread
-  for (int w = w0 + stream; w < w1; w += 2 * streams) {
-    Window Wa, Wb;
-    const bool two = (w + streams < w1);
-    load_window(w, Wa);
-    if (two) load_window(w + streams, Wb);
-    apply_window(w, Wa);
-    if (two) apply_window(w + streams, Wb);
+  // 8 / kPool windows in flight per thread (the same bytes for either pool size): with two windows of MaxPool(2) a
+  // thread had 64-96 bytes outstanding and blocks 2-4 ran at 2-4 TB/s
+  constexpr int kFlight = 8 / kPool;
+  for (int w = w0 + stream; w < w1; w += kFlight * streams) {
+    Window Wf[kFlight];
+#pragma unroll
+    for (int f = 0; f < kFlight; ++f)
+      if (w + f * streams < w1) load_window(w + f * streams, Wf[f]);
+#pragma unroll
+    for (int f = 0; f < kFlight; ++f)
+      if (w + f * streams < w1) apply_window(w + f * streams, Wf[f]);
   }
   const float inv = 1.0f / scale;
   float* row = dbias_partial + ((size_t(n) * chunks + chunk) * streams + stream) * C + c;
@@ -927,11 +939,15 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
   const dim3 grid(N, chunks);
   const float4* bc = reinterpret_cast<const float4*>(bn_const);
   const float4* bw = reinterpret_cast<const float4*>(bwd_const);
-#define VM_RELU_BWD(SPARSE, PLANES)                                                                                 \
-  bn_relu_bwd_kernel<SPARSE, PLANES><<<grid, kEwThreads, 0, st>>>(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bc, \
-                                                                  bw, mask, absmax, du_hi, du_lo, dbias_partial)
-  if (dy_pooled == nullptr) { if (du_lo) VM_RELU_BWD(true, 2); else VM_RELU_BWD(true, 1); }
-  else { if (du_lo) VM_RELU_BWD(false, 2); else VM_RELU_BWD(false, 1); }
+  if (pool != 2 && pool != 4) return set_error(VM_ERR_UNSUPPORTED, "bn_bwd: pool must be 2 or 4");
+#define VM_RELU_BWD(SPARSE, PLANES, POOL)                                                                          \
+  bn_relu_bwd_kernel<SPARSE, PLANES, POOL><<<grid, kEwThreads, 0, st>>>(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, \
+                                                                        bc, bw, mask, absmax, du_hi, du_lo, dbias_partial)
+#define VM_RELU_BWD_P(SPARSE, PLANES) \
+  do { if (pool == 2) VM_RELU_BWD(SPARSE, PLANES, 2); else VM_RELU_BWD(SPARSE, PLANES, 4); } while (0)
+  if (dy_pooled == nullptr) { if (du_lo) VM_RELU_BWD_P(true, 2); else VM_RELU_BWD_P(true, 1); }
+  else { if (du_lo) VM_RELU_BWD_P(false, 2); else VM_RELU_BWD_P(false, 1); }
+#undef VM_RELU_BWD_P
 #undef VM_RELU_BWD
   const ColsumFin fin{C, dbias};
   rowsum_fused_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial, size_t(N) * chunks * streams,
