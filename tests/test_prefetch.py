@@ -50,11 +50,11 @@ def test_generator_producers_distinct_streams_and_slot_lifetime():
         for _ in range(25):
             batch = pre.next()
             if previous is not None:
-                _check(previous)          # still intact: a batch is valid until the next next() call ... of the NEXT round
+                _check(previous)          # still intact: a batch stays valid through the next next() call
             seen.append(_check(batch))
             previous = None if len(seen) == 1 else batch      # (the very first batch is the parent's own, not a slot)
         assert len(set(seen)) == 25       # reseeded children: no two workers replay the same "random" batches
-        assert len(pre.pool.blocks) == 7 and all(p.is_alive() for p in pre.pool.procs)
+        assert len(pre.pool.blocks) == 8 and all(p.is_alive() for p in pre.pool.procs)   # 2 * workers + 2 slots
     finally:
         pre.close()
     assert not any(p.is_alive() for p in pre.pool.procs)

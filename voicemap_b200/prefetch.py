@@ -8,8 +8,10 @@ raw, 12 MB after the reference's preprocessing) is never pickled through a pipe.
 * a child reseeds ``numpy.random`` / ``random`` (forked copies would otherwise all produce the same "random" batches),
   then loops: take a free slot number, ``next(generator)``, copy every array of the batch into the slot, send
   ``(slot, structure)`` -- a few hundred bytes -- to the parent;
-* the parent rebuilds the batch as numpy views of the slot (no copy).  A batch is valid until the next ``next()`` call,
-  which hands its slot back to the children; ``fit_generator`` has staged the arrays into its pinned buffers by then.
+* the parent rebuilds the batch as numpy views of the slot (no copy).  A batch stays valid through the NEXT ``next()``
+  call and is recycled by the one after it (the slot goes back to the children then); ``fit_generator`` has staged the
+  arrays into its pinned buffers long before.  (Recycling at the very next call -- the first version -- made "look at
+  the previous batch once more" a race with the producers, which one of this module's own tests lost now and then.)
 
 A ``Sequence`` (experiments/train_classifier.py:48-86) is served the same way, except that the parent hands out the
 indices of the epoch and returns the batches in index order (Keras' OrderedEnqueuer), and that the children are
@@ -226,17 +228,18 @@ class ProcessPrefetcher:
     def __init__(self, generator, workers, slots=None, seed=None):
         iterator = iter(generator)
         self._first = next(iterator)                       # also tells the slot size; trained on like any other batch
-        self.pool = _Pool(iterator, workers, int(slots) if slots else 2 * int(workers) + 1, self._first, seed, False)
-        self._held = None                                  # slot of the batch handed out last
+        # two slots stay with the caller (see the module docstring), the producers need at least one more
+        self.pool = _Pool(iterator, workers, max(3, int(slots)) if slots else 2 * int(workers) + 2, self._first, seed,
+                          False)
+        self._held = []                                    # slots of the last two batches handed out (oldest first)
         self._live = self.pool.workers
 
     def next(self):
         if self._first is not None:
             batch, self._first = self._first, None
             return batch
-        if self._held is not None:                         # the previous batch has been consumed: recycle its slot
-            self.pool.free_q.put(self._held)
-            self._held = None
+        if len(self._held) == 2:                           # the batch before the previous one: recycle its slot
+            self.pool.free_q.put(self._held.pop(0))
         while True:
             if self._live == 0:
                 raise StopIteration
@@ -245,7 +248,7 @@ class ProcessPrefetcher:
                 self._live -= 1
                 self.pool.free_q.put(message[2])
                 continue
-            self._held = message[2]
+            self._held.append(message[2])
             return self.pool.batch(message)
 
     def close(self):
@@ -263,16 +266,17 @@ class SequencePrefetcher:
 
     def __init__(self, sequence, indices, workers, slots=None, seed=None):
         self.indices = list(indices)
-        self.slots = int(slots) if slots else 2 * int(workers) + 1
+        self.slots = max(3, int(slots)) if slots else 2 * int(workers) + 2
         self._first = sequence[self.indices[0]] if self.indices else None
         self.pool = _Pool(sequence, workers, self.slots, self._first, seed, True) if len(self.indices) > 1 else None
         self.issued = 1                                    # index 0 was computed here
         self.consumed = 0
         self.waiting = {}                                  # sequence number -> message, arrived early
-        self._held = None
+        self._held = []                                    # slots of the last two batches handed out
 
     def _issue(self):
-        while self.issued < len(self.indices) and self.issued < self.consumed + self.slots:
+        # tasks beyond the consumed ones never exceed the slots the children can actually get: two stay with the caller
+        while self.issued < len(self.indices) and self.issued < self.consumed + max(1, self.slots - 2):
             self.pool.task_q.put((self.issued, self.indices[self.issued]))
             self.issued += 1
 
@@ -284,16 +288,15 @@ class SequencePrefetcher:
             if self.pool is not None:
                 self._issue()
             return self._first
-        if self._held is not None:
-            self.pool.free_q.put(self._held)
-            self._held = None
+        if len(self._held) == 2:
+            self.pool.free_q.put(self._held.pop(0))
         self._issue()
         while self.consumed not in self.waiting:
             message = self.pool.receive()
             self.waiting[message[5]] = message
         message = self.waiting.pop(self.consumed)
         self.consumed += 1
-        self._held = message[2]
+        self._held.append(message[2])
         return self.pool.batch(message)
 
     def close(self):
