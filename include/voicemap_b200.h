@@ -171,7 +171,8 @@ int vm_pack_train(const float* const* kernels, const float* const* biases, int f
  *                          winner on ties; the arg-MIN of u where gamma[c] < 0, i.e. the arg-max after BatchNorm);
  *   ext (N, L/pool, Cout)  fp32 extreme of u per window (max, or min where gamma[c] < 0): the forward pass continues
  *                          from these exact values, BatchNorm being monotone per channel;
- *   stat_partial           per-channel {sum, sumsq} rows (N * 2*ceil(L/256), Cpad) float2 for the batch statistics.
+ *   stat_partial           per-channel {sum, sumsq} rows (N * rows_per_clip, Cpad) float2 for the batch statistics
+ *                          (rows_per_clip: vm_stat_rows_per_clip for block 1, vm_conv3_train_rows_per_clip for 2-4).
  * gamma (Cout) supplies the signs only (NULL = all maxima).  pool: 4 or 2 for block 1, always 2 for blocks 2-4.
  * precision 2 (blocks 2-4): in_lo is the e5m2x2 Q plane; 3: the fp16 residual plane. */
 int vm_conv1_train_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,
@@ -185,15 +186,17 @@ int vm_conv3_train_fwd(const uint16_t* in_hi, const uint16_t* in_lo, int N, int 
  * (du_lo NULL), dUh*Wh + dUh*Wl; 1: dUh*Wh.
  * below_* (optional, below_partial NULL = off): the BatchNorm-backward reduction of the block BELOW, whose pooled
  * gradient this call produces, taken in the epilogue while the values are in registers: below_ext (N, L, Cin) its
- * window extremes, below_bn_const (G, Cin) x 4, below_mask (N, Cin) or NULL -> below_partial, vm_stat_rows_per_clip(L)
- * rows of Cpad float2 {sum dy, sum dy * xhat} per clip, and *below_absmax (largest |s * dy|).  The following
- * vm_bn_bwd of that block is then called with presummed_rows_per_clip = vm_stat_rows_per_clip(L), scratch_f2 =
+ * window extremes, below_bn_const (G, Cin) x 4, below_mask (N, Cin) or NULL -> below_partial,
+ * vm_conv3_train_rows_per_clip(L) rows of Cpad float2 {sum dy, sum dy * xhat} per clip, and *below_absmax (largest
+ * |s * dy|).  The following vm_bn_bwd of that block is then called with presummed_rows_per_clip = that row count, scratch_f2 =
  * below_partial, grad_absmax = below_absmax, and skips its own pass over the pooled tensors. */
 int vm_conv3_dgrad(const uint16_t* du_hi, const uint16_t* du_lo, int N, int L, int cout, int cin,
                    const void* wpack_dgrad, const float* epi_dgrad, const uint32_t* grad_absmax, float* dx,
                    int precision, const float* below_ext, const float* below_bn_const, const float* below_mask,
                    int below_groups, float* below_partial, uint32_t* below_absmax, void* stream);
-int vm_stat_rows_per_clip(int L); /* 2 * ceil(L / 256) */
+int vm_stat_rows_per_clip(int L);        /* 2 * ceil(L / 256): partial rows per clip written by vm_conv1_train_fwd */
+int vm_conv3_train_rows_per_clip(int L); /* 4 * ceil(L / 256): ... by vm_conv3_train_fwd (stat_partial) and by the fused
+                                          * reduction of vm_conv3_dgrad (below_partial) */
 /* bytes of the `red_scratch` buffer the two-stage (deterministic, atomics-free) channel reductions need */
 size_t vm_reduce_scratch_bytes(int G, int C);
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "vm_conv3_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "vm_conv3_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "vm_stat_rows_per_clip": (_i, [_i]),
+    "vm_conv3_train_rows_per_clip": (_i, [_i]),
     "vm_bn_stats_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "vm_reduce_scratch_bytes": (_sz, [_i, _i]),
     "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

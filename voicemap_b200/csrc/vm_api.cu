@@ -225,6 +225,7 @@ int vm_pack_train(const float* const* kernels, const float* const* biases, int f
   return launch_pack_train(kernels, biases, filters, wraw, eraw, wdg, edg, ST);
 }
 int vm_stat_rows_per_clip(int L) { return 2 * ((L + 255) / 256); }
+int vm_conv3_train_rows_per_clip(int L) { return 4 * ((L + 255) / 256); }   // two epilogue sets x two column halves
 size_t vm_reduce_scratch_bytes(int G, int C) { return size_t(G > 0 ? G : 1) * 32 * size_t(C) * 16; }
 
 int vm_conv1_train_fwd(const float* x, int N, int L, int cout, int pool, const void* wpack, const float* epi,

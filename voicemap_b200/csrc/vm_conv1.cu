@@ -602,14 +602,15 @@ constexpr int kTStages = 2;
 constexpr int kUHalfBytes = kSub * 128;            // 64 positions x 64 channels
 constexpr int kUPlaneBytes = 2 * kUHalfBytes;      // 128 channels
 constexpr int kUStageBytes = 2 * kUPlaneBytes;     // hi + lo
-constexpr int kUStages = 4;
+constexpr int kUStages = 4;                        // two-plane stages; a one-plane gradient cuts the ring into 8
+constexpr int kUMaxStages = 8;
 constexpr int kThreads = 192;                      // warps 0-1 Toeplitz producers, 0-3 final epilogue, 4 TMA, 5 MMA
 constexpr int kSmemBytes = kTStages * kTStageBytes + kUStages * kUStageBytes + 1024 + 256;
 }  // namespace w1
 
 struct __align__(8) Wgrad1Barriers {
   uint64_t tfull[w1::kTStages], tempty[w1::kTStages];
-  uint64_t ufull[w1::kUStages], uempty[w1::kUStages];
+  uint64_t ufull[w1::kUMaxStages], uempty[w1::kUMaxStages];
   uint64_t done;
   uint32_t tmem_base;
 };
@@ -635,10 +636,13 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
   const int uplanes = (p.products == 3) ? 2 : 1;
   const int ntiles = p.N * p.nptile;
   const int co0 = blockIdx.y * 128;
+  // gradient ring: stages hold only the planes in use (8 one-plane stages = twice the bytes in flight per SM)
+  const int ustage_bytes = uplanes * kUPlaneBytes;
+  const int ustages = (uplanes == 1) ? kUMaxStages : kUStages;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
-    for (int i = 0; i < kUStages; ++i) { mbar_init(&bars->ufull[i], 1); mbar_init(&bars->uempty[i], 1); }
+    for (int i = 0; i < kUMaxStages; ++i) { mbar_init(&bars->ufull[i], 1); mbar_init(&bars->uempty[i], 1); }
     mbar_init(&bars->done, 1);
     fence_mbar_init();
   }
@@ -671,9 +675,9 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
         const int n = tile / p.nptile;
         const int p0 = (tile % p.nptile) * kTileN;
         for (int j = 0; j < kTileN / kSub; ++j, ++it) {
-          const int s = it % kUStages;
-          mbar_wait(&bars->uempty[s], ((it / kUStages) & 1) ^ 1);
-          uint8_t* base = uring + s * kUStageBytes;
+          const int s = it % ustages;
+          mbar_wait(&bars->uempty[s], ((it / ustages) & 1) ^ 1);
+          uint8_t* base = uring + s * ustage_bytes;
           mbar_arrive_expect_tx(&bars->ufull[s], uplanes * kUPlaneBytes);
           for (int pl = 0; pl < uplanes; ++pl) {
             const CUtensorMap* m = pl ? &tm_ul : &tm_uh;
@@ -695,10 +699,10 @@ wgrad1_tc_kernel(const __grid_constant__ CUtensorMap tm_uh, const __grid_constan
         tc_fence_after_sync();
         const uint32_t th = smem_u32(tring + ts * kTStageBytes), tl = th + kTPlaneBytes;
         for (int j = 0; j < kTileN / kSub; ++j, ++uit) {
-          const int us = uit % kUStages;
-          mbar_wait(&bars->ufull[us], (uit / kUStages) & 1);
+          const int us = uit % ustages;
+          mbar_wait(&bars->ufull[us], (uit / ustages) & 1);
           tc_fence_after_sync();
-          const uint32_t uh = smem_u32(uring + us * kUStageBytes), ul = uh + kUPlaneBytes;
+          const uint32_t uh = smem_u32(uring + us * ustage_bytes), ul = uh + kUPlaneBytes;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t arow = kk * 16 * 128;                       // 16 positions down the dU tile

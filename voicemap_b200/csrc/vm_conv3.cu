@@ -30,7 +30,8 @@ constexpr int kXRows = 264;              // 258 halo rows, padded to a multiple 
 constexpr int kXPlaneBytes = kXRows * 128;         // 33792
 constexpr int kXMainBytes = 256 * 128;             // 32768 (rows 0..255)
 constexpr int kXSlotBytes = 2 * kXPlaneBytes;      // hi + lo
-constexpr int kXStages = 2;
+constexpr int kXStages = 2;                          // two-plane slots; a one-plane launch cuts them into 4 half slots
+constexpr int kXMaxStages = 4;
 constexpr int kWTileBytes = kTileM * 128;          // 16384
 constexpr int kWStages = 4;
 constexpr int kStagePos = 16;                       // pooled positions per output granule
@@ -45,7 +46,7 @@ constexpr int kSmemBytes =
 }  // namespace c3
 
 struct __align__(8) Conv3Barriers {
-  uint64_t xfull[c3::kXStages], xempty[c3::kXStages];
+  uint64_t xfull[c3::kXMaxStages], xempty[c3::kXMaxStages];
   uint64_t wfull[c3::kWStages], wempty[c3::kWStages];
   uint64_t tfull[2], tempty[2];
   uint64_t sfull[2], sempty[2];   // pooled-output staging buffers: epilogue warps -> store warp -> epilogue warps
@@ -132,16 +133,20 @@ __device__ __forceinline__ void pooled_tile(const float4& ep, uint32_t taddr, ui
 // min for channels whose BatchNorm scale is negative: the value the normalised maximum comes from).  Granule = 16
 // positions: staging buffer = [u16: 2 boxes of 16 pos x 64 ch][extremes: 4 boxes of 8 windows x 32 ch fp32] = 8 KB,
 // handed to the store warp like the pooled granules.
+// kSets epilogue sets of 8 warps: with two, set s takes the granules g = s, s + 2, ... and owns staging buffer s
+// (gcount counts this set's granules; the store warp walks all granules in order, buffer g & 1).
+template <int kSets>
 __device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t taddr, uint8_t* stage, int ch, int chalf,
-                                          Conv3Barriers* bars, int buf, uint32_t& gcount, int pos_base, int L,
+                                          int set, Conv3Barriers* bars, int buf, uint32_t& gcount, int pos_base, int L,
                                           int lvalid, float& s1, float& s2) {
   using namespace c3;
   const uint32_t off_u = (ch >> 6) * 2048 + (chalf * 8) * 128 + (ch & 63) * 2;
   const uint32_t off_m = 4096 + (ch >> 5) * 1024 + (chalf * 4) * 128 + (ch & 31) * 4;
   auto granule = [&](const uint32_t (&r)[8], int gr) {
-    const int sb = gcount & 1;
+    const int sb = (kSets == 2) ? set : int(gcount & 1);
+    const uint32_t use = (kSets == 2) ? gcount : (gcount >> 1);   // how often this buffer has been filled before
     const uint32_t st = smem_u32(stage + sb * kStageBufBytes);
-    if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+    if (use >= 1) mbar_wait(&bars->sempty[sb], (use - 1) & 1);
     const int pos0 = pos_base + gr * 16 + chalf * 8;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -160,20 +165,22 @@ __device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t t
     ++gcount;
   };
   uint32_t ra[8], rb[8];
-  tmem_ld_32x8_issue(taddr + chalf * 8, ra);
+  const uint32_t tcol = taddr + chalf * 8;
+  constexpr int kStep = kSets;   // granules between two of this set's
+  tmem_ld_32x8_issue(tcol + set * 16, ra);
 #pragma unroll 1
-  for (int gr = 0; gr < kTileN / 16; gr += 2) {
+  for (int gr = set; gr < kTileN / 16; gr += 2 * kStep) {
     tmem_ld_wait(ra);
-    tmem_ld_32x8_issue(taddr + (gr + 1) * 16 + chalf * 8, rb);
+    tmem_ld_32x8_issue(tcol + (gr + kStep) * 16, rb);
     granule(ra, gr);
     tmem_ld_wait(rb);
-    if (gr + 2 < kTileN / 16) {
-      tmem_ld_32x8_issue(taddr + (gr + 2) * 16 + chalf * 8, ra);
+    if (gr + 2 * kStep < kTileN / 16) {
+      tmem_ld_32x8_issue(tcol + (gr + 2 * kStep) * 16, ra);
     } else {
       tc_fence_before_sync();
       mbar_arrive(&bars->tempty[buf]);
     }
-    granule(rb, gr + 1);
+    granule(rb, gr + kStep);
   }
 }
 
@@ -182,14 +189,14 @@ __device__ __forceinline__ void raw2_tile(const float4& ep, bool neg, uint32_t t
 // kReduce: also accumulate, per channel, the BatchNorm-backward sums of the block below from the values in registers
 // (red_*: the thread's channel constants; erow: its column of the window extremes of this clip; lrem: valid positions
 // from this tile's first one).
-template <bool kReduce>
-__device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8_t* stage, int ch, int chalf,
+template <bool kReduce, int kSets>
+__device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8_t* stage, int ch, int chalf, int set,
                                             Conv3Barriers* bars, int buf, uint32_t& gcount, const float* erow,
                                             size_t estride, int lrem, float mk, float mean, float rstd, float sabs,
                                             float& s1, float& s2, float& amax) {
   using namespace c3;
   const uint32_t off = (ch >> 5) * 2048 + (chalf * 8) * 128 + (ch & 31) * 4;
-  int gr_pos = chalf * 8;   // first position (relative to the tile) of the granule being processed
+  int gr_pos = set * 16 + chalf * 8;   // first position (relative to the tile) of the granule being processed
   auto load_ext = [&](float (&e)[8], int pos) {   // the thread's 8 window extremes of the granule starting at pos
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] = (pos + j < lrem) ? __ldg(erow + size_t(pos + j) * estride) : mean;
@@ -199,9 +206,10 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
   // one DRAM latency per granule and doubled the kernel time.  (Also tried: prefetch.global.L2 of the next tile's
   // extremes at tile start -- 8 % slower, the epilogue is issue-bound once the latency is covered.)
   auto granule = [&](const uint32_t (&r)[8], float (&e)[8]) {
-    const int sb = gcount & 1;
+    const int sb = (kSets == 2) ? set : int(gcount & 1);
+    const uint32_t use = (kSets == 2) ? gcount : (gcount >> 1);
     const uint32_t st = smem_u32(stage + sb * kStageBufBytes) + off;
-    if (gcount >= 2) mbar_wait(&bars->sempty[sb], ((gcount >> 1) - 1) & 1);
+    if (use >= 1) mbar_wait(&bars->sempty[sb], (use - 1) & 1);
     float dy[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -218,26 +226,28 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
         s2 = fmaf(d, (e[j] - mean) * rstd, s2);
         amax = fmaxf(amax, fabsf(d) * sabs);
       }
-      load_ext(e, gr_pos + 32);
+      load_ext(e, gr_pos + 32 * kSets);
     }
-    gr_pos += 16;
+    gr_pos += 16 * kSets;
     ++gcount;
   };
   uint32_t ra[8], rb[8];
   float ea[8], eb[8];
   if (kReduce) {
     load_ext(ea, gr_pos);
-    load_ext(eb, gr_pos + 16);
+    load_ext(eb, gr_pos + 16 * kSets);
   }
-  tmem_ld_32x8_issue(taddr + chalf * 8, ra);
+  const uint32_t tcol = taddr + chalf * 8;
+  constexpr int kStep = kSets;
+  tmem_ld_32x8_issue(tcol + set * 16, ra);
 #pragma unroll 1
-  for (int gr = 0; gr < kTileN / 16; gr += 2) {
+  for (int gr = set; gr < kTileN / 16; gr += 2 * kStep) {
     tmem_ld_wait(ra);
-    tmem_ld_32x8_issue(taddr + (gr + 1) * 16 + chalf * 8, rb);
+    tmem_ld_32x8_issue(tcol + (gr + kStep) * 16, rb);
     granule(ra, ea);
     tmem_ld_wait(rb);
-    if (gr + 2 < kTileN / 16) {
-      tmem_ld_32x8_issue(taddr + (gr + 2) * 16 + chalf * 8, ra);
+    if (gr + 2 * kStep < kTileN / 16) {
+      tmem_ld_32x8_issue(tcol + (gr + 2 * kStep) * 16, ra);
     } else {
       tc_fence_before_sync();
       mbar_arrive(&bars->tempty[buf]);
@@ -246,7 +256,11 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
   }
 }
 
-__global__ void __launch_bounds__(c3::kThreads, 1)
+// kSets: epilogue sets of 8 warps.  1: the pooled / global-max epilogues of the eval forward.  2: the train-mode
+// forward and dgrad, whose epilogues do 2-3x the work per accumulator column (statistics, encoding, window extremes;
+// fused BatchNorm-backward sums) and left the tensor pipe 42-64 % busy with one set.
+template <int kSets>
+__global__ void __launch_bounds__((4 + 8 * kSets) * 32, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
              const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
@@ -268,9 +282,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   const bool mixed = (p.products == 2);   // second plane of X and W is the e5m2x2 Q plane
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
+    for (int i = 0; i < kXMaxStages; ++i) { mbar_init(&bars->xfull[i], 1); mbar_init(&bars->xempty[i], 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(&bars->wfull[i], 1); mbar_init(&bars->wempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 8 * kSets * 32); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->sfull[i], kEpiWarps * 32); mbar_init(&bars->sempty[i], 1); }
     fence_mbar_init();
   }
@@ -292,9 +306,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         const int n = pt_lin / p.nptile;
         const int p0 = (pt_lin % p.nptile) * kTileN;
         for (int c = 0; c < p.nchunk; ++c, ++it) {
-          const int s = it % kXStages;
-          mbar_wait(&bars->xempty[s], ((it / kXStages) & 1) ^ 1);
-          uint8_t* dst = xring + s * kXSlotBytes;
+          const int s = it % p.xstages;
+          mbar_wait(&bars->xempty[s], ((it / p.xstages) & 1) ^ 1);
+          uint8_t* dst = xring + s * p.xslot_bytes;
           const int xplanes = p.x_single ? 1 : wplanes;
           mbar_arrive_expect_tx(&bars->xfull[s], xplanes * kXPlaneBytes);
           tma_load_3d(dst, &tm_xh_main, &bars->xfull[s], c * kKC, p0 - 1, n);
@@ -346,12 +360,12 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         uint32_t acc = 0;
         for (int c = 0; c < p.nchunk; ++c) {
           const uint32_t xi = xit + c;   // X chunks of this unit (loaded once, by its first tile)
-          const int xs = xi % kXStages;
+          const int xs = xi % p.xstages;
           if (ti.first()) {
-            mbar_wait(&bars->xfull[xs], (xi / kXStages) & 1);
+            mbar_wait(&bars->xfull[xs], (xi / p.xstages) & 1);
             tc_fence_after_sync();
           }
-          const uint32_t xh = smem_u32(xring + xs * kXSlotBytes);
+          const uint32_t xh = smem_u32(xring + xs * p.xslot_bytes);
           const uint32_t xl = xh + kXPlaneBytes;
           for (int tap = 0; tap < 3; ++tap) {
             const uint32_t bh = xh + tap * 128, bl = xl + tap * 128;
@@ -509,9 +523,10 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
     // leader waits until the store issued one granule earlier has drained its buffer (that store had a whole
     // granule of compute to finish), so the buffer written next is known to be free by everyone who passes.
     const int q = warp & 3;
-    const int chalf = (warp - 4) >> 2;
-    const bool leader = (threadIdx.x == 4 * 32);
+    const int set = (warp - 4) >> 3;          // 0 with one set
+    const int chalf = ((warp - 4) & 7) >> 2;
     const int ch = q * 32 + lane;
+    const int rows = 2 * kSets, row = chalf * kSets + set;   // partial-sum rows per tile / this thread's row
     const int lvalid = p.lout * 2;  // 'valid' pooling drops an odd tail position
     uint32_t tit = 0, gcount = 0;   // gcount: granules staged so far (selects the staging buffer)
     for (TileIter ti(blockIdx.x, gridDim.x, ntiles, spu); ti.valid(); ti.next(), ++tit) {
@@ -525,16 +540,18 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
       const int co = slab * kTileM + ch;
       const float4 ep = p.epi[co];  // {a, c, lo, hi} (see apply_epi); padded channels hold zeros
       // one polling warp; the other seven block in bar.sync instead of spinning on the mbarrier
-      if (warp == 4) mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
-      named_bar_sync(1, kEpiWarps * 32);
+      if (((warp - 4) & 7) == 0) mbar_wait(&bars->tfull[buf], (tit >> 1) & 1);
+      named_bar_sync(1 + set, 256);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * kTileN;
       if (p.out_u16 != nullptr) {
         const bool neg = (p.sign_src != nullptr && co < p.cout) ? (p.sign_src[co] < 0.f) : false;
         float s1 = 0.f, s2 = 0.f;
-        raw2_tile(ep, neg, taddr, stage, ch, chalf, bars, buf, gcount, p0, p.L, lvalid, s1, s2);
+        raw2_tile<kSets>(ep, neg, taddr, stage, ch, chalf, set, bars, buf, gcount, p0, p.L, lvalid, s1, s2);
         if (p.stat_partial != nullptr)
-          p.stat_partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+          p.stat_partial[(size_t(n) * (rows * p.nptile) + rows * pt + row) * p.cout_pad + co] = make_float2(s1, s2);
+      } else if (kSets != 1 && p.out_f32 == nullptr) {
+        __trap();   // the pooled / global-max epilogues are instantiated with one set only (host-side dispatch)
       } else if (p.gmax_partial != nullptr) {
         float m = -INFINITY;
 #pragma unroll 1
@@ -569,14 +586,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
           const float4 bc = live ? p.red.bn_const[size_t(g) * p.cout + co] : make_float4(0.f, 0.f, 0.f, 0.f);
           const float mk = live ? (p.red.mask ? p.red.mask[size_t(n) * p.cout + co] : 1.f) : 0.f;
           const float* erow = p.red.ext + (size_t(n) * p.L + p0) * p.cout + (live ? co : 0);
-          linear_tile<true>(unscale, taddr, stage, ch, chalf, bars, buf, gcount, erow, size_t(p.cout),
-                            live ? p.L - p0 : 0, mk, bc.z, bc.w, fabsf(bc.x), s1, s2, amax);
-          p.red.partial[(size_t(n) * (2 * p.nptile) + 2 * pt + chalf) * p.cout_pad + co] = make_float2(s1, s2);
+          linear_tile<true, kSets>(unscale, taddr, stage, ch, chalf, set, bars, buf, gcount, erow, size_t(p.cout),
+                                   live ? p.L - p0 : 0, mk, bc.z, bc.w, fabsf(bc.x), s1, s2, amax);
+          p.red.partial[(size_t(n) * (rows * p.nptile) + rows * pt + row) * p.cout_pad + co] = make_float2(s1, s2);
           for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
           if (lane == 0 && amax > 0.f) atomicMax(p.red.absmax, __float_as_uint(amax));
         } else {
-          linear_tile<false>(unscale, taddr, stage, ch, chalf, bars, buf, gcount, nullptr, 0, 0, 0.f, 0.f, 0.f, 0.f, s1,
-                             s2, amax);
+          linear_tile<false, kSets>(unscale, taddr, stage, ch, chalf, set, bars, buf, gcount, nullptr, 0, 0, 0.f, 0.f,
+                                    0.f, 0.f, s1, s2, amax);
         }
       } else {
         // pooled outputs: granule = 16 pooled positions x 128 channels x 2 planes; the two warps of a lane quarter
@@ -596,7 +613,6 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         }
       }
     }
-    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
@@ -707,15 +723,26 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
     oh = wh;  // unused by the kernel in gmax mode
     ol = wh;
   }
-  cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  const bool two_sets = (extra.out_u16 != nullptr || out_f32 != nullptr);
+  cudaError_t e = cudaFuncSetAttribute(two_sets ? conv3_kernel<2> : conv3_kernel<1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
   const int ntiles = N * p.nptile * p.nslab;
   // all cout slabs of a position tile on one CTA when its X tile fits the ring (see TileIter)
-  p.slabs_per_unit = (p.nchunk <= kXStages && p.nslab > 1) ? p.nslab : 1;
+  // X ring: the same bytes hold 2 two-plane slots or 4 one-plane slots.  A one-plane chunk is only 1536 MMA cycles, and
+  // two of them in flight did not cover the latency of the next TMA load (dgrad with one-plane gradients ran at half
+  // its MMA rate)
+  const bool one_x_plane = (products == 1) || extra.x_single;
+  p.xstages = one_x_plane ? kXMaxStages : kXStages;
+  p.xslot_bytes = one_x_plane ? kXPlaneBytes : kXSlotBytes;
+  p.slabs_per_unit = (p.nchunk <= p.xstages && p.nslab > 1) ? p.nslab : 1;
   const int nunits = ntiles / p.slabs_per_unit;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > nunits) grid = nunits;
-  conv3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
+  if (two_sets)
+    conv3_kernel<2><<<grid, (4 + 16) * 32, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
+  else
+    conv3_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: launch");
   return VM_OK;

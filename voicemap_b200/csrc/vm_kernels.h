@@ -77,6 +77,7 @@ struct Conv3Params {
   int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
   int x_single;          // products 3 with a single input plane: Xh*Wh + Xh*Wl (dgrad of a one-plane gradient)
   int slabs_per_unit;    // tile schedule: 1, or nslab when the X tile stays in shared memory for all cout slabs
+  int xstages, xslot_bytes;  // X ring geometry: 2 two-plane slots or 4 one-plane slots in the same shared memory
   // train-mode forward (out_u16 != null): encoded un-pooled activations (N, L, cout) (encode_u) + fp32 window
   // extremes (N, lout, cout); sign_src[cout] < 0 selects the minimum (negative BatchNorm scale), null = all maxima
   uint16_t* out_u16;

@@ -209,7 +209,7 @@ class TrainEngine:
         self.XL = [torch.empty((nb, ls[b + 1], c[b]), dtype=f16, device=dev) if want_lo else None for b in range(3)]
         self.XQ = [torch.empty((nb, ls[b + 1], c[b]), dtype=f16, device=dev) if self.precision == 2 else None
                    for b in range(3)]
-        rows = [self.lib.vm_stat_rows_per_clip(ls[b]) for b in range(4)]
+        rows = [self.lib.vm_stat_rows_per_clip(ls[0])] + [self.lib.vm_conv3_train_rows_per_clip(ls[b]) for b in (1, 2, 3)]
         self.stat = [torch.empty((nb * rows[b], self.lib.vm_padded_channels(c[b]), 2), dtype=f32, device=dev)
                      for b in range(4)]
         self.stat_rows = rows
@@ -224,7 +224,7 @@ class TrainEngine:
         self.dU = torch.empty((2 if self.bwd_precision == 3 else 1, nb * max_u), dtype=f16, device=dev)
         self.gabs = torch.zeros((4,), dtype=torch.int32, device=dev)   # per block: bits of max |s * dy| -> gradient scale
         # blocks 1-3: partial rows of the BatchNorm-backward sums, written by the dgrad epilogue of the block above
-        self.redp = [torch.empty((nb * self.lib.vm_stat_rows_per_clip(ls[b + 1]), self.lib.vm_padded_channels(c[b]), 2),
+        self.redp = [torch.empty((nb * self.lib.vm_conv3_train_rows_per_clip(ls[b + 1]), self.lib.vm_padded_channels(c[b]), 2),
                                  dtype=f32, device=dev) for b in range(3)]
         max_x = max(ls[b + 1] * c[b] for b in range(3))
         self.dX = torch.empty(nb * max_x, dtype=f32, device=dev)
@@ -406,7 +406,7 @@ class TrainEngine:
                 dy, dg, js = self.dX, None, None
             grads = (_ptr(g[f"bn{b + 1}_gamma"]), _ptr(g[f"bn{b + 1}_beta"]))
             # blocks 1-3: the sums of dy and dy * xhat were taken by the dgrad epilogue of the block above
-            pre_rows = lib.vm_stat_rows_per_clip(ls[b + 1]) if b < 3 else 0
+            pre_rows = lib.vm_conv3_train_rows_per_clip(ls[b + 1]) if b < 3 else 0
             part = self.redp[b] if b < 3 else self.scr2
             if self.sync_allreduce is None:
                 plan.launch(lib.vm_bn_bwd, f"vm_bn_bwd block {b + 1}", _ptr(self.U16[b]), _ptr(self.EXT[b]), _ptr(dy),
