@@ -223,6 +223,16 @@ int vm_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const floa
                           float* d_head_b, float* accuracy, void* stream);
 int vm_dense_bwd(const float* x, const float* dy, const float* w, int N, int C, int E, float* dw, float* db, float* dx,
                  void* stream);
+/* The siamese training head in one call (two launches): for pair n of the 2N-clip batch (gmax (2N, C): branch 1 rows,
+ * then branch 2 rows) Dense -> emb (2N, E), the distance layer and Dense(1, sigmoid) of voicemap/models.py:52-69 ->
+ * prob (N, optional), the loss (1 contrastive, voicemap/utils.py:77-85; 2 binary cross-entropy) -> loss_acc {mean loss,
+ * keras accuracy}, and the backward pass down to d_gmax (2N, C): d_emb (2N, E), the Dense gradients d_dense_w (C, E) /
+ * d_dense_b (E) and the head gradients d_head_w (1 | E) / d_head_b (1), all multiplied by loss_scale.  Equivalent to
+ * vm_dense_fwd + vm_pair_head_loss_fwd + vm_pair_head_loss_bwd + vm_dense_bwd.  pair_scratch: 4 * N floats. */
+int vm_siamese_head_train(const float* gmax, int N, int C, int E, const float* dense_w, const float* dense_b, int metric,
+                          const float* head_w, const float* head_b, const float* y_true, int loss_kind, float loss_scale,
+                          float* emb, float* prob, float* d_emb, float* d_gmax, float* pair_scratch, float* d_dense_w,
+                          float* d_dense_b, float* d_head_w, float* d_head_b, float* loss_acc, void* stream);
 /* BN + MaxPool + ReLU backward of one block.  Give dy_pooled (N, L/pool, C) (blocks 1-3) XOR d_gmax (N, C) + jstar
  * (block 4: the gradient sits in window jstar[n][c]).  Outputs: dgamma, dbeta, dbias (C) and dU (N, L, C) as fp16
  * planes scaled by a power of two that is derived from the largest |s * dy| of the block (stored as float bits in
@@ -276,6 +286,20 @@ int vm_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* pe
                    int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* bwd_const,
                    float* dgamma, float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
                    float* scratch_f, float* dbias, double* red_scratch, void* stream);
+/* The same in ONE launch each: the reduction kernel's finishing block of every 32-channel column exchanges that
+ * column's sums with the peers and derives the constants (vm_bn_stats_sums + vm_bn_stats_sync, resp. vm_bn_bwd_sums +
+ * vm_bn_bwd_sync, without the second launch; arguments as in vm_bn_stats_finalize / vm_bn_bwd plus the peer arguments
+ * of the *_sync calls).  local_sums (2*G*C doubles; optional for the statistics), total_sums (2*G*C doubles), G <= 4. */
+int vm_bn_stats_finalize_peers(const float* stat_partial, int rows_per_clip, int N, int G, int C, const float* gamma,
+                               const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                               float* bn_const, double* red_scratch, void* const* peers, int rank, int world,
+                               uint32_t seq, double count, double* local_sums, double* total_sums, void* stream);
+int vm_bn_bwd_peers(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax,
+                    const int32_t* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                    float* scratch_f2, float* bwd_const, float* dgamma, float* dbeta, uint32_t* grad_absmax,
+                    uint16_t* du_hi, uint16_t* du_lo, float* scratch_f, float* dbias, double* red_scratch,
+                    int presummed_rows_per_clip, void* const* peers, int rank, int world, uint32_t seq, double count,
+                    double* local_sums, double* total_sums, void* stream);
 /* dW (3, Cin, Cout) = sum_{n,p} X[n][p+tap-1][ci] * dU[n][p][co] on tensor cores.  x_hi / x_lo: the fp16 planes the
  * forward conv of the block consumed (x_lo = fp16 residual plane: training keeps precision-3 planes for this);
  * du_*: the scaled gradient planes of vm_bn_bwd, grad_absmax their scale word.  precision 3: Xh*Uh + Xl*Uh + Xh*Ul;

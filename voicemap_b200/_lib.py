@@ -67,6 +67,8 @@ SIGNATURES = {
     "vm_bn_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_bn_gmax_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_fwd": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "vm_siamese_head_train": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _vp]),
     "vm_pair_head_loss_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "vm_dense_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vm_bn_bwd_scratch_elems": (_sz, [_i]),
@@ -83,6 +85,10 @@ SIGNATURES = {
     "vm_p2p_export": (_i, [_vp, C.c_char_p]),
     "vm_p2p_import": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "vm_p2p_unimport": (_i, [_vp]),
+    "vm_bn_stats_finalize_peers": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, C.POINTER(_vp), _i, _i,
+                                        C.c_uint32, C.c_double, _vp, _vp, _vp]),
+    "vm_bn_bwd_peers": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp, _vp, _i, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _vp, _vp, _vp]),
     "vm_bn_stats_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp,
                               _vp, _vp, _vp]),
     "vm_bn_bwd_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i,

@@ -259,7 +259,10 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
 // kSets: epilogue sets of 8 warps.  1: the pooled / global-max epilogues of the eval forward.  2: the train-mode
 // forward and dgrad, whose epilogues do 2-3x the work per accumulator column (statistics, encoding, window extremes;
 // fused BatchNorm-backward sums) and left the tensor pipe 42-64 % busy with one set.
-template <int kSets>
+// kXS: slots of the X ring (2 two-plane slots, or 4 one-plane slots in the same shared memory) -- a compile-time constant:
+// as a kernel parameter the slot index cost two integer divisions per K chunk in the MMA-issuing thread and the eval
+// forward lost 2-3 % (same-box A/B, profiles/r02_ab_forward.log).
+template <int kSets, int kXS>
 __global__ void __launch_bounds__((4 + 8 * kSets) * 32, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,
              const __grid_constant__ CUtensorMap tm_xl_main, const __grid_constant__ CUtensorMap tm_xl_halo,
@@ -274,6 +277,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
   uint8_t* stage = wring + kWStages * kWTileBytes;
   Conv3Barriers* bars = reinterpret_cast<Conv3Barriers*>(stage + kStageBytes);
 
+  constexpr int kXSlot = (kXS == kXStages) ? kXSlotBytes : kXPlaneBytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntiles = p.N * p.nptile * p.nslab;
@@ -306,9 +310,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         const int n = pt_lin / p.nptile;
         const int p0 = (pt_lin % p.nptile) * kTileN;
         for (int c = 0; c < p.nchunk; ++c, ++it) {
-          const int s = it % p.xstages;
-          mbar_wait(&bars->xempty[s], ((it / p.xstages) & 1) ^ 1);
-          uint8_t* dst = xring + s * p.xslot_bytes;
+          const int s = it % kXS;
+          mbar_wait(&bars->xempty[s], ((it / kXS) & 1) ^ 1);
+          uint8_t* dst = xring + s * kXSlot;
           const int xplanes = p.x_single ? 1 : wplanes;
           mbar_arrive_expect_tx(&bars->xfull[s], xplanes * kXPlaneBytes);
           tma_load_3d(dst, &tm_xh_main, &bars->xfull[s], c * kKC, p0 - 1, n);
@@ -360,12 +364,12 @@ conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_consta
         uint32_t acc = 0;
         for (int c = 0; c < p.nchunk; ++c) {
           const uint32_t xi = xit + c;   // X chunks of this unit (loaded once, by its first tile)
-          const int xs = xi % p.xstages;
+          const int xs = xi % kXS;
           if (ti.first()) {
-            mbar_wait(&bars->xfull[xs], (xi / p.xstages) & 1);
+            mbar_wait(&bars->xfull[xs], (xi / kXS) & 1);
             tc_fence_after_sync();
           }
-          const uint32_t xh = smem_u32(xring + xs * p.xslot_bytes);
+          const uint32_t xh = smem_u32(xring + xs * kXSlot);
           const uint32_t xl = xh + kXPlaneBytes;
           for (int tap = 0; tap < 3; ++tap) {
             const uint32_t bh = xh + tap * 128, bl = xl + tap * 128;
@@ -724,25 +728,29 @@ int launch_conv3(const __half* in_hi, const __half* in_lo, int N, int L, int cin
     ol = wh;
   }
   const bool two_sets = (extra.out_u16 != nullptr || out_f32 != nullptr);
-  cudaError_t e = cudaFuncSetAttribute(two_sets ? conv3_kernel<2> : conv3_kernel<1>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e != cudaSuccess) return set_cuda_error(e, "conv3: cudaFuncSetAttribute");
-  const int ntiles = N * p.nptile * p.nslab;
-  // all cout slabs of a position tile on one CTA when its X tile fits the ring (see TileIter)
   // X ring: the same bytes hold 2 two-plane slots or 4 one-plane slots.  A one-plane chunk is only 1536 MMA cycles, and
   // two of them in flight did not cover the latency of the next TMA load (dgrad with one-plane gradients ran at half
   // its MMA rate)
   const bool one_x_plane = (products == 1) || extra.x_single;
-  p.xstages = one_x_plane ? kXMaxStages : kXStages;
-  p.xslot_bytes = one_x_plane ? kXPlaneBytes : kXSlotBytes;
-  p.slabs_per_unit = (p.nchunk <= p.xstages && p.nslab > 1) ? p.nslab : 1;
+  const int xstages = one_x_plane ? kXMaxStages : kXStages;
+  const int ntiles = N * p.nptile * p.nslab;
+  // all cout slabs of a position tile on one CTA when its X tile fits the ring (see TileIter)
+  p.slabs_per_unit = (p.nchunk <= xstages && p.nslab > 1) ? p.nslab : 1;
   const int nunits = ntiles / p.slabs_per_unit;
   int grid = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > nunits) grid = nunits;
-  if (two_sets)
-    conv3_kernel<2><<<grid, (4 + 16) * 32, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
-  else
-    conv3_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, wl, oh, ol, p);
+#define VM_CONV3_LAUNCH(SETS, XS)                                                                                   \
+  do {                                                                                                              \
+    cudaError_t ea = cudaFuncSetAttribute(conv3_kernel<SETS, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          kSmemBytes);                                                              \
+    if (ea != cudaSuccess) return set_cuda_error(ea, "conv3: cudaFuncSetAttribute");                                \
+    conv3_kernel<SETS, XS><<<grid, (4 + 8 * SETS) * 32, kSmemBytes, stream>>>(xh_main, xh_halo, xl_main, xl_halo, wh, \
+                                                                              wl, oh, ol, p);                       \
+  } while (0)
+  if (two_sets) { if (one_x_plane) VM_CONV3_LAUNCH(2, kXMaxStages); else VM_CONV3_LAUNCH(2, kXStages); }
+  else { if (one_x_plane) VM_CONV3_LAUNCH(1, kXMaxStages); else VM_CONV3_LAUNCH(1, kXStages); }
+#undef VM_CONV3_LAUNCH
+  cudaError_t e;
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "conv3: launch");
   return VM_OK;

@@ -77,7 +77,6 @@ struct Conv3Params {
   int linear;            // out_f32 mode: 1 = store the raw accumulator (dgrad), 0 = apply the epilogue constants
   int x_single;          // products 3 with a single input plane: Xh*Wh + Xh*Wl (dgrad of a one-plane gradient)
   int slabs_per_unit;    // tile schedule: 1, or nslab when the X tile stays in shared memory for all cout slabs
-  int xstages, xslot_bytes;  // X ring geometry: 2 two-plane slots or 4 one-plane slots in the same shared memory
   // train-mode forward (out_u16 != null): encoded un-pooled activations (N, L, cout) (encode_u) + fp32 window
   // extremes (N, lout, cout); sign_src[cout] < 0 selects the minimum (negative BatchNorm scale), null = all maxima
   uint16_t* out_u16;
@@ -132,6 +131,22 @@ int launch_dense_bwd(const float* x, const float* dy, const float* w, int N, int
 int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const float* head_w, const float* head_b,
                               const float* y_true, int loss_kind, float loss_scale, float* d_emb, float* d_head_w,
                               float* d_head_b, float* accuracy, cudaStream_t st);
+int launch_bn_stats_finalize_peers(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C,
+                                   double* red_scratch, void* const* peers, int rank, int world, unsigned int seq,
+                                   double count, const float* gamma, const float* beta, float eps, float momentum,
+                                   float* moving_mean, float* moving_var, float* bn_const, double* local_sums,
+                                   double* total_sums, cudaStream_t st);
+int launch_bn_bwd_peers(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax,
+                        const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                        float* partial, float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax,
+                        __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias, double* red_scratch,
+                        int presummed_rows, void* const* peers, int rank, int world, unsigned int seq, double count,
+                        double* local_sums, double* total_sums, cudaStream_t st);
+int launch_siamese_head_train(const float* gmax, int N, int C, int E, const float* dense_w, const float* dense_b,
+                              int metric, const float* head_w, const float* head_b, const float* y_true, int loss_kind,
+                              float loss_scale, float* emb, float* prob, float* d_emb, float* d_gmax, float* pair_scratch,
+                              float* d_dense_w, float* d_dense_b, float* d_head_w, float* d_head_b, float* loss_acc,
+                              cudaStream_t st);
 size_t bn_bwd_scratch_elems(int N);
 int launch_bn_bwd(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax, const int* jstar,
                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* partial,

@@ -20,7 +20,9 @@ namespace vm {
 
 constexpr int kP2PMaxRanks = 8;
 constexpr int kP2PMaxDoubles = 8192;          // 2 sums x 2 groups x 2048 channels
-constexpr size_t kP2PDataOffset = 256;
+constexpr int kP2PMaxColumns = 64;            // column form (below): 32-channel columns, C <= 2048
+constexpr size_t kP2PColFlagOffset = 256;     // column flags [2 slots][kP2PMaxColumns][kP2PMaxRanks] uint32 = 4 KB
+constexpr size_t kP2PDataOffset = kP2PColFlagOffset + size_t(2) * kP2PMaxColumns * kP2PMaxRanks * 4;
 constexpr size_t kP2PBufferBytes = kP2PDataOffset + size_t(2) * kP2PMaxRanks * kP2PMaxDoubles * sizeof(double);
 
 struct P2PPeers {
@@ -42,6 +44,56 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Column form: ONE WARP exchanges the G double2 sums of its 32 channels (lane = channel c of column `col`), so the
+// finishing block of every channel column of a reduction kernel can run its own exchange while the other columns are
+// still being summed -- the reduction and the exchange are one launch.  Vector layout as above (double2 index g*C + c);
+// a column has its own flag per (slot, rank); the data slots are shared with the block form (a call uses one form).
+// The two-slot argument holds per column: a peer raises a flag of call k+1 only after its kernel of call k has finished.
+__device__ __forceinline__ unsigned int* p2p_col_flag(void* base, int slot, int col, int r) {
+  return reinterpret_cast<unsigned int*>(static_cast<char*>(base) + kP2PColFlagOffset) +
+         (size_t(slot) * kP2PMaxColumns + col) * kP2PMaxRanks + r;
+}
+// mine[g] (this rank's sums of channel c, c < C only) -> returns with total[g*C + c] written (sum over ranks in rank
+// order) for every valid lane.  All 32 lanes of the warp must call.
+template <int kMaxG>
+__device__ __forceinline__ void p2p_allreduce_column(const double2 (&mine)[kMaxG], int G, int C, int c, int col,
+                                                     const P2PPeers& peers, unsigned int seq,
+                                                     double2* __restrict__ total) {
+  const int slot = seq & 1, lane = threadIdx.x & 31;
+  if (c < C) {
+    for (int q = 0; q < peers.world; ++q) {
+      double2* dst = reinterpret_cast<double2*>(p2p_data(peers.buf[q], slot, peers.rank));
+      for (int g = 0; g < G; ++g) dst[size_t(g) * C + c] = mine[g];
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < peers.world) {
+    st_release_sys(p2p_col_flag(peers.buf[lane], slot, col, peers.rank), seq);
+    const unsigned int* flag = p2p_col_flag(peers.buf[peers.rank], slot, col, lane);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) != seq) {
+      if (clock64() - t0 > 8000000000LL) {   // ~4 s: a peer never arrived
+        printf("vm: p2p column exchange timeout rank %d waiting for rank %d seq %u column %d\n", peers.rank, lane, seq,
+               col);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  if (c < C) {
+    for (int g = 0; g < G; ++g) {
+      double a = 0.0, b = 0.0;
+      for (int r = 0; r < peers.world; ++r) {   // L2: written by the peers
+        const double* src = p2p_data(peers.buf[peers.rank], slot, r) + 2 * (size_t(g) * C + c);
+        a += __ldcg(src);
+        b += __ldcg(src + 1);
+      }
+      total[size_t(g) * C + c] = make_double2(a, b);
+    }
+  }
 }
 
 // One thread block.  local[n] (this rank's vector, global memory) -> total[n] (sum over the ranks, global memory,

@@ -75,13 +75,22 @@ __global__ void rowsum_fused_kernel(const float* __restrict__ m, size_t rows_per
   const size_t r1 = min(size_t(g + 1) * rows_per_group, r0 + per);
   double a = 0.0, b = 0.0;
   if (c < C) {
-    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      if (NC == 2) {
-        const float2 v = reinterpret_cast<const float2*>(m)[r * stride + c];
-        a += double(v.x);
-        b += double(v.y);
-      } else {
-        a += double(m[r * stride + c]);
+    // four rows in flight per thread, added in row order (one load per iteration made this a chain of memory latencies)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 32) {
+      float2 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t ri = r + 8 * i;
+        v[i] = make_float2(0.f, 0.f);
+        if (ri < r1) {
+          if (NC == 2) v[i] = reinterpret_cast<const float2*>(m)[ri * stride + c];
+          else v[i].x = m[ri * stride + c];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a += double(v[i].x);
+        if (NC == 2) b += double(v[i].y);
       }
     }
   }
@@ -99,9 +108,10 @@ __global__ void rowsum_fused_kernel(const float* __restrict__ m, size_t rows_per
     if (last) g_rowsum_tickets[blockIdx.x] = 0u;       // ready for the next launch
   }
   __syncthreads();
-  if (last && threadIdx.y == 0 && c < C) {
+  if (last && threadIdx.y == 0) {
     __threadfence();                                   // the other blocks' partials after their tickets
-    fin(tmp, c);
+    if constexpr (Fin::kWarp) fin(tmp, c);             // warp-collective finisher (all 32 lanes; it checks c < C itself)
+    else if (c < C) fin(tmp, c);
   }
 }
 
@@ -109,6 +119,7 @@ __global__ void rowsum_fused_kernel(const float* __restrict__ m, size_t rows_per
 // batch statistics -> BN constants {s, t, mean, rstd} per (group, channel); moving-average update
 // ---------------------------------------------------------------------------------------------
 struct BnStatsFin {
+  static constexpr bool kWarp = false;
   int N, G, L, C;
   const float* gamma;
   const float* beta;
@@ -145,6 +156,7 @@ struct BnStatsFin {
 // (2) the caller all-reduces them, (3) constants from the global sums and the global count.
 // ---------------------------------------------------------------------------------------------
 struct SumsFin {
+  static constexpr bool kWarp = false;
   int G, C;
   double2* sums;
   __device__ void operator()(const double2* __restrict__ tmp, int c) const {
@@ -210,6 +222,57 @@ __device__ __forceinline__ void bn_bwd_from_sums_channel(int c, const double2* _
   dgamma[c] = float(tg);
   dbeta[c] = float(tb);
 }
+// Column finishers with the cross-rank sum inside (p2p_allreduce_column): the reduction kernel's last block of every
+// 32-channel column exchanges that column's sums and derives the constants -- reduction, exchange and constants are
+// ONE launch (they were two: *_sums, then a one-block *_sync kernel).
+constexpr int kPeersMaxGroups = 4;
+struct BnStatsPeersFin {
+  static constexpr bool kWarp = true;
+  int G, C;
+  double cnt;
+  P2PPeers peers;
+  unsigned int seq;
+  double2* local;   // (G, C) this rank's sums (kept for inspection; may be null)
+  double2* total;   // (G, C) sums over the ranks
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* moving_mean;
+  float* moving_var;
+  float4* bn_const;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const {
+    double2 mine[kPeersMaxGroups];
+    for (int g = 0; g < G; ++g) {
+      mine[g] = (c < C) ? rowsum_stage2(tmp, g, C, c) : make_double2(0.0, 0.0);
+      if (local != nullptr && c < C) local[size_t(g) * C + c] = mine[g];
+    }
+    p2p_allreduce_column<kPeersMaxGroups>(mine, G, C, c, blockIdx.x, peers, seq, total);
+    if (c < C)
+      bn_stats_from_sums_channel(c, total, cnt, G, C, gamma, beta, eps, momentum, moving_mean, moving_var, bn_const);
+  }
+};
+struct BnBwdPeersFin {
+  static constexpr bool kWarp = true;
+  int G, C;
+  double cnt;
+  P2PPeers peers;
+  unsigned int seq;
+  double2* local;   // (G, C) this rank's sums: dgamma / dbeta come from them
+  double2* total;
+  const float4* bn_const;
+  float4* bwd_const;
+  float* dgamma;
+  float* dbeta;
+  __device__ void operator()(const double2* __restrict__ tmp, int c) const {
+    double2 mine[kPeersMaxGroups];
+    for (int g = 0; g < G; ++g) {
+      mine[g] = (c < C) ? rowsum_stage2(tmp, g, C, c) : make_double2(0.0, 0.0);
+      if (c < C) local[size_t(g) * C + c] = mine[g];
+    }
+    p2p_allreduce_column<kPeersMaxGroups>(mine, G, C, c, blockIdx.x, peers, seq, total);
+    if (c < C) bn_bwd_from_sums_channel(c, local, total, cnt, G, C, bn_const, bwd_const, dgamma, dbeta);
+  }
+};
 __global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const double2* __restrict__ global,
                                         double cnt, int G, int C, const float4* __restrict__ bn_const,
                                         float4* __restrict__ bwd_const, float* __restrict__ dgamma,
@@ -323,8 +386,20 @@ __global__ void bn_gmax_fwd_kernel(const float* __restrict__ ext, int N, int lou
     const float4 bc = bn_const[size_t(g) * C + c];
     const float mk = mask ? mask[size_t(n) * C + c] : 1.f;
     const float s = bc.x * mk, t = bc.y * mk;
-    for (int j = threadIdx.y; j < lout; j += 8) {
-      const float y = fmaf(s, ext[(size_t(n) * lout + j) * C + c], t);
+    const float* col = ext + size_t(n) * lout * C + c;
+    int j = threadIdx.y;
+    for (; j + 56 < lout; j += 64) {   // eight windows in flight per thread, compared in window order
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldcs(col + size_t(j + 8 * i) * C);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(s, v[i], t);
+        if (y > best) { best = y; bi = j + 8 * i; }
+      }
+    }
+    for (; j < lout; j += 8) {
+      const float y = fmaf(s, col[size_t(j) * C], t);
       if (y > best) { best = y; bi = j; }
     }
   }
@@ -516,6 +591,221 @@ __global__ void pair_head_loss_bwd_kernel(const float* __restrict__ emb, int N, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// The siamese training head in two launches (was five: dense_fwd, pair_head_loss, pair_head_loss_bwd, dense_bwd_w,
+// dense_bwd_x -- 86 us of a 64-pair step, most of it launch and drain latency of one-block kernels).
+// A pair's loss term depends on its own two clips only, so everything up to d loss / d gmax runs per pair:
+//   kernel 1, one block per pair n: Dense (both clips, the arithmetic of dense_fwd_kernel) -> distance -> sigmoid ->
+//     loss term, hit, dL/dz -> d_emb (branch 2 is the exact negative of branch 1) -> d_gmax = d_emb . W^T;
+//   kernel 2: Dense weight gradient (blocks of 8 channels, the arithmetic of dense_bwd_w_kernel) and, in one extra
+//     block, the batch reductions in a fixed order: loss mean, accuracy, head gradients.
+// Semantics: voicemap/models.py:39,52-69 (Dense, the K-lambdas of the head, Dense(1, sigmoid)), voicemap/utils.py:77-85.
+// ---------------------------------------------------------------------------------------------
+struct SiameseHeadArgs {
+  const float* gmax;      // (2N, C) GlobalMaxPool output: branch 1 rows, then branch 2 rows
+  int N, C, E, metric, loss_kind;
+  const float* dense_w;   // (C, E)
+  const float* dense_b;   // (E)
+  const float* head_w;    // (1) uniform_euclidean, (E) weighted_l1
+  const float* head_b;    // (1)
+  const float* y_true;    // (N)
+  float loss_scale;
+  float* emb;             // (2N, E)
+  float* prob;            // (N) or null
+  float* d_emb;           // (2N, E)
+  float* d_gmax;          // (2N, C)
+  float4* pair;           // (N) {loss term, hit, dL/dz (scaled), distance}
+  float* d_dense_w;       // (C, E)
+  float* d_dense_b;       // (E)
+  float* d_head_w;
+  float* d_head_b;
+  float* loss_acc;        // [2] {mean loss, accuracy}
+};
+
+// y[e] = sum_c xs[c] * w[c][e] + b[e] for e < E: 256 threads = 4 channel quarters x 64 outputs (see dense_fwd_kernel)
+__device__ __forceinline__ void dense_row_256(const float* __restrict__ xs, int C, const float* __restrict__ w,
+                                              const float* __restrict__ b, int E, float* __restrict__ red,
+                                              float* __restrict__ ys, float* __restrict__ yg) {
+  const int part = threadIdx.x >> 6, lane_e = threadIdx.x & 63;
+  const int cq = (C + 3) / 4;
+  const int c0 = part * cq, c1 = min(C, c0 + cq);
+  for (int e0 = 0; e0 < E; e0 += 64) {
+    const int e = e0 + lane_e;
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e < E) {
+      int c = c0;
+      for (; c + 32 <= c1; c += 32) {
+        float wv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) wv[i] = __ldg(w + size_t(c + i) * E + e);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a4[i & 3] = fmaf(xs[c + i], wv[i], a4[i & 3]);
+      }
+      for (; c < c1; ++c) a4[0] = fmaf(xs[c], __ldg(w + size_t(c) * E + e), a4[0]);
+    }
+    red[part * 64 + lane_e] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    __syncthreads();
+    if (part == 0 && e < E) {
+      const float y = ((red[lane_e] + red[64 + lane_e]) + (red[128 + lane_e] + red[192 + lane_e])) + b[e];
+      ys[e] = y;
+      yg[e] = y;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+siamese_head_pair_kernel(const SiameseHeadArgs a) {
+  extern __shared__ float sh[];   // [2][C] gmax rows, [2][E] embeddings, [E] d_emb of branch 1, [256] partials
+  const int n = blockIdx.x, N = a.N, C = a.C, E = a.E;
+  float* xs = sh;
+  float* es = xs + 2 * C;
+  float* de = es + 2 * E;
+  float* red = de + E;
+  __shared__ float s_dz, s_dist;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    xs[c] = a.gmax[size_t(n) * C + c];
+    xs[C + c] = a.gmax[size_t(N + n) * C + c];
+  }
+  __syncthreads();
+  dense_row_256(xs, C, a.dense_w, a.dense_b, E, red, es, a.emb + size_t(n) * E);
+  dense_row_256(xs + C, C, a.dense_w, a.dense_b, E, red, es + E, a.emb + size_t(N + n) * E);
+  if (threadIdx.x == 0) {   // the pair's scalar chain, in the summation order of pair_head_loss_kernel
+    float z, d = 0.f;
+    if (a.metric == 0) {
+      float ss = 0.f;
+      for (int j = 0; j < E; ++j) { const float t = es[j] - es[E + j]; ss = fmaf(t, t, ss); }
+      d = sqrtf(fmaxf(ss, 0.f));
+      z = fmaf(d, a.head_w[0], a.head_b[0]);
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < E; ++j) acc = fmaf(fabsf(es[j] - es[E + j]), a.head_w[j], acc);
+      z = acc + a.head_b[0];
+    }
+    const float p = 1.0f / (1.0f + expf(-z));
+    const float y = a.y_true[n];
+    float term, dp;
+    if (a.loss_kind == 1) {   // contrastive: (1-y) p^2 + y max(1-p,0)^2
+      const float mg = fmaxf(1.0f - p, 0.f);
+      term = (1.f - y) * p * p + y * mg * mg;
+      dp = (1.f - y) * 2.f * p - y * 2.f * mg;
+    } else {                  // BCE on clip(p, 1e-7, 1-1e-7): zero gradient outside the clip range
+      const float lo = 1e-7f, hi = 1.0f - 1e-7f;
+      const float pc = fminf(fmaxf(p, lo), hi);
+      term = -y * logf(pc) - (1.f - y) * logf(1.0f - pc);
+      dp = (p < lo || p > hi) ? 0.f : (-y / p + (1.f - y) / (1.f - p));
+    }
+    const float dz = dp * p * (1.f - p) * (a.loss_scale / float(N));
+    const float hit = ((p > 0.5f ? 1.f : 0.f) == y) ? 1.f : 0.f;   // keras 'accuracy' of a sigmoid output
+    if (a.prob != nullptr) a.prob[n] = p;
+    a.pair[n] = make_float4(term, hit, dz, d);
+    s_dz = dz;
+    s_dist = d;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    const float diff = es[j] - es[E + j];
+    float g;
+    if (a.metric == 0)
+      g = (s_dist > 0.f) ? s_dz * a.head_w[0] * diff / s_dist : 0.f;   // sqrt'(0) guarded (the reference yields NaN)
+    else
+      g = s_dz * a.head_w[j] * ((diff > 0.f) - (diff < 0.f));
+    de[j] = g;
+    a.d_emb[size_t(n) * E + j] = g;
+    a.d_emb[size_t(N + n) * E + j] = -g;
+  }
+  __syncthreads();
+  // d_gmax[c] = sum_e d_emb[e] * W[c][e]; four partial chains per channel, summed in a fixed order.  Branch 2 receives
+  // the exact negative (d_emb2 = -d_emb1 and rounding is symmetric).
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float4* wr = reinterpret_cast<const float4*>(a.dense_w + size_t(c) * E);
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((E & 3) == 0) {
+      for (int e = 0; e < E; e += 4) {
+        const float4 w4 = __ldg(wr + (e >> 2));
+        a4[0] = fmaf(de[e], w4.x, a4[0]);
+        a4[1] = fmaf(de[e + 1], w4.y, a4[1]);
+        a4[2] = fmaf(de[e + 2], w4.z, a4[2]);
+        a4[3] = fmaf(de[e + 3], w4.w, a4[3]);
+      }
+    } else {
+      for (int e = 0; e < E; ++e) a4[e & 3] = fmaf(de[e], __ldg(a.dense_w + size_t(c) * E + e), a4[e & 3]);
+    }
+    const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    a.d_gmax[size_t(n) * C + c] = acc;
+    a.d_gmax[size_t(N + n) * C + c] = -acc;
+  }
+}
+
+// blocks [0, ceil(C/8)): dW rows of 8 channels over all 2N clips (clips in order, as dense_bwd_w_kernel);
+// the last block: loss, accuracy and head gradients from the per-pair records, fixed order.
+__global__ void __launch_bounds__(64)
+siamese_head_finish_kernel(const SiameseHeadArgs a) {
+  const int N = a.N, C = a.C, E = a.E, NB = 2 * a.N;
+  const int wblocks = (C + 7) / 8;
+  if (int(blockIdx.x) < wblocks) {
+    const int c0 = blockIdx.x * 8;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
+      int n = 0;
+      for (; n + 4 <= NB; n += 4) {
+        float d[4], xv[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          d[i] = a.d_emb[size_t(n + i) * E + e];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xv[i][k] = (c0 + k < C) ? __ldg(a.gmax + size_t(n + i) * C + c0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          accb += d[i];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[i][k], d[i], acc[k]);
+        }
+      }
+      for (; n < NB; ++n) {
+        const float d = a.d_emb[size_t(n) * E + e];
+        accb += d;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k < C) acc[k] = fmaf(a.gmax[size_t(n) * C + c0 + k], d, acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c0 + k < C) a.d_dense_w[size_t(c0 + k) * E + e] = acc[k];
+      if (blockIdx.x == 0) a.d_dense_b[e] = accb;
+    }
+    return;
+  }
+  if (a.metric == 0) {
+    if (threadIdx.x == 0) {
+      float gw = 0.f, gb = 0.f;
+      for (int n = 0; n < N; ++n) { const float4 r = a.pair[n]; gw = fmaf(r.z, r.w, gw); gb += r.z; }
+      a.d_head_w[0] = gw;
+      a.d_head_b[0] = gb;
+    }
+  } else {
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+      float gw = 0.f;
+      for (int n = 0; n < N; ++n)
+        gw = fmaf(a.pair[n].z, fabsf(a.emb[size_t(n) * E + j] - a.emb[size_t(N + n) * E + j]), gw);
+      a.d_head_w[j] = gw;
+    }
+    if (threadIdx.x == 0) {
+      float gb = 0.f;
+      for (int n = 0; n < N; ++n) gb += a.pair[n].z;
+      a.d_head_b[0] = gb;
+    }
+  }
+  if (threadIdx.x == 32) {   // another warp: loss mean (double, pairs in order) and accuracy
+    double ls = 0.0;
+    float hits = 0.f;
+    for (int n = 0; n < N; ++n) { const float4 r = a.pair[n]; ls += double(r.x); hits += r.y; }
+    a.loss_acc[0] = float(ls / double(N));
+    a.loss_acc[1] = hits / float(N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // BN backward, pass 1: per-channel sums of dy and dy * xhat over the batch, and the largest |s * dy|.
 // The gradient of a pooled output lands on the window's arg-max, where u equals the stored extreme, so
 //   sum dy        = sum over windows of dy,      sum dy * xhat = sum over windows of dy * (ext - mean) * rstd
@@ -590,6 +880,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ ext, const float* __restrict__ dy
 
 // pass 2: per (group, channel) means -> bwd constants {s, mean_dy, mean_dyxhat, 0}; dgamma/dbeta summed over groups.
 struct BnBwdFin {
+  static constexpr bool kWarp = false;
   int N, G, L, C;
   const float4* bn_const;
   float4* bwd_const;
@@ -626,7 +917,9 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
                    __half* __restrict__ du_hi, __half* __restrict__ du_lo, float* __restrict__ dbias_partial) {
   const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
   const int groups = C >> 3, streams = ew_streams(C, 8);
-  if (int(threadIdx.x) >= groups * streams) return;
+  __shared__ float bias_red[kEwThreads * 8];   // [stream][C] conv-bias partials of the block's threads
+  if (int(threadIdx.x) >= groups * streams) return;   // (a barrier waits for the non-exited threads only)
+  {
   const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 8 * cg;
   const int g = n / (N / G);
   constexpr int pool = kPool;
@@ -713,6 +1006,8 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
   // 8 / kPool windows in flight per thread (the same bytes for either pool size): with two windows of MaxPool(2) a
   // thread had 64-96 bytes outstanding and blocks 2-4 ran at 2-4 TB/s
   constexpr int kFlight = 8 / kPool;
+  // (requesting the first windows before the constants' loads was measured: no gain for MaxPool(4), and the MaxPool(2)
+  // variants spill at the 128-register cap and lose 15 %)
   for (int w = w0 + stream; w < w1; w += kFlight * streams) {
     Window Wf[kFlight];
 #pragma unroll
@@ -723,13 +1018,22 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
       if (w + f * streams < w1) apply_window(w + f * streams, Wf[f]);
   }
   const float inv = 1.0f / scale;
-  float* row = dbias_partial + ((size_t(n) * chunks + chunk) * streams + stream) * C + c;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) row[k] = sb[k] * inv;
+  for (int k = 0; k < 8; ++k) bias_red[stream * C + c + k] = sb[k] * inv;
+  }
+  // one partial row per block: the streams' sums are added in stream order (deterministic)
+  __syncthreads();
+  float* row = dbias_partial + (size_t(n) * chunks + chunk) * C;
+  for (int t = threadIdx.x; t < C; t += groups * streams) {
+    float s = 0.f;
+    for (int st = 0; st < streams; ++st) s += bias_red[st * C + t];
+    row[t] = s;
+  }
 }
 
 // second stage of a plain column sum -> out[C]
 struct ColsumFin {
+  static constexpr bool kWarp = false;
   int C;
   float* out;
   __device__ void operator()(const double2* __restrict__ tmp, int c) const { out[c] = float(rowsum_stage2(tmp, 0, C, c).x); }
@@ -836,6 +1140,25 @@ int launch_bn_stats_sync(const double* local_sums, double* total_sums, void* con
   return check_launch_t("bn_stats_sync");
 }
 
+int launch_bn_stats_finalize_peers(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C,
+                                   double* red_scratch, void* const* peers, int rank, int world, unsigned int seq,
+                                   double count, const float* gamma, const float* beta, float eps, float momentum,
+                                   float* moving_mean, float* moving_var, float* bn_const, double* local_sums,
+                                   double* total_sums, cudaStream_t st) {
+  if (red_scratch == nullptr) return set_error(VM_ERR_SHAPE, "bn_stats_finalize_peers: reduction scratch missing");
+  if (N <= 0 || G <= 0 || G > kPeersMaxGroups || N % G != 0 || C > 2048 || total_sums == nullptr || !(count > 0.0))
+    return set_error(VM_ERR_SHAPE, "bn_stats_finalize_peers: bad arguments");
+  P2PPeers pp{};
+  int rc = p2p_check(peers, rank, world, 2 * G * C, &pp);
+  if (rc) return rc;
+  const BnStatsPeersFin fin{G, C, count, pp, seq, reinterpret_cast<double2*>(local_sums),
+                            reinterpret_cast<double2*>(total_sums), gamma, beta, eps, momentum, moving_mean, moving_var,
+                            reinterpret_cast<float4*>(bn_const)};
+  rowsum_fused_kernel<2><<<dim3((C + 31) / 32, G * kRB), dim3(32, 8), 0, st>>>(
+      partial, size_t(N / G) * rows_per_clip, c_pad, C, reinterpret_cast<double2*>(red_scratch), fin);
+  return check_launch_t("bn_stats_finalize_peers");
+}
+
 int launch_bn_pool_fwd(const float* ext, int N, int lout, int C, int G, const float* bn_const, const float* mask,
                        __half* out_hi, __half* out_lo, uint16_t* out_q, cudaStream_t st) {
   if (C % 8 != 0 || N <= 0 || G <= 0 || N % G != 0 || lout <= 0) return set_error(VM_ERR_SHAPE, "bn_pool_fwd: bad shape");
@@ -883,6 +1206,27 @@ int launch_pair_head_loss_bwd(const float* emb, int N, int E, int metric, const 
                                                                    loss_kind, loss_scale, d_emb, d_head_w, d_head_b,
                                                                    accuracy);
   return check_launch_t("pair_head_loss_bwd");
+}
+
+int launch_siamese_head_train(const float* gmax, int N, int C, int E, const float* dense_w, const float* dense_b,
+                              int metric, const float* head_w, const float* head_b, const float* y_true, int loss_kind,
+                              float loss_scale, float* emb, float* prob, float* d_emb, float* d_gmax, float* pair_scratch,
+                              float* d_dense_w, float* d_dense_b, float* d_head_w, float* d_head_b, float* loss_acc,
+                              cudaStream_t st) {
+  if (N <= 0 || C <= 0 || E <= 0) return set_error(VM_ERR_SHAPE, "siamese_head_train: bad shape");
+  if (metric != 0 && metric != 1) return set_error(VM_ERR_UNSUPPORTED, "siamese_head_train: metric not implemented");
+  if (loss_kind != 1 && loss_kind != 2) return set_error(VM_ERR_UNSUPPORTED, "siamese_head_train: loss not implemented");
+  if (!gmax || !dense_w || !dense_b || !head_w || !head_b || !y_true || !emb || !d_emb || !d_gmax || !pair_scratch ||
+      !d_dense_w || !d_dense_b || !d_head_w || !d_head_b || !loss_acc)
+    return set_error(VM_ERR_SHAPE, "siamese_head_train: null pointer");
+  const size_t smem = (size_t(2) * C + size_t(3) * E + 256) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(VM_ERR_UNSUPPORTED, "siamese_head_train: C / E too large");
+  const SiameseHeadArgs a{gmax, N, C, E, metric, loss_kind, dense_w, dense_b, head_w, head_b, y_true, loss_scale, emb,
+                          prob, d_emb, d_gmax, reinterpret_cast<float4*>(pair_scratch), d_dense_w, d_dense_b, d_head_w,
+                          d_head_b, loss_acc};
+  siamese_head_pair_kernel<<<N, 256, smem, st>>>(a);
+  siamese_head_finish_kernel<<<(C + 7) / 8 + 1, 64, 0, st>>>(a);
+  return check_launch_t("siamese_head_train");
 }
 
 static int bn_bwd_check(const double* red_scratch, int N, int G, int C, const void* dy_pooled, const void* d_gmax,
@@ -950,8 +1294,8 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
 #undef VM_RELU_BWD_P
 #undef VM_RELU_BWD
   const ColsumFin fin{C, dbias};
-  rowsum_fused_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial, size_t(N) * chunks * streams,
-                                                                          C, C, tmp, fin);
+  rowsum_fused_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial, size_t(N) * chunks, C, C, tmp,
+                                                                          fin);
   return VM_OK;
 }
 
@@ -1019,6 +1363,29 @@ int launch_bn_bwd_sync(const double* local_sums, double* total_sums, void* const
   bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
                dbias_partial, dbias, red_scratch, st);
   return check_launch_t("bn_bwd_sync");
+}
+
+int launch_bn_bwd_peers(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax,
+                        const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
+                        float* partial, float* bwd_const, float* dgamma, float* dbeta, unsigned int* absmax,
+                        __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias, double* red_scratch,
+                        int presummed_rows, void* const* peers, int rank, int world, unsigned int seq, double count,
+                        double* local_sums, double* total_sums, cudaStream_t st) {
+  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
+  if (rc) return rc;
+  if (local_sums == nullptr || total_sums == nullptr || !(count > 0.0) || G > kPeersMaxGroups)
+    return set_error(VM_ERR_SHAPE, "bn_bwd_peers: bad sums / count / groups");
+  P2PPeers pp{};
+  if ((rc = p2p_check(peers, rank, world, 2 * G * C, &pp))) return rc;
+  const BnBwdPeersFin fin{G, C, count, pp, seq, reinterpret_cast<double2*>(local_sums),
+                          reinterpret_cast<double2*>(total_sums), reinterpret_cast<const float4*>(bn_const),
+                          reinterpret_cast<float4*>(bwd_const), dgamma, dbeta};
+  if ((rc = bn_bwd_reduce(ext, dy_pooled, d_gmax, jstar, N, L / pool, C, G, bn_const, mask, partial, absmax,
+                          red_scratch, fin, presummed_rows, st)))
+    return rc;
+  bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
+               dbias_partial, dbias, red_scratch, st);
+  return check_launch_t("bn_bwd_peers");
 }
 
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,

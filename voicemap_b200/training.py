@@ -241,6 +241,7 @@ class TrainEngine:
         self.maskbuf = [torch.empty((nb, c[b]), dtype=f32, device=dev) for b in range(4)]
         self.prob = torch.empty((max(1, nb // groups), 1), dtype=f32, device=dev)
         self.lossv = torch.zeros((2,), dtype=f32, device=dev)      # [loss, accuracy] of the step
+        self.pairrec = torch.empty((max(1, nb // groups), 4), dtype=f32, device=dev)   # per pair {loss, hit, dL/dz, dist}
         self.masks = [None] * 4
         self._plans = {}
         self._buf_key = key
@@ -278,8 +279,9 @@ class TrainEngine:
         return True
 
     # ------------------------------------------------------------------ forward (train mode)
-    def forward_train(self, x, groups, masks=None, update_moving=True):
-        """x: CUDA fp32 (NB, L).  Returns embeddings (NB, E).  Keeps everything backward needs."""
+    def forward_train(self, x, groups, masks=None, update_moving=True, dense=True):
+        """x: CUDA fp32 (NB, L).  Returns embeddings (NB, E).  Keeps everything backward needs.  dense=False stops after
+        GlobalMaxPool1D (the siamese step's fused head call applies the embedding Dense itself)."""
         nb, length = x.shape
         self._buffers(nb, length, groups)
         if x.data_ptr() != self.xin.data_ptr():
@@ -288,14 +290,14 @@ class TrainEngine:
         self.groups = groups
         dropout_on = self._set_masks(nb, masks)
         key = ("fwd", dropout_on, bool(update_moving), self.sync_allreduce is not None, self.sync_peers is not None,
-               torch.cuda.current_stream().cuda_stream)
+               bool(dense), torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
-            plan = self._plans[key] = self._build_forward_plan(nb, length, groups, update_moving)
+            plan = self._plans[key] = self._build_forward_plan(nb, length, groups, update_moving, dense)
         plan.run()
         return self.embv
 
-    def _build_forward_plan(self, nb, length, groups, update_moving):
+    def _build_forward_plan(self, nb, length, groups, update_moving, dense=True):
         lib, plan, st = self.lib, _Plan(), _stream()
         self._plan_pack(plan, st)
         c, ls = self.channels, self.ls
@@ -318,16 +320,16 @@ class TrainEngine:
                             groups, ls[b], c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv), _ptr(self.bnc[b]),
                             _ptr(self.red), st)
             elif self.sync_peers is not None:
+                # reduction, exchange over peer memory and constants in one launch (column finishers, vm_p2p.cuh)
                 pe = self.sync_peers
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
-                plan.launch(lib.vm_bn_stats_sums, "vm_bn_stats_sums", _ptr(self.stat[b]), self.stat_rows[b], nb, groups,
-                            c[b], _ptr(self.red), _ptr(loc), st)
                 plan.host(pe.bump)
                 count = float(self.sync_world) * (nb // groups) * ls[b]   # equal shards on every rank
-                plan.launch(lib.vm_bn_stats_sync, "vm_bn_stats_sync", _ptr(loc), _ptr(glo), pe.peers, pe.rank, pe.world,
-                            pe.seq, C.c_double(count), groups, c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv),
-                            _ptr(self.bnc[b]), st)
+                plan.launch(lib.vm_bn_stats_finalize_peers, "vm_bn_stats_finalize_peers", _ptr(self.stat[b]),
+                            self.stat_rows[b], nb, groups, c[b], gamma, beta, eps, mom, _ptr(mm), _ptr(mv),
+                            _ptr(self.bnc[b]), _ptr(self.red), pe.peers, pe.rank, pe.world, pe.seq, C.c_double(count),
+                            _ptr(loc), _ptr(glo), st)
             else:
                 sums = self.sums[1][:groups * c[b] * 2]
                 plan.launch(lib.vm_bn_stats_sums, "vm_bn_stats_sums", _ptr(self.stat[b]), self.stat_rows[b], nb, groups,
@@ -343,8 +345,9 @@ class TrainEngine:
             else:
                 plan.launch(lib.vm_bn_gmax_fwd, "vm_bn_gmax_fwd", _ptr(self.EXT[3]), nb, ls[4], c[3], groups,
                             _ptr(self.bnc[3]), _ptr(self.masks[3]), _ptr(self.gmax), _ptr(self.jstar), st)
-        plan.launch(lib.vm_dense_fwd, "vm_dense_fwd", _ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]),
-                    _ptr(self.p["dense_bias"]), self.emb, _ptr(self.embv), st)
+        if dense:
+            plan.launch(lib.vm_dense_fwd, "vm_dense_fwd", _ptr(self.gmax), nb, c[3], _ptr(self.p["dense_kernel"]),
+                        _ptr(self.p["dense_bias"]), self.emb, _ptr(self.embv), st)
         return plan
 
     def bucket_bounds(self):
@@ -375,22 +378,24 @@ class TrainEngine:
         self._plans = {}
 
     # ------------------------------------------------------------------ backward of the encoder
-    def backward_encoder(self, d_emb):
-        """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters."""
-        if d_emb.data_ptr() != self.d_emb.data_ptr():
+    def backward_encoder(self, d_emb, dense=True):
+        """d_emb (NB, E) (already multiplied by the loss scale).  Fills self.g for all encoder parameters.  dense=False:
+        the caller has already written self.d_gmax and the Dense gradients (the siamese step's fused head call)."""
+        if dense and d_emb.data_ptr() != self.d_emb.data_ptr():
             self.d_emb.copy_(d_emb)
         key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None, self.sync_peers is not None,
-               self.grad_buckets is not None, torch.cuda.current_stream().cuda_stream)
+               self.grad_buckets is not None, bool(dense), torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
-            plan = self._plans[key] = self._build_backward_plan(self.d_emb.shape[0])
+            plan = self._plans[key] = self._build_backward_plan(self.d_emb.shape[0], dense)
         plan.run()
 
-    def _build_backward_plan(self, nb):
+    def _build_backward_plan(self, nb, dense=True):
         lib, plan, st = self.lib, _Plan(), _stream()
         c, ls, g, groups = self.channels, self.ls, self.g, self.groups
-        plan.launch(lib.vm_dense_bwd, "vm_dense_bwd", _ptr(self.gmax), _ptr(self.d_emb), _ptr(self.p["dense_kernel"]), nb,
-                    c[3], self.emb, _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
+        if dense:
+            plan.launch(lib.vm_dense_bwd, "vm_dense_bwd", _ptr(self.gmax), _ptr(self.d_emb), _ptr(self.p["dense_kernel"]),
+                        nb, c[3], self.emb, _ptr(g["dense_kernel"]), _ptr(g["dense_bias"]), _ptr(self.d_gmax), st)
         buckets = self.grad_buckets
         if buckets is not None:    # Dense + head gradients are complete (the head's were written before this plan)
             plan.host(lambda: buckets.launch(0))
@@ -417,16 +422,13 @@ class TrainEngine:
                 pe = self.sync_peers
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
-                plan.launch(lib.vm_bn_bwd_sums, f"vm_bn_bwd_sums block {b + 1}", _ptr(self.EXT[b]), _ptr(dy), _ptr(dg),
-                            _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]),
-                            _ptr(part), gabs, _ptr(self.red), _ptr(loc), pre_rows, st)
                 plan.host(pe.bump)
                 count = float(self.sync_world) * (nb // groups) * ls[b]
-                plan.launch(lib.vm_bn_bwd_sync, f"vm_bn_bwd_sync block {b + 1}", _ptr(loc), _ptr(glo), pe.peers, pe.rank,
-                            pe.world, pe.seq, C.c_double(count), _ptr(self.U16[b]), _ptr(dy), _ptr(dg), _ptr(js), nb,
-                            ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.bwc[b]),
-                            *grads, gabs, _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]),
-                            _ptr(self.red), st)
+                plan.launch(lib.vm_bn_bwd_peers, f"vm_bn_bwd_peers block {b + 1}", _ptr(self.U16[b]), _ptr(self.EXT[b]),
+                            _ptr(dy), _ptr(dg), _ptr(js), nb, ls[b], c[b], groups, self.pools[b], _ptr(self.bnc[b]),
+                            _ptr(self.masks[b]), _ptr(part), _ptr(self.bwc[b]), *grads, gabs, _ptr(du_hi), _ptr(du_lo),
+                            _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), pre_rows, pe.peers, pe.rank,
+                            pe.world, pe.seq, C.c_double(count), _ptr(loc), _ptr(glo), st)
             else:
                 k = groups * c[b] * 2
                 loc, glo = self.sums[0][:k], self.sums[1][:k]
@@ -526,13 +528,13 @@ class TrainEngine:
         self._stage(x1, self.xin[:n])
         self._stage(x2, self.xin[n:])
         self._stage(np.asarray(y, dtype=np.float32).reshape(-1) if not isinstance(y, torch.Tensor) else y, self.yin)
-        self.forward_train(self.xin, groups=2, masks=masks)
+        self.forward_train(self.xin, groups=2, masks=masks, dense=False)
         key = ("head", torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = self._build_siamese_head_plan(n)
         plan.run()
-        self.backward_encoder(self.d_emb)
+        self.backward_encoder(self.d_emb, dense=False)
         self._share_gradients(allreduce)
         if apply:
             self.apply_gradients(world)
@@ -551,12 +553,14 @@ class TrainEngine:
         metric_id = {"uniform_euclidean": 0, "weighted_l1": 1}[metric]
         loss_id = 1 if self.loss == "contrastive_loss" else 2
         hw, hb = self.p["head_kernel"].reshape(-1), self.p["head_bias"]
-        e1, e2 = self.embv[:n], self.embv[n:]
-        plan.launch(lib.vm_pair_head_loss_fwd, "vm_pair_head_loss_fwd", _ptr(e1), _ptr(e2), n, self.emb, metric_id,
-                    _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, None, _ptr(self.prob), _ptr(self.lossv), st)
-        plan.launch(lib.vm_pair_head_loss_bwd, "vm_pair_head_loss_bwd", _ptr(self.embv), n, self.emb, metric_id,
-                    _ptr(hw), _ptr(hb), _ptr(self.yin), loss_id, C.c_float(self.loss_scale), _ptr(self.d_emb),
-                    _ptr(self.g["head_kernel"]), _ptr(self.g["head_bias"]), _ptr(self.lossv[1:]), st)
+        g = self.g
+        # embedding Dense, distance layer, Dense(1, sigmoid), loss, accuracy and their backward pass down to d_gmax: one
+        # call, two launches (per-pair kernel + Dense weight gradient / batch reductions)
+        plan.launch(lib.vm_siamese_head_train, "vm_siamese_head_train", _ptr(self.gmax), n, self.channels[3], self.emb,
+                    _ptr(self.p["dense_kernel"]), _ptr(self.p["dense_bias"]), metric_id, _ptr(hw), _ptr(hb),
+                    _ptr(self.yin), loss_id, C.c_float(self.loss_scale), _ptr(self.embv), _ptr(self.prob),
+                    _ptr(self.d_emb), _ptr(self.d_gmax), _ptr(self.pairrec), _ptr(g["dense_kernel"]),
+                    _ptr(g["dense_bias"]), _ptr(g["head_kernel"]), _ptr(g["head_bias"]), _ptr(self.lossv), st)
         return plan
 
     def classifier_step(self, x, y_onehot, apply=True, masks=None, allreduce=None, world=1):
