@@ -261,7 +261,7 @@ __device__ __forceinline__ void linear_tile(float unscale, uint32_t taddr, uint8
 // fused BatchNorm-backward sums) and left the tensor pipe 42-64 % busy with one set.
 // kXS: slots of the X ring (2 two-plane slots, or 4 one-plane slots in the same shared memory) -- a compile-time constant:
 // as a kernel parameter the slot index cost two integer divisions per K chunk in the MMA-issuing thread and the eval
-// forward lost 2-3 % (same-box A/B, profiles/r02_ab_forward.log).
+// forward lost 2-3 % (same-box A/B, profiles/r02_ab_forward_fused_head_and_xring.log).
 template <int kSets, int kXS>
 __global__ void __launch_bounds__((4 + 8 * kSets) * 32, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tm_xh_main, const __grid_constant__ CUtensorMap tm_xh_halo,

@@ -106,6 +106,11 @@ class TrainEngine:
         self.sync_world = 1
         self.sync_peers = None     # parallel.PeerExchange: the BatchNorm sums cross the ranks inside the kernels (NVLink)
         self.grad_buckets = None   # parallel.GradientBuckets: per-block asynchronous gradient all-reduce (data parallel)
+        # weight gradients on a side stream: wgrad of block b only feeds the optimizer, so it runs beside the BatchNorm /
+        # ReLU backward pass of block b-1 (HBM-bound, no shared memory) instead of in front of it (VOICEMAP_WGRAD_STREAM=0
+        # or overlap_wgrad = False: everything on one stream, as the per-launch timeline needs it)
+        self.overlap_wgrad = os.environ.get("VOICEMAP_WGRAD_STREAM", "1") != "0"
+        self._side = None
         if isinstance(model, SiameseModel):
             self.kind = "siamese"
             self.encoder_model = model.encoder
@@ -221,7 +226,10 @@ class TrainEngine:
         self.d_emb = torch.empty((nb, self.emb), dtype=f32, device=dev)
         self.d_gmax = torch.empty((nb, c[3]), dtype=f32, device=dev)
         max_u = max(ls[b] * c[b] for b in range(4))
-        self.dU = torch.empty((2 if self.bwd_precision == 3 else 1, nb * max_u), dtype=f16, device=dev)
+        # gradient planes, two sets used alternately by the blocks: block b-2 may overwrite a set only after block b's
+        # weight gradient (side stream) has read it
+        self.dU = [torch.empty((2 if self.bwd_precision == 3 else 1, nb * max_u), dtype=f16, device=dev)
+                   for _ in range(2)]
         self.gabs = torch.zeros((4,), dtype=torch.int32, device=dev)   # per block: bits of max |s * dy| -> gradient scale
         # blocks 1-3: partial rows of the BatchNorm-backward sums, written by the dgrad epilogue of the block above
         self.redp = [torch.empty((nb * self.lib.vm_conv3_train_rows_per_clip(ls[b + 1]), self.lib.vm_padded_channels(c[b]), 2),
@@ -384,7 +392,8 @@ class TrainEngine:
         if dense and d_emb.data_ptr() != self.d_emb.data_ptr():
             self.d_emb.copy_(d_emb)
         key = ("bwd", self.masks[0] is not None, self.sync_allreduce is not None, self.sync_peers is not None,
-               self.grad_buckets is not None, bool(dense), torch.cuda.current_stream().cuda_stream)
+               self.grad_buckets is not None, bool(dense), bool(self.overlap_wgrad),
+               torch.cuda.current_stream().cuda_stream)
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = self._build_backward_plan(self.d_emb.shape[0], dense)
@@ -400,11 +409,22 @@ class TrainEngine:
         if buckets is not None:    # Dense + head gradients are complete (the head's were written before this plan)
             plan.host(lambda: buckets.launch(0))
         bp = self.bwd_precision
+        side = None
+        if self.overlap_wgrad:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            main = torch.cuda.current_stream()
+            st2 = C.c_void_p(side.cuda_stream)
+            du_ready = [torch.cuda.Event() for _ in range(4)]     # block b's dU written (main stream)
+            wgrad_done = [torch.cuda.Event() for _ in range(4)]   # block b's weight gradient finished (side stream)
         for b in (3, 2, 1, 0):
             n_u = nb * ls[b] * c[b]
-            du_hi = self.dU[0][:n_u]
-            du_lo = self.dU[1][:n_u] if bp == 3 else None
+            du_hi = self.dU[b % 2][0][:n_u]
+            du_lo = self.dU[b % 2][1][:n_u] if bp == 3 else None
             gabs = _ptr(self.gabs[b:b + 1])
+            if side is not None and b <= 1:    # this block's dU set was last read by block b+2's weight gradient
+                plan.host(lambda e=wgrad_done[b + 2]: main.wait_event(e))
             if b == 3:
                 dy, dg, js = None, self.d_gmax, self.jstar
             else:
@@ -445,25 +465,46 @@ class TrainEngine:
                             C.c_double(count), _ptr(self.U16[b]), _ptr(dy), _ptr(dg), _ptr(js), nb, ls[b], c[b], groups,
                             self.pools[b], _ptr(self.bnc[b]), _ptr(self.masks[b]), _ptr(self.bwc[b]), *grads, gabs,
                             _ptr(du_hi), _ptr(du_lo), _ptr(self.scr1), _ptr(g[f"conv{b + 1}_bias"]), _ptr(self.red), st)
-            if b == 0:
-                plan.launch(lib.vm_wgrad1, "vm_wgrad1", _ptr(self.xin), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp,
-                            gabs, _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), st)
-                if buckets is not None:
-                    plan.host(lambda: buckets.launch(4))
-            else:
-                x_lo = self.XL[b - 1]
-                wp = bp if x_lo is not None else 1      # forward precision 1 keeps no second activation plane
-                plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.X[b - 1]), _ptr(x_lo), _ptr(du_hi),
-                            _ptr(du_lo if wp == 3 else None), nb, ls[b], c[b - 1], c[b], wp, gabs, _ptr(self.wpart),
-                            self.wpart.numel() * 4, _ptr(g[f"conv{b + 1}_kernel"]), st)
-                if buckets is not None:    # block b+1's gradients are complete: share them while dgrad and the
-                    plan.host(lambda i=4 - b: buckets.launch(i))   # blocks below keep the device busy
+            if b > 0:
                 # dgrad: dX_{b-1} = conv3(dU_b, flipped/transposed W_b), fp32 (NB, ls[b], c[b-1])
                 # ... and, in its epilogue, the BatchNorm-backward sums of block b (dX is that block's pooled gradient)
                 plan.launch(lib.vm_conv3_dgrad, f"dgrad block {b + 1}", _ptr(du_hi), _ptr(du_lo), nb, ls[b], c[b],
                             c[b - 1], _ptr(self.wdg[b]), _ptr(self.edg[b]), gabs, _ptr(self.dX), bp,
                             _ptr(self.EXT[b - 1]), _ptr(self.bnc[b - 1]), _ptr(self.masks[b - 1]), groups,
                             _ptr(self.redp[b - 1]), _ptr(self.gabs[b - 1:b]), st)
+            stw = st
+            if side is not None:
+                # the weight gradient starts when dgrad has left the SMs (both kernels take a whole SM's shared memory):
+                # it then runs beside the next block's BatchNorm / ReLU backward pass
+                def fork(e=du_ready[b]):
+                    e.record(main)
+                    side.wait_event(e)
+                plan.host(fork)
+                stw = st2
+
+            def share(i):   # block's gradients complete (its BatchNorm / bias gradients precede du_ready): all-reduce them
+                if side is None:
+                    buckets.launch(i)
+                else:
+                    with torch.cuda.stream(side):
+                        buckets.launch(i)
+            if b == 0:
+                plan.launch(lib.vm_wgrad1, "vm_wgrad1", _ptr(self.xin), _ptr(du_hi), _ptr(du_lo), nb, ls[0], c[0], bp,
+                            gabs, _ptr(self.wpart), self.wpart.numel() * 4, _ptr(g["conv1_kernel"]), stw)
+                if buckets is not None:
+                    plan.host(lambda: share(4))
+            else:
+                x_lo = self.XL[b - 1]
+                wp = bp if x_lo is not None else 1      # forward precision 1 keeps no second activation plane
+                plan.launch(lib.vm_wgrad3, f"vm_wgrad3 block {b + 1}", _ptr(self.X[b - 1]), _ptr(x_lo), _ptr(du_hi),
+                            _ptr(du_lo if wp == 3 else None), nb, ls[b], c[b - 1], c[b], wp, gabs, _ptr(self.wpart),
+                            self.wpart.numel() * 4, _ptr(g[f"conv{b + 1}_kernel"]), stw)
+                if buckets is not None:    # block b+1's gradients are complete: share them while dgrad and the
+                    plan.host(lambda i=4 - b: share(i))            # blocks below keep the device busy
+            if side is not None:
+                plan.host(lambda e=wgrad_done[b]: e.record(side))
+        if side is not None:    # the optimizer (and the next step's forward pass) follow the last weight gradient
+            plan.host(lambda e=wgrad_done[0]: main.wait_event(e))
         return plan
 
     # ------------------------------------------------------------------ optimizer
@@ -604,24 +645,28 @@ class TrainEngine:
     def time_siamese_step(self, x1, x2, y, steps=10):
         """Live per-launch durations of a siamese step (CUDA events between the C-ABI calls, averaged over ``steps``
         steps after one warm-up step): [(what, ms), ...] in launch order, Adam last."""
-        self.siamese_step(x1, x2, y)
-        acc = None
-        for _ in range(steps):
-            timings = []
-            run, _Plan.run = _Plan.run, lambda plan: plan.run_timed(timings)
-            try:
-                self.siamese_step(x1, x2, y, apply=False)
-            finally:
-                _Plan.run = run
-            t0 = torch.cuda.Event(enable_timing=True)
-            t0.record()
-            self.apply_gradients()
-            t1 = torch.cuda.Event(enable_timing=True)
-            t1.record()
-            timings.append(("vm_adam_step", t0, t1))
-            torch.cuda.synchronize()
-            ms = [(w, a.elapsed_time(b)) for w, a, b in timings]
-            acc = ms if acc is None else [(w, t + u) for (w, t), (_, u) in zip(acc, ms)]
+        overlap, self.overlap_wgrad = self.overlap_wgrad, False   # one stream: an event after a launch brackets it
+        try:
+            self.siamese_step(x1, x2, y)
+            acc = None
+            for _ in range(steps):
+                timings = []
+                run, _Plan.run = _Plan.run, lambda plan: plan.run_timed(timings)
+                try:
+                    self.siamese_step(x1, x2, y, apply=False)
+                finally:
+                    _Plan.run = run
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record()
+                self.apply_gradients()
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record()
+                timings.append(("vm_adam_step", t0, t1))
+                torch.cuda.synchronize()
+                ms = [(w, a.elapsed_time(b)) for w, a, b in timings]
+                acc = ms if acc is None else [(w, t + u) for (w, t), (_, u) in zip(acc, ms)]
+        finally:
+            self.overlap_wgrad = overlap
         return [(w, t / steps) for w, t in acc]
 
     # ------------------------------------------------------------------ views for tests / diagnostics
@@ -641,7 +686,7 @@ class TrainEngine:
         gradient scale and loss scale taken out).  Only the block written last is still in the buffer (block 1 after
         a full backward)."""
         n_u = self.U16[b].numel()
-        planes = self.dU[:, :n_u].to(torch.float32).sum(dim=0)
+        planes = self.dU[b % 2][:, :n_u].to(torch.float32).sum(dim=0)
         absmax = self.gabs[b:b + 1].view(torch.float32).item()
         if absmax > 0:
             import math
