@@ -28,6 +28,7 @@
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 #include "vm_p2p.cuh"
+#include <cstdlib>
 
 namespace vm {
 
@@ -908,19 +909,23 @@ struct BnBwdFin {
 // sum_positions dU per channel (un-scaled).  Per channel the expression is affine in u and dy:
 //   dU = A*dy + B + Cc*u,  A = s*mk,  B = s*(mean*rstd*mean_dyxhat - mean_dy),  Cc = -s*rstd*mean_dyxhat
 // with u and the arg-max flag decoded from the 16-bit activation word.  grid (N, chunks) over pool windows.
-template <bool kSparse, int kPlanes, int kPool>
-__global__ void __launch_bounds__(kEwThreads, 2)
+template <bool kSparse, int kPlanes, int kPool, int kPer>
+__global__ void __launch_bounds__(kEwThreads, kPer == 8 ? 2 : 3)
 bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ dy_pooled,
                    const float* __restrict__ d_gmax, const int* __restrict__ jstar, int N, int L, int C, int G,
                    int /*pool == kPool*/, const float4* __restrict__ bn_const, const float4* __restrict__ bwd_const,
                    const float* __restrict__ mask, const unsigned int* __restrict__ absmax,
                    __half* __restrict__ du_hi, __half* __restrict__ du_lo, float* __restrict__ dbias_partial) {
+  // kPer adjacent channels per thread: 8 (16-byte rows, 128 registers, 2 blocks per SM) or 4 (8-byte rows, 64
+  // registers, 4 blocks per SM: the same bytes in flight per SM from twice the threads, and blocks small enough to
+  // share an SM with a weight-gradient CTA of the side stream)
+  constexpr int kWords = kPer / 2;
   const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
-  const int groups = C >> 3, streams = ew_streams(C, 8);
-  __shared__ float bias_red[kEwThreads * 8];   // [stream][C] conv-bias partials of the block's threads
+  const int groups = C / kPer, streams = ew_streams(C, kPer);
+  __shared__ float bias_red[kEwThreads * kPer];   // [stream][C] conv-bias partials of the block's threads
   if (int(threadIdx.x) >= groups * streams) return;   // (a barrier waits for the non-exited threads only)
   {
-  const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = 8 * cg;
+  const int cg = threadIdx.x % groups, stream = threadIdx.x / groups, c = kPer * cg;
   const int g = n / (N / G);
   constexpr int pool = kPool;
   const int lout = L / pool;
@@ -928,11 +933,11 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
   const int per = (wins + chunks - 1) / chunks;
   const int w0 = chunk * per, w1 = min(wins, w0 + per);
   const float scale = grad_scale_from_absmax(__uint_as_float(*absmax));
-  float A[8], B[8], Cc[8], sb[8];
-  int js[kSparse ? 8 : 1];
-  float dg[kSparse ? 8 : 1];
+  float A[kPer], B[kPer], Cc[kPer], sb[kPer];
+  int js[kSparse ? kPer : 1];
+  float dg[kSparse ? kPer : 1];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < kPer; ++k) {
     const float4 bc = bn_const[size_t(g) * C + c + k];
     const float4 bw = bwd_const[size_t(g) * C + c + k];
     const float mk = mask ? mask[size_t(n) * C + c + k] : 1.f;
@@ -946,29 +951,45 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
     }
   }
   struct Window {
-    uint4 ur[kPool];  // the window's rows of 8 encoded activations
-    float4 d0, d1;    // its pooled gradient
+    uint32_t ur[kPool][kWords];  // the window's rows of kPer encoded activations
+    float d[kPer];               // its pooled gradient
   };
   auto load_window = [&](int w, Window& W) {
     const int l0 = w * pool, wl = min(pool, L - l0);
     const uint16_t* up = u16 + (size_t(n) * L + l0) * C + c;
 #pragma unroll
-    for (int i = 0; i < kPool; ++i)
-      W.ur[i] = (i < wl) ? __ldcs(reinterpret_cast<const uint4*>(up + size_t(i) * C)) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < kPool; ++i) {
+      if (i < wl) {
+        if (kPer == 8) {
+          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(up + size_t(i) * C));
+          W.ur[i][0] = v.x; W.ur[i][1] = v.y; W.ur[i][kWords - 2] = v.z; W.ur[i][kWords - 1] = v.w;
+        } else {
+          const uint2 v = __ldcs(reinterpret_cast<const uint2*>(up + size_t(i) * C));
+          W.ur[i][0] = v.x; W.ur[i][1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < kWords; ++q) W.ur[i][q] = 0u;
+      }
+    }
     if (!kSparse && w < lout) {
       const float4* dp = reinterpret_cast<const float4*>(dy_pooled + (size_t(n) * lout + w) * C + c);
-      W.d0 = __ldcs(dp);
-      W.d1 = __ldcs(dp + 1);
+#pragma unroll
+      for (int h = 0; h < kPer / 4; ++h) {
+        const float4 v = __ldcs(dp + h);
+        W.d[4 * h] = v.x; W.d[4 * h + 1] = v.y; W.d[4 * h + 2] = v.z; W.d[4 * h + 3] = v.w;
+      }
     } else {
-      W.d0 = W.d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) W.d[k] = 0.f;
     }
   };
   auto apply_window = [&](int w, const Window& W) {
     const int l0 = w * pool, wl = min(pool, L - l0);
-    float Bf[8];   // B + A * dy of this window: what the flagged element receives instead of B
+    float Bf[kPer];   // B + A * dy of this window: what the flagged element receives instead of B
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float dy = kSparse ? ((w == js[k]) ? dg[k] : 0.f) : (k < 4 ? f4get(W.d0, k) : f4get(W.d1, k - 4));
+    for (int k = 0; k < kPer; ++k) {
+      const float dy = kSparse ? ((w == js[k]) ? dg[k] : 0.f) : W.d[k];
       Bf[k] = fmaf(A[k], dy, B[k]);
     }
     __half* oh = du_hi + (size_t(n) * L + l0) * C + c;
@@ -976,15 +997,15 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
 #pragma unroll
     for (int i = 0; i < kPool; ++i) {
       if (i < wl) {
-        const uint32_t wd[4] = {W.ur[i].x, W.ur[i].y, W.ur[i].z, W.ur[i].w};
-        uint32_t ph[4], pl[4];
+        uint32_t ph[kWords], pl[kWords];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {   // two channels per 32-bit word: paired conversions both ways
-          const uint32_t mag = wd[q] & 0x7FFF7FFFu;
+        for (int q = 0; q < kWords; ++q) {   // two channels per 32-bit word: paired conversions both ways
+          const uint32_t wd = W.ur[i][q];
+          const uint32_t mag = wd & 0x7FFF7FFFu;
           const __half2 uh = *reinterpret_cast<const __half2*>(&mag);
           const float2 u = __half22float2(uh);
-          const float b0 = (wd[q] & 0x8000u) ? Bf[2 * q] : B[2 * q];
-          const float b1 = (int(wd[q]) < 0) ? Bf[2 * q + 1] : B[2 * q + 1];
+          const float b0 = (wd & 0x8000u) ? Bf[2 * q] : B[2 * q];
+          const float b1 = (int(wd) < 0) ? Bf[2 * q + 1] : B[2 * q + 1];
           float d0 = fmaf(Cc[2 * q], u.x, b0), d1 = fmaf(Cc[2 * q + 1], u.y, b1);
           d0 = (u.x > 0.f) ? d0 : 0.f;      // relu'(u)
           d1 = (u.y > 0.f) ? d1 : 0.f;
@@ -998,12 +1019,18 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
             pl[q] = *reinterpret_cast<const uint32_t*>(&lo);
           }
         }
-        __stcs(reinterpret_cast<uint4*>(oh + size_t(i) * C), make_uint4(ph[0], ph[1], ph[2], ph[3]));
-        if (kPlanes == 2) __stcs(reinterpret_cast<uint4*>(ol + size_t(i) * C), make_uint4(pl[0], pl[1], pl[2], pl[3]));
+        if (kPer == 8) {
+          __stcs(reinterpret_cast<uint4*>(oh + size_t(i) * C), make_uint4(ph[0], ph[1], ph[kWords - 2], ph[kWords - 1]));
+          if (kPlanes == 2)
+            __stcs(reinterpret_cast<uint4*>(ol + size_t(i) * C), make_uint4(pl[0], pl[1], pl[kWords - 2], pl[kWords - 1]));
+        } else {
+          __stcs(reinterpret_cast<uint2*>(oh + size_t(i) * C), make_uint2(ph[0], ph[1]));
+          if (kPlanes == 2) __stcs(reinterpret_cast<uint2*>(ol + size_t(i) * C), make_uint2(pl[0], pl[1]));
+        }
       }
     }
   };
-  // 8 / kPool windows in flight per thread (the same bytes for either pool size): with two windows of MaxPool(2) a
+  // 8 / kPool windows in flight per thread (the same row count for either pool size): with two windows of MaxPool(2) a
   // thread had 64-96 bytes outstanding and blocks 2-4 ran at 2-4 TB/s
   constexpr int kFlight = 8 / kPool;
   // (requesting the first windows before the constants' loads was measured: no gain for MaxPool(4), and the MaxPool(2)
@@ -1019,7 +1046,7 @@ bn_relu_bwd_kernel(const uint16_t* __restrict__ u16, const float* __restrict__ d
   }
   const float inv = 1.0f / scale;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) bias_red[stream * C + c + k] = sb[k] * inv;
+  for (int k = 0; k < kPer; ++k) bias_red[stream * C + c + k] = sb[k] * inv;
   }
   // one partial row per block: the streams' sums are added in stream order (deterministic)
   __syncthreads();
@@ -1278,20 +1305,28 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
                         const unsigned int* absmax, __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias,
                         double* red_scratch, cudaStream_t st) {
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  const int streams = ew_streams(C, 8);
+  // channels per thread: 4 when the block then still has a thread for every channel group (C <= 1024); VOICEMAP_RELU_BWD_PER=8
+  // selects the wider form for measurements
+  static const bool wide_env = (getenv("VOICEMAP_RELU_BWD_PER") != nullptr && atoi(getenv("VOICEMAP_RELU_BWD_PER")) == 8);
+  const int per = (wide_env || C > 1024 || C % 4 != 0) ? 8 : 4;
+  const int streams = ew_streams(C, per);
   const int chunks = ew_chunks(N, (L + pool - 1) / pool, streams);
   const dim3 grid(N, chunks);
   const float4* bc = reinterpret_cast<const float4*>(bn_const);
   const float4* bw = reinterpret_cast<const float4*>(bwd_const);
   if (pool != 2 && pool != 4) return set_error(VM_ERR_UNSUPPORTED, "bn_bwd: pool must be 2 or 4");
-#define VM_RELU_BWD(SPARSE, PLANES, POOL)                                                                          \
-  bn_relu_bwd_kernel<SPARSE, PLANES, POOL><<<grid, kEwThreads, 0, st>>>(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, \
-                                                                        bc, bw, mask, absmax, du_hi, du_lo, dbias_partial)
+#define VM_RELU_BWD(SPARSE, PLANES, POOL, PER)                                                                          \
+  bn_relu_bwd_kernel<SPARSE, PLANES, POOL, PER><<<grid, kEwThreads, 0, st>>>(u16, dy_pooled, d_gmax, jstar, N, L, C, G, \
+                                                                             pool, bc, bw, mask, absmax, du_hi, du_lo,  \
+                                                                             dbias_partial)
+#define VM_RELU_BWD_Q(SPARSE, PLANES, POOL) \
+  do { if (per == 8) VM_RELU_BWD(SPARSE, PLANES, POOL, 8); else VM_RELU_BWD(SPARSE, PLANES, POOL, 4); } while (0)
 #define VM_RELU_BWD_P(SPARSE, PLANES) \
-  do { if (pool == 2) VM_RELU_BWD(SPARSE, PLANES, 2); else VM_RELU_BWD(SPARSE, PLANES, 4); } while (0)
+  do { if (pool == 2) VM_RELU_BWD_Q(SPARSE, PLANES, 2); else VM_RELU_BWD_Q(SPARSE, PLANES, 4); } while (0)
   if (dy_pooled == nullptr) { if (du_lo) VM_RELU_BWD_P(true, 2); else VM_RELU_BWD_P(true, 1); }
   else { if (du_lo) VM_RELU_BWD_P(false, 2); else VM_RELU_BWD_P(false, 1); }
 #undef VM_RELU_BWD_P
+#undef VM_RELU_BWD_Q
 #undef VM_RELU_BWD
   const ColsumFin fin{C, dbias};
   rowsum_fused_kernel<1><<<dim3((C + 31) / 32, kRB), dim3(32, 8), 0, st>>>(dbias_partial, size_t(N) * chunks, C, C, tmp,
