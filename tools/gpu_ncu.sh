@@ -20,7 +20,7 @@ idx = [i for i, r in enumerate(rows) if "conv1_kernel" in r[name]]
 # launches of conv1: [fwd, train] per iteration; the tail starts at the last eval forward's conv1
 start = idx[-2]
 import re
-pat = re.compile("conv1_kernel|conv3_kernel|wgrad|bn_relu_bwd|bn_bwd_reduce|bn_pool_fwd|gmax_dense")
+pat = re.compile("conv1_kernel|conv3_kernel|wgrad|bn_relu_bwd|bn_bwd_reduce|bn_pool_fwd|gmax_dense|siamese_head|bn_gmax_fwd")
 # --launch-skip counts only launches that pass the -k filter of the full capture
 open(f"gpurun_out/{tag}_ncu_skip.txt", "w").write(str(sum(1 for r in rows[:start] if pat.search(r[name]))))
 val = hdr.index("Metric Value")
@@ -34,7 +34,7 @@ SKIP=$(cat gpurun_out/${TAG}_ncu_skip.txt)
 # the report itself (~80 MB) stays on the box: gpurun brings back at most 64 MiB, so only the text / csv exports travel
 REP=/tmp/${TAG}_full
 ncu --set full --clock-control none --import-source on --launch-skip $SKIP \
-    -k regex:'conv1_kernel|conv3_kernel|wgrad|bn_relu_bwd|bn_bwd_reduce|bn_pool_fwd|gmax_dense' -f -o $REP \
+    -k regex:'conv1_kernel|conv3_kernel|wgrad|bn_relu_bwd|bn_bwd_reduce|bn_pool_fwd|gmax_dense|siamese_head|bn_gmax_fwd' -f -o $REP \
     python tools/ncu_targets.py >> gpurun_out/${TAG}_ncu_run.log 2>&1
 ncu -i $REP.ncu-rep --page details > gpurun_out/${TAG}_ncu_details.txt 2>&1
 ncu -i $REP.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_raw.csv 2>&1

@@ -11,11 +11,13 @@
 // Forward (train):  conv -> bn_stats_finalize (batch moments per BN group, Keras moving-average update)
 //                   -> bn_pool_fwd (y = s*ext + t, SpatialDropout mask -> fp16 planes (hi, lo | Q) of the next conv)
 //                      / bn_gmax_fwd for block 4 (GlobalMaxPool1D over the windows, with the winning window)
-//                   -> dense_fwd -> pair head + loss (vm_head.cu)
-// Backward:         pair_head_loss_bwd -> dense_bwd -> per block (4..1):
-//                   bn_bwd_reduce (sum dy, sum dy*xhat: dy is non-zero at the window arg-max only, where u == ext, so
-//                   this pass reads pooled tensors only; also the largest |s*dy| -> gradient scale)
-//                   -> bn_bwd_finalize (+ dgamma, dbeta)
+//                   -> siamese_head_train (embedding Dense, pair head, loss and their backward: two launches)
+//                      [classifier: dense_fwd, torch softmax head, dense_bwd]
+// Backward:         per block (4..1):
+//                   sum dy, sum dy*xhat (dy is non-zero at the window arg-max only, where u == ext, so these come from
+//                   pooled tensors only -- taken in the dgrad epilogue of the block above, block 4: bn_bwd_reduce; also
+//                   the largest |s*dy| -> gradient scale)
+//                   -> column reduction + finishing step (+ dgamma, dbeta; data parallel: + the exchange with the peers)
 //                   -> bn_relu_bwd (u16 + dy -> dU = relu'(u) * s * (dy - mean_dy - xhat*mean_dyxhat) as scaled fp16
 //                      planes, + conv-bias gradient partials)
 //                   -> wgrad (vm_wgrad.cu) and dgrad (conv3_kernel on flipped/transposed weights).

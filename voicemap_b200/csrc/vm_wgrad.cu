@@ -193,7 +193,11 @@ int launch_wgrad3(const __half* x_hi, const __half* x_lo, const __half* du_hi, c
   p.nco_tiles = (cout + 127) / 128;
   p.ncombo = ((cin + 127) / 128) * p.nco_tiles;
   const size_t wsize = size_t(3) * cin * cout;
-  int nsplit = max(1, (2 * num_sms()) / p.ncombo);
+  // ONE wave of CTAs (a CTA takes an SM's whole shared memory).  Two waves (the first version) paid the prologue, the
+  // 196 KB partial tile and its share of the reduce twice per SM, and as a side-stream kernel one wave shares the GPU
+  // better with the main stream: 64-pair step 2.57 -> 2.44 ms, 16-pair 0.99 -> 0.93 ms; three waves 2.64 ms
+  // (profiles/r02_wgrad_waves_ab.log)
+  int nsplit = max(1, num_sms() / p.ncombo);
   nsplit = min(nsplit, N * p.nchunk);
   while (nsplit > 1 && size_t(nsplit) * wsize * 4 > partial_bytes) --nsplit;
   if (size_t(nsplit) * wsize * 4 > partial_bytes) return set_error(VM_ERR_SHAPE, "wgrad3: partial buffer too small");
