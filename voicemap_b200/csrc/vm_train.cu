@@ -739,67 +739,86 @@ siamese_head_pair_kernel(const SiameseHeadArgs a) {
   }
 }
 
-// blocks [0, ceil(C/8)): dW rows of 8 channels over all 2N clips (clips in order, as dense_bwd_w_kernel);
+// blocks [0, ceil(C/8)): dW rows of 8 channels over all 2N clips -- block (E-lane 64, clip quarter 4): a thread sums
+// its quarter of the clips in order (four clips in flight), the quarters are added in a fixed order;
 // the last block: loss, accuracy and head gradients from the per-pair records, fixed order.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 siamese_head_finish_kernel(const SiameseHeadArgs a) {
   const int N = a.N, C = a.C, E = a.E, NB = 2 * a.N;
   const int wblocks = (C + 7) / 8;
+  const int lane_e = threadIdx.x, part = threadIdx.y;   // blockDim = (64, 4)
   if (int(blockIdx.x) < wblocks) {
+    __shared__ float red[3][9][64];   // quarters 1-3: 8 channel sums + the bias sum per E-lane
     const int c0 = blockIdx.x * 8;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int nq = (NB + 3) / 4;
+    const int n0 = part * nq, n1 = min(NB, n0 + nq);
+    for (int e0 = 0; e0 < E; e0 += 64) {
+      const int e = e0 + lane_e;
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
-      int n = 0;
-      for (; n + 4 <= NB; n += 4) {
-        float d[4], xv[4][8];
+      if (e < E) {
+        int n = n0;
+        for (; n + 4 <= n1; n += 4) {
+          float d[4], xv[4][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          d[i] = a.d_emb[size_t(n + i) * E + e];
+          for (int i = 0; i < 4; ++i) {
+            d[i] = a.d_emb[size_t(n + i) * E + e];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) xv[i][k] = (c0 + k < C) ? __ldg(a.gmax + size_t(n + i) * C + c0 + k) : 0.f;
+            for (int k = 0; k < 8; ++k) xv[i][k] = (c0 + k < C) ? __ldg(a.gmax + size_t(n + i) * C + c0 + k) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            accb += d[i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[i][k], d[i], acc[k]);
+          }
         }
+        for (; n < n1; ++n) {
+          const float d = a.d_emb[size_t(n) * E + e];
+          accb += d;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          accb += d[i];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[i][k], d[i], acc[k]);
+          for (int k = 0; k < 8; ++k)
+            if (c0 + k < C) acc[k] = fmaf(a.gmax[size_t(n) * C + c0 + k], d, acc[k]);
         }
       }
-      for (; n < NB; ++n) {
-        const float d = a.d_emb[size_t(n) * E + e];
-        accb += d;
+      if (part > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[part - 1][k][lane_e] = acc[k];
+        red[part - 1][8][lane_e] = accb;
+      }
+      __syncthreads();
+      if (part == 0 && e < E) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (c0 + k < C) acc[k] = fmaf(a.gmax[size_t(n) * C + c0 + k], d, acc[k]);
+          if (c0 + k < C)
+            a.d_dense_w[size_t(c0 + k) * E + e] = ((acc[k] + red[0][k][lane_e]) + red[1][k][lane_e]) + red[2][k][lane_e];
+        if (blockIdx.x == 0) a.d_dense_b[e] = ((accb + red[0][8][lane_e]) + red[1][8][lane_e]) + red[2][8][lane_e];
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (c0 + k < C) a.d_dense_w[size_t(c0 + k) * E + e] = acc[k];
-      if (blockIdx.x == 0) a.d_dense_b[e] = accb;
+      __syncthreads();
     }
     return;
   }
+  const int t = part * 64 + lane_e;
   if (a.metric == 0) {
-    if (threadIdx.x == 0) {
+    if (t == 0) {
       float gw = 0.f, gb = 0.f;
       for (int n = 0; n < N; ++n) { const float4 r = a.pair[n]; gw = fmaf(r.z, r.w, gw); gb += r.z; }
       a.d_head_w[0] = gw;
       a.d_head_b[0] = gb;
     }
   } else {
-    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    for (int j = t; j < E; j += 256) {
       float gw = 0.f;
       for (int n = 0; n < N; ++n)
         gw = fmaf(a.pair[n].z, fabsf(a.emb[size_t(n) * E + j] - a.emb[size_t(N + n) * E + j]), gw);
       a.d_head_w[j] = gw;
     }
-    if (threadIdx.x == 0) {
+    if (t == 255) {
       float gb = 0.f;
       for (int n = 0; n < N; ++n) gb += a.pair[n].z;
       a.d_head_b[0] = gb;
     }
   }
-  if (threadIdx.x == 32) {   // another warp: loss mean (double, pairs in order) and accuracy
+  if (t == 32) {   // another warp: loss mean (double, pairs in order) and accuracy
     double ls = 0.0;
     float hits = 0.f;
     for (int n = 0; n < N; ++n) { const float4 r = a.pair[n]; ls += double(r.x); hits += r.y; }
@@ -1254,7 +1273,7 @@ int launch_siamese_head_train(const float* gmax, int N, int C, int E, const floa
                           prob, d_emb, d_gmax, reinterpret_cast<float4*>(pair_scratch), d_dense_w, d_dense_b, d_head_w,
                           d_head_b, loss_acc};
   siamese_head_pair_kernel<<<N, 256, smem, st>>>(a);
-  siamese_head_finish_kernel<<<(C + 7) / 8 + 1, 64, 0, st>>>(a);
+  siamese_head_finish_kernel<<<(C + 7) / 8 + 1, dim3(64, 4), 0, st>>>(a);
   return check_launch_t("siamese_head_train");
 }
 
