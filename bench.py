@@ -257,7 +257,8 @@ def bench_train(args, dev, rank, world, peaks):
                                        f"{(1023808 + 2) * 4 / 1e6:.1f} MB fp32 per step, NCCL) overlapped with backward + 8 "
                                        f"BatchNorm statistics sums (<= 16 KB each) "
                                        f"{'inside the kernels over NVLink peer memory' if os.environ.get('VOICEMAP_SYNCBN', 'p2p').lower() != 'nccl' else 'as NCCL all-reduces'}"
-                           if world > 1 else "dp1"),
+                           if world > 1 else "dp1",
+                           streams="weight gradients on a side stream beside the next block's BatchNorm/ReLU backward pass"),
                modes={})
     for name, bwd in (("bwd1", 1), ("bwd3", 3)):
         enc = get_baseline_convolutional_encoder(FILTERS, EMB, dropout=0.0)
@@ -543,11 +544,11 @@ def run_b200(args):
                    "this fraction",
                 1: "precision=1: one fp16 MMA per algorithmic MAC (not a parity mode)"}[args.precision],
             mma_issue_frac=round(achieved_tf * args.precision / peaks["bf16_tflops"], 4),
-            # dram__bytes_read + dram__bytes_write of the three conv3 launches (ncu --set full, profiles/r01_ncu_summary.md:
-            # 738 + 651 + 304 MB at batch 256, the same for precision 2 and 3: both move 4 bytes per activation)
+            # dram__bytes_read + dram__bytes_write of the three conv3 launches (ncu --set full, profiles/r02b_ncu_summary.md:
+            # 735 + 652 + 306 MB at batch 256, the same for precision 2 and 3: both move 4 bytes per activation)
             # averaged per launch; algorithmic bytes per launch average 590 MB
             traffic=(5.64e8 if (n, length) == (256, 12000) and args.precision in (2, 3) else None),
-            traffic_source="ncu --set full capture of the same kernels at this batch, profiles/r01_ncu_summary.md "
+            traffic_source="ncu --set full capture of the same kernels at this batch, profiles/r02b_ncu_summary.md "
                            "(dram__bytes_read.sum + dram__bytes_write.sum, mean of the three conv3 launches)",
             blocks=blocks,
             network=dict(us_per_clip=round(us_per_clip, 3),
