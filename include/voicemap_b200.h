@@ -264,32 +264,22 @@ int vm_bn_bwd_from_sums(const double* local_sums, const double* global_sums, dou
                         int pool, const float* bn_const, const float* mask, float* bwd_const, float* dgamma,
                         float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo, float* scratch_f,
                         float* dbias, double* red_scratch, void* stream);
-/* The same two pairs with the sum over the ranks INSIDE the consuming kernel, over NVLink peer memory instead of a
- * collective call: every rank of the node (at most 8) owns one exchange buffer (vm_p2p_alloc) that all ranks have
- * mapped through CUDA IPC (vm_p2p_export -> 64-byte handle -> vm_p2p_import on the peers).  A call pushes this rank's
- * sums into every peer's buffer, raises a flag, waits for the peers' flags on its own buffer and adds the W vectors in
- * rank order (bit-identical totals on every rank), then forms the constants -- one launch, no host involvement.
- * peers: W buffer addresses as mapped in THIS process (peers[rank] = the local one); seq: 1, 2, 3, ... identical on
- * every rank and incremented per call (all ranks must issue the same calls in the same order); total_sums receives the
- * global sums (2*G*C doubles).  vm_bn_stats_sync follows vm_bn_stats_sums, vm_bn_bwd_sync follows vm_bn_bwd_sums. */
+/* The same with the sum over the ranks INSIDE the reduction kernel, over NVLink peer memory instead of a collective
+ * call: every rank of the node (at most 8) owns one exchange buffer (vm_p2p_alloc) that all ranks have mapped through
+ * CUDA IPC (vm_p2p_export -> 64-byte handle -> vm_p2p_import on the peers).  The block that finishes a 32-channel
+ * column of the reduction pushes that column's sums into every peer's buffer, raises a flag, waits for the peers' flags
+ * on its own buffer, adds the W vectors in rank order (bit-identical totals on every rank) and forms the constants --
+ * no extra launch, no host involvement.  peers: W buffer addresses as mapped in THIS process (peers[rank] = the local
+ * one); seq: 1, 2, 3, ... identical on every rank and incremented per call (all ranks must issue the same calls in the
+ * same order); total_sums receives the global sums (2*G*C doubles). */
 size_t vm_p2p_buffer_bytes(void);
 int vm_p2p_alloc(void** ptr);
 int vm_p2p_free(void* ptr);
 int vm_p2p_export(void* ptr, unsigned char* handle64);
 int vm_p2p_import(const unsigned char* handle64, void** ptr);
 int vm_p2p_unimport(void* ptr);
-int vm_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                     uint32_t seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
-                     float momentum, float* moving_mean, float* moving_var, float* bn_const, void* stream);
-int vm_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world, uint32_t seq,
-                   double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
-                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* bwd_const,
-                   float* dgamma, float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
-                   float* scratch_f, float* dbias, double* red_scratch, void* stream);
-/* The same in ONE launch each: the reduction kernel's finishing block of every 32-channel column exchanges that
- * column's sums with the peers and derives the constants (vm_bn_stats_sums + vm_bn_stats_sync, resp. vm_bn_bwd_sums +
- * vm_bn_bwd_sync, without the second launch; arguments as in vm_bn_stats_finalize / vm_bn_bwd plus the peer arguments
- * of the *_sync calls).  local_sums (2*G*C doubles; optional for the statistics), total_sums (2*G*C doubles), G <= 4. */
+/* vm_bn_stats_finalize / vm_bn_bwd with that exchange (arguments as there, plus the peer arguments).  local_sums
+ * (2*G*C doubles; optional for the statistics), total_sums (2*G*C doubles), G <= 4. */
 int vm_bn_stats_finalize_peers(const float* stat_partial, int rows_per_clip, int N, int G, int C, const float* gamma,
                                const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                                float* bn_const, double* red_scratch, void* const* peers, int rank, int world,

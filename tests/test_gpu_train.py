@@ -309,3 +309,57 @@ def test_train_step_at_baseline_shape_64_pairs_12000():
         assert max(worst.values()) < GRAD_TOL[bwd], (bwd, worst)
         del tr, sia
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n,c,e", [(5, 512, 64), (64, 512, 64), (7, 136, 24), (3, 64, 100)])
+@pytest.mark.parametrize("metric,loss_id", [(0, 1), (0, 2), (1, 2)])
+def test_siamese_head_train_equals_the_four_separate_calls(n, c, e, metric, loss_id):
+    """vm_siamese_head_train (the siamese training head in two launches) against vm_dense_fwd + vm_pair_head_loss_fwd +
+    vm_pair_head_loss_bwd + vm_dense_bwd, which it replaces in the training step: embeddings, probabilities, d_emb,
+    d_gmax bit for bit (same summation orders, or exact negation); loss, accuracy and the reduced gradients to float
+    rounding of differently ordered sums."""
+    import ctypes as C
+    from voicemap_b200 import _lib
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(100 * n + c + e)
+    dev = "cuda"
+    gmax = torch.randn(2 * n, c, generator=g).to(dev)
+    w = (torch.randn(c, e, generator=g) / np.sqrt(c)).to(dev)
+    b = (0.1 * torch.randn(e, generator=g)).to(dev)
+    hw = (torch.rand(1 if metric == 0 else e, generator=g) * 0.5 + 0.1).to(dev)
+    hb = torch.tensor([-0.4]).to(dev)
+    y = (torch.arange(n) % 2).to(torch.float32).to(dev)
+    scale = 8.0
+    p = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    # separate calls
+    emb0 = torch.empty(2 * n, e, device=dev)
+    prob0, loss0, acc0 = torch.empty(n, device=dev), torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    d_emb0, d_gmax0 = torch.empty(2 * n, e, device=dev), torch.empty(2 * n, c, device=dev)
+    dw0, db0 = torch.empty(c, e, device=dev), torch.empty(e, device=dev)
+    dhw0, dhb0 = torch.empty_like(hw), torch.empty(1, device=dev)
+    _lib.check(lib.vm_dense_fwd(p(gmax), 2 * n, c, p(w), p(b), e, p(emb0), st), "dense_fwd")
+    _lib.check(lib.vm_pair_head_loss_fwd(p(emb0[:n]), p(emb0[n:]), n, e, metric, p(hw), p(hb), p(y), loss_id, None,
+                                         p(prob0), p(loss0), st), "head_fwd")
+    _lib.check(lib.vm_pair_head_loss_bwd(p(emb0), n, e, metric, p(hw), p(hb), p(y), loss_id, C.c_float(scale), p(d_emb0),
+                                         p(dhw0), p(dhb0), p(acc0), st), "head_bwd")
+    _lib.check(lib.vm_dense_bwd(p(gmax), p(d_emb0), p(w), 2 * n, c, e, p(dw0), p(db0), p(d_gmax0), st), "dense_bwd")
+    # fused call
+    emb1 = torch.empty(2 * n, e, device=dev)
+    prob1, la1 = torch.empty(n, device=dev), torch.zeros(2, device=dev)
+    d_emb1, d_gmax1 = torch.empty(2 * n, e, device=dev), torch.empty(2 * n, c, device=dev)
+    dw1, db1 = torch.empty(c, e, device=dev), torch.empty(e, device=dev)
+    dhw1, dhb1 = torch.empty_like(hw), torch.empty(1, device=dev)
+    rec = torch.empty(n, 4, device=dev)
+    _lib.check(lib.vm_siamese_head_train(p(gmax), n, c, e, p(w), p(b), metric, p(hw), p(hb), p(y), loss_id,
+                                         C.c_float(scale), p(emb1), p(prob1), p(d_emb1), p(d_gmax1), p(rec), p(dw1),
+                                         p(db1), p(dhw1), p(dhb1), p(la1), st), "siamese_head_train")
+    torch.cuda.synchronize()
+    assert torch.equal(emb1, emb0) and torch.equal(prob1, prob0) and torch.equal(d_emb1, d_emb0)
+
+    def close(a, ref, tol=2e-6):
+        a, ref = a.double().cpu().numpy(), ref.double().cpu().numpy()
+        return np.abs(a - ref).max() <= tol * max(np.abs(ref).max(), 1e-30) + 1e-12
+    assert close(d_gmax1, d_gmax0) and close(dw1, dw0) and close(dhw1, dhw0) and close(dhb1, dhb0)
+    assert np.abs(db1.cpu().numpy() - db0.cpu().numpy()).max() <= 1e-6 * np.abs(d_emb0.cpu().numpy()).max() * n
+    assert close(la1[:1], loss0) and float(la1[1]) == float(acc0[0])

@@ -89,10 +89,6 @@ SIGNATURES = {
                                         C.c_uint32, C.c_double, _vp, _vp, _vp]),
     "vm_bn_bwd_peers": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _i, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _vp, _vp, _vp]),
-    "vm_bn_stats_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _i, _i, _vp, _vp, _f, _f, _vp,
-                              _vp, _vp, _vp]),
-    "vm_bn_bwd_sync": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, C.c_uint32, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
-                            _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vm_wgrad3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "vm_wgrad1": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "vm_adam_step": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _f, _f, _f, _f, _f, _f, _vp]),

@@ -384,21 +384,6 @@ int vm_p2p_unimport(void* ptr) {
   cudaError_t e = cudaIpcCloseMemHandle(ptr);
   return e == cudaSuccess ? VM_OK : set_cuda_error(e, "p2p_unimport");
 }
-int vm_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                     uint32_t seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
-                     float momentum, float* moving_mean, float* moving_var, float* bn_const, void* stream) {
-  return launch_bn_stats_sync(local_sums, total_sums, peers, rank, world, seq, count, G, C, gamma, beta, eps, momentum,
-                              moving_mean, moving_var, bn_const, ST);
-}
-int vm_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world, uint32_t seq,
-                   double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax, const int32_t* jstar,
-                   int N, int L, int C, int G, int pool, const float* bn_const, const float* mask, float* bwd_const,
-                   float* dgamma, float* dbeta, const uint32_t* grad_absmax, uint16_t* du_hi, uint16_t* du_lo,
-                   float* scratch_f, float* dbias, double* red_scratch, void* stream) {
-  return launch_bn_bwd_sync(local_sums, total_sums, peers, rank, world, seq, count, u16, dy_pooled, d_gmax, jstar, N, L,
-                            C, G, pool, bn_const, mask, bwd_const, dgamma, dbeta, grad_absmax, H16(du_hi), H16(du_lo),
-                            scratch_f, dbias, red_scratch, ST);
-}
 int vm_bn_stats_finalize_peers(const float* stat_partial, int rows_per_clip, int N, int G, int C, const float* gamma,
                                const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                                float* bn_const, double* red_scratch, void* const* peers, int rank, int world,

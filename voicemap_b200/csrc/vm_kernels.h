@@ -167,14 +167,6 @@ int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums,
                             float* dbeta, const unsigned int* absmax, __half* du_hi, __half* du_lo,
                             float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st);
 // cross-rank forms: the sum over the ranks happens inside the kernel, over NVLink peer memory (vm_p2p.cuh)
-int launch_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                         unsigned int seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
-                         float momentum, float* moving_mean, float* moving_var, float* bn_const, cudaStream_t st);
-int launch_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                       unsigned int seq, double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax,
-                       const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                       float* bwd_const, float* dgamma, float* dbeta, const unsigned int* absmax, __half* du_hi,
-                       __half* du_lo, float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st);
 int launch_adam_step(float* p, const float* g, float* m, float* v, size_t n, double* sumsq_scratch, float inv_scale,
                      float clipnorm, float lr_t, float beta1, float beta2, float eps, cudaStream_t st);
 int launch_pack_conv3_dgrad(const float* w, int cin, int cout, void* wpack, float* epi, cudaStream_t stream);

@@ -1,17 +1,19 @@
 // Cross-rank sum of a small vector (the per-(group, channel) BatchNorm sums, <= 64 KB) over NVLink peer memory, inside
-// the kernel that consumes the result -- no NCCL call, no host involvement, one launch.
+// the reduction kernel that produces the local sums -- no NCCL call, no host involvement, no extra launch.
 //
 // Every rank owns one exchange buffer that all ranks of the node have mapped (CUDA IPC):
-//     flags [2 slots][kMaxRanks] uint32          (offset 0)
-//     data  [2 slots][kMaxRanks][kP2PMaxDoubles] (offset kP2PDataOffset)
-// A call with sequence number seq (the same on every rank, starting at 1) uses slot seq & 1:
-//   1. PUSH: rank r stores its vector into data[slot][r] of EVERY rank's buffer (remote stores over NVLink), fences
-//      (system scope) and then stores seq into flags[slot][r] of every rank's buffer (release);
-//   2. WAIT: it spins on its OWN buffer until flags[slot][q] == seq for all q (acquire) -- local polling;
+//     flags [2 slots][kP2PMaxColumns][kP2PMaxRanks] uint32   (offset kP2PColFlagOffset)
+//     data  [2 slots][kP2PMaxRanks][kP2PMaxDoubles]          (offset kP2PDataOffset)
+// The unit of exchange is a COLUMN of 32 channels (one warp: lane = channel): the block that finishes a column of the
+// two-stage reduction exchanges that column while the other columns are still being summed.
+// A call with sequence number seq (the same on every rank, starting at 1) uses slot seq & 1; per column:
+//   1. PUSH: rank r stores the column's sums into data[slot][r] of EVERY rank's buffer (remote stores over NVLink),
+//      fences (system scope) and then stores seq into flags[slot][column][r] of every rank's buffer (release);
+//   2. WAIT: it spins on its OWN buffer until flags[slot][column][q] == seq for all q (acquire) -- local polling;
 //   3. SUM:  it adds data[slot][0 .. W-1] of its own buffer in rank order: the same order on every rank, so all ranks
 //      hold bit-identical sums (BatchNorm constants must agree exactly or the replicas drift apart).
-// Two slots are enough: a rank can only be one call ahead of the slowest one (call k+1 cannot complete before every
-// rank has raised its flag for k+1, which it does after it finished reading call k).
+// Two slots are enough: a rank can only be one call ahead of the slowest one (a column of call k+1 cannot complete
+// before every rank has raised that column's flag for k+1, which it does after its kernel of call k has finished).
 // The wait is bounded: a missing peer traps the kernel (an error) instead of hanging the GPU.
 #pragma once
 #include <stdint.h>
@@ -20,8 +22,8 @@ namespace vm {
 
 constexpr int kP2PMaxRanks = 8;
 constexpr int kP2PMaxDoubles = 8192;          // 2 sums x 2 groups x 2048 channels
-constexpr int kP2PMaxColumns = 64;            // column form (below): 32-channel columns, C <= 2048
-constexpr size_t kP2PColFlagOffset = 256;     // column flags [2 slots][kP2PMaxColumns][kP2PMaxRanks] uint32 = 4 KB
+constexpr int kP2PMaxColumns = 64;            // 32-channel columns, C <= 2048
+constexpr size_t kP2PColFlagOffset = 256;     // flags [2 slots][kP2PMaxColumns][kP2PMaxRanks] uint32 = 4 KB
 constexpr size_t kP2PDataOffset = kP2PColFlagOffset + size_t(2) * kP2PMaxColumns * kP2PMaxRanks * 4;
 constexpr size_t kP2PBufferBytes = kP2PDataOffset + size_t(2) * kP2PMaxRanks * kP2PMaxDoubles * sizeof(double);
 
@@ -30,9 +32,6 @@ struct P2PPeers {
   int rank, world;
 };
 
-__device__ __forceinline__ unsigned int* p2p_flag(void* base, int slot, int r) {
-  return reinterpret_cast<unsigned int*>(base) + slot * kP2PMaxRanks + r;
-}
 __device__ __forceinline__ double* p2p_data(void* base, int slot, int r) {
   return reinterpret_cast<double*>(static_cast<char*>(base) + kP2PDataOffset) +
          (size_t(slot) * kP2PMaxRanks + r) * kP2PMaxDoubles;
@@ -46,11 +45,8 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   return v;
 }
 
-// Column form: ONE WARP exchanges the G double2 sums of its 32 channels (lane = channel c of column `col`), so the
-// finishing block of every channel column of a reduction kernel can run its own exchange while the other columns are
-// still being summed -- the reduction and the exchange are one launch.  Vector layout as above (double2 index g*C + c);
-// a column has its own flag per (slot, rank); the data slots are shared with the block form (a call uses one form).
-// The two-slot argument holds per column: a peer raises a flag of call k+1 only after its kernel of call k has finished.
+// ONE WARP exchanges the G double2 sums of its 32 channels (lane = channel c of column `col`).  Vector layout: double2
+// index g*C + c.
 __device__ __forceinline__ unsigned int* p2p_col_flag(void* base, int slot, int col, int r) {
   return reinterpret_cast<unsigned int*>(static_cast<char*>(base) + kP2PColFlagOffset) +
          (size_t(slot) * kP2PMaxColumns + col) * kP2PMaxRanks + r;
@@ -94,38 +90,6 @@ __device__ __forceinline__ void p2p_allreduce_column(const double2 (&mine)[kMaxG
       total[size_t(g) * C + c] = make_double2(a, b);
     }
   }
-}
-
-// One thread block.  local[n] (this rank's vector, global memory) -> total[n] (sum over the ranks, global memory,
-// visible to the whole block on return).
-__device__ __forceinline__ void p2p_allreduce_block(const double* __restrict__ local, int n, const P2PPeers& peers,
-                                                    unsigned int seq, double* __restrict__ total) {
-  const int slot = seq & 1;
-  for (int q = 0; q < peers.world; ++q) {
-    double* dst = p2p_data(peers.buf[q], slot, peers.rank);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = local[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (int(threadIdx.x) < peers.world) {
-    st_release_sys(p2p_flag(peers.buf[threadIdx.x], slot, peers.rank), seq);
-    const unsigned int* mine = p2p_flag(peers.buf[peers.rank], slot, threadIdx.x);
-    const long long t0 = clock64();
-    while (ld_acquire_sys(mine) != seq) {
-      if (clock64() - t0 > 8000000000LL) {   // ~4 s: a peer never arrived
-        printf("vm: p2p exchange timeout rank %d waiting for rank %d seq %u\n", peers.rank, int(threadIdx.x), seq);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-  const double* base = p2p_data(peers.buf[peers.rank], slot, 0);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < peers.world; ++r) s += __ldcg(base + size_t(r) * kP2PMaxDoubles + i);   // L2: written by peers
-    total[i] = s;
-  }
-  __syncthreads();
 }
 
 }  // namespace vm

@@ -30,7 +30,6 @@
 #include "vm_common.cuh"
 #include "vm_kernels.h"
 #include "vm_p2p.cuh"
-#include <cstdlib>
 
 namespace vm {
 
@@ -196,17 +195,6 @@ __global__ void bn_stats_from_sums_kernel(const double2* __restrict__ sums, doub
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) bn_stats_from_sums_channel(c, sums, cnt, G, C, gamma, beta, eps, momentum, moving_mean, moving_var, bn_const);
 }
-// The same with the cross-rank sum inside the kernel (vm_p2p.cuh): local sums -> peer exchange -> constants, one block.
-__global__ void __launch_bounds__(256)
-bn_stats_sync_kernel(const double* __restrict__ local, double* __restrict__ total, const P2PPeers peers,
-                     unsigned int seq, double cnt, int G, int C, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float eps, float momentum, float* __restrict__ moving_mean,
-                     float* __restrict__ moving_var, float4* __restrict__ bn_const) {
-  p2p_allreduce_block(local, 2 * G * C, peers, seq, total);
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    bn_stats_from_sums_channel(c, reinterpret_cast<const double2*>(total), cnt, G, C, gamma, beta, eps, momentum,
-                               moving_mean, moving_var, bn_const);
-}
 // backward: the batch means of dy and dy*xhat come from the GLOBAL sums, dgamma / dbeta from this rank's own sums
 // (the gradient all-reduce adds the ranks' contributions)
 __device__ __forceinline__ void bn_bwd_from_sums_channel(int c, const double2* __restrict__ local,
@@ -282,15 +270,6 @@ __global__ void bn_bwd_from_sums_kernel(const double2* __restrict__ local, const
                                         float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) bn_bwd_from_sums_channel(c, local, global, cnt, G, C, bn_const, bwd_const, dgamma, dbeta);
-}
-__global__ void __launch_bounds__(256)
-bn_bwd_sync_kernel(const double* __restrict__ local, double* __restrict__ total, const P2PPeers peers, unsigned int seq,
-                   double cnt, int G, int C, const float4* __restrict__ bn_const, float4* __restrict__ bwd_const,
-                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  p2p_allreduce_block(local, 2 * G * C, peers, seq, total);
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    bn_bwd_from_sums_channel(c, reinterpret_cast<const double2*>(local), reinterpret_cast<const double2*>(total), cnt, G,
-                             C, bn_const, bwd_const, dgamma, dbeta);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1176,17 +1155,6 @@ static int p2p_check(void* const* peers, int rank, int world, int n, P2PPeers* o
   return VM_OK;
 }
 
-int launch_bn_stats_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                         unsigned int seq, double count, int G, int C, const float* gamma, const float* beta, float eps,
-                         float momentum, float* moving_mean, float* moving_var, float* bn_const, cudaStream_t st) {
-  if (G <= 0 || C <= 0 || !(count > 1.0)) return set_error(VM_ERR_SHAPE, "bn_stats_sync: bad shape");
-  P2PPeers pp{};
-  int rc = p2p_check(peers, rank, world, 2 * G * C, &pp);
-  if (rc) return rc;
-  bn_stats_sync_kernel<<<1, 256, 0, st>>>(local_sums, total_sums, pp, seq, count, G, C, gamma, beta, eps, momentum,
-                                          moving_mean, moving_var, reinterpret_cast<float4*>(bn_const));
-  return check_launch_t("bn_stats_sync");
-}
 
 int launch_bn_stats_finalize_peers(const float* partial, int rows_per_clip, int c_pad, int N, int G, int C,
                                    double* red_scratch, void* const* peers, int rank, int world, unsigned int seq,
@@ -1326,10 +1294,8 @@ static int bn_bwd_apply(const uint16_t* u16, const float* dy_pooled, const float
                         const unsigned int* absmax, __half* du_hi, __half* du_lo, float* dbias_partial, float* dbias,
                         double* red_scratch, cudaStream_t st) {
   double2* tmp = reinterpret_cast<double2*>(red_scratch);
-  // channels per thread: 4 when the block then still has a thread for every channel group (C <= 1024); VOICEMAP_RELU_BWD_PER=8
-  // selects the wider form for measurements
-  static const bool wide_env = (getenv("VOICEMAP_RELU_BWD_PER") != nullptr && atoi(getenv("VOICEMAP_RELU_BWD_PER")) == 8);
-  const int per = (wide_env || C > 1024 || C % 4 != 0) ? 8 : 4;
+  // channels per thread: 4 when the block then still has a thread for every channel group (C <= 1024), else 8
+  const int per = (C > 1024) ? 8 : 4;
   const int streams = ew_streams(C, per);
   const int chunks = ew_chunks(N, (L + pool - 1) / pool, streams);
   const dim3 grid(N, chunks);
@@ -1402,24 +1368,6 @@ int launch_bn_bwd_from_sums(const double* local_sums, const double* global_sums,
   return check_launch_t("bn_bwd_from_sums");
 }
 
-int launch_bn_bwd_sync(const double* local_sums, double* total_sums, void* const* peers, int rank, int world,
-                       unsigned int seq, double count, const uint16_t* u16, const float* dy_pooled, const float* d_gmax,
-                       const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,
-                       float* bwd_const, float* dgamma, float* dbeta, const unsigned int* absmax, __half* du_hi,
-                       __half* du_lo, float* dbias_partial, float* dbias, double* red_scratch, cudaStream_t st) {
-  int rc = bn_bwd_check(red_scratch, N, G, C, dy_pooled, d_gmax, absmax);
-  if (rc) return rc;
-  if (local_sums == nullptr || total_sums == nullptr || !(count > 0.0))
-    return set_error(VM_ERR_SHAPE, "bn_bwd_sync: bad sums / count");
-  P2PPeers pp{};
-  if ((rc = p2p_check(peers, rank, world, 2 * G * C, &pp))) return rc;
-  bn_bwd_sync_kernel<<<1, 256, 0, st>>>(local_sums, total_sums, pp, seq, count, G, C,
-                                        reinterpret_cast<const float4*>(bn_const),
-                                        reinterpret_cast<float4*>(bwd_const), dgamma, dbeta);
-  bn_bwd_apply(u16, dy_pooled, d_gmax, jstar, N, L, C, G, pool, bn_const, mask, bwd_const, absmax, du_hi, du_lo,
-               dbias_partial, dbias, red_scratch, st);
-  return check_launch_t("bn_bwd_sync");
-}
 
 int launch_bn_bwd_peers(const uint16_t* u16, const float* ext, const float* dy_pooled, const float* d_gmax,
                         const int* jstar, int N, int L, int C, int G, int pool, const float* bn_const, const float* mask,

@@ -78,7 +78,7 @@ class GradientBuckets:
 
 
 class PeerExchange:
-    """Peer-memory exchange buffers for the cross-rank BatchNorm sums (``vm_bn_stats_sync`` / ``vm_bn_bwd_sync``,
+    """Peer-memory exchange buffers for the cross-rank BatchNorm sums (``vm_bn_stats_finalize_peers`` / ``vm_bn_bwd_peers``,
     csrc/vm_p2p.cuh): every rank of the node allocates one buffer in libvoicemap_b200.so, publishes its CUDA IPC handle
     through ``torch.distributed`` (64 bytes per rank, once) and maps the others'.  The sums then travel over NVLink
     inside the consuming kernel -- no collective call, no host involvement per step.  ``seq`` is the call counter every
