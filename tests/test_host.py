@@ -546,3 +546,29 @@ def test_host_stage_casts_in_order_and_recycles_slots(monkeypatch):
     ints = rng.integers(-5, 5, size=(9, 4))
     got = np.concatenate([view.numpy().copy() for _, _, view, _ in stage.chunks(ints)])
     np.testing.assert_array_equal(got, ints.astype(np.float32))
+
+
+def test_staging_copy_plain_and_pooled_agree():
+    """training._host_copy: the plain assignment and the four-thread row-block form fill the staging buffer alike (any
+    source dtype, ragged row counts); which one runs is decided by measurement on the host."""
+    from voicemap_b200 import training as T
+    rng = np.random.default_rng(0)
+    saved = (T._COPY_POOL, T._COPY_THREADS)
+    try:
+        for rows, cols, dtype in ((128, 12000, np.float32), (37, 20011, np.float64), (9, 70000, np.float32)):
+            src = rng.standard_normal((rows, cols)).astype(dtype)
+            want = src.astype(np.float32)
+            for threads in (1, 4):
+                from concurrent.futures import ThreadPoolExecutor
+                T._COPY_THREADS = threads
+                T._COPY_POOL = ThreadPoolExecutor(max_workers=4) if threads == 4 else None
+                dst = np.full((rows, cols), np.nan, dtype=np.float32)
+                T._host_copy(dst, src)
+                assert np.array_equal(dst, want)
+        T._COPY_POOL, T._COPY_THREADS = None, None      # first use: measures, keeps one of the two, result is right
+        dst = np.zeros((64, 12000), dtype=np.float32)
+        src = rng.standard_normal((64, 12000))
+        T._host_copy(dst, src)
+        assert np.array_equal(dst, src.astype(np.float32)) and T._COPY_THREADS in (1, 4)
+    finally:
+        T._COPY_POOL, T._COPY_THREADS = saved
