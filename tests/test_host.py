@@ -515,8 +515,8 @@ def test_host_stage_casts_in_order_and_recycles_slots(monkeypatch):
     import torch
     from voicemap_b200 import models as M
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-    assert M._cast_plan(256) == [(0, 64), (64, 128), (128, 192), (192, 256)]
-    assert M._cast_plan(5) == [(0, 5)] and M._cast_plan(40) == [(0, 16), (16, 32), (32, 40)]
+    assert M._cast_plan(256) == [(0, 128), (128, 256)]          # halves (row blocks of a chunk go to all threads)
+    assert M._cast_plan(5) == [(0, 5)] and M._cast_plan(40) == [(0, 20), (20, 40)] and M._cast_plan(20) == [(0, 16), (16, 20)]
     for n in (1, 7, 63, 64, 300, 5000):
         plan = M._cast_plan(n)
         assert plan[0][0] == 0 and plan[-1][1] == n and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))

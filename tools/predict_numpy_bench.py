@@ -34,6 +34,41 @@ def main():
     print("host cast alone (one thread, astype)       %.2f ms" % timed(lambda: np.ascontiguousarray(x64[:, :, 0], dtype=np.float32), 5))
     print("predict(pinned float32 tensor)             %.3f ms" % timed(lambda: enc.predict(x32)))
     print("predict(numpy float64), staged             %.3f ms  (%d cast threads)" % (timed(lambda: enc.predict(x64)), enc._host_stage.workers))
+    # same-process A/B of staging orders (alternated): chunk plans x threads per chunk
+    from concurrent.futures import ThreadPoolExecutor
+    from voicemap_b200 import models as M
+    hs = enc._host_stage
+    keep = (M._cast_plan, hs.pool, hs.workers, hs.pieces)
+
+    def fixed(sizes):
+        def plan(n):
+            out, lo = [], 0
+            for sz in sizes:
+                if lo >= n:
+                    break
+                out.append((lo, min(n, lo + sz)))
+                lo += sz
+            while lo < n:
+                out.append((lo, min(n, lo + sizes[-1])))
+                lo += sizes[-1]
+            return out
+        return plan
+    plans = {"4 x 64": fixed([64]), "2 x 128": fixed([128]), "1 x 256": fixed([256]), "64 + 192": fixed([64, 192]),
+             "96 + 160": fixed([96, 160]), "3 x 86": fixed([86])}
+    pools = {w: ThreadPoolExecutor(max_workers=w) for w in (2, 3, 4, 6)}
+    for rnd in range(2):
+        for w, pool in pools.items():
+            for name, plan in plans.items():
+                hs.pool, hs.workers, hs.pieces = pool, w, True
+                M._cast_plan = plan
+                ok = bool(np.array_equal(enc.predict(x64), a))
+                print("round %d  row blocks on %d threads, plan %-9s %.3f ms  bit identical %s" % (
+                    rnd, w, name, timed(lambda: enc.predict(x64)), ok))
+        hs.pool, hs.workers, hs.pieces = keep[1], keep[2], False
+        M._cast_plan = fixed([64])
+        print("round %d  one thread per chunk (4 threads), plan 4 x 64  %.3f ms" % (rnd, timed(lambda: enc.predict(x64))))
+    M._cast_plan, hs.pool, hs.workers, hs.pieces = keep
+    print("predict(numpy float64), staged (defaults)  %.3f ms  (%d cast threads)" % (timed(lambda: enc.predict(x64)), hs.workers))
     big = O.WHITEN_RMS * np.random.default_rng(1).standard_normal((2048, length, 1))
     print("predict(numpy float64, 2048 clips)         %.3f ms" % timed(lambda: enc.predict(big), 5))
     small = x64[:5]

@@ -41,13 +41,15 @@ def _pipeline_plan(n, pinned=True):
 
 
 def _cast_plan(n):
-    """[(lo, hi), ...]: staging chunks of a numpy batch of n clips -- a quarter of the batch each, 16 .. 128 clips.
-    Every chunk costs the encoder its fixed ~0.06 ms of launches and prologues, so chunks are large; up to four are
-    cast at the same time, one worker thread each.  Measured on the B200 box for 256 x 12000 doubles
-    (tools/predict_numpy_bench.py, profiles/r01_predict_numpy.log): 16 chunks of 16 clips 2.8 ms, 4 chunks of 64 clips
-    1.7 ms, a small first chunk then doubling 1.65 - 1.95 ms, pieces of a chunk on several threads 1.8 - 2.0 ms;
-    the host-side cast alone is 1.5 ms on one thread and a batch that is already float32 and pinned takes 1.05 ms."""
-    rows = int(min(n, 128, max(16, -(-n // 4))))
+    """[(lo, hi), ...]: staging chunks of a numpy batch of n clips -- half of the batch each, 16 .. 128 clips.  Every
+    chunk costs the encoder its fixed ~0.06 ms of launches and prologues, so chunks are large; a chunk is cast as row
+    blocks on all of ``_HostStage``'s threads, so the first one is ready after half of the whole cast.  Measured on the
+    B200 box for 256 x 12000 doubles (tools/predict_numpy_bench.py, profiles/r02_predict_numpy_staging_probe.log;
+    predict() of the same batch as pinned float32: 1.03 ms): one thread per chunk, 4 chunks of 64 clips in parallel (the
+    first form) 1.65 - 1.75 ms; row blocks on 3 threads: 2 x 128 clips 1.45 - 1.48 ms, 3 x 86 1.47 - 1.49, 4 x 64
+    1.51 - 1.53, 64 + 192 1.65 - 1.74, 1 x 256 1.92 - 1.96; the same on 2 / 4 / 6 threads 1.48 - 1.53 / 1.55 - 1.56 /
+    1.72 - 1.73 ms (more threads take the GIL from the thread that issues the launches)."""
+    rows = int(min(n, 128, max(16, -(-n // 2))))
     return [(lo, min(n, lo + rows)) for lo in range(0, n, rows)]
 
 
@@ -55,15 +57,16 @@ class _HostStage:
     """numpy batches (the batcher and the reference's preprocessing hand out float64, voicemap/librispeech.py:103) ->
     float32 chunks in pinned memory.  The cast is the expensive part of ``predict(numpy)`` -- 1.5 ms (B200 box) to 15 ms
     (build container) on one host thread for 256 x 12000 doubles, against 0.9 ms of kernels -- so it runs chunk by chunk on worker threads (numpy releases the
-    GIL while it converts), a few chunks ahead of the copy engine, and every chunk is copied and embedded as soon as it
-    is ready.  Slots are pinned once and reused; a slot is recycled after the copy that read it has finished."""
+    GIL while it converts; a chunk = row blocks on all threads), a few chunks ahead of the copy engine, and every chunk
+    is copied and embedded as soon as it is ready.  Slots are pinned once and reused; a slot is recycled after the copy that read it has finished."""
 
     def __init__(self):
         try:
             cpus = len(os.sched_getaffinity(0))
         except AttributeError:
             cpus = os.cpu_count() or 1
-        self.workers = max(1, min(4, cpus))
+        self.workers = max(1, min(3, cpus))
+        self.pieces = True       # a chunk is cast as row blocks on all threads (False: one thread per chunk)
         self.pool = ThreadPoolExecutor(max_workers=self.workers)
         self.slots = []          # [pinned float32 tensor, copy-done event or None]
 
@@ -89,17 +92,27 @@ class _HostStage:
         depth = min(count, 4)
         pending = {}
 
+        pieces = self.workers if self.pieces else 1
+
         def submit(i):
             lo, hi = plan[i]
             slot = self._slot(i % depth, rows * length)
             view = slot[0][:(hi - lo) * length].view(hi - lo, length)
-            pending[i] = (self.pool.submit(np.copyto, view.numpy(), src[lo:hi], casting='unsafe'), lo, hi, view, slot)
+            dst = view.numpy()
+            # a chunk goes to the pool as `pieces` row blocks: the pool is first-in first-out, so all threads work on
+            # the oldest chunk and chunk 0 is ready after 1/count of the whole cast instead of all chunks finishing
+            # together at the end of it
+            step = -(-(hi - lo) // pieces)
+            futs = [self.pool.submit(np.copyto, dst[r:r + step], src[lo + r:min(hi, lo + r + step)], casting='unsafe')
+                    for r in range(0, hi - lo, step)]
+            pending[i] = (futs, lo, hi, view, slot)
 
         for i in range(depth):
             submit(i)
         for i in range(count):
-            done, lo, hi, view, slot = pending.pop(i)
-            done.result()
+            futs, lo, hi, view, slot = pending.pop(i)
+            for f in futs:
+                f.result()
             yield lo, hi, view, slot
             if i + depth < count:
                 submit(i + depth)
