@@ -39,8 +39,7 @@ constexpr int kStageBoxBytes = kStagePos * 128;     // one TMA store box: 16 pos
 constexpr int kStageBufBytes = 4 * kStageBoxBytes;  // [plane][channel half][pos][64 ch] = 8 KB
 constexpr int kStageBytes = 2 * kStageBufBytes;     // double-buffered
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;                         // 2 per TMEM lane quarter
-constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int kEpiWarps = 8;                         // per epilogue set: 2 per TMEM lane quarter (threads = (4 + 8 * sets) * 32)
 constexpr int kSmemBytes =
     kXStages * kXSlotBytes + kWStages * kWTileBytes + kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 }  // namespace c3
